@@ -1,0 +1,177 @@
+/*
+ * conclave_b200.h — C ABI of the B200-native conclave voting engine.
+ *
+ * The reference (potalora/conclave_sim) is pure Python and has no FFI of its
+ * own; this header is the boundary a maintainer would bind (ctypes stub in
+ * INTEGRATION.md) to replace, for the Monte Carlo hot path only:
+ *
+ *   csim_upload_roster   <- TransitionModel.__init__            src/model.py:172-254
+ *                           (captures ideology_score / region / is_papabile, :199-213)
+ *   csim_beta_schedule   <- TransitionModel.update_beta_weight  src/model.py:562-580
+ *   csim_need_votes      <- the supermajority test              src/simulate.py:174-175
+ *   csim_prob_matrix     <- TransitionModel.calculate_transition_probabilities
+ *                                                               src/model.py:269-560
+ *   csim_run             <- _run_single_simulation_worker       src/simulate.py:30-218
+ *                           fanned out over trials like         src/simulate.py:330-351
+ *                           + the histograms the aggregation    src/simulate.py:356-387
+ *                           needs
+ *
+ * Conventions: plain pointers and sizes, caller owns every buffer, no
+ * exceptions cross the boundary.  Every call returns CSIM_OK (0) or a negative
+ * csim_status; csim_last_error() gives the message of the calling thread's
+ * last failure.  A context is bound to one CUDA device and is re-entrant per
+ * (context, stream); contexts are independent.  There is NO CPU fallback: with
+ * no usable CUDA device csim_create fails with CSIM_ERR_CUDA.
+ */
+#ifndef CONCLAVE_B200_H
+#define CONCLAVE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSIM_ABI_VERSION 1
+
+typedef enum csim_status {
+    CSIM_OK = 0,
+    CSIM_ERR_INVALID = -1,   /* bad argument */
+    CSIM_ERR_CUDA = -2,      /* CUDA runtime error (message has the cudaError string) */
+    CSIM_ERR_STATE = -3,     /* e.g. roster not uploaded */
+    CSIM_ERR_UNSUPPORTED = -4
+} csim_status;
+
+/* wiring: which inputs of the model are connected */
+#define CSIM_WIRING_REF_CLI 0 /* what `python -m src.simulate` computes: previous votes never reach the model */
+#define CSIM_WIRING_MODEL   1 /* bandwagon / stickiness / fatigue / stop-candidate live, fed per trial */
+
+/* engine */
+#define CSIM_ENGINE_AUTO  0
+#define CSIM_ENGINE_DENSE 1   /* every trial re-evaluates its E x C scores each round */
+#define CSIM_ENGINE_TABLE 2   /* ref_cli only: trial-invariant per-round CDF tables, built once */
+
+/* arithmetic */
+#define CSIM_FP32 0           /* fast path: fp32 scores, ex2.approx, 24-bit uniforms */
+#define CSIM_FP64 1           /* exact path: fp64, numpy summation order, 53-bit uniforms;
+                                 bit-exact against the reference under a shared uniform tape */
+
+/* reason codes (strings of src/simulate.py:61,130,178) */
+#define CSIM_REASON_MAX_ROUNDS 0 /* "Max rounds reached" */
+#define CSIM_REASON_WINNER     1 /* "Winner found by supermajority (NN% threshold)" */
+#define CSIM_REASON_NO_PROBS   2 /* "No probabilities generated" */
+
+/* beta_mode: which branch of update_beta_weight is live (model.py:569-578) */
+#define CSIM_BETA_STEPPED 0   /* beta_increment_amount is not None: beta += amount when r % interval == 0 */
+#define CSIM_BETA_GROWTH  1   /* beta_increment_amount is None and growth_rate > 1: beta *= rate */
+
+/* One parameter set = TransitionModel kwargs (model.py:172-191) + worker arguments
+ * (simulate.py:30-41).  fp64 like the reference; all fields plain scalars. */
+typedef struct csim_params {
+    double  initial_beta_weight;
+    double  beta_increment_amount;
+    double  beta_growth_rate;
+    double  stickiness_factor;
+    double  bandwagon_strength;
+    double  regional_affinity_bonus;
+    double  papabile_weight_factor;
+    double  fatigue_vote_share_threshold;
+    double  fatigue_penalty_factor;
+    double  stop_candidate_threshold_unacceptable_distance;
+    double  stop_candidate_threat_min_vote_share;
+    double  stop_candidate_boost_factor;
+    double  supermajority_threshold;
+    int32_t enable_dynamic_beta;
+    int32_t beta_mode;
+    int32_t beta_increment_interval_rounds;
+    int32_t enable_candidate_fatigue;
+    int32_t fatigue_threshold_rounds;
+    int32_t fatigue_top_n_immune;
+    int32_t enable_stop_candidate;
+    int32_t max_rounds;
+    int32_t runoff_threshold_rounds;
+    int32_t runoff_candidate_count;
+    int32_t reserved0;
+    int32_t reserved1;
+} csim_params;
+
+typedef struct csim_ctx csim_ctx;
+
+/* Arguments of one batch of trials.  Trials are laid out [set][sim]:
+ * trial t = set * n_sims + i simulates parameter set `set` with
+ * sim_id = sim_id_begin + i.  Under the native RNG (uniform_tape == NULL) the
+ * votes of a trial depend only on (seed, sim_id, params): results do not
+ * depend on batching, sharding or device. */
+typedef struct csim_run_args {
+    const csim_params* params;      /* [n_param_sets] (host memory, always) */
+    int32_t  n_param_sets;
+    int32_t  wiring;                /* CSIM_WIRING_* */
+    int32_t  engine;                /* CSIM_ENGINE_* */
+    int32_t  precision;             /* CSIM_FP32 / CSIM_FP64 */
+    uint64_t sim_id_begin;
+    uint64_t n_sims;                /* per parameter set */
+    uint64_t seed;                  /* Philox4x32-10 key; counter = (sim_lo, sim_hi, round, elector>>1) */
+    const double* uniform_tape;     /* nullable: [n_trials, max_rounds * E], E uniforms per round in
+                                       elector order — "the identical uniform draws exported from the
+                                       reference".  Requires precision == CSIM_FP64. */
+    /* per-trial outputs; n_trials = n_param_sets * n_sims */
+    int32_t* winner;                /* [n_trials]  candidate index, -1 = none              (required) */
+    int32_t* rounds;                /* [n_trials]  round of the win, or max_rounds          (required) */
+    uint8_t* reason;                /* [n_trials]  CSIM_REASON_*                            (nullable) */
+    int32_t* final_votes;           /* [n_trials, E]  last round's tally                    (nullable) */
+    int32_t* round_tallies;         /* [n_trials, max_rounds, E], -1 beyond `rounds`        (nullable) */
+    /* aggregated outputs, ACCUMULATED into (caller zeroes them) */
+    int64_t* winner_hist;           /* [n_param_sets, E + 1]; slot E = no winner            (nullable) */
+    int64_t* rounds_hist;           /* [n_param_sets, max_rounds + 1] over winning trials   (nullable) */
+    int64_t* totals;                /* [n_param_sets, 2]: {sum of rounds played, trials}    (nullable) */
+    int32_t  buffers_on_device;     /* 0: every pointer above is host memory; the call copies, runs and
+                                          synchronises.  1: device pointers of ctx's device; the call only
+                                          enqueues work on `stream` (uniform_tape included). */
+    int32_t  reserved;
+    void*    stream;                /* cudaStream_t, NULL = default stream */
+} csim_run_args;
+
+int         csim_abi_version(void);
+const char* csim_last_error(void);
+
+csim_status csim_create(csim_ctx** out, int device);
+csim_status csim_destroy(csim_ctx* ctx);
+csim_status csim_device_info(csim_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int* clock_khz);
+
+/* Roster: uploaded once.  region = arbitrary integer codes (equal code == same region). */
+csim_status csim_upload_roster(csim_ctx* ctx, int32_t n_electors, const double* ideology_score,
+                               const int32_t* region_code, const uint8_t* is_papabile);
+
+/* Host-side, fp64, bit-identical to the reference's repeated add / multiply:
+ * out[i] = beta in effect in round first_round + i when the model is called once per round. */
+csim_status csim_beta_schedule(const csim_params* p, int32_t first_round, int32_t n_rounds, double* out);
+/* smallest integer v with (double)v >= threshold * n_electors */
+int32_t     csim_need_votes(double supermajority_threshold, int32_t n_electors);
+
+/* P[E, E] for one round with effective beta `beta` (host buffers in and out).
+ * prev_vote[E]  : candidate index each elector voted for last round, -1 = none   (nullable -> stickiness off)
+ * prev_count[E] : last round's count per candidate                              (nullable -> bandwagon off)
+ * fatigued[E]   : 1 = candidate fatigued (used iff p->enable_candidate_fatigue) (nullable)
+ * shares[E]     : last round's vote shares (used iff p->enable_stop_candidate)  (nullable)
+ * precision     : CSIM_FP64 -> P_out is double*, CSIM_FP32 -> float*. */
+csim_status csim_prob_matrix(csim_ctx* ctx, const csim_params* p, double beta,
+                             const int32_t* prev_vote, const int32_t* prev_count,
+                             const uint8_t* fatigued, const double* shares,
+                             int32_t precision, void* P_out);
+
+/* The hot path: a batch of independent trials. */
+csim_status csim_run(csim_ctx* ctx, const csim_run_args* args);
+
+/* Diagnostics for bench.py: number of kernel launches this context has issued,
+ * and the device time (ms, CUDA events on the launch stream) of the last csim_run's trial kernel. */
+csim_status csim_stats(csim_ctx* ctx, int64_t* kernel_launches, float* last_trial_kernel_ms);
+
+/* Instruction-throughput microbenchmarks used as roofline denominators:
+ * kind 0 = FP32 FFMA, 1 = MUFU.EX2, 2 = mixed FADD/FMUL/FFMA + 1 MUFU per 8.
+ * Returns giga thread-instructions per second over the whole device. */
+csim_status csim_microbench(csim_ctx* ctx, int32_t kind, double* ginstr_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONCLAVE_B200_H */
