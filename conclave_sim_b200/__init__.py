@@ -1,0 +1,20 @@
+"""conclave_sim_b200 — B200-native Monte Carlo voting engine, drop-in for the hot path of
+potalora/conclave_sim (src/simulate.py per-round body + src/model.py transition model).
+
+Layout:
+  csrc/            hand-written sm_100a CUDA kernels + the C ABI (include/conclave_b200.h)
+  _cabi.py         ctypes binding of the C ABI (fails loudly when the library is missing)
+  engine.py        device context: roster upload, batched trials, probability matrix
+  model.py         TransitionModel           (mirror of src/model.py:133-586)
+  simulate.py      parse_args / model_params_from_args / _run_single_simulation_worker / main
+                   (mirror of src/simulate.py)
+  ingest.py        ElectorDataIngester        (mirror of src/ingest.py:611-663)
+  dist.py          trial sharding across GPUs + histogram all-reduce (torch.distributed)
+"""
+from ._cabi import (CsimError, WIRING_REF_CLI, WIRING_MODEL, ENGINE_AUTO, ENGINE_DENSE, ENGINE_TABLE,
+                    FP32, FP64, REASON_MAX_ROUNDS, REASON_WINNER, REASON_NO_PROBS)
+from .engine import Engine, get_engine, make_params, RunResult
+
+__all__ = ["Engine", "get_engine", "make_params", "RunResult", "CsimError",
+           "WIRING_REF_CLI", "WIRING_MODEL", "ENGINE_AUTO", "ENGINE_DENSE", "ENGINE_TABLE", "FP32", "FP64",
+           "REASON_MAX_ROUNDS", "REASON_WINNER", "REASON_NO_PROBS"]

@@ -1,0 +1,98 @@
+"""ctypes binding of include/conclave_b200.h.  No torch types cross this boundary.
+
+The product path has no CPU fallback: if the shared library is missing, or no CUDA device is
+usable, calls raise (CsimError / RuntimeError) instead of computing anything on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libconclave_b200.so")
+
+WIRING_REF_CLI, WIRING_MODEL = 0, 1
+ENGINE_AUTO, ENGINE_DENSE, ENGINE_TABLE = 0, 1, 2
+FP32, FP64 = 0, 1
+REASON_MAX_ROUNDS, REASON_WINNER, REASON_NO_PROBS = 0, 1, 2
+BETA_STEPPED, BETA_GROWTH = 0, 1
+ABI_VERSION = 1
+
+EXPORTS = ["csim_abi_version", "csim_last_error", "csim_create", "csim_destroy", "csim_device_info",
+           "csim_upload_roster", "csim_beta_schedule", "csim_need_votes", "csim_prob_matrix", "csim_run",
+           "csim_stats", "csim_microbench"]
+
+
+class CsimError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"conclave_b200 error {status}: {message}")
+        self.status = status
+
+
+class CsimParams(C.Structure):
+    """struct csim_params"""
+    _fields_ = [(n, C.c_double) for n in (
+        "initial_beta_weight", "beta_increment_amount", "beta_growth_rate", "stickiness_factor",
+        "bandwagon_strength", "regional_affinity_bonus", "papabile_weight_factor",
+        "fatigue_vote_share_threshold", "fatigue_penalty_factor",
+        "stop_candidate_threshold_unacceptable_distance", "stop_candidate_threat_min_vote_share",
+        "stop_candidate_boost_factor", "supermajority_threshold")] + [(n, C.c_int32) for n in (
+        "enable_dynamic_beta", "beta_mode", "beta_increment_interval_rounds", "enable_candidate_fatigue",
+        "fatigue_threshold_rounds", "fatigue_top_n_immune", "enable_stop_candidate", "max_rounds",
+        "runoff_threshold_rounds", "runoff_candidate_count", "reserved0", "reserved1")]
+
+
+class CsimRunArgs(C.Structure):
+    """struct csim_run_args"""
+    _fields_ = [
+        ("params", C.POINTER(CsimParams)), ("n_param_sets", C.c_int32), ("wiring", C.c_int32),
+        ("engine", C.c_int32), ("precision", C.c_int32),
+        ("sim_id_begin", C.c_uint64), ("n_sims", C.c_uint64), ("seed", C.c_uint64),
+        ("uniform_tape", C.c_void_p),
+        ("winner", C.c_void_p), ("rounds", C.c_void_p), ("reason", C.c_void_p),
+        ("final_votes", C.c_void_p), ("round_tallies", C.c_void_p),
+        ("winner_hist", C.c_void_p), ("rounds_hist", C.c_void_p), ("totals", C.c_void_p),
+        ("buffers_on_device", C.c_int32), ("reserved", C.c_int32), ("stream", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  conclave_sim_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.csim_abi_version.restype = C.c_int
+    lib.csim_last_error.restype = C.c_char_p
+    lib.csim_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    lib.csim_destroy.argtypes = [C.c_void_p]
+    lib.csim_device_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
+    lib.csim_upload_roster.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.csim_beta_schedule.argtypes = [C.POINTER(CsimParams), C.c_int32, C.c_int32, C.c_void_p]
+    lib.csim_need_votes.argtypes = [C.c_double, C.c_int32]
+    lib.csim_need_votes.restype = C.c_int32
+    lib.csim_prob_matrix.argtypes = [C.c_void_p, C.POINTER(CsimParams), C.c_double, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.csim_run.argtypes = [C.c_void_p, C.POINTER(CsimRunArgs)]
+    lib.csim_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_float)]
+    lib.csim_microbench.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double)]
+    for name in ("csim_create", "csim_destroy", "csim_device_info", "csim_upload_roster", "csim_beta_schedule",
+                 "csim_prob_matrix", "csim_run", "csim_stats", "csim_microbench"):
+        getattr(lib, name).restype = C.c_int
+    v = lib.csim_abi_version()
+    if v != ABI_VERSION:
+        raise RuntimeError(f"{LIB_PATH}: ABI version {v}, binding expects {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(status: int):
+    if status != 0:
+        msg = load_library().csim_last_error()
+        raise CsimError(status, msg.decode("utf-8", "replace") if msg else "")

@@ -1,0 +1,505 @@
+// cabi.cu — implementation of include/conclave_b200.h (the C ABI) on top of the kernels.
+//
+// Host-side responsibilities: validate arguments, derive the per-set constants exactly as the
+// reference derives them in fp64 (beta schedule model.py:562-580, vote threshold
+// simulate.py:175), size grids as multiples of the SM count, and move buffers when the caller
+// hands host memory.  There is no CPU implementation of the hot path in this file.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "conclave_b200.h"
+#include "common.cuh"
+#include "exact64.cuh"
+#include "dense32.cuh"
+#include "prob32.cuh"
+
+static thread_local std::string g_err;
+
+static csim_status fail(csim_status st, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return st;
+}
+
+#define CU_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess)                                                                         \
+            return fail(CSIM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// grow-only device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct csim_ctx {
+    int device = 0;
+    cudaDeviceProp prop{};
+    int E = 0, Epad = 0, G = 0;
+    DevBuf x64, x32, region, pap;
+    DevBuf sets, betas, nbeta, W;
+    // host-buffer mode staging
+    DevBuf o_winner, o_rounds, o_reason, o_final, o_tallies, o_whist, o_rhist, o_totals, i_tape;
+    // prob-matrix staging
+    DevBuf p_prev, p_cnt, p_fat, p_shares, p_bw, p_out;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+    int64_t launches = 0;
+    float last_ms = -1.f;
+};
+
+extern "C" int csim_abi_version(void) { return CSIM_ABI_VERSION; }
+extern "C" const char* csim_last_error(void) { return g_err.c_str(); }
+
+extern "C" csim_status csim_create(csim_ctx** out, int device) {
+    if (!out) return fail(CSIM_ERR_INVALID, "csim_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(CSIM_ERR_CUDA, "csim_create: no usable CUDA device (%s); this engine has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n) return fail(CSIM_ERR_INVALID, "csim_create: device %d out of range [0,%d)", device, n);
+    CU_TRY(cudaSetDevice(device));
+    csim_ctx* c = new csim_ctx();
+    c->device = device;
+    e = cudaGetDeviceProperties(&c->prop, device);
+    if (e != cudaSuccess) { delete c; return fail(CSIM_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
+    if (c->prop.major < 10) {
+        int major = c->prop.major, minor = c->prop.minor;
+        delete c;
+        return fail(CSIM_ERR_UNSUPPORTED, "csim_create: device is sm_%d%d; this library is built for sm_100a only", major, minor);
+    }
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    *out = c;
+    return CSIM_OK;
+}
+
+extern "C" csim_status csim_destroy(csim_ctx* c) {
+    if (!c) return CSIM_OK;
+    cudaSetDevice(c->device);
+    for (DevBuf* b : {&c->x64, &c->x32, &c->region, &c->pap, &c->sets, &c->betas, &c->nbeta, &c->W, &c->o_winner, &c->o_rounds,
+                      &c->o_reason, &c->o_final, &c->o_tallies, &c->o_whist, &c->o_rhist, &c->o_totals, &c->i_tape,
+                      &c->p_prev, &c->p_cnt, &c->p_fat, &c->p_shares, &c->p_bw, &c->p_out})
+        b->release();
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    delete c;
+    return CSIM_OK;
+}
+
+extern "C" csim_status csim_device_info(csim_ctx* c, int* sm_count, int* cc_major, int* cc_minor, int* clock_khz) {
+    if (!c) return fail(CSIM_ERR_INVALID, "csim_device_info: ctx is NULL");
+    if (sm_count) *sm_count = c->prop.multiProcessorCount;
+    if (cc_major) *cc_major = c->prop.major;
+    if (cc_minor) *cc_minor = c->prop.minor;
+    if (clock_khz) { int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device); *clock_khz = khz; }
+    return CSIM_OK;
+}
+
+extern "C" csim_status csim_upload_roster(csim_ctx* c, int32_t E, const double* x, const int32_t* region, const uint8_t* pap) {
+    if (!c) return fail(CSIM_ERR_INVALID, "csim_upload_roster: ctx is NULL");
+    if (E <= 0 || !x || !region || !pap) return fail(CSIM_ERR_INVALID, "csim_upload_roster: need E > 0 and non-NULL columns (E=%d)", E);
+    CU_TRY(cudaSetDevice(c->device));
+    // dense region codes (equal code == same region), order of first appearance
+    std::map<int32_t, int32_t> code;
+    std::vector<int32_t> dense(E);
+    for (int i = 0; i < E; ++i) {
+        auto it = code.find(region[i]);
+        if (it == code.end()) it = code.emplace(region[i], (int32_t)code.size()).first;
+        dense[i] = it->second;
+    }
+    std::vector<float> xf(E);
+    std::vector<uint8_t> pp(E);
+    for (int i = 0; i < E; ++i) { xf[i] = (float)x[i]; pp[i] = pap[i] ? 1 : 0; }
+    CU_TRY(c->x64.reserve(sizeof(double) * E));
+    CU_TRY(c->x32.reserve(sizeof(float) * E));
+    CU_TRY(c->region.reserve(sizeof(int32_t) * E));
+    CU_TRY(c->pap.reserve(E));
+    CU_TRY(cudaMemcpy(c->x64.p, x, sizeof(double) * E, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(c->x32.p, xf.data(), sizeof(float) * E, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(c->region.p, dense.data(), sizeof(int32_t) * E, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(c->pap.p, pp.data(), E, cudaMemcpyHostToDevice));
+    c->E = E; c->Epad = (E + 31) & ~31; c->G = (int)code.size();
+    return CSIM_OK;
+}
+
+// model.py:562-580
+static double beta_step(const csim_params* p, double beta, int r) {
+    if (!p->enable_dynamic_beta || r <= 0) return beta;
+    if (p->beta_mode == CSIM_BETA_STEPPED) {
+        const int iv = p->beta_increment_interval_rounds;
+        if (iv > 0 && r % iv == 0) beta = beta + p->beta_increment_amount;
+    } else if (p->beta_growth_rate > 1.0) {
+        beta = beta * p->beta_growth_rate;
+    }
+    return beta;
+}
+
+extern "C" csim_status csim_beta_schedule(const csim_params* p, int32_t first_round, int32_t n_rounds, double* out) {
+    if (!p || !out || n_rounds < 0 || first_round < 1) return fail(CSIM_ERR_INVALID, "csim_beta_schedule: bad arguments");
+    double b = p->initial_beta_weight;
+    for (int r = 1; r < first_round + n_rounds; ++r) {
+        b = beta_step(p, b, r);
+        if (r >= first_round) out[r - first_round] = b;
+    }
+    return CSIM_OK;
+}
+
+extern "C" int32_t csim_need_votes(double thr, int32_t E) {
+    const double t = thr * (double)E;               // simulate.py:175
+    if (!(t == t)) return INT32_MAX;                // NaN threshold: never reached
+    if (t <= 0.0) return 0;
+    if (t > 2.0e9) return INT32_MAX;
+    int32_t v = (int32_t)floor(t);
+    while ((double)v < t) ++v;
+    while (v > 0 && (double)(v - 1) >= t) --v;
+    return v;
+}
+
+static RosterDev roster_dev(const csim_ctx* c) {
+    RosterDev r;
+    r.E = c->E; r.Epad = c->Epad; r.G = c->G;
+    r.x64 = (const double*)c->x64.p; r.x32 = (const float*)c->x32.p;
+    r.region = (const int32_t*)c->region.p; r.pap = (const uint8_t*)c->pap.p;
+    return r;
+}
+
+static DevSet make_set(const csim_params* p, int E, int wiring) {
+    DevSet s;
+    memset(&s, 0, sizeof s);
+    const bool model = wiring == CSIM_WIRING_MODEL;
+    s.st1p = 1 + p->stickiness_factor;
+    s.bandwagon = p->bandwagon_strength;
+    s.bonus = p->regional_affinity_bonus;
+    s.pwf = p->papabile_weight_factor;
+    s.fat_thr = p->fatigue_vote_share_threshold;
+    s.fat_pen = p->fatigue_penalty_factor;
+    s.stop_D = p->stop_candidate_threshold_unacceptable_distance;
+    s.stop_T = p->stop_candidate_threat_min_vote_share;
+    s.stop_boost = p->stop_candidate_boost_factor;
+    s.f_st1p = (float)s.st1p; s.f_bandwagon = (float)s.bandwagon; s.f_bonus = (float)s.bonus; s.f_pwf = (float)s.pwf;
+    s.f_fat_pen = (float)s.fat_pen; s.f_stop_D = (float)s.stop_D; s.f_stop_boost = (float)s.stop_boost;
+    s.need = csim_need_votes(p->supermajority_threshold, E);
+    s.max_rounds = p->max_rounds;
+    s.rr = p->runoff_threshold_rounds;
+    s.k = std::max(0, std::min(p->runoff_candidate_count, E));
+    s.has_sticky = model && p->stickiness_factor > 0;
+    s.has_bw = model && p->bandwagon_strength > 0;
+    s.en_fat = model && p->enable_candidate_fatigue;
+    s.fat_rounds = std::max(0, p->fatigue_threshold_rounds);
+    s.fat_top_n = std::max(0, p->fatigue_top_n_immune);
+    s.en_stop = model && p->enable_stop_candidate;
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// csim_prob_matrix
+// ---------------------------------------------------------------------------------------------
+extern "C" csim_status csim_prob_matrix(csim_ctx* c, const csim_params* p, double beta, const int32_t* prev_vote,
+                                        const int32_t* prev_count, const uint8_t* fatigued, const double* shares,
+                                        int32_t precision, void* P_out) {
+    if (!c || !p || !P_out) return fail(CSIM_ERR_INVALID, "csim_prob_matrix: NULL argument");
+    if (c->E <= 0) return fail(CSIM_ERR_STATE, "csim_prob_matrix: roster not uploaded");
+    if (precision != CSIM_FP32 && precision != CSIM_FP64) return fail(CSIM_ERR_INVALID, "csim_prob_matrix: bad precision %d", precision);
+    CU_TRY(cudaSetDevice(c->device));
+    const int E = c->E;
+    DevSet S = make_set(p, E, CSIM_WIRING_MODEL);   // the standalone model honours every term it is given
+    const int32_t* d_prev = nullptr; const int32_t* d_cnt = nullptr; const uint8_t* d_fat = nullptr; const double* d_sh = nullptr;
+    if (prev_vote) { CU_TRY(c->p_prev.reserve(4 * E)); CU_TRY(cudaMemcpy(c->p_prev.p, prev_vote, 4 * E, cudaMemcpyHostToDevice)); d_prev = (const int32_t*)c->p_prev.p; }
+    if (prev_count) { CU_TRY(c->p_cnt.reserve(4 * E)); CU_TRY(cudaMemcpy(c->p_cnt.p, prev_count, 4 * E, cudaMemcpyHostToDevice)); d_cnt = (const int32_t*)c->p_cnt.p; }
+    if (fatigued) { CU_TRY(c->p_fat.reserve(E)); CU_TRY(cudaMemcpy(c->p_fat.p, fatigued, E, cudaMemcpyHostToDevice)); d_fat = (const uint8_t*)c->p_fat.p; }
+    if (shares) { CU_TRY(c->p_shares.reserve(8 * E)); CU_TRY(cudaMemcpy(c->p_shares.p, shares, 8 * E, cudaMemcpyHostToDevice)); d_sh = (const double*)c->p_shares.p; }
+    RosterDev ro = roster_dev(c);
+    if (precision == CSIM_FP64) {
+        CU_TRY(c->sets.reserve(sizeof(DevSet)));
+        CU_TRY(c->betas.reserve(sizeof(double)));
+        CU_TRY(cudaMemcpy(c->sets.p, &S, sizeof S, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(c->betas.p, &beta, sizeof beta, cudaMemcpyHostToDevice));
+        CU_TRY(c->W.reserve(sizeof(double) * (size_t)E * c->Epad));
+        CU_TRY(c->p_bw.reserve(8 * E));
+        CU_TRY(c->p_out.reserve(sizeof(double) * (size_t)E * E));
+        dim3 g((c->Epad + 127) / 128, E, 1);
+        k_base_scores64<<<g, 128>>>(ro, (const DevSet*)c->sets.p, (const double*)c->betas.p, 1, (double*)c->W.p);
+        ++c->launches;
+        ProbArgs a;
+        a.ro = ro; a.S = S; a.W = (const double*)c->W.p; a.prev_vote = d_prev; a.prev_count = d_cnt; a.fatigued = d_fat;
+        a.shares = d_sh; a.bw = (double*)c->p_bw.p; a.P = (double*)c->p_out.p;
+        int use_bw = 0;
+        if (d_cnt && S.has_bw) {
+            int mx = 0;
+            for (int i = 0; i < E; ++i) mx = std::max(mx, prev_count[i]);
+            if (mx > 0) { use_bw = 1; k_prob_bw64<<<1, 256>>>(a); ++c->launches; }
+        }
+        k_prob_matrix64<<<(E + 63) / 64, 64>>>(a, use_bw);
+        ++c->launches;
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpy(P_out, c->p_out.p, sizeof(double) * (size_t)E * E, cudaMemcpyDeviceToHost));
+    } else {
+        CU_TRY(c->p_out.reserve(sizeof(float) * (size_t)E * E));
+        Prob32Args a;
+        a.ro = ro; a.S = S; a.nb = (float)(-beta * 1.4426950408889634);
+        a.prev_vote = d_prev; a.prev_count = d_cnt; a.fatigued = d_fat; a.shares = d_sh; a.P = (float*)c->p_out.p;
+        k_prob_matrix32<<<(E + 3) / 4, 128>>>(a);
+        ++c->launches;
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpy(P_out, c->p_out.p, sizeof(float) * (size_t)E * E, cudaMemcpyDeviceToHost));
+    }
+    return CSIM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// csim_run
+// ---------------------------------------------------------------------------------------------
+template <class K>
+static csim_status persistent_grid(csim_ctx* c, K kernel, int threads, size_t smem, uint64_t n_trials, int warps_per_cta, int* grid) {
+    CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    if (per_sm < 1) return fail(CSIM_ERR_UNSUPPORTED, "kernel does not fit on an SM (threads=%d, smem=%zu)", threads, smem);
+    const uint64_t want = (n_trials + warps_per_cta - 1) / warps_per_cta;
+    const uint64_t full = (uint64_t)c->prop.multiProcessorCount * per_sm;     // a multiple of the SM count
+    *grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, full));
+    return CSIM_OK;
+}
+
+static csim_status launch_exact64(csim_ctx* c, const csim_run_args* ra, const std::vector<DevSet>& hs, const BatchDev& b,
+                                  const TrialOut& out, cudaStream_t st) {
+    const int E = c->E, R = b.R;
+    const size_t wbytes = sizeof(double) * (size_t)b.n_sets * R * E * c->Epad;
+    if (wbytes > ((size_t)96 << 30)) return fail(CSIM_ERR_UNSUPPORTED, "fp64 base-score tables need %zu bytes", wbytes);
+    CU_TRY(c->W.reserve(wbytes));
+    RosterDev ro = roster_dev(c);
+    dim3 g((c->Epad + 127) / 128, E, b.n_sets * R);
+    if (g.z > 65535) return fail(CSIM_ERR_UNSUPPORTED, "n_param_sets * max_rounds = %u exceeds 65535 in fp64 mode", g.z);
+    k_base_scores64<<<g, 128, 0, st>>>(ro, b.sets, (const double*)c->betas.p, R, (double*)c->W.p);
+    ++c->launches;
+    Exact64Args a;
+    a.ro = ro; a.b = b; a.out = out; a.W = (const double*)c->W.p; a.wiring = ra->wiring;
+    int Fmax = 1, kmax = 1;
+    for (const DevSet& s : hs) { Fmax = std::max(Fmax, s.fat_rounds); kmax = std::max(kmax, s.k); }
+    a.Fmax = Fmax; a.kmax = kmax;
+    a.warp_smem = exact64_warp_smem(E, Fmax, kmax);
+    int wpc = (int)std::min<size_t>(8, (200 * 1024) / a.warp_smem);
+    if (wpc < 1) return fail(CSIM_ERR_UNSUPPORTED, "roster of %d electors needs %zu B of shared memory per trial", E, a.warp_smem);
+    a.warps_per_cta = wpc;
+    const size_t smem = a.warp_smem * wpc;
+    int grid = 1;
+    csim_status s = persistent_grid(c, k_trials_exact64, wpc * 32, smem, (uint64_t)b.n_sets * b.n_sims, wpc, &grid);
+    if (s != CSIM_OK) return s;
+    CU_TRY(cudaEventRecord(c->ev0, st));
+    k_trials_exact64<<<grid, wpc * 32, smem, st>>>(a);
+    CU_TRY(cudaEventRecord(c->ev1, st));
+    c->ev_valid = true;
+    ++c->launches;
+    CU_TRY(cudaGetLastError());
+    return CSIM_OK;
+}
+
+template <int NCH, int LC, bool MODEL>
+static csim_status launch_dense32_t(csim_ctx* c, Dense32Args& a, cudaStream_t st) {
+    a.cta_smem = dense32_cta_smem<NCH>(a.L, a.ro.G);
+    a.warp_smem = dense32_warp_smem<NCH>(a.ro.E, a.L, a.kmax, MODEL);
+    int wpc = 8;
+    while (wpc > 1 && a.cta_smem + a.warp_smem * wpc > 220 * 1024) wpc >>= 1;
+    if (a.cta_smem + a.warp_smem * wpc > 220 * 1024)
+        return fail(CSIM_ERR_UNSUPPORTED, "roster of %d electors / %d regions needs %zu B of shared memory", a.ro.E, a.ro.G, a.cta_smem + a.warp_smem);
+    a.warps_per_cta = wpc;
+    const size_t smem = a.cta_smem + a.warp_smem * wpc;
+    int grid = 1;
+    auto kern = k_trials_dense32<NCH, LC, MODEL>;
+    csim_status s = persistent_grid(c, kern, wpc * 32, smem, (uint64_t)a.b.n_sets * a.b.n_sims, wpc, &grid);
+    if (s != CSIM_OK) return s;
+    CU_TRY(cudaEventRecord(c->ev0, st));
+    kern<<<grid, wpc * 32, smem, st>>>(a);
+    CU_TRY(cudaEventRecord(c->ev1, st));
+    c->ev_valid = true;
+    ++c->launches;
+    CU_TRY(cudaGetLastError());
+    return CSIM_OK;
+}
+
+static csim_status launch_dense32(csim_ctx* c, const csim_run_args* ra, const std::vector<DevSet>& hs, const BatchDev& b,
+                                  const TrialOut& out, cudaStream_t st) {
+    for (const DevSet& s : hs)
+        if (s.en_fat || s.en_stop)
+            return fail(CSIM_ERR_UNSUPPORTED, "candidate fatigue / stop-candidate are implemented in CSIM_FP64 precision only");
+    for (int i = 0; i < ra->n_param_sets; ++i)
+        if (ra->params[i].regional_affinity_bonus < 0 || ra->params[i].bandwagon_strength < 0 || ra->params[i].papabile_weight_factor < 0)
+            return fail(CSIM_ERR_UNSUPPORTED, "negative bonus / strength / papabile factor: use CSIM_FP64 precision");
+    if (c->G > 64) return fail(CSIM_ERR_UNSUPPORTED, "%d distinct regions (> 64): use CSIM_FP64 precision", c->G);
+    Dense32Args a;
+    a.ro = roster_dev(c); a.b = b; a.out = out; a.nbeta = (const float*)c->nbeta.p; a.wiring = ra->wiring;
+    int kmax = 1;
+    for (const DevSet& s : hs) kmax = std::max(kmax, s.k);
+    a.kmax = kmax;
+    const bool model = ra->wiring == CSIM_WIRING_MODEL;
+    const int E = c->E;
+    if (E <= 17 * 8) {
+        a.L = 8;
+        return model ? launch_dense32_t<17, 8, true>(c, a, st) : launch_dense32_t<17, 8, false>(c, a, st);
+    }
+    a.L = (((E + 31) / 32) + 3) & ~3;
+    return model ? launch_dense32_t<32, 0, true>(c, a, st) : launch_dense32_t<32, 0, false>(c, a, st);
+}
+
+extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
+    if (!c || !ra) return fail(CSIM_ERR_INVALID, "csim_run: NULL argument");
+    if (c->E <= 0) return fail(CSIM_ERR_STATE, "csim_run: roster not uploaded");
+    if (!ra->params || ra->n_param_sets < 1) return fail(CSIM_ERR_INVALID, "csim_run: need at least one parameter set");
+    if (!ra->winner || !ra->rounds) return fail(CSIM_ERR_INVALID, "csim_run: winner and rounds outputs are required");
+    if (ra->wiring != CSIM_WIRING_REF_CLI && ra->wiring != CSIM_WIRING_MODEL) return fail(CSIM_ERR_INVALID, "csim_run: bad wiring %d", ra->wiring);
+    if (ra->precision != CSIM_FP32 && ra->precision != CSIM_FP64) return fail(CSIM_ERR_INVALID, "csim_run: bad precision %d", ra->precision);
+    if (ra->engine != CSIM_ENGINE_AUTO && ra->engine != CSIM_ENGINE_DENSE && ra->engine != CSIM_ENGINE_TABLE)
+        return fail(CSIM_ERR_INVALID, "csim_run: bad engine %d", ra->engine);
+    if (ra->engine == CSIM_ENGINE_TABLE) return fail(CSIM_ERR_UNSUPPORTED, "csim_run: the table engine is not built yet");
+    if (ra->uniform_tape && ra->precision != CSIM_FP64) return fail(CSIM_ERR_INVALID, "csim_run: a uniform tape requires CSIM_FP64 precision");
+    const int R = ra->params[0].max_rounds;
+    if (R < 0) return fail(CSIM_ERR_INVALID, "csim_run: max_rounds < 0");
+    for (int i = 0; i < ra->n_param_sets; ++i)
+        if (ra->params[i].max_rounds != R) return fail(CSIM_ERR_INVALID, "csim_run: every parameter set of a batch must share max_rounds");
+    const uint64_t n = (uint64_t)ra->n_param_sets * ra->n_sims;
+    if (n == 0) return CSIM_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)ra->stream;
+    const int E = c->E;
+    const bool dev = ra->buffers_on_device != 0;
+
+    // per-set constants
+    std::vector<DevSet> hs(ra->n_param_sets);
+    std::vector<double> hb((size_t)ra->n_param_sets * std::max(R, 1));
+    std::vector<float> hnb(hb.size());
+    for (int i = 0; i < ra->n_param_sets; ++i) {
+        hs[i] = make_set(&ra->params[i], E, ra->wiring);
+        if (R > 0) csim_beta_schedule(&ra->params[i], 1, R, &hb[(size_t)i * R]);
+        for (int r = 0; r < R; ++r) hnb[(size_t)i * R + r] = (float)(-hb[(size_t)i * R + r] * 1.4426950408889634);
+    }
+    CU_TRY(c->sets.reserve(sizeof(DevSet) * hs.size()));
+    CU_TRY(c->betas.reserve(sizeof(double) * hb.size()));
+    CU_TRY(c->nbeta.reserve(sizeof(float) * hnb.size()));
+    CU_TRY(cudaMemcpyAsync(c->sets.p, hs.data(), sizeof(DevSet) * hs.size(), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(c->betas.p, hb.data(), sizeof(double) * hb.size(), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(c->nbeta.p, hnb.data(), sizeof(float) * hnb.size(), cudaMemcpyHostToDevice, st));
+    // the vectors above are pageable: the async copies have completed their host read on return
+
+    BatchDev b;
+    b.sets = (const DevSet*)c->sets.p; b.n_sets = ra->n_param_sets; b.R = R; b.n_sims = ra->n_sims;
+    b.sim_id_begin = ra->sim_id_begin; b.seed_lo = (uint32_t)ra->seed; b.seed_hi = (uint32_t)(ra->seed >> 32);
+    b.tape = nullptr;
+    TrialOut out;
+    memset(&out, 0, sizeof out);
+    const size_t nh_w = (size_t)ra->n_param_sets * (E + 1), nh_r = (size_t)ra->n_param_sets * (R + 1), nh_t = (size_t)ra->n_param_sets * 2;
+    if (dev) {
+        b.tape = ra->uniform_tape;
+        out.winner = ra->winner; out.rounds = ra->rounds; out.reason = ra->reason; out.final_votes = ra->final_votes;
+        out.round_tallies = ra->round_tallies;
+        out.winner_hist = (unsigned long long*)ra->winner_hist; out.rounds_hist = (unsigned long long*)ra->rounds_hist;
+        out.totals = (unsigned long long*)ra->totals;
+    } else {
+        if (ra->uniform_tape) {
+            const size_t tb = sizeof(double) * n * (size_t)R * E;
+            CU_TRY(c->i_tape.reserve(tb));
+            CU_TRY(cudaMemcpyAsync(c->i_tape.p, ra->uniform_tape, tb, cudaMemcpyHostToDevice, st));
+            b.tape = (const double*)c->i_tape.p;
+        }
+        CU_TRY(c->o_winner.reserve(4 * n)); out.winner = (int32_t*)c->o_winner.p;
+        CU_TRY(c->o_rounds.reserve(4 * n)); out.rounds = (int32_t*)c->o_rounds.p;
+        if (ra->reason) { CU_TRY(c->o_reason.reserve(n)); out.reason = (uint8_t*)c->o_reason.p; }
+        if (ra->final_votes) { CU_TRY(c->o_final.reserve(4 * n * E)); out.final_votes = (int32_t*)c->o_final.p; }
+        if (ra->round_tallies) { CU_TRY(c->o_tallies.reserve(4 * n * (size_t)R * E)); out.round_tallies = (int32_t*)c->o_tallies.p; }
+        if (ra->winner_hist) { CU_TRY(c->o_whist.reserve(8 * nh_w)); CU_TRY(cudaMemsetAsync(c->o_whist.p, 0, 8 * nh_w, st)); out.winner_hist = (unsigned long long*)c->o_whist.p; }
+        if (ra->rounds_hist) { CU_TRY(c->o_rhist.reserve(8 * nh_r)); CU_TRY(cudaMemsetAsync(c->o_rhist.p, 0, 8 * nh_r, st)); out.rounds_hist = (unsigned long long*)c->o_rhist.p; }
+        if (ra->totals) { CU_TRY(c->o_totals.reserve(8 * nh_t)); CU_TRY(cudaMemsetAsync(c->o_totals.p, 0, 8 * nh_t, st)); out.totals = (unsigned long long*)c->o_totals.p; }
+    }
+
+    csim_status s = ra->precision == CSIM_FP64 ? launch_exact64(c, ra, hs, b, out, st) : launch_dense32(c, ra, hs, b, out, st);
+    if (s != CSIM_OK) return s;
+
+    if (!dev) {
+        CU_TRY(cudaMemcpyAsync(ra->winner, out.winner, 4 * n, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(ra->rounds, out.rounds, 4 * n, cudaMemcpyDeviceToHost, st));
+        if (ra->reason) CU_TRY(cudaMemcpyAsync(ra->reason, out.reason, n, cudaMemcpyDeviceToHost, st));
+        if (ra->final_votes) CU_TRY(cudaMemcpyAsync(ra->final_votes, out.final_votes, 4 * n * E, cudaMemcpyDeviceToHost, st));
+        if (ra->round_tallies) CU_TRY(cudaMemcpyAsync(ra->round_tallies, out.round_tallies, 4 * n * (size_t)R * E, cudaMemcpyDeviceToHost, st));
+        std::vector<int64_t> tw, tr, tt;
+        if (ra->winner_hist) { tw.resize(nh_w); CU_TRY(cudaMemcpyAsync(tw.data(), out.winner_hist, 8 * nh_w, cudaMemcpyDeviceToHost, st)); }
+        if (ra->rounds_hist) { tr.resize(nh_r); CU_TRY(cudaMemcpyAsync(tr.data(), out.rounds_hist, 8 * nh_r, cudaMemcpyDeviceToHost, st)); }
+        if (ra->totals) { tt.resize(nh_t); CU_TRY(cudaMemcpyAsync(tt.data(), out.totals, 8 * nh_t, cudaMemcpyDeviceToHost, st)); }
+        CU_TRY(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < tw.size(); ++i) ra->winner_hist[i] += tw[i];
+        for (size_t i = 0; i < tr.size(); ++i) ra->rounds_hist[i] += tr[i];
+        for (size_t i = 0; i < tt.size(); ++i) ra->totals[i] += tt[i];
+        float ms = -1.f;
+        if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last_ms = ms;
+    }
+    return CSIM_OK;
+}
+
+extern "C" csim_status csim_stats(csim_ctx* c, int64_t* kernel_launches, float* last_trial_kernel_ms) {
+    if (!c) return fail(CSIM_ERR_INVALID, "csim_stats: ctx is NULL");
+    if (kernel_launches) *kernel_launches = c->launches;
+    if (last_trial_kernel_ms) {
+        float ms = c->last_ms;
+        if (c->ev_valid && cudaEventQuery(c->ev1) == cudaSuccess) {
+            float m2 = -1.f;
+            if (cudaEventElapsedTime(&m2, c->ev0, c->ev1) == cudaSuccess) ms = c->last_ms = m2;
+        }
+        *last_trial_kernel_ms = ms;
+    }
+    return CSIM_OK;
+}
+
+extern "C" csim_status csim_microbench(csim_ctx* c, int32_t kind, double* ginstr_per_s) {
+    if (!c || !ginstr_per_s) return fail(CSIM_ERR_INVALID, "csim_microbench: NULL argument");
+    if (kind < 0 || kind > 2) return fail(CSIM_ERR_INVALID, "csim_microbench: kind %d", kind);
+    CU_TRY(cudaSetDevice(c->device));
+    float* sink = nullptr;
+    CU_TRY(cudaMalloc(&sink, 4));
+    const int iters = 1 << 15, threads = 256, grid = c->prop.multiProcessorCount * 8;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        if (kind == 0) k_microbench<0><<<grid, threads>>>(sink, iters, 1.0000001f, 1e-9f);
+        else if (kind == 1) k_microbench<1><<<grid, threads>>>(sink, iters, 0.f, 0.f);
+        else k_microbench<2><<<grid, threads>>>(sink, iters, 0.37f, -1.3f);
+        cudaEventRecord(e1);
+        ++c->launches;
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) { cudaFree(sink); return fail(CSIM_ERR_CUDA, "microbench: %s", cudaGetErrorString(e)); }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double per_iter = kind == 2 ? 32.0 : 8.0;      // thread-instructions per loop iteration (kind 2: 8 x {FADD,FMUL,MUFU,FFMA})
+        const double g = (double)grid * threads * iters * per_iter / (ms * 1e-3) * 1e-9;
+        if (rep > 0) best = std::max(best, g);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(sink);
+    *ginstr_per_s = best;
+    return CSIM_OK;
+}

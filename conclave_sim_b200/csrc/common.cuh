@@ -1,0 +1,137 @@
+// common.cuh — device-side structures and helpers shared by the conclave kernels.
+//
+// Reference semantics (file:line into the reference repo) are cited at each
+// function; the arithmetic itself is restated from SURVEY.md Appendix A and the
+// CPU oracle, never copied.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "conclave_b200.h"
+
+#define CSIM_WARP 32
+#define CSIM_FULL 0xffffffffu
+
+// Per parameter-set constants, precomputed on the host (fp64 exactly as the
+// reference computes them; fp32 copies for the fast path).
+struct DevSet {
+    double st1p;          // 1 + stickiness_factor                    (model.py:363)
+    double bandwagon;     // bandwagon_strength                        (model.py:349)
+    double bonus;         // regional_affinity_bonus                   (model.py:323)
+    double pwf;           // papabile_weight_factor                    (model.py:319)
+    double fat_thr;       // fatigue_vote_share_threshold              (simulate.py:111)
+    double fat_pen;       // fatigue_penalty_factor                    (model.py:379)
+    double stop_D;        // stop_candidate_threshold_unacceptable_distance (model.py:390)
+    double stop_T;        // stop_candidate_threat_min_vote_share      (model.py:397)
+    double stop_boost;    // stop_candidate_boost_factor               (model.py:414)
+    float  f_st1p, f_bandwagon, f_bonus, f_pwf, f_fat_pen, f_stop_D, f_stop_boost, f_pad;
+    int32_t need;         // smallest int v with (double)v >= thr*E    (simulate.py:175)
+    int32_t max_rounds;
+    int32_t rr;           // runoff_threshold_rounds                   (simulate.py:183)
+    int32_t k;            // min(runoff_candidate_count, E)
+    int32_t has_sticky;   // stickiness_factor > 0 and wiring == model
+    int32_t has_bw;       // bandwagon_strength > 0 and wiring == model
+    int32_t en_fat;       // candidate fatigue live (model wiring only)
+    int32_t fat_rounds;
+    int32_t fat_top_n;
+    int32_t en_stop;      // stop-candidate live (model wiring only)
+    int32_t pad0, pad1;
+};
+
+struct RosterDev {
+    int32_t E;            // electors == candidates
+    int32_t Epad;         // E rounded up to a multiple of 32 (row pitch of [c][e] tables)
+    int32_t G;            // number of distinct regions (dense codes 0..G-1)
+    const double*  x64;   // [E]   ideology_score
+    const float*   x32;   // [E]
+    const int32_t* region;// [E]   dense region code
+    const uint8_t* pap;   // [E]   is_papabile
+};
+
+struct TrialOut {
+    int32_t* winner;        // [n]
+    int32_t* rounds;        // [n]
+    uint8_t* reason;        // [n] or null
+    int32_t* final_votes;   // [n, E] or null
+    int32_t* round_tallies; // [n, R, E] or null
+    unsigned long long* winner_hist;  // [sets, E+1] or null
+    unsigned long long* rounds_hist;  // [sets, R+1] or null
+    unsigned long long* totals;       // [sets, 2] or null
+};
+
+struct BatchDev {
+    const DevSet* sets;     // [n_sets]
+    int32_t  n_sets;
+    int32_t  R;             // max_rounds (same for every set of a batch)
+    uint64_t n_sims;        // per set
+    uint64_t sim_id_begin;
+    uint32_t seed_lo, seed_hi;
+    const double* tape;     // [n, R*E] or null
+};
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw — SC'11).  Stream layout shared
+// with the oracle: key = (seed_lo, seed_hi);
+//   call A: counter = (sim_lo, sim_hi, round, e >> 2)               -> word (e & 3) = w_a(e)
+//   call B: counter = (sim_lo, sim_hi, round, (e >> 2) | 0x80000000) -> word (e & 3) = w_b(e)
+//   fp64 uniform  u = ((w_a >> 5) * 2^26 + (w_b >> 6)) / 2^53   (the construction numpy's
+//                     MT19937 random_sample uses, so tape and native modes share one path)
+//   fp32 uniform  u = (w_a >> 8) * 2^-24  (= the leading 24 bits of the fp64 uniform)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ double u53_from_words(uint32_t a, uint32_t b) {
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+__device__ __forceinline__ float u24_from_word(uint32_t a) {
+    return (float)(a >> 8) * (1.0f / 16777216.0f);
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ---------------------------------------------------------------------------
+// Warp-level helpers (one warp owns one trial).
+// ---------------------------------------------------------------------------
+// max tally and the LOWEST index attaining it (idxmax, simulate.py:174-176).
+__device__ __forceinline__ void warp_argmax_first(const int32_t* tally, int C, int lane, int& mx, int& arg,
+                                                  const uint8_t* excluded = nullptr) {
+    int bm = -1, ba = 0x7fffffff;
+    for (int c = lane; c < C; c += CSIM_WARP) {
+        if (excluded && excluded[c]) continue;
+        const int v = tally[c];
+        if (v > bm) { bm = v; ba = c; }          // strided scan keeps the lowest c per lane on ties
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const int om = __shfl_xor_sync(CSIM_FULL, bm, off), oa = __shfl_xor_sync(CSIM_FULL, ba, off);
+        if (om > bm || (om == bm && oa < ba)) { bm = om; ba = oa; }
+    }
+    mx = bm; arg = ba;
+}
+
+// First k of a stable descending sort of the tally (ties -> lowest index):
+// Series.nlargest(k) as used at simulate.py:185.  `mark` is a [C] scratch of bytes.
+__device__ __forceinline__ void warp_top_k(const int32_t* tally, int C, int k, int lane, int32_t* eff, uint8_t* mark) {
+    for (int c = lane; c < C; c += CSIM_WARP) mark[c] = 0;
+    __syncwarp();
+    for (int j = 0; j < k; ++j) {
+        int mx, arg;
+        warp_argmax_first(tally, C, lane, mx, arg, mark);
+        if (lane == 0) { eff[j] = arg; mark[arg] = 1; }
+        __syncwarp();
+    }
+}

@@ -1,0 +1,91 @@
+// prob32.cuh — fp32 probability matrix (public API, checked to 1e-5 relative against the
+// fp64 reference values) and the instruction-throughput microbenchmarks used as roofline
+// denominators.
+#pragma once
+#include "common.cuh"
+
+struct Prob32Args {
+    RosterDev ro;
+    DevSet S;
+    float nb;                 // -beta * log2(e)
+    const int32_t* prev_vote; // [E] or null
+    const int32_t* prev_count;// [E] or null
+    const uint8_t* fatigued;  // [E] or null
+    const double* shares;     // [E] or null
+    float* P;                 // [E][C]
+};
+
+// One warp per elector row; lanes stride over candidates (model.py:311-486 in fp32).
+__global__ void k_prob_matrix32(Prob32Args a) {
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int E = a.ro.E, C = E;
+    if (e >= E) return;
+    const float xe = a.ro.x32[e];
+    const int ge = a.ro.region[e];
+    int mx = 0;
+    if (a.prev_count && a.S.has_bw) {
+        for (int c = lane; c < C; c += 32) mx = max(mx, a.prev_count[c]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(CSIM_FULL, mx, off));
+    }
+    const float inv = mx > 0 ? 1.0f / (float)mx : 0.0f;
+    const int prev = (a.prev_vote && a.S.has_sticky) ? a.prev_vote[e] : -1;
+    bool trig = false;
+    if (a.S.en_stop && a.shares) {
+        for (int q = lane; q < C; q += 32)
+            if (fabs(a.ro.x64[e] - a.ro.x64[q]) > a.S.stop_D && a.shares[q] > a.S.stop_T) trig = true;
+        trig = __any_sync(CSIM_FULL, trig);
+    }
+    auto score = [&](int c) -> float {
+        float v = ex2_approx(fabsf(xe - a.ro.x32[c]) * a.nb);
+        if (a.ro.pap[c]) v *= a.S.f_pwf;
+        if (a.ro.region[c] == ge) v += a.S.f_bonus;
+        if (mx > 0) v += (float)a.prev_count[c] * inv * a.S.f_bandwagon;
+        if (c == prev) v *= a.S.f_st1p;
+        v = fmaxf(v, 0.0f);
+        if (a.S.en_fat && a.fatigued && a.fatigued[c]) v *= a.S.f_fat_pen;
+        if (trig && !(fabs(a.ro.x64[e] - a.ro.x64[c]) > a.S.stop_D)) v *= a.S.f_stop_boost;
+        return c == e ? 0.0f : v;
+    };
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) sum += score(c);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(CSIM_FULL, sum, off);
+    if (!(sum > 0.0f)) {
+        for (int c = lane; c < C; c += 32) a.P[(size_t)e * C + c] = 1.0f / (float)C;      // model.py:447-449
+    } else {
+        const float r = 1.0f / sum;
+        for (int c = lane; c < C; c += 32) a.P[(size_t)e * C + c] = score(c) * r;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Microbenchmarks: thread-instructions per second of the pipes the dense kernel lives on.
+// Each thread runs `iters` iterations of 8 independent dependency chains.
+// ---------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256) k_microbench(float* sink, int iters, float a, float b) {
+    float r0 = threadIdx.x * 1e-3f, r1 = r0 + 0.1f, r2 = r0 + 0.2f, r3 = r0 + 0.3f,
+          r4 = r0 + 0.4f, r5 = r0 + 0.5f, r6 = r0 + 0.6f, r7 = r0 + 0.7f;
+    for (int i = 0; i < iters; ++i) {
+        if (KIND == 0) {            // 8 FFMA
+            r0 = fmaf(r0, a, b); r1 = fmaf(r1, a, b); r2 = fmaf(r2, a, b); r3 = fmaf(r3, a, b);
+            r4 = fmaf(r4, a, b); r5 = fmaf(r5, a, b); r6 = fmaf(r6, a, b); r7 = fmaf(r7, a, b);
+        } else if (KIND == 1) {     // 8 MUFU.EX2
+            r0 = ex2_approx(r0); r1 = ex2_approx(r1); r2 = ex2_approx(r2); r3 = ex2_approx(r3);
+            r4 = ex2_approx(r4); r5 = ex2_approx(r5); r6 = ex2_approx(r6); r7 = ex2_approx(r7);
+        } else {                    // the dense kernel's pair body: FADD, FMUL|.|, MUFU.EX2, FFMA  (x2 chains x4)
+            r0 = fmaf(ex2_approx(fabsf(a - r4) * b), r4, r0);
+            r1 = fmaf(ex2_approx(fabsf(a - r5) * b), r5, r1);
+            r2 = fmaf(ex2_approx(fabsf(a - r6) * b), r6, r2);
+            r3 = fmaf(ex2_approx(fabsf(a - r7) * b), r7, r3);
+            r4 = fmaf(ex2_approx(fabsf(a - r0) * b), r0, r4);
+            r5 = fmaf(ex2_approx(fabsf(a - r1) * b), r1, r5);
+            r6 = fmaf(ex2_approx(fabsf(a - r2) * b), r2, r6);
+            r7 = fmaf(ex2_approx(fabsf(a - r3) * b), r3, r7);
+        }
+    }
+    const float s = r0 + r1 + r2 + r3 + r4 + r5 + r6 + r7;
+    if (s == 123.456f) sink[0] = s;   // never true in practice; keeps the chains alive
+}

@@ -1,0 +1,231 @@
+"""Device context of the voting engine: roster upload (once), batched trials, probability matrix.
+
+Replaces the per-trial process pool of the reference (src/simulate.py:330-351): one call runs a
+whole batch of trials on the GPU.  All numerics happen in the CUDA library behind the C ABI
+(include/conclave_b200.h); this module only marshals buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import CsimParams, CsimRunArgs, FP32, FP64, WIRING_MODEL, WIRING_REF_CLI, ENGINE_AUTO, check
+
+# TransitionModel.__init__ defaults, src/model.py:172-191
+MODEL_DEFAULTS: Dict[str, Any] = dict(
+    initial_beta_weight=1.0, enable_dynamic_beta=False, beta_growth_rate=1.05, beta_increment_amount=None,
+    beta_increment_interval_rounds=1, stickiness_factor=0.0, bandwagon_strength=0.0, regional_affinity_bonus=0.0,
+    papabile_weight_factor=1.0, enable_candidate_fatigue=False, fatigue_threshold_rounds=3,
+    fatigue_vote_share_threshold=0.05, fatigue_penalty_factor=0.5, fatigue_top_n_immune=0,
+    enable_stop_candidate=False, stop_candidate_threshold_unacceptable_distance=1.0,
+    stop_candidate_threat_min_vote_share=0.15, stop_candidate_boost_factor=1.5)
+
+
+def make_params(model_params: Optional[Dict[str, Any]] = None, *, max_rounds: int = 100,
+                supermajority_threshold: float = 2 / 3, runoff_threshold_rounds: int = 5,
+                runoff_candidate_count: int = 2, enable_candidate_fatigue: Optional[bool] = None,
+                fatigue_threshold_rounds: Optional[int] = None, fatigue_vote_share_threshold: Optional[float] = None,
+                fatigue_top_n_immune: Optional[int] = None, enable_stop_candidate: Optional[bool] = None) -> CsimParams:
+    """One csim_params from the reference's two argument groups: the TransitionModel kwargs dict
+    (what model_params_from_args returns, src/simulate.py:263-277) and the worker arguments
+    (src/simulate.py:30-41).  Worker-level fatigue / stop arguments, when given, override the
+    model-level ones (the `model` wiring forwards them; under `ref_cli` the engine ignores both)."""
+    unknown = set(model_params or {}) - set(MODEL_DEFAULTS)
+    if unknown:
+        raise TypeError(f"unexpected TransitionModel parameter(s): {sorted(unknown)}")
+    mp = dict(MODEL_DEFAULTS)
+    mp.update(model_params or {})
+    p = CsimParams()
+    p.initial_beta_weight = float(mp["initial_beta_weight"]) if mp["initial_beta_weight"] is not None else 0.0
+    p.enable_dynamic_beta = int(bool(mp["enable_dynamic_beta"]))
+    p.beta_mode = _cabi.BETA_GROWTH if mp["beta_increment_amount"] is None else _cabi.BETA_STEPPED
+    p.beta_increment_amount = 0.0 if mp["beta_increment_amount"] is None else float(mp["beta_increment_amount"])
+    p.beta_increment_interval_rounds = int(mp["beta_increment_interval_rounds"])
+    p.beta_growth_rate = float(mp["beta_growth_rate"])
+    p.stickiness_factor = float(mp["stickiness_factor"])
+    p.bandwagon_strength = float(mp["bandwagon_strength"])
+    p.regional_affinity_bonus = float(mp["regional_affinity_bonus"])
+    p.papabile_weight_factor = float(mp["papabile_weight_factor"])
+    p.fatigue_penalty_factor = float(mp["fatigue_penalty_factor"])
+    p.stop_candidate_threshold_unacceptable_distance = float(mp["stop_candidate_threshold_unacceptable_distance"])
+    p.stop_candidate_threat_min_vote_share = float(mp["stop_candidate_threat_min_vote_share"])
+    p.stop_candidate_boost_factor = float(mp["stop_candidate_boost_factor"])
+    pick = lambda override, key: mp[key] if override is None else override
+    p.enable_candidate_fatigue = int(bool(pick(enable_candidate_fatigue, "enable_candidate_fatigue")))
+    p.fatigue_threshold_rounds = int(pick(fatigue_threshold_rounds, "fatigue_threshold_rounds"))
+    p.fatigue_vote_share_threshold = float(pick(fatigue_vote_share_threshold, "fatigue_vote_share_threshold"))
+    p.fatigue_top_n_immune = int(pick(fatigue_top_n_immune, "fatigue_top_n_immune"))
+    p.enable_stop_candidate = int(bool(pick(enable_stop_candidate, "enable_stop_candidate")))
+    p.max_rounds = int(max_rounds)
+    p.supermajority_threshold = float(supermajority_threshold)
+    p.runoff_threshold_rounds = int(runoff_threshold_rounds)
+    p.runoff_candidate_count = int(runoff_candidate_count)
+    return p
+
+
+@dataclass
+class RunResult:
+    """Per-trial arrays are laid out [set][sim] (flattened); histograms are [set, ...]."""
+    winner: np.ndarray                  # int32 [n]   candidate index, -1 = no winner
+    rounds: np.ndarray                  # int32 [n]
+    reason: Optional[np.ndarray]        # uint8 [n]
+    final_votes: Optional[np.ndarray]   # int32 [n, E]
+    round_tallies: Optional[np.ndarray] # int32 [n, R, E], -1 beyond `rounds`
+    winner_hist: np.ndarray             # int64 [sets, E+1]  (slot E = no winner)
+    rounds_hist: np.ndarray             # int64 [sets, R+1]  (winning trials only)
+    totals: np.ndarray                  # int64 [sets, 2]    (sum of rounds played, trials)
+    n_electors: int
+    kernel_ms: float = -1.0
+
+    @property
+    def elector_rounds(self) -> int:
+        return int(self.totals[:, 0].sum()) * self.n_electors
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """One CUDA device.  Not a CPU fallback: construction fails without a usable sm_100 GPU."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _cabi.load_library()
+        self._ctx = C.c_void_p()
+        check(self._lib.csim_create(C.byref(self._ctx), int(device)))
+        self.device = int(device)
+        self.n_electors = 0
+        self._roster_key = None
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self._lib.csim_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ roster
+    def upload_roster(self, ideology_score, region_code, is_papabile) -> None:
+        """TransitionModel.__init__ captures exactly these three columns (src/model.py:199-213)."""
+        x = np.ascontiguousarray(ideology_score, dtype=np.float64)
+        g = np.ascontiguousarray(region_code, dtype=np.int32)
+        p = np.ascontiguousarray(np.asarray(is_papabile).astype(bool), dtype=np.uint8)
+        if not (x.ndim == g.ndim == p.ndim == 1 and len(x) == len(g) == len(p)):
+            raise ValueError("roster columns must be 1-D and of equal length")
+        key = (x.tobytes(), g.tobytes(), p.tobytes())
+        if key == self._roster_key:
+            return
+        check(self._lib.csim_upload_roster(self._ctx, len(x), _ptr(x), _ptr(g), _ptr(p)))
+        self.n_electors = len(x)
+        self._roster_key = key
+
+    def device_info(self) -> dict:
+        sm, ma, mi, khz = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        check(self._lib.csim_device_info(self._ctx, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(khz)))
+        return dict(sm_count=sm.value, cc=(ma.value, mi.value), clock_khz=khz.value)
+
+    # ------------------------------------------------------------------ model
+    def beta_schedule(self, params: CsimParams, first_round: int, n_rounds: int) -> np.ndarray:
+        out = np.zeros(n_rounds, np.float64)
+        check(self._lib.csim_beta_schedule(C.byref(params), first_round, n_rounds, _ptr(out)))
+        return out
+
+    def need_votes(self, threshold: float, n_electors: Optional[int] = None) -> int:
+        return int(self._lib.csim_need_votes(float(threshold), int(self.n_electors if n_electors is None else n_electors)))
+
+    def prob_matrix(self, params: CsimParams, beta: float, prev_vote=None, prev_count=None, fatigued=None,
+                    shares=None, precision: int = FP64) -> np.ndarray:
+        E = self.n_electors
+        pv = None if prev_vote is None else np.ascontiguousarray(prev_vote, np.int32)
+        pc = None if prev_count is None else np.ascontiguousarray(prev_count, np.int32)
+        ft = None if fatigued is None else np.ascontiguousarray(np.asarray(fatigued).astype(bool), np.uint8)
+        sh = None if shares is None else np.ascontiguousarray(shares, np.float64)
+        for a in (pv, pc, ft, sh):
+            if a is not None and a.shape != (E,):
+                raise ValueError(f"per-candidate / per-elector inputs must have shape ({E},)")
+        P = np.empty((E, E), np.float64 if precision == FP64 else np.float32)
+        check(self._lib.csim_prob_matrix(self._ctx, C.byref(params), float(beta), _ptr(pv), _ptr(pc), _ptr(ft), _ptr(sh),
+                                         int(precision), _ptr(P)))
+        return P
+
+    # ------------------------------------------------------------------ trials
+    def run(self, param_sets: Sequence[CsimParams], n_sims: int, *, sim_id_begin: int = 0, seed: int = 0,
+            wiring: int = WIRING_REF_CLI, engine: int = ENGINE_AUTO, precision: int = FP32,
+            tapes: Optional[np.ndarray] = None, want_reason: bool = True, want_final_votes: bool = False,
+            want_round_tallies: bool = False) -> RunResult:
+        """Host-buffer call: copies in, runs, copies out, synchronises."""
+        E = self.n_electors
+        sets = (CsimParams * len(param_sets))(*param_sets)
+        R = int(sets[0].max_rounds)
+        n = len(param_sets) * int(n_sims)
+        winner = np.full(n, -1, np.int32)
+        rounds = np.zeros(n, np.int32)
+        reason = np.zeros(n, np.uint8) if want_reason else None
+        final = np.zeros((n, E), np.int32) if want_final_votes else None
+        tall = np.zeros((n, R, E), np.int32) if want_round_tallies else None
+        wh = np.zeros((len(param_sets), E + 1), np.int64)
+        rh = np.zeros((len(param_sets), R + 1), np.int64)
+        tot = np.zeros((len(param_sets), 2), np.int64)
+        tp = None
+        if tapes is not None:
+            tp = np.ascontiguousarray(tapes, np.float64)
+            if tp.shape != (n, R * E):
+                raise ValueError(f"uniform tape must have shape ({n}, {R * E}), got {tp.shape}")
+        a = CsimRunArgs()
+        a.params = sets; a.n_param_sets = len(param_sets); a.wiring = wiring; a.engine = engine; a.precision = precision
+        a.sim_id_begin = int(sim_id_begin); a.n_sims = int(n_sims); a.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        a.uniform_tape = _ptr(tp)
+        a.winner = _ptr(winner); a.rounds = _ptr(rounds); a.reason = _ptr(reason)
+        a.final_votes = _ptr(final); a.round_tallies = _ptr(tall)
+        a.winner_hist = _ptr(wh); a.rounds_hist = _ptr(rh); a.totals = _ptr(tot)
+        a.buffers_on_device = 0; a.stream = None
+        check(self._lib.csim_run(self._ctx, C.byref(a)))
+        return RunResult(winner, rounds, reason, final, tall, wh, rh, tot, E, self.stats()[1])
+
+    def run_device(self, param_sets: Sequence[CsimParams], n_sims: int, *, winner, rounds, winner_hist=None,
+                   rounds_hist=None, totals=None, reason=None, final_votes=None, round_tallies=None,
+                   uniform_tape=None, sim_id_begin: int = 0, seed: int = 0, wiring: int = WIRING_REF_CLI,
+                   engine: int = ENGINE_AUTO, precision: int = FP32, stream: int = 0) -> None:
+        """Device-buffer call: every array argument is a torch CUDA tensor (or anything with
+        data_ptr()) on this engine's device; work is only ENQUEUED on `stream` (a raw cudaStream_t
+        handle, e.g. torch.cuda.current_stream().cuda_stream).  Histograms are accumulated into."""
+        sets = (CsimParams * len(param_sets))(*param_sets)
+        dp = lambda t: None if t is None else C.c_void_p(int(t.data_ptr()))
+        a = CsimRunArgs()
+        a.params = sets; a.n_param_sets = len(param_sets); a.wiring = wiring; a.engine = engine; a.precision = precision
+        a.sim_id_begin = int(sim_id_begin); a.n_sims = int(n_sims); a.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        a.uniform_tape = dp(uniform_tape)
+        a.winner = dp(winner); a.rounds = dp(rounds); a.reason = dp(reason)
+        a.final_votes = dp(final_votes); a.round_tallies = dp(round_tallies)
+        a.winner_hist = dp(winner_hist); a.rounds_hist = dp(rounds_hist); a.totals = dp(totals)
+        a.buffers_on_device = 1; a.stream = C.c_void_p(int(stream)) if stream else None
+        check(self._lib.csim_run(self._ctx, C.byref(a)))
+
+    # ------------------------------------------------------------------ diagnostics
+    def stats(self):
+        n, ms = C.c_int64(), C.c_float()
+        check(self._lib.csim_stats(self._ctx, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
+
+    def microbench(self, kind: int) -> float:
+        g = C.c_double()
+        check(self._lib.csim_microbench(self._ctx, int(kind), C.byref(g)))
+        return g.value
+
+
+_engines: Dict[int, Engine] = {}
+
+
+def get_engine(device: int = 0) -> Engine:
+    """Process-wide engine per device (the worker mirror is called once per trial)."""
+    if device not in _engines:
+        _engines[device] = Engine(device)
+    return _engines[device]

@@ -1,0 +1,331 @@
+"""Drop-in for `python -m src.simulate` (mirror of src/simulate.py) with the trials on the GPU.
+
+Unchanged surface: the CLI flags (names, short forms, types, defaults — src/simulate.py:220-259),
+`model_params_from_args` (:261-295), `_run_single_simulation_worker` (:30-218, same arguments and
+result dict), the results CSV (`sim_id,winner,rounds,reason`, :395-412) and the stats JSON
+(:374-387,423) that viz.py / generate_visualizations.py consume.
+
+What replaces the reference's ProcessPoolExecutor fan-out (:330-351): ONE batched call into the
+CUDA library for all trials (`run_simulations`).  New, opt-in flags only: --wiring, --seed,
+--device, --precision, --engine.
+
+Wiring: `ref_cli` (default) reproduces what the reference's CLI computes — the
+previous round's votes never reach the model, so bandwagon / stickiness / fatigue /
+stop-candidate are inert; `model` connects them as the model's own signature documents.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import logging
+import os
+import time
+from collections import Counter
+from pathlib import Path
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import pandas as pd
+
+from . import _cabi
+from .engine import Engine, get_engine, make_params, RunResult
+from .ingest import ElectorDataIngester, roster_arrays
+
+logging.basicConfig(level=logging.INFO, format="%(asctime)s - %(name)s - %(levelname)s - %(message)s")
+log = logging.getLogger(__name__)
+worker_log = logging.getLogger(f"{__name__}.worker")
+
+DEFAULT_NUM_SIMULATIONS = 100
+DEFAULT_MAX_ROUNDS = 100
+DEFAULT_SUPERMAJORITY_THRESHOLD = 2 / 3
+DEFAULT_RUNOFF_THRESHOLD_ROUNDS = 5
+DEFAULT_RUNOFF_CANDIDATE_COUNT = 2
+
+# Process-wide defaults of the opt-in knobs (the reference draws from an unseeded global RNG, so
+# every process sees a different stream; we draw a fresh Philox key per process unless told).
+RUNTIME: Dict[str, Any] = dict(wiring="ref_cli", seed=None, device=0, precision="fp32", engine="auto")
+_WIRING = {"ref_cli": _cabi.WIRING_REF_CLI, "model": _cabi.WIRING_MODEL}
+_PRECISION = {"fp32": _cabi.FP32, "fp64": _cabi.FP64}
+_ENGINE = {"auto": _cabi.ENGINE_AUTO, "dense": _cabi.ENGINE_DENSE, "table": _cabi.ENGINE_TABLE}
+
+
+def _seed() -> int:
+    if RUNTIME["seed"] is None:
+        RUNTIME["seed"] = int.from_bytes(os.urandom(8), "little")
+    return int(RUNTIME["seed"])
+
+
+def reason_text(code: int, supermajority_threshold: float) -> str:
+    """The three strings of src/simulate.py:61,130,178."""
+    if code == _cabi.REASON_WINNER:
+        return f"Winner found by supermajority ({supermajority_threshold*100:.0f}% threshold)"
+    if code == _cabi.REASON_NO_PROBS:
+        return "No probabilities generated"
+    return "Max rounds reached"
+
+
+def run_simulations(elector_data_full: pd.DataFrame, model_params: Dict[str, Any], num_simulations: int, *,
+                    max_rounds: int, supermajority_threshold: float, runoff_threshold_rounds: int,
+                    runoff_candidate_count: int, enable_candidate_fatigue: bool = False,
+                    fatigue_threshold_rounds: int = 3, fatigue_vote_share_threshold: float = 0.05,
+                    fatigue_top_n_immune: int = 3, enable_stop_candidate: bool = False,
+                    sim_id_begin: int = 0, seed: Optional[int] = None, wiring: Optional[str] = None,
+                    device: Optional[int] = None, precision: Optional[str] = None, engine: Optional[str] = None,
+                    want_final_votes: bool = False, want_round_tallies: bool = False,
+                    uniform_tapes: Optional[np.ndarray] = None) -> RunResult:
+    """All trials of one parameter set in one GPU batch (replaces src/simulate.py:330-351)."""
+    wiring = wiring or RUNTIME["wiring"]
+    precision = precision or RUNTIME["precision"]
+    engine = engine or RUNTIME["engine"]
+    eng = get_engine(RUNTIME["device"] if device is None else device)
+    x, g, pap = roster_arrays(elector_data_full)
+    eng.upload_roster(x, g, pap)
+    params = make_params(model_params, max_rounds=max_rounds, supermajority_threshold=supermajority_threshold,
+                         runoff_threshold_rounds=runoff_threshold_rounds, runoff_candidate_count=runoff_candidate_count,
+                         enable_candidate_fatigue=enable_candidate_fatigue,
+                         fatigue_threshold_rounds=fatigue_threshold_rounds,
+                         fatigue_vote_share_threshold=fatigue_vote_share_threshold,
+                         fatigue_top_n_immune=fatigue_top_n_immune, enable_stop_candidate=enable_stop_candidate)
+    prec = _PRECISION[precision]
+    if uniform_tapes is not None:
+        prec = _cabi.FP64
+    elif prec == _cabi.FP32 and _WIRING[wiring] == _cabi.WIRING_MODEL and (enable_candidate_fatigue or enable_stop_candidate):
+        prec = _cabi.FP64      # those two terms exist in the fp64 kernel only
+    return eng.run([params], num_simulations, sim_id_begin=sim_id_begin, seed=_seed() if seed is None else seed,
+                   wiring=_WIRING[wiring], engine=_ENGINE[engine], precision=prec, tapes=uniform_tapes,
+                   want_final_votes=want_final_votes, want_round_tallies=want_round_tallies)
+
+
+def _run_single_simulation_worker(sim_id: int, elector_data_full: pd.DataFrame, model_params: Dict[str, Any],
+                                  max_rounds: int, supermajority_threshold: float,
+                                  runoff_threshold_rounds: int, runoff_candidate_count: int,
+                                  verbose: bool,
+                                  enable_candidate_fatigue: bool,
+                                  fatigue_threshold_rounds: int,
+                                  fatigue_vote_share_threshold: float,
+                                  fatigue_top_n_immune: int,
+                                  enable_stop_candidate: bool) -> Dict[str, Any]:
+    """One trial; same arguments and result dict as src/simulate.py:30-218.  The trial's random
+    stream is the Philox stream of (process seed, sim_id)."""
+    worker_log.setLevel(logging.DEBUG if verbose else logging.INFO)
+    candidate_ids = list(elector_data_full.index) if not elector_data_full.empty else []
+    if len(candidate_ids) == 0 or "ideology_score" not in elector_data_full or "region" not in elector_data_full:
+        # empty model -> probabilities.size == 0 in round 1 (src/simulate.py:128-131)
+        rounds = 1 if max_rounds >= 1 else 0
+        reason = "No probabilities generated" if max_rounds >= 1 else "Max rounds reached"
+        if max_rounds >= 1:
+            worker_log.warning(f"[Sim {sim_id}] No probabilities returned. Ending simulation.")
+        return {"sim_id": sim_id, "winner": None, "rounds": rounds, "reason": reason, "final_votes": {}, "run_details": []}
+    res = run_simulations(elector_data_full, model_params, 1, max_rounds=max_rounds,
+                          supermajority_threshold=supermajority_threshold,
+                          runoff_threshold_rounds=runoff_threshold_rounds, runoff_candidate_count=runoff_candidate_count,
+                          enable_candidate_fatigue=enable_candidate_fatigue,
+                          fatigue_threshold_rounds=fatigue_threshold_rounds,
+                          fatigue_vote_share_threshold=fatigue_vote_share_threshold,
+                          fatigue_top_n_immune=fatigue_top_n_immune, enable_stop_candidate=enable_stop_candidate,
+                          sim_id_begin=int(sim_id), want_final_votes=True)
+    w = int(res.winner[0])
+    winner = str(candidate_ids[w]) if w >= 0 else None
+    rounds = int(res.rounds[0])
+    reason = reason_text(int(res.reason[0]), supermajority_threshold)
+    if winner is not None:
+        worker_log.info(f"[Sim {sim_id}] {reason} in round {rounds}: {winner}")
+    elif rounds == max_rounds:
+        worker_log.info(f"[Sim {sim_id}] Max rounds ({max_rounds}) reached. No winner decided through threshold.")
+    final_votes = {cid: int(v) for cid, v in zip(candidate_ids, res.final_votes[0])} if max_rounds >= 1 else {}
+    return {"sim_id": sim_id, "winner": winner, "rounds": rounds, "reason": reason,
+            "final_votes": final_votes, "run_details": []}
+
+
+def build_parser() -> argparse.ArgumentParser:
+    parser = argparse.ArgumentParser(description="Run Conclave simulations.")
+    parser.add_argument("-n", "--num-simulations", type=int, default=DEFAULT_NUM_SIMULATIONS, help="Number of simulations to run.")
+    parser.add_argument("-r", "--max-rounds", type=int, default=DEFAULT_MAX_ROUNDS, help="Maximum number of voting rounds per simulation.")
+    parser.add_argument("-t", "--supermajority-threshold", type=float, default=DEFAULT_SUPERMAJORITY_THRESHOLD, help="Supermajority threshold for winning.")
+    parser.add_argument("--runoff-rounds", type=int, default=DEFAULT_RUNOFF_THRESHOLD_ROUNDS, help="Rounds after which to trigger a runoff if no winner.")
+    parser.add_argument("--runoff-candidates", type=int, default=DEFAULT_RUNOFF_CANDIDATE_COUNT, help="Number of top candidates in a runoff.")
+    parser.add_argument("-f", "--elector-data-file", type=str, default="merged_electors.csv", help="Path to the elector data CSV file.")
+    parser.add_argument("-o", "--output-results", type=str, default="data/simulation_results.csv", help="Path to save detailed simulation results.")
+    parser.add_argument("-s", "--output-stats", type=str, default="data/simulation_stats.json", help="Path to save aggregate simulation statistics.")
+    parser.add_argument("-v", "--verbose", action="store_true", help="Enable verbose logging for simulation workers.")
+    parser.add_argument("-w", "--workers", type=int, default=None, help="Number of worker processes (accepted for compatibility; trials run as one GPU batch).")
+
+    model_group = parser.add_argument_group("Transition Model Parameters")
+    model_group.add_argument("--initial-beta-weight", type=float, default=1.0, help="Initial weight for ideological distance sensitivity.")
+    model_group.add_argument("--beta-increment-amount", type=float, default=0.05, help="Increment to beta weight per N scaled rounds (for Dynamic Beta).")
+    model_group.add_argument("--beta-increment-interval-rounds", type=float, default=10.0, help="Number of rounds over which beta increments fully (for Dynamic Beta).")
+    model_group.add_argument("--enable-dynamic-beta", action="store_true", help="Enable dynamic beta adjustment.")
+    model_group.add_argument("--stickiness-factor", type=float, default=0.5, help="Factor for elector stickiness to previous vote.")
+    model_group.add_argument("--bandwagon-strength", type=float, default=0.0, help="Strength of the bandwagon effect.")
+    model_group.add_argument("--regional-bonus", type=float, default=0.1, help="Bonus for candidates from the same region.")
+    model_group.add_argument("--papabile-weight-factor", type=float, default=1.5, help="Multiplicative weight for papabile candidates.")
+
+    fatigue_group = parser.add_argument_group("Candidate Fatigue Parameters")
+    fatigue_group.add_argument("--enable-candidate-fatigue", action="store_true", help="Enable candidate fatigue mechanism.")
+    fatigue_group.add_argument("--fatigue-threshold-rounds", type=int, default=3, help="Number of recent rounds to consider for fatigue.")
+    fatigue_group.add_argument("--fatigue-vote-share-threshold", type=float, default=0.05, help="Vote share below which a candidate is considered for fatigue.")
+    fatigue_group.add_argument("--fatigue-penalty-factor", type=float, default=0.5, help="Factor to penalize preference scores of fatigued candidates.")
+    fatigue_group.add_argument("--fatigue-top-n-immune", type=int, default=3, help="Top N candidates (by recent vote share) immune to fatigue.")
+
+    stop_group = parser.add_argument_group("Stop Candidate Parameters")
+    stop_group.add_argument("--enable-stop-candidate", action="store_true", help="Enable stop candidate behavior.")
+    stop_group.add_argument("--stop-candidate-threshold-unacceptable-distance", type=float, default=0.5, help="Ideological distance beyond which a candidate is 'unacceptable'.")
+    stop_group.add_argument("--stop-candidate-threat-min-vote-share", type=float, default=0.15, help="Vote share a candidate needs to be a 'threat'.")
+    stop_group.add_argument("--stop-candidate-boost-factor", type=float, default=1.5, help="Factor to boost preference for a strategic 'blocker' candidate.")
+
+    gpu = parser.add_argument_group("B200 engine options (additions; defaults reproduce the reference CLI)")
+    gpu.add_argument("--wiring", choices=["ref_cli", "model"], default="ref_cli", help="ref_cli: what the reference CLI computes; model: bandwagon/stickiness/fatigue/stop-candidate live.")
+    gpu.add_argument("--seed", type=int, default=None, help="Philox key (default: fresh per process, like the reference's unseeded RNG).")
+    gpu.add_argument("--device", type=int, default=0, help="CUDA device ordinal.")
+    gpu.add_argument("--precision", choices=["fp32", "fp64"], default="fp32", help="fp32 fast path or fp64 exact path.")
+    gpu.add_argument("--engine", choices=["auto", "dense", "table"], default="auto")
+    return parser
+
+
+def parse_args(argv: Optional[List[str]] = None):
+    return build_parser().parse_args(argv)
+
+
+def model_params_from_args(args: argparse.Namespace) -> Dict[str, Any]:
+    """The 12 TransitionModel kwargs the reference CLI forwards (src/simulate.py:263-277)."""
+    params = {
+        "initial_beta_weight": args.initial_beta_weight,
+        "enable_dynamic_beta": args.enable_dynamic_beta,
+        "beta_increment_amount": args.beta_increment_amount,
+        "beta_increment_interval_rounds": int(args.beta_increment_interval_rounds),
+        "stickiness_factor": args.stickiness_factor,
+        "bandwagon_strength": args.bandwagon_strength,
+        "regional_affinity_bonus": args.regional_bonus,
+        "papabile_weight_factor": args.papabile_weight_factor,
+        "fatigue_penalty_factor": args.fatigue_penalty_factor,
+        "stop_candidate_threshold_unacceptable_distance": args.stop_candidate_threshold_unacceptable_distance,
+        "stop_candidate_boost_factor": args.stop_candidate_boost_factor,
+        "stop_candidate_threat_min_vote_share": args.stop_candidate_threat_min_vote_share,
+    }
+    if args.enable_dynamic_beta:
+        if args.beta_increment_amount is not None and args.beta_increment_amount != 0:
+            log.info(f"Dynamic Beta Enabled (stepped): Increment Amount={args.beta_increment_amount}, Interval Rounds={int(args.beta_increment_interval_rounds)}.")
+        else:
+            log.info(f"Dynamic Beta Enabled (likely multiplicative growth): beta_increment_amount is {args.beta_increment_amount}. TransitionModel's default beta_growth_rate will apply if > 1.0.")
+    else:
+        log.info("Dynamic Beta Disabled.")
+    if args.enable_candidate_fatigue:
+        log.info(f"Candidate Fatigue Enabled: Threshold Rounds={args.fatigue_threshold_rounds}, Vote Share Threshold={args.fatigue_vote_share_threshold*100:.0f}%, Penalty={args.fatigue_penalty_factor}, Top N Immune={args.fatigue_top_n_immune}")
+    if args.enable_stop_candidate:
+        log.info(f"Stop Candidate Enabled: Unacceptable Distance={args.stop_candidate_threshold_unacceptable_distance}, "
+                 f"Threat Share={args.stop_candidate_threat_min_vote_share*100:.0f}%, "
+                 f"Boost Factor={args.stop_candidate_boost_factor}")
+    return params
+
+
+def aggregate_results(results: List[Dict[str, Any]], num_simulations: int) -> Dict[str, Any]:
+    """src/simulate.py:356-387 — same keys, same expressions (so the JSON text is identical)."""
+    successful = sum(1 for r in results if r["winner"] is not None)
+    rounds_ok = [r["rounds"] for r in results if r["winner"] is not None]
+    winner_counts = Counter(r["winner"] for r in results if r["winner"] is not None)
+    top = winner_counts.most_common(1)
+    return {
+        "total_simulations": num_simulations,
+        "successful_simulations": successful,
+        "success_rate": successful / num_simulations if num_simulations > 0 else 0,
+        "average_rounds_successful": np.mean(rounds_ok) if rounds_ok else None,
+        "min_rounds_successful": np.min(rounds_ok) if rounds_ok else None,
+        "max_rounds_successful": np.max(rounds_ok) if rounds_ok else None,
+        "median_rounds_successful": np.median(rounds_ok) if rounds_ok else None,
+        "winner_counts": dict(winner_counts),
+        "most_frequent_winner": top[0][0] if top else None,
+        "most_frequent_winner_count": top[0][1] if top else 0,
+        "most_frequent_winner_percentage": (top[0][1] / num_simulations if num_simulations > 0 else 0) if top else 0,
+        "average_rounds_all": np.mean([r["rounds"] for r in results]) if results else 0,
+    }
+
+
+def results_from_batch(res: RunResult, candidate_ids: List[Any], supermajority_threshold: float,
+                       sim_id_begin: int = 0) -> List[Dict[str, Any]]:
+    out = []
+    for i in range(len(res.winner)):
+        w = int(res.winner[i])
+        out.append({"sim_id": sim_id_begin + i, "winner": str(candidate_ids[w]) if w >= 0 else None,
+                    "rounds": int(res.rounds[i]),
+                    "reason": reason_text(int(res.reason[i]) if res.reason is not None else
+                                          (_cabi.REASON_WINNER if w >= 0 else _cabi.REASON_MAX_ROUNDS), supermajority_threshold)})
+    return out
+
+
+def _json_default(x):
+    if isinstance(x, np.integer):
+        return int(x)
+    if x is None or (isinstance(x, float) and np.isnan(x)):
+        return None
+    return x
+
+
+def write_outputs(results: List[Dict[str, Any]], aggregate_stats: Dict[str, Any], output_results: str, output_stats: str):
+    """src/simulate.py:395-426."""
+    rows = [{"sim_id": r["sim_id"], "winner": r["winner"], "rounds": r["rounds"], "reason": r["reason"]} for r in results]
+    results_df = pd.DataFrame(rows)
+    try:
+        results_df.to_csv(output_results, index=False)
+        log.info(f"Saving simulation results ({len(results_df)} rows) to: {output_results}")
+    except Exception as exc:
+        log.error(f"Failed to save results CSV: {exc}")
+    stats_path = Path(output_stats)
+    stats_path.parent.mkdir(parents=True, exist_ok=True)
+    try:
+        with open(stats_path, "w") as f:
+            json.dump(aggregate_stats, f, indent=4, default=_json_default)
+        log.info(f"Saving aggregate stats to: {stats_path}")
+    except Exception as exc:
+        log.error(f"Failed to save stats JSON: {exc}")
+
+
+def main(argv: Optional[List[str]] = None):
+    args = parse_args(argv)
+    log.setLevel(logging.DEBUG if args.verbose else logging.INFO)
+    RUNTIME.update(wiring=args.wiring, seed=args.seed, device=args.device, precision=args.precision, engine=args.engine)
+
+    log.info(f"Starting Conclave simulation with {args.num_simulations} simulations.")
+    log.info(f"Parameters: Max Rounds={args.max_rounds}, Supermajority={args.supermajority_threshold*100:.0f}%"
+             f", Runoff Rounds={args.runoff_rounds}, Runoff Candidates={args.runoff_candidates}")
+    log.info(f"Model Params: Initial Beta={args.initial_beta_weight}, Stickiness={args.stickiness_factor}, Bandwagon={args.bandwagon_strength}, "
+             f"Regional Bonus={args.regional_bonus}, Papabile Factor={args.papabile_weight_factor}")
+    if args.beta_increment_amount > 0:
+        log.info(f"Dynamic Beta Enabled: Increment={args.beta_increment_amount} per {args.beta_increment_interval_rounds} rounds.")
+
+    elector_data_full = ElectorDataIngester(args.elector_data_file).load_and_prepare_data()
+    if elector_data_full.empty:
+        log.error("Failed to load or prepare elector data. Exiting.")
+        return
+    model_params = model_params_from_args(args)
+
+    start = time.time()
+    results: List[Dict[str, Any]] = []
+    try:
+        batch = run_simulations(
+            elector_data_full, model_params, args.num_simulations, max_rounds=args.max_rounds,
+            supermajority_threshold=args.supermajority_threshold, runoff_threshold_rounds=args.runoff_rounds,
+            runoff_candidate_count=args.runoff_candidates, enable_candidate_fatigue=args.enable_candidate_fatigue,
+            fatigue_threshold_rounds=args.fatigue_threshold_rounds,
+            fatigue_vote_share_threshold=args.fatigue_vote_share_threshold,
+            fatigue_top_n_immune=args.fatigue_top_n_immune, enable_stop_candidate=args.enable_stop_candidate)
+        results = results_from_batch(batch, list(elector_data_full.index), args.supermajority_threshold)
+    except Exception as exc:   # the reference logs worker errors and carries on with what it has (:350-351)
+        log.error(f"Error in simulation worker: {exc}", exc_info=True)
+    log.info(f"Simulation time: {time.time() - start:.2f} seconds")
+
+    aggregate_stats = aggregate_results(results, args.num_simulations)
+    log.info(f"Calculated aggregate stats: {aggregate_stats}")
+    write_outputs(results, aggregate_stats, args.output_results, args.output_stats)
+
+    sr = aggregate_stats["success_rate"]
+    avg = aggregate_stats["average_rounds_successful"]
+    log.info("\n--- Simulation Finished ---")
+    log.info(f"Success Rate: {sr*100:.2f}%")
+    log.info(f"Average Rounds (Successful): {avg if avg is not None else 'N/A'}")
+    log.info(f"Most Frequent Winner: Elector {aggregate_stats['most_frequent_winner']} "
+             f"({aggregate_stats['most_frequent_winner_count']} times, {aggregate_stats['most_frequent_winner_percentage']*100:.2f}%)")
+    return aggregate_stats
+
+
+if __name__ == "__main__":
+    main()

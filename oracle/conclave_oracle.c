@@ -164,13 +164,15 @@ static inline double u53(uint32_t a, uint32_t b) {
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
 }
 
+/* stream layout: see include/conclave_b200.h (csim_run_args.seed) and csrc/common.cuh */
 void co_philox_uniforms(uint64_t seed, uint64_t sim, int round_num, int E, double* u) {
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-    for (int j = 0; j < (E + 1) / 2; ++j) {
-        uint32_t ctr[4] = {(uint32_t)sim, (uint32_t)(sim >> 32), (uint32_t)round_num, (uint32_t)j}, w[4];
-        co_philox4x32_10(ctr, key, w);
-        u[2 * j] = u53(w[0], w[1]);
-        if (2 * j + 1 < E) u[2 * j + 1] = u53(w[2], w[3]);
+    for (int q = 0; q < (E + 3) / 4; ++q) {
+        uint32_t ca[4] = {(uint32_t)sim, (uint32_t)(sim >> 32), (uint32_t)round_num, (uint32_t)q}, wa[4];
+        uint32_t cb[4] = {(uint32_t)sim, (uint32_t)(sim >> 32), (uint32_t)round_num, (uint32_t)q | 0x80000000u}, wb[4];
+        co_philox4x32_10(ca, key, wa);
+        co_philox4x32_10(cb, key, wb);
+        for (int i = 0; i < 4 && 4 * q + i < E; ++i) u[4 * q + i] = u53(wa[i], wb[i]);
     }
 }
 

@@ -303,10 +303,12 @@ def fatigue_set(shares_hist: List[np.ndarray], r: int, ep: EngineParams, C: int)
 
 # --------------------------------------------------------------------------
 # Philox4x32-10 (Salmon et al., SC'11), the native RNG shared with the CUDA path
-# key = (seed_lo, seed_hi); counter = (sim_lo, sim_hi, round, elector >> 1);
-# elector & 1 selects output words (0,1) or (2,3);
-# u = ((w_a >> 5) * 2^26 + (w_b >> 6)) / 2^53   (same construction as MT19937's
-# random_sample, so tape and native modes share one sampling path).
+# key = (seed_lo, seed_hi);
+#   call A: counter = (sim_lo, sim_hi, round, e >> 2)                -> word (e & 3) = w_a(e)
+#   call B: counter = (sim_lo, sim_hi, round, (e >> 2) | 0x80000000) -> word (e & 3) = w_b(e)
+#   u = ((w_a >> 5) * 2^26 + (w_b >> 6)) / 2^53   (same construction as MT19937's
+#   random_sample, so tape and native modes share one sampling path); the fp32 fast
+#   path of the CUDA engine uses (w_a >> 8) * 2^-24, the leading 24 bits of u.
 # --------------------------------------------------------------------------
 _PH_M0 = np.uint64(0xD2511F53)
 _PH_M1 = np.uint64(0xCD9E8D57)
@@ -334,17 +336,29 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
+def philox_words(seed: int, sim_id: int, round_num: int, E: int, second: bool = False) -> np.ndarray:
+    nq = (E + 3) // 4
+    q = np.arange(nq, dtype=np.uint64)
+    if second:
+        q = q | np.uint64(0x80000000)
+    w = philox4x32_10(np.full(nq, sim_id & 0xFFFFFFFF, np.uint64),
+                      np.full(nq, (sim_id >> 32) & 0xFFFFFFFF, np.uint64),
+                      np.full(nq, round_num, np.uint64), q,
+                      seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    return np.stack(w, axis=1).reshape(-1)[:E]
+
+
 def philox_uniforms(seed: int, sim_id: int, round_num: int, E: int) -> np.ndarray:
     """The E fp64 uniforms of (sim, round) in elector order."""
-    npair = (E + 1) // 2
-    j = np.arange(npair, dtype=np.uint64)
-    w = philox4x32_10(np.full(npair, sim_id & 0xFFFFFFFF, np.uint64),
-                      np.full(npair, (sim_id >> 32) & 0xFFFFFFFF, np.uint64),
-                      np.full(npair, round_num, np.uint64), j,
-                      seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    a = np.stack([w[0], w[2]], axis=1).reshape(-1)[:E]
-    b = np.stack([w[1], w[3]], axis=1).reshape(-1)[:E]
+    a = philox_words(seed, sim_id, round_num, E, False)
+    b = philox_words(seed, sim_id, round_num, E, True)
     return ((a >> np.uint64(5)).astype(np.float64) * 67108864.0 + (b >> np.uint64(6)).astype(np.float64)) / 9007199254740992.0
+
+
+def philox_uniforms_f32(seed: int, sim_id: int, round_num: int, E: int) -> np.ndarray:
+    """The 24-bit uniforms the fp32 fast path consumes (leading bits of the fp64 ones)."""
+    a = philox_words(seed, sim_id, round_num, E, False)
+    return ((a >> np.uint64(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)).astype(np.float32)
 
 
 def philox_tape(seed: int, sim_id: int, max_rounds: int, E: int) -> np.ndarray:

@@ -1,0 +1,316 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI.
+
+  * fp64 engine + the reference's own MT19937 uniform tapes  -> winners, rounds, per-round tallies
+    bit-exact against the golden vectors the unmodified reference produced
+  * fp64 engine + native Philox stream -> bit-exact against the C oracle at larger N
+  * probability matrix: fp64 within a few ulp, fp32 within 1e-5 relative (north_star tolerance)
+  * fp32 engine: per-trial agreement with the oracle under the shared stream, and chi-square / KS
+    against an independently seeded sample of the reference itself (tests/golden/dist_cfg2.json)
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import conclave_oracle as O
+from oracle import c_oracle as CO
+import golden_util as G
+
+pytestmark = pytest.mark.gpu
+
+MODEL_KEYS = ("initial_beta_weight", "enable_dynamic_beta", "beta_growth_rate", "beta_increment_amount",
+              "beta_increment_interval_rounds", "stickiness_factor", "bandwagon_strength", "regional_affinity_bonus",
+              "papabile_weight_factor", "enable_candidate_fatigue", "fatigue_threshold_rounds",
+              "fatigue_vote_share_threshold", "fatigue_penalty_factor", "fatigue_top_n_immune", "enable_stop_candidate",
+              "stop_candidate_threshold_unacceptable_distance", "stop_candidate_threat_min_vote_share",
+              "stop_candidate_boost_factor")
+
+
+def to_params(mp, ep=None):
+    from conclave_sim_b200 import make_params
+    kw = {k: getattr(mp, k) for k in MODEL_KEYS}
+    if ep is None:
+        return make_params(kw)
+    return make_params(kw, max_rounds=ep.max_rounds, supermajority_threshold=ep.supermajority_threshold,
+                       runoff_threshold_rounds=ep.runoff_threshold_rounds, runoff_candidate_count=ep.runoff_candidate_count,
+                       enable_candidate_fatigue=ep.enable_candidate_fatigue if mp.enable_candidate_fatigue or ep.enable_candidate_fatigue else False,
+                       fatigue_threshold_rounds=ep.fatigue_threshold_rounds,
+                       fatigue_vote_share_threshold=ep.fatigue_vote_share_threshold,
+                       fatigue_top_n_immune=ep.fatigue_top_n_immune,
+                       enable_stop_candidate=ep.enable_stop_candidate or mp.enable_stop_candidate)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from conclave_sim_b200 import Engine
+    CO.build()
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def upload(eng, roster):
+    eng.upload_roster(roster.ideology, roster.region, roster.papabile)
+
+
+CFG2 = dict(initial_beta_weight=1.5, enable_dynamic_beta=True, beta_increment_amount=0.3,
+            beta_increment_interval_rounds=1, stickiness_factor=0.8, bandwagon_strength=0.7,
+            regional_affinity_bonus=0.1, papabile_weight_factor=2.0)
+EP2 = O.EngineParams(max_rounds=20, supermajority_threshold=0.56)
+
+
+# ------------------------------------------------------------------ probability matrix
+@pytest.mark.parametrize("case", list(G.model_cases()), ids=lambda c: c["name"])
+def test_prob_matrix_fp64_matches_reference(eng, case):
+    from conclave_sim_b200 import FP64, FP32
+    mp, roster = case["mp"], case["roster"]
+    upload(eng, roster)
+    p = to_params(mp)
+    for r in range(1, case["P"].shape[0] + 1):
+        assert eng.beta_schedule(p, r, 1)[0] == case["beta"][r - 1]
+        pv = None if r == 1 else case["prev_vote"][r - 1]
+        pc = None if pv is None else np.bincount(pv[pv >= 0], minlength=roster.E).astype(np.int32)
+        P = eng.prob_matrix(p, case["beta"][r - 1], pv, pc, case["fatigued"][r - 1], case["shares"][r - 1], precision=FP64)
+        assert np.allclose(P, case["P"][r - 1], rtol=1e-13, atol=0)
+        P32 = eng.prob_matrix(p, case["beta"][r - 1], pv, pc, case["fatigued"][r - 1], case["shares"][r - 1], precision=FP32)
+        ref = case["P"][r - 1]
+        if case["name"] != "c05":        # c05 = exp-underflow row; fp32 flushes earlier than fp64 by construction
+            assert np.allclose(P32, ref, rtol=1e-5, atol=1e-12), np.abs(P32 - ref).max()
+
+
+def test_prob_matrix_real_roster(eng):
+    from conclave_sim_b200 import FP64, FP32
+    z = np.load(os.path.join(G.GOLD, "model_real.npz"))
+    roster = G.real_roster()
+    upload(eng, roster)
+    from oracle.gen_golden import CFG1, CFG2 as C2
+    for name, kw in (("cfg1", CFG1), ("cfg2", C2)):
+        p = to_params(O.ModelParams(**kw))
+        for key in z.files:
+            if key.startswith(name + "/P"):
+                r = int(key.split("/P")[1])
+                beta = eng.beta_schedule(p, r, 1)[0]
+                assert beta == float(z[f"{name}/beta{r}"])
+                P = eng.prob_matrix(p, beta, precision=FP64)
+                assert np.allclose(P, z[key], rtol=1e-13, atol=0)
+                assert (np.diag(P) == 0).all() and np.allclose(P.sum(1), 1.0, rtol=1e-12)
+                P32 = eng.prob_matrix(p, beta, precision=FP32)
+                assert np.allclose(P32, z[key], rtol=1e-5, atol=0)
+    p = to_params(O.ModelParams(**C2))
+    pv = z["cfg2_model/prev_vote"]
+    P = eng.prob_matrix(p, float(z["cfg2_model/beta2"]), pv, np.bincount(pv, minlength=134).astype(np.int32), precision=FP64)
+    assert np.allclose(P, z["cfg2_model/P2"], rtol=1e-13, atol=0)
+
+
+# ------------------------------------------------------------------ engine under the reference's own uniforms
+@pytest.mark.parametrize("case", list(G.engine_cases()), ids=lambda c: c["name"])
+def test_engine_bit_exact_under_reference_tapes(eng, case):
+    from conclave_sim_b200 import FP64
+    upload(eng, case["roster"])
+    tapes = G.case_tapes(case)
+    p = to_params(case["mp"], case["ep"])
+    out = eng.run([p], case["n"], wiring=case["wiring"], precision=FP64, tapes=tapes, want_round_tallies=True,
+                  want_final_votes=True)
+    ok = ~case["fatigue_tie"]
+    assert ok.any() or case["name"] == "m_cfg2_fatigue"
+    assert np.array_equal(out.winner[ok], case["winners"][ok])
+    assert np.array_equal(out.rounds[ok], case["rounds"][ok])
+    assert np.array_equal(out.reason[ok], case["reason"][ok].astype(np.uint8))
+    assert np.array_equal(out.round_tallies[ok], case["tallies"][ok])
+    for i in np.where(ok)[0]:
+        assert np.array_equal(out.final_votes[i], case["tallies"][i, case["rounds"][i] - 1])
+    # fatigue-tie trials: the reference's own pick is numpy-sort dependent; ours must equal the oracle's rule
+    ref = CO.run(case["roster"], [(case["mp"], case["ep"])], case["wiring"], case["n"], tapes=tapes, want_tallies=True)
+    assert np.array_equal(out.winner, ref["winner"]) and np.array_equal(out.round_tallies, ref["round_tallies"])
+
+
+# ------------------------------------------------------------------ native stream, larger N
+@pytest.mark.parametrize("wiring,n", [(O.WIRING_REF_CLI, 20000), (O.WIRING_MODEL, 1500)])
+def test_fp64_native_stream_bit_exact_vs_oracle(eng, wiring, n):
+    from conclave_sim_b200 import FP64
+    roster = G.real_roster()
+    upload(eng, roster)
+    mp = O.ModelParams(**CFG2)
+    out = eng.run([to_params(mp, EP2)], n, seed=20250507, sim_id_begin=10**9, wiring=wiring, precision=FP64,
+                  want_final_votes=True)
+    ref = CO.run(roster, [(mp, EP2)], wiring, n, seed=20250507, sim_id_begin=10**9)
+    assert np.array_equal(out.winner, ref["winner"])
+    assert np.array_equal(out.rounds, ref["rounds"])
+    assert np.array_equal(out.final_votes, ref["final_votes"])
+    assert np.array_equal(out.winner_hist, ref["winner_hist"]) and np.array_equal(out.rounds_hist, ref["rounds_hist"])
+    assert np.array_equal(out.totals, ref["totals"])
+
+
+def test_fp64_fatigue_and_stop_vs_oracle(eng):
+    from conclave_sim_b200 import FP64
+    roster = G.real_roster()
+    upload(eng, roster)
+    mp = O.ModelParams(**CFG2, enable_candidate_fatigue=True, enable_stop_candidate=True,
+                       stop_candidate_threshold_unacceptable_distance=0.3)
+    ep = O.EngineParams(max_rounds=14, supermajority_threshold=0.56, runoff_threshold_rounds=7, enable_candidate_fatigue=True,
+                        fatigue_threshold_rounds=2, fatigue_vote_share_threshold=0.03, fatigue_top_n_immune=3, enable_stop_candidate=True)
+    out = eng.run([to_params(mp, ep)], 300, seed=3, wiring=O.WIRING_MODEL, precision=FP64, want_round_tallies=True)
+    ref = CO.run(roster, [(mp, ep)], O.WIRING_MODEL, 300, seed=3, want_tallies=True)
+    assert np.array_equal(out.winner, ref["winner"]) and np.array_equal(out.rounds, ref["rounds"])
+    assert np.array_equal(out.round_tallies, ref["round_tallies"])
+
+
+def test_param_sets_batching_and_sharding_independence(eng):
+    from conclave_sim_b200 import FP64, FP32
+    roster = G.real_roster()
+    upload(eng, roster)
+    from oracle.gen_golden import CFG1
+    sets = [(O.ModelParams(**CFG2), EP2), (O.ModelParams(**CFG1), O.EngineParams(max_rounds=20, supermajority_threshold=2 / 3))]
+    ps = [to_params(*s) for s in sets]
+    for prec in (FP64, FP32):
+        full = eng.run(ps, 400, seed=11, precision=prec)
+        w = full.winner.reshape(2, 400); r = full.rounds.reshape(2, 400)
+        for s in range(2):
+            assert full.winner_hist[s, :134].sum() == (w[s] >= 0).sum() and full.winner_hist[s, 134] == (w[s] < 0).sum()
+            assert np.array_equal(full.rounds_hist[s], np.bincount(r[s][w[s] >= 0], minlength=21))
+            assert full.totals[s, 0] == r[s].sum() and full.totals[s, 1] == 400
+        assert (w[1] < 0).all() and (r[1] == 20).all()      # cfg-1: nobody reaches 2/3
+        # a shard of the sim-id range gives the same trials (what multi-GPU sharding relies on)
+        part = eng.run(ps[:1], 150, seed=11, sim_id_begin=200, precision=prec)
+        assert np.array_equal(part.winner, w[0][200:350]) and np.array_equal(part.rounds, r[0][200:350])
+    if True:
+        ref = CO.run(roster, sets, O.WIRING_REF_CLI, 400, seed=11)
+        full = eng.run(ps, 400, seed=11, precision=FP64)
+        assert np.array_equal(full.winner, ref["winner"]) and np.array_equal(full.rounds, ref["rounds"])
+
+
+# ------------------------------------------------------------------ fp32 fast path
+@pytest.mark.parametrize("wiring,n", [(O.WIRING_REF_CLI, 20000), (O.WIRING_MODEL, 4000)])
+def test_fp32_agrees_with_oracle_per_trial(eng, wiring, n):
+    from conclave_sim_b200 import FP32
+    roster = G.real_roster()
+    upload(eng, roster)
+    mp = O.ModelParams(**CFG2)
+    out = eng.run([to_params(mp, EP2)], n, seed=5, wiring=wiring, precision=FP32, want_final_votes=True)
+    ref = CO.run(roster, [(mp, EP2)], wiring, n, seed=5)
+    same = (out.winner == ref["winner"]) & (out.rounds == ref["rounds"]) & (out.final_votes == ref["final_votes"]).all(axis=1)
+    # 24-bit uniforms + fp32 sums flip ~1e-5 of the draws; a flipped draw may change the trial
+    assert same.mean() > 0.95, same.mean()
+    assert abs(out.rounds.mean() - ref["rounds"].mean()) < 0.05
+
+
+def _chi2_homogeneity(a, b, min_expected=5.0):
+    """Two-sample chi-square on count vectors a, b with small-expectation bins pooled."""
+    from scipy import stats
+    a = np.asarray(a, float); b = np.asarray(b, float)
+    tot = a + b
+    exp_b = tot * b.sum() / tot.sum()
+    exp_a = tot * a.sum() / tot.sum()
+    small = (exp_a < min_expected) | (exp_b < min_expected)
+    if small.any():
+        a = np.concatenate([a[~small], [a[small].sum()]]); b = np.concatenate([b[~small], [b[small].sum()]])
+    keep = (a + b) > 0
+    return stats.chi2_contingency(np.stack([a[keep], b[keep]]))[1]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_distribution_matches_reference_sample(eng, precision):
+    """north_star: 'Under the native RNG, winner and rounds distributions must pass a
+    chi-square/KS test at p>0.01 against the reference's own CPU run.'"""
+    from scipy import stats
+    from conclave_sim_b200 import FP32, FP64
+    with open(os.path.join(G.GOLD, "dist_cfg2.json")) as f:
+        ref = json.load(f)
+    roster = G.real_roster()
+    upload(eng, roster)
+    n = 1_000_000 if precision == "fp32" else 200_000
+    out = eng.run([to_params(O.ModelParams(**CFG2), EP2)], n, seed=987654321, precision=FP32 if precision == "fp32" else FP64,
+                  want_reason=False)
+    gw = np.concatenate([out.winner_hist[0, :134], [out.winner_hist[0, 134]]])
+    rw = np.concatenate([ref["winner_hist"], [ref["no_winner"]]])
+    p_w = _chi2_homogeneity(gw, rw)
+    gr = np.concatenate([out.rounds_hist[0], [out.winner_hist[0, 134]]])
+    rr = np.concatenate([ref["rounds_hist_success"], [ref["no_winner"]]])
+    p_r = _chi2_homogeneity(gr, rr)
+    # KS on rounds-to-convergence of successful trials
+    g_rounds = np.repeat(np.arange(21), out.rounds_hist[0])
+    r_rounds = np.repeat(np.arange(21), ref["rounds_hist_success"])
+    p_ks = stats.ks_2samp(g_rounds, r_rounds).pvalue
+    print(f"[{precision}] chi2 winners p={p_w:.4f}  chi2 rounds p={p_r:.4f}  KS rounds p={p_ks:.4f}  "
+          f"success gpu={1 - gw[-1] / n:.4f} ref={1 - ref['no_winner'] / ref['n']:.4f}")
+    assert p_w > 0.01 and p_r > 0.01 and p_ks > 0.01
+
+
+def test_edge_rosters(eng):
+    from conclave_sim_b200 import FP32, FP64
+    from oracle.gen_golden import CFG1
+    for E in (1, 2, 3, 33, 127, 128, 129, 136, 137, 200):
+        roster = O.synthetic_roster(E, seed=E)
+        upload(eng, roster)
+        mp = O.ModelParams(**CFG2)
+        ep = O.EngineParams(max_rounds=9, supermajority_threshold=0.56, runoff_threshold_rounds=3)
+        out = eng.run([to_params(mp, ep)], 64, seed=1, precision=FP64, want_round_tallies=True)
+        ref = CO.run(roster, [(mp, ep)], O.WIRING_REF_CLI, 64, seed=1, want_tallies=True)
+        assert np.array_equal(out.winner, ref["winner"]) and np.array_equal(out.round_tallies, ref["round_tallies"]), E
+        o32 = eng.run([to_params(mp, ep)], 256, seed=1, precision=FP32, want_round_tallies=True)
+        r32 = CO.run(roster, [(mp, ep)], O.WIRING_REF_CLI, 256, seed=1, want_tallies=True)
+        played = o32.round_tallies[:, 0, :]
+        assert (played.sum(axis=1) == E).all()                 # every elector votes exactly once per round
+        if E > 1:
+            assert np.mean(o32.winner == r32["winner"]) > 0.85, (E, np.mean(o32.winner == r32["winner"]))
+
+
+def test_large_roster_cfg5_shape(eng):
+    """cfg-5 shape (E = C = 1024) at a size the oracle finishes in seconds."""
+    from conclave_sim_b200 import FP32, FP64
+    roster = O.synthetic_roster(1024)
+    upload(eng, roster)
+    mp = O.ModelParams(**CFG2)
+    ep = O.EngineParams(max_rounds=8, supermajority_threshold=0.56)
+    ref = CO.run(roster, [(mp, ep)], O.WIRING_REF_CLI, 48, seed=9, want_tallies=True)
+    out = eng.run([to_params(mp, ep)], 48, seed=9, precision=FP64, want_round_tallies=True)
+    assert np.array_equal(out.winner, ref["winner"]) and np.array_equal(out.round_tallies, ref["round_tallies"])
+    o32 = eng.run([to_params(mp, ep)], 48, seed=9, precision=FP32, want_round_tallies=True)
+    first = o32.round_tallies[:, 0, :]
+    assert (first.sum(axis=1) == 1024).all()
+    # round-1 tallies of the two precisions differ in at most a handful of votes
+    assert np.abs(first - ref["round_tallies"][:, 0, :]).sum(axis=1).mean() < 4.0
+
+
+# ------------------------------------------------------------------ the reference-facing Python API
+def test_worker_and_cli_end_to_end(eng, tmp_path):
+    import pandas as pd
+    from conclave_sim_b200 import simulate as S
+    from conclave_sim_b200.model import TransitionModel
+    roster = G.real_roster()
+    df = pd.DataFrame({"ideology_score": roster.ideology, "region": [f"R{g}" for g in roster.region],
+                       "is_papabile": roster.papabile}, index=pd.Index(roster.ids, name="elector_id"))
+    csv = tmp_path / "roster.csv"
+    df.reset_index().to_csv(csv, index=False)
+    S.RUNTIME.update(seed=123, precision="fp64", wiring="ref_cli")
+    mp = dict(CFG2, fatigue_penalty_factor=0.5, stop_candidate_threshold_unacceptable_distance=0.5,
+              stop_candidate_boost_factor=1.5, stop_candidate_threat_min_vote_share=0.15)
+    r = S._run_single_simulation_worker(7, df, mp, 20, 0.56, 5, 2, False, False, 3, 0.05, 3, False)
+    assert set(r) == {"sim_id", "winner", "rounds", "reason", "final_votes", "run_details"}
+    ref = CO.run(roster, [(O.ModelParams(**CFG2), EP2)], O.WIRING_REF_CLI, 1, seed=123, sim_id_begin=7)
+    assert r["rounds"] == ref["rounds"][0] and sum(r["final_votes"].values()) == 134
+    assert r["winner"] == (None if ref["winner"][0] < 0 else roster.ids[ref["winner"][0]])
+    out_csv, out_json = tmp_path / "res.csv", tmp_path / "stats.json"
+    stats = S.main(["-n", "500", "-r", "20", "-t", "0.56", "-f", str(csv), "-o", str(out_csv), "-s", str(out_json),
+                    "--enable-dynamic-beta", "--beta-increment-amount", "0.3", "--beta-increment-interval-rounds", "1",
+                    "--initial-beta-weight", "1.5", "--bandwagon-strength", "0.7", "--papabile-weight-factor", "2.0",
+                    "--stickiness-factor", "0.8", "--seed", "42"])
+    got = pd.read_csv(out_csv)
+    assert list(got.columns) == ["sim_id", "winner", "rounds", "reason"] and len(got) == 500
+    js = json.load(open(out_json))
+    assert js["total_simulations"] == 500 and 0.8 < js["success_rate"] < 0.97
+    assert abs(js["average_rounds_successful"] - 10.4) < 0.8
+    assert js["successful_simulations"] == int(got["winner"].notna().sum())
+    # the model mirror
+    m = TransitionModel(df, **CFG2)
+    P, details = m.calculate_transition_probabilities(None, 1)
+    assert details == [] and P.shape == (134, 134) and m.effective_beta_weight == 1.8
+    z = np.load(os.path.join(G.GOLD, "model_real.npz"))
+    assert np.allclose(P, z["cfg2/P1"], rtol=1e-13, atol=0)
+
+
+def test_microbench_runs(eng):
+    for kind in (0, 1, 2):
+        g = eng.microbench(kind)
+        assert g > 100.0     # giga thread-instructions per second

@@ -1,0 +1,193 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol the header
+declares (no compute call is made without a GPU), the ctypes struct mirrors match the header,
+the host-only entry points (beta schedule, vote threshold) agree with the oracle, the CLI /
+aggregation / writers keep the reference's contract, and the product path FAILS LOUDLY
+without a CUDA device."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import conclave_oracle as O
+import golden_util as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "conclave_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from conclave_sim_b200 import _build, _cabi
+    _build.build()
+    return _cabi.load_library()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    src = open(HEADER).read()
+    declared = set(re.findall(r"\b(csim_[a-z_0-9]+)\s*\(", src))
+    from conclave_sim_b200._cabi import EXPORTS
+    assert declared == set(EXPORTS), declared ^ set(EXPORTS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.csim_abi_version() == 1
+
+
+def test_struct_mirrors_match_header(tmp_path):
+    """Compile a tiny C program printing sizeof/offsetof of the header's structs; compare with ctypes."""
+    from conclave_sim_b200._cabi import CsimParams, CsimRunArgs
+    from oracle.c_oracle import CParams
+    fields_p = [f[0] for f in CsimParams._fields_]
+    fields_r = [f[0] for f in CsimRunArgs._fields_]
+    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "conclave_b200.h"\nint main(){\n'
+    prog += 'printf("%zu\\n", sizeof(csim_params));\n'
+    for f in fields_p:
+        prog += f'printf("%zu\\n", offsetof(csim_params, {f}));\n'
+    prog += 'printf("%zu\\n", sizeof(csim_run_args));\n'
+    for f in fields_r:
+        prog += f'printf("%zu\\n", offsetof(csim_run_args, {f}));\n'
+    prog += "return 0;}\n"
+    c = tmp_path / "t.c"
+    c.write_text(prog)
+    exe = tmp_path / "t"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)], check=True)
+    nums = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    exp = [ctypes.sizeof(CsimParams)] + [getattr(CsimParams, f).offset for f in fields_p] + \
+          [ctypes.sizeof(CsimRunArgs)] + [getattr(CsimRunArgs, f).offset for f in fields_r]
+    assert nums == exp
+    assert ctypes.sizeof(CParams) == ctypes.sizeof(CsimParams)
+    assert [f[0] for f in CParams._fields_] == fields_p
+
+
+def test_host_entry_points_match_oracle(lib):
+    from conclave_sim_b200 import make_params
+    for thr, E in [(0.56, 134), (2 / 3, 134), (2 / 3, 135), (0.5, 134), (0.0, 10), (1.0, 7), (0.8, 5), (0.56, 1024)]:
+        assert lib.csim_need_votes(thr, E) == O.need_votes(thr, E)
+    cases = [dict(initial_beta_weight=1.5, enable_dynamic_beta=True, beta_increment_amount=0.3, beta_increment_interval_rounds=1),
+             dict(initial_beta_weight=1.0, enable_dynamic_beta=True, beta_increment_amount=0.5, beta_increment_interval_rounds=3),
+             dict(initial_beta_weight=2.0, enable_dynamic_beta=True, beta_growth_rate=1.2),
+             dict(initial_beta_weight=1.0, enable_dynamic_beta=False, beta_increment_amount=0.05, beta_increment_interval_rounds=10),
+             dict(initial_beta_weight=1.0, enable_dynamic_beta=True, beta_increment_amount=0.1, beta_increment_interval_rounds=0)]
+    for kw in cases:
+        p = make_params(kw, max_rounds=50)
+        out = np.zeros(50)
+        assert lib.csim_beta_schedule(ctypes.byref(p), 1, 50, out.ctypes.data_as(ctypes.c_void_p)) == 0
+        assert np.array_equal(out, O.beta_schedule(O.ModelParams(**kw), 50))
+        out2 = np.zeros(5)
+        lib.csim_beta_schedule(ctypes.byref(p), 7, 5, out2.ctypes.data_as(ctypes.c_void_p))
+        assert np.array_equal(out2, out[6:11])
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from conclave_sim_b200 import Engine, CsimError
+    with pytest.raises(CsimError) as ei:
+        Engine(0)
+    assert "no CPU fallback" in str(ei.value)
+    import pandas as pd
+    from conclave_sim_b200 import simulate as S
+    df = pd.DataFrame({"ideology_score": [0.1, 0.5], "region": ["a", "b"], "is_papabile": [True, False]},
+                      index=pd.Index(["0", "1"], name="elector_id"))
+    with pytest.raises(CsimError):
+        S._run_single_simulation_worker(0, df, {}, 5, 0.5, 5, 2, False, False, 3, 0.05, 3, False)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "conclave_sim_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
+                assert "conclave_oracle" not in txt, f
+
+
+def test_cli_surface_matches_reference():
+    from conclave_sim_b200 import simulate as S
+    a = S.parse_args([])
+    assert (a.num_simulations, a.max_rounds, a.runoff_rounds, a.runoff_candidates) == (100, 100, 5, 2)
+    assert a.supermajority_threshold == 2 / 3 and a.elector_data_file == "merged_electors.csv"
+    assert a.output_results == "data/simulation_results.csv" and a.output_stats == "data/simulation_stats.json"
+    assert (a.initial_beta_weight, a.beta_increment_amount, a.beta_increment_interval_rounds) == (1.0, 0.05, 10.0)
+    assert (a.stickiness_factor, a.bandwagon_strength, a.regional_bonus, a.papabile_weight_factor) == (0.5, 0.0, 0.1, 1.5)
+    assert (a.fatigue_threshold_rounds, a.fatigue_vote_share_threshold, a.fatigue_penalty_factor, a.fatigue_top_n_immune) == (3, 0.05, 0.5, 3)
+    assert (a.stop_candidate_threshold_unacceptable_distance, a.stop_candidate_threat_min_vote_share, a.stop_candidate_boost_factor) == (0.5, 0.15, 1.5)
+    assert not (a.enable_dynamic_beta or a.enable_candidate_fatigue or a.enable_stop_candidate or a.verbose) and a.workers is None
+    a = S.parse_args("-n 7 -r 9 -t 0.56 -f x.csv -o o.csv -s s.json -v -w 3 --regional-bonus 0.2 --beta-increment-interval-rounds 2.0".split())
+    assert (a.num_simulations, a.max_rounds, a.supermajority_threshold, a.workers, a.verbose) == (7, 9, 0.56, 3, True)
+    mp = S.model_params_from_args(a)
+    assert set(mp) == {"initial_beta_weight", "enable_dynamic_beta", "beta_increment_amount", "beta_increment_interval_rounds",
+                       "stickiness_factor", "bandwagon_strength", "regional_affinity_bonus", "papabile_weight_factor",
+                       "fatigue_penalty_factor", "stop_candidate_threshold_unacceptable_distance",
+                       "stop_candidate_boost_factor", "stop_candidate_threat_min_vote_share"}
+    assert mp["regional_affinity_bonus"] == 0.2 and mp["beta_increment_interval_rounds"] == 2 and isinstance(mp["beta_increment_interval_rounds"], int)
+
+
+def test_aggregation_and_writers_match_reference_contract(tmp_path):
+    from conclave_sim_b200 import simulate as S
+    results = [dict(sim_id=i, winner=w, rounds=r, reason=S.reason_text(1 if w else 0, 0.56))
+               for i, (w, r) in enumerate([("39", 7), (None, 20), ("12", 9), ("39", 11), (None, 20), ("7", 6)])]
+    agg = S.aggregate_results(results, 6)
+    ref = O.aggregate([r["winner"] for r in results], [r["rounds"] for r in results], 6)
+    for k in ref:
+        assert (agg[k] == ref[k]) or np.isclose(agg[k], ref[k]), k
+    assert list(agg) == list(ref)      # same key order -> same JSON text
+    S.write_outputs(results, agg, str(tmp_path / "r.csv"), str(tmp_path / "d" / "s.json"))
+    lines = (tmp_path / "r.csv").read_text().splitlines()
+    assert lines[0] == "sim_id,winner,rounds,reason"
+    assert lines[1] == "0,39,7,Winner found by supermajority (56% threshold)"
+    assert lines[2] == "1,,20,Max rounds reached"
+    js = json.loads((tmp_path / "d" / "s.json").read_text())
+    assert js["winner_counts"] == {"39": 2, "12": 1, "7": 1} and js["most_frequent_winner"] == "39"
+    assert js["median_rounds_successful"] == 8.0 and js["min_rounds_successful"] == 6
+    empty = S.aggregate_results([dict(sim_id=0, winner=None, rounds=20, reason="Max rounds reached")], 1)
+    S.write_outputs([], empty, str(tmp_path / "e.csv"), str(tmp_path / "e.json"))
+    assert json.loads((tmp_path / "e.json").read_text())["average_rounds_successful"] is None
+    assert S.reason_text(2, 0.5) == "No probabilities generated" and S.reason_text(1, 2 / 3) == "Winner found by supermajority (67% threshold)"
+
+
+def test_ingest_and_model_mirror_host_behaviour(tmp_path, caplog):
+    import logging
+    import pandas as pd
+    from conclave_sim_b200.ingest import ElectorDataIngester, roster_arrays
+    from conclave_sim_b200.model import TransitionModel
+    p = tmp_path / "e.csv"
+    p.write_text("elector_id,region,is_papabile,ideology_score\n0,Europe,True,0.25\n1,Asia,False,0.5\n2,Europe,False,0.75\n")
+    df = ElectorDataIngester(str(p)).load_and_prepare_data()
+    assert list(df.index) == ["0", "1", "2"] and df.index.name == "elector_id"
+    x, g, pap = roster_arrays(df)
+    assert list(x) == [0.25, 0.5, 0.75] and g[0] == g[2] != g[1] and list(pap) == [True, False, False]
+    assert ElectorDataIngester(str(tmp_path / "missing.csv")).load_and_prepare_data().empty
+    (tmp_path / "g.csv").write_text("gc_id,region,ideology_score\n5,a,0.1\n")
+    assert list(ElectorDataIngester(str(tmp_path / "g.csv")).load_and_prepare_data().index) == ["5"]
+    # model mirror: attributes, stateful beta, empty-data behaviour and log texts (tests/test_model.py:428-468,1006-1079,1165-1216)
+    m = TransitionModel(df, initial_beta_weight=1.0, enable_dynamic_beta=True, beta_growth_rate=1.1)
+    for r, want in ((1, 1.1), (2, 1.1 * 1.1)):
+        m.update_beta_weight(r)
+        assert m.effective_beta_weight == pytest.approx(want, rel=1e-15)
+    assert m.get_candidate_ids() == ["0", "1", "2"] and m.get_elector_data() is df
+    with caplog.at_level(logging.WARNING):
+        e = TransitionModel(pd.DataFrame(), initial_beta_weight=1.0)
+        P, d = e.calculate_transition_probabilities(current_round_num=1)
+    assert P.shape == (0, 0) and d == []
+    assert "TransitionModel initialized with empty elector_data. Most operations will result in empty outputs." in caplog.text
+    assert "No electors or actual candidates to calculate transition probabilities for." in caplog.text
+    caplog.clear()
+    with caplog.at_level(logging.WARNING):
+        TransitionModel(df.reset_index(drop=True))
+    assert "Elector data index is not named 'elector_id' and 'elector_id' column not found." in caplog.text
+    with pytest.raises(TypeError):
+        from conclave_sim_b200 import make_params
+        make_params({"not_a_model_kwarg": 1})
+
+
+def test_worker_on_empty_roster_matches_reference():
+    import pandas as pd
+    from conclave_sim_b200 import simulate as S
+    r = S._run_single_simulation_worker(3, pd.DataFrame(), {}, 10, 0.5, 5, 2, False, False, 3, 0.05, 3, False)
+    assert r == {"sim_id": 3, "winner": None, "rounds": 1, "reason": "No probabilities generated", "final_votes": {}, "run_details": []}
