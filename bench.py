@@ -239,22 +239,24 @@ def main():
 
     # ---- roofline of the dominant kernel (k_trials_dense32), per launch, this rank
     try:
-        peak_fp32 = eng.microbench(0); peak_mufu = eng.microbench(1); peak_mix = eng.microbench(2); peak_src = "measured (csim_microbench on this GPU)"
+        peak_fp32 = eng.microbench(0); peak_mufu = eng.microbench(1); peak_mix = eng.microbench(2); peak_fact = eng.microbench(3)
+        peak_src = "measured (csim_microbench on this GPU)"
     except Exception:
-        peak_fp32, peak_mufu, peak_mix, peak_src = FALLBACK_FP32_GINSTR, FALLBACK_MUFU_GINSTR, None, "architectural fallback"
+        peak_fp32, peak_mufu, peak_mix, peak_fact, peak_src = FALLBACK_FP32_GINSTR, FALLBACK_MUFU_GINSTR, None, None, "architectural fallback"
     pairs_per_launch = tot_pairs / args.steps
     kern_s = (sum(kernel_ms) / args.steps) * 1e-3
     ach_fp32 = pairs_per_launch * FP32_PER_PAIR / kern_s * 1e-9
     ach_mufu = pairs_per_launch * MUFU_PER_PAIR / kern_s * 1e-9
     out_bytes = n_local * 9 + (E + 1 + R + 1 + 2) * 8
-    roofline = {"bound": "fp32", "kernel": "k_trials_dense32<17,8,false>", "achieved": ach_fp32, "peak": peak_fp32,
+    roofline = {"bound": "fp32", "kernel": "k_trials_dense32<17,8,false,FACT=true>", "achieved": ach_fp32, "peak": peak_fp32,
                 "unit": "G thread-instr/s", "frac": ach_fp32 / peak_fp32, "traffic": None,
                 "algorithmic": f"{FP32_PER_PAIR} FP32-pipe instr per (elector,candidate) pair evaluation (SURVEY 8d); "
                                f"{pairs_per_launch:.4g} pair evaluations per launch (E*C in full-field rounds, E*k in run-off rounds)",
                 "peak_source": peak_src, "kernel_ms_per_launch": kern_s * 1e3,
                 "sfu": {"achieved": ach_mufu, "peak": peak_mufu, "unit": "G MUFU/s", "frac": ach_mufu / peak_mufu},
                 "pair_evals_per_s": pairs_per_launch / kern_s,
-                "mixed_pair_body_peak_ginstr": peak_mix,
+                "mufu_pair_body_peak_pairs_per_s": None if peak_mix is None else peak_mix / 4 * 1e9,
+                "factorised_pair_body_peak_pairs_per_s": None if peak_fact is None else peak_fact / 2.5 * 1e9,
                 "hbm_writeback_gbs": out_bytes / kern_s * 1e-9}
 
     # ---- e2e: the host-buffer public API (roster + params uploaded, results copied back, every step)

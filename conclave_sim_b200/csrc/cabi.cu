@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -60,7 +61,8 @@ struct csim_ctx {
     cudaDeviceProp prop{};
     int E = 0, Epad = 0, G = 0;
     DevBuf x64, x32, region, pap;
-    DevBuf sets, betas, nbeta, W;
+    DevBuf sets, betas, nbeta, W, tab;
+    double x_mid = 0.0, x_half = 0.0;   // centre and half-range of ideology_score (factorised exp)
     // host-buffer mode staging
     DevBuf o_winner, o_rounds, o_reason, o_final, o_tallies, o_whist, o_rhist, o_totals, i_tape;
     // prob-matrix staging
@@ -102,7 +104,7 @@ extern "C" csim_status csim_create(csim_ctx** out, int device) {
 extern "C" csim_status csim_destroy(csim_ctx* c) {
     if (!c) return CSIM_OK;
     cudaSetDevice(c->device);
-    for (DevBuf* b : {&c->x64, &c->x32, &c->region, &c->pap, &c->sets, &c->betas, &c->nbeta, &c->W, &c->o_winner, &c->o_rounds,
+    for (DevBuf* b : {&c->x64, &c->x32, &c->region, &c->pap, &c->sets, &c->betas, &c->nbeta, &c->W, &c->tab, &c->o_winner, &c->o_rounds,
                       &c->o_reason, &c->o_final, &c->o_tallies, &c->o_whist, &c->o_rhist, &c->o_totals, &c->i_tape,
                       &c->p_prev, &c->p_cnt, &c->p_fat, &c->p_shares, &c->p_bw, &c->p_out})
         b->release();
@@ -145,6 +147,10 @@ extern "C" csim_status csim_upload_roster(csim_ctx* c, int32_t E, const double* 
     CU_TRY(cudaMemcpy(c->region.p, dense.data(), sizeof(int32_t) * E, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(c->pap.p, pp.data(), E, cudaMemcpyHostToDevice));
     c->E = E; c->Epad = (E + 31) & ~31; c->G = (int)code.size();
+    double lo = x[0], hi = x[0];
+    for (int i = 1; i < E; ++i) { lo = std::min(lo, x[i]); hi = std::max(hi, x[i]); }
+    c->x_mid = 0.5 * (lo + hi); c->x_half = 0.5 * (hi - lo);
+    if (!(c->x_mid == c->x_mid) || !(c->x_half == c->x_half)) { c->x_mid = 0.0; c->x_half = 1e300; }
     return CSIM_OK;
 }
 
@@ -320,7 +326,7 @@ static csim_status launch_exact64(csim_ctx* c, const csim_run_args* ra, const st
     return CSIM_OK;
 }
 
-template <int NCH, int LC, bool MODEL>
+template <int NCH, int LC, bool MODEL, bool FACT>
 static csim_status launch_dense32_t(csim_ctx* c, Dense32Args& a, cudaStream_t st) {
     a.cta_smem = dense32_cta_smem<NCH>(a.L, a.ro.G);
     a.warp_smem = dense32_warp_smem<NCH>(a.ro.E, a.L, a.kmax, MODEL);
@@ -331,9 +337,18 @@ static csim_status launch_dense32_t(csim_ctx* c, Dense32Args& a, cudaStream_t st
     a.warps_per_cta = wpc;
     const size_t smem = a.cta_smem + a.warp_smem * wpc;
     int grid = 1;
-    auto kern = k_trials_dense32<NCH, LC, MODEL>;
+    auto kern = k_trials_dense32<NCH, LC, MODEL, FACT>;
     csim_status s = persistent_grid(c, kern, wpc * 32, smem, (uint64_t)a.b.n_sets * a.b.n_sims, wpc, &grid);
     if (s != CSIM_OK) return s;
+    if (FACT) {
+        const int CP = NCH * a.L;
+        const size_t tb = sizeof(float) * (size_t)a.b.n_sets * a.b.R * 4 * CP;
+        CU_TRY(c->tab.reserve(tb));
+        a.tab = (const float*)c->tab.p;
+        dim3 g((CP + 127) / 128, a.b.n_sets * a.b.R);
+        k_round_tables32<<<g, 128, 0, st>>>(a.ro, a.b.sets, (const double*)c->betas.p, a.b.R, CP, c->x_mid, (float*)c->tab.p);
+        ++c->launches;
+    }
     CU_TRY(cudaEventRecord(c->ev0, st));
     kern<<<grid, wpc * 32, smem, st>>>(a);
     CU_TRY(cudaEventRecord(c->ev1, st));
@@ -343,8 +358,14 @@ static csim_status launch_dense32_t(csim_ctx* c, Dense32Args& a, cudaStream_t st
     return CSIM_OK;
 }
 
-static csim_status launch_dense32(csim_ctx* c, const csim_run_args* ra, const std::vector<DevSet>& hs, const BatchDev& b,
-                                  const TrialOut& out, cudaStream_t st) {
+template <int NCH, int LC>
+static csim_status launch_dense32_d(csim_ctx* c, Dense32Args& a, bool model, bool fact, cudaStream_t st) {
+    if (model) return fact ? launch_dense32_t<NCH, LC, true, true>(c, a, st) : launch_dense32_t<NCH, LC, true, false>(c, a, st);
+    return fact ? launch_dense32_t<NCH, LC, false, true>(c, a, st) : launch_dense32_t<NCH, LC, false, false>(c, a, st);
+}
+
+static csim_status launch_dense32(csim_ctx* c, const csim_run_args* ra, const std::vector<DevSet>& hs, const std::vector<double>& hb,
+                                  const BatchDev& b, const TrialOut& out, cudaStream_t st) {
     for (const DevSet& s : hs)
         if (s.en_fat || s.en_stop)
             return fail(CSIM_ERR_UNSUPPORTED, "candidate fatigue / stop-candidate are implemented in CSIM_FP64 precision only");
@@ -353,18 +374,18 @@ static csim_status launch_dense32(csim_ctx* c, const csim_run_args* ra, const st
             return fail(CSIM_ERR_UNSUPPORTED, "negative bonus / strength / papabile factor: use CSIM_FP64 precision");
     if (c->G > 64) return fail(CSIM_ERR_UNSUPPORTED, "%d distinct regions (> 64): use CSIM_FP64 precision", c->G);
     Dense32Args a;
-    a.ro = roster_dev(c); a.b = b; a.out = out; a.nbeta = (const float*)c->nbeta.p; a.wiring = ra->wiring;
+    a.ro = roster_dev(c); a.b = b; a.out = out; a.nbeta = (const float*)c->nbeta.p; a.wiring = ra->wiring; a.tab = nullptr;
     int kmax = 1;
     for (const DevSet& s : hs) kmax = std::max(kmax, s.k);
     a.kmax = kmax;
+    // factorised exponential: needs beta >= 0 and e^{+-beta x'} comfortably inside fp32 range
+    bool fact = getenv("CSIM_DENSE_MUFU") == nullptr;
+    for (double be : hb) if (!(be >= 0.0) || !(be * c->x_half <= 40.0)) fact = false;
     const bool model = ra->wiring == CSIM_WIRING_MODEL;
     const int E = c->E;
-    if (E <= 17 * 8) {
-        a.L = 8;
-        return model ? launch_dense32_t<17, 8, true>(c, a, st) : launch_dense32_t<17, 8, false>(c, a, st);
-    }
+    if (E <= 17 * 8) { a.L = 8; return launch_dense32_d<17, 8>(c, a, model, fact, st); }
     a.L = (((E + 31) / 32) + 3) & ~3;
-    return model ? launch_dense32_t<32, 0, true>(c, a, st) : launch_dense32_t<32, 0, false>(c, a, st);
+    return launch_dense32_d<32, 0>(c, a, model, fact, st);
 }
 
 extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
@@ -436,7 +457,7 @@ extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
         if (ra->totals) { CU_TRY(c->o_totals.reserve(8 * nh_t)); CU_TRY(cudaMemsetAsync(c->o_totals.p, 0, 8 * nh_t, st)); out.totals = (unsigned long long*)c->o_totals.p; }
     }
 
-    csim_status s = ra->precision == CSIM_FP64 ? launch_exact64(c, ra, hs, b, out, st) : launch_dense32(c, ra, hs, b, out, st);
+    csim_status s = ra->precision == CSIM_FP64 ? launch_exact64(c, ra, hs, b, out, st) : launch_dense32(c, ra, hs, hb, b, out, st);
     if (s != CSIM_OK) return s;
 
     if (!dev) {
@@ -475,7 +496,7 @@ extern "C" csim_status csim_stats(csim_ctx* c, int64_t* kernel_launches, float* 
 
 extern "C" csim_status csim_microbench(csim_ctx* c, int32_t kind, double* ginstr_per_s) {
     if (!c || !ginstr_per_s) return fail(CSIM_ERR_INVALID, "csim_microbench: NULL argument");
-    if (kind < 0 || kind > 2) return fail(CSIM_ERR_INVALID, "csim_microbench: kind %d", kind);
+    if (kind < 0 || kind > 3) return fail(CSIM_ERR_INVALID, "csim_microbench: kind %d", kind);
     CU_TRY(cudaSetDevice(c->device));
     float* sink = nullptr;
     CU_TRY(cudaMalloc(&sink, 4));
@@ -487,14 +508,16 @@ extern "C" csim_status csim_microbench(csim_ctx* c, int32_t kind, double* ginstr
         cudaEventRecord(e0);
         if (kind == 0) k_microbench<0><<<grid, threads>>>(sink, iters, 1.0000001f, 1e-9f);
         else if (kind == 1) k_microbench<1><<<grid, threads>>>(sink, iters, 0.f, 0.f);
-        else k_microbench<2><<<grid, threads>>>(sink, iters, 0.37f, -1.3f);
+        else if (kind == 2) k_microbench<2><<<grid, threads>>>(sink, iters, 0.37f, -1.3f);
+        else k_microbench<3><<<grid, threads>>>(sink, iters, 0.999f, 0.998f);
         cudaEventRecord(e1);
         ++c->launches;
         cudaError_t e = cudaEventSynchronize(e1);
         if (e != cudaSuccess) { cudaFree(sink); return fail(CSIM_ERR_CUDA, "microbench: %s", cudaGetErrorString(e)); }
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
-        const double per_iter = kind == 2 ? 32.0 : 8.0;      // thread-instructions per loop iteration (kind 2: 8 x {FADD,FMUL,MUFU,FFMA})
+        // thread-instructions per loop iteration (kind 2: 8 pairs x {FADD,FMUL,MUFU,FFMA}; kind 3: 8 pairs = 4 x {2 FMUL2, 2 FMNMX, FADD2})
+        const double per_iter = kind == 2 ? 32.0 : (kind == 3 ? 20.0 : 8.0);
         const double g = (double)grid * threads * iters * per_iter / (ms * 1e-3) * 1e-9;
         if (rep > 0) best = std::max(best, g);
     }

@@ -23,6 +23,15 @@
 //
 // Run-off rounds (simulate.py:144-154,183-186) only need the first k columns of the row
 // (P[e, :k] renormalised), so they cost k pair evaluations per elector.
+//
+// Factorised evaluation (template flag FACT, the default whenever beta_r >= 0 and
+// beta_r * half-range(x) <= 40): with x' = x - x_mid,
+//     exp(-beta |x_e - x_c|) = min( e^{-beta x'_e} e^{+beta x'_c} ,  e^{+beta x'_e} e^{-beta x'_c} )
+// so a pair costs two multiplies and a min instead of FADD + FMUL + MUFU.EX2, and the multiplies and
+// the accumulation run as sm_100 packed-fp32 instructions (FMUL2 / FADD2, two pairs per issue slot):
+// 3 issue slots per pair including the shared-memory operand loads.  The four per-round vectors
+// A = e^{-beta x'}, A' = e^{+beta x'}, BP = A' * pw, BP' = A * pw come from k_round_tables32 (fp64 exp,
+// rounded once).  FACT = false keeps the MUFU.EX2 form (any roster, any beta).
 #pragma once
 #include "common.cuh"
 
@@ -31,6 +40,7 @@ struct Dense32Args {
     BatchDev b;
     TrialOut out;
     const float* nbeta;     // [sets][R]  -beta_r * log2(e)
+    const float* tab;       // [sets][R][4][NCH*L]  A, A', BP, BP' (FACT only)
     int wiring;
     int L;                  // candidates per chunk (multiple of 4); NCH * L >= C
     int kmax;
@@ -47,16 +57,48 @@ __host__ __device__ inline size_t dense32_cta_smem(int L, int G) {
 template <int NCH>
 __host__ __device__ inline size_t dense32_warp_smem(int E, int L, int kmax, bool model) {
     const size_t CP = (size_t)NCH * L;
-    size_t n = CP * 4 /*pw*/ + (size_t)E * 4 /*tally*/ + (size_t)kmax * 4 /*eff*/ + (((size_t)E + 3) & ~(size_t)3) /*mark*/;
+    size_t n = CP * 4 * 2 /*pw | bp, bpp*/ + (size_t)E * 4 /*tally*/ + (size_t)kmax * 4 /*eff*/ + (((size_t)E + 3) & ~(size_t)3) /*mark*/;
     if (model) n += (size_t)E * 4 * 2 /*prev_tally, votes*/ + CP * 4 /*bw*/ + (size_t)((NCH + 3) & ~3) * 4 /*bwchunk*/;
     return (n + 15) & ~(size_t)15;
 }
 
+// sm_100 packed fp32 (two lanes of a 64-bit register pair per instruction)
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+    unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+    unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+    return ((unsigned long long)__float_as_uint(hi) << 32) | (unsigned long long)__float_as_uint(lo);
+}
+__device__ __forceinline__ float f2_lo(unsigned long long v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float f2_hi(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
+
+// K0 (FACT): per (set, round) vectors of the factorised exponential, fp64 exp rounded once to fp32.
+// grid = (ceil(CP/128), sets*R), block = 128.
+__global__ void k_round_tables32(RosterDev ro, const DevSet* sets, const double* betas, int R, int CP, double xm, float* tab) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int sr = blockIdx.y;
+    if (c >= CP) return;
+    float A = 0.f, Ap = 0.f, BP = 0.f, BPp = 0.f;
+    if (c < ro.E) {
+        const double beta = betas[sr], xp = ro.x64[c] - xm;
+        const double ea = exp(-beta * xp), eb = exp(beta * xp);
+        const double pw = ro.pap[c] ? sets[sr / R].pwf : 1.0;
+        A = (float)ea; Ap = (float)eb; BP = (float)(eb * pw); BPp = (float)(ea * pw);
+    }
+    float* t = tab + (size_t)sr * 4 * CP;
+    t[c] = A; t[CP + c] = Ap; t[2 * CP + c] = BP; t[3 * CP + c] = BPp;
+}
+
 // every term of one score, inline (run-off rounds and the generic re-scan)
-template <bool MODEL>
-__device__ __forceinline__ float full_score32(int e, int c, float xe, int ge, float nb, float bonus, float st1p, int prev,
-                                              bool use_bw, const float* xs, const int32_t* reg, const float* pw, const float* bw) {
-    float v = ex2_approx(fabsf(xe - xs[c]) * nb) * pw[c];
+template <bool MODEL, bool FACT>
+__device__ __forceinline__ float full_score32(int e, int c, float xe, float ae, float ape, int ge, float nb, float bonus, float st1p,
+                                              int prev, bool use_bw, const float* xs, const int32_t* reg, const float* pw,
+                                              const float* bpp, const float* bw) {
+    // FACT: pw = BP, bpp = BP';  else pw = per-candidate papabile weight
+    float v = FACT ? fminf(ae * pw[c], ape * bpp[c]) : ex2_approx(fabsf(xe - xs[c]) * nb) * pw[c];
     if (reg[c] == ge) v += bonus;
     if (MODEL) {
         if (use_bw) v += bw[c];
@@ -84,24 +126,25 @@ __device__ __forceinline__ void warp_top2(const int32_t* tally, int C, int lane,
 
 struct LaneCtx32 {              // per-warp / per-round constants of the draw
     const float* xs; const int32_t* reg; const float* regcnt; const uint32_t* regmask;
-    const float* pw; const float* bw; const float* bwchunk;
+    const float* pw; const float* bpp; const float* bw; const float* bwchunk;   // FACT: pw = BP, bpp = BP'
     float nb, bonus, st1p;
     int C, G, L;
     bool use_bw;
 };
 
 // One full-field draw, chunk length 8 (E <= 136): phase 1 + chunk search + vectorised re-scan.
-template <int NCH, bool MODEL>
-__device__ __forceinline__ int draw_full_lc8(const LaneCtx32& k, int e, float u, int prev) {
-    const float xe = k.xs[e];
+template <int NCH, bool MODEL, bool FACT>
+__device__ __forceinline__ int draw_full_lc8(const LaneCtx32& k, int e, float u, int prev, float ae, float ape) {
+    const float xe = FACT ? 0.f : k.xs[e];
     const int ge = k.reg[e];
     const float nb = k.nb;
     const int je = e >> 3;
-    float see = k.pw[e] + k.bonus;                       // the self score, removed from its chunk (model.py:418-424)
+    // the self score, removed from its chunk (model.py:418-424); same expression as phase 1 so it cancels
+    float see = (FACT ? fminf(ae * k.pw[e], ape * k.bpp[e]) : k.pw[e]) + k.bonus;
     if (MODEL && k.use_bw) see += k.bw[e];
     int jp = -1; float sadd = 0.f;
     if (MODEL && prev >= 0 && prev != e) {               // stickiness: + st * s[e, prev] in prev's chunk (model.py:357-367)
-        float sp = ex2_approx(fabsf(xe - k.xs[prev]) * nb) * k.pw[prev];
+        float sp = FACT ? fminf(ae * k.pw[prev], ape * k.bpp[prev]) : ex2_approx(fabsf(xe - k.xs[prev]) * nb) * k.pw[prev];
         if (k.reg[prev] == ge) sp += k.bonus;
         if (k.use_bw) sp += k.bw[prev];
         sadd = sp * (k.st1p - 1.0f);
@@ -110,19 +153,35 @@ __device__ __forceinline__ int draw_full_lc8(const LaneCtx32& k, int e, float u,
     // ---------------- phase 1: chunk sums -----------------------------------------------------------
     float cs[NCH];
     float S = 0.f;
+    const unsigned long long a2 = f2_pack(ae, ae), ap2 = f2_pack(ape, ape);
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
         float acc0 = (j == je) ? -see : 0.f;
         float acc1 = (MODEL && j == jp) ? sadd : 0.f;
-        const float4* x4 = reinterpret_cast<const float4*>(k.xs + j * 8);
-        const float4* p4 = reinterpret_cast<const float4*>(k.pw + j * 8);
+        if (FACT) {
+            unsigned long long acc = f2_pack(acc0, acc1);
+            const ulonglong2* b4 = reinterpret_cast<const ulonglong2*>(k.pw + j * 8);
+            const ulonglong2* c4 = reinterpret_cast<const ulonglong2*>(k.bpp + j * 8);
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const float4 xv = x4[i], pv = p4[i];
-            acc0 = fmaf(ex2_approx(fabsf(xe - xv.x) * nb), pv.x, acc0);
-            acc1 = fmaf(ex2_approx(fabsf(xe - xv.y) * nb), pv.y, acc1);
-            acc0 = fmaf(ex2_approx(fabsf(xe - xv.z) * nb), pv.z, acc0);
-            acc1 = fmaf(ex2_approx(fabsf(xe - xv.w) * nb), pv.w, acc1);
+            for (int i = 0; i < 2; ++i) {
+                const ulonglong2 b = b4[i], c = c4[i];
+                unsigned long long t1 = f2_mul(a2, b.x), t2 = f2_mul(ap2, c.x);
+                acc = f2_add(acc, f2_pack(fminf(f2_lo(t1), f2_lo(t2)), fminf(f2_hi(t1), f2_hi(t2))));
+                t1 = f2_mul(a2, b.y); t2 = f2_mul(ap2, c.y);
+                acc = f2_add(acc, f2_pack(fminf(f2_lo(t1), f2_lo(t2)), fminf(f2_hi(t1), f2_hi(t2))));
+            }
+            acc0 = f2_lo(acc); acc1 = f2_hi(acc);
+        } else {
+            const float4* x4 = reinterpret_cast<const float4*>(k.xs + j * 8);
+            const float4* p4 = reinterpret_cast<const float4*>(k.pw + j * 8);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float4 xv = x4[i], pv = p4[i];
+                acc0 = fmaf(ex2_approx(fabsf(xe - xv.x) * nb), pv.x, acc0);
+                acc1 = fmaf(ex2_approx(fabsf(xe - xv.y) * nb), pv.y, acc1);
+                acc0 = fmaf(ex2_approx(fabsf(xe - xv.z) * nb), pv.z, acc0);
+                acc1 = fmaf(ex2_approx(fabsf(xe - xv.w) * nb), pv.w, acc1);
+            }
         }
         float s = fmaf(k.bonus, k.regcnt[j * k.G + ge], acc0 + acc1);    // regional bonus of the chunk (model.py:322-323)
         if (MODEL && k.use_bw) s += k.bwchunk[j];                        // bandwagon of the chunk (model.py:354)
@@ -148,7 +207,9 @@ __device__ __forceinline__ int draw_full_lc8(const LaneCtx32& k, int e, float u,
     jstar = jstar > last_chunk ? last_chunk : jstar;
     // ---------------- phase 2b: re-scan that chunk, every term inline, roster order ------------------
     const int c0 = jstar * 8;
-    const float4 xa = *reinterpret_cast<const float4*>(k.xs + c0), xb = *reinterpret_cast<const float4*>(k.xs + c0 + 4);
+    // FACT: (xa, xb) hold BP', (pa, pb) hold BP;  else x and pw
+    const float* src_x = FACT ? k.bpp : k.xs;
+    const float4 xa = *reinterpret_cast<const float4*>(src_x + c0), xb = *reinterpret_cast<const float4*>(src_x + c0 + 4);
     const float4 pa = *reinterpret_cast<const float4*>(k.pw + c0), pb = *reinterpret_cast<const float4*>(k.pw + c0 + 4);
     const uint32_t rm = k.regmask[jstar * k.G + ge];                     // bit i: candidate c0+i is of e's region
     const uint32_t dm = (jstar == je) ? (1u << (e & 7)) : 0u;            // bit i: candidate c0+i is e itself
@@ -162,7 +223,8 @@ __device__ __forceinline__ int draw_full_lc8(const LaneCtx32& k, int e, float u,
     int cnt = 0;
 #define CSIM_RESCAN(i, xv, pv, bv)                                              \
     {                                                                           \
-        float v = fmaf(ex2_approx(fabsf(xe - (xv)) * nb), (pv), ((rm >> (i)) & 1u) ? k.bonus : 0.0f); \
+        const float ex = FACT ? fminf(ae * (pv), ape * (xv)) : ex2_approx(fabsf(xe - (xv)) * nb) * (pv); \
+        float v = ex + (((rm >> (i)) & 1u) ? k.bonus : 0.0f);                   \
         if (MODEL) { v += (bv); if ((pm >> (i)) & 1u) v *= k.st1p; }            \
         if ((dm >> (i)) & 1u) v = 0.0f;                                         \
         cum += v;                                                               \
@@ -179,18 +241,18 @@ __device__ __forceinline__ int draw_full_lc8(const LaneCtx32& k, int e, float u,
 }
 
 // Generic chunk length (runtime L, multiple of 4): same algorithm, scalar re-scan.
-template <int NCH, bool MODEL>
-__device__ __forceinline__ int draw_full_generic(const LaneCtx32& k, int e, float u, int prev) {
+template <int NCH, bool MODEL, bool FACT>
+__device__ __forceinline__ int draw_full_generic(const LaneCtx32& k, int e, float u, int prev, float ae, float ape) {
     const int L = k.L, C = k.C;
-    const float xe = k.xs[e];
+    const float xe = FACT ? 0.f : k.xs[e];
     const int ge = k.reg[e];
     const float nb = k.nb;
     const int je = e / L;
-    float see = k.pw[e] + k.bonus;
+    float see = (FACT ? fminf(ae * k.pw[e], ape * k.bpp[e]) : k.pw[e]) + k.bonus;
     if (MODEL && k.use_bw) see += k.bw[e];
     int jp = -1; float sadd = 0.f;
     if (MODEL && prev >= 0 && prev != e) {
-        float sp = ex2_approx(fabsf(xe - k.xs[prev]) * nb) * k.pw[prev];
+        float sp = FACT ? fminf(ae * k.pw[prev], ape * k.bpp[prev]) : ex2_approx(fabsf(xe - k.xs[prev]) * nb) * k.pw[prev];
         if (k.reg[prev] == ge) sp += k.bonus;
         if (k.use_bw) sp += k.bw[prev];
         sadd = sp * (k.st1p - 1.0f);
@@ -198,18 +260,34 @@ __device__ __forceinline__ int draw_full_generic(const LaneCtx32& k, int e, floa
     }
     float cs[NCH];
     float S = 0.f;
+    const unsigned long long a2 = f2_pack(ae, ae), ap2 = f2_pack(ape, ape);
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
         float acc0 = (j == je) ? -see : 0.f;
         float acc1 = (MODEL && j == jp) ? sadd : 0.f;
-        const float4* x4 = reinterpret_cast<const float4*>(k.xs + j * L);
-        const float4* p4 = reinterpret_cast<const float4*>(k.pw + j * L);
-        for (int i = 0; i < (L >> 2); ++i) {
-            const float4 xv = x4[i], pv = p4[i];
-            acc0 = fmaf(ex2_approx(fabsf(xe - xv.x) * nb), pv.x, acc0);
-            acc1 = fmaf(ex2_approx(fabsf(xe - xv.y) * nb), pv.y, acc1);
-            acc0 = fmaf(ex2_approx(fabsf(xe - xv.z) * nb), pv.z, acc0);
-            acc1 = fmaf(ex2_approx(fabsf(xe - xv.w) * nb), pv.w, acc1);
+        if (FACT) {
+            unsigned long long acc = f2_pack(acc0, acc1);
+            const ulonglong2* b4 = reinterpret_cast<const ulonglong2*>(k.pw + j * L);
+            const ulonglong2* c4 = reinterpret_cast<const ulonglong2*>(k.bpp + j * L);
+#pragma unroll 2
+            for (int i = 0; i < (L >> 2); ++i) {
+                const ulonglong2 b = b4[i], c = c4[i];
+                unsigned long long t1 = f2_mul(a2, b.x), t2 = f2_mul(ap2, c.x);
+                acc = f2_add(acc, f2_pack(fminf(f2_lo(t1), f2_lo(t2)), fminf(f2_hi(t1), f2_hi(t2))));
+                t1 = f2_mul(a2, b.y); t2 = f2_mul(ap2, c.y);
+                acc = f2_add(acc, f2_pack(fminf(f2_lo(t1), f2_lo(t2)), fminf(f2_hi(t1), f2_hi(t2))));
+            }
+            acc0 = f2_lo(acc); acc1 = f2_hi(acc);
+        } else {
+            const float4* x4 = reinterpret_cast<const float4*>(k.xs + j * L);
+            const float4* p4 = reinterpret_cast<const float4*>(k.pw + j * L);
+            for (int i = 0; i < (L >> 2); ++i) {
+                const float4 xv = x4[i], pv = p4[i];
+                acc0 = fmaf(ex2_approx(fabsf(xe - xv.x) * nb), pv.x, acc0);
+                acc1 = fmaf(ex2_approx(fabsf(xe - xv.y) * nb), pv.y, acc1);
+                acc0 = fmaf(ex2_approx(fabsf(xe - xv.z) * nb), pv.z, acc0);
+                acc1 = fmaf(ex2_approx(fabsf(xe - xv.w) * nb), pv.w, acc1);
+            }
         }
         float s = fmaf(k.bonus, k.regcnt[j * k.G + ge], acc0 + acc1);
         if (MODEL && k.use_bw) s += k.bwchunk[j];
@@ -237,7 +315,7 @@ __device__ __forceinline__ int draw_full_generic(const LaneCtx32& k, int e, floa
     int cnt = 0;
     for (int i = 0; i < L; ++i) {
         const int c = c0 + i;
-        const float v = c < C ? full_score32<MODEL>(e, c, xe, ge, nb, k.bonus, k.st1p, prev, k.use_bw, k.xs, k.reg, k.pw, k.bw) : 0.0f;
+        const float v = c < C ? full_score32<MODEL, FACT>(e, c, xe, ae, ape, ge, nb, k.bonus, k.st1p, prev, k.use_bw, k.xs, k.reg, k.pw, k.bpp, k.bw) : 0.0f;
         cum += v;
         cnt += (cum <= tgt) ? 1 : 0;
     }
@@ -248,7 +326,7 @@ __device__ __forceinline__ int draw_full_generic(const LaneCtx32& k, int e, floa
     return vote;
 }
 
-template <int NCH, int LC, bool MODEL>
+template <int NCH, int LC, bool MODEL, bool FACT>
 __global__ void __launch_bounds__(256, LC == 8 ? 3 : 1) k_trials_dense32(Dense32Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -275,7 +353,8 @@ __global__ void __launch_bounds__(256, LC == 8 ? 3 : 1) k_trials_dense32(Dense32
     // ---- per-warp state ----------------------------------------------------------------------
     unsigned char* base = smem_raw + a.cta_smem + (size_t)wib * a.warp_smem;
     // 16-byte aligned float arrays first (they are read with 128-bit loads), then the int arrays
-    float* pw = (float*)base;                   base += sizeof(float) * CP;
+    float* pw = (float*)base;                   base += sizeof(float) * CP;      // FACT: BP of the current round
+    float* bpp = (float*)base;                  base += sizeof(float) * CP;      // FACT: BP'
     float* bw = nullptr; float* bwchunk = nullptr;
     if (MODEL) {
         bw = (float*)base;                      base += sizeof(float) * CP;
@@ -302,7 +381,7 @@ __global__ void __launch_bounds__(256, LC == 8 ? 3 : 1) k_trials_dense32(Dense32
     const bool top2_ok = C >= 2 && C < 32768;
 
     LaneCtx32 kx;
-    kx.xs = xs; kx.reg = reg; kx.regcnt = regcnt; kx.regmask = regmask; kx.pw = pw; kx.bw = bw; kx.bwchunk = bwchunk;
+    kx.xs = xs; kx.reg = reg; kx.regcnt = regcnt; kx.regmask = regmask; kx.pw = pw; kx.bpp = bpp; kx.bw = bw; kx.bwchunk = bwchunk;
     kx.C = C; kx.G = G; kx.L = L; kx.use_bw = false; kx.nb = 0.f; kx.bonus = 0.f; kx.st1p = 1.f;
 
     int cur_set = -1;
@@ -326,20 +405,26 @@ __global__ void __launch_bounds__(256, LC == 8 ? 3 : 1) k_trials_dense32(Dense32
             has_sticky = MODEL && S->has_sticky; has_bw = MODEL && S->has_bw;
             const float pwf = S->f_pwf;
             __syncwarp();
-            for (int c = lane; c < CP; c += 32) pw[c] = c < C ? (a.ro.pap[c] ? pwf : 1.0f) : 0.0f;
+            if (!FACT) for (int c = lane; c < CP; c += 32) pw[c] = c < C ? (a.ro.pap[c] ? pwf : 1.0f) : 0.0f;
             if (MODEL) for (int c = lane; c < CP; c += 32) bw[c] = 0.0f;
             __syncwarp();
         }
         const float* nbeta = a.nbeta + (size_t)set * R;
         const bool fast2 = (k == 2) && top2_ok;                  // two-candidate run-off: O(1) closing
         bool have_eff = false, have_prev = false;
-        int winner = -1, rounds = 0, reason = CSIM_REASON_WINNER * 0 + CSIM_REASON_MAX_ROUNDS;
+        int winner = -1, rounds = 0, reason = CSIM_REASON_MAX_ROUNDS;
         int ef0 = 0, ef1 = 0;                                    // run-off pair when fast2
 
         for (int r = 1; r <= R; ++r) {
             rounds = r;
             kx.nb = __ldg(&nbeta[r - 1]);
             kx.use_bw = false;
+            const float* tabA = nullptr;
+            if (FACT) {                                          // stage this round's BP / BP' (trial-invariant vectors)
+                tabA = a.tab + ((size_t)set * R + (r - 1)) * 4 * CP;
+                __syncwarp();
+                for (int c = lane; c < CP; c += 32) { pw[c] = __ldg(tabA + 2 * CP + c); bpp[c] = __ldg(tabA + 3 * CP + c); }
+            }
             if (MODEL) {
                 if (has_bw && have_prev) {                                   // model.py:326-354
                     int mx, arg;
@@ -371,16 +456,18 @@ __global__ void __launch_bounds__(256, LC == 8 ? 3 : 1) k_trials_dense32(Dense32
                 const uint32_t wa = sel == 0 ? w[0] : (sel == 1 ? w[1] : (sel == 2 ? w[2] : w[3]));
                 const float u = u24_from_word(wa);
                 const int prev = (MODEL && have_prev && has_sticky) ? votes[e] : -1;
+                float ae = 0.f, ape = 0.f;
+                if (FACT) { ae = __ldg(tabA + e); ape = __ldg(tabA + CP + e); }
                 int vote;
                 if (!have_eff) {
-                    if (LC == 8) vote = draw_full_lc8<NCH, MODEL>(kx, e, u, prev);
-                    else vote = draw_full_generic<NCH, MODEL>(kx, e, u, prev);
+                    if (LC == 8) vote = draw_full_lc8<NCH, MODEL, FACT>(kx, e, u, prev, ae, ape);
+                    else vote = draw_full_generic<NCH, MODEL, FACT>(kx, e, u, prev, ae, ape);
                     atomicAdd(&tally[vote], 1);
                 } else if (fast2) {
                     // ---------------- two-candidate run-off: columns 0 and 1, renormalised (simulate.py:144-154)
-                    const float xe = xs[e]; const int ge = reg[e];
-                    const float v0 = full_score32<MODEL>(e, 0, xe, ge, kx.nb, kx.bonus, kx.st1p, prev, kx.use_bw, xs, reg, pw, bw);
-                    const float v1 = full_score32<MODEL>(e, 1, xe, ge, kx.nb, kx.bonus, kx.st1p, prev, kx.use_bw, xs, reg, pw, bw);
+                    const float xe = FACT ? 0.f : xs[e]; const int ge = reg[e];
+                    const float v0 = full_score32<MODEL, FACT>(e, 0, xe, ae, ape, ge, kx.nb, kx.bonus, kx.st1p, prev, kx.use_bw, xs, reg, pw, bpp, bw);
+                    const float v1 = full_score32<MODEL, FACT>(e, 1, xe, ae, ape, ge, kx.nb, kx.bonus, kx.st1p, prev, kx.use_bw, xs, reg, pw, bpp, bw);
                     const float sum = v0 + v1;
                     int j;
                     if (!(sum > 0.0f)) j = (u * 2.0f >= 1.0f) ? 1 : 0;       // simulate.py:151 uniform fallback
@@ -389,10 +476,10 @@ __global__ void __launch_bounds__(256, LC == 8 ? 3 : 1) k_trials_dense32(Dense32
                     vote = j == 0 ? ef0 : ef1;
                 } else {
                     // ---------------- k-candidate run-off (generic) --------------------------------------------
-                    const float xe = xs[e]; const int ge = reg[e];
+                    const float xe = FACT ? 0.f : xs[e]; const int ge = reg[e];
                     float sum = 0.f;
                     for (int j = 0; j < k; ++j)
-                        sum += full_score32<MODEL>(e, j, xe, ge, kx.nb, kx.bonus, kx.st1p, prev, kx.use_bw, xs, reg, pw, bw);
+                        sum += full_score32<MODEL, FACT>(e, j, xe, ae, ape, ge, kx.nb, kx.bonus, kx.st1p, prev, kx.use_bw, xs, reg, pw, bpp, bw);
                     int jsel;
                     if (!(sum > 0.0f)) {
                         jsel = (int)(u * (float)k);
@@ -400,7 +487,7 @@ __global__ void __launch_bounds__(256, LC == 8 ? 3 : 1) k_trials_dense32(Dense32
                         const float tgt = u * sum;
                         float cum = 0.f; jsel = -1; int lastpos = 0;
                         for (int j = 0; j < k; ++j) {
-                            const float v = full_score32<MODEL>(e, j, xe, ge, kx.nb, kx.bonus, kx.st1p, prev, kx.use_bw, xs, reg, pw, bw);
+                            const float v = full_score32<MODEL, FACT>(e, j, xe, ae, ape, ge, kx.nb, kx.bonus, kx.st1p, prev, kx.use_bw, xs, reg, pw, bpp, bw);
                             cum += v;
                             if (v > 0.0f) lastpos = j;
                             if (jsel < 0 && v > 0.0f && cum > tgt) jsel = j;

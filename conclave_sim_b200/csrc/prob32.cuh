@@ -75,6 +75,29 @@ __global__ void __launch_bounds__(256) k_microbench(float* sink, int iters, floa
         } else if (KIND == 1) {     // 8 MUFU.EX2
             r0 = ex2_approx(r0); r1 = ex2_approx(r1); r2 = ex2_approx(r2); r3 = ex2_approx(r3);
             r4 = ex2_approx(r4); r5 = ex2_approx(r5); r6 = ex2_approx(r6); r7 = ex2_approx(r7);
+        } else if (KIND == 3) {     // the factorised pair body, packed: 2 x FMUL2, 2 x FMNMX, FADD2 per two pairs (x4)
+            unsigned long long A2 = ((unsigned long long)__float_as_uint(a) << 32) | __float_as_uint(a);
+            unsigned long long B2 = ((unsigned long long)__float_as_uint(b) << 32) | __float_as_uint(b);
+            unsigned long long p0 = ((unsigned long long)__float_as_uint(r1) << 32) | __float_as_uint(r0);
+            unsigned long long p1 = ((unsigned long long)__float_as_uint(r3) << 32) | __float_as_uint(r2);
+            unsigned long long p2 = ((unsigned long long)__float_as_uint(r5) << 32) | __float_as_uint(r4);
+            unsigned long long p3 = ((unsigned long long)__float_as_uint(r7) << 32) | __float_as_uint(r6);
+            unsigned long long t1, t2;
+#define CSIM_MB3(P, Q)                                                                                         \
+            asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t1) : "l"(A2), "l"(Q));                                        \
+            asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t2) : "l"(B2), "l"(Q));                                        \
+            {                                                                                                  \
+                const float m0 = fminf(__uint_as_float((unsigned)t1), __uint_as_float((unsigned)t2));          \
+                const float m1 = fminf(__uint_as_float((unsigned)(t1 >> 32)), __uint_as_float((unsigned)(t2 >> 32))); \
+                const unsigned long long mm = ((unsigned long long)__float_as_uint(m1) << 32) | __float_as_uint(m0);  \
+                asm("add.rn.f32x2 %0, %1, %2;" : "=l"(P) : "l"(P), "l"(mm));                                     \
+            }
+            CSIM_MB3(p0, p1) CSIM_MB3(p1, p2) CSIM_MB3(p2, p3) CSIM_MB3(p3, p0)
+#undef CSIM_MB3
+            r0 = __uint_as_float((unsigned)p0); r1 = __uint_as_float((unsigned)(p0 >> 32));
+            r2 = __uint_as_float((unsigned)p1); r3 = __uint_as_float((unsigned)(p1 >> 32));
+            r4 = __uint_as_float((unsigned)p2); r5 = __uint_as_float((unsigned)(p2 >> 32));
+            r6 = __uint_as_float((unsigned)p3); r7 = __uint_as_float((unsigned)(p3 >> 32));
         } else {                    // the dense kernel's pair body: FADD, FMUL|.|, MUFU.EX2, FFMA  (x2 chains x4)
             r0 = fmaf(ex2_approx(fabsf(a - r4) * b), r4, r0);
             r1 = fmaf(ex2_approx(fabsf(a - r5) * b), r5, r1);

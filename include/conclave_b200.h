@@ -110,7 +110,7 @@ typedef struct csim_run_args {
     int32_t  precision;             /* CSIM_FP32 / CSIM_FP64 */
     uint64_t sim_id_begin;
     uint64_t n_sims;                /* per parameter set */
-    uint64_t seed;                  /* Philox4x32-10 key; counter = (sim_lo, sim_hi, round, elector>>1) */
+    uint64_t seed;                  /* Philox4x32-10 key; counter = (sim_lo, sim_hi, round, elector>>2 [| 1<<31]), word elector&3 */
     const double* uniform_tape;     /* nullable: [n_trials, max_rounds * E], E uniforms per round in
                                        elector order — "the identical uniform draws exported from the
                                        reference".  Requires precision == CSIM_FP64. */
@@ -167,7 +167,8 @@ csim_status csim_run(csim_ctx* ctx, const csim_run_args* args);
 csim_status csim_stats(csim_ctx* ctx, int64_t* kernel_launches, float* last_trial_kernel_ms);
 
 /* Instruction-throughput microbenchmarks used as roofline denominators:
- * kind 0 = FP32 FFMA, 1 = MUFU.EX2, 2 = mixed FADD/FMUL/FFMA + 1 MUFU per 8.
+ * kind 0 = FP32 FFMA, 1 = MUFU.EX2, 2 = the MUFU pair body (FADD, FMUL, MUFU.EX2, FFMA),
+ * 3 = the factorised packed pair body (2 FMUL2 + 2 FMNMX + FADD2 per two pairs; 8 pairs = 20 instr).
  * Returns giga thread-instructions per second over the whole device. */
 csim_status csim_microbench(csim_ctx* ctx, int32_t kind, double* ginstr_per_s);
 
