@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libconclave_b200.so")
+LIB_PATH = os.environ.get("CSIM_LIB") or os.path.join(HERE, "libconclave_b200.so")   # CSIM_LIB: tuning builds only
 
 WIRING_REF_CLI, WIRING_MODEL = 0, 1
 ENGINE_AUTO, ENGINE_DENSE, ENGINE_TABLE = 0, 1, 2

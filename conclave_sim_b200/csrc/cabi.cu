@@ -326,22 +326,23 @@ static csim_status launch_exact64(csim_ctx* c, const csim_run_args* ra, const st
     return CSIM_OK;
 }
 
-template <int NCH, int LC, bool MODEL, bool FACT>
+template <int LC, bool MODEL, bool FACT>
 static csim_status launch_dense32_t(csim_ctx* c, Dense32Args& a, cudaStream_t st) {
-    a.cta_smem = dense32_cta_smem<NCH>(a.L, a.ro.G);
-    a.warp_smem = dense32_warp_smem<NCH>(a.ro.E, a.L, a.kmax, MODEL);
+    a.cta_smem = dense32_cta_smem(a.nch, a.L, a.ro.G);
+    a.warp_smem = dense32_warp_smem(a.ro.E, a.nch, a.L, a.kmax, MODEL);
     int wpc = 8;
-    while (wpc > 1 && a.cta_smem + a.warp_smem * wpc > 220 * 1024) wpc >>= 1;
+    const size_t budget = (size_t)(220 * 1024) / CSIM_MINB;                        // CSIM_MINB CTAs per SM
+    while (wpc > 1 && a.cta_smem + a.warp_smem * wpc > budget) --wpc;
     if (a.cta_smem + a.warp_smem * wpc > 220 * 1024)
         return fail(CSIM_ERR_UNSUPPORTED, "roster of %d electors / %d regions needs %zu B of shared memory", a.ro.E, a.ro.G, a.cta_smem + a.warp_smem);
     a.warps_per_cta = wpc;
     const size_t smem = a.cta_smem + a.warp_smem * wpc;
     int grid = 1;
-    auto kern = k_trials_dense32<NCH, LC, MODEL, FACT>;
+    auto kern = k_trials_dense32<LC, MODEL, FACT>;
     csim_status s = persistent_grid(c, kern, wpc * 32, smem, (uint64_t)a.b.n_sets * a.b.n_sims, wpc, &grid);
     if (s != CSIM_OK) return s;
     if (FACT) {
-        const int CP = NCH * a.L;
+        const int CP = a.nch * a.L;
         const size_t tb = sizeof(float) * (size_t)a.b.n_sets * a.b.R * 4 * CP;
         CU_TRY(c->tab.reserve(tb));
         a.tab = (const float*)c->tab.p;
@@ -358,10 +359,10 @@ static csim_status launch_dense32_t(csim_ctx* c, Dense32Args& a, cudaStream_t st
     return CSIM_OK;
 }
 
-template <int NCH, int LC>
+template <int LC>
 static csim_status launch_dense32_d(csim_ctx* c, Dense32Args& a, bool model, bool fact, cudaStream_t st) {
-    if (model) return fact ? launch_dense32_t<NCH, LC, true, true>(c, a, st) : launch_dense32_t<NCH, LC, true, false>(c, a, st);
-    return fact ? launch_dense32_t<NCH, LC, false, true>(c, a, st) : launch_dense32_t<NCH, LC, false, false>(c, a, st);
+    if (model) return fact ? launch_dense32_t<LC, true, true>(c, a, st) : launch_dense32_t<LC, true, false>(c, a, st);
+    return fact ? launch_dense32_t<LC, false, true>(c, a, st) : launch_dense32_t<LC, false, false>(c, a, st);
 }
 
 static csim_status launch_dense32(csim_ctx* c, const csim_run_args* ra, const std::vector<DevSet>& hs, const std::vector<double>& hb,
@@ -373,6 +374,7 @@ static csim_status launch_dense32(csim_ctx* c, const csim_run_args* ra, const st
         if (ra->params[i].regional_affinity_bonus < 0 || ra->params[i].bandwagon_strength < 0 || ra->params[i].papabile_weight_factor < 0)
             return fail(CSIM_ERR_UNSUPPORTED, "negative bonus / strength / papabile factor: use CSIM_FP64 precision");
     if (c->G > 64) return fail(CSIM_ERR_UNSUPPORTED, "%d distinct regions (> 64): use CSIM_FP64 precision", c->G);
+    if (b.R > 0 && (size_t)b.n_sets * b.R > 65535) return fail(CSIM_ERR_UNSUPPORTED, "n_param_sets * max_rounds exceeds 65535");
     Dense32Args a;
     a.ro = roster_dev(c); a.b = b; a.out = out; a.nbeta = (const float*)c->nbeta.p; a.wiring = ra->wiring; a.tab = nullptr;
     int kmax = 1;
@@ -383,9 +385,13 @@ static csim_status launch_dense32(csim_ctx* c, const csim_run_args* ra, const st
     for (double be : hb) if (!(be >= 0.0) || !(be * c->x_half <= 40.0)) fact = false;
     const bool model = ra->wiring == CSIM_WIRING_MODEL;
     const int E = c->E;
-    if (E <= 17 * 8) { a.L = 8; return launch_dense32_d<17, 8>(c, a, model, fact, st); }
-    a.L = (((E + 31) / 32) + 3) & ~3;
-    return launch_dense32_d<32, 0>(c, a, model, fact, st);
+    if (E <= 256) {                       // chunks of 8 candidates, at most 32 chunks
+        a.L = 8; a.nch = (E + 7) / 8;
+        return launch_dense32_d<8>(c, a, model, fact, st);
+    }
+    a.L = (((E + 31) / 32) + 3) & ~3;     // at most 32 chunks of L candidates
+    a.nch = (E + a.L - 1) / a.L;
+    return launch_dense32_d<0>(c, a, model, fact, st);
 }
 
 extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {

@@ -3,35 +3,38 @@
 // This is the kernel the roofline is quoted on (SURVEY §8d "canonical dense per-trial
 // formulation").  One warp owns one trial and walks it from round 1 to its end, then takes the
 // next trial (static stride over trials: results never depend on the schedule).  No block-level
-// barrier exists anywhere; only __syncwarp.
+// barrier exists after the roster tables are staged; only __syncwarp.
 //
-// A lane owns the electors of whole Philox quads (4q..4q+3, one Philox call -> four 24-bit
-// uniforms) plus at most a few leftover singles.  For one elector and one full-field round:
+// Full-field round, for every elector e (candidates are cut into chunks of L, L = 8 up to E = 256):
 //
-//   phase 1  for every candidate c:  v = ex2(|x_e - x_c| * nb_r) ; chunk_sum[c / L] += v * pw_c
-//            4 issue slots per (elector, candidate) pair: FADD, FMUL(|.|), MUFU.EX2, FFMA; the
-//            candidate operands come from shared memory as warp-uniform (broadcast) 128-bit loads.
-//            The terms that do not need the exponential are added per CHUNK, not per pair:
-//            regional bonus  = bonus * #{c in chunk : region_c == region_e}   (roster table)
-//            bandwagon       = sum of bw_c over the chunk                       (per trial-round)
-//            self vote       = - s_ee  in e's chunk            (model.py:418-424)
-//            stickiness      = + st * s_e,prev  in prev's chunk (model.py:357-367)
-//   phase 2  S = sum of chunk sums, t = u * S; the chunk whose prefix crosses t is found on the
-//            register-resident chunk sums, then ONLY that chunk's L candidates are re-evaluated
-//            with every term inline, in roster order, to find the first c with cum > t
-//            (== searchsorted(cumsum(p)/sum, u, 'right'), simulate.py:153).
-//
-// Run-off rounds (simulate.py:144-154,183-186) only need the first k columns of the row
-// (P[e, :k] renormalised), so they cost k pair evaluations per elector.
+//   phase 1   chunk_sum[j] = sum over c in chunk j of  exp(-beta_r |x_e - x_c|) * pw_c
+//             evaluated for FOUR electors of a lane at once (the electors 4q..4q+3 of one Philox
+//             quad), so every candidate operand fetched from shared memory (a warp-uniform 128-bit
+//             load, which costs 4 cycles of the SM's 128 B/clk shared-memory return path) feeds
+//             4 x 4 pair evaluations.  The terms that need no exponential are added per CHUNK:
+//               regional bonus  = bonus * #{c in chunk : region_c == region_e}   (roster table)
+//               bandwagon       = sum of bw_c over the chunk                       (per trial-round)
+//               self vote       = - s_ee  in e's chunk            (model.py:418-424)
+//               stickiness      = + st * s_e,prev  in prev's chunk (model.py:357-367)
+//             and the running prefix over chunks goes to a per-lane column of shared memory.
+//   phase 2   t = u * S; a 5-probe binary search over the prefix column finds the chunk that t falls
+//             into; ONLY that chunk's L candidates are re-evaluated with every term inline, in
+//             roster order, to find the first c with cum > t
+//             (== searchsorted(cumsum(p)/sum, u, 'right'), simulate.py:153).
+//   The E mod 128 electors that do not fill a quad per lane are split P lanes per elector (P = 4 at
+//   E = 135), each lane summing every P-th chunk, so the leftover costs ~1/4 of a full pass.
 //
 // Factorised evaluation (template flag FACT, the default whenever beta_r >= 0 and
 // beta_r * half-range(x) <= 40): with x' = x - x_mid,
 //     exp(-beta |x_e - x_c|) = min( e^{-beta x'_e} e^{+beta x'_c} ,  e^{+beta x'_e} e^{-beta x'_c} )
 // so a pair costs two multiplies and a min instead of FADD + FMUL + MUFU.EX2, and the multiplies and
-// the accumulation run as sm_100 packed-fp32 instructions (FMUL2 / FADD2, two pairs per issue slot):
-// 3 issue slots per pair including the shared-memory operand loads.  The four per-round vectors
-// A = e^{-beta x'}, A' = e^{+beta x'}, BP = A' * pw, BP' = A * pw come from k_round_tables32 (fp64 exp,
-// rounded once).  FACT = false keeps the MUFU.EX2 form (any roster, any beta).
+// the accumulation run as sm_100 packed-fp32 instructions (FMUL2 / FADD2, two pairs per issue slot).
+// The four per-round vectors A = e^{-beta x'}, A' = e^{+beta x'}, BP = A' * pw, BP' = A * pw come from
+// k_round_tables32 (fp64 exp, rounded once).  FACT = false keeps the MUFU.EX2 form (any roster, any beta).
+//
+// Run-off rounds (simulate.py:144-154,183-186) only need the first k columns of the row
+// (P[e, :k] renormalised), so they cost k pair evaluations per elector; with k = 2 the tally is a
+// warp-reduced count and the round closes in O(1).
 #pragma once
 #include "common.cuh"
 
@@ -40,25 +43,29 @@ struct Dense32Args {
     BatchDev b;
     TrialOut out;
     const float* nbeta;     // [sets][R]  -beta_r * log2(e)
-    const float* tab;       // [sets][R][4][NCH*L]  A, A', BP, BP' (FACT only)
+    const float* tab;       // [sets][R][4][nch*L]  A, A', BP, BP' (FACT only)
     int wiring;
-    int L;                  // candidates per chunk (multiple of 4); NCH * L >= C
+    int L;                  // candidates per chunk (multiple of 4)
+    int nch;                // number of chunks, nch * L >= C, nch <= 32
     int kmax;
     int warps_per_cta;
     size_t cta_smem;        // bytes of CTA-shared tables
     size_t warp_smem;       // bytes per warp
 };
 
-template <int NCH>
-__host__ __device__ inline size_t dense32_cta_smem(int L, int G) {
-    const size_t CP = (size_t)NCH * L;
-    return ((CP * 4 /*xs*/ + CP * 4 /*reg*/ + (size_t)NCH * G * 4 * 2 /*regcnt, regmask*/) + 15) & ~(size_t)15;
+#ifndef CSIM_NE
+#define CSIM_NE 4
+#endif
+#define DENSE32_PREF_COLS (CSIM_NE > 1 ? CSIM_NE : 1)
+__host__ __device__ inline size_t dense32_cta_smem(int nch, int L, int G) {
+    const size_t CP = (size_t)nch * L;
+    return ((CP * 4 /*xs*/ + CP * 4 /*reg*/ + (size_t)nch * G * 4 * 2 /*regcnt, regmask*/) + 15) & ~(size_t)15;
 }
-template <int NCH>
-__host__ __device__ inline size_t dense32_warp_smem(int E, int L, int kmax, bool model) {
-    const size_t CP = (size_t)NCH * L;
-    size_t n = CP * 4 * 2 /*pw | bp, bpp*/ + (size_t)E * 4 /*tally*/ + (size_t)kmax * 4 /*eff*/ + (((size_t)E + 3) & ~(size_t)3) /*mark*/;
-    if (model) n += (size_t)E * 4 * 2 /*prev_tally, votes*/ + CP * 4 /*bw*/ + (size_t)((NCH + 3) & ~3) * 4 /*bwchunk*/;
+__host__ __device__ inline size_t dense32_warp_smem(int E, int nch, int L, int kmax, bool model) {
+    const size_t CP = (size_t)nch * L, Ei = ((size_t)E + 3) & ~(size_t)3, n4 = ((size_t)nch + 3) & ~(size_t)3;
+    size_t n = CP * 4 * 2 /*pw | bp, bpp*/ + (size_t)DENSE32_PREF_COLS * nch * 32 * 4 /*prefix columns*/ + Ei * 4 /*tally*/ +
+               (((size_t)kmax + 3) & ~(size_t)3) * 4 /*eff*/ + Ei /*mark*/;
+    if (model) n += CP * 4 /*bw*/ + n4 * 4 /*bwchunk*/ + Ei * 4 * 2 /*prev_tally, votes*/;
     return (n + 15) & ~(size_t)15;
 }
 
@@ -92,22 +99,33 @@ __global__ void k_round_tables32(RosterDev ro, const DevSet* sets, const double*
     t[c] = A; t[CP + c] = Ap; t[2 * CP + c] = BP; t[3 * CP + c] = BPp;
 }
 
+struct LaneCtx32 {              // per-warp / per-round constants of the draw
+    const float* xs; const int32_t* reg; const float* regcnt; const uint32_t* regmask;
+    const float* pw; const float* bpp; const float* bw; const float* bwchunk;   // FACT: pw = BP, bpp = BP'
+    float nb, bonus, st1p;
+    int C, G, L, nch, step0;
+    bool use_bw;
+};
+
+// exp(-beta |x_e - x_c|) * pw_c for one pair
+template <bool FACT>
+__device__ __forceinline__ float pair32(const LaneCtx32& k, int c, float xe, float ae, float ape) {
+    return FACT ? fminf(ae * k.pw[c], ape * k.bpp[c]) : ex2_approx(fabsf(xe - k.xs[c]) * k.nb) * k.pw[c];
+}
+
 // every term of one score, inline (run-off rounds and the generic re-scan)
 template <bool MODEL, bool FACT>
-__device__ __forceinline__ float full_score32(int e, int c, float xe, float ae, float ape, int ge, float nb, float bonus, float st1p,
-                                              int prev, bool use_bw, const float* xs, const int32_t* reg, const float* pw,
-                                              const float* bpp, const float* bw) {
-    // FACT: pw = BP, bpp = BP';  else pw = per-candidate papabile weight
-    float v = FACT ? fminf(ae * pw[c], ape * bpp[c]) : ex2_approx(fabsf(xe - xs[c]) * nb) * pw[c];
-    if (reg[c] == ge) v += bonus;
+__device__ __forceinline__ float full_score32(const LaneCtx32& k, int e, int c, float xe, float ae, float ape, int ge, int prev) {
+    float v = pair32<FACT>(k, c, xe, ae, ape);
+    if (k.reg[c] == ge) v += k.bonus;
     if (MODEL) {
-        if (use_bw) v += bw[c];
-        if (c == prev) v *= st1p;
+        if (k.use_bw) v += k.bw[c];
+        if (c == prev) v *= k.st1p;
     }
     return c == e ? 0.0f : v;
 }
 
-// Top two tallies by (count desc, index asc) as packed keys (count << 16 | 0xFFFF - index); needs C < 65536.
+// Top two tallies by (count desc, index asc) as packed keys (count << 16 | 0xFFFF - index); needs C < 32768.
 __device__ __forceinline__ void warp_top2(const int32_t* tally, int C, int lane, uint32_t& k1, uint32_t& k2) {
     uint32_t a = 0, b = 0;
     for (int c = lane; c < C; c += CSIM_WARP) {
@@ -124,225 +142,153 @@ __device__ __forceinline__ void warp_top2(const int32_t* tally, int C, int lane,
     k1 = a; k2 = b;
 }
 
-struct LaneCtx32 {              // per-warp / per-round constants of the draw
-    const float* xs; const int32_t* reg; const float* regcnt; const uint32_t* regmask;
-    const float* pw; const float* bpp; const float* bw; const float* bwchunk;   // FACT: pw = BP, bpp = BP'
-    float nb, bonus, st1p;
-    int C, G, L;
-    bool use_bw;
-};
-
-// One full-field draw, chunk length 8 (E <= 136): phase 1 + chunk search + vectorised re-scan.
-template <int NCH, bool MODEL, bool FACT>
-__device__ __forceinline__ int draw_full_lc8(const LaneCtx32& k, int e, float u, int prev, float ae, float ape) {
-    const float xe = FACT ? 0.f : k.xs[e];
-    const int ge = k.reg[e];
-    const float nb = k.nb;
-    const int je = e >> 3;
-    // the self score, removed from its chunk (model.py:418-424); same expression as phase 1 so it cancels
-    float see = (FACT ? fminf(ae * k.pw[e], ape * k.bpp[e]) : k.pw[e]) + k.bonus;
-    if (MODEL && k.use_bw) see += k.bw[e];
-    int jp = -1; float sadd = 0.f;
-    if (MODEL && prev >= 0 && prev != e) {               // stickiness: + st * s[e, prev] in prev's chunk (model.py:357-367)
-        float sp = FACT ? fminf(ae * k.pw[prev], ape * k.bpp[prev]) : ex2_approx(fabsf(xe - k.xs[prev]) * nb) * k.pw[prev];
-        if (k.reg[prev] == ge) sp += k.bonus;
-        if (k.use_bw) sp += k.bw[prev];
-        sadd = sp * (k.st1p - 1.0f);
-        jp = prev >> 3;
-    }
-    // ---------------- phase 1: chunk sums -----------------------------------------------------------
-    float cs[NCH];
-    float S = 0.f;
-    const unsigned long long a2 = f2_pack(ae, ae), ap2 = f2_pack(ape, ape);
+// Phase 1 of one chunk for NE electors of a lane: acc0/acc1 += the exponential part of the chunk.
+// The candidate operands are loaded once (warp-uniform 128-bit loads) and reused by all NE electors.
+template <int NE, int LC, bool FACT>
+__device__ __forceinline__ void chunk_acc(const LaneCtx32& k, int j, const float (&xe)[NE], const unsigned long long (&a2)[NE],
+                                          const unsigned long long (&ap2)[NE], float (&acc0)[NE], float (&acc1)[NE]) {
+    const int L = LC > 0 ? LC : k.L;
+    if (FACT) {
+        unsigned long long acc[NE];
 #pragma unroll
-    for (int j = 0; j < NCH; ++j) {
-        float acc0 = (j == je) ? -see : 0.f;
-        float acc1 = (MODEL && j == jp) ? sadd : 0.f;
-        if (FACT) {
-            unsigned long long acc = f2_pack(acc0, acc1);
-            const ulonglong2* b4 = reinterpret_cast<const ulonglong2*>(k.pw + j * 8);
-            const ulonglong2* c4 = reinterpret_cast<const ulonglong2*>(k.bpp + j * 8);
+        for (int t = 0; t < NE; ++t) acc[t] = f2_pack(acc0[t], acc1[t]);
+        const ulonglong2* b4 = reinterpret_cast<const ulonglong2*>(k.pw + j * L);
+        const ulonglong2* c4 = reinterpret_cast<const ulonglong2*>(k.bpp + j * L);
+#pragma unroll 2
+        for (int i = 0; i < (L >> 2); ++i) {
+            const ulonglong2 b = b4[i], c = c4[i];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const ulonglong2 b = b4[i], c = c4[i];
-                unsigned long long t1 = f2_mul(a2, b.x), t2 = f2_mul(ap2, c.x);
-                acc = f2_add(acc, f2_pack(fminf(f2_lo(t1), f2_lo(t2)), fminf(f2_hi(t1), f2_hi(t2))));
-                t1 = f2_mul(a2, b.y); t2 = f2_mul(ap2, c.y);
-                acc = f2_add(acc, f2_pack(fminf(f2_lo(t1), f2_lo(t2)), fminf(f2_hi(t1), f2_hi(t2))));
-            }
-            acc0 = f2_lo(acc); acc1 = f2_hi(acc);
-        } else {
-            const float4* x4 = reinterpret_cast<const float4*>(k.xs + j * 8);
-            const float4* p4 = reinterpret_cast<const float4*>(k.pw + j * 8);
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const float4 xv = x4[i], pv = p4[i];
-                acc0 = fmaf(ex2_approx(fabsf(xe - xv.x) * nb), pv.x, acc0);
-                acc1 = fmaf(ex2_approx(fabsf(xe - xv.y) * nb), pv.y, acc1);
-                acc0 = fmaf(ex2_approx(fabsf(xe - xv.z) * nb), pv.z, acc0);
-                acc1 = fmaf(ex2_approx(fabsf(xe - xv.w) * nb), pv.w, acc1);
+            for (int t = 0; t < NE; ++t) {
+                unsigned long long t1 = f2_mul(a2[t], b.x), t2 = f2_mul(ap2[t], c.x);
+                acc[t] = f2_add(acc[t], f2_pack(fminf(f2_lo(t1), f2_lo(t2)), fminf(f2_hi(t1), f2_hi(t2))));
+                t1 = f2_mul(a2[t], b.y); t2 = f2_mul(ap2[t], c.y);
+                acc[t] = f2_add(acc[t], f2_pack(fminf(f2_lo(t1), f2_lo(t2)), fminf(f2_hi(t1), f2_hi(t2))));
             }
         }
-        float s = fmaf(k.bonus, k.regcnt[j * k.G + ge], acc0 + acc1);    // regional bonus of the chunk (model.py:322-323)
-        if (MODEL && k.use_bw) s += k.bwchunk[j];                        // bandwagon of the chunk (model.py:354)
-        cs[j] = s;
-        S += s;
-    }
-    if (!(S > 0.0f)) {            // all scores vanished: the reference makes the row uniform INCLUDING self (model.py:447-449)
-        const int j = (int)(u * (float)k.C);
-        return j < k.C ? j : k.C - 1;
-    }
-    // ---------------- phase 2a: the chunk whose prefix crosses u * S --------------------------------
-    const float tgt = u * S;
-    float prefix = 0.f, below = 0.f;
-    int jstar = 0;
 #pragma unroll
-    for (int j = 0; j < NCH; ++j) {
-        prefix += cs[j];
-        const bool le = prefix <= tgt;
-        below = le ? prefix : below;
-        jstar += le ? 1 : 0;
+        for (int t = 0; t < NE; ++t) { acc0[t] = f2_lo(acc[t]); acc1[t] = f2_hi(acc[t]); }
+    } else {
+        const float4* x4 = reinterpret_cast<const float4*>(k.xs + j * L);
+        const float4* p4 = reinterpret_cast<const float4*>(k.pw + j * L);
+        const float nb = k.nb;
+#pragma unroll 2
+        for (int i = 0; i < (L >> 2); ++i) {
+            const float4 xv = x4[i], pv = p4[i];
+#pragma unroll
+            for (int t = 0; t < NE; ++t) {
+                acc0[t] = fmaf(ex2_approx(fabsf(xe[t] - xv.x) * nb), pv.x, acc0[t]);
+                acc1[t] = fmaf(ex2_approx(fabsf(xe[t] - xv.y) * nb), pv.y, acc1[t]);
+                acc0[t] = fmaf(ex2_approx(fabsf(xe[t] - xv.z) * nb), pv.z, acc0[t]);
+                acc1[t] = fmaf(ex2_approx(fabsf(xe[t] - xv.w) * nb), pv.w, acc1[t]);
+            }
+        }
     }
-    const int last_chunk = (k.C - 1) >> 3;
-    jstar = jstar > last_chunk ? last_chunk : jstar;
-    // ---------------- phase 2b: re-scan that chunk, every term inline, roster order ------------------
-    const int c0 = jstar * 8;
-    // FACT: (xa, xb) hold BP', (pa, pb) hold BP;  else x and pw
-    const float* src_x = FACT ? k.bpp : k.xs;
-    const float4 xa = *reinterpret_cast<const float4*>(src_x + c0), xb = *reinterpret_cast<const float4*>(src_x + c0 + 4);
-    const float4 pa = *reinterpret_cast<const float4*>(k.pw + c0), pb = *reinterpret_cast<const float4*>(k.pw + c0 + 4);
-    const uint32_t rm = k.regmask[jstar * k.G + ge];                     // bit i: candidate c0+i is of e's region
-    const uint32_t dm = (jstar == je) ? (1u << (e & 7)) : 0u;            // bit i: candidate c0+i is e itself
-    uint32_t pm = 0;
-    float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
-    if (MODEL) {
-        if (prev >= 0 && (prev >> 3) == jstar) pm = 1u << (prev & 7);
-        if (k.use_bw) { ba = *reinterpret_cast<const float4*>(k.bw + c0); bb = *reinterpret_cast<const float4*>(k.bw + c0 + 4); }
-    }
-    float cum = below;
-    int cnt = 0;
-#define CSIM_RESCAN(i, xv, pv, bv)                                              \
-    {                                                                           \
-        const float ex = FACT ? fminf(ae * (pv), ape * (xv)) : ex2_approx(fabsf(xe - (xv)) * nb) * (pv); \
-        float v = ex + (((rm >> (i)) & 1u) ? k.bonus : 0.0f);                   \
-        if (MODEL) { v += (bv); if ((pm >> (i)) & 1u) v *= k.st1p; }            \
-        if ((dm >> (i)) & 1u) v = 0.0f;                                         \
-        cum += v;                                                               \
-        cnt += (cum <= tgt) ? 1 : 0;                                            \
-    }
-    CSIM_RESCAN(0, xa.x, pa.x, ba.x) CSIM_RESCAN(1, xa.y, pa.y, ba.y) CSIM_RESCAN(2, xa.z, pa.z, ba.z) CSIM_RESCAN(3, xa.w, pa.w, ba.w)
-    CSIM_RESCAN(4, xb.x, pb.x, bb.x) CSIM_RESCAN(5, xb.y, pb.y, bb.y) CSIM_RESCAN(6, xb.z, pb.z, bb.z) CSIM_RESCAN(7, xb.w, pb.w, bb.w)
-#undef CSIM_RESCAN
-    int vote = c0 + cnt;                                 // == first c with cum > tgt (searchsorted 'right', simulate.py:153)
-    const int maxc = min(c0 + 7, k.C - 1);
-    vote = vote > maxc ? maxc : vote;                    // rounding at the chunk's upper edge
-    if (vote == e) vote = e > 0 ? e - 1 : (k.C > 1 ? 1 : 0);
-    return vote;
 }
 
-// Generic chunk length (runtime L, multiple of 4): same algorithm, scalar re-scan.
-template <int NCH, bool MODEL, bool FACT>
-__device__ __forceinline__ int draw_full_generic(const LaneCtx32& k, int e, float u, int prev, float ae, float ape) {
-    const int L = k.L, C = k.C;
-    const float xe = FACT ? 0.f : k.xs[e];
-    const int ge = k.reg[e];
-    const float nb = k.nb;
-    const int je = e / L;
-    float see = (FACT ? fminf(ae * k.pw[e], ape * k.bpp[e]) : k.pw[e]) + k.bonus;
+// Per-elector corrections that enter the chunk sums: the self score (removed) and stickiness (added).
+template <bool MODEL, bool FACT>
+__device__ __forceinline__ void corrections32(const LaneCtx32& k, int e, float xe, float ae, float ape, int ge, int prev,
+                                              float& see, float& sadd, int& jp) {
+    see = pair32<FACT>(k, e, xe, ae, ape) + k.bonus;      // same expression as phase 1, so it cancels (model.py:418-424)
     if (MODEL && k.use_bw) see += k.bw[e];
-    int jp = -1; float sadd = 0.f;
-    if (MODEL && prev >= 0 && prev != e) {
-        float sp = FACT ? fminf(ae * k.pw[prev], ape * k.bpp[prev]) : ex2_approx(fabsf(xe - k.xs[prev]) * nb) * k.pw[prev];
+    jp = -1; sadd = 0.f;
+    if (MODEL && prev >= 0 && prev != e) {                // + st * s[e, prev] (model.py:357-367)
+        float sp = pair32<FACT>(k, prev, xe, ae, ape);
         if (k.reg[prev] == ge) sp += k.bonus;
         if (k.use_bw) sp += k.bw[prev];
         sadd = sp * (k.st1p - 1.0f);
-        jp = prev / L;
+        jp = prev / k.L;
     }
-    float cs[NCH];
-    float S = 0.f;
-    const unsigned long long a2 = f2_pack(ae, ae), ap2 = f2_pack(ape, ape);
-#pragma unroll
-    for (int j = 0; j < NCH; ++j) {
-        float acc0 = (j == je) ? -see : 0.f;
-        float acc1 = (MODEL && j == jp) ? sadd : 0.f;
-        if (FACT) {
-            unsigned long long acc = f2_pack(acc0, acc1);
-            const ulonglong2* b4 = reinterpret_cast<const ulonglong2*>(k.pw + j * L);
-            const ulonglong2* c4 = reinterpret_cast<const ulonglong2*>(k.bpp + j * L);
-#pragma unroll 2
-            for (int i = 0; i < (L >> 2); ++i) {
-                const ulonglong2 b = b4[i], c = c4[i];
-                unsigned long long t1 = f2_mul(a2, b.x), t2 = f2_mul(ap2, c.x);
-                acc = f2_add(acc, f2_pack(fminf(f2_lo(t1), f2_lo(t2)), fminf(f2_hi(t1), f2_hi(t2))));
-                t1 = f2_mul(a2, b.y); t2 = f2_mul(ap2, c.y);
-                acc = f2_add(acc, f2_pack(fminf(f2_lo(t1), f2_lo(t2)), fminf(f2_hi(t1), f2_hi(t2))));
-            }
-            acc0 = f2_lo(acc); acc1 = f2_hi(acc);
-        } else {
-            const float4* x4 = reinterpret_cast<const float4*>(k.xs + j * L);
-            const float4* p4 = reinterpret_cast<const float4*>(k.pw + j * L);
-            for (int i = 0; i < (L >> 2); ++i) {
-                const float4 xv = x4[i], pv = p4[i];
-                acc0 = fmaf(ex2_approx(fabsf(xe - xv.x) * nb), pv.x, acc0);
-                acc1 = fmaf(ex2_approx(fabsf(xe - xv.y) * nb), pv.y, acc1);
-                acc0 = fmaf(ex2_approx(fabsf(xe - xv.z) * nb), pv.z, acc0);
-                acc1 = fmaf(ex2_approx(fabsf(xe - xv.w) * nb), pv.w, acc1);
-            }
-        }
-        float s = fmaf(k.bonus, k.regcnt[j * k.G + ge], acc0 + acc1);
-        if (MODEL && k.use_bw) s += k.bwchunk[j];
-        cs[j] = s;
-        S += s;
-    }
-    if (!(S > 0.0f)) {
+}
+
+// Phase 2: given the prefix sums over chunks (pref[j * pstride], j < nch) and their total S, draw the vote.
+template <int LC, bool MODEL, bool FACT>
+__device__ __forceinline__ int finish_draw(const LaneCtx32& k, const float* pref, int pstride, int e, float u, float S,
+                                           float xe, float ae, float ape, int ge, int prev) {
+    const int C = k.C, L = LC > 0 ? LC : k.L, nch = k.nch;
+    if (!(S > 0.0f)) {            // all scores vanished: the reference makes the row uniform INCLUDING self (model.py:447-449)
         const int j = (int)(u * (float)C);
         return j < C ? j : C - 1;
     }
     const float tgt = u * S;
-    float prefix = 0.f, below = 0.f;
-    int jstar = 0;
-#pragma unroll
-    for (int j = 0; j < NCH; ++j) {
-        prefix += cs[j];
-        const bool le = prefix <= tgt;
-        below = le ? prefix : below;
-        jstar += le ? 1 : 0;
+    int pos = 0;                  // number of chunks whose prefix is <= tgt
+    for (int step = k.step0; step > 0; step >>= 1) {
+        const int np = pos + step;
+        if (np <= nch && pref[(np - 1) * pstride] <= tgt) pos = np;
     }
     const int last_chunk = (C - 1) / L;
-    jstar = jstar > last_chunk ? last_chunk : jstar;
+    const int jstar = pos > last_chunk ? last_chunk : pos;
+    const float below = jstar > 0 ? pref[(jstar - 1) * pstride] : 0.0f;
     const int c0 = jstar * L;
     float cum = below;
     int cnt = 0;
-    for (int i = 0; i < L; ++i) {
-        const int c = c0 + i;
-        const float v = c < C ? full_score32<MODEL, FACT>(e, c, xe, ae, ape, ge, nb, k.bonus, k.st1p, prev, k.use_bw, k.xs, k.reg, k.pw, k.bpp, k.bw) : 0.0f;
-        cum += v;
-        cnt += (cum <= tgt) ? 1 : 0;
+    if (LC == 8) {
+        // vectorised re-scan.  FACT: (xa, xb) hold BP', (pa, pb) hold BP;  else x and pw
+        const float* src_x = FACT ? k.bpp : k.xs;
+        const float4 xa = *reinterpret_cast<const float4*>(src_x + c0), xb = *reinterpret_cast<const float4*>(src_x + c0 + 4);
+        const float4 pa = *reinterpret_cast<const float4*>(k.pw + c0), pb = *reinterpret_cast<const float4*>(k.pw + c0 + 4);
+        const uint32_t rm = k.regmask[jstar * k.G + ge];                     // bit i: candidate c0+i is of e's region
+        const uint32_t dm = (jstar == (e >> 3)) ? (1u << (e & 7)) : 0u;      // bit i: candidate c0+i is e itself
+        uint32_t pm = 0;
+        float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
+        if (MODEL) {
+            if (prev >= 0 && (prev >> 3) == jstar) pm = 1u << (prev & 7);
+            if (k.use_bw) { ba = *reinterpret_cast<const float4*>(k.bw + c0); bb = *reinterpret_cast<const float4*>(k.bw + c0 + 4); }
+        }
+        const float nb = k.nb;
+#define CSIM_RESCAN(i, xv, pv, bv)                                              \
+        {                                                                       \
+            const float ex = FACT ? fminf(ae * (pv), ape * (xv)) : ex2_approx(fabsf(xe - (xv)) * nb) * (pv); \
+            float v = ex + (((rm >> (i)) & 1u) ? k.bonus : 0.0f);               \
+            if (MODEL) { v += (bv); if ((pm >> (i)) & 1u) v *= k.st1p; }        \
+            if ((dm >> (i)) & 1u) v = 0.0f;                                     \
+            cum += v;                                                           \
+            cnt += (cum <= tgt) ? 1 : 0;                                        \
+        }
+        CSIM_RESCAN(0, xa.x, pa.x, ba.x) CSIM_RESCAN(1, xa.y, pa.y, ba.y) CSIM_RESCAN(2, xa.z, pa.z, ba.z) CSIM_RESCAN(3, xa.w, pa.w, ba.w)
+        CSIM_RESCAN(4, xb.x, pb.x, bb.x) CSIM_RESCAN(5, xb.y, pb.y, bb.y) CSIM_RESCAN(6, xb.z, pb.z, bb.z) CSIM_RESCAN(7, xb.w, pb.w, bb.w)
+#undef CSIM_RESCAN
+    } else {
+        for (int i = 0; i < L; ++i) {
+            const int c = c0 + i;
+            const float v = c < C ? full_score32<MODEL, FACT>(k, e, c, xe, ae, ape, ge, prev) : 0.0f;
+            cum += v;
+            cnt += (cum <= tgt) ? 1 : 0;
+        }
     }
-    int vote = c0 + cnt;
+    int vote = c0 + cnt;                                 // == first c with cum > tgt (searchsorted 'right', simulate.py:153)
     const int maxc = min(c0 + L - 1, C - 1);
-    vote = vote > maxc ? maxc : vote;
+    vote = vote > maxc ? maxc : vote;                    // rounding at the chunk's upper edge
     if (vote == e) vote = e > 0 ? e - 1 : (C > 1 ? 1 : 0);
     return vote;
 }
 
-template <int NCH, int LC, bool MODEL, bool FACT>
-__global__ void __launch_bounds__(256, LC == 8 ? 3 : 1) k_trials_dense32(Dense32Args a) {
+#ifndef CSIM_NE
+#define CSIM_NE 4          // electors of a lane evaluated together in phase 1 (1, 2 or 4)
+#endif
+#ifndef CSIM_MINB
+#define CSIM_MINB 2        // resident CTAs per SM the register allocation is bounded for
+#endif
+template <int LC, bool MODEL, bool FACT>
+__global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a) {
+    constexpr int NE = CSIM_NE;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int E = a.ro.E, C = E, R = a.b.R, G = a.ro.G;
     const int L = LC > 0 ? LC : a.L;
-    const int CP = NCH * L;
+    const int nch = a.nch;
+    const int CP = nch * L;
+    const int Ei = (E + 3) & ~3;
     // ---- CTA-shared roster tables ------------------------------------------------------------
     float* xs = (float*)smem_raw;
     int32_t* reg = (int32_t*)(xs + CP);
     float* regcnt = (float*)(reg + CP);
-    uint32_t* regmask = (uint32_t*)(regcnt + NCH * G);
+    uint32_t* regmask = (uint32_t*)(regcnt + nch * G);
     for (int c = threadIdx.x; c < CP; c += blockDim.x) {
         xs[c] = c < C ? a.ro.x32[c] : 0.0f;
         reg[c] = c < C ? a.ro.region[c] : -1;
     }
-    for (int i = threadIdx.x; i < NCH * G; i += blockDim.x) {
+    for (int i = threadIdx.x; i < nch * G; i += blockDim.x) {
         const int j = i / G, g = i - j * G;
         int n = 0; uint32_t m = 0;
         for (int c = j * L; c < (j + 1) * L && c < C; ++c)
@@ -355,34 +301,39 @@ __global__ void __launch_bounds__(256, LC == 8 ? 3 : 1) k_trials_dense32(Dense32
     // 16-byte aligned float arrays first (they are read with 128-bit loads), then the int arrays
     float* pw = (float*)base;                   base += sizeof(float) * CP;      // FACT: BP of the current round
     float* bpp = (float*)base;                  base += sizeof(float) * CP;      // FACT: BP'
+    float* pref = (float*)base;                 base += sizeof(float) * DENSE32_PREF_COLS * nch * 32;   // prefix columns [t][j][lane]
     float* bw = nullptr; float* bwchunk = nullptr;
     if (MODEL) {
         bw = (float*)base;                      base += sizeof(float) * CP;
-        bwchunk = (float*)base;                 base += sizeof(float) * ((NCH + 3) & ~3);
+        bwchunk = (float*)base;                 base += sizeof(float) * ((nch + 3) & ~3);
     }
-    int32_t* tally = (int32_t*)base;            base += sizeof(int32_t) * E;
+    int32_t* tally = (int32_t*)base;            base += sizeof(int32_t) * Ei;
     int32_t* prev_tally = nullptr; int32_t* votes = nullptr;
     if (MODEL) {
-        prev_tally = (int32_t*)base;            base += sizeof(int32_t) * E;
-        votes = (int32_t*)base;                 base += sizeof(int32_t) * E;
+        prev_tally = (int32_t*)base;            base += sizeof(int32_t) * Ei;
+        votes = (int32_t*)base;                 base += sizeof(int32_t) * Ei;
     }
-    int32_t* eff = (int32_t*)base;              base += sizeof(int32_t) * a.kmax;
+    int32_t* eff = (int32_t*)base;              base += sizeof(int32_t) * ((a.kmax + 3) & ~3);
     uint8_t* mark = (uint8_t*)base;
     __syncthreads();   // the only block barrier: roster tables are read-only from here on
 
     const uint64_t n_trials = (uint64_t)a.b.n_sets * a.b.n_sims;
     const uint64_t warp_global = (uint64_t)blockIdx.x * a.warps_per_cta + wib;
     const uint64_t n_warps = (uint64_t)gridDim.x * a.warps_per_cta;
-    const int m_quads = E >> 7;                              // whole quads per lane
+    const int m_quads = E >> 7;                              // whole Philox quads per lane
     const int n_main = 4 * m_quads;
-    const int e_single0 = 128 * m_quads + lane;
+    const int e_left0 = 128 * m_quads;                       // first elector that does not fill a quad per lane
+    const int n_left = E - e_left0;
+    const int e_single0 = e_left0 + lane;
     const int n_single = e_single0 < E ? (E - e_single0 + 31) >> 5 : 0;
     const int n_slots = n_main + n_single;
     const bool top2_ok = C >= 2 && C < 32768;
 
     LaneCtx32 kx;
     kx.xs = xs; kx.reg = reg; kx.regcnt = regcnt; kx.regmask = regmask; kx.pw = pw; kx.bpp = bpp; kx.bw = bw; kx.bwchunk = bwchunk;
-    kx.C = C; kx.G = G; kx.L = L; kx.use_bw = false; kx.nb = 0.f; kx.bonus = 0.f; kx.st1p = 1.f;
+    kx.C = C; kx.G = G; kx.L = L; kx.nch = nch; kx.use_bw = false; kx.nb = 0.f; kx.bonus = 0.f; kx.st1p = 1.f;
+    kx.step0 = 1;
+    while (kx.step0 * 2 <= nch) kx.step0 *= 2;
 
     int cur_set = -1;
     float bw_strength = 0.f;
@@ -410,6 +361,7 @@ __global__ void __launch_bounds__(256, LC == 8 ? 3 : 1) k_trials_dense32(Dense32
             __syncwarp();
         }
         const float* nbeta = a.nbeta + (size_t)set * R;
+        const uint32_t s_lo = (uint32_t)sim, s_hi = (uint32_t)(sim >> 32);
         const bool fast2 = (k == 2) && top2_ok;                  // two-candidate run-off: O(1) closing
         bool have_eff = false, have_prev = false;
         int winner = -1, rounds = 0, reason = CSIM_REASON_MAX_ROUNDS;
@@ -434,7 +386,7 @@ __global__ void __launch_bounds__(256, LC == 8 ? 3 : 1) k_trials_dense32(Dense32
                         const float inv = 1.0f / (float)mx;
                         for (int c = lane; c < C; c += 32) bw[c] = (float)prev_tally[c] * inv * bw_strength;
                         __syncwarp();
-                        if (lane < NCH) {
+                        if (lane < nch) {
                             float s = 0.f;
                             for (int c = lane * L; c < (lane + 1) * L; ++c) s += bw[c];
                             bwchunk[lane] = s;
@@ -445,60 +397,160 @@ __global__ void __launch_bounds__(256, LC == 8 ? 3 : 1) k_trials_dense32(Dense32
             for (int c = lane; c < C; c += 32) tally[c] = 0;
             __syncwarp();
 
-            uint32_t w[4] = {0, 0, 0, 0};
             int cnt0 = 0;                                        // run-off (fast2): this lane's votes for ef0
-            for (int n = 0; n < n_slots; ++n) {
-                int e, q; bool gen;
-                if (n < n_main) { q = lane + 32 * (n >> 2); e = 4 * q + (n & 3); gen = (n & 3) == 0; }
-                else { e = e_single0 + 32 * (n - n_main); q = e >> 2; gen = true; }
-                if (gen) philox4x32_10((uint32_t)sim, (uint32_t)(sim >> 32), (uint32_t)r, (uint32_t)q, a.b.seed_lo, a.b.seed_hi, w);
-                const int sel = e & 3;
-                const uint32_t wa = sel == 0 ? w[0] : (sel == 1 ? w[1] : (sel == 2 ? w[2] : w[3]));
-                const float u = u24_from_word(wa);
-                const int prev = (MODEL && have_prev && has_sticky) ? votes[e] : -1;
-                float ae = 0.f, ape = 0.f;
-                if (FACT) { ae = __ldg(tabA + e); ape = __ldg(tabA + CP + e); }
-                int vote;
-                if (!have_eff) {
-                    if (LC == 8) vote = draw_full_lc8<NCH, MODEL, FACT>(kx, e, u, prev, ae, ape);
-                    else vote = draw_full_generic<NCH, MODEL, FACT>(kx, e, u, prev, ae, ape);
-                    atomicAdd(&tally[vote], 1);
-                } else if (fast2) {
-                    // ---------------- two-candidate run-off: columns 0 and 1, renormalised (simulate.py:144-154)
-                    const float xe = FACT ? 0.f : xs[e]; const int ge = reg[e];
-                    const float v0 = full_score32<MODEL, FACT>(e, 0, xe, ae, ape, ge, kx.nb, kx.bonus, kx.st1p, prev, kx.use_bw, xs, reg, pw, bpp, bw);
-                    const float v1 = full_score32<MODEL, FACT>(e, 1, xe, ae, ape, ge, kx.nb, kx.bonus, kx.st1p, prev, kx.use_bw, xs, reg, pw, bpp, bw);
-                    const float sum = v0 + v1;
-                    int j;
-                    if (!(sum > 0.0f)) j = (u * 2.0f >= 1.0f) ? 1 : 0;       // simulate.py:151 uniform fallback
-                    else j = (v0 > u * sum || !(v1 > 0.0f)) ? 0 : 1;
-                    cnt0 += (j == 0);
-                    vote = j == 0 ? ef0 : ef1;
-                } else {
-                    // ---------------- k-candidate run-off (generic) --------------------------------------------
-                    const float xe = FACT ? 0.f : xs[e]; const int ge = reg[e];
-                    float sum = 0.f;
-                    for (int j = 0; j < k; ++j)
-                        sum += full_score32<MODEL, FACT>(e, j, xe, ae, ape, ge, kx.nb, kx.bonus, kx.st1p, prev, kx.use_bw, xs, reg, pw, bpp, bw);
-                    int jsel;
-                    if (!(sum > 0.0f)) {
-                        jsel = (int)(u * (float)k);
-                    } else {
-                        const float tgt = u * sum;
-                        float cum = 0.f; jsel = -1; int lastpos = 0;
-                        for (int j = 0; j < k; ++j) {
-                            const float v = full_score32<MODEL, FACT>(e, j, xe, ae, ape, ge, kx.nb, kx.bonus, kx.st1p, prev, kx.use_bw, xs, reg, pw, bpp, bw);
-                            cum += v;
-                            if (v > 0.0f) lastpos = j;
-                            if (jsel < 0 && v > 0.0f && cum > tgt) jsel = j;
+            if (!have_eff) {
+                // =============== full-field round: NE electors of a lane at once =====================
+                for (int qi = 0; qi < m_quads; ++qi) {
+                    const int q = lane + 32 * qi;
+                    uint32_t w[4];
+                    philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)q, a.b.seed_lo, a.b.seed_hi, w);
+#pragma unroll 1
+                    for (int g = 0; g < 4 / NE; ++g) {
+                        const int e0 = 4 * q + NE * g;
+                        float xe[NE], ae[NE], ape[NE], see[NE], sadd[NE], run[NE];
+                        int ge[NE], prev[NE], jp[NE];
+                        unsigned long long a2[NE], ap2[NE];
+                        const float* rc[NE];
+#pragma unroll
+                        for (int i = 0; i < NE; ++i) {
+                            ae[i] = FACT ? __ldg(tabA + e0 + i) : 0.f;
+                            ape[i] = FACT ? __ldg(tabA + CP + e0 + i) : 0.f;
+                            xe[i] = FACT ? 0.f : xs[e0 + i];
+                            ge[i] = reg[e0 + i];
+                            prev[i] = (MODEL && have_prev && has_sticky) ? votes[e0 + i] : -1;
+                            corrections32<MODEL, FACT>(kx, e0 + i, xe[i], ae[i], ape[i], ge[i], prev[i], see[i], sadd[i], jp[i]);
+                            a2[i] = f2_pack(ae[i], ae[i]); ap2[i] = f2_pack(ape[i], ape[i]);
+                            run[i] = 0.f;
+                            rc[i] = regcnt + ge[i];
                         }
-                        if (jsel < 0) jsel = lastpos;
+                        const int je = e0 / L;                   // the electors of a group share their chunk (L % 4 == 0)
+                        float* pcol = pref + lane;
+#pragma unroll 1
+                        for (int j = 0; j < nch; ++j) {
+                            float acc0[NE], acc1[NE];
+#pragma unroll
+                            for (int i = 0; i < NE; ++i) {
+                                acc0[i] = (j == je) ? -see[i] : 0.f;
+                                acc1[i] = (MODEL && j == jp[i]) ? sadd[i] : 0.f;
+                            }
+                            chunk_acc<NE, LC, FACT>(kx, j, xe, a2, ap2, acc0, acc1);
+#pragma unroll
+                            for (int i = 0; i < NE; ++i) {
+                                float s = fmaf(kx.bonus, *rc[i], acc0[i] + acc1[i]);       // regional bonus (model.py:322-323)
+                                if (MODEL && kx.use_bw) s += bwchunk[j];                  // bandwagon (model.py:354)
+                                run[i] += s;
+                                pcol[i * nch * 32] = run[i];
+                                rc[i] += G;
+                            }
+                            pcol += 32;
+                        }
+#pragma unroll 1
+                        for (int i = 0; i < NE; ++i) {
+                            const int wi = NE * g + i;
+                            const uint32_t wa = wi == 0 ? w[0] : (wi == 1 ? w[1] : (wi == 2 ? w[2] : w[3]));
+                            float S = run[0], xei = xe[0], aei = ae[0], apei = ape[0]; int gei = ge[0], pvi = prev[0];
+#pragma unroll
+                            for (int m = 1; m < NE; ++m)
+                                if (i == m) { S = run[m]; xei = xe[m]; aei = ae[m]; apei = ape[m]; gei = ge[m]; pvi = prev[m]; }
+                            const int vote = finish_draw<LC, MODEL, FACT>(kx, pref + (size_t)i * nch * 32 + lane, 32, e0 + i,
+                                                                          u24_from_word(wa), S, xei, aei, apei, gei, pvi);
+                            atomicAdd(&tally[vote], 1);
+                            if (MODEL) votes[e0 + i] = vote;   // read only by this lane for its own electors: in-place is safe
+                        }
                     }
-                    if (jsel >= k) jsel = k - 1;
-                    vote = eff[jsel];
-                    atomicAdd(&tally[vote], 1);
                 }
-                if (MODEL) votes[e] = vote;      // read only by this lane for its own electors: in-place update is safe
+                // =============== leftover electors: P lanes per elector, every P-th chunk each ========
+                for (int gb = 0; gb < n_left; gb += 32) {
+                    const int n_it = min(32, n_left - gb);
+                    int P = 1;
+                    while (P * 2 * n_it <= 32) P *= 2;
+                    const int el = lane / P, sub = lane - el * P;
+                    const bool act = el < n_it;
+                    const int e = e_left0 + gb + (act ? el : 0);
+                    uint32_t w[4];
+                    philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)(e >> 2), a.b.seed_lo, a.b.seed_hi, w);
+                    const int sel = e & 3;
+                    const uint32_t wa = sel == 0 ? w[0] : (sel == 1 ? w[1] : (sel == 2 ? w[2] : w[3]));
+                    float xe1[1], see, sadd; int jp;
+                    float ae = 0.f, ape = 0.f;
+                    if (FACT) { ae = __ldg(tabA + e); ape = __ldg(tabA + CP + e); }
+                    xe1[0] = FACT ? 0.f : xs[e];
+                    const int ge = reg[e];
+                    const int prev = (MODEL && have_prev && has_sticky) ? votes[e] : -1;
+                    corrections32<MODEL, FACT>(kx, e, xe1[0], ae, ape, ge, prev, see, sadd, jp);
+                    const unsigned long long a2[1] = {f2_pack(ae, ae)}, ap2[1] = {f2_pack(ape, ape)};
+                    const int je = e / L;
+                    float* cl = pref + el * nch;                 // this elector's chunk sums, then prefixes
+                    __syncwarp();
+                    if (act) {
+                        for (int j = sub; j < nch; j += P) {
+                            float acc0[1] = {(j == je) ? -see : 0.f}, acc1[1] = {(MODEL && j == jp) ? sadd : 0.f};
+                            chunk_acc<1, LC, FACT>(kx, j, xe1, a2, ap2, acc0, acc1);
+                            float s = fmaf(kx.bonus, regcnt[j * G + ge], acc0[0] + acc1[0]);
+                            if (MODEL && kx.use_bw) s += bwchunk[j];
+                            cl[j] = s;
+                        }
+                    }
+                    __syncwarp();
+                    if (act && sub == 0) {
+                        float run = 0.f;
+                        for (int j = 0; j < nch; ++j) { run += cl[j]; cl[j] = run; }
+                        const int vote = finish_draw<LC, MODEL, FACT>(kx, cl, 1, e, u24_from_word(wa), run, xe1[0], ae, ape, ge, prev);
+                        atomicAdd(&tally[vote], 1);
+                        if (MODEL) votes[e] = vote;
+                    }
+                    __syncwarp();
+                }
+            } else {
+                // =============== run-off round: one elector per slot, first k columns ==================
+                uint32_t w[4] = {0, 0, 0, 0};
+                for (int n = 0; n < n_slots; ++n) {
+                    int e, q; bool gen;
+                    if (n < n_main) { q = lane + 32 * (n >> 2); e = 4 * q + (n & 3); gen = (n & 3) == 0; }
+                    else { e = e_single0 + 32 * (n - n_main); q = e >> 2; gen = true; }
+                    if (gen) philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)q, a.b.seed_lo, a.b.seed_hi, w);
+                    const int sel = e & 3;
+                    const uint32_t wa = sel == 0 ? w[0] : (sel == 1 ? w[1] : (sel == 2 ? w[2] : w[3]));
+                    const float u = u24_from_word(wa);
+                    const int prev = (MODEL && have_prev && has_sticky) ? votes[e] : -1;
+                    float ae = 0.f, ape = 0.f;
+                    if (FACT) { ae = __ldg(tabA + e); ape = __ldg(tabA + CP + e); }
+                    const float xe = FACT ? 0.f : xs[e];
+                    const int ge = reg[e];
+                    int vote;
+                    if (fast2) {
+                        // two-candidate run-off: columns 0 and 1, renormalised (simulate.py:144-154)
+                        const float v0 = full_score32<MODEL, FACT>(kx, e, 0, xe, ae, ape, ge, prev);
+                        const float v1 = full_score32<MODEL, FACT>(kx, e, 1, xe, ae, ape, ge, prev);
+                        const float sum = v0 + v1;
+                        int j;
+                        if (!(sum > 0.0f)) j = (u * 2.0f >= 1.0f) ? 1 : 0;       // simulate.py:151 uniform fallback
+                        else j = (v0 > u * sum || !(v1 > 0.0f)) ? 0 : 1;
+                        cnt0 += (j == 0);
+                        vote = j == 0 ? ef0 : ef1;
+                    } else {
+                        float sum = 0.f;
+                        for (int j = 0; j < k; ++j) sum += full_score32<MODEL, FACT>(kx, e, j, xe, ae, ape, ge, prev);
+                        int jsel;
+                        if (!(sum > 0.0f)) {
+                            jsel = (int)(u * (float)k);
+                        } else {
+                            const float tgt = u * sum;
+                            float cum = 0.f; jsel = -1; int lastpos = 0;
+                            for (int j = 0; j < k; ++j) {
+                                const float v = full_score32<MODEL, FACT>(kx, e, j, xe, ae, ape, ge, prev);
+                                cum += v;
+                                if (v > 0.0f) lastpos = j;
+                                if (jsel < 0 && v > 0.0f && cum > tgt) jsel = j;
+                            }
+                            if (jsel < 0) jsel = lastpos;
+                        }
+                        if (jsel >= k) jsel = k - 1;
+                        vote = eff[jsel];
+                        atomicAdd(&tally[vote], 1);
+                    }
+                    if (MODEL) votes[e] = vote;
+                }
             }
             int n0 = 0, n1 = 0;
             if (have_eff && fast2) {
