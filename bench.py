@@ -104,11 +104,15 @@ def pair_evals(rounds: np.ndarray, E: int, rr: int, k: int) -> int:
     return int(full.sum()) * E * E + int((rounds - full).sum()) * E * k
 
 
-def cpu_oracle_rate(trials: int, threads: int, E: int):
-    """Times the C oracle (oracle/conclave_oracle.c, OpenMP) on `trials` trials of the workload."""
+def cpu_oracle_rate(trials: int, threads: int, E: int, faithful: bool = True):
+    """Times the C oracle (oracle/conclave_oracle.c, OpenMP) on `trials` trials of the workload.
+    faithful=True: the whole E x C matrix (exp included) is re-evaluated per trial per round, as the
+    reference does (src/simulate.py:121, src/model.py:311-486) -- the like-for-like baseline of the
+    dense GPU engine.  faithful=False: the same port with trial-invariant per-round CDF tables."""
     from oracle import conclave_oracle as O
     from oracle import c_oracle as CO
     CO.build()
+    CO.set_faithful(faithful)
     roster = O.synthetic_roster(E)
     mp = O.ModelParams(**CFG2)
     ep = O.EngineParams(max_rounds=20, supermajority_threshold=0.56)
@@ -123,7 +127,9 @@ def reference_arm(args):
     """--impl reference: the CPU implementation of the path on this box's host cores.  The
     reference itself is Python and cannot travel to the GPU box (and /root/reference does not exist
     there), so this is the oracle PORT (kind "port"): the C restatement, OpenMP over all cores,
-    using the same trial-invariant per-round tables a careful CPU implementation would."""
+    re-evaluating the E x C matrix per trial per round exactly as the reference does (the dense
+    formulation the GPU arm is timed on).  The table-optimised variant of the same port is reported
+    beside it (cpu_baseline.table_optimised_value)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -137,6 +143,7 @@ def reference_arm(args):
         er, c, dt = cpu_oracle_rate(per_step, cores, E_HEADLINE)
         t_er.append(er * dt); t_c.append(c * dt); t_dt += dt
     value = sum(t_er) / t_dt
+    tab_er, tab_c, _ = cpu_oracle_rate(max(20000, int(probe_c * 40)), cores, E_HEADLINE, faithful=False)
     line = {
         "impl": "reference", "metric": "elector_rounds_per_sec", "value": value, "unit": "elector-rounds/s",
         "conclaves_per_sec": sum(t_c) / t_dt, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -145,7 +152,9 @@ def reference_arm(args):
         "config": {"workload": f"cfg2 README params, synthetic E={E_HEADLINE}, ref_cli wiring, max_rounds 20",
                    "trials_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": "elector-rounds/s", "cores": cores, "kind": "port",
-                         "sample": f"{per_step} trials per step x {args.steps} steps, C oracle with OpenMP on {cores} threads"},
+                         "sample": f"{per_step} trials per step x {args.steps} steps, C oracle (dense per-trial matrix like the "
+                                   f"reference), OpenMP on {cores} threads",
+                         "table_optimised_value": tab_er},
         "e2e": {"value": value, "unit": "elector-rounds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -166,7 +175,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from conclave_sim_b200 import Engine, make_params, FP32, WIRING_REF_CLI, ENGINE_DENSE
+    from conclave_sim_b200 import Engine, make_params, FP32, WIRING_REF_CLI, ENGINE_DENSE, ENGINE_TABLE
     from conclave_sim_b200.dist import DeviceBatch, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -196,10 +205,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(i: int, reduce: bool = True):
+    def step(i: int, reduce: bool = True, engine: int = ENGINE_DENSE):
         begin, _ = shard_range(n_global, rank, world)
         batch.run([params], sim_id_begin=i * n_global + begin, seed=SEED, wiring=WIRING_REF_CLI,
-                  engine=ENGINE_DENSE, precision=FP32, reduce=reduce)
+                  engine=engine, precision=FP32, reduce=reduce)
 
     for i in range(args.warmup):
         step(i)
@@ -259,6 +268,33 @@ def main():
                 "factorised_pair_body_peak_pairs_per_s": None if peak_fact is None else peak_fact / 2.5 * 1e9,
                 "hbm_writeback_gbs": out_bytes / kern_s * 1e-9}
 
+    # ---- the TABLE engine (trial-invariant per-round CDF tables; what ENGINE_AUTO picks for ref_cli), reported
+    #      SEPARATELY from the dense kernel's value / roofline (never mixed)
+    for i in range(2):
+        step(500 + i, engine=ENGINE_TABLE)
+    barrier()
+    tev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_rounds = 0
+    for i in range(args.steps):
+        flush.zero_()
+        tev[i][0].record()
+        step(502 + i, engine=ENGINE_TABLE)
+        tev[i][1].record()
+        tev[i][1].synchronize()
+        t_rounds += int(batch.totals[0].item())
+    barrier()
+    tt = torch.tensor([sum(a.elapsed_time(b) for a, b in tev), float(t_rounds)], dtype=torch.float64, device=dev)
+    if world > 1:
+        a_ = tt.clone(); dist.all_reduce(a_, op=dist.ReduceOp.MAX)
+        b_ = tt.clone(); dist.all_reduce(b_, op=dist.ReduceOp.SUM)
+        tt = torch.stack([a_[0], b_[1]])
+    table_ms, table_rounds = tt[0].item(), tt[1].item()
+    table_engine = {"value": table_rounds * E / (table_ms * 1e-3), "unit": "elector-rounds/s",
+                    "conclaves_per_sec": n_global * args.steps / (table_ms * 1e-3), "ms_per_step": table_ms / args.steps,
+                    "kernel": "k_trials_table<float> (+ k_base_scores64, k_cdf_tables64, k_f64_to_f32 per step)",
+                    "note": "ref_cli wiring only: the probability matrix is trial-invariant there, so CDF rows are built once per "
+                            "step and a draw is a binary search; NOT comparable with the dense roofline"}
+
     # ---- e2e: the host-buffer public API (roster + params uploaded, results copied back, every step)
     e2e_steps = max(2, min(args.steps, 3))
     begin, _ = shard_range(n_global, rank, world)
@@ -303,6 +339,7 @@ def main():
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": "elector-rounds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "api": "conclave_sim_b200.Engine.run (host buffers) -> csim_run"},
+        "table_engine": table_engine,
         "gpu_launches": int(launches1 - launches0),
         "clocks": clocks,
         "mean_rounds": all_rounds / (n_global * args.steps),
@@ -312,8 +349,11 @@ def main():
         probe_er, probe_c, _ = cpu_oracle_rate(2000, cores, E)
         n_cpu = max(2000, int(probe_c * 12.0))       # ~12 s of CPU work
         er, c, dt = cpu_oracle_rate(n_cpu, cores, E)
+        tab_er, _, _ = cpu_oracle_rate(max(20000, int(probe_c * 40)), cores, E, faithful=False)
         line["cpu_baseline"] = {"value": er, "unit": "elector-rounds/s", "conclaves_per_sec": c, "cores": cores, "kind": "port",
-                                "sample": f"{n_cpu} trials of the same workload, C oracle (OpenMP, {cores} threads), {dt:.1f} s",
+                                "sample": f"{n_cpu} trials of the same workload, C oracle re-evaluating the E x C matrix per trial "
+                                          f"per round like the reference (OpenMP, {cores} threads), {dt:.1f} s",
+                                "table_optimised_value": tab_er,
                                 "python_reference_in_build_container": "38.2 conclaves/s, 58.7k elector-rounds/s on 8 cores "
                                                                        "(unmodified reference, 20000 trials; tests/golden/dist_cfg2.json)"}
     if rank == 0:

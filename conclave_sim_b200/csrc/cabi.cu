@@ -21,6 +21,7 @@
 #include "exact64.cuh"
 #include "dense32.cuh"
 #include "prob32.cuh"
+#include "table.cuh"
 
 static thread_local std::string g_err;
 
@@ -61,7 +62,7 @@ struct csim_ctx {
     cudaDeviceProp prop{};
     int E = 0, Epad = 0, G = 0;
     DevBuf x64, x32, region, pap;
-    DevBuf sets, betas, nbeta, W, tab;
+    DevBuf sets, betas, nbeta, W, tab, cdf64, cdfk64, cdf32, cdfk32;
     double x_mid = 0.0, x_half = 0.0;   // centre and half-range of ideology_score (factorised exp)
     // host-buffer mode staging
     DevBuf o_winner, o_rounds, o_reason, o_final, o_tallies, o_whist, o_rhist, o_totals, i_tape;
@@ -104,7 +105,7 @@ extern "C" csim_status csim_create(csim_ctx** out, int device) {
 extern "C" csim_status csim_destroy(csim_ctx* c) {
     if (!c) return CSIM_OK;
     cudaSetDevice(c->device);
-    for (DevBuf* b : {&c->x64, &c->x32, &c->region, &c->pap, &c->sets, &c->betas, &c->nbeta, &c->W, &c->tab, &c->o_winner, &c->o_rounds,
+    for (DevBuf* b : {&c->x64, &c->x32, &c->region, &c->pap, &c->sets, &c->betas, &c->nbeta, &c->W, &c->tab, &c->cdf64, &c->cdfk64, &c->cdf32, &c->cdfk32, &c->o_winner, &c->o_rounds,
                       &c->o_reason, &c->o_final, &c->o_tallies, &c->o_whist, &c->o_rhist, &c->o_totals, &c->i_tape,
                       &c->p_prev, &c->p_cnt, &c->p_fat, &c->p_shares, &c->p_bw, &c->p_out})
         b->release();
@@ -382,7 +383,7 @@ static csim_status launch_dense32(csim_ctx* c, const csim_run_args* ra, const st
     a.kmax = kmax;
     // factorised exponential: needs beta >= 0 and e^{+-beta x'} comfortably inside fp32 range
     bool fact = getenv("CSIM_DENSE_MUFU") == nullptr;
-    for (double be : hb) if (!(be >= 0.0) || !(be * c->x_half <= 40.0)) fact = false;
+    for (double be : hb) if (!(be >= 0.0) || !(be * c->x_half <= 26.0)) fact = false;   // e^{3 beta x'} must stay finite in fp32
     const bool model = ra->wiring == CSIM_WIRING_MODEL;
     const int E = c->E;
     if (E <= 256) {                       // chunks of 8 candidates, at most 32 chunks
@@ -394,6 +395,70 @@ static csim_status launch_dense32(csim_ctx* c, const csim_run_args* ra, const st
     return launch_dense32_d<0>(c, a, model, fact, st);
 }
 
+template <class Real>
+static csim_status launch_table_t(csim_ctx* c, const BatchDev& b, const TrialOut& out, int kmax, const Real* cdf, const Real* cdfk,
+                                  cudaStream_t st) {
+    TableArgs<Real> a;
+    a.ro = roster_dev(c); a.b = b; a.out = out; a.cdf = cdf; a.cdfk = cdfk; a.kmax = kmax;
+    const int E = c->E;
+    const size_t Ei = ((size_t)E + 3) & ~(size_t)3;
+    a.warp_smem = (Ei * 4 + (((size_t)kmax + 3) & ~(size_t)3) * 4 + Ei + 15) & ~(size_t)15;
+    const size_t qtab = (((size_t)b.R * E * sizeof(Real)) + 15) & ~(size_t)15;
+    const size_t full = (((size_t)E * E * sizeof(Real)) + 15) & ~(size_t)15;
+    int wpc = 8;
+    a.stage = (full + qtab + a.warp_smem * wpc <= 200 * 1024) ? 1 : 0;
+    a.cta_smem = (a.stage ? full : 0) + qtab;
+    if (a.cta_smem + a.warp_smem * wpc > 220 * 1024)
+        return fail(CSIM_ERR_UNSUPPORTED, "table engine: %d rounds x %d electors do not fit in shared memory", b.R, E);
+    a.warps_per_cta = wpc;
+    const size_t smem = a.cta_smem + a.warp_smem * wpc;
+    auto kern = k_trials_table<Real>;
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpc * 32, smem));
+    if (per_sm < 1) return fail(CSIM_ERR_UNSUPPORTED, "table kernel does not fit on an SM (smem=%zu)", smem);
+    const uint64_t sb_trials = (uint64_t)wpc * 32;
+    const uint64_t n_sb = ((b.n_sims + sb_trials - 1) / sb_trials) * b.n_sets;
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_sb, (uint64_t)c->prop.multiProcessorCount * per_sm));
+    CU_TRY(cudaEventRecord(c->ev0, st));
+    kern<<<grid, wpc * 32, smem, st>>>(a);
+    CU_TRY(cudaEventRecord(c->ev1, st));
+    c->ev_valid = true;
+    ++c->launches;
+    CU_TRY(cudaGetLastError());
+    return CSIM_OK;
+}
+
+static csim_status launch_table(csim_ctx* c, const csim_run_args* ra, const std::vector<DevSet>& hs, const BatchDev& b,
+                                const TrialOut& out, cudaStream_t st) {
+    if (ra->wiring != CSIM_WIRING_REF_CLI)
+        return fail(CSIM_ERR_UNSUPPORTED, "the table engine exists for the ref_cli wiring only (under `model` the matrix depends on the trial)");
+    const int E = c->E, R = b.R;
+    if ((size_t)b.n_sets * R > 65535) return fail(CSIM_ERR_UNSUPPORTED, "n_param_sets * max_rounds exceeds 65535");
+    int kmax = 1;
+    for (const DevSet& s : hs) kmax = std::max(kmax, s.k);
+    const size_t rows = (size_t)b.n_sets * R * E;
+    const size_t wbytes = sizeof(double) * (size_t)b.n_sets * R * E * c->Epad;
+    if (wbytes + rows * E * 12 > ((size_t)120 << 30)) return fail(CSIM_ERR_UNSUPPORTED, "CDF tables need more than 120 GB");
+    CU_TRY(c->W.reserve(wbytes));
+    CU_TRY(c->cdf64.reserve(sizeof(double) * rows * E));
+    CU_TRY(c->cdfk64.reserve(sizeof(double) * rows * kmax));
+    RosterDev ro = roster_dev(c);
+    dim3 g((c->Epad + 127) / 128, E, b.n_sets * R);
+    k_base_scores64<<<g, 128, 0, st>>>(ro, b.sets, (const double*)c->betas.p, R, (double*)c->W.p);
+    dim3 g2((E + 63) / 64, b.n_sets * R);
+    k_cdf_tables64<<<g2, 64, 0, st>>>(ro, b.sets, (const double*)c->W.p, R, kmax, (double*)c->cdf64.p, (double*)c->cdfk64.p);
+    c->launches += 2;
+    if (ra->precision == CSIM_FP64)
+        return launch_table_t<double>(c, b, out, kmax, (const double*)c->cdf64.p, (const double*)c->cdfk64.p, st);
+    CU_TRY(c->cdf32.reserve(sizeof(float) * rows * E));
+    CU_TRY(c->cdfk32.reserve(sizeof(float) * rows * kmax));
+    k_f64_to_f32<<<c->prop.multiProcessorCount * 4, 256, 0, st>>>((const double*)c->cdf64.p, (float*)c->cdf32.p, rows * E);
+    k_f64_to_f32<<<c->prop.multiProcessorCount, 256, 0, st>>>((const double*)c->cdfk64.p, (float*)c->cdfk32.p, rows * kmax);
+    c->launches += 2;
+    return launch_table_t<float>(c, b, out, kmax, (const float*)c->cdf32.p, (const float*)c->cdfk32.p, st);
+}
+
 extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
     if (!c || !ra) return fail(CSIM_ERR_INVALID, "csim_run: NULL argument");
     if (c->E <= 0) return fail(CSIM_ERR_STATE, "csim_run: roster not uploaded");
@@ -403,7 +468,6 @@ extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
     if (ra->precision != CSIM_FP32 && ra->precision != CSIM_FP64) return fail(CSIM_ERR_INVALID, "csim_run: bad precision %d", ra->precision);
     if (ra->engine != CSIM_ENGINE_AUTO && ra->engine != CSIM_ENGINE_DENSE && ra->engine != CSIM_ENGINE_TABLE)
         return fail(CSIM_ERR_INVALID, "csim_run: bad engine %d", ra->engine);
-    if (ra->engine == CSIM_ENGINE_TABLE) return fail(CSIM_ERR_UNSUPPORTED, "csim_run: the table engine is not built yet");
     if (ra->uniform_tape && ra->precision != CSIM_FP64) return fail(CSIM_ERR_INVALID, "csim_run: a uniform tape requires CSIM_FP64 precision");
     const int R = ra->params[0].max_rounds;
     if (R < 0) return fail(CSIM_ERR_INVALID, "csim_run: max_rounds < 0");
@@ -463,7 +527,10 @@ extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
         if (ra->totals) { CU_TRY(c->o_totals.reserve(8 * nh_t)); CU_TRY(cudaMemsetAsync(c->o_totals.p, 0, 8 * nh_t, st)); out.totals = (unsigned long long*)c->o_totals.p; }
     }
 
-    csim_status s = ra->precision == CSIM_FP64 ? launch_exact64(c, ra, hs, b, out, st) : launch_dense32(c, ra, hs, hb, b, out, st);
+    // engine choice: the table engine when the matrix is trial-invariant (ref_cli), else the dense engines
+    const bool use_table = ra->engine == CSIM_ENGINE_TABLE || (ra->engine == CSIM_ENGINE_AUTO && ra->wiring == CSIM_WIRING_REF_CLI);
+    csim_status s = use_table ? launch_table(c, ra, hs, b, out, st)
+                              : (ra->precision == CSIM_FP64 ? launch_exact64(c, ra, hs, b, out, st) : launch_dense32(c, ra, hs, hb, b, out, st));
     if (s != CSIM_OK) return s;
 
     if (!dev) {

@@ -135,3 +135,21 @@ __device__ __forceinline__ void warp_top_k(const int32_t* tally, int C, int k, i
         __syncwarp();
     }
 }
+
+// Top two tallies by (count desc, index asc) as packed keys (count << 16 | 0xFFFF - index); needs C < 32768.
+__device__ __forceinline__ void warp_top2(const int32_t* tally, int C, int lane, uint32_t& k1, uint32_t& k2) {
+    uint32_t a = 0, b = 0;
+    for (int c = lane; c < C; c += CSIM_WARP) {
+        const uint32_t key = ((uint32_t)tally[c] << 16) | (uint32_t)(0xFFFF - c);
+        if (key > a) { b = a; a = key; } else if (key > b) { b = key; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const uint32_t oa = __shfl_xor_sync(CSIM_FULL, a, off), ob = __shfl_xor_sync(CSIM_FULL, b, off);
+        const uint32_t hi = max(a, oa), lo = min(a, oa);
+        b = max(lo, max(b, ob));
+        a = hi;
+    }
+    k1 = a; k2 = b;
+}
+

@@ -8,15 +8,15 @@
 // Full-field round, for every elector e (candidates are cut into chunks of L, L = 8 up to E = 256):
 //
 //   phase 1   chunk_sum[j] = sum over c in chunk j of  exp(-beta_r |x_e - x_c|) * pw_c
-//             evaluated for FOUR electors of a lane at once (the electors 4q..4q+3 of one Philox
-//             quad), so every candidate operand fetched from shared memory (a warp-uniform 128-bit
-//             load, which costs 4 cycles of the SM's 128 B/clk shared-memory return path) feeds
-//             4 x 4 pair evaluations.  The terms that need no exponential are added per CHUNK:
-//               regional bonus  = bonus * #{c in chunk : region_c == region_e}   (roster table)
-//               bandwagon       = sum of bw_c over the chunk                       (per trial-round)
+//             evaluated for NE (= 2) electors of a lane at once, so every candidate operand fetched
+//             from shared memory (a warp-uniform 128-bit load) feeds NE x 4 pair evaluations.  The terms that need no exponential are added per CHUNK:
 //               self vote       = - s_ee  in e's chunk            (model.py:418-424)
 //               stickiness      = + st * s_e,prev  in prev's chunk (model.py:357-367)
 //             and the running prefix over chunks goes to a per-lane column of shared memory.
+//             The terms that are sums of per-candidate constants are not accumulated at all: they are
+//             read from prefix tables when a prefix is probed:
+//               regional bonus  = bonus * #{c <= chunk j : region_c == region_e}   (roster table RBp)
+//               bandwagon       = sum of bw_c over chunks <= j                     (per trial-round BWp)
 //   phase 2   t = u * S; a 5-probe binary search over the prefix column finds the chunk that t falls
 //             into; ONLY that chunk's L candidates are re-evaluated with every term inline, in
 //             roster order, to find the first c with cum > t
@@ -27,10 +27,13 @@
 // Factorised evaluation (template flag FACT, the default whenever beta_r >= 0 and
 // beta_r * half-range(x) <= 40): with x' = x - x_mid,
 //     exp(-beta |x_e - x_c|) = min( e^{-beta x'_e} e^{+beta x'_c} ,  e^{+beta x'_e} e^{-beta x'_c} )
-// so a pair costs two multiplies and a min instead of FADD + FMUL + MUFU.EX2, and the multiplies and
-// the accumulation run as sm_100 packed-fp32 instructions (FMUL2 / FADD2, two pairs per issue slot).
-// The four per-round vectors A = e^{-beta x'}, A' = e^{+beta x'}, BP = A' * pw, BP' = A * pw come from
-// k_round_tables32 (fp64 exp, rounded once).  FACT = false keeps the MUFU.EX2 form (any roster, any beta).
+//                            = A_e * min( BP_c , R_e * BQ_c ) / pw_c     with A = e^{-beta x'}, R = e^{+2 beta x'},
+//                                                                        BP = e^{+beta x'} pw, BQ = e^{-beta x'} pw
+// so a pair costs ONE multiply, a min and an add instead of FADD + FMUL + MUFU.EX2 + FFMA; the multiply and
+// the add run as sm_100 packed-fp32 instructions (FMUL2 / FADD2, two pairs per issue slot): 2 issue slots
+// per pair.  The factor A_e multiplies the chunk prefix once, when it is probed.  The per-round vectors
+// come from k_round_tables32 (fp64 exp, rounded once).  FACT = false keeps the MUFU.EX2 form (any roster,
+// any beta).
 //
 // Run-off rounds (simulate.py:144-154,183-186) only need the first k columns of the row
 // (P[e, :k] renormalised), so they cost k pair evaluations per elector; with k = 2 the tally is a
@@ -54,18 +57,21 @@ struct Dense32Args {
 };
 
 #ifndef CSIM_NE
-#define CSIM_NE 4
+#define CSIM_NE 2          // electors of a lane evaluated together in phase 1 (1, 2 or 4)
+#endif
+#ifndef CSIM_MINB
+#define CSIM_MINB 3        // resident CTAs per SM the register allocation is bounded for
 #endif
 #define DENSE32_PREF_COLS (CSIM_NE > 1 ? CSIM_NE : 1)
 __host__ __device__ inline size_t dense32_cta_smem(int nch, int L, int G) {
     const size_t CP = (size_t)nch * L;
-    return ((CP * 4 /*xs*/ + CP * 4 /*reg*/ + (size_t)nch * G * 4 * 2 /*regcnt, regmask*/) + 15) & ~(size_t)15;
+    return ((CP * 4 /*xs*/ + CP * 4 /*reg*/ + (size_t)nch * G * 4 * 2 /*RBp, regmask*/) + 15) & ~(size_t)15;
 }
 __host__ __device__ inline size_t dense32_warp_smem(int E, int nch, int L, int kmax, bool model) {
     const size_t CP = (size_t)nch * L, Ei = ((size_t)E + 3) & ~(size_t)3, n4 = ((size_t)nch + 3) & ~(size_t)3;
-    size_t n = CP * 4 * 2 /*pw | bp, bpp*/ + (size_t)DENSE32_PREF_COLS * nch * 32 * 4 /*prefix columns*/ + Ei * 4 /*tally*/ +
+    size_t n = CP * 4 * 2 /*pw | BP, BQ*/ + (size_t)DENSE32_PREF_COLS * nch * 32 * 4 /*prefix columns*/ + Ei * 4 /*tally*/ +
                (((size_t)kmax + 3) & ~(size_t)3) * 4 /*eff*/ + Ei /*mark*/;
-    if (model) n += CP * 4 /*bw*/ + n4 * 4 /*bwchunk*/ + Ei * 4 * 2 /*prev_tally, votes*/;
+    if (model) n += CP * 4 /*bw*/ + n4 * 4 /*bwp*/ + Ei * 4 * 2 /*prev_tally, votes*/;
     return (n + 15) & ~(size_t)15;
 }
 
@@ -100,73 +106,54 @@ __global__ void k_round_tables32(RosterDev ro, const DevSet* sets, const double*
 }
 
 struct LaneCtx32 {              // per-warp / per-round constants of the draw
-    const float* xs; const int32_t* reg; const float* regcnt; const uint32_t* regmask;
-    const float* pw; const float* bpp; const float* bw; const float* bwchunk;   // FACT: pw = BP, bpp = BP'
+    const float* xs; const int32_t* reg; const float* rbp; const uint32_t* regmask;
+    const float* pw; const float* bq; const float* bw; const float* bwp;   // FACT: pw = BP, bq = BQ;  bwp = prefix of bw over chunks
     float nb, bonus, st1p;
     int C, G, L, nch, step0;
     bool use_bw;
 };
 
-// exp(-beta |x_e - x_c|) * pw_c for one pair
+// One elector's scalars.  FACT: score(e,c) = A * min(BP_c, R * BQ_c);  else A = 1 and x is the ideology.
+struct Elector32 { float x, A, Ainv, R; int g, prev; };
+
+// the exponential part of one score in "m" units (score = A * m)
 template <bool FACT>
-__device__ __forceinline__ float pair32(const LaneCtx32& k, int c, float xe, float ae, float ape) {
-    return FACT ? fminf(ae * k.pw[c], ape * k.bpp[c]) : ex2_approx(fabsf(xe - k.xs[c]) * k.nb) * k.pw[c];
+__device__ __forceinline__ float pair_m32(const LaneCtx32& k, int c, const Elector32& el) {
+    return FACT ? fminf(k.pw[c], el.R * k.bq[c]) : ex2_approx(fabsf(el.x - k.xs[c]) * k.nb) * k.pw[c];
 }
 
 // every term of one score, inline (run-off rounds and the generic re-scan)
 template <bool MODEL, bool FACT>
-__device__ __forceinline__ float full_score32(const LaneCtx32& k, int e, int c, float xe, float ae, float ape, int ge, int prev) {
-    float v = pair32<FACT>(k, c, xe, ae, ape);
-    if (k.reg[c] == ge) v += k.bonus;
+__device__ __forceinline__ float full_score32(const LaneCtx32& k, int e, int c, const Elector32& el) {
+    float v = el.A * pair_m32<FACT>(k, c, el);
+    if (k.reg[c] == el.g) v += k.bonus;
     if (MODEL) {
         if (k.use_bw) v += k.bw[c];
-        if (c == prev) v *= k.st1p;
+        if (c == el.prev) v *= k.st1p;
     }
     return c == e ? 0.0f : v;
 }
 
-// Top two tallies by (count desc, index asc) as packed keys (count << 16 | 0xFFFF - index); needs C < 32768.
-__device__ __forceinline__ void warp_top2(const int32_t* tally, int C, int lane, uint32_t& k1, uint32_t& k2) {
-    uint32_t a = 0, b = 0;
-    for (int c = lane; c < C; c += CSIM_WARP) {
-        const uint32_t key = ((uint32_t)tally[c] << 16) | (uint32_t)(0xFFFF - c);
-        if (key > a) { b = a; a = key; } else if (key > b) { b = key; }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const uint32_t oa = __shfl_xor_sync(CSIM_FULL, a, off), ob = __shfl_xor_sync(CSIM_FULL, b, off);
-        const uint32_t hi = max(a, oa), lo = min(a, oa);
-        b = max(lo, max(b, ob));
-        a = hi;
-    }
-    k1 = a; k2 = b;
-}
-
-// Phase 1 of one chunk for NE electors of a lane: acc0/acc1 += the exponential part of the chunk.
+// Phase 1 of one chunk for NE electors of a lane: acc (packed pair of partial sums, m units) += chunk j.
 // The candidate operands are loaded once (warp-uniform 128-bit loads) and reused by all NE electors.
 template <int NE, int LC, bool FACT>
-__device__ __forceinline__ void chunk_acc(const LaneCtx32& k, int j, const float (&xe)[NE], const unsigned long long (&a2)[NE],
-                                          const unsigned long long (&ap2)[NE], float (&acc0)[NE], float (&acc1)[NE]) {
+__device__ __forceinline__ void chunk_acc(const LaneCtx32& k, int j, const float (&xe)[NE], const unsigned long long (&r2)[NE],
+                                          unsigned long long (&acc)[NE]) {
     const int L = LC > 0 ? LC : k.L;
     if (FACT) {
-        unsigned long long acc[NE];
-#pragma unroll
-        for (int t = 0; t < NE; ++t) acc[t] = f2_pack(acc0[t], acc1[t]);
         const ulonglong2* b4 = reinterpret_cast<const ulonglong2*>(k.pw + j * L);
-        const ulonglong2* c4 = reinterpret_cast<const ulonglong2*>(k.bpp + j * L);
+        const ulonglong2* c4 = reinterpret_cast<const ulonglong2*>(k.bq + j * L);
 #pragma unroll 2
         for (int i = 0; i < (L >> 2); ++i) {
             const ulonglong2 b = b4[i], c = c4[i];
 #pragma unroll
             for (int t = 0; t < NE; ++t) {
-                unsigned long long t1 = f2_mul(a2[t], b.x), t2 = f2_mul(ap2[t], c.x);
-                acc[t] = f2_add(acc[t], f2_pack(fminf(f2_lo(t1), f2_lo(t2)), fminf(f2_hi(t1), f2_hi(t2))));
-                t1 = f2_mul(a2[t], b.y); t2 = f2_mul(ap2[t], c.y);
-                acc[t] = f2_add(acc[t], f2_pack(fminf(f2_lo(t1), f2_lo(t2)), fminf(f2_hi(t1), f2_hi(t2))));
+                unsigned long long t2 = f2_mul(r2[t], c.x);
+                acc[t] = f2_add(acc[t], f2_pack(fminf(f2_lo(b.x), f2_lo(t2)), fminf(f2_hi(b.x), f2_hi(t2))));
+                t2 = f2_mul(r2[t], c.y);
+                acc[t] = f2_add(acc[t], f2_pack(fminf(f2_lo(b.y), f2_lo(t2)), fminf(f2_hi(b.y), f2_hi(t2))));
             }
         }
-#pragma unroll
-        for (int t = 0; t < NE; ++t) { acc0[t] = f2_lo(acc[t]); acc1[t] = f2_hi(acc[t]); }
     } else {
         const float4* x4 = reinterpret_cast<const float4*>(k.xs + j * L);
         const float4* p4 = reinterpret_cast<const float4*>(k.pw + j * L);
@@ -176,36 +163,47 @@ __device__ __forceinline__ void chunk_acc(const LaneCtx32& k, int j, const float
             const float4 xv = x4[i], pv = p4[i];
 #pragma unroll
             for (int t = 0; t < NE; ++t) {
-                acc0[t] = fmaf(ex2_approx(fabsf(xe[t] - xv.x) * nb), pv.x, acc0[t]);
-                acc1[t] = fmaf(ex2_approx(fabsf(xe[t] - xv.y) * nb), pv.y, acc1[t]);
-                acc0[t] = fmaf(ex2_approx(fabsf(xe[t] - xv.z) * nb), pv.z, acc0[t]);
-                acc1[t] = fmaf(ex2_approx(fabsf(xe[t] - xv.w) * nb), pv.w, acc1[t]);
+                float a0 = f2_lo(acc[t]), a1 = f2_hi(acc[t]);
+                a0 = fmaf(ex2_approx(fabsf(xe[t] - xv.x) * nb), pv.x, a0);
+                a1 = fmaf(ex2_approx(fabsf(xe[t] - xv.y) * nb), pv.y, a1);
+                a0 = fmaf(ex2_approx(fabsf(xe[t] - xv.z) * nb), pv.z, a0);
+                a1 = fmaf(ex2_approx(fabsf(xe[t] - xv.w) * nb), pv.w, a1);
+                acc[t] = f2_pack(a0, a1);
             }
         }
     }
 }
 
-// Per-elector corrections that enter the chunk sums: the self score (removed) and stickiness (added).
+// Per-elector corrections to the exponential-part prefix, in m units: the self score (removed at e's
+// chunk, model.py:418-424) and stickiness (added at prev's chunk, model.py:357-367).
 template <bool MODEL, bool FACT>
-__device__ __forceinline__ void corrections32(const LaneCtx32& k, int e, float xe, float ae, float ape, int ge, int prev,
-                                              float& see, float& sadd, int& jp) {
-    see = pair32<FACT>(k, e, xe, ae, ape) + k.bonus;      // same expression as phase 1, so it cancels (model.py:418-424)
-    if (MODEL && k.use_bw) see += k.bw[e];
-    jp = -1; sadd = 0.f;
-    if (MODEL && prev >= 0 && prev != e) {                // + st * s[e, prev] (model.py:357-367)
-        float sp = pair32<FACT>(k, prev, xe, ae, ape);
-        if (k.reg[prev] == ge) sp += k.bonus;
-        if (k.use_bw) sp += k.bw[prev];
-        sadd = sp * (k.st1p - 1.0f);
-        jp = prev / k.L;
+__device__ __forceinline__ void corrections32(const LaneCtx32& k, int e, const Elector32& el, float& see_m, float& sadd_m, int& jp) {
+    float flat = k.bonus;                                  // the self pair is of e's own region
+    if (MODEL && k.use_bw) flat += k.bw[e];
+    see_m = pair_m32<FACT>(k, e, el) + flat * el.Ainv;     // same expression as phase 1, so it cancels
+    jp = -1; sadd_m = 0.f;
+    if (MODEL && el.prev >= 0 && el.prev != e) {
+        float fl = (k.reg[el.prev] == el.g) ? k.bonus : 0.f;
+        if (k.use_bw) fl += k.bw[el.prev];
+        sadd_m = (pair_m32<FACT>(k, el.prev, el) + fl * el.Ainv) * (k.st1p - 1.0f);
+        jp = el.prev / k.L;
     }
 }
 
-// Phase 2: given the prefix sums over chunks (pref[j * pstride], j < nch) and their total S, draw the vote.
+// prefix of the scores over chunks 0..j:  A * (exponential part) + regional bonus + bandwagon
+template <bool MODEL>
+__device__ __forceinline__ float probe32(const LaneCtx32& k, const float* pref, int pstride, const float* rbrow, float A, int j) {
+    float v = fmaf(k.bonus, rbrow[j], A * pref[j * pstride]);
+    if (MODEL && k.use_bw) v += k.bwp[j];
+    return v;
+}
+
+// Phase 2: given the exponential-part prefix over chunks (pref[j * pstride], m units), draw the vote.
 template <int LC, bool MODEL, bool FACT>
-__device__ __forceinline__ int finish_draw(const LaneCtx32& k, const float* pref, int pstride, int e, float u, float S,
-                                           float xe, float ae, float ape, int ge, int prev) {
+__device__ __forceinline__ int finish_draw(const LaneCtx32& k, const float* pref, int pstride, int e, float u, const Elector32& el) {
     const int C = k.C, L = LC > 0 ? LC : k.L, nch = k.nch;
+    const float* rbrow = k.rbp + el.g * nch;
+    const float S = probe32<MODEL>(k, pref, pstride, rbrow, el.A, nch - 1);
     if (!(S > 0.0f)) {            // all scores vanished: the reference makes the row uniform INCLUDING self (model.py:447-449)
         const int j = (int)(u * (float)C);
         return j < C ? j : C - 1;
@@ -214,32 +212,32 @@ __device__ __forceinline__ int finish_draw(const LaneCtx32& k, const float* pref
     int pos = 0;                  // number of chunks whose prefix is <= tgt
     for (int step = k.step0; step > 0; step >>= 1) {
         const int np = pos + step;
-        if (np <= nch && pref[(np - 1) * pstride] <= tgt) pos = np;
+        if (np <= nch && probe32<MODEL>(k, pref, pstride, rbrow, el.A, np - 1) <= tgt) pos = np;
     }
     const int last_chunk = (C - 1) / L;
     const int jstar = pos > last_chunk ? last_chunk : pos;
-    const float below = jstar > 0 ? pref[(jstar - 1) * pstride] : 0.0f;
+    const float below = jstar > 0 ? probe32<MODEL>(k, pref, pstride, rbrow, el.A, jstar - 1) : 0.0f;
     const int c0 = jstar * L;
     float cum = below;
     int cnt = 0;
     if (LC == 8) {
-        // vectorised re-scan.  FACT: (xa, xb) hold BP', (pa, pb) hold BP;  else x and pw
-        const float* src_x = FACT ? k.bpp : k.xs;
+        // vectorised re-scan.  FACT: (xa, xb) hold BQ, (pa, pb) hold BP;  else x and pw
+        const float* src_x = FACT ? k.bq : k.xs;
         const float4 xa = *reinterpret_cast<const float4*>(src_x + c0), xb = *reinterpret_cast<const float4*>(src_x + c0 + 4);
         const float4 pa = *reinterpret_cast<const float4*>(k.pw + c0), pb = *reinterpret_cast<const float4*>(k.pw + c0 + 4);
-        const uint32_t rm = k.regmask[jstar * k.G + ge];                     // bit i: candidate c0+i is of e's region
+        const uint32_t rm = k.regmask[jstar * k.G + el.g];                   // bit i: candidate c0+i is of e's region
         const uint32_t dm = (jstar == (e >> 3)) ? (1u << (e & 7)) : 0u;      // bit i: candidate c0+i is e itself
         uint32_t pm = 0;
         float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
         if (MODEL) {
-            if (prev >= 0 && (prev >> 3) == jstar) pm = 1u << (prev & 7);
+            if (el.prev >= 0 && (el.prev >> 3) == jstar) pm = 1u << (el.prev & 7);
             if (k.use_bw) { ba = *reinterpret_cast<const float4*>(k.bw + c0); bb = *reinterpret_cast<const float4*>(k.bw + c0 + 4); }
         }
         const float nb = k.nb;
 #define CSIM_RESCAN(i, xv, pv, bv)                                              \
         {                                                                       \
-            const float ex = FACT ? fminf(ae * (pv), ape * (xv)) : ex2_approx(fabsf(xe - (xv)) * nb) * (pv); \
-            float v = ex + (((rm >> (i)) & 1u) ? k.bonus : 0.0f);               \
+            const float m = FACT ? fminf((pv), el.R * (xv)) : ex2_approx(fabsf(el.x - (xv)) * nb) * (pv); \
+            float v = fmaf(el.A, m, ((rm >> (i)) & 1u) ? k.bonus : 0.0f);       \
             if (MODEL) { v += (bv); if ((pm >> (i)) & 1u) v *= k.st1p; }        \
             if ((dm >> (i)) & 1u) v = 0.0f;                                     \
             cum += v;                                                           \
@@ -251,7 +249,7 @@ __device__ __forceinline__ int finish_draw(const LaneCtx32& k, const float* pref
     } else {
         for (int i = 0; i < L; ++i) {
             const int c = c0 + i;
-            const float v = c < C ? full_score32<MODEL, FACT>(k, e, c, xe, ae, ape, ge, prev) : 0.0f;
+            const float v = c < C ? full_score32<MODEL, FACT>(k, e, c, el) : 0.0f;
             cum += v;
             cnt += (cum <= tgt) ? 1 : 0;
         }
@@ -263,12 +261,6 @@ __device__ __forceinline__ int finish_draw(const LaneCtx32& k, const float* pref
     return vote;
 }
 
-#ifndef CSIM_NE
-#define CSIM_NE 4          // electors of a lane evaluated together in phase 1 (1, 2 or 4)
-#endif
-#ifndef CSIM_MINB
-#define CSIM_MINB 2        // resident CTAs per SM the register allocation is bounded for
-#endif
 template <int LC, bool MODEL, bool FACT>
 __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a) {
     constexpr int NE = CSIM_NE;
@@ -282,8 +274,8 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
     // ---- CTA-shared roster tables ------------------------------------------------------------
     float* xs = (float*)smem_raw;
     int32_t* reg = (int32_t*)(xs + CP);
-    float* regcnt = (float*)(reg + CP);
-    uint32_t* regmask = (uint32_t*)(regcnt + nch * G);
+    float* rbp = (float*)(reg + CP);                         // [G][nch]: #{c in chunks 0..j : region_c == g}
+    uint32_t* regmask = (uint32_t*)(rbp + nch * G);          // [nch][G]: bit i <-> candidate j*L+i is of region g
     for (int c = threadIdx.x; c < CP; c += blockDim.x) {
         xs[c] = c < C ? a.ro.x32[c] : 0.0f;
         reg[c] = c < C ? a.ro.region[c] : -1;
@@ -291,21 +283,21 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
     for (int i = threadIdx.x; i < nch * G; i += blockDim.x) {
         const int j = i / G, g = i - j * G;
         int n = 0; uint32_t m = 0;
-        for (int c = j * L; c < (j + 1) * L && c < C; ++c)
-            if (a.ro.region[c] == g) { ++n; if (c - j * L < 32) m |= 1u << (c - j * L); }
-        regcnt[i] = (float)n;
+        for (int c = 0; c < (j + 1) * L && c < C; ++c)
+            if (a.ro.region[c] == g) { ++n; if (c >= j * L && c - j * L < 32) m |= 1u << (c - j * L); }
+        rbp[g * nch + j] = (float)n;
         regmask[i] = m;
     }
     // ---- per-warp state ----------------------------------------------------------------------
     unsigned char* base = smem_raw + a.cta_smem + (size_t)wib * a.warp_smem;
     // 16-byte aligned float arrays first (they are read with 128-bit loads), then the int arrays
     float* pw = (float*)base;                   base += sizeof(float) * CP;      // FACT: BP of the current round
-    float* bpp = (float*)base;                  base += sizeof(float) * CP;      // FACT: BP'
+    float* bq = (float*)base;                   base += sizeof(float) * CP;      // FACT: BQ
     float* pref = (float*)base;                 base += sizeof(float) * DENSE32_PREF_COLS * nch * 32;   // prefix columns [t][j][lane]
-    float* bw = nullptr; float* bwchunk = nullptr;
+    float* bw = nullptr; float* bwp = nullptr;
     if (MODEL) {
         bw = (float*)base;                      base += sizeof(float) * CP;
-        bwchunk = (float*)base;                 base += sizeof(float) * ((nch + 3) & ~3);
+        bwp = (float*)base;                     base += sizeof(float) * ((nch + 3) & ~3);
     }
     int32_t* tally = (int32_t*)base;            base += sizeof(int32_t) * Ei;
     int32_t* prev_tally = nullptr; int32_t* votes = nullptr;
@@ -330,7 +322,7 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
     const bool top2_ok = C >= 2 && C < 32768;
 
     LaneCtx32 kx;
-    kx.xs = xs; kx.reg = reg; kx.regcnt = regcnt; kx.regmask = regmask; kx.pw = pw; kx.bpp = bpp; kx.bw = bw; kx.bwchunk = bwchunk;
+    kx.xs = xs; kx.reg = reg; kx.rbp = rbp; kx.regmask = regmask; kx.pw = pw; kx.bq = bq; kx.bw = bw; kx.bwp = bwp;
     kx.C = C; kx.G = G; kx.L = L; kx.nch = nch; kx.use_bw = false; kx.nb = 0.f; kx.bonus = 0.f; kx.st1p = 1.f;
     kx.step0 = 1;
     while (kx.step0 * 2 <= nch) kx.step0 *= 2;
@@ -340,6 +332,17 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
     int need = 0, k = 0, rr = 0;
     bool has_sticky = false, has_bw = false;
     unsigned long long acc_rounds = 0, acc_trials = 0;
+    const float* tabA = nullptr;
+
+    // one elector's scalars for this round
+    auto load_elector = [&](int e, bool sticky_live) {
+        Elector32 el;
+        if (FACT) { el.A = __ldg(tabA + e); el.Ainv = __ldg(tabA + CP + e); el.R = el.Ainv * el.Ainv; el.x = 0.f; }
+        else { el.A = 1.f; el.Ainv = 1.f; el.R = 1.f; el.x = xs[e]; }
+        el.g = reg[e];
+        el.prev = (MODEL && sticky_live) ? votes[e] : -1;
+        return el;
+    };
 
     for (uint64_t t = warp_global; t < n_trials; t += n_warps) {
         const int set = (int)(t / a.b.n_sims);
@@ -371,11 +374,10 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
             rounds = r;
             kx.nb = __ldg(&nbeta[r - 1]);
             kx.use_bw = false;
-            const float* tabA = nullptr;
-            if (FACT) {                                          // stage this round's BP / BP' (trial-invariant vectors)
+            if (FACT) {                                          // stage this round's BP / BQ (trial-invariant vectors)
                 tabA = a.tab + ((size_t)set * R + (r - 1)) * 4 * CP;
                 __syncwarp();
-                for (int c = lane; c < CP; c += 32) { pw[c] = __ldg(tabA + 2 * CP + c); bpp[c] = __ldg(tabA + 3 * CP + c); }
+                for (int c = lane; c < CP; c += 32) { pw[c] = __ldg(tabA + 2 * CP + c); bq[c] = __ldg(tabA + 3 * CP + c); }
             }
             if (MODEL) {
                 if (has_bw && have_prev) {                                   // model.py:326-354
@@ -386,16 +388,20 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                         const float inv = 1.0f / (float)mx;
                         for (int c = lane; c < C; c += 32) bw[c] = (float)prev_tally[c] * inv * bw_strength;
                         __syncwarp();
-                        if (lane < nch) {
-                            float s = 0.f;
-                            for (int c = lane * L; c < (lane + 1) * L; ++c) s += bw[c];
-                            bwchunk[lane] = s;
+                        float s = 0.f;                                       // bandwagon of chunk `lane`, then prefix over chunks
+                        if (lane < nch) for (int c = lane * L; c < (lane + 1) * L; ++c) s += bw[c];
+#pragma unroll
+                        for (int off = 1; off < 32; off <<= 1) {
+                            const float o = __shfl_up_sync(CSIM_FULL, s, off);
+                            if (lane >= off) s += o;
                         }
+                        if (lane < nch) bwp[lane] = s;
                     }
                 }
             }
             for (int c = lane; c < C; c += 32) tally[c] = 0;
             __syncwarp();
+            const bool sticky_live = have_prev && has_sticky;
 
             int cnt0 = 0;                                        // run-off (fast2): this lane's votes for ef0
             if (!have_eff) {
@@ -407,40 +413,31 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
 #pragma unroll 1
                     for (int g = 0; g < 4 / NE; ++g) {
                         const int e0 = 4 * q + NE * g;
-                        float xe[NE], ae[NE], ape[NE], see[NE], sadd[NE], run[NE];
-                        int ge[NE], prev[NE], jp[NE];
-                        unsigned long long a2[NE], ap2[NE];
-                        const float* rc[NE];
+                        Elector32 el[NE];
+                        float xe[NE], see[NE], sadd[NE];
+                        int jp[NE];
+                        unsigned long long r2[NE], acc[NE];
 #pragma unroll
                         for (int i = 0; i < NE; ++i) {
-                            ae[i] = FACT ? __ldg(tabA + e0 + i) : 0.f;
-                            ape[i] = FACT ? __ldg(tabA + CP + e0 + i) : 0.f;
-                            xe[i] = FACT ? 0.f : xs[e0 + i];
-                            ge[i] = reg[e0 + i];
-                            prev[i] = (MODEL && have_prev && has_sticky) ? votes[e0 + i] : -1;
-                            corrections32<MODEL, FACT>(kx, e0 + i, xe[i], ae[i], ape[i], ge[i], prev[i], see[i], sadd[i], jp[i]);
-                            a2[i] = f2_pack(ae[i], ae[i]); ap2[i] = f2_pack(ape[i], ape[i]);
-                            run[i] = 0.f;
-                            rc[i] = regcnt + ge[i];
+                            el[i] = load_elector(e0 + i, sticky_live);
+                            corrections32<MODEL, FACT>(kx, e0 + i, el[i], see[i], sadd[i], jp[i]);
+                            xe[i] = el[i].x;
+                            r2[i] = f2_pack(el[i].R, el[i].R);
+                            acc[i] = 0ull;
                         }
                         const int je = e0 / L;                   // the electors of a group share their chunk (L % 4 == 0)
                         float* pcol = pref + lane;
 #pragma unroll 1
                         for (int j = 0; j < nch; ++j) {
-                            float acc0[NE], acc1[NE];
+                            chunk_acc<NE, LC, FACT>(kx, j, xe, r2, acc);
+                            if (j == je) {
 #pragma unroll
-                            for (int i = 0; i < NE; ++i) {
-                                acc0[i] = (j == je) ? -see[i] : 0.f;
-                                acc1[i] = (MODEL && j == jp[i]) ? sadd[i] : 0.f;
+                                for (int i = 0; i < NE; ++i) acc[i] = f2_add(acc[i], f2_pack(-see[i], 0.f));
                             }
-                            chunk_acc<NE, LC, FACT>(kx, j, xe, a2, ap2, acc0, acc1);
 #pragma unroll
                             for (int i = 0; i < NE; ++i) {
-                                float s = fmaf(kx.bonus, *rc[i], acc0[i] + acc1[i]);       // regional bonus (model.py:322-323)
-                                if (MODEL && kx.use_bw) s += bwchunk[j];                  // bandwagon (model.py:354)
-                                run[i] += s;
-                                pcol[i * nch * 32] = run[i];
-                                rc[i] += G;
+                                if (MODEL && j == jp[i]) acc[i] = f2_add(acc[i], f2_pack(sadd[i], 0.f));
+                                pcol[i * nch * 32] = f2_lo(acc[i]) + f2_hi(acc[i]);     // running prefix, m units
                             }
                             pcol += 32;
                         }
@@ -448,12 +445,11 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                         for (int i = 0; i < NE; ++i) {
                             const int wi = NE * g + i;
                             const uint32_t wa = wi == 0 ? w[0] : (wi == 1 ? w[1] : (wi == 2 ? w[2] : w[3]));
-                            float S = run[0], xei = xe[0], aei = ae[0], apei = ape[0]; int gei = ge[0], pvi = prev[0];
+                            Elector32 ei = el[0];
 #pragma unroll
-                            for (int m = 1; m < NE; ++m)
-                                if (i == m) { S = run[m]; xei = xe[m]; aei = ae[m]; apei = ape[m]; gei = ge[m]; pvi = prev[m]; }
+                            for (int m = 1; m < NE; ++m) if (i == m) ei = el[m];
                             const int vote = finish_draw<LC, MODEL, FACT>(kx, pref + (size_t)i * nch * 32 + lane, 32, e0 + i,
-                                                                          u24_from_word(wa), S, xei, aei, apei, gei, pvi);
+                                                                          u24_from_word(wa), ei);
                             atomicAdd(&tally[vote], 1);
                             if (MODEL) votes[e0 + i] = vote;   // read only by this lane for its own electors: in-place is safe
                         }
@@ -464,38 +460,33 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                     const int n_it = min(32, n_left - gb);
                     int P = 1;
                     while (P * 2 * n_it <= 32) P *= 2;
-                    const int el = lane / P, sub = lane - el * P;
-                    const bool act = el < n_it;
-                    const int e = e_left0 + gb + (act ? el : 0);
+                    const int eli = lane / P, sub = lane - eli * P;
+                    const bool act = eli < n_it;
+                    const int e = e_left0 + gb + (act ? eli : 0);
                     uint32_t w[4];
                     philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)(e >> 2), a.b.seed_lo, a.b.seed_hi, w);
                     const int sel = e & 3;
                     const uint32_t wa = sel == 0 ? w[0] : (sel == 1 ? w[1] : (sel == 2 ? w[2] : w[3]));
-                    float xe1[1], see, sadd; int jp;
-                    float ae = 0.f, ape = 0.f;
-                    if (FACT) { ae = __ldg(tabA + e); ape = __ldg(tabA + CP + e); }
-                    xe1[0] = FACT ? 0.f : xs[e];
-                    const int ge = reg[e];
-                    const int prev = (MODEL && have_prev && has_sticky) ? votes[e] : -1;
-                    corrections32<MODEL, FACT>(kx, e, xe1[0], ae, ape, ge, prev, see, sadd, jp);
-                    const unsigned long long a2[1] = {f2_pack(ae, ae)}, ap2[1] = {f2_pack(ape, ape)};
+                    const Elector32 el = load_elector(e, sticky_live);
+                    float see, sadd; int jp;
+                    corrections32<MODEL, FACT>(kx, e, el, see, sadd, jp);
+                    const float xe1[1] = {el.x};
+                    const unsigned long long r2[1] = {f2_pack(el.R, el.R)};
                     const int je = e / L;
-                    float* cl = pref + el * nch;                 // this elector's chunk sums, then prefixes
+                    float* cl = pref + eli * nch;                // this elector's chunk sums, then prefixes (m units)
                     __syncwarp();
                     if (act) {
                         for (int j = sub; j < nch; j += P) {
-                            float acc0[1] = {(j == je) ? -see : 0.f}, acc1[1] = {(MODEL && j == jp) ? sadd : 0.f};
-                            chunk_acc<1, LC, FACT>(kx, j, xe1, a2, ap2, acc0, acc1);
-                            float s = fmaf(kx.bonus, regcnt[j * G + ge], acc0[0] + acc1[0]);
-                            if (MODEL && kx.use_bw) s += bwchunk[j];
-                            cl[j] = s;
+                            unsigned long long acc[1] = {f2_pack((j == je) ? -see : 0.f, (MODEL && j == jp) ? sadd : 0.f)};
+                            chunk_acc<1, LC, FACT>(kx, j, xe1, r2, acc);
+                            cl[j] = f2_lo(acc[0]) + f2_hi(acc[0]);
                         }
                     }
                     __syncwarp();
                     if (act && sub == 0) {
                         float run = 0.f;
                         for (int j = 0; j < nch; ++j) { run += cl[j]; cl[j] = run; }
-                        const int vote = finish_draw<LC, MODEL, FACT>(kx, cl, 1, e, u24_from_word(wa), run, xe1[0], ae, ape, ge, prev);
+                        const int vote = finish_draw<LC, MODEL, FACT>(kx, cl, 1, e, u24_from_word(wa), el);
                         atomicAdd(&tally[vote], 1);
                         if (MODEL) votes[e] = vote;
                     }
@@ -512,16 +503,12 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                     const int sel = e & 3;
                     const uint32_t wa = sel == 0 ? w[0] : (sel == 1 ? w[1] : (sel == 2 ? w[2] : w[3]));
                     const float u = u24_from_word(wa);
-                    const int prev = (MODEL && have_prev && has_sticky) ? votes[e] : -1;
-                    float ae = 0.f, ape = 0.f;
-                    if (FACT) { ae = __ldg(tabA + e); ape = __ldg(tabA + CP + e); }
-                    const float xe = FACT ? 0.f : xs[e];
-                    const int ge = reg[e];
+                    const Elector32 el = load_elector(e, sticky_live);
                     int vote;
                     if (fast2) {
                         // two-candidate run-off: columns 0 and 1, renormalised (simulate.py:144-154)
-                        const float v0 = full_score32<MODEL, FACT>(kx, e, 0, xe, ae, ape, ge, prev);
-                        const float v1 = full_score32<MODEL, FACT>(kx, e, 1, xe, ae, ape, ge, prev);
+                        const float v0 = full_score32<MODEL, FACT>(kx, e, 0, el);
+                        const float v1 = full_score32<MODEL, FACT>(kx, e, 1, el);
                         const float sum = v0 + v1;
                         int j;
                         if (!(sum > 0.0f)) j = (u * 2.0f >= 1.0f) ? 1 : 0;       // simulate.py:151 uniform fallback
@@ -530,7 +517,7 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                         vote = j == 0 ? ef0 : ef1;
                     } else {
                         float sum = 0.f;
-                        for (int j = 0; j < k; ++j) sum += full_score32<MODEL, FACT>(kx, e, j, xe, ae, ape, ge, prev);
+                        for (int j = 0; j < k; ++j) sum += full_score32<MODEL, FACT>(kx, e, j, el);
                         int jsel;
                         if (!(sum > 0.0f)) {
                             jsel = (int)(u * (float)k);
@@ -538,7 +525,7 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                             const float tgt = u * sum;
                             float cum = 0.f; jsel = -1; int lastpos = 0;
                             for (int j = 0; j < k; ++j) {
-                                const float v = full_score32<MODEL, FACT>(kx, e, j, xe, ae, ape, ge, prev);
+                                const float v = full_score32<MODEL, FACT>(kx, e, j, el);
                                 cum += v;
                                 if (v > 0.0f) lastpos = j;
                                 if (jsel < 0 && v > 0.0f && cum > tgt) jsel = j;

@@ -1,0 +1,327 @@
+// table.cuh — the TABLE engine (CSIM_ENGINE_TABLE; what CSIM_ENGINE_AUTO picks for the ref_cli wiring).
+//
+// Under the ref_cli wiring the probability matrix depends on (roster, parameters, round) only — it is
+// the same for every trial (the previous round's votes never reach the model).  So the
+// per-round CDF rows are built ONCE per parameter set, with exactly the fp64 arithmetic of the exact
+// engine (model.py:303-486, simulate.py:144-153), and a trial only has to draw:
+//
+//   full-field round r:   vote_e = #{c : cdf_r[e][c] <= u}      binary search over a row of C entries
+//   run-off round r:      vote_e = eff[ #{j < k : cdfk_r[e][j] <= u} ]   (k = 2: one compare with cdfk_r[e][0])
+//
+// Work is organised round-major per CTA: a CTA owns a super-batch of (warps x 32) trials of ONE
+// parameter set; for r = 1..(last full-field round) it stages cdf_r (E x C, 72 KB in fp32 at E = 134)
+// into shared memory once and every warp then plays round r of its 32 trials, one trial at a time with
+// the 32 lanes over electors.  Lane i keeps trial i's state (alive, winner, rounds, run-off pair) in
+// registers.  Rounds of a trial do not depend on each other in this wiring except through "still
+// alive", which is what makes the round-major order legal.  The run-off rounds are then played per
+// trial from a small staged table.  When E x C does not fit in shared memory (cfg-5: 1024 x 1024) the
+// rows are searched in global memory (L2-resident) instead — same code, different base pointer.
+//
+// Real = double: tables are the exact fp64 CDFs and uniforms have 53 bits (tape or Philox): results are
+// bit-identical to the exact engine and to the oracle.  Real = float: the same CDFs rounded once to
+// fp32, 24-bit uniforms: the fast path.
+#pragma once
+#include "common.cuh"
+#include "exact64.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// K0: CDF tables.  One thread per (set, round, elector) row.
+//   cdf  [sets][R][E][C]   full-field rows            (RandomState.choice: cumsum(p) / cumsum(p)[-1])
+//   cdfk [sets][R][E][kmax] run-off rows over the first k columns, renormalised as simulate.py:148-151
+// ---------------------------------------------------------------------------------------------
+template <class F>
+__device__ __forceinline__ void cdf_row_exact64(F& prob, int ncol, double* out) {
+    const double sm = np_pairwise(prob, ncol);                        // simulate.py:148 np.sum(prob_row)
+    const bool close = fabs(sm - 1.0) <= (1e-8 + 1e-5 * 1.0);         // np.isclose(sm, 1.0)
+    const int mode = close ? 0 : (sm > 0.0 ? 1 : 2);                  // simulate.py:151
+    const double unif = 1.0 / (double)ncol;
+    double acc = 0.0;
+    for (int i = 0; i < ncol; ++i) {                                  // cdf = p.cumsum()
+        const double v = mode == 0 ? prob(i) : (mode == 1 ? __ddiv_rn(prob(i), sm) : unif);
+        acc = (i == 0) ? v : __dadd_rn(acc, v);
+        out[i] = acc;
+    }
+    const double last = acc;
+    for (int i = 0; i < ncol; ++i) out[i] = __ddiv_rn(out[i], last);  // cdf /= cdf[-1]
+}
+
+__global__ void k_cdf_tables64(RosterDev ro, const DevSet* sets, const double* W, int R, int kmax,
+                               double* cdf, double* cdfk) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int sr = blockIdx.y;                   // set * R + (round - 1)
+    const int E = ro.E, C = E;
+    if (e >= E) return;
+    const DevSet S = sets[sr / R];
+    Row64 row;
+    row.Wcol = W + (size_t)sr * C * ro.Epad + e; row.Epad = ro.Epad; row.e = e;
+    row.prev = -1; row.sticky = false; row.st1p = 1.0; row.bw = nullptr; row.fat = nullptr; row.fat_pen = 1.0;
+    row.x = ro.x64; row.xe = ro.x64[e]; row.stop_D = 0.0; row.stop_boost = 1.0; row.trig = false; row.degenerate = false;
+    double rs = np_pairwise(row, C);                                  // model.py:451
+    if (rs == 0.0) { row.degenerate = true; rs = np_pairwise(row, C); }
+    Prob64 p{&row, rs};
+    cdf_row_exact64(p, C, cdf + ((size_t)sr * E + e) * C);
+    if (S.k > 0) cdf_row_exact64(p, S.k, cdfk + ((size_t)sr * E + e) * kmax);
+}
+
+__global__ void k_f64_to_f32(const double* in, float* out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = (float)in[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: trials.
+// ---------------------------------------------------------------------------------------------
+template <class Real>
+struct TableArgs {
+    RosterDev ro;
+    BatchDev b;
+    TrialOut out;
+    const Real* cdf;        // [sets][R][E][C]
+    const Real* cdfk;       // [sets][R][E][kmax]
+    int kmax;
+    int warps_per_cta;
+    int stage;              // 1: E x C rows fit in shared memory and are staged per round
+    size_t cta_smem;        // staged table + run-off table
+    size_t warp_smem;
+};
+
+template <class Real>
+__device__ __forceinline__ int upper_bound_row(const Real* row, int n, int step0, Real u) {
+    int pos = 0;                                       // #{i : row[i] <= u}  == searchsorted(row, u, 'right')
+    if (step0 == 128) {                                // 128 <= n <= 255: eight probes, fully unrolled
+#pragma unroll
+        for (int step = 128; step > 0; step >>= 1) {
+            const int np = pos + step;
+            const Real v = row[min(np, n) - 1];
+            pos = (np <= n && v <= u) ? np : pos;
+        }
+        return pos;
+    }
+    for (int step = step0; step > 0; step >>= 1) {
+        const int np = pos + step;
+        if (np <= n && row[np - 1] <= u) pos = np;
+    }
+    return pos;
+}
+
+template <class Real>
+__global__ void __launch_bounds__(256) k_trials_table(TableArgs<Real> a) {
+    constexpr bool F64 = sizeof(Real) == 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int E = a.ro.E, C = E, R = a.b.R, kmax = a.kmax;
+    const int Ei = (E + 3) & ~3;
+    Real* tab_s = (Real*)smem_raw;                               // staged cdf_r  [E][C]   (stage == 1)
+    Real* q_s = tab_s + (a.stage ? (size_t)E * C : 0);           // run-off first-column table [R][E]
+    unsigned char* base = smem_raw + a.cta_smem + (size_t)wib * a.warp_smem;
+    int32_t* tally = (int32_t*)base;            base += sizeof(int32_t) * Ei;
+    int32_t* eff = (int32_t*)base;              base += sizeof(int32_t) * ((kmax + 3) & ~3);
+    uint8_t* mark = (uint8_t*)base;
+
+    const int wpc = a.warps_per_cta;
+    const uint64_t sb_trials = (uint64_t)wpc * 32;                           // trials per super-batch
+    const uint64_t sb_per_set = (a.b.n_sims + sb_trials - 1) / sb_trials;
+    const uint64_t n_sb = sb_per_set * a.b.n_sets;
+    int step0 = 1;
+    while (step0 * 2 <= C) step0 *= 2;
+    const bool top2_ok = C >= 2 && C < 32768;
+
+    // Electors are dealt lane-major (e = 128 g + 32 s + lane) so that the 32 lanes probe 32 different rows at
+    // the same column without bank conflicts (row pitch C is odd at E = 135; the first probes of a binary search
+    // all hit the same column).  Lane l computes the Philox call of quad 32 g + l; the word of elector e lives
+    // in lane (e >> 2) & 31 and is fetched with four shuffles.
+    const int n_groups = (E + 127) >> 7;
+    auto for_each_elector = [&](int r, uint64_t t, uint32_t s_lo, uint32_t s_hi, auto&& fn) {
+        const bool use_tape = F64 && a.b.tape != nullptr;
+        for (int gi = 0; gi < n_groups; ++gi) {
+            uint32_t w[4] = {0, 0, 0, 0}, wb[4] = {0, 0, 0, 0};
+            if (!use_tape) {
+                const uint32_t q = (uint32_t)(32 * gi + lane);
+                philox4x32_10(s_lo, s_hi, (uint32_t)r, q, a.b.seed_lo, a.b.seed_hi, w);
+                if (F64) philox4x32_10(s_lo, s_hi, (uint32_t)r, q | 0x80000000u, a.b.seed_lo, a.b.seed_hi, wb);
+            }
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl) {
+                const int e = 128 * gi + 32 * sl + lane;
+                const int src = 8 * sl + (lane >> 2), sel = lane & 3;
+                const uint32_t a0 = __shfl_sync(CSIM_FULL, w[0], src), a1 = __shfl_sync(CSIM_FULL, w[1], src);
+                const uint32_t a2 = __shfl_sync(CSIM_FULL, w[2], src), a3 = __shfl_sync(CSIM_FULL, w[3], src);
+                const uint32_t wa = sel == 0 ? a0 : (sel == 1 ? a1 : (sel == 2 ? a2 : a3));
+                uint32_t wbb = 0;
+                if (F64) {
+                    const uint32_t b0 = __shfl_sync(CSIM_FULL, wb[0], src), b1 = __shfl_sync(CSIM_FULL, wb[1], src);
+                    const uint32_t b2 = __shfl_sync(CSIM_FULL, wb[2], src), b3 = __shfl_sync(CSIM_FULL, wb[3], src);
+                    wbb = sel == 0 ? b0 : (sel == 1 ? b1 : (sel == 2 ? b2 : b3));
+                }
+                if (e < E) {
+                    Real u;
+                    if (use_tape) u = (Real)a.b.tape[(t * (uint64_t)R + (uint64_t)(r - 1)) * (uint64_t)E + e];
+                    else u = F64 ? (Real)u53_from_words(wa, wbb) : (Real)u24_from_word(wa);
+                    fn(e, u);
+                }
+            }
+        }
+    };
+
+    for (uint64_t sb = blockIdx.x; sb < n_sb; sb += gridDim.x) {
+        const int set = (int)(sb / sb_per_set);
+        const uint64_t i0 = (sb % sb_per_set) * sb_trials + (uint64_t)wib * 32;     // first sim index of this warp's batch
+        const DevSet S = a.b.sets[set];
+        const int k = S.k, need = S.need, rr = S.rr;
+        const int r_full = k > 0 ? min(R, max(rr, 1)) : R;       // rounds 1..r_full are full-field (round 1 always is)
+        const bool fast2 = (k == 2) && top2_ok;
+        // lane i holds the state of trial i0 + i
+        const uint64_t my_i = i0 + lane;
+        bool alive = my_i < a.b.n_sims;
+        const bool exists = alive;
+        int winner = -1, rounds = 0, ef0 = 0, ef1 = 0;
+        const uint64_t my_t = (uint64_t)set * a.b.n_sims + my_i;
+
+        // stage the run-off first-column table (k == 2 fast path) once per super-batch
+        __syncthreads();
+        if (fast2)
+            for (int i = threadIdx.x; i < R * E; i += blockDim.x) q_s[i] = a.cdfk[(((size_t)set * R) * E + i) * kmax];
+
+        // =============== full-field rounds, round-major ===========================================
+        for (int r = 1; r <= r_full; ++r) {
+            const Real* tab_g = a.cdf + ((size_t)set * R + (r - 1)) * (size_t)E * C;
+            if (a.stage) {
+                __syncthreads();                                  // previous round's readers are done
+                for (size_t i = threadIdx.x; i < (size_t)E * C; i += blockDim.x) tab_s[i] = tab_g[i];
+            }
+            __syncthreads();
+            const Real* tab = a.stage ? tab_s : tab_g;
+            if (!__any_sync(CSIM_FULL, alive)) continue;
+            for (int ti = 0; ti < 32; ++ti) {
+                if (!__shfl_sync(CSIM_FULL, alive ? 1 : 0, ti)) continue;
+                const uint64_t sim = a.b.sim_id_begin + i0 + ti;
+                const uint64_t t = (uint64_t)set * a.b.n_sims + i0 + ti;
+                const uint32_t s_lo = (uint32_t)sim, s_hi = (uint32_t)(sim >> 32);
+                for (int c = lane; c < C; c += 32) tally[c] = 0;
+                __syncwarp();
+                for_each_elector(r, t, s_lo, s_hi, [&](int e, Real u) {
+                    int vote = upper_bound_row<Real>(tab + (size_t)e * C, C, step0, u);
+                    vote = vote < C ? vote : C - 1;
+                    atomicAdd(&tally[vote], 1);
+                });
+                __syncwarp();
+                if (a.out.round_tallies)
+                    for (int c = lane; c < C; c += 32)
+                        a.out.round_tallies[(t * (uint64_t)R + (uint64_t)(r - 1)) * (uint64_t)C + c] = tally[c];
+                int mx, arg, second = 0;
+                if (top2_ok) {
+                    uint32_t k1, k2;
+                    warp_top2(tally, C, lane, k1, k2);
+                    mx = (int)(k1 >> 16); arg = 0xFFFF - (int)(k1 & 0xFFFFu); second = 0xFFFF - (int)(k2 & 0xFFFFu);
+                } else {
+                    warp_argmax_first(tally, C, lane, mx, arg);
+                }
+                const bool won = mx >= need;                                        // simulate.py:174-180
+                const bool last = won || r == R;
+                if (last && a.out.final_votes) for (int c = lane; c < C; c += 32) a.out.final_votes[t * (uint64_t)C + c] = tally[c];
+                if (lane == ti) {
+                    rounds = r;
+                    if (won) { winner = arg; alive = false; }
+                    else if (r == R) { alive = false; }
+                    else if (r >= rr && k > 0) { ef0 = arg; ef1 = second; }          // simulate.py:183-186 (k == 2)
+                }
+                __syncwarp();
+            }
+        }
+        // =============== run-off rounds, per trial =================================================
+        if (k > 0 && r_full < R) {
+            for (int ti = 0; ti < 32; ++ti) {
+                if (!__shfl_sync(CSIM_FULL, alive ? 1 : 0, ti)) continue;
+                const uint64_t sim = a.b.sim_id_begin + i0 + ti;
+                const uint64_t t = (uint64_t)set * a.b.n_sims + i0 + ti;
+                const uint32_t s_lo = (uint32_t)sim, s_hi = (uint32_t)(sim >> 32);
+                int e0 = __shfl_sync(CSIM_FULL, ef0, ti), e1 = __shfl_sync(CSIM_FULL, ef1, ti);
+                int win = -1, rnd = r_full;
+                if (!fast2) {
+                    // generic k: rebuild round r_full's stable top-k from its tally: replay that round's draws
+                    // (rare path; k != 2).  The tally is recomputed exactly as in the loop above.
+                    const Real* tab_g = a.cdf + ((size_t)set * R + (r_full - 1)) * (size_t)E * C;
+                    for (int c = lane; c < C; c += 32) tally[c] = 0;
+                    __syncwarp();
+                    for_each_elector(r_full, t, s_lo, s_hi, [&](int e, Real u) {
+                        const int vote = upper_bound_row<Real>(tab_g + (size_t)e * C, C, step0, u);
+                        atomicAdd(&tally[vote < C ? vote : C - 1], 1);
+                    });
+                    __syncwarp();
+                    warp_top_k(tally, C, k, lane, eff, mark);
+                    __syncwarp();
+                }
+                for (int r = r_full + 1; r <= R; ++r) {
+                    rnd = r;
+                    int cnt0 = 0;
+                    if (!fast2) { for (int c = lane; c < C; c += 32) tally[c] = 0; __syncwarp(); }
+                    for_each_elector(r, t, s_lo, s_hi, [&](int e, Real u) {
+                        if (fast2) {
+                            cnt0 += (q_s[(r - 1) * E + e] <= u) ? 0 : 1;             // j = #{cdf_j <= u}; vote eff[0] iff cdf_0 > u
+                        } else {
+                            const Real* rowk = a.cdfk + (((size_t)set * R + (r - 1)) * E + e) * kmax;
+                            int j = 0;
+                            for (int i = 0; i < k; ++i) j += (rowk[i] <= u) ? 1 : 0;
+                            atomicAdd(&tally[eff[j < k ? j : k - 1]], 1);
+                        }
+                    });
+                    int mx, arg, second;
+                    if (fast2) {
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) cnt0 += __shfl_xor_sync(CSIM_FULL, cnt0, off);
+                        const int n0 = cnt0, n1 = E - cnt0;
+                        if (a.out.round_tallies || a.out.final_votes) {
+                            for (int c = lane; c < C; c += 32) tally[c] = 0;
+                            __syncwarp();
+                            if (lane == 0) { tally[e0] = n0; tally[e1] = n1; }
+                            __syncwarp();
+                        }
+                        if (n0 > 0 && n1 > 0) {
+                            const bool first0 = n0 > n1 || (n0 == n1 && e0 < e1);
+                            mx = first0 ? n0 : n1; arg = first0 ? e0 : e1; second = first0 ? e1 : e0;
+                        } else {
+                            // one of the pair got nothing: the second place is the lowest-index zero-tally candidate
+                            for (int c = lane; c < C; c += 32) tally[c] = 0;
+                            __syncwarp();
+                            if (lane == 0) { tally[e0] = n0; tally[e1] = n1; }
+                            __syncwarp();
+                            uint32_t k1, k2;
+                            warp_top2(tally, C, lane, k1, k2);
+                            mx = (int)(k1 >> 16); arg = 0xFFFF - (int)(k1 & 0xFFFFu); second = 0xFFFF - (int)(k2 & 0xFFFFu);
+                        }
+                    } else {
+                        __syncwarp();
+                        warp_argmax_first(tally, C, lane, mx, arg);
+                        second = 0;
+                    }
+                    if (a.out.round_tallies)
+                        for (int c = lane; c < C; c += 32)
+                            a.out.round_tallies[(t * (uint64_t)R + (uint64_t)(r - 1)) * (uint64_t)C + c] = tally[c];
+                    const bool won = mx >= need;
+                    if ((won || r == R) && a.out.final_votes)
+                        for (int c = lane; c < C; c += 32) a.out.final_votes[t * (uint64_t)C + c] = tally[c];
+                    if (won) { win = arg; break; }
+                    if (fast2) { e0 = arg; e1 = second; }
+                    else { warp_top_k(tally, C, k, lane, eff, mark); }
+                    __syncwarp();
+                }
+                if (lane == ti) { winner = win; rounds = rnd; alive = false; }
+                __syncwarp();
+            }
+        }
+        // =============== outputs ===================================================================
+        if (exists) {
+            a.out.winner[my_t] = winner; a.out.rounds[my_t] = rounds;
+            if (a.out.reason) a.out.reason[my_t] = (uint8_t)(winner >= 0 ? CSIM_REASON_WINNER : CSIM_REASON_MAX_ROUNDS);
+            if (a.out.winner_hist) atomicAdd(&a.out.winner_hist[(size_t)set * (C + 1) + (winner >= 0 ? winner : C)], 1ULL);
+            if (a.out.rounds_hist && winner >= 0) atomicAdd(&a.out.rounds_hist[(size_t)set * (R + 1) + rounds], 1ULL);
+            if (a.out.round_tallies)
+                for (size_t i = (size_t)rounds * C; i < (size_t)R * C; ++i) a.out.round_tallies[my_t * (uint64_t)R * C + i] = -1;
+        }
+        if (a.out.totals) {
+            unsigned long long rs = exists ? (unsigned long long)rounds : 0ULL, ts = exists ? 1ULL : 0ULL;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) { rs += __shfl_xor_sync(CSIM_FULL, rs, off); ts += __shfl_xor_sync(CSIM_FULL, ts, off); }
+            if (lane == 0 && ts) { atomicAdd(&a.out.totals[2 * set], rs); atomicAdd(&a.out.totals[2 * set + 1], ts); }
+        }
+    }
+}

@@ -57,6 +57,12 @@ def lib():
     return _lib
 
 
+def set_faithful(on: bool) -> None:
+    """True: co_run re-evaluates the whole E x C matrix per trial per round like the reference does
+    (no trial-invariant tables).  Same results, reference-like cost; used for the CPU baseline."""
+    lib().co_set_faithful(C.c_int(1 if on else 0))
+
+
 def to_cparams(mp, ep) -> CParams:
     """mp/ep: oracle.conclave_oracle.ModelParams / EngineParams."""
     p = CParams()

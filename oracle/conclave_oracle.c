@@ -29,7 +29,14 @@
 #endif
 #include "conclave_b200.h"
 
-int co_version(void) { return 1; }
+int co_version(void) { return 2; }
+
+/* co_set_faithful(1): co_run re-evaluates the whole E x C matrix (exp included) for every trial and every
+ * round, exactly as the reference does (simulate.py:121 calls the model each round; model.py:311-486),
+ * instead of using trial-invariant per-round tables.  Results are identical; only the cost differs.
+ * This is the mode the cpu_baseline / --impl reference legs of bench.py time. */
+static int g_faithful = 0;
+void co_set_faithful(int on) { g_faithful = on; }
 
 /* ---------------- beta schedule: model.py:562-580 ---------------- */
 static double beta_step(const csim_params* p, double beta, int r) {
@@ -287,7 +294,8 @@ int co_run(int E, const double* x, const int32_t* region, const uint8_t* pap,
         double* W = (double*)malloc(sizeof(double) * EC * (size_t)(R > 0 ? R : 1));   /* base scores (model wiring) or P (ref_cli) */
         double* cdf_full = NULL; double* cdf_run = NULL;
         if (!W) { free(betas); return -1; }
-        if (wiring == CSIM_WIRING_REF_CLI) {
+        const int tables = (wiring == CSIM_WIRING_REF_CLI) && !g_faithful;
+        if (tables) {
             cdf_full = (double*)malloc(sizeof(double) * EC * (size_t)R);
             cdf_run = (double*)malloc(sizeof(double) * (size_t)E * (k > 0 ? k : 1) * (size_t)R);
             if (!cdf_full || !cdf_run) { free(betas); free(W); free(cdf_full); free(cdf_run); return -1; }
@@ -321,7 +329,9 @@ int co_run(int E, const double* x, const int32_t* region, const uint8_t* pap,
             double* P = NULL; double* bw = NULL; double* cdf = NULL; int32_t* hist = NULL;
             uint8_t* fat = NULL; uint8_t* immune = NULL; double* avg = NULL; double* shares = NULL;
             const int32_t** last = NULL;
-            if (wiring == CSIM_WIRING_MODEL) {
+            double* Wt = NULL;
+            if (g_faithful) Wt = (double*)malloc(sizeof(double) * EC);
+            if (!tables) {
                 P = (double*)malloc(sizeof(double) * EC); bw = (double*)malloc(sizeof(double) * E);
                 cdf = (double*)malloc(sizeof(double) * C);
                 hist = (int32_t*)malloc(sizeof(int32_t) * (size_t)(F > 0 ? F : 1) * C);
@@ -343,18 +353,21 @@ int co_run(int E, const double* x, const int32_t* region, const uint8_t* pap,
                     rr = r;
                     if (tape) memcpy(u, tape + (t * (uint64_t)R + (uint64_t)(r - 1)) * (uint64_t)E, sizeof(double) * E);
                     else co_philox_uniforms(seed, sim, r, E, u);
-                    if (wiring == CSIM_WIRING_MODEL) {
+                    if (!tables) {
+                        const int live = wiring == CSIM_WIRING_MODEL;
+                        const double* Wr = W + EC * (r - 1);
+                        if (g_faithful) { base_scores(E, x, region, pap, p, betas[r - 1], Wt); Wr = Wt; }
                         int nh = n_hist < F ? n_hist : F;
                         for (int q = 0; q < nh; ++q) last[q] = hist + (size_t)((n_hist - nh + q) % (F > 0 ? F : 1)) * C;
                         fatigue_mask(p, r, n_hist, hist, last, nh, C, E, fat, immune, avg);
                         for (int c = 0; c < C; ++c) shares[c] = have_prev ? (double)tally[c] / (double)E : 0.0;
-                        finish_matrix(E, x, p, W + EC * (r - 1), have_prev ? votes : NULL, have_prev ? tally : NULL,
-                                      fat, shares, P, bw);
+                        finish_matrix(E, x, p, Wr, (live && have_prev) ? votes : NULL, (live && have_prev) ? tally : NULL,
+                                      live ? fat : NULL, live ? shares : NULL, P, bw);
                     }
                     /* all E draws of the round are made against round r-1's state; prev votes stay intact until then */
                     for (int e = 0; e < E; ++e) {
                         int j;
-                        if (wiring == CSIM_WIRING_REF_CLI) {
+                        if (tables) {
                             if (!have_eff) j = upper_bound(cdf_full + EC * (r - 1) + (size_t)e * C, C, u[e]);
                             else j = eff[upper_bound(cdf_run + ((size_t)(r - 1) * E + e) * k, k, u[e])];
                         } else {
@@ -391,7 +404,7 @@ int co_run(int E, const double* x, const int32_t* region, const uint8_t* pap,
                 if (totals) { totals[2 * set] += tot_rounds; totals[2 * set + 1] += tot_trials; }
             }
             free(cur); free(tally); free(votes); free(eff); free(used); free(u); free(P); free(bw); free(cdf); free(hist);
-            free(fat); free(immune); free(avg); free(shares); free((void*)last); free(wh); free(rh);
+            free(fat); free(immune); free(avg); free(shares); free((void*)last); free(wh); free(rh); free(Wt);
         }
         free(betas); free(W); free(cdf_full); free(cdf_run);
     }

@@ -54,6 +54,9 @@ def upload(eng, roster):
     eng.upload_roster(roster.ideology, roster.region, roster.papabile)
 
 
+ENGINES = {"dense": 1, "table": 2}
+
+
 CFG2 = dict(initial_beta_weight=1.5, enable_dynamic_beta=True, beta_increment_amount=0.3,
             beta_increment_interval_rounds=1, stickiness_factor=0.8, bandwagon_strength=0.7,
             regional_affinity_bonus=0.1, papabile_weight_factor=2.0)
@@ -110,8 +113,16 @@ def test_engine_bit_exact_under_reference_tapes(eng, case):
     upload(eng, case["roster"])
     tapes = G.case_tapes(case)
     p = to_params(case["mp"], case["ep"])
-    out = eng.run([p], case["n"], wiring=case["wiring"], precision=FP64, tapes=tapes, want_round_tallies=True,
-                  want_final_votes=True)
+    engines = ["dense", "table"] if case["wiring"] == O.WIRING_REF_CLI else ["dense"]
+    for en in engines:
+        out = eng.run([p], case["n"], wiring=case["wiring"], engine=ENGINES[en], precision=FP64, tapes=tapes,
+                      want_round_tallies=True, want_final_votes=True)
+        _check_case(case, out)
+    ref = CO.run(case["roster"], [(case["mp"], case["ep"])], case["wiring"], case["n"], tapes=tapes, want_tallies=True)
+    assert np.array_equal(out.winner, ref["winner"]) and np.array_equal(out.round_tallies, ref["round_tallies"])
+
+
+def _check_case(case, out):
     ok = ~case["fatigue_tie"]
     assert ok.any() or case["name"] == "m_cfg2_fatigue"
     assert np.array_equal(out.winner[ok], case["winners"][ok])
@@ -120,20 +131,19 @@ def test_engine_bit_exact_under_reference_tapes(eng, case):
     assert np.array_equal(out.round_tallies[ok], case["tallies"][ok])
     for i in np.where(ok)[0]:
         assert np.array_equal(out.final_votes[i], case["tallies"][i, case["rounds"][i] - 1])
-    # fatigue-tie trials: the reference's own pick is numpy-sort dependent; ours must equal the oracle's rule
-    ref = CO.run(case["roster"], [(case["mp"], case["ep"])], case["wiring"], case["n"], tapes=tapes, want_tallies=True)
-    assert np.array_equal(out.winner, ref["winner"]) and np.array_equal(out.round_tallies, ref["round_tallies"])
+    # (fatigue-tie trials: the reference's own pick is numpy-sort dependent; the caller checks them against the oracle's rule)
 
 
 # ------------------------------------------------------------------ native stream, larger N
-@pytest.mark.parametrize("wiring,n", [(O.WIRING_REF_CLI, 20000), (O.WIRING_MODEL, 1500)])
-def test_fp64_native_stream_bit_exact_vs_oracle(eng, wiring, n):
+@pytest.mark.parametrize("wiring,n,engine", [(O.WIRING_REF_CLI, 20000, "dense"), (O.WIRING_REF_CLI, 100000, "table"),
+                                             (O.WIRING_MODEL, 1500, "dense")])
+def test_fp64_native_stream_bit_exact_vs_oracle(eng, wiring, n, engine):
     from conclave_sim_b200 import FP64
     roster = G.real_roster()
     upload(eng, roster)
     mp = O.ModelParams(**CFG2)
-    out = eng.run([to_params(mp, EP2)], n, seed=20250507, sim_id_begin=10**9, wiring=wiring, precision=FP64,
-                  want_final_votes=True)
+    out = eng.run([to_params(mp, EP2)], n, seed=20250507, sim_id_begin=10**9, wiring=wiring, engine=ENGINES[engine],
+                  precision=FP64, want_final_votes=True)
     ref = CO.run(roster, [(mp, EP2)], wiring, n, seed=20250507, sim_id_begin=10**9)
     assert np.array_equal(out.winner, ref["winner"])
     assert np.array_equal(out.rounds, ref["rounds"])
@@ -163,8 +173,8 @@ def test_param_sets_batching_and_sharding_independence(eng):
     from oracle.gen_golden import CFG1
     sets = [(O.ModelParams(**CFG2), EP2), (O.ModelParams(**CFG1), O.EngineParams(max_rounds=20, supermajority_threshold=2 / 3))]
     ps = [to_params(*s) for s in sets]
-    for prec in (FP64, FP32):
-        full = eng.run(ps, 400, seed=11, precision=prec)
+    for prec, en in ((FP64, 1), (FP32, 1), (FP64, 2), (FP32, 2)):
+        full = eng.run(ps, 400, seed=11, precision=prec, engine=en)
         w = full.winner.reshape(2, 400); r = full.rounds.reshape(2, 400)
         for s in range(2):
             assert full.winner_hist[s, :134].sum() == (w[s] >= 0).sum() and full.winner_hist[s, 134] == (w[s] < 0).sum()
@@ -172,7 +182,7 @@ def test_param_sets_batching_and_sharding_independence(eng):
             assert full.totals[s, 0] == r[s].sum() and full.totals[s, 1] == 400
         assert (w[1] < 0).all() and (r[1] == 20).all()      # cfg-1: nobody reaches 2/3
         # a shard of the sim-id range gives the same trials (what multi-GPU sharding relies on)
-        part = eng.run(ps[:1], 150, seed=11, sim_id_begin=200, precision=prec)
+        part = eng.run(ps[:1], 150, seed=11, sim_id_begin=200, precision=prec, engine=en)
         assert np.array_equal(part.winner, w[0][200:350]) and np.array_equal(part.rounds, r[0][200:350])
     if True:
         ref = CO.run(roster, sets, O.WIRING_REF_CLI, 400, seed=11)
@@ -181,13 +191,14 @@ def test_param_sets_batching_and_sharding_independence(eng):
 
 
 # ------------------------------------------------------------------ fp32 fast path
-@pytest.mark.parametrize("wiring,n", [(O.WIRING_REF_CLI, 20000), (O.WIRING_MODEL, 4000)])
-def test_fp32_agrees_with_oracle_per_trial(eng, wiring, n):
+@pytest.mark.parametrize("wiring,n,engine", [(O.WIRING_REF_CLI, 20000, "dense"), (O.WIRING_REF_CLI, 20000, "table"),
+                                             (O.WIRING_MODEL, 4000, "dense")])
+def test_fp32_agrees_with_oracle_per_trial(eng, wiring, n, engine):
     from conclave_sim_b200 import FP32
     roster = G.real_roster()
     upload(eng, roster)
     mp = O.ModelParams(**CFG2)
-    out = eng.run([to_params(mp, EP2)], n, seed=5, wiring=wiring, precision=FP32, want_final_votes=True)
+    out = eng.run([to_params(mp, EP2)], n, seed=5, wiring=wiring, engine=ENGINES[engine], precision=FP32, want_final_votes=True)
     ref = CO.run(roster, [(mp, EP2)], wiring, n, seed=5)
     same = (out.winner == ref["winner"]) & (out.rounds == ref["rounds"]) & (out.final_votes == ref["final_votes"]).all(axis=1)
     # 24-bit uniforms + fp32 sums flip ~1e-5 of the draws; a flipped draw may change the trial
@@ -209,8 +220,8 @@ def _chi2_homogeneity(a, b, min_expected=5.0):
     return stats.chi2_contingency(np.stack([a[keep], b[keep]]))[1]
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp64"])
-def test_distribution_matches_reference_sample(eng, precision):
+@pytest.mark.parametrize("precision,engine", [("fp32", "dense"), ("fp32", "table"), ("fp64", "table")])
+def test_distribution_matches_reference_sample(eng, precision, engine):
     """north_star: 'Under the native RNG, winner and rounds distributions must pass a
     chi-square/KS test at p>0.01 against the reference's own CPU run.'"""
     from scipy import stats
@@ -219,9 +230,9 @@ def test_distribution_matches_reference_sample(eng, precision):
         ref = json.load(f)
     roster = G.real_roster()
     upload(eng, roster)
-    n = 1_000_000 if precision == "fp32" else 200_000
+    n = 1_000_000
     out = eng.run([to_params(O.ModelParams(**CFG2), EP2)], n, seed=987654321, precision=FP32 if precision == "fp32" else FP64,
-                  want_reason=False)
+                  engine=ENGINES[engine], want_reason=False)
     gw = np.concatenate([out.winner_hist[0, :134], [out.winner_hist[0, 134]]])
     rw = np.concatenate([ref["winner_hist"], [ref["no_winner"]]])
     p_w = _chi2_homogeneity(gw, rw)
@@ -232,7 +243,7 @@ def test_distribution_matches_reference_sample(eng, precision):
     g_rounds = np.repeat(np.arange(21), out.rounds_hist[0])
     r_rounds = np.repeat(np.arange(21), ref["rounds_hist_success"])
     p_ks = stats.ks_2samp(g_rounds, r_rounds).pvalue
-    print(f"[{precision}] chi2 winners p={p_w:.4f}  chi2 rounds p={p_r:.4f}  KS rounds p={p_ks:.4f}  "
+    print(f"[{precision}/{engine}] chi2 winners p={p_w:.4f}  chi2 rounds p={p_r:.4f}  KS rounds p={p_ks:.4f}  "
           f"success gpu={1 - gw[-1] / n:.4f} ref={1 - ref['no_winner'] / ref['n']:.4f}")
     assert p_w > 0.01 and p_r > 0.01 and p_ks > 0.01
 
@@ -245,15 +256,16 @@ def test_edge_rosters(eng):
         upload(eng, roster)
         mp = O.ModelParams(**CFG2)
         ep = O.EngineParams(max_rounds=9, supermajority_threshold=0.56, runoff_threshold_rounds=3)
-        out = eng.run([to_params(mp, ep)], 64, seed=1, precision=FP64, want_round_tallies=True)
         ref = CO.run(roster, [(mp, ep)], O.WIRING_REF_CLI, 64, seed=1, want_tallies=True)
-        assert np.array_equal(out.winner, ref["winner"]) and np.array_equal(out.round_tallies, ref["round_tallies"]), E
-        o32 = eng.run([to_params(mp, ep)], 256, seed=1, precision=FP32, want_round_tallies=True)
         r32 = CO.run(roster, [(mp, ep)], O.WIRING_REF_CLI, 256, seed=1, want_tallies=True)
-        played = o32.round_tallies[:, 0, :]
-        assert (played.sum(axis=1) == E).all()                 # every elector votes exactly once per round
-        if E > 1:
-            assert np.mean(o32.winner == r32["winner"]) > 0.85, (E, np.mean(o32.winner == r32["winner"]))
+        for en in (1, 2):
+            out = eng.run([to_params(mp, ep)], 64, seed=1, precision=FP64, engine=en, want_round_tallies=True)
+            assert np.array_equal(out.winner, ref["winner"]) and np.array_equal(out.round_tallies, ref["round_tallies"]), (E, en)
+            o32 = eng.run([to_params(mp, ep)], 256, seed=1, precision=FP32, engine=en, want_round_tallies=True)
+            played = o32.round_tallies[:, 0, :]
+            assert (played.sum(axis=1) == E).all()                 # every elector votes exactly once per round
+            if E > 1:
+                assert np.mean(o32.winner == r32["winner"]) > 0.85, (E, en, np.mean(o32.winner == r32["winner"]))
 
 
 def test_large_roster_cfg5_shape(eng):
@@ -264,13 +276,14 @@ def test_large_roster_cfg5_shape(eng):
     mp = O.ModelParams(**CFG2)
     ep = O.EngineParams(max_rounds=8, supermajority_threshold=0.56)
     ref = CO.run(roster, [(mp, ep)], O.WIRING_REF_CLI, 48, seed=9, want_tallies=True)
-    out = eng.run([to_params(mp, ep)], 48, seed=9, precision=FP64, want_round_tallies=True)
-    assert np.array_equal(out.winner, ref["winner"]) and np.array_equal(out.round_tallies, ref["round_tallies"])
-    o32 = eng.run([to_params(mp, ep)], 48, seed=9, precision=FP32, want_round_tallies=True)
-    first = o32.round_tallies[:, 0, :]
-    assert (first.sum(axis=1) == 1024).all()
-    # round-1 tallies of the two precisions differ in at most a handful of votes
-    assert np.abs(first - ref["round_tallies"][:, 0, :]).sum(axis=1).mean() < 4.0
+    for en in (1, 2):     # the table engine searches its rows in global memory here (1024 x 1024 does not fit in smem)
+        out = eng.run([to_params(mp, ep)], 48, seed=9, precision=FP64, engine=en, want_round_tallies=True)
+        assert np.array_equal(out.winner, ref["winner"]) and np.array_equal(out.round_tallies, ref["round_tallies"])
+        o32 = eng.run([to_params(mp, ep)], 48, seed=9, precision=FP32, engine=en, want_round_tallies=True)
+        first = o32.round_tallies[:, 0, :]
+        assert (first.sum(axis=1) == 1024).all()
+        # round-1 tallies of the two precisions differ in at most a handful of votes
+        assert np.abs(first - ref["round_tallies"][:, 0, :]).sum(axis=1).mean() < 4.0
 
 
 # ------------------------------------------------------------------ the reference-facing Python API

@@ -85,3 +85,16 @@ def test_histograms_and_param_sets():
     # same sims in one set alone give the same results (independent of batching)
     solo = CO.run(roster, sets[:1], O.WIRING_REF_CLI, 50, seed=5, sim_id_begin=100)
     assert np.array_equal(solo["winner"], w[0][100:150]) and np.array_equal(solo["rounds"], r[0][100:150])
+
+
+def test_faithful_mode_gives_identical_results():
+    from oracle.gen_golden import CFG2
+    roster = G.real_roster()
+    sets = [(O.ModelParams(**CFG2), O.EngineParams(max_rounds=20, supermajority_threshold=0.56))]
+    a = CO.run(roster, sets, O.WIRING_REF_CLI, 60, seed=3, want_tallies=True)
+    CO.set_faithful(True)
+    try:
+        b = CO.run(roster, sets, O.WIRING_REF_CLI, 60, seed=3, want_tallies=True)
+    finally:
+        CO.set_faithful(False)
+    assert np.array_equal(a["winner"], b["winner"]) and np.array_equal(a["round_tallies"], b["round_tallies"])
