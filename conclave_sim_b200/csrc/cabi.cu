@@ -406,10 +406,12 @@ static csim_status launch_table_t(csim_ctx* c, const BatchDev& b, const TrialOut
     const size_t qtab = (((size_t)b.R * E * sizeof(Real)) + 15) & ~(size_t)15;
     const size_t full = (((size_t)E * E * sizeof(Real)) + 15) & ~(size_t)15;
     int wpc = 8;
-    a.stage = (full + qtab + a.warp_smem * wpc <= 200 * 1024) ? 1 : 0;
-    a.cta_smem = (a.stage ? full : 0) + qtab;
+    a.stage_q = (qtab + a.warp_smem * wpc <= 64 * 1024) ? 1 : 0;
+    a.stage = (a.stage_q && full + qtab + a.warp_smem * wpc <= 200 * 1024) ? 1 : 0;
+    a.cta_smem = (a.stage ? full : 0) + (a.stage_q ? qtab : 0);
+    while (wpc > 1 && a.cta_smem + a.warp_smem * wpc > 220 * 1024) --wpc;
     if (a.cta_smem + a.warp_smem * wpc > 220 * 1024)
-        return fail(CSIM_ERR_UNSUPPORTED, "table engine: %d rounds x %d electors do not fit in shared memory", b.R, E);
+        return fail(CSIM_ERR_UNSUPPORTED, "table engine: a roster of %d electors does not fit in shared memory", E);
     a.warps_per_cta = wpc;
     const size_t smem = a.cta_smem + a.warp_smem * wpc;
     auto kern = k_trials_table<Real>;

@@ -80,6 +80,7 @@ struct TableArgs {
     int kmax;
     int warps_per_cta;
     int stage;              // 1: E x C rows fit in shared memory and are staged per round
+    int stage_q;            // 1: the [R][E] run-off first-column table is staged too
     size_t cta_smem;        // staged table + run-off table
     size_t warp_smem;
 };
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(256) k_trials_table(TableArgs<Real> a) {
 
         // stage the run-off first-column table (k == 2 fast path) once per super-batch
         __syncthreads();
-        if (fast2)
+        if (fast2 && a.stage_q)
             for (int i = threadIdx.x; i < R * E; i += blockDim.x) q_s[i] = a.cdfk[(((size_t)set * R) * E + i) * kmax];
 
         // =============== full-field rounds, round-major ===========================================
@@ -256,7 +257,8 @@ __global__ void __launch_bounds__(256) k_trials_table(TableArgs<Real> a) {
                     if (!fast2) { for (int c = lane; c < C; c += 32) tally[c] = 0; __syncwarp(); }
                     for_each_elector(r, t, s_lo, s_hi, [&](int e, Real u) {
                         if (fast2) {
-                            cnt0 += (q_s[(r - 1) * E + e] <= u) ? 0 : 1;             // j = #{cdf_j <= u}; vote eff[0] iff cdf_0 > u
+                            const Real q0 = a.stage_q ? q_s[(r - 1) * E + e] : a.cdfk[(((size_t)set * R + (r - 1)) * E + e) * kmax];
+                            cnt0 += (q0 <= u) ? 0 : 1;                               // j = #{cdf_j <= u}; vote eff[0] iff cdf_0 > u
                         } else {
                             const Real* rowk = a.cdfk + (((size_t)set * R + (r - 1)) * E + e) * kmax;
                             int j = 0;

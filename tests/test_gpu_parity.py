@@ -274,7 +274,7 @@ def test_large_roster_cfg5_shape(eng):
     roster = O.synthetic_roster(1024)
     upload(eng, roster)
     mp = O.ModelParams(**CFG2)
-    ep = O.EngineParams(max_rounds=8, supermajority_threshold=0.56)
+    ep = O.EngineParams(max_rounds=8, supermajority_threshold=0.56, runoff_threshold_rounds=3)
     ref = CO.run(roster, [(mp, ep)], O.WIRING_REF_CLI, 48, seed=9, want_tallies=True)
     for en in (1, 2):     # the table engine searches its rows in global memory here (1024 x 1024 does not fit in smem)
         out = eng.run([to_params(mp, ep)], 48, seed=9, precision=FP64, engine=en, want_round_tallies=True)
@@ -327,3 +327,18 @@ def test_microbench_runs(eng):
     for kind in (0, 1, 2):
         g = eng.microbench(kind)
         assert g > 100.0     # giga thread-instructions per second
+
+
+def test_table_engine_without_shared_memory_staging(eng):
+    """Roster / round count too large for shared memory: CDF rows and the run-off table are read from global memory."""
+    from conclave_sim_b200 import FP32, FP64
+    roster = O.synthetic_roster(300, seed=4)
+    upload(eng, roster)
+    mp = O.ModelParams(**CFG2)
+    ep = O.EngineParams(max_rounds=60, supermajority_threshold=0.75, runoff_threshold_rounds=4)
+    ref = CO.run(roster, [(mp, ep)], O.WIRING_REF_CLI, 40, seed=21, want_tallies=True)
+    out = eng.run([to_params(mp, ep)], 40, seed=21, precision=FP64, engine=ENGINES["table"], want_round_tallies=True)
+    assert np.array_equal(out.winner, ref["winner"]) and np.array_equal(out.rounds, ref["rounds"])
+    assert np.array_equal(out.round_tallies, ref["round_tallies"])
+    o32 = eng.run([to_params(mp, ep)], 40, seed=21, precision=FP32, engine=ENGINES["table"])
+    assert np.mean(o32.rounds == ref["rounds"]) > 0.8
