@@ -262,7 +262,11 @@ def main():
                 "algorithmic": f"{FP32_PER_PAIR} FP32-pipe instr per (elector,candidate) pair evaluation (SURVEY 8d); "
                                f"{pairs_per_launch:.4g} pair evaluations per launch (E*C in full-field rounds, E*k in run-off rounds)",
                 "peak_source": peak_src, "kernel_ms_per_launch": kern_s * 1e3,
-                "sfu": {"achieved": ach_mufu, "peak": peak_mufu, "unit": "G MUFU/s", "frac": ach_mufu / peak_mufu},
+                "sfu": {"achieved": ach_mufu, "peak": peak_mufu, "unit": "G MUFU/s", "frac": ach_mufu / peak_mufu,
+                        "note": "canonical 1 MUFU.EX2 per pair; the factorised kernel (FACT) issues none per pair"},
+                "note": "achieved uses the CANONICAL 10 FP32 instr/pair of SURVEY 8d so that rounds are comparable; the factorised "
+                        "kernel executes ~2.5 issue slots per pair in phase 1 (FMUL2/FMNMX/FADD2), see DESIGN.md 5 and "
+                        "profiles/*ncu_dense32*summary.txt for executed-instruction pipe utilisation",
                 "pair_evals_per_s": pairs_per_launch / kern_s,
                 "mufu_pair_body_peak_pairs_per_s": None if peak_mix is None else peak_mix / 4 * 1e9,
                 "factorised_pair_body_peak_pairs_per_s": None if peak_fact is None else peak_fact / 2.5 * 1e9,
