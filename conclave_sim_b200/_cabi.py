@@ -78,7 +78,7 @@ def load_library() -> C.CDLL:
     lib.csim_need_votes.argtypes = [C.c_double, C.c_int32]
     lib.csim_need_votes.restype = C.c_int32
     lib.csim_prob_matrix.argtypes = [C.c_void_p, C.POINTER(CsimParams), C.c_double, C.c_void_p, C.c_void_p,
-                                     C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     lib.csim_run.argtypes = [C.c_void_p, C.POINTER(CsimRunArgs)]
     lib.csim_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_float)]
     lib.csim_microbench.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double)]

@@ -67,7 +67,7 @@ struct csim_ctx {
     // host-buffer mode staging
     DevBuf o_winner, o_rounds, o_reason, o_final, o_tallies, o_whist, o_rhist, o_totals, i_tape;
     // prob-matrix staging
-    DevBuf p_prev, p_cnt, p_fat, p_shares, p_bw, p_out;
+    DevBuf p_prev, p_cnt, p_fat, p_shares, p_bw, p_out, p_cand;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_valid = false;
     int64_t launches = 0;
@@ -107,7 +107,7 @@ extern "C" csim_status csim_destroy(csim_ctx* c) {
     cudaSetDevice(c->device);
     for (DevBuf* b : {&c->x64, &c->x32, &c->region, &c->pap, &c->sets, &c->betas, &c->nbeta, &c->W, &c->tab, &c->cdf64, &c->cdfk64, &c->cdf32, &c->cdfk32, &c->o_winner, &c->o_rounds,
                       &c->o_reason, &c->o_final, &c->o_tallies, &c->o_whist, &c->o_rhist, &c->o_totals, &c->i_tape,
-                      &c->p_prev, &c->p_cnt, &c->p_fat, &c->p_shares, &c->p_bw, &c->p_out})
+                      &c->p_prev, &c->p_cnt, &c->p_fat, &c->p_shares, &c->p_bw, &c->p_out, &c->p_cand})
         b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -229,12 +229,20 @@ static DevSet make_set(const csim_params* p, int E, int wiring) {
 // ---------------------------------------------------------------------------------------------
 extern "C" csim_status csim_prob_matrix(csim_ctx* c, const csim_params* p, double beta, const int32_t* prev_vote,
                                         const int32_t* prev_count, const uint8_t* fatigued, const double* shares,
-                                        int32_t precision, void* P_out) {
+                                        const int32_t* cand_index, int32_t n_cand, int32_t precision, void* P_out) {
     if (!c || !p || !P_out) return fail(CSIM_ERR_INVALID, "csim_prob_matrix: NULL argument");
     if (c->E <= 0) return fail(CSIM_ERR_STATE, "csim_prob_matrix: roster not uploaded");
     if (precision != CSIM_FP32 && precision != CSIM_FP64) return fail(CSIM_ERR_INVALID, "csim_prob_matrix: bad precision %d", precision);
     CU_TRY(cudaSetDevice(c->device));
     const int E = c->E;
+    const int NC = cand_index ? n_cand : E;
+    if (cand_index) {
+        if (n_cand < 1) return fail(CSIM_ERR_INVALID, "csim_prob_matrix: n_cand must be >= 1 when cand_index is given");
+        for (int i = 0; i < n_cand; ++i)
+            if (cand_index[i] < 0 || cand_index[i] >= E) return fail(CSIM_ERR_INVALID, "csim_prob_matrix: cand_index[%d] = %d out of range", i, cand_index[i]);
+    }
+    const int32_t* d_cand = nullptr;
+    if (cand_index) { CU_TRY(c->p_cand.reserve(4 * (size_t)n_cand)); CU_TRY(cudaMemcpy(c->p_cand.p, cand_index, 4 * (size_t)n_cand, cudaMemcpyHostToDevice)); d_cand = (const int32_t*)c->p_cand.p; }
     DevSet S = make_set(p, E, CSIM_WIRING_MODEL);   // the standalone model honours every term it is given
     const int32_t* d_prev = nullptr; const int32_t* d_cnt = nullptr; const uint8_t* d_fat = nullptr; const double* d_sh = nullptr;
     if (prev_vote) { CU_TRY(c->p_prev.reserve(4 * E)); CU_TRY(cudaMemcpy(c->p_prev.p, prev_vote, 4 * E, cudaMemcpyHostToDevice)); d_prev = (const int32_t*)c->p_prev.p; }
@@ -249,13 +257,13 @@ extern "C" csim_status csim_prob_matrix(csim_ctx* c, const csim_params* p, doubl
         CU_TRY(cudaMemcpy(c->betas.p, &beta, sizeof beta, cudaMemcpyHostToDevice));
         CU_TRY(c->W.reserve(sizeof(double) * (size_t)E * c->Epad));
         CU_TRY(c->p_bw.reserve(8 * E));
-        CU_TRY(c->p_out.reserve(sizeof(double) * (size_t)E * E));
+        CU_TRY(c->p_out.reserve(sizeof(double) * (size_t)E * NC));
         dim3 g((c->Epad + 127) / 128, E, 1);
         k_base_scores64<<<g, 128>>>(ro, (const DevSet*)c->sets.p, (const double*)c->betas.p, 1, (double*)c->W.p);
         ++c->launches;
         ProbArgs a;
         a.ro = ro; a.S = S; a.W = (const double*)c->W.p; a.prev_vote = d_prev; a.prev_count = d_cnt; a.fatigued = d_fat;
-        a.shares = d_sh; a.bw = (double*)c->p_bw.p; a.P = (double*)c->p_out.p;
+        a.shares = d_sh; a.cand = d_cand; a.ncand = NC; a.bw = (double*)c->p_bw.p; a.P = (double*)c->p_out.p;
         int use_bw = 0;
         if (d_cnt && S.has_bw) {
             int mx = 0;
@@ -265,16 +273,16 @@ extern "C" csim_status csim_prob_matrix(csim_ctx* c, const csim_params* p, doubl
         k_prob_matrix64<<<(E + 63) / 64, 64>>>(a, use_bw);
         ++c->launches;
         CU_TRY(cudaGetLastError());
-        CU_TRY(cudaMemcpy(P_out, c->p_out.p, sizeof(double) * (size_t)E * E, cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(P_out, c->p_out.p, sizeof(double) * (size_t)E * NC, cudaMemcpyDeviceToHost));
     } else {
-        CU_TRY(c->p_out.reserve(sizeof(float) * (size_t)E * E));
+        CU_TRY(c->p_out.reserve(sizeof(float) * (size_t)E * NC));
         Prob32Args a;
         a.ro = ro; a.S = S; a.nb = (float)(-beta * 1.4426950408889634);
-        a.prev_vote = d_prev; a.prev_count = d_cnt; a.fatigued = d_fat; a.shares = d_sh; a.P = (float*)c->p_out.p;
+        a.prev_vote = d_prev; a.prev_count = d_cnt; a.fatigued = d_fat; a.shares = d_sh; a.cand = d_cand; a.ncand = NC; a.P = (float*)c->p_out.p;
         k_prob_matrix32<<<(E + 3) / 4, 128>>>(a);
         ++c->launches;
         CU_TRY(cudaGetLastError());
-        CU_TRY(cudaMemcpy(P_out, c->p_out.p, sizeof(float) * (size_t)E * E, cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(P_out, c->p_out.p, sizeof(float) * (size_t)E * NC, cudaMemcpyDeviceToHost));
     }
     return CSIM_OK;
 }

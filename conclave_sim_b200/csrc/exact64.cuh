@@ -101,9 +101,11 @@ struct Row64 {
     const double* x;          // [C] ideology (stop-candidate distances)
     double xe, st1p, fat_pen, stop_D, stop_boost;
     bool sticky, trig, degenerate;
+    const int32_t* cand = nullptr;   // optional column subset (model.py:280-296): column a is candidate cand[a]
 
-    __device__ __forceinline__ double operator()(int c) const {
+    __device__ __forceinline__ double operator()(int a) const {
         if (degenerate) return 1e-9;                                  // model.py:447-449
+        const int c = cand ? cand[a] : a;
         double s = Wcol[(size_t)c * Epad];
         if (bw) s = __dadd_rn(s, bw[c]);                              // model.py:354
         if (sticky && c == prev) s = __dmul_rn(s, st1p);              // model.py:363
@@ -341,8 +343,10 @@ struct ProbArgs {
     const int32_t* prev_count;// [E] or null
     const uint8_t* fatigued;  // [E] or null
     const double* shares;     // [E] or null
+    const int32_t* cand;      // [ncand] or null (all candidates)
+    int ncand;
     double* bw;               // [E] scratch (device)
-    double* P;                // [E][C] out
+    double* P;                // [E][ncand] out
 };
 
 __global__ void k_prob_bw64(ProbArgs a) {       // single block: bandwagon bonuses (model.py:326-354)
@@ -363,7 +367,9 @@ __global__ void k_prob_matrix64(ProbArgs a, int use_bw) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const int E = a.ro.E, C = E;
     if (e >= E) return;
+    const int NC = a.cand ? a.ncand : C;
     Row64 row;
+    row.cand = a.cand;
     row.Wcol = a.W + e; row.Epad = a.ro.Epad; row.e = e;
     row.prev = a.prev_vote ? a.prev_vote[e] : -1;
     row.sticky = a.prev_vote != nullptr && a.S.has_sticky;
@@ -377,7 +383,7 @@ __global__ void k_prob_matrix64(ProbArgs a, int use_bw) {
     if (a.S.en_stop && a.shares)
         for (int q = 0; q < C; ++q)
             if (fabs(row.xe - a.ro.x64[q]) > a.S.stop_D && a.shares[q] > a.S.stop_T) { row.trig = true; break; }
-    double rs = np_pairwise(row, C);
-    if (rs == 0.0) { row.degenerate = true; rs = np_pairwise(row, C); }
-    for (int c = 0; c < C; ++c) a.P[(size_t)e * C + c] = __ddiv_rn(row(c), rs);
+    double rs = np_pairwise(row, NC);
+    if (rs == 0.0) { row.degenerate = true; rs = np_pairwise(row, NC); }
+    for (int c = 0; c < NC; ++c) a.P[(size_t)e * NC + c] = __ddiv_rn(row(c), rs);
 }

@@ -12,7 +12,9 @@ struct Prob32Args {
     const int32_t* prev_count;// [E] or null
     const uint8_t* fatigued;  // [E] or null
     const double* shares;     // [E] or null
-    float* P;                 // [E][C]
+    const int32_t* cand;      // [ncand] or null
+    int ncand;
+    float* P;                 // [E][ncand]
 };
 
 // One warp per elector row; lanes stride over candidates (model.py:311-486 in fp32).
@@ -37,7 +39,9 @@ __global__ void k_prob_matrix32(Prob32Args a) {
             if (fabs(a.ro.x64[e] - a.ro.x64[q]) > a.S.stop_D && a.shares[q] > a.S.stop_T) trig = true;
         trig = __any_sync(CSIM_FULL, trig);
     }
-    auto score = [&](int c) -> float {
+    const int NC = a.cand ? a.ncand : C;
+    auto score = [&](int col) -> float {
+        const int c = a.cand ? a.cand[col] : col;
         float v = ex2_approx(fabsf(xe - a.ro.x32[c]) * a.nb);
         if (a.ro.pap[c]) v *= a.S.f_pwf;
         if (a.ro.region[c] == ge) v += a.S.f_bonus;
@@ -49,14 +53,14 @@ __global__ void k_prob_matrix32(Prob32Args a) {
         return c == e ? 0.0f : v;
     };
     float sum = 0.f;
-    for (int c = lane; c < C; c += 32) sum += score(c);
+    for (int c = lane; c < NC; c += 32) sum += score(c);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(CSIM_FULL, sum, off);
     if (!(sum > 0.0f)) {
-        for (int c = lane; c < C; c += 32) a.P[(size_t)e * C + c] = 1.0f / (float)C;      // model.py:447-449
+        for (int c = lane; c < NC; c += 32) a.P[(size_t)e * NC + c] = 1.0f / (float)NC;   // model.py:447-449
     } else {
         const float r = 1.0f / sum;
-        for (int c = lane; c < C; c += 32) a.P[(size_t)e * C + c] = score(c) * r;
+        for (int c = lane; c < NC; c += 32) a.P[(size_t)e * NC + c] = score(c) * r;
     }
 }
 

@@ -142,7 +142,8 @@ class Engine:
         return int(self._lib.csim_need_votes(float(threshold), int(self.n_electors if n_electors is None else n_electors)))
 
     def prob_matrix(self, params: CsimParams, beta: float, prev_vote=None, prev_count=None, fatigued=None,
-                    shares=None, precision: int = FP64) -> np.ndarray:
+                    shares=None, precision: int = FP64, cand_index=None) -> np.ndarray:
+        """P[E, n_cand]; `cand_index` = roster indices of the effective candidates (None = all)."""
         E = self.n_electors
         pv = None if prev_vote is None else np.ascontiguousarray(prev_vote, np.int32)
         pc = None if prev_count is None else np.ascontiguousarray(prev_count, np.int32)
@@ -151,9 +152,11 @@ class Engine:
         for a in (pv, pc, ft, sh):
             if a is not None and a.shape != (E,):
                 raise ValueError(f"per-candidate / per-elector inputs must have shape ({E},)")
-        P = np.empty((E, E), np.float64 if precision == FP64 else np.float32)
+        ci = None if cand_index is None else np.ascontiguousarray(cand_index, np.int32)
+        nc = E if ci is None else len(ci)
+        P = np.empty((E, nc), np.float64 if precision == FP64 else np.float32)
         check(self._lib.csim_prob_matrix(self._ctx, C.byref(params), float(beta), _ptr(pv), _ptr(pc), _ptr(ft), _ptr(sh),
-                                         int(precision), _ptr(P)))
+                                         _ptr(ci), int(nc), int(precision), _ptr(P)))
         return P
 
     # ------------------------------------------------------------------ trials

@@ -147,14 +147,13 @@ class TransitionModel:
                                            candidate_vote_shares_current_round: Optional[np.ndarray] = None,
                                            effective_candidate_ids: Optional[List[Any]] = None):
         """(P[E, C] float64, []) — src/model.py:269-560."""
+        cand_index = None        # roster indices of the candidates of this call, in column order (model.py:280-296)
         if effective_candidate_ids is not None and len(effective_candidate_ids) > 0:
-            subset = [cid for cid in effective_candidate_ids if cid in self.candidate_ids_set]
-            if subset and subset != list(self.candidate_ids):
-                raise NotImplementedError(
-                    "candidate subsetting (effective_candidate_ids) is not on the simulation path "
-                    "(src/simulate.py never passes it) and is not built yet")
+            subset = [cid for cid in effective_candidate_ids if _hashable(cid) and cid in self.candidate_ids_set]
             if not subset:
                 log.warning("Provided effective_candidate_ids resulted in an empty list after validation. Falling back to all candidates.")
+            else:
+                cand_index = np.array([self._cand_pos[cid] for cid in subset], dtype=np.int32)
         E = self.num_electors
         if E == 0 or self.num_total_candidates == 0:
             log.warning("No electors or actual candidates to calculate transition probabilities for.")
@@ -173,10 +172,11 @@ class TransitionModel:
                 # stickiness needs the voter to be a known elector as well (model.py:358-363)
                 prev_vote = np.full(E, -1, np.int32)
                 prev_count = np.zeros(E, np.int32)
+                in_subset = None if cand_index is None else set(int(i) for i in cand_index)
                 for voter, chosen in items:
                     ci = self._cand_lookup(chosen)
-                    if ci is None:
-                        continue
+                    if ci is None or (in_subset is not None and ci not in in_subset):
+                        continue            # votes for candidates outside the effective set are ignored (model.py:337,359)
                     prev_count[ci] += 1
                     ei = self._index_pos.get(voter) if _hashable(voter) else None
                     if ei is not None:
@@ -192,7 +192,7 @@ class TransitionModel:
             shares = np.asarray(candidate_vote_shares_current_round, dtype=np.float64)
         params = make_params(self.model_kwargs())
         P = self._engine().prob_matrix(params, self.effective_beta_weight, prev_vote, prev_count, fat, shares,
-                                       precision=self._precision)
+                                       precision=self._precision, cand_index=cand_index)
         return P, []
 
     def _cand_lookup(self, cid):

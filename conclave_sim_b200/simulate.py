@@ -327,5 +327,116 @@ def main(argv: Optional[List[str]] = None):
     return aggregate_stats
 
 
+# ---------------------------------------------------------------------------------------------
+# Aggregation straight from the device histograms: one stats dict per parameter
+# set of a sweep, without touching the per-trial rows.
+# ---------------------------------------------------------------------------------------------
+def stats_from_histograms(winner_hist: np.ndarray, rounds_hist: np.ndarray, totals: np.ndarray,
+                          candidate_ids: List[Any], num_simulations: Optional[int] = None) -> Dict[str, Any]:
+    """Same keys / values as aggregate_results (src/simulate.py:356-387) from
+    winner_hist[E+1] (slot E = no winner), rounds_hist[R+1] (winning trials) and totals = (sum of rounds, trials).
+    `most_frequent_winner` breaks count ties by roster order (the reference's tie-break is its
+    completion order, i.e. unspecified)."""
+    winner_hist = np.asarray(winner_hist, dtype=np.int64)
+    rounds_hist = np.asarray(rounds_hist, dtype=np.int64)
+    E = len(winner_hist) - 1
+    n = int(totals[1]) if num_simulations is None else int(num_simulations)
+    successful = int(winner_hist[:E].sum())
+    rvals = np.nonzero(rounds_hist)[0]
+    if successful:
+        cum = np.cumsum(rounds_hist)
+        lo = int(np.searchsorted(cum, (successful - 1) // 2 + 1))            # lower middle (1-based rank)
+        hi = int(np.searchsorted(cum, successful // 2 + 1))                  # upper middle
+        avg = float((np.arange(len(rounds_hist)) * rounds_hist).sum() / successful)
+        median = (lo + hi) / 2.0
+        rmin, rmax = int(rvals[0]), int(rvals[-1])
+    else:
+        avg = median = rmin = rmax = None
+    counts = {str(candidate_ids[i]): int(c) for i, c in enumerate(winner_hist[:E]) if c > 0}
+    if counts:
+        best = int(np.argmax(winner_hist[:E]))
+        mf, mfc = str(candidate_ids[best]), int(winner_hist[best])
+    else:
+        mf, mfc = None, 0
+    return {
+        "total_simulations": n,
+        "successful_simulations": successful,
+        "success_rate": successful / n if n > 0 else 0,
+        "average_rounds_successful": avg,
+        "min_rounds_successful": rmin,
+        "max_rounds_successful": rmax,
+        "median_rounds_successful": median,
+        "winner_counts": counts,
+        "most_frequent_winner": mf,
+        "most_frequent_winner_count": mfc,
+        "most_frequent_winner_percentage": mfc / n if n > 0 else 0,
+        "average_rounds_all": float(totals[0]) / float(totals[1]) if totals[1] > 0 else 0,
+    }
+
+
+def run_sweep(elector_data_full: pd.DataFrame, param_sets: List[Dict[str, Any]], num_simulations: int, *,
+              seed: Optional[int] = None, wiring: Optional[str] = None, device: Optional[int] = None,
+              precision: Optional[str] = None, engine: Optional[str] = None) -> List[Dict[str, Any]]:
+    """Parameter sweep (BASELINE config 4): every entry of `param_sets` is a dict with the keys of
+    make_params (a 'model_params' dict plus max_rounds / supermajority_threshold / runoff_* ...); all sets run in
+    ONE launch with per-CTA parameters and each gets its stats dict from the device histograms."""
+    wiring = wiring or RUNTIME["wiring"]
+    eng = get_engine(RUNTIME["device"] if device is None else device)
+    x, g, pap = roster_arrays(elector_data_full)
+    eng.upload_roster(x, g, pap)
+    sets = []
+    for ps in param_sets:
+        kw = dict(ps)
+        mp = kw.pop("model_params", {})
+        sets.append(make_params(mp, **kw))
+    res = eng.run(sets, num_simulations, seed=_seed() if seed is None else seed, wiring=_WIRING[wiring],
+                  engine=_ENGINE[engine or RUNTIME["engine"]], precision=_PRECISION[precision or RUNTIME["precision"]],
+                  want_reason=False)
+    ids = list(elector_data_full.index)
+    return [stats_from_histograms(res.winner_hist[i], res.rounds_hist[i], res.totals[i], ids, num_simulations)
+            for i in range(len(sets))]
+
+
+# ---------------------------------------------------------------------------------------------
+# Legacy entry point (SURVEY §8f.4): `src/__main__.py:18,118` and the stale tests/test_simulate.py
+# import a `run_monte_carlo_simulation` that no longer exists upstream; this shim provides it.
+# ---------------------------------------------------------------------------------------------
+REQUIRED_MAJORITY_FRACTION = DEFAULT_SUPERMAJORITY_THRESHOLD
+MAX_ROUNDS = DEFAULT_MAX_ROUNDS
+
+
+def run_monte_carlo_simulation(num_simulations: int, elector_data: pd.DataFrame, model_parameters: Dict[str, Any],
+                               verbose: bool = False, max_rounds: int = MAX_ROUNDS,
+                               supermajority_threshold: float = REQUIRED_MAJORITY_FRACTION):
+    """(results_df[simulation_id, winner_id, rounds_taken, status], aggregate_stats) — the old schema
+    (tests/test_simulate.py:60-68).  `model_parameters` may use the old key 'beta_weight'."""
+    if elector_data is None or elector_data.empty:
+        raise ValueError("Elector data cannot be empty")
+    if "elector_id" not in elector_data.columns and elector_data.index.name != "elector_id":
+        raise ValueError("Elector data must contain an 'elector_id' column")
+    df = elector_data
+    if "elector_id" in df.columns:
+        df = df.copy()
+        df["elector_id"] = df["elector_id"].astype(str)
+        df = df.set_index("elector_id")
+    if "region" not in df.columns:
+        df = df.assign(region=[f"_r{i}" for i in range(len(df))])      # no regional information: nobody shares a region
+    mp = dict(model_parameters or {})
+    if "beta_weight" in mp:
+        mp["initial_beta_weight"] = mp.pop("beta_weight")
+    res = run_simulations(df, mp, num_simulations, max_rounds=max_rounds, supermajority_threshold=supermajority_threshold,
+                          runoff_threshold_rounds=DEFAULT_RUNOFF_THRESHOLD_ROUNDS,
+                          runoff_candidate_count=DEFAULT_RUNOFF_CANDIDATE_COUNT)
+    ids = list(df.index)
+    rows = [{"simulation_id": i, "winner_id": ids[w] if w >= 0 else None, "rounds_taken": int(r),
+             "status": "Success" if w >= 0 else "Max rounds reached"} for i, (w, r) in enumerate(zip(res.winner, res.rounds))]
+    results_df = pd.DataFrame(rows, columns=["simulation_id", "winner_id", "rounds_taken", "status"])
+    ok = res.winner >= 0
+    stats = {"num_simulations": num_simulations, "success_rate": float(ok.mean()) if num_simulations else 0.0,
+             "avg_rounds_success": float(res.rounds[ok].mean()) if ok.any() else None,
+             "winner_counts": {ids[i]: int(c) for i, c in enumerate(res.winner_hist[0, :-1]) if c > 0}}
+    return results_df, stats
+
+
 if __name__ == "__main__":
     main()

@@ -148,15 +148,20 @@ csim_status csim_beta_schedule(const csim_params* p, int32_t first_round, int32_
 /* smallest integer v with (double)v >= threshold * n_electors */
 int32_t     csim_need_votes(double supermajority_threshold, int32_t n_electors);
 
-/* P[E, E] for one round with effective beta `beta` (host buffers in and out).
- * prev_vote[E]  : candidate index each elector voted for last round, -1 = none   (nullable -> stickiness off)
+/* P[E, n_cand] for one round with effective beta `beta` (host buffers in and out).
+ * prev_vote[E]  : candidate index (roster order) each elector voted for last round, -1 = none (nullable -> stickiness off)
  * prev_count[E] : last round's count per candidate                              (nullable -> bandwagon off)
  * fatigued[E]   : 1 = candidate fatigued (used iff p->enable_candidate_fatigue) (nullable)
  * shares[E]     : last round's vote shares (used iff p->enable_stop_candidate)  (nullable)
+ * cand_index[n_cand] : the "effective candidates" of model.py:280-296 as roster indices, in output column
+ *                 order; NULL -> all E candidates (n_cand ignored).  Rows are normalised over these columns only;
+ *                 the caller zeroes prev_count / prev_vote entries of candidates outside the subset
+ *                 (model.py:337,359 filter them the same way).
  * precision     : CSIM_FP64 -> P_out is double*, CSIM_FP32 -> float*. */
 csim_status csim_prob_matrix(csim_ctx* ctx, const csim_params* p, double beta,
                              const int32_t* prev_vote, const int32_t* prev_count,
                              const uint8_t* fatigued, const double* shares,
+                             const int32_t* cand_index, int32_t n_cand,
                              int32_t precision, void* P_out);
 
 /* The hot path: a batch of independent trials. */

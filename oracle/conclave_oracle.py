@@ -178,6 +178,7 @@ def prob_matrix(
     prev_count: Optional[np.ndarray] = None,  # int [C], previous-round counts for bandwagon (default: from prev_vote)
     fatigued: Optional[np.ndarray] = None,    # bool [C]
     shares: Optional[np.ndarray] = None,      # f64 [C], previous-round vote shares (stop-candidate)
+    cand_index: Optional[np.ndarray] = None,  # int [n_cand]: the effective candidates (model.py:280-296), column order
 ) -> np.ndarray:
     """P[E, C] fp64 for one round with effective beta ``beta``.
     ``prev_vote`` / ``prev_count`` None == the reference's "no previous votes"
@@ -186,6 +187,18 @@ def prob_matrix(
     E = roster.E
     if E == 0:
         return np.zeros((0, 0))
+    if cand_index is not None:
+        # votes for candidates outside the effective set are ignored (model.py:337,359)
+        inside = np.zeros(E, bool)
+        inside[np.asarray(cand_index)] = True
+        if prev_vote is not None:
+            pv0 = np.asarray(prev_vote).copy()
+            if prev_count is None:
+                prev_count = np.bincount(pv0[pv0 >= 0], minlength=E)
+            pv0[(pv0 >= 0) & ~inside[np.clip(pv0, 0, E - 1)]] = -1
+            prev_vote = pv0
+        if prev_count is not None:
+            prev_count = np.where(inside, np.asarray(prev_count), 0)
     d = np.abs(x[:, None] - x[None, :])                      # model.py:312
     s = np.exp(-beta * d)                                    # model.py:313
     pap = np.where(roster.papabile)[0]
@@ -219,6 +232,8 @@ def prob_matrix(
         s = s * np.where(trig[:, None] & ~unacc, mp.stop_candidate_boost_factor, 1.0)
     s[np.arange(E), np.arange(E)] = 0.0                       # model.py:418-424
     s = np.maximum(s, 0)                                      # model.py:427
+    if cand_index is not None:
+        s = np.ascontiguousarray(s[:, np.asarray(cand_index)])
     rs = s.sum(axis=1)
     zero = rs == 0
     if zero.any():

@@ -10,6 +10,7 @@ Outputs (committed):
                                     (model.py:199-213), region factorised
   tests/golden/model_cases.npz      TransitionModel.calculate_transition_probabilities outputs
                                     on random small rosters, every term exercised (`model` wiring)
+  tests/golden/model_subset.npz     same with effective_candidate_ids column subsets (model.py:280-296)
   tests/golden/model_real.npz       same on the real roster (cfg-1 / cfg-2, selected rounds)
   tests/golden/engine_cases.json    engine-level case manifest (params, seeds)
   tests/golden/engine_cases.npz     winners / rounds / per-round tallies of
@@ -119,6 +120,45 @@ def gen_model_cases():
         meta.append(dict(name=k, kwargs=kw))
     out["meta"] = np.array(json.dumps(meta))
     np.savez_compressed(os.path.join(GOLD, "model_cases.npz"), **out)
+
+
+def gen_model_subset():
+    """effective_candidate_ids (model.py:280-296): column subsets in caller order, every term exercised."""
+    import pandas as pd
+    ref_model, _ = H.load_reference()
+    rng = np.random.default_rng(424242)
+    regs = np.array(["R0", "R1", "R2"])
+    out = {}
+    meta = []
+    for t in range(10):
+        E = int(rng.integers(4, 20))
+        ideo = rng.random(E)
+        reg = rng.integers(0, 3, E)
+        pap = rng.random(E) < 0.4
+        kw = dict(initial_beta_weight=float(rng.uniform(0.5, 3)), stickiness_factor=float(rng.choice([0, 0.6])),
+                  bandwagon_strength=float(rng.choice([0, 0.5])), regional_affinity_bonus=float(rng.choice([0, 0.2])),
+                  papabile_weight_factor=float(rng.choice([1, 2])), enable_candidate_fatigue=bool(rng.integers(2)),
+                  fatigue_penalty_factor=0.5, enable_stop_candidate=bool(rng.integers(2)),
+                  stop_candidate_threshold_unacceptable_distance=float(rng.uniform(0.2, 0.6)),
+                  stop_candidate_threat_min_vote_share=0.1, stop_candidate_boost_factor=1.7)
+        df = H.make_df(ideo, regs[reg], pap)
+        model = ref_model.TransitionModel(df.copy(), **kw)
+        n_c = int(rng.integers(1, E + 1))
+        cand = rng.permutation(E)[:n_c].astype(np.int32)
+        pv = rng.integers(0, E, E).astype(np.int32)
+        ser = pd.Series({str(e): str(pv[e]) for e in range(E)}, dtype=object)
+        fat = rng.random(E) < 0.25
+        cnt = np.bincount(pv, minlength=E)
+        shares = cnt / cnt.sum()
+        P, _ = model.calculate_transition_probabilities(ser, 2, set(np.where(fat)[0].tolist()), shares,
+                                                        effective_candidate_ids=[str(c) for c in cand] + ["not-a-candidate"])
+        k = f"s{t:02d}"
+        out[k + "/ideology"] = ideo; out[k + "/region"] = reg.astype(np.int32); out[k + "/papabile"] = pap
+        out[k + "/prev_vote"] = pv; out[k + "/fatigued"] = fat; out[k + "/shares"] = shares; out[k + "/cand"] = cand
+        out[k + "/P"] = P; out[k + "/beta"] = np.array(model.effective_beta_weight)
+        meta.append(dict(name=k, kwargs=kw))
+    out["meta"] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(GOLD, "model_subset.npz"), **out)
 
 
 def gen_model_real(df):
@@ -274,6 +314,7 @@ def main():
     if not a.only_dist:
         df = gen_roster()
         gen_model_cases()
+        gen_model_subset()
         gen_model_real(df)
         gen_engine_cases(df)
     if a.dist:

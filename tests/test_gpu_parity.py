@@ -342,3 +342,54 @@ def test_table_engine_without_shared_memory_staging(eng):
     assert np.array_equal(out.round_tallies, ref["round_tallies"])
     o32 = eng.run([to_params(mp, ep)], 40, seed=21, precision=FP32, engine=ENGINES["table"])
     assert np.mean(o32.rounds == ref["rounds"]) > 0.8
+
+
+def test_sweep_stats_and_legacy_shim(eng):
+    import pandas as pd
+    from conclave_sim_b200 import simulate as S
+    roster = G.real_roster()
+    df = pd.DataFrame({"ideology_score": roster.ideology, "region": [f"R{g}" for g in roster.region],
+                       "is_papabile": roster.papabile}, index=pd.Index(roster.ids, name="elector_id"))
+    S.RUNTIME.update(seed=77, precision="fp32", wiring="ref_cli", engine="auto")
+    sets = [dict(model_params=dict(CFG2, papabile_weight_factor=pw), max_rounds=20, supermajority_threshold=thr)
+            for pw in (1.5, 2.0) for thr in (0.5, 0.56)]
+    stats = S.run_sweep(df, sets, 5000)
+    assert len(stats) == 4 and all(s["total_simulations"] == 5000 for s in stats)
+    assert stats[0]["success_rate"] > stats[1]["success_rate"]            # lower threshold converges more often
+    # one set alone, row-level aggregation, must agree with the histogram route
+    solo = S.run_simulations(df, dict(CFG2, papabile_weight_factor=2.0), 5000, max_rounds=20, supermajority_threshold=0.56,
+                             runoff_threshold_rounds=5, runoff_candidate_count=2, seed=77)
+    rows = S.results_from_batch(solo, roster.ids, 0.56)
+    agg = S.aggregate_results(rows, 5000)
+    for k in ("successful_simulations", "average_rounds_successful", "median_rounds_successful", "average_rounds_all", "winner_counts"):
+        assert agg[k] == stats[3][k] or np.isclose(agg[k], stats[3][k]), k
+    legacy = pd.DataFrame({"elector_id": [1, 2, 3], "name": list("ABC"), "ideology_score": [-0.5, 0.0, 0.5]})
+    rdf, st = S.run_monte_carlo_simulation(16, legacy, {"beta_weight": 0.1}, max_rounds=30)
+    assert list(rdf.columns) == ["simulation_id", "winner_id", "rounds_taken", "status"] and len(rdf) == 16
+    assert "success_rate" in st and "avg_rounds_success" in st
+
+
+@pytest.mark.parametrize("case", list(G.subset_cases()), ids=lambda c: c["name"])
+def test_prob_matrix_candidate_subset(eng, case):
+    """effective_candidate_ids (model.py:280-296) through csim_prob_matrix and through the TransitionModel mirror."""
+    import pandas as pd
+    from conclave_sim_b200 import FP64, FP32
+    from conclave_sim_b200.model import TransitionModel
+    roster, mp = case["roster"], case["mp"]
+    upload(eng, roster)
+    E = roster.E
+    inside = np.zeros(E, bool); inside[case["cand"]] = True
+    pv = case["prev_vote"].copy()
+    pc = np.where(inside, np.bincount(pv, minlength=E), 0).astype(np.int32)
+    pv[~inside[pv]] = -1
+    P = eng.prob_matrix(to_params(mp), case["beta"], pv, pc, case["fatigued"], case["shares"], precision=FP64, cand_index=case["cand"])
+    assert P.shape == case["P"].shape and np.allclose(P, case["P"], rtol=1e-13, atol=0)
+    P32 = eng.prob_matrix(to_params(mp), case["beta"], pv, pc, case["fatigued"], case["shares"], precision=FP32, cand_index=case["cand"])
+    assert np.allclose(P32, case["P"], rtol=1e-5, atol=1e-12)
+    df = pd.DataFrame({"ideology_score": roster.ideology, "region": [f"R{g}" for g in roster.region], "is_papabile": roster.papabile},
+                      index=pd.Index([str(i) for i in range(E)], name="elector_id"))
+    m = TransitionModel(df, **{k: getattr(mp, k) for k in MODEL_KEYS})
+    ser = pd.Series({str(e): str(case["prev_vote"][e]) for e in range(E)}, dtype=object)
+    Pm, details = m.calculate_transition_probabilities(ser, 2, set(np.where(case["fatigued"])[0].tolist()), case["shares"],
+                                                       effective_candidate_ids=[str(c) for c in case["cand"]] + ["not-a-candidate"])
+    assert details == [] and np.allclose(Pm, case["P"], rtol=1e-13, atol=0)

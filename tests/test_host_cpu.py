@@ -191,3 +191,39 @@ def test_worker_on_empty_roster_matches_reference():
     from conclave_sim_b200 import simulate as S
     r = S._run_single_simulation_worker(3, pd.DataFrame(), {}, 10, 0.5, 5, 2, False, False, 3, 0.05, 3, False)
     assert r == {"sim_id": 3, "winner": None, "rounds": 1, "reason": "No probabilities generated", "final_votes": {}, "run_details": []}
+
+
+def test_stats_from_histograms_equals_row_aggregation():
+    from conclave_sim_b200 import simulate as S
+    rng = np.random.default_rng(5)
+    ids = [str(i) for i in range(30)]
+    for n in (0, 1, 2, 7, 50, 501):
+        w = rng.integers(-1, 30, n)
+        w[rng.random(n) < 0.3] = -1
+        r = np.where(w >= 0, rng.integers(1, 21, n), 20)
+        results = [dict(sim_id=i, winner=(ids[w[i]] if w[i] >= 0 else None), rounds=int(r[i]), reason="") for i in range(n)]
+        ref = S.aggregate_results(results, n)
+        wh = np.bincount(np.where(w >= 0, w, 30), minlength=31)
+        rh = np.bincount(r[w >= 0], minlength=21)
+        got = S.stats_from_histograms(wh, rh, np.array([r.sum(), n]), ids, n)
+        for k in ref:
+            if k in ("most_frequent_winner",):
+                assert (got[k] is None) == (ref[k] is None)
+                if got[k] is not None:
+                    assert ref["winner_counts"][got[k]] == ref["most_frequent_winner_count"]
+            elif ref[k] is None:
+                assert got[k] is None, k
+            elif isinstance(ref[k], dict):
+                assert got[k] == ref[k], k
+            else:
+                assert np.isclose(got[k], ref[k]), (k, got[k], ref[k])
+        assert list(got) == list(ref)
+
+
+def test_legacy_shim_input_validation():
+    import pandas as pd
+    from conclave_sim_b200 import simulate as S
+    with pytest.raises(ValueError, match="Elector data cannot be empty"):
+        S.run_monte_carlo_simulation(1, pd.DataFrame(columns=["elector_id", "ideology_score"]), {"beta_weight": 0.1})
+    with pytest.raises(ValueError, match="must contain an 'elector_id' column"):
+        S.run_monte_carlo_simulation(1, pd.DataFrame({"ideology_score": [0.1, 0.2]}), {"beta_weight": 0.1})

@@ -148,3 +148,11 @@ def test_philox_known_answers():
     assert [int(w[0]) for w in out] == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
     u = O.philox_uniforms(7, 3, 1, 9)
     assert u.shape == (9,) and (u >= 0).all() and (u < 1).all()
+
+
+@pytest.mark.parametrize("case", list(G.subset_cases()), ids=lambda c: c["name"])
+def test_prob_matrix_candidate_subset_matches_reference(case):
+    """effective_candidate_ids (model.py:280-296)."""
+    P = O.prob_matrix(case["roster"], case["mp"], case["beta"], prev_vote=case["prev_vote"], fatigued=case["fatigued"],
+                      shares=case["shares"], cand_index=case["cand"])
+    assert P.shape == case["P"].shape and np.array_equal(P, case["P"])
