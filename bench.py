@@ -285,14 +285,12 @@ def main():
         step(502 + i, engine=ENGINE_TABLE)
         tev[i][1].record()
         tev[i][1].synchronize()
-        t_rounds += int(batch.totals[0].item())
+        t_rounds += int(batch.totals[0].item())           # already summed over ranks by the step's all-reduce
     barrier()
-    tt = torch.tensor([sum(a.elapsed_time(b) for a, b in tev), float(t_rounds)], dtype=torch.float64, device=dev)
+    tt = torch.tensor([sum(a.elapsed_time(b) for a, b in tev)], dtype=torch.float64, device=dev)
     if world > 1:
-        a_ = tt.clone(); dist.all_reduce(a_, op=dist.ReduceOp.MAX)
-        b_ = tt.clone(); dist.all_reduce(b_, op=dist.ReduceOp.SUM)
-        tt = torch.stack([a_[0], b_[1]])
-    table_ms, table_rounds = tt[0].item(), tt[1].item()
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    table_ms, table_rounds = tt[0].item(), float(t_rounds)
     table_engine = {"value": table_rounds * E / (table_ms * 1e-3), "unit": "elector-rounds/s",
                     "conclaves_per_sec": n_global * args.steps / (table_ms * 1e-3), "ms_per_step": table_ms / args.steps,
                     "kernel": "k_trials_table<float> (+ k_base_scores64, k_cdf_tables64, k_f64_to_f32 per step)",
