@@ -258,7 +258,9 @@ def main():
     ach_mufu = pairs_per_launch * MUFU_PER_PAIR / kern_s * 1e-9
     out_bytes = n_local * 9 + (E + 1 + R + 1 + 2) * 8
     roofline = {"bound": "fp32", "kernel": "k_trials_dense32<LC=8,MODEL=false,FACT=true>", "achieved": ach_fp32, "peak": peak_fp32,
-                "unit": "G thread-instr/s", "frac": ach_fp32 / peak_fp32, "traffic": None,
+                "unit": "G thread-instr/s", "frac": ach_fp32 / peak_fp32, "traffic": 111872,
+                "traffic_note": "ncu dram__bytes_read+write of one launch at 250k trials (profiles/r01_ncu_dense32_v5_summary.txt); "
+                                "the kernel is compute-bound, HBM only sees the 9 B/trial result writeback",
                 "algorithmic": f"{FP32_PER_PAIR} FP32-pipe instr per (elector,candidate) pair evaluation (SURVEY 8d); "
                                f"{pairs_per_launch:.4g} pair evaluations per launch (E*C in full-field rounds, E*k in run-off rounds)",
                 "peak_source": peak_src, "kernel_ms_per_launch": kern_s * 1e3,

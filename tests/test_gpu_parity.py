@@ -393,3 +393,26 @@ def test_prob_matrix_candidate_subset(eng, case):
     Pm, details = m.calculate_transition_probabilities(ser, 2, set(np.where(case["fatigued"])[0].tolist()), case["shares"],
                                                        effective_candidate_ids=[str(c) for c in case["cand"]] + ["not-a-candidate"])
     assert details == [] and np.allclose(Pm, case["P"], rtol=1e-13, atol=0)
+
+
+def test_integration_md_stub_runs(eng):
+    """The ctypes binding printed in INTEGRATION.md is executed verbatim: it must drive the library end to end."""
+    import argparse, re
+    import pandas as pd
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, "INTEGRATION.md")).read()
+    code = re.search(r"```python\n(.*?)```", md, re.S).group(1)
+    code = code.replace('"conclave_sim_b200/libconclave_b200.so"', repr(os.path.join(root, "conclave_sim_b200", "libconclave_b200.so")))
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    roster = G.real_roster()
+    df = pd.DataFrame({"ideology_score": roster.ideology, "region": [f"R{g}" for g in roster.region],
+                       "is_papabile": roster.papabile}, index=pd.Index(roster.ids, name="elector_id"))
+    args = argparse.Namespace(max_rounds=20, supermajority_threshold=0.56, runoff_rounds=5, runoff_candidates=2, num_simulations=300)
+    mp = dict(CFG2, fatigue_penalty_factor=0.5, stop_candidate_threshold_unacceptable_distance=0.5,
+              stop_candidate_boost_factor=1.5, stop_candidate_threat_min_vote_share=0.15)
+    results = ns["run_trials_on_gpu"](args, df, mp)
+    assert len(results) == 300 and set(results[0]) == {"sim_id", "winner", "rounds", "reason", "final_votes", "run_details"}
+    ok = [r for r in results if r["winner"] is not None]
+    assert 0.75 < len(ok) / 300 < 0.98 and all(r["winner"] in roster.ids for r in ok)
+    assert all(r["reason"].startswith("Winner found by supermajority (56%") for r in ok)
