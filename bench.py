@@ -328,6 +328,33 @@ def main():
         b = te.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
         e2e_s, e2e_rounds = a[0].item(), b[1].item()
     e2e_value = e2e_rounds * E / e2e_s
+    # the same through the reference-facing Python call (DataFrame roster, default engine = table for ref_cli)
+    import pandas as pd
+    from conclave_sim_b200 import simulate as S
+    df = pd.DataFrame({"ideology_score": ideology, "region": region, "is_papabile": pap},
+                      index=pd.Index([str(i) for i in range(E)], name="elector_id"))
+    S.RUNTIME.update(seed=SEED, device=local_rank, precision="fp32", engine="auto", wiring="ref_cli")
+    api_kw = dict(max_rounds=R, supermajority_threshold=ENGINE_KW["supermajority_threshold"], runoff_threshold_rounds=rr,
+                  runoff_candidate_count=k)
+    S.run_simulations(df, CFG2, n_local, sim_id_begin=begin, **api_kw)
+    barrier()
+    t0 = time.perf_counter()
+    api_rounds = 0
+    for i in range(e2e_steps):
+        eng_api = S.get_engine(local_rank)
+        eng_api._roster_key = None
+        r = S.run_simulations(df, CFG2, n_local, sim_id_begin=(2000 + i) * n_global + begin, **api_kw)
+        api_rounds += int(r.totals[0, 0])
+    barrier()
+    api_s = time.perf_counter() - t0
+    ta = torch.tensor([api_s, float(api_rounds)], dtype=torch.float64, device=dev)
+    if world > 1:
+        a = ta.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
+        b = ta.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        api_s, api_rounds = a[0].item(), b[1].item()
+    table_engine["e2e_default_api"] = {"value": api_rounds * E / api_s, "unit": "elector-rounds/s",
+                                       "conclaves_per_sec": n_global * e2e_steps / api_s,
+                                       "api": "conclave_sim_b200.simulate.run_simulations(DataFrame, ...) with default engine"}
     h2d = E * (8 + 4 + 1) + 152 + 20 * 12
     d2h = n_local * 9 + ((E + 1) + (R + 1) + 2) * 8
 
