@@ -47,6 +47,7 @@ struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     cudaError_t reserve(size_t n) {
+        if (n == 0) n = 16;
         if (n <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
@@ -311,8 +312,7 @@ static csim_status launch_exact64(csim_ctx* c, const csim_run_args* ra, const st
     RosterDev ro = roster_dev(c);
     dim3 g((c->Epad + 127) / 128, E, b.n_sets * R);
     if (g.z > 65535) return fail(CSIM_ERR_UNSUPPORTED, "n_param_sets * max_rounds = %u exceeds 65535 in fp64 mode", g.z);
-    k_base_scores64<<<g, 128, 0, st>>>(ro, b.sets, (const double*)c->betas.p, R, (double*)c->W.p);
-    ++c->launches;
+    if (R > 0) { k_base_scores64<<<g, 128, 0, st>>>(ro, b.sets, (const double*)c->betas.p, R, (double*)c->W.p); ++c->launches; }
     Exact64Args a;
     a.ro = ro; a.b = b; a.out = out; a.W = (const double*)c->W.p; a.wiring = ra->wiring;
     int Fmax = 1, kmax = 1;
@@ -350,7 +350,7 @@ static csim_status launch_dense32_t(csim_ctx* c, Dense32Args& a, cudaStream_t st
     auto kern = k_trials_dense32<LC, MODEL, FACT>;
     csim_status s = persistent_grid(c, kern, wpc * 32, smem, (uint64_t)a.b.n_sets * a.b.n_sims, wpc, &grid);
     if (s != CSIM_OK) return s;
-    if (FACT) {
+    if (FACT && a.b.R > 0) {
         const int CP = a.nch * a.L;
         const size_t tb = sizeof(float) * (size_t)a.b.n_sets * a.b.R * 4 * CP;
         CU_TRY(c->tab.reserve(tb));
@@ -455,17 +455,21 @@ static csim_status launch_table(csim_ctx* c, const csim_run_args* ra, const std:
     CU_TRY(c->cdfk64.reserve(sizeof(double) * rows * kmax));
     RosterDev ro = roster_dev(c);
     dim3 g((c->Epad + 127) / 128, E, b.n_sets * R);
-    k_base_scores64<<<g, 128, 0, st>>>(ro, b.sets, (const double*)c->betas.p, R, (double*)c->W.p);
-    dim3 g2((E + 63) / 64, b.n_sets * R);
-    k_cdf_tables64<<<g2, 64, 0, st>>>(ro, b.sets, (const double*)c->W.p, R, kmax, (double*)c->cdf64.p, (double*)c->cdfk64.p);
-    c->launches += 2;
+    if (R > 0) {
+        k_base_scores64<<<g, 128, 0, st>>>(ro, b.sets, (const double*)c->betas.p, R, (double*)c->W.p);
+        dim3 g2((E + 63) / 64, b.n_sets * R);
+        k_cdf_tables64<<<g2, 64, 0, st>>>(ro, b.sets, (const double*)c->W.p, R, kmax, (double*)c->cdf64.p, (double*)c->cdfk64.p);
+        c->launches += 2;
+    }
     if (ra->precision == CSIM_FP64)
         return launch_table_t<double>(c, b, out, kmax, (const double*)c->cdf64.p, (const double*)c->cdfk64.p, st);
     CU_TRY(c->cdf32.reserve(sizeof(float) * rows * E));
     CU_TRY(c->cdfk32.reserve(sizeof(float) * rows * kmax));
-    k_f64_to_f32<<<c->prop.multiProcessorCount * 4, 256, 0, st>>>((const double*)c->cdf64.p, (float*)c->cdf32.p, rows * E);
-    k_f64_to_f32<<<c->prop.multiProcessorCount, 256, 0, st>>>((const double*)c->cdfk64.p, (float*)c->cdfk32.p, rows * kmax);
-    c->launches += 2;
+    if (R > 0) {
+        k_f64_to_f32<<<c->prop.multiProcessorCount * 4, 256, 0, st>>>((const double*)c->cdf64.p, (float*)c->cdf32.p, rows * E);
+        k_f64_to_f32<<<c->prop.multiProcessorCount, 256, 0, st>>>((const double*)c->cdfk64.p, (float*)c->cdfk32.p, rows * kmax);
+        c->launches += 2;
+    }
     return launch_table_t<float>(c, b, out, kmax, (const float*)c->cdf32.p, (const float*)c->cdfk32.p, st);
 }
 

@@ -369,6 +369,7 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
         bool have_eff = false, have_prev = false;
         int winner = -1, rounds = 0, reason = CSIM_REASON_MAX_ROUNDS;
         int ef0 = 0, ef1 = 0;                                    // run-off pair when fast2
+        if (R == 0) { for (int c = lane; c < C; c += 32) tally[c] = 0; __syncwarp(); }
 
         for (int r = 1; r <= R; ++r) {
             rounds = r;

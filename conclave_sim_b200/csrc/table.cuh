@@ -311,6 +311,7 @@ __global__ void __launch_bounds__(256) k_trials_table(TableArgs<Real> a) {
             }
         }
         // =============== outputs ===================================================================
+        if (exists && R == 0 && a.out.final_votes) for (int c = 0; c < C; ++c) a.out.final_votes[my_t * (uint64_t)C + c] = 0;
         if (exists) {
             a.out.winner[my_t] = winner; a.out.rounds[my_t] = rounds;
             if (a.out.reason) a.out.reason[my_t] = (uint8_t)(winner >= 0 ? CSIM_REASON_WINNER : CSIM_REASON_MAX_ROUNDS);

@@ -416,3 +416,35 @@ def test_integration_md_stub_runs(eng):
     ok = [r for r in results if r["winner"] is not None]
     assert 0.75 < len(ok) / 300 < 0.98 and all(r["winner"] in roster.ids for r in ok)
     assert all(r["reason"].startswith("Winner found by supermajority (56%") for r in ok)
+
+
+@pytest.mark.parametrize("ep_kw", [
+    dict(max_rounds=0), dict(max_rounds=1), dict(max_rounds=6, runoff_threshold_rounds=0), dict(max_rounds=6, runoff_threshold_rounds=-3),
+    dict(max_rounds=6, runoff_candidate_count=500), dict(max_rounds=6, runoff_candidate_count=1),
+    dict(max_rounds=5, supermajority_threshold=0.0), dict(max_rounds=5, supermajority_threshold=1.5),
+    dict(max_rounds=7, runoff_threshold_rounds=100), dict(max_rounds=9, runoff_threshold_rounds=2, runoff_candidate_count=3),
+], ids=lambda d: ",".join(f"{k}={v}" for k, v in d.items()))
+def test_edge_engine_parameters(eng, ep_kw):
+    """Degenerate worker arguments the reference accepts (simulate.py:30-41): every engine must follow the oracle."""
+    from conclave_sim_b200 import FP64, FP32
+    roster = O.synthetic_roster(37, seed=11)
+    upload(eng, roster)
+    mp = O.ModelParams(**CFG2)
+    kw = dict(max_rounds=6, supermajority_threshold=0.56)
+    kw.update(ep_kw)
+    ep = O.EngineParams(**kw)
+    for wiring, engines in ((O.WIRING_REF_CLI, (1, 2)), (O.WIRING_MODEL, (1,))):
+        ref = CO.run(roster, [(mp, ep)], wiring, 48, seed=2, want_tallies=True)
+        for en in engines:
+            out = eng.run([to_params(mp, ep)], 48, seed=2, wiring=wiring, engine=en, precision=FP64, want_round_tallies=True, want_final_votes=True)
+            assert np.array_equal(out.winner, ref["winner"]) and np.array_equal(out.rounds, ref["rounds"]), (wiring, en)
+            assert np.array_equal(out.reason, ref["reason"]), (wiring, en)
+            if ep.max_rounds > 0:
+                assert np.array_equal(out.round_tallies, ref["round_tallies"]) and np.array_equal(out.final_votes, ref["final_votes"]), (wiring, en)
+            else:
+                assert (out.final_votes == 0).all()
+            o32 = eng.run([to_params(mp, ep)], 48, seed=2, wiring=wiring, engine=en, precision=FP32, want_final_votes=True)
+            assert np.mean(o32.rounds == ref["rounds"]) > 0.8, (wiring, en)
+            if ep.max_rounds == 0:
+                assert (o32.final_votes == 0).all() and (o32.rounds == 0).all()
+    assert eng.run([to_params(mp, ep)], 0, seed=2).winner.shape == (0,)
