@@ -19,9 +19,11 @@
  * Conventions: plain pointers and sizes, caller owns every buffer, no
  * exceptions cross the boundary.  Every call returns CSIM_OK (0) or a negative
  * csim_status; csim_last_error() gives the message of the calling thread's
- * last failure.  A context is bound to one CUDA device and is re-entrant per
- * (context, stream); contexts are independent.  There is NO CPU fallback: with
- * no usable CUDA device csim_create fails with CSIM_ERR_CUDA.
+ * last failure.  A context is bound to one CUDA device and owns staging
+ * buffers that successive calls reuse: calls on ONE context must be issued
+ * from one thread at a time and are ordered on the stream they are given;
+ * use one context per host thread (contexts are independent).  There is NO CPU
+ * fallback: with no usable CUDA device csim_create fails with CSIM_ERR_CUDA.
  */
 #ifndef CONCLAVE_B200_H
 #define CONCLAVE_B200_H

@@ -448,3 +448,27 @@ def test_edge_engine_parameters(eng, ep_kw):
             if ep.max_rounds == 0:
                 assert (o32.final_votes == 0).all() and (o32.rounds == 0).all()
     assert eng.run([to_params(mp, ep)], 0, seed=2).winner.shape == (0,)
+
+
+def test_heterogeneous_parameter_sets_and_wide_sim_ids(eng):
+    """One batch mixing run-off widths, run-off start rounds and thresholds; sim ids beyond 2^32 (Philox counter word 1)."""
+    from conclave_sim_b200 import FP64, FP32
+    roster = G.real_roster()
+    upload(eng, roster)
+    mp = O.ModelParams(**CFG2)
+    eps = [O.EngineParams(max_rounds=12, supermajority_threshold=0.56, runoff_threshold_rounds=5, runoff_candidate_count=2),
+           O.EngineParams(max_rounds=12, supermajority_threshold=0.50, runoff_threshold_rounds=3, runoff_candidate_count=3),
+           O.EngineParams(max_rounds=12, supermajority_threshold=0.60, runoff_threshold_rounds=4, runoff_candidate_count=0),
+           O.EngineParams(max_rounds=12, supermajority_threshold=0.45, runoff_threshold_rounds=1, runoff_candidate_count=5)]
+    sets = [(mp, ep) for ep in eps]
+    base = 2**40 + 5
+    for wiring, engines in ((O.WIRING_REF_CLI, (1, 2)), (O.WIRING_MODEL, (1,))):
+        ref = CO.run(roster, sets, wiring, 40, seed=2**63 + 11, sim_id_begin=base, want_tallies=True)
+        for en in engines:
+            out = eng.run([to_params(*s) for s in sets], 40, seed=2**63 + 11, sim_id_begin=base, wiring=wiring, engine=en,
+                          precision=FP64, want_round_tallies=True)
+            assert np.array_equal(out.winner, ref["winner"]) and np.array_equal(out.rounds, ref["rounds"]), (wiring, en)
+            assert np.array_equal(out.round_tallies, ref["round_tallies"]), (wiring, en)
+            assert np.array_equal(out.winner_hist, ref["winner_hist"]) and np.array_equal(out.totals, ref["totals"])
+            o32 = eng.run([to_params(*s) for s in sets], 40, seed=2**63 + 11, sim_id_begin=base, wiring=wiring, engine=en, precision=FP32)
+            assert np.mean(o32.rounds == ref["rounds"]) > 0.85, (wiring, en)
