@@ -141,8 +141,8 @@ __device__ __forceinline__ void chunk_acc(const LaneCtx32& k, int j, const float
                                           unsigned long long (&acc)[NE]) {
     const int L = LC > 0 ? LC : k.L;
     if (FACT) {
-        const ulonglong2* b4 = reinterpret_cast<const ulonglong2*>(k.pw + j * L);
-        const ulonglong2* c4 = reinterpret_cast<const ulonglong2*>(k.bq + j * L);
+        const ulonglong2* b4 = reinterpret_cast<const ulonglong2*>(k.pw) + j * (L >> 2);
+        const ulonglong2* c4 = reinterpret_cast<const ulonglong2*>(k.bq) + j * (L >> 2);
 #pragma unroll 2
         for (int i = 0; i < (L >> 2); ++i) {
             const ulonglong2 b = b4[i], c = c4[i];
@@ -427,20 +427,21 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                             acc[i] = 0ull;
                         }
                         const int je = e0 / L;                   // the electors of a group share their chunk (L % 4 == 0)
-                        float* pcol = pref + lane;
+                        float* pc[NE];
+                        float corr[NE];                           // running self-vote / stickiness correction of the prefix
+#pragma unroll
+                        for (int i = 0; i < NE; ++i) { pc[i] = pref + (size_t)i * nch * 32 + lane; corr[i] = 0.f; }
 #pragma unroll 1
                         for (int j = 0; j < nch; ++j) {
                             chunk_acc<NE, LC, FACT>(kx, j, xe, r2, acc);
-                            if (j == je) {
-#pragma unroll
-                                for (int i = 0; i < NE; ++i) acc[i] = f2_add(acc[i], f2_pack(-see[i], 0.f));
-                            }
+                            const bool at_self = j == je;
 #pragma unroll
                             for (int i = 0; i < NE; ++i) {
-                                if (MODEL && j == jp[i]) acc[i] = f2_add(acc[i], f2_pack(sadd[i], 0.f));
-                                pcol[i * nch * 32] = f2_lo(acc[i]) + f2_hi(acc[i]);     // running prefix, m units
+                                if (at_self) corr[i] -= see[i];
+                                if (MODEL && j == jp[i]) corr[i] += sadd[i];
+                                *pc[i] = (f2_lo(acc[i]) + f2_hi(acc[i])) + corr[i];     // running prefix, m units
+                                pc[i] += 32;
                             }
-                            pcol += 32;
                         }
 #pragma unroll 1
                         for (int i = 0; i < NE; ++i) {
