@@ -472,3 +472,56 @@ def test_heterogeneous_parameter_sets_and_wide_sim_ids(eng):
             assert np.array_equal(out.winner_hist, ref["winner_hist"]) and np.array_equal(out.totals, ref["totals"])
             o32 = eng.run([to_params(*s) for s in sets], 40, seed=2**63 + 11, sim_id_begin=base, wiring=wiring, engine=en, precision=FP32)
             assert np.mean(o32.rounds == ref["rounds"]) > 0.85, (wiring, en)
+
+
+def test_full_size_properties_cfg3_share(eng):
+    """BASELINE config 3 at this GPU's full share (1.25 M trials): size-independent properties.
+    (a) conservation: histograms, totals and per-trial rows agree; (b) a trial's outcome does not depend on
+    how the sim-id range is cut (what multi-GPU sharding relies on): two halves == the whole, bit for bit;
+    (c) the dense and the table engines — different kernels, same Philox stream — agree on > 99 % of trials and
+    their histograms are statistically indistinguishable; (d) fp32 vs fp64 likewise."""
+    from scipy import stats
+    from conclave_sim_b200 import FP32, FP64
+    roster = O.synthetic_roster(135)
+    upload(eng, roster)
+    p = [to_params(O.ModelParams(**CFG2), EP2)]
+    n = 1_250_000
+    dense = eng.run(p, n, seed=31337, engine=ENGINES["dense"], precision=FP32)
+    table = eng.run(p, n, seed=31337, engine=ENGINES["table"], precision=FP32)
+    exact = eng.run(p, n, seed=31337, engine=ENGINES["table"], precision=FP64)
+    for r in (dense, table, exact):
+        w, rd = r.winner, r.rounds
+        assert r.winner_hist.sum() == n and r.totals[0, 1] == n and r.totals[0, 0] == rd.astype(np.int64).sum()
+        assert np.array_equal(r.winner_hist[0], np.bincount(np.where(w >= 0, w, 135), minlength=136))
+        assert np.array_equal(r.rounds_hist[0], np.bincount(rd[w >= 0], minlength=21))
+        assert ((w >= 0) | (rd == 20)).all() and (rd >= 1).all() and (rd <= 20).all()
+        assert np.array_equal(r.reason, (w >= 0).astype(np.uint8))
+    half = n // 2
+    a = eng.run(p, half, seed=31337, sim_id_begin=0, engine=ENGINES["dense"], precision=FP32)
+    b = eng.run(p, n - half, seed=31337, sim_id_begin=half, engine=ENGINES["dense"], precision=FP32)
+    assert np.array_equal(np.concatenate([a.winner, b.winner]), dense.winner)
+    assert np.array_equal(np.concatenate([a.rounds, b.rounds]), dense.rounds)
+    assert np.array_equal(a.winner_hist + b.winner_hist, dense.winner_hist)
+    same_dt = np.mean((dense.winner == table.winner) & (dense.rounds == table.rounds))
+    same_te = np.mean((table.winner == exact.winner) & (table.rounds == exact.rounds))
+    print(f"dense==table on {same_dt:.5f}, table32==table64 on {same_te:.5f} of {n} trials")
+    assert same_dt > 0.99 and same_te > 0.99
+    for x, y in ((dense, table), (dense, exact)):
+        assert _chi2_homogeneity(x.winner_hist[0], y.winner_hist[0]) > 1e-3
+        assert _chi2_homogeneity(np.append(x.rounds_hist[0], x.winner_hist[0, 135]), np.append(y.rounds_hist[0], y.winner_hist[0, 135])) > 1e-3
+
+
+def test_cfg5_shape_at_scale(eng):
+    """BASELINE config 5 shape (1024 x 1024, 50 rounds) on 20 000 trials: engines agree, votes are conserved."""
+    from conclave_sim_b200 import FP32
+    roster = O.synthetic_roster(1024)
+    upload(eng, roster)
+    ep = O.EngineParams(max_rounds=50, supermajority_threshold=0.56)
+    p = [to_params(O.ModelParams(**CFG2), ep)]
+    n = 20000
+    d = eng.run(p, n, seed=5, engine=ENGINES["dense"], precision=FP32, want_final_votes=True)
+    t = eng.run(p, n, seed=5, engine=ENGINES["table"], precision=FP32, want_final_votes=True)
+    assert (d.final_votes.sum(axis=1) == 1024).all() and (t.final_votes.sum(axis=1) == 1024).all()
+    assert np.mean((d.winner == t.winner) & (d.rounds == t.rounds)) > 0.97
+    ref = CO.run(roster, [(O.ModelParams(**CFG2), ep)], O.WIRING_REF_CLI, 64, seed=5)
+    assert np.mean(t.winner[:64] == ref["winner"]) > 0.9
