@@ -303,11 +303,14 @@ def main():
     e2e_steps = max(2, min(args.steps, 3))
     begin, _ = shard_range(n_global, rank, world)
     hist_dev = torch.zeros((E + 1) + (R + 1) + 2, dtype=torch.int64, device=dev)
+    pinned = {"winner": torch.empty(n_local, dtype=torch.int32).pin_memory().numpy(),
+              "rounds": torch.empty(n_local, dtype=torch.int32).pin_memory().numpy(),
+              "reason": torch.empty(n_local, dtype=torch.uint8).pin_memory().numpy()}
     def e2e_step(i):
         eng._roster_key = None                      # force the roster upload inside the timed region
         eng.upload_roster(ideology, region, pap)
         r = eng.run([params], n_local, sim_id_begin=(1000 + i) * n_global + begin, seed=SEED, wiring=WIRING_REF_CLI,
-                    engine=ENGINE_DENSE, precision=FP32, want_reason=True)
+                    engine=ENGINE_DENSE, precision=FP32, want_reason=True, out=pinned)
         if world > 1:
             h = torch.from_numpy(np.concatenate([r.winner_hist.ravel(), r.rounds_hist.ravel(), r.totals.ravel()])).to(dev)
             dist.all_reduce(h)
@@ -369,7 +372,7 @@ def main():
                    "collective": "1 NCCL all-reduce (int64 sum) of winner/rounds histograms per step" if world > 1 else "none (1 GPU)"},
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": "elector-rounds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "conclave_sim_b200.Engine.run (host buffers) -> csim_run"},
+                "steps": e2e_steps, "api": "conclave_sim_b200.Engine.run (host buffers; results land in page-locked arrays) -> csim_run"},
         "table_engine": table_engine,
         "gpu_launches": int(launches1 - launches0),
         "clocks": clocks,

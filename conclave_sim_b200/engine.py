@@ -163,15 +163,24 @@ class Engine:
     def run(self, param_sets: Sequence[CsimParams], n_sims: int, *, sim_id_begin: int = 0, seed: int = 0,
             wiring: int = WIRING_REF_CLI, engine: int = ENGINE_AUTO, precision: int = FP32,
             tapes: Optional[np.ndarray] = None, want_reason: bool = True, want_final_votes: bool = False,
-            want_round_tallies: bool = False) -> RunResult:
-        """Host-buffer call: copies in, runs, copies out, synchronises."""
+            want_round_tallies: bool = False, out: Optional[Dict[str, np.ndarray]] = None) -> RunResult:
+        """Host-buffer call: copies in, runs, copies out, synchronises.
+        `out` may supply preallocated result arrays ('winner', 'rounds', 'reason': int32 / int32 / uint8 of n trials),
+        e.g. views of page-locked memory, so that the device-to-host copies run at full PCIe speed."""
         E = self.n_electors
         sets = (CsimParams * len(param_sets))(*param_sets)
         R = int(sets[0].max_rounds)
         n = len(param_sets) * int(n_sims)
-        winner = np.full(n, -1, np.int32)
-        rounds = np.zeros(n, np.int32)
-        reason = np.zeros(n, np.uint8) if want_reason else None
+        def _take(name, dtype):
+            a = None if out is None else out.get(name)
+            if a is None:
+                return np.zeros(n, dtype)
+            if a.dtype != dtype or a.shape != (n,) or not a.flags.c_contiguous:
+                raise ValueError(f"out['{name}'] must be a contiguous {np.dtype(dtype).name} array of shape ({n},)")
+            return a
+        winner = _take("winner", np.int32)
+        rounds = _take("rounds", np.int32)
+        reason = _take("reason", np.uint8) if want_reason else None
         final = np.zeros((n, E), np.int32) if want_final_votes else None
         tall = np.zeros((n, R, E), np.int32) if want_round_tallies else None
         wh = np.zeros((len(param_sets), E + 1), np.int64)
