@@ -422,7 +422,7 @@ static csim_status launch_table_t(csim_ctx* c, const BatchDev& b, const TrialOut
         return fail(CSIM_ERR_UNSUPPORTED, "table engine: a roster of %d electors does not fit in shared memory", E);
     a.warps_per_cta = wpc;
     const size_t smem = a.cta_smem + a.warp_smem * wpc;
-    auto kern = k_trials_table<Real>;
+    void (*kern)(TableArgs<Real>) = a.stage ? k_trials_table<Real, true> : k_trials_table<Real, false>;
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpc * 32, smem));

@@ -104,7 +104,7 @@ __device__ __forceinline__ int upper_bound_row(const Real* row, int n, int step0
     return pos;
 }
 
-template <class Real>
+template <class Real, bool STAGE>
 __global__ void __launch_bounds__(256) k_trials_table(TableArgs<Real> a) {
     constexpr bool F64 = sizeof(Real) == 8;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) k_trials_table(TableArgs<Real> a) {
     const int E = a.ro.E, C = E, R = a.b.R, kmax = a.kmax;
     const int Ei = (E + 3) & ~3;
     Real* tab_s = (Real*)smem_raw;                               // staged cdf_r  [E][C]   (stage == 1)
-    Real* q_s = tab_s + (a.stage ? (size_t)E * C : 0);           // run-off first-column table [R][E]
+    Real* q_s = tab_s + (STAGE ? (size_t)E * C : 0);             // run-off first-column table [R][E]
     unsigned char* base = smem_raw + a.cta_smem + (size_t)wib * a.warp_smem;
     int32_t* tally = (int32_t*)base;            base += sizeof(int32_t) * Ei;
     int32_t* eff = (int32_t*)base;              base += sizeof(int32_t) * ((kmax + 3) & ~3);
@@ -185,12 +185,11 @@ __global__ void __launch_bounds__(256) k_trials_table(TableArgs<Real> a) {
         // =============== full-field rounds, round-major ===========================================
         for (int r = 1; r <= r_full; ++r) {
             const Real* tab_g = a.cdf + ((size_t)set * R + (r - 1)) * (size_t)E * C;
-            if (a.stage) {
+            if (STAGE) {
                 __syncthreads();                                  // previous round's readers are done
                 for (size_t i = threadIdx.x; i < (size_t)E * C; i += blockDim.x) tab_s[i] = tab_g[i];
             }
             __syncthreads();
-            const Real* tab = a.stage ? tab_s : tab_g;
             if (!__any_sync(CSIM_FULL, alive)) continue;
             for (int ti = 0; ti < 32; ++ti) {
                 if (!__shfl_sync(CSIM_FULL, alive ? 1 : 0, ti)) continue;
@@ -200,7 +199,9 @@ __global__ void __launch_bounds__(256) k_trials_table(TableArgs<Real> a) {
                 for (int c = lane; c < C; c += 32) tally[c] = 0;
                 __syncwarp();
                 for_each_elector(r, t, s_lo, s_hi, [&](int e, Real u) {
-                    int vote = upper_bound_row<Real>(tab + (size_t)e * C, C, step0, u);
+                    // STAGE: the row lives in shared memory (a typed pointer keeps these LDS, not generic loads)
+                    int vote = STAGE ? upper_bound_row<Real>(tab_s + (size_t)e * C, C, step0, u)
+                                     : upper_bound_row<Real>(tab_g + (size_t)e * C, C, step0, u);
                     vote = vote < C ? vote : C - 1;
                     atomicAdd(&tally[vote], 1);
                 });
