@@ -412,7 +412,7 @@ static csim_status launch_table_t(csim_ctx* c, const BatchDev& b, const TrialOut
     const size_t Ei = ((size_t)E + 3) & ~(size_t)3;
     a.warp_smem = (Ei * 4 + (((size_t)kmax + 3) & ~(size_t)3) * 4 + Ei + 15) & ~(size_t)15;
     const size_t qtab = (((size_t)b.R * E * sizeof(Real)) + 15) & ~(size_t)15;
-    const size_t full = (((size_t)E * E * sizeof(Real)) + 15) & ~(size_t)15;
+    const size_t full = (cdf_round_stride(E) * sizeof(Real) + 15) & ~(size_t)15;
     int wpc = 8;
     a.stage_q = (qtab + a.warp_smem * wpc <= 64 * 1024) ? 1 : 0;
     a.stage = (a.stage_q && full + qtab + a.warp_smem * wpc <= 200 * 1024) ? 1 : 0;
@@ -448,10 +448,11 @@ static csim_status launch_table(csim_ctx* c, const csim_run_args* ra, const std:
     int kmax = 1;
     for (const DevSet& s : hs) kmax = std::max(kmax, s.k);
     const size_t rows = (size_t)b.n_sets * R * E;
+    const size_t cdf_elems = (size_t)b.n_sets * R * cdf_round_stride(E);
     const size_t wbytes = sizeof(double) * (size_t)b.n_sets * R * E * c->Epad;
     if (wbytes + rows * E * 12 > ((size_t)120 << 30)) return fail(CSIM_ERR_UNSUPPORTED, "CDF tables need more than 120 GB");
     CU_TRY(c->W.reserve(wbytes));
-    CU_TRY(c->cdf64.reserve(sizeof(double) * rows * E));
+    CU_TRY(c->cdf64.reserve(sizeof(double) * cdf_elems));
     CU_TRY(c->cdfk64.reserve(sizeof(double) * rows * kmax));
     RosterDev ro = roster_dev(c);
     dim3 g((c->Epad + 127) / 128, E, b.n_sets * R);
@@ -463,10 +464,10 @@ static csim_status launch_table(csim_ctx* c, const csim_run_args* ra, const std:
     }
     if (ra->precision == CSIM_FP64)
         return launch_table_t<double>(c, b, out, kmax, (const double*)c->cdf64.p, (const double*)c->cdfk64.p, st);
-    CU_TRY(c->cdf32.reserve(sizeof(float) * rows * E));
+    CU_TRY(c->cdf32.reserve(sizeof(float) * cdf_elems));
     CU_TRY(c->cdfk32.reserve(sizeof(float) * rows * kmax));
     if (R > 0) {
-        k_f64_to_f32<<<c->prop.multiProcessorCount * 4, 256, 0, st>>>((const double*)c->cdf64.p, (float*)c->cdf32.p, rows * E);
+        k_f64_to_f32<<<c->prop.multiProcessorCount * 4, 256, 0, st>>>((const double*)c->cdf64.p, (float*)c->cdf32.p, cdf_elems);
         k_f64_to_f32<<<c->prop.multiProcessorCount, 256, 0, st>>>((const double*)c->cdfk64.p, (float*)c->cdfk32.p, rows * kmax);
         c->launches += 2;
     }

@@ -26,7 +26,8 @@
 
 // ---------------------------------------------------------------------------------------------
 // K0: CDF tables.  One thread per (set, round, elector) row.
-//   cdf  [sets][R][E][C]   full-field rows            (RandomState.choice: cumsum(p) / cumsum(p)[-1])
+//   cdf  [sets][R][ECp]    full-field rows [E][C] of one round, ECp = E*C rounded up to 4 elements so that every
+//                          round starts 16-byte aligned  (RandomState.choice: cumsum(p) / cumsum(p)[-1])
 //   cdfk [sets][R][E][kmax] run-off rows over the first k columns, renormalised as simulate.py:148-151
 // ---------------------------------------------------------------------------------------------
 template <class F>
@@ -45,6 +46,8 @@ __device__ __forceinline__ void cdf_row_exact64(F& prob, int ncol, double* out) 
     for (int i = 0; i < ncol; ++i) out[i] = __ddiv_rn(out[i], last);  // cdf /= cdf[-1]
 }
 
+__host__ __device__ inline size_t cdf_round_stride(int E) { return ((size_t)E * E + 3) & ~(size_t)3; }
+
 __global__ void k_cdf_tables64(RosterDev ro, const DevSet* sets, const double* W, int R, int kmax,
                                double* cdf, double* cdfk) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -59,7 +62,8 @@ __global__ void k_cdf_tables64(RosterDev ro, const DevSet* sets, const double* W
     double rs = np_pairwise(row, C);                                  // model.py:451
     if (rs == 0.0) { row.degenerate = true; rs = np_pairwise(row, C); }
     Prob64 p{&row, rs};
-    cdf_row_exact64(p, C, cdf + ((size_t)sr * E + e) * C);
+    cdf_row_exact64(p, C, cdf + (size_t)sr * cdf_round_stride(E) + (size_t)e * C);
+    if (e == 0) for (size_t i = (size_t)E * C; i < cdf_round_stride(E); ++i) cdf[(size_t)sr * cdf_round_stride(E) + i] = 1.0;   // pad
     if (S.k > 0) cdf_row_exact64(p, S.k, cdfk + ((size_t)sr * E + e) * kmax);
 }
 
@@ -75,7 +79,7 @@ struct TableArgs {
     RosterDev ro;
     BatchDev b;
     TrialOut out;
-    const Real* cdf;        // [sets][R][E][C]
+    const Real* cdf;        // [sets][R][ECp]  (ECp = cdf_round_stride(E))
     const Real* cdfk;       // [sets][R][E][kmax]
     int kmax;
     int warps_per_cta;
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(256) k_trials_table(TableArgs<Real> a) {
     const int E = a.ro.E, C = E, R = a.b.R, kmax = a.kmax;
     const int Ei = (E + 3) & ~3;
     Real* tab_s = (Real*)smem_raw;                               // staged cdf_r  [E][C]   (stage == 1)
-    Real* q_s = tab_s + (STAGE ? (size_t)E * C : 0);             // run-off first-column table [R][E]
+    Real* q_s = tab_s + (STAGE ? cdf_round_stride(E) : 0);       // run-off first-column table [R][E]
     unsigned char* base = smem_raw + a.cta_smem + (size_t)wib * a.warp_smem;
     int32_t* tally = (int32_t*)base;            base += sizeof(int32_t) * Ei;
     int32_t* eff = (int32_t*)base;              base += sizeof(int32_t) * ((kmax + 3) & ~3);
@@ -184,10 +188,17 @@ __global__ void __launch_bounds__(256) k_trials_table(TableArgs<Real> a) {
 
         // =============== full-field rounds, round-major ===========================================
         for (int r = 1; r <= r_full; ++r) {
-            const Real* tab_g = a.cdf + ((size_t)set * R + (r - 1)) * (size_t)E * C;
+            const Real* tab_g = a.cdf + ((size_t)set * R + (r - 1)) * cdf_round_stride(E);
             if (STAGE) {
                 __syncthreads();                                  // previous round's readers are done
-                for (size_t i = threadIdx.x; i < (size_t)E * C; i += blockDim.x) tab_s[i] = tab_g[i];
+                // asynchronous 16-byte copies global -> shared (LDGSTS): all of a thread's ~18 chunks are in flight at once
+                const uint32_t n16 = (uint32_t)(cdf_round_stride(E) * sizeof(Real) / 16);
+                const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(tab_s);
+                const char* gbase = reinterpret_cast<const char*>(tab_g);
+                for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + i * 16), "l"(gbase + (size_t)i * 16) : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
             __syncthreads();
             if (!__any_sync(CSIM_FULL, alive)) continue;
@@ -241,7 +252,7 @@ __global__ void __launch_bounds__(256) k_trials_table(TableArgs<Real> a) {
                 if (!fast2) {
                     // generic k: rebuild round r_full's stable top-k from its tally: replay that round's draws
                     // (rare path; k != 2).  The tally is recomputed exactly as in the loop above.
-                    const Real* tab_g = a.cdf + ((size_t)set * R + (r_full - 1)) * (size_t)E * C;
+                    const Real* tab_g = a.cdf + ((size_t)set * R + (r_full - 1)) * cdf_round_stride(E);
                     for (int c = lane; c < C; c += 32) tally[c] = 0;
                     __syncwarp();
                     for_each_elector(r_full, t, s_lo, s_hi, [&](int e, Real u) {
