@@ -413,7 +413,7 @@ static csim_status launch_table_t(csim_ctx* c, const BatchDev& b, const TrialOut
     a.warp_smem = (Ei * 4 + (((size_t)kmax + 3) & ~(size_t)3) * 4 + Ei + 15) & ~(size_t)15;
     const size_t qtab = (((size_t)b.R * E * sizeof(Real)) + 15) & ~(size_t)15;
     const size_t full = (cdf_round_stride(E) * sizeof(Real) + 15) & ~(size_t)15;
-    int wpc = 8;
+    int wpc = CSIM_TABLE_WPC;
     a.stage_q = (qtab + a.warp_smem * wpc <= 64 * 1024) ? 1 : 0;
     a.stage = (a.stage_q && full + qtab + a.warp_smem * wpc <= 200 * 1024) ? 1 : 0;
     a.cta_smem = (a.stage ? full : 0) + (a.stage_q ? qtab : 0);
@@ -542,8 +542,14 @@ extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
         if (ra->totals) { CU_TRY(c->o_totals.reserve(8 * nh_t)); CU_TRY(cudaMemsetAsync(c->o_totals.p, 0, 8 * nh_t, st)); out.totals = (unsigned long long*)c->o_totals.p; }
     }
 
-    // engine choice: the table engine when the matrix is trial-invariant (ref_cli), else the dense engines
-    const bool use_table = ra->engine == CSIM_ENGINE_TABLE || (ra->engine == CSIM_ENGINE_AUTO && ra->wiring == CSIM_WIRING_REF_CLI);
+    // engine choice (CSIM_ENGINE_AUTO): the table engine when the matrix is trial-invariant (ref_cli) AND the batch
+    // fills the GPU with its 512-trial super-batches (or the roster is large, where a dense row costs E^2);
+    // small fp32 batches (BASELINE configs 1-2: 100 / 1000 trials) finish sooner on the dense kernel's one-warp-per-trial grid
+    bool use_table = ra->engine == CSIM_ENGINE_TABLE;
+    if (ra->engine == CSIM_ENGINE_AUTO && ra->wiring == CSIM_WIRING_REF_CLI) {
+        const uint64_t n_sb = ((ra->n_sims + (uint64_t)CSIM_TABLE_WPC * 32 - 1) / ((uint64_t)CSIM_TABLE_WPC * 32)) * ra->n_param_sets;
+        use_table = ra->precision == CSIM_FP64 || E > 256 || n_sb >= (uint64_t)c->prop.multiProcessorCount / 2;
+    }
     csim_status s = use_table ? launch_table(c, ra, hs, b, out, st)
                               : (ra->precision == CSIM_FP64 ? launch_exact64(c, ra, hs, b, out, st) : launch_dense32(c, ra, hs, hb, b, out, st));
     if (s != CSIM_OK) return s;

@@ -108,8 +108,11 @@ __device__ __forceinline__ int upper_bound_row(const Real* row, int n, int step0
     return pos;
 }
 
+#ifndef CSIM_TABLE_WPC
+#define CSIM_TABLE_WPC 16
+#endif
 template <class Real, bool STAGE>
-__global__ void __launch_bounds__(256) k_trials_table(TableArgs<Real> a) {
+__global__ void __launch_bounds__(CSIM_TABLE_WPC * 32, 1024 / (CSIM_TABLE_WPC * 32)) k_trials_table(TableArgs<Real> a) {
     constexpr bool F64 = sizeof(Real) == 8;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
