@@ -169,7 +169,10 @@ __host__ __device__ inline size_t exact64_warp_smem(int E, int Fmax, int kmax) {
     return (n + 15) & ~(size_t)15;
 }
 
-__global__ void __launch_bounds__(256) k_trials_exact64(Exact64Args a) {
+#ifndef CSIM_EXACT_MINB
+#define CSIM_EXACT_MINB 3      // 80 registers: the fp64 engine is latency-bound, three CTAs per SM nearly halve its time
+#endif
+__global__ void __launch_bounds__(256, CSIM_EXACT_MINB) k_trials_exact64(Exact64Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int E = a.ro.E, C = E, R = a.b.R;
