@@ -525,3 +525,22 @@ def test_cfg5_shape_at_scale(eng):
     assert np.mean((d.winner == t.winner) & (d.rounds == t.rounds)) > 0.97
     ref = CO.run(roster, [(O.ModelParams(**CFG2), ep)], O.WIRING_REF_CLI, 64, seed=5)
     assert np.mean(t.winner[:64] == ref["winner"]) > 0.9
+
+
+@pytest.mark.parametrize("E", [2, 33, 129, 200, 300])
+def test_model_wiring_on_ragged_rosters(eng, E):
+    """`model` wiring (bandwagon + stickiness live) on roster sizes around the 32 / 128 lane and quad boundaries."""
+    from conclave_sim_b200 import FP32, FP64
+    roster = O.synthetic_roster(E, seed=100 + E)
+    upload(eng, roster)
+    mp = O.ModelParams(**dict(CFG2, stickiness_factor=1.5, bandwagon_strength=1.0))
+    ep = O.EngineParams(max_rounds=9, supermajority_threshold=0.6, runoff_threshold_rounds=4)
+    n = 96
+    ref = CO.run(roster, [(mp, ep)], O.WIRING_MODEL, n, seed=8, want_tallies=True)
+    out = eng.run([to_params(mp, ep)], n, seed=8, wiring=O.WIRING_MODEL, precision=FP64, want_round_tallies=True)
+    assert np.array_equal(out.winner, ref["winner"]) and np.array_equal(out.round_tallies, ref["round_tallies"])
+    o32 = eng.run([to_params(mp, ep)], n, seed=8, wiring=O.WIRING_MODEL, precision=FP32, want_round_tallies=True)
+    first = o32.round_tallies[:, 0, :]
+    assert (first.sum(axis=1) == E).all()
+    agree = np.mean((o32.winner == ref["winner"]) & (o32.rounds == ref["rounds"]))
+    assert agree > 0.85, (E, agree)
