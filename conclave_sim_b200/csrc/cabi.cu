@@ -22,6 +22,7 @@
 #include "dense32.cuh"
 #include "prob32.cuh"
 #include "table.cuh"
+#include "prefix.cuh"
 
 static thread_local std::string g_err;
 
@@ -63,7 +64,7 @@ struct csim_ctx {
     cudaDeviceProp prop{};
     int E = 0, Epad = 0, G = 0;
     DevBuf x64, x32, region, pap;
-    DevBuf sets, betas, nbeta, W, tab, cdf64, cdfk64, cdf32, cdfk32;
+    DevBuf sets, betas, nbeta, W, tab, cdf64, cdfk64, cdf32, cdfk32, ptab;
     double x_mid = 0.0, x_half = 0.0;   // centre and half-range of ideology_score (factorised exp)
     // host-buffer mode staging
     DevBuf o_winner, o_rounds, o_reason, o_final, o_tallies, o_whist, o_rhist, o_totals, i_tape;
@@ -106,7 +107,7 @@ extern "C" csim_status csim_create(csim_ctx** out, int device) {
 extern "C" csim_status csim_destroy(csim_ctx* c) {
     if (!c) return CSIM_OK;
     cudaSetDevice(c->device);
-    for (DevBuf* b : {&c->x64, &c->x32, &c->region, &c->pap, &c->sets, &c->betas, &c->nbeta, &c->W, &c->tab, &c->cdf64, &c->cdfk64, &c->cdf32, &c->cdfk32, &c->o_winner, &c->o_rounds,
+    for (DevBuf* b : {&c->x64, &c->x32, &c->region, &c->pap, &c->sets, &c->betas, &c->nbeta, &c->W, &c->tab, &c->cdf64, &c->cdfk64, &c->cdf32, &c->cdfk32, &c->ptab, &c->o_winner, &c->o_rounds,
                       &c->o_reason, &c->o_final, &c->o_tallies, &c->o_whist, &c->o_rhist, &c->o_totals, &c->i_tape,
                       &c->p_prev, &c->p_cnt, &c->p_fat, &c->p_shares, &c->p_bw, &c->p_out, &c->p_cand})
         b->release();
@@ -474,6 +475,110 @@ static csim_status launch_table(csim_ctx* c, const csim_run_args* ra, const std:
     return launch_table_t<float>(c, b, out, kmax, (const float*)c->cdf32.p, (const float*)c->cdfk32.p, st);
 }
 
+// ---------------------------------------------------------------------------------------------
+// PREFIX engine (prefix.cuh)
+// ---------------------------------------------------------------------------------------------
+template <bool LC8, bool MODEL, bool STAGE>
+static csim_status launch_prefix_t(csim_ctx* c, PrefixArgs& a, cudaStream_t st) {
+    auto kern = k_trials_prefix<LC8, MODEL, STAGE>;
+    const int wpc = a.warps_per_cta;
+    const size_t smem = a.cta_smem + a.warp_smem * wpc;
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpc * 32, smem));
+    if (per_sm < 1) return fail(CSIM_ERR_UNSUPPORTED, "prefix kernel does not fit on an SM (threads=%d, smem=%zu)", wpc * 32, smem);
+    const uint64_t ctas = (uint64_t)c->prop.multiProcessorCount * per_sm;      // persistent: a multiple of the SM count
+    // work item = warps_per_cta x tpi trials of one set; ~8 items per CTA keeps the tail short while a CTA
+    // that stays inside one parameter set never re-stages its tables
+    uint64_t tpi = a.b.n_sims / ((uint64_t)wpc * ctas * 8);
+    tpi = std::max<uint64_t>(1, std::min<uint64_t>(tpi, 64));
+    a.tpi = (int)tpi;
+    const uint64_t per_item = (uint64_t)wpc * tpi;
+    const uint64_t n_items = ((a.b.n_sims + per_item - 1) / per_item) * a.b.n_sets;
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_items, ctas));
+    CU_TRY(cudaEventRecord(c->ev0, st));
+    kern<<<grid, wpc * 32, smem, st>>>(a);
+    CU_TRY(cudaEventRecord(c->ev1, st));
+    c->ev_valid = true;
+    ++c->launches;
+    CU_TRY(cudaGetLastError());
+    return CSIM_OK;
+}
+
+static csim_status launch_prefix(csim_ctx* c, const csim_run_args* ra, const std::vector<DevSet>& hs, const BatchDev& b,
+                                 const TrialOut& out, cudaStream_t st) {
+    for (const DevSet& s : hs)
+        if (s.en_fat || s.en_stop)
+            return fail(CSIM_ERR_UNSUPPORTED, "candidate fatigue / stop-candidate are implemented in CSIM_FP64 precision only");
+    for (int i = 0; i < ra->n_param_sets; ++i)
+        if (ra->params[i].regional_affinity_bonus < 0 || ra->params[i].bandwagon_strength < 0 || ra->params[i].papabile_weight_factor < 0)
+            return fail(CSIM_ERR_UNSUPPORTED, "negative bonus / strength / papabile factor: use CSIM_FP64 precision");
+    if (ra->precision != CSIM_FP32) return fail(CSIM_ERR_UNSUPPORTED, "the prefix engine is an fp32 engine (use DENSE or TABLE with CSIM_FP64)");
+    const int E = c->E, R = b.R;
+    if (c->G > 64) return fail(CSIM_ERR_UNSUPPORTED, "%d distinct regions (> 64): use CSIM_FP64 precision", c->G);
+    if (E >= 32768) return fail(CSIM_ERR_UNSUPPORTED, "prefix engine: at most 32767 electors");
+    if (R > 0 && (size_t)b.n_sets * R > 65535) return fail(CSIM_ERR_UNSUPPORTED, "n_param_sets * max_rounds exceeds 65535");
+    const bool model = ra->wiring == CSIM_WIRING_MODEL;
+    PrefixArgs a;
+    memset(&a, 0, sizeof a);
+    a.ro = roster_dev(c); a.b = b; a.out = out; a.nbeta = (const float*)c->nbeta.p;
+    int kmax = 1;
+    for (const DevSet& s : hs) kmax = std::max(kmax, s.k);
+    a.kmax = kmax;
+    // electors are dealt to lanes as whole Philox quads (128 per warp pass group); a tail of <= 64 electors goes one per lane
+    const int n_left = E & 127;
+    a.e_quad_end = (E & ~127) + (n_left > 64 ? 128 : 0);
+    a.rows = std::max(E, a.e_quad_end);
+    const int max_wpc = CSIM_PREFIX_THREADS / 32;
+    const size_t budget = (size_t)c->prop.sharedMemPerBlockOptin;
+    // smallest chunk (fewest re-scanned candidates) whose tables of all R rounds fit in shared memory next to >= 8 warps
+    int Ls_min = 3;
+    while (((E + (1 << Ls_min) - 1) >> Ls_min) > 32) ++Ls_min;
+    int Ls = -1, wpc = 0;
+    bool stage = false;
+    const char* force = getenv("CSIM_PREFIX_NOSTAGE");
+    for (int l = Ls_min; l <= Ls_min + 3 && !force; ++l) {
+        const int nch = (E + (1 << l) - 1) >> l, stride = nch | 1, CP = nch << l;
+        const size_t tab = (((size_t)std::max(R, 1) * a.rows * stride * 4) + 15) & ~(size_t)15;
+        const size_t fixed = tab + prefix_roster_smem(CP, c->G, R), per_warp = prefix_warp_smem(E, CP, kmax, model);
+        if (fixed + 8 * per_warp > budget) continue;
+        Ls = l; stage = true;
+        wpc = (int)std::min<size_t>(max_wpc, (budget - fixed) / per_warp);
+        break;
+    }
+    if (!stage) {
+        Ls = Ls_min;
+        const int nch = (E + (1 << Ls) - 1) >> Ls, CP = nch << Ls;
+        const size_t fixed = prefix_roster_smem(CP, c->G, R), per_warp = prefix_warp_smem(E, CP, kmax, model);
+        if (fixed + per_warp > budget) return fail(CSIM_ERR_UNSUPPORTED, "prefix engine: a roster of %d electors does not fit in shared memory", E);
+        wpc = (int)std::min<size_t>(max_wpc, (budget - fixed) / per_warp);
+    }
+    a.Ls = Ls; a.nch = (E + (1 << Ls) - 1) >> Ls; a.stride = a.nch | 1;
+    const int CP = a.nch << Ls;
+    a.set_pitch = (((size_t)std::max(R, 1) * a.rows * a.stride) + 3) & ~(size_t)3;
+    a.tab_smem = stage ? a.set_pitch * 4 : 0;
+    a.cta_smem = a.tab_smem + prefix_roster_smem(CP, c->G, R);
+    a.warp_smem = prefix_warp_smem(E, CP, kmax, model);
+    a.warps_per_cta = wpc;
+    const size_t tbytes = a.set_pitch * 4 * (size_t)b.n_sets;
+    if (tbytes > ((size_t)64 << 30)) return fail(CSIM_ERR_UNSUPPORTED, "prefix tables need %zu bytes", tbytes);
+    CU_TRY(c->ptab.reserve(tbytes));
+    a.T = (const float*)c->ptab.p;
+    if (R > 0) {
+        dim3 g((E + 7) / 8, b.n_sets * R);
+        k_prefix_tables32<<<g, 256, 0, st>>>(a.ro, b.sets, (const double*)c->betas.p, R, a.Ls, a.nch, a.stride, a.rows, a.e_quad_end,
+                                             a.set_pitch, (float*)c->ptab.p);
+        ++c->launches;
+    }
+    const bool lc8 = Ls == 3;
+    if (model) {
+        if (stage) return lc8 ? launch_prefix_t<true, true, true>(c, a, st) : launch_prefix_t<false, true, true>(c, a, st);
+        return lc8 ? launch_prefix_t<true, true, false>(c, a, st) : launch_prefix_t<false, true, false>(c, a, st);
+    }
+    if (stage) return lc8 ? launch_prefix_t<true, false, true>(c, a, st) : launch_prefix_t<false, false, true>(c, a, st);
+    return lc8 ? launch_prefix_t<true, false, false>(c, a, st) : launch_prefix_t<false, false, false>(c, a, st);
+}
+
 extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
     if (!c || !ra) return fail(CSIM_ERR_INVALID, "csim_run: NULL argument");
     if (c->E <= 0) return fail(CSIM_ERR_STATE, "csim_run: roster not uploaded");
@@ -481,7 +586,7 @@ extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
     if (!ra->winner || !ra->rounds) return fail(CSIM_ERR_INVALID, "csim_run: winner and rounds outputs are required");
     if (ra->wiring != CSIM_WIRING_REF_CLI && ra->wiring != CSIM_WIRING_MODEL) return fail(CSIM_ERR_INVALID, "csim_run: bad wiring %d", ra->wiring);
     if (ra->precision != CSIM_FP32 && ra->precision != CSIM_FP64) return fail(CSIM_ERR_INVALID, "csim_run: bad precision %d", ra->precision);
-    if (ra->engine != CSIM_ENGINE_AUTO && ra->engine != CSIM_ENGINE_DENSE && ra->engine != CSIM_ENGINE_TABLE)
+    if (ra->engine != CSIM_ENGINE_AUTO && ra->engine != CSIM_ENGINE_DENSE && ra->engine != CSIM_ENGINE_TABLE && ra->engine != CSIM_ENGINE_PREFIX)
         return fail(CSIM_ERR_INVALID, "csim_run: bad engine %d", ra->engine);
     if (ra->uniform_tape && ra->precision != CSIM_FP64) return fail(CSIM_ERR_INVALID, "csim_run: a uniform tape requires CSIM_FP64 precision");
     const int R = ra->params[0].max_rounds;
@@ -550,7 +655,8 @@ extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
         const uint64_t n_sb = ((ra->n_sims + (uint64_t)CSIM_TABLE_WPC * 32 - 1) / ((uint64_t)CSIM_TABLE_WPC * 32)) * ra->n_param_sets;
         use_table = ra->precision == CSIM_FP64 || E > 256 || n_sb >= (uint64_t)c->prop.multiProcessorCount / 2;
     }
-    csim_status s = use_table ? launch_table(c, ra, hs, b, out, st)
+    csim_status s = ra->engine == CSIM_ENGINE_PREFIX ? launch_prefix(c, ra, hs, b, out, st)
+                    : use_table ? launch_table(c, ra, hs, b, out, st)
                               : (ra->precision == CSIM_FP64 ? launch_exact64(c, ra, hs, b, out, st) : launch_dense32(c, ra, hs, hb, b, out, st));
     if (s != CSIM_OK) return s;
 

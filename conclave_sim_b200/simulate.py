@@ -46,7 +46,7 @@ DEFAULT_RUNOFF_CANDIDATE_COUNT = 2
 RUNTIME: Dict[str, Any] = dict(wiring="ref_cli", seed=None, device=0, precision="fp32", engine="auto")
 _WIRING = {"ref_cli": _cabi.WIRING_REF_CLI, "model": _cabi.WIRING_MODEL}
 _PRECISION = {"fp32": _cabi.FP32, "fp64": _cabi.FP64}
-_ENGINE = {"auto": _cabi.ENGINE_AUTO, "dense": _cabi.ENGINE_DENSE, "table": _cabi.ENGINE_TABLE}
+_ENGINE = {"auto": _cabi.ENGINE_AUTO, "dense": _cabi.ENGINE_DENSE, "table": _cabi.ENGINE_TABLE, "prefix": _cabi.ENGINE_PREFIX}
 
 
 def _seed() -> int:
@@ -178,7 +178,7 @@ def build_parser() -> argparse.ArgumentParser:
     gpu.add_argument("--seed", type=int, default=None, help="Philox key (default: fresh per process, like the reference's unseeded RNG).")
     gpu.add_argument("--device", type=int, default=0, help="CUDA device ordinal.")
     gpu.add_argument("--precision", choices=["fp32", "fp64"], default="fp32", help="fp32 fast path or fp64 exact path.")
-    gpu.add_argument("--engine", choices=["auto", "dense", "table"], default="auto")
+    gpu.add_argument("--engine", choices=["auto", "dense", "table", "prefix"], default="auto")
     return parser
 
 

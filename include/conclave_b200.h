@@ -52,6 +52,8 @@ typedef enum csim_status {
 #define CSIM_ENGINE_AUTO  0   /* ref_cli: TABLE when the batch is large enough to fill the GPU, else DENSE; model: DENSE */
 #define CSIM_ENGINE_DENSE 1   /* every trial re-evaluates its E x C scores each round */
 #define CSIM_ENGINE_TABLE 2   /* ref_cli only: trial-invariant per-round CDF tables, built once */
+#define CSIM_ENGINE_PREFIX 3  /* fp32, both wirings: trial-invariant chunk-prefix tables + per-trial bandwagon /
+                                 stickiness corrections, binary search over chunks, re-scan of one chunk */
 
 /* arithmetic */
 #define CSIM_FP32 0           /* fast path: fp32 scores, ex2.approx, 24-bit uniforms */
