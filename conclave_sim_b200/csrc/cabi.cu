@@ -505,6 +505,16 @@ static csim_status launch_prefix_t(csim_ctx* c, PrefixArgs& a, cudaStream_t st) 
     return CSIM_OK;
 }
 
+// preconditions of the fp32 PREFIX engine (launch_prefix reports the same conditions as errors)
+static bool prefix_supported(const csim_ctx* c, const csim_run_args* ra, const std::vector<DevSet>& hs, int R) {
+    for (const DevSet& s : hs) if (s.en_fat || s.en_stop) return false;
+    for (int i = 0; i < ra->n_param_sets; ++i)
+        if (ra->params[i].regional_affinity_bonus < 0 || ra->params[i].bandwagon_strength < 0 || ra->params[i].papabile_weight_factor < 0) return false;
+    if (c->G > 64 || c->E >= 32768) return false;
+    if (R > 0 && (size_t)ra->n_param_sets * R > 65535) return false;
+    return true;
+}
+
 static csim_status launch_prefix(csim_ctx* c, const csim_run_args* ra, const std::vector<DevSet>& hs, const BatchDev& b,
                                  const TrialOut& out, cudaStream_t st) {
     for (const DevSet& s : hs)
@@ -529,18 +539,24 @@ static csim_status launch_prefix(csim_ctx* c, const csim_run_args* ra, const std
     const int n_left = E & 127;
     a.e_quad_end = (E & ~127) + (n_left > 64 ? 128 : 0);
     a.rows = std::max(E, a.e_quad_end);
+    // only rounds that can be full-field need tables: once a run-off exists (k > 0) every round after
+    // max(runoff_threshold_rounds, 1) is a run-off round (simulate.py:183-186)
+    int Rt = 1;
+    for (const DevSet& s : hs) Rt = std::max(Rt, s.k > 0 ? std::min(R, std::max(s.rr, 1)) : R);
+    Rt = std::max(1, std::min(Rt, std::max(R, 1)));
+    a.Rt = Rt;
     const int max_wpc = CSIM_PREFIX_THREADS / 32;
     const size_t budget = (size_t)c->prop.sharedMemPerBlockOptin;
-    // smallest chunk (fewest re-scanned candidates) whose tables of all R rounds fit in shared memory next to >= 8 warps
+    // smallest chunk (fewest re-scanned candidates) whose tables fit in shared memory next to >= 8 warps
     int Ls_min = 3;
     while (((E + (1 << Ls_min) - 1) >> Ls_min) > 32) ++Ls_min;
     int Ls = -1, wpc = 0;
     bool stage = false;
     const char* force = getenv("CSIM_PREFIX_NOSTAGE");
-    for (int l = Ls_min; l <= Ls_min + 3 && !force; ++l) {
-        const int nch = (E + (1 << l) - 1) >> l, stride = nch | 1, CP = nch << l;
-        const size_t tab = (((size_t)std::max(R, 1) * a.rows * stride * 4) + 15) & ~(size_t)15;
-        const size_t fixed = tab + prefix_roster_smem(CP, c->G, R), per_warp = prefix_warp_smem(E, CP, kmax, model);
+    for (int l = Ls_min; l <= 4 && !force; ++l) {          // a chunk of more than 16 costs more to re-scan than L2 probes do
+        const int nch = (E + (1 << l) - 1) >> l, stride = nch | 1, CPP = prefix_cpp(nch, l);
+        const size_t tab = (((size_t)Rt * a.rows * stride * 4) + 15) & ~(size_t)15;
+        const size_t fixed = tab + prefix_roster_smem(CPP, c->G, R, a.rows), per_warp = prefix_warp_smem(E, CPP, kmax, a.rows, model);
         if (fixed + 8 * per_warp > budget) continue;
         Ls = l; stage = true;
         wpc = (int)std::min<size_t>(max_wpc, (budget - fixed) / per_warp);
@@ -548,25 +564,25 @@ static csim_status launch_prefix(csim_ctx* c, const csim_run_args* ra, const std
     }
     if (!stage) {
         Ls = Ls_min;
-        const int nch = (E + (1 << Ls) - 1) >> Ls, CP = nch << Ls;
-        const size_t fixed = prefix_roster_smem(CP, c->G, R), per_warp = prefix_warp_smem(E, CP, kmax, model);
+        const int nch = (E + (1 << Ls) - 1) >> Ls, CPP = prefix_cpp(nch, Ls);
+        const size_t fixed = prefix_roster_smem(CPP, c->G, R, a.rows), per_warp = prefix_warp_smem(E, CPP, kmax, a.rows, model);
         if (fixed + per_warp > budget) return fail(CSIM_ERR_UNSUPPORTED, "prefix engine: a roster of %d electors does not fit in shared memory", E);
         wpc = (int)std::min<size_t>(max_wpc, (budget - fixed) / per_warp);
     }
     a.Ls = Ls; a.nch = (E + (1 << Ls) - 1) >> Ls; a.stride = a.nch | 1;
-    const int CP = a.nch << Ls;
-    a.set_pitch = (((size_t)std::max(R, 1) * a.rows * a.stride) + 3) & ~(size_t)3;
+    const int CPP = prefix_cpp(a.nch, Ls);
+    a.set_pitch = (((size_t)Rt * a.rows * a.stride) + 3) & ~(size_t)3;
     a.tab_smem = stage ? a.set_pitch * 4 : 0;
-    a.cta_smem = a.tab_smem + prefix_roster_smem(CP, c->G, R);
-    a.warp_smem = prefix_warp_smem(E, CP, kmax, model);
+    a.cta_smem = a.tab_smem + prefix_roster_smem(CPP, c->G, R, a.rows);
+    a.warp_smem = prefix_warp_smem(E, CPP, kmax, a.rows, model);
     a.warps_per_cta = wpc;
     const size_t tbytes = a.set_pitch * 4 * (size_t)b.n_sets;
     if (tbytes > ((size_t)64 << 30)) return fail(CSIM_ERR_UNSUPPORTED, "prefix tables need %zu bytes", tbytes);
     CU_TRY(c->ptab.reserve(tbytes));
     a.T = (const float*)c->ptab.p;
     if (R > 0) {
-        dim3 g((E + 7) / 8, b.n_sets * R);
-        k_prefix_tables32<<<g, 256, 0, st>>>(a.ro, b.sets, (const double*)c->betas.p, R, a.Ls, a.nch, a.stride, a.rows, a.e_quad_end,
+        dim3 g((E + 7) / 8, b.n_sets * Rt);
+        k_prefix_tables32<<<g, 256, 0, st>>>(a.ro, b.sets, (const double*)c->betas.p, R, Rt, a.Ls, a.nch, a.stride, a.rows, a.e_quad_end,
                                              a.set_pitch, (float*)c->ptab.p);
         ++c->launches;
     }
@@ -647,17 +663,27 @@ extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
         if (ra->totals) { CU_TRY(c->o_totals.reserve(8 * nh_t)); CU_TRY(cudaMemsetAsync(c->o_totals.p, 0, 8 * nh_t, st)); out.totals = (unsigned long long*)c->o_totals.p; }
     }
 
-    // engine choice (CSIM_ENGINE_AUTO): the table engine when the matrix is trial-invariant (ref_cli) AND the batch
-    // fills the GPU with its 512-trial super-batches (or the roster is large, where a dense row costs E^2);
-    // small fp32 batches (BASELINE configs 1-2: 100 / 1000 trials) finish sooner on the dense kernel's one-warp-per-trial grid
-    bool use_table = ra->engine == CSIM_ENGINE_TABLE;
-    if (ra->engine == CSIM_ENGINE_AUTO && ra->wiring == CSIM_WIRING_REF_CLI) {
-        const uint64_t n_sb = ((ra->n_sims + (uint64_t)CSIM_TABLE_WPC * 32 - 1) / ((uint64_t)CSIM_TABLE_WPC * 32)) * ra->n_param_sets;
-        use_table = ra->precision == CSIM_FP64 || E > 256 || n_sb >= (uint64_t)c->prop.multiProcessorCount / 2;
+    // engine choice (CSIM_ENGINE_AUTO)
+    //   model wiring, fp32: the PREFIX engine (trial-invariant chunk-prefix tables + per-trial corrections) whenever its
+    //     preconditions hold, else DENSE;
+    //   ref_cli wiring: the TABLE engine when the batch fills the GPU with its 512-trial super-batches (or fp64); rosters
+    //     whose E x C rows do not fit in shared memory (E > 256) go to PREFIX; small fp32 batches (BASELINE configs 1-2:
+    //     100 / 1000 trials) finish sooner on the dense kernel's one-warp-per-trial grid.
+    int engine = ra->engine;
+    if (engine == CSIM_ENGINE_AUTO) {
+        const bool pfx_ok = ra->precision == CSIM_FP32 && prefix_supported(c, ra, hs, R);
+        if (ra->wiring == CSIM_WIRING_MODEL) {
+            engine = pfx_ok ? CSIM_ENGINE_PREFIX : CSIM_ENGINE_DENSE;
+        } else {
+            const uint64_t n_sb = ((ra->n_sims + (uint64_t)CSIM_TABLE_WPC * 32 - 1) / ((uint64_t)CSIM_TABLE_WPC * 32)) * ra->n_param_sets;
+            if (ra->precision == CSIM_FP64) engine = CSIM_ENGINE_TABLE;
+            else if (E > 256) engine = pfx_ok ? CSIM_ENGINE_PREFIX : CSIM_ENGINE_TABLE;
+            else engine = n_sb >= (uint64_t)c->prop.multiProcessorCount / 2 ? CSIM_ENGINE_TABLE : CSIM_ENGINE_DENSE;
+        }
     }
-    csim_status s = ra->engine == CSIM_ENGINE_PREFIX ? launch_prefix(c, ra, hs, b, out, st)
-                    : use_table ? launch_table(c, ra, hs, b, out, st)
-                              : (ra->precision == CSIM_FP64 ? launch_exact64(c, ra, hs, b, out, st) : launch_dense32(c, ra, hs, hb, b, out, st));
+    csim_status s = engine == CSIM_ENGINE_PREFIX ? launch_prefix(c, ra, hs, b, out, st)
+                    : engine == CSIM_ENGINE_TABLE ? launch_table(c, ra, hs, b, out, st)
+                    : (ra->precision == CSIM_FP64 ? launch_exact64(c, ra, hs, b, out, st) : launch_dense32(c, ra, hs, hb, b, out, st));
     if (s != CSIM_OK) return s;
 
     if (!dev) {

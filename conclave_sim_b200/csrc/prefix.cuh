@@ -42,7 +42,8 @@ struct PrefixArgs {
     BatchDev b;
     TrialOut out;
     const float* nbeta;     // [sets][R]  -beta_r * log2(e)
-    const float* T;         // [sets][R][rows][stride]  chunk-prefix tables
+    const float* T;         // [sets][Rt][rows][stride]  chunk-prefix tables of the full-field rounds
+    int Rt;                 // rounds that can be full-field: min(R, max(runoff_threshold_rounds, 1)) when a run-off exists, else R
     int Ls;                 // log2(candidates per chunk); L = 1 << Ls >= 8
     int nch;                // chunks, nch * L >= C, nch <= 32
     int stride;             // row pitch in floats (odd, >= nch)
@@ -62,28 +63,31 @@ struct PrefixArgs {
 __host__ __device__ inline int prefix_slot(int e, int e_quad_end) {
     return e < e_quad_end ? ((e >> 7) << 7) + ((e & 3) << 5) + ((e >> 2) & 31) : e;
 }
-__host__ __device__ inline size_t prefix_roster_smem(int CP, int G, int R) {
-    const size_t nblk = (size_t)CP >> 3;
-    return ((size_t)CP * 8 /*xs, reg*/ + nblk * G * 4 /*regmask*/ + nblk * 4 /*papmask*/ + (size_t)R * 4 /*nbeta*/ + 63) & ~(size_t)15;
+// Per-candidate arrays are stored with 4 floats of padding after every chunk of L: a lane reads its chunk with
+// 128-bit loads, and with a pitch of L + 4 floats the chunks start in 8 different 4-bank groups instead of 4 (L = 8).
+__host__ __device__ inline int prefix_cpp(int nch, int Ls) { return nch * ((1 << Ls) + 4); }
+__host__ __device__ inline size_t prefix_roster_smem(int CPP, int G, int R, int rows) {
+    const size_t rows8 = ((size_t)rows + 7) & ~(size_t)7;
+    return ((size_t)CPP * 8 /*xs, pw*/ + (size_t)CPP * G * 4 /*rb*/ + rows8 * 8 /*xg*/ + (size_t)R * 4 /*nbeta*/ + 31) & ~(size_t)15;
 }
-__host__ __device__ inline size_t prefix_warp_smem(int E, int CP, int kmax, bool model) {
-    const size_t Ei = ((size_t)E + 7) & ~(size_t)7;
+__host__ __device__ inline size_t prefix_warp_smem(int E, int CPP, int kmax, int rows, bool model) {
+    const size_t Ei = ((size_t)E + 7) & ~(size_t)7, rows8 = ((size_t)rows + 7) & ~(size_t)7;
     size_t n = Ei * 4 /*tally*/ + (((size_t)kmax + 3) & ~(size_t)3) * 4 /*eff*/ + Ei /*mark*/;
-    if (model) n += (size_t)CP * 4 /*bw*/ + 32 * 4 /*bwp*/ + Ei * 2 /*votes*/;
+    if (model) n += (size_t)CPP * 4 /*bw*/ + 32 * 4 /*bwp*/ + rows8 * 2 /*votes*/;
     return (n + 15) & ~(size_t)15;
 }
 
 // K0: chunk-prefix tables.  One warp per (set, round, elector), lane j sums chunk j in fp64 (the order of the
 // terms is model.py:311-324: exp, papabile factor, regional bonus), an inclusive warp scan makes the prefixes.
-// grid = (ceil(E / 8), sets * R), block = 256.
-__global__ void k_prefix_tables32(RosterDev ro, const DevSet* sets, const double* betas, int R, int Ls, int nch, int stride,
+// grid = (ceil(E / 8), sets * Rt), block = 256.
+__global__ void k_prefix_tables32(RosterDev ro, const DevSet* sets, const double* betas, int R, int Rt, int Ls, int nch, int stride,
                                   int rows, int e_quad_end, size_t set_pitch, float* T) {
     const int lane = threadIdx.x & 31, e = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int sr = blockIdx.y;                       // set * R + (round - 1)
+    const int set = blockIdx.y / Rt, r0 = blockIdx.y - set * Rt;       // r0 = round - 1
     const int C = ro.E;
     if (e >= C) return;
-    const DevSet* S = &sets[sr / R];
-    const double beta = betas[sr], xe = ro.x64[e], pwf = S->pwf, bonus = S->bonus;
+    const DevSet* S = &sets[set];
+    const double beta = betas[(size_t)set * R + r0], xe = ro.x64[e], pwf = S->pwf, bonus = S->bonus;
     const int ge = ro.region[e];
     double s = 0.0;
     if (lane < nch) {
@@ -102,109 +106,128 @@ __global__ void k_prefix_tables32(RosterDev ro, const DevSet* sets, const double
         if (lane >= off) s += o;
     }
     const double last = __shfl_sync(CSIM_FULL, s, nch - 1);
-    float* row = T + (size_t)(sr / R) * set_pitch + ((size_t)(sr % R) * rows + prefix_slot(e, e_quad_end)) * stride;
+    float* row = T + (size_t)set * set_pitch + ((size_t)r0 * rows + prefix_slot(e, e_quad_end)) * stride;
     if (lane < stride) row[lane] = (float)(lane < nch ? s : last);
     if (lane == 0 && stride > 32) row[32] = (float)last;
 }
 
-struct PrefixCtx {              // per-warp / per-round constants of a draw
-    const float* xs; const int32_t* reg; const uint32_t* regmask; const uint32_t* papmask;
-    const float* bw; const float* bwp;
-    float nb, bonus, st1p, pwf;
-    int C, G, Ls, nch, step0;
+// ---- shared memory through 32-bit window addresses ---------------------------------------------------
+// The draw touches ~10 shared arrays; as generic pointers they cost 20 registers and the compiler
+// re-derives them inside the hot loop.  One 32-bit address per array and explicit ld.shared keeps the
+// draw in registers.  (`asm volatile`: never merged or hoisted across a round; ptxas still schedules them.)
+__device__ __forceinline__ float lds_f(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int lds_i(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int lds_u16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return (int)v; }
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+    float4 v; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ void lds_xg(uint32_t a, float& x, int& g) { asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=f"(x), "=r"(g) : "r"(a)); }
+__device__ __forceinline__ void sts_u16(uint32_t a, int v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
+__device__ __forceinline__ void red_inc(uint32_t a) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory"); }
+
+struct PrefixCtx {              // per-warp / per-round constants of a draw (shared-window byte addresses)
+    uint32_t xs, pw, rb, xg;    // CTA: ideology f32[CPP], papabile weight f32[CPP] (0 beyond C), bonus table f32[G][CPP] (padded
+                                //      candidate order, prefix_cpp);  {ideology, region} of the electors in slot order, 8 B each
+    uint32_t bw, bwp, votes, tally;   // warp: bandwagon f32[CPP], its chunk prefix f32[32], last votes u16[rows] (slot order), tally i32[E]
+    uint32_t cp4;               // CPP * 4 (row pitch of rb)
+    float nb, st1p;
+    int C, Ls, nch4, step0_4;   // nch4 = 4 nch, step0_4 = 4 x (largest power of two <= nch)
 };
 
-__device__ __forceinline__ float prefix_pw(const PrefixCtx& k, int c) {
-    return ((k.papmask[c >> 3] >> (c & 7)) & 1u) ? k.pwf : 1.0f;
-}
-
-// every term of one score, inline (run-off rounds)
+// every term of one score, inline (run-off rounds; c is warp-uniform)
 template <bool MODEL>
 __device__ __forceinline__ float prefix_full_score(const PrefixCtx& k, int e, int c, float xe, int ge, int prev) {
-    float v = ex2_approx(fabsf(xe - k.xs[c]) * k.nb) * prefix_pw(k, c);
-    if (k.reg[c] == ge) v += k.bonus;
+    const uint32_t o = 4u * (uint32_t)(c + ((c >> k.Ls) << 2));
+    float v = fmaf(ex2_approx(fabsf(xe - lds_f(k.xs + o)) * k.nb), lds_f(k.pw + o), lds_f(k.rb + ge * k.cp4 + o));
     if (MODEL) {
-        v += k.bw[c];
+        v += lds_f(k.bw + o);
         if (c == prev) v *= k.st1p;
     }
     return c == e ? 0.0f : v;
 }
 
-// One vote of a full-field round.  Trow = this elector's row of the round's chunk-prefix table.
-template <bool LC8, bool MODEL>
-__device__ __forceinline__ int prefix_draw(const PrefixCtx& k, const float* __restrict__ Trow, int e, float u, int prev) {
-    const int C = k.C, Ls = LC8 ? 3 : k.Ls, nch = k.nch;
-    const float xe = k.xs[e];
-    const int ge = k.reg[e];
-    const int je = e >> Ls;
+// One vote of a full-field round.  STAGE: trow = shared address of this elector's row of the round's chunk-prefix
+// table; else Tg = the row in global memory.
+template <bool LC8, bool MODEL, bool STAGE>
+__device__ __forceinline__ int prefix_draw(const PrefixCtx& k, uint32_t trow, const float* __restrict__ Tg, int e, int slot, float u, int prev) {
+    const int Ls = LC8 ? 3 : k.Ls, nch4 = k.nch4;
+    float xe; int ge;
+    lds_xg(k.xg + 8 * slot, xe, ge);
+    const uint32_t rbrow = k.rb + ge * k.cp4;
+    const float nb = k.nb;
     float selfbw = 0.f, sadd = 0.f;
-    int jp = 0x7fffffff;
+    const int je4 = (e >> Ls) << 2;
+    int jp4 = 0x7fffffff;
     if (MODEL) {
-        selfbw = k.bw[e];                                   // bwp counts e's own bandwagon term; its score is 0 (model.py:418-424)
+        selfbw = lds_f(k.bw + 4 * (e + (je4 & ~3)));        // bwp counts e's own bandwagon term; its score is 0 (model.py:418-424)
         if (prev >= 0 && prev != e) {                       // stickiness, model.py:357-367
-            float b = ex2_approx(fabsf(xe - k.xs[prev]) * k.nb) * prefix_pw(k, prev);
-            if (k.reg[prev] == ge) b += k.bonus;
-            b += k.bw[prev];
+            jp4 = (prev >> Ls) << 2;
+            const uint32_t o = 4u * (uint32_t)(prev + jp4);
+            float b = fmaf(ex2_approx(fabsf(xe - lds_f(k.xs + o)) * nb), lds_f(k.pw + o), lds_f(rbrow + o));
+            b += lds_f(k.bw + o);
             sadd = b * (k.st1p - 1.0f);
-            jp = prev >> Ls;
         }
     }
-    auto F = [&](int j) -> float {                          // prefix of the row over chunks 0..j
-        float v = Trow[j];
+    auto F = [&](int j4) -> float {                         // prefix of the row over chunks 0..j  (j4 = 4 j)
+        float v = STAGE ? lds_f(trow + j4) : __ldg(reinterpret_cast<const float*>(reinterpret_cast<const char*>(Tg) + j4));
         if (MODEL) {
-            v += k.bwp[j];
-            v -= (j >= je) ? selfbw : 0.0f;
-            v += (j >= jp) ? sadd : 0.0f;
+            v += lds_f(k.bwp + j4);
+            v = (j4 >= je4) ? v - selfbw : v;
+            v = (j4 >= jp4) ? v + sadd : v;
         }
         return v;
     };
-    const float S = F(nch - 1);
+    const float S = F(nch4 - 4);
     if (!(S > 0.0f)) {            // all scores vanished: the reference makes the row uniform INCLUDING self (model.py:447-449)
-        const int j = (int)(u * (float)C);
-        return j < C ? j : C - 1;
+        const int j = (int)(u * (float)k.C);
+        return j < k.C ? j : k.C - 1;
     }
     const float tgt = u * S;
-    int pos = 0;                  // number of chunks whose prefix is <= tgt
-    for (int step = k.step0; step > 0; step >>= 1) {
-        const int np = pos + step;
-        if (np <= nch && F(np - 1) <= tgt) pos = np;
+    int pos4 = 0;                 // 4 x number of chunks whose prefix is <= tgt
+    float cum = 0.0f;             // prefix below the chunk the target falls into
+    for (int st = k.step0_4; st >= 4; st >>= 1) {
+        const int np4 = min(pos4 + st, nch4);               // probing the last entry twice is harmless
+        const float f = F(np4 - 4);
+        const bool le = f <= tgt;
+        pos4 = le ? np4 : pos4;
+        cum = le ? f : cum;
     }
-    const int jstar = pos > nch - 1 ? nch - 1 : pos;
-    float cum = jstar > 0 ? F(jstar - 1) : 0.0f;
-    const int c0 = jstar << Ls;
+    if (pos4 >= nch4) {           // u S rounded up to S: the vote is in the last chunk
+        pos4 = nch4 - 4;
+        cum = pos4 > 0 ? F(pos4 - 4) : 0.0f;
+    }
+    const int c0 = (pos4 >> 2) << Ls;
     int cnt = 0;
     const int nb8 = LC8 ? 1 : (1 << (Ls - 3));
-    const float nb = k.nb;
-    for (int bi = 0; bi < nb8; ++bi) {                      // blocks of 8 candidates of chunk jstar, in roster order
-        const int blk = (c0 >> 3) + bi, cb = blk << 3;
-        const float4 xa = *reinterpret_cast<const float4*>(k.xs + cb), xb = *reinterpret_cast<const float4*>(k.xs + cb + 4);
-        const uint32_t rm = k.regmask[blk * k.G + ge];       // bit i: candidate cb+i is of e's region
-        const uint32_t pz = k.papmask[blk];                  // bits 0-7: papabile; bits 8-15: index >= C (padding)
-        const uint32_t zm = (pz >> 8) | ((blk == (e >> 3)) ? (1u << (e & 7)) : 0u);   // bit i: score is zero (self / padding)
-        uint32_t sm = 0;
+    for (int bi = 0; bi < nb8; ++bi) {                      // blocks of 8 candidates of the chunk, in roster order
+        const int cb = c0 + 8 * bi;
+        const uint32_t o = 4u * (uint32_t)cb + 4u * (uint32_t)pos4;     // padded order: 4 extra floats per chunk before this one
+        const float4 xa = lds_f4(k.xs + o), xb = lds_f4(k.xs + o + 16);
+        const float4 pa = lds_f4(k.pw + o), pb = lds_f4(k.pw + o + 16);          // 0 beyond C: padding scores nothing
+        const float4 ra = lds_f4(rbrow + o), rb = lds_f4(rbrow + o + 16);        // regional bonus of e's region
         float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
-        if (MODEL) {
-            if (prev >= 0 && (prev >> 3) == blk) sm = 1u << (prev & 7);
-            ba = *reinterpret_cast<const float4*>(k.bw + cb); bb = *reinterpret_cast<const float4*>(k.bw + cb + 4);
-        }
-#define CSIM_PRESCAN(i, xv, bv)                                                          \
+        if (MODEL) { ba = lds_f4(k.bw + o); bb = lds_f4(k.bw + o + 16); }
+        const int is = e - cb;                               // position of e itself / of prev inside this block (else outside 0..7)
+        const int ip = MODEL ? prev - cb : -1;
+#define CSIM_PRESCAN(i, xv, pv, rv, bv)                                                  \
         {                                                                                \
-            const float m = ex2_approx(fabsf(xe - (xv)) * nb);                           \
-            float v = fmaf(m, ((pz >> (i)) & 1u) ? k.pwf : 1.0f, ((rm >> (i)) & 1u) ? k.bonus : 0.0f); \
-            if (MODEL) { v += (bv); if ((sm >> (i)) & 1u) v *= k.st1p; }                 \
-            if ((zm >> (i)) & 1u) v = 0.0f;                                              \
+            float v = fmaf(ex2_approx(fabsf(xe - (xv)) * nb), (pv), (rv));               \
+            if (MODEL) { v += (bv); if (ip == (i)) v *= k.st1p; }                        \
+            if (is == (i)) v = 0.0f;                                                     \
             cum += v;                                                                    \
             cnt += (cum <= tgt) ? 1 : 0;                                                 \
         }
-        CSIM_PRESCAN(0, xa.x, ba.x) CSIM_PRESCAN(1, xa.y, ba.y) CSIM_PRESCAN(2, xa.z, ba.z) CSIM_PRESCAN(3, xa.w, ba.w)
-        CSIM_PRESCAN(4, xb.x, bb.x) CSIM_PRESCAN(5, xb.y, bb.y) CSIM_PRESCAN(6, xb.z, bb.z) CSIM_PRESCAN(7, xb.w, bb.w)
+        CSIM_PRESCAN(0, xa.x, pa.x, ra.x, ba.x) CSIM_PRESCAN(1, xa.y, pa.y, ra.y, ba.y)
+        CSIM_PRESCAN(2, xa.z, pa.z, ra.z, ba.z) CSIM_PRESCAN(3, xa.w, pa.w, ra.w, ba.w)
+        CSIM_PRESCAN(4, xb.x, pb.x, rb.x, bb.x) CSIM_PRESCAN(5, xb.y, pb.y, rb.y, bb.y)
+        CSIM_PRESCAN(6, xb.z, pb.z, rb.z, bb.z) CSIM_PRESCAN(7, xb.w, pb.w, rb.w, bb.w)
 #undef CSIM_PRESCAN
         if (cnt < 8 * (bi + 1)) break;                       // the crossing is inside this block
     }
     int vote = c0 + cnt;                                     // == first c with cum > tgt
-    const int maxc = min(c0 + (1 << Ls) - 1, C - 1);
+    const int maxc = min(c0 + (1 << Ls) - 1, k.C - 1);
     vote = vote > maxc ? maxc : vote;                        // rounding at the chunk's upper edge
-    if (vote == e) vote = e > 0 ? e - 1 : (C > 1 ? 1 : 0);
+    if (vote == e) vote = e > 0 ? e - 1 : (k.C > 1 ? 1 : 0);
     return vote;
 }
 
@@ -213,54 +236,53 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(Prefix
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int E = a.ro.E, C = E, R = a.b.R, G = a.ro.G;
-    const int Ls = LC8 ? 3 : a.Ls, nch = a.nch, CP = nch << Ls, nblk = CP >> 3;
-    const int Ei = (E + 7) & ~7;
+    const int Ls = LC8 ? 3 : a.Ls, nch = a.nch, Lp = (1 << Ls) + 4, CPP = nch * Lp;
+    const int Ei = (E + 7) & ~7, rows8 = (a.rows + 7) & ~7;
+    auto pc = [&](int c) { return c + ((c >> Ls) << 2); };   // index of candidate c in the padded arrays
     const int wpc = a.warps_per_cta;
     // ---- CTA-shared: staged tables of the current set, then roster tables --------------------------
     float* Ts = (float*)smem_raw;
     unsigned char* p = smem_raw + a.tab_smem;
-    float* xs = (float*)p;                      p += sizeof(float) * CP;
-    int32_t* reg = (int32_t*)p;                 p += sizeof(int32_t) * CP;
-    uint32_t* regmask = (uint32_t*)p;           p += sizeof(uint32_t) * nblk * G;   // [blk][G]: bit i <-> candidate 8 blk + i is of region g
-    uint32_t* papmask = (uint32_t*)p;           p += sizeof(uint32_t) * nblk;
+    float* xs = (float*)p;                      p += sizeof(float) * CPP;
+    float* pwv = (float*)p;                     p += sizeof(float) * CPP;           // papabile weight of the current set (0 = padding)
+    float* rbv = (float*)p;                     p += sizeof(float) * CPP * G;       // [g][c]: bonus if region_c == g else 0
+    int2* xg = (int2*)p;                        p += sizeof(int2) * rows8;          // {ideology bits, region} by elector slot
     float* nbs = (float*)p;                                                         // [R] -beta_r log2 e of the current set
-    for (int c = threadIdx.x; c < CP; c += blockDim.x) {
-        xs[c] = c < C ? a.ro.x32[c] : 0.0f;
-        reg[c] = c < C ? a.ro.region[c] : -1;
-    }
-    for (int i = threadIdx.x; i < nblk * G; i += blockDim.x) {
-        const int blk = i / G, g = i - blk * G;
-        uint32_t m = 0;
-        for (int j = 0; j < 8; ++j) { const int c = 8 * blk + j; if (c < C && a.ro.region[c] == g) m |= 1u << j; }
-        regmask[i] = m;
-    }
-    for (int blk = threadIdx.x; blk < nblk; blk += blockDim.x) {
-        uint32_t m = 0;
-        for (int j = 0; j < 8; ++j) { const int c = 8 * blk + j; if (c >= C) m |= 0x100u << j; else if (a.ro.pap[c]) m |= 1u << j; }
-        papmask[blk] = m;
+    for (int i = threadIdx.x; i < CPP; i += blockDim.x) { xs[i] = 0.0f; pwv[i] = 0.0f; }
+    for (int i = threadIdx.x; i < CPP * G; i += blockDim.x) rbv[i] = 0.0f;
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        xs[pc(c)] = a.ro.x32[c];
+        xg[prefix_slot(c, a.e_quad_end)] = make_int2(__float_as_int(a.ro.x32[c]), a.ro.region[c]);
     }
     // ---- per-warp state ----------------------------------------------------------------------------
     unsigned char* base = smem_raw + a.cta_smem + (size_t)wib * a.warp_smem;
     float* bw = nullptr; float* bwp = nullptr;
     if (MODEL) {
-        bw = (float*)base;                      base += sizeof(float) * CP;
+        bw = (float*)base;                      base += sizeof(float) * CPP;
         bwp = (float*)base;                     base += sizeof(float) * 32;
     }
     int32_t* tally = (int32_t*)base;            base += sizeof(int32_t) * Ei;
     int32_t* eff = (int32_t*)base;              base += sizeof(int32_t) * ((a.kmax + 3) & ~3);
     uint16_t* votes = nullptr;
-    if (MODEL) { votes = (uint16_t*)base;       base += sizeof(uint16_t) * Ei; }
+    if (MODEL) { votes = (uint16_t*)base;       base += sizeof(uint16_t) * rows8; }
     uint8_t* mark = (uint8_t*)base;
 
     const int n_qit = a.e_quad_end >> 7;                     // quad iterations (128 electors each)
     const bool top2_ok = C >= 2 && C < 32768;
     const size_t round_pitch = (size_t)a.rows * a.stride;
+    const uint32_t stride4 = 4u * (uint32_t)a.stride;
 
     PrefixCtx kx;
-    kx.xs = xs; kx.reg = reg; kx.regmask = regmask; kx.papmask = papmask; kx.bw = bw; kx.bwp = bwp;
-    kx.C = C; kx.G = G; kx.Ls = Ls; kx.nch = nch; kx.nb = 0.f; kx.bonus = 0.f; kx.st1p = 1.f; kx.pwf = 1.f;
-    kx.step0 = 1;
-    while (kx.step0 * 2 <= nch) kx.step0 *= 2;
+    kx.xs = (uint32_t)__cvta_generic_to_shared(xs); kx.xg = (uint32_t)__cvta_generic_to_shared(xg);
+    kx.pw = (uint32_t)__cvta_generic_to_shared(pwv); kx.rb = (uint32_t)__cvta_generic_to_shared(rbv);
+    kx.bw = MODEL ? (uint32_t)__cvta_generic_to_shared(bw) : 0u; kx.bwp = MODEL ? (uint32_t)__cvta_generic_to_shared(bwp) : 0u;
+    kx.votes = MODEL ? (uint32_t)__cvta_generic_to_shared(votes) : 0u; kx.tally = (uint32_t)__cvta_generic_to_shared(tally);
+    kx.cp4 = 4u * (uint32_t)CPP;
+    kx.C = C; kx.Ls = Ls; kx.nch4 = 4 * nch; kx.nb = 0.f; kx.st1p = 1.f;
+    kx.step0_4 = 4;
+    while (kx.step0_4 * 2 <= 4 * nch) kx.step0_4 *= 2;
+    const uint32_t Ts_a = (uint32_t)__cvta_generic_to_shared(Ts);
 
     // the electors of one round, each lane with its uniform: whole Philox quads per lane, then the tail one per lane
     auto for_each_elector = [&](int r, uint32_t s_lo, uint32_t s_hi, auto&& fn) {
@@ -306,22 +328,26 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(Prefix
             acc_rounds = acc_trials = 0;
             cur_set = set;
             const DevSet* S = &a.b.sets[set];
-            kx.bonus = S->f_bonus; kx.st1p = S->f_st1p; kx.pwf = S->f_pwf; bw_strength = S->f_bandwagon;
+            kx.st1p = S->f_st1p; bw_strength = S->f_bandwagon;
             need = S->need; k = S->k; rr = S->rr;
             has_sticky = MODEL && S->has_sticky; has_bw = MODEL && S->has_bw;
+            const float pwf = S->f_pwf, bonus = S->f_bonus;
             Tset = a.T + (size_t)set * a.set_pitch;
             __syncthreads();                                    // readers of the previous set's tables are done
             if (STAGE) {
                 // asynchronous 16-byte copies global -> shared (LDGSTS), all of a thread's chunks in flight at once
                 const uint32_t n16 = (uint32_t)(a.tab_smem / 16);
-                const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(Ts);
                 const char* gbase = reinterpret_cast<const char*>(Tset);
                 for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + i * 16), "l"(gbase + (size_t)i * 16) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(Ts_a + i * 16), "l"(gbase + (size_t)i * 16) : "memory");
                 asm volatile("cp.async.commit_group;" ::: "memory");
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
             for (int r = threadIdx.x; r < R; r += blockDim.x) nbs[r] = a.nbeta[(size_t)set * R + r];
+            for (int c = threadIdx.x; c < C; c += blockDim.x) {
+                pwv[pc(c)] = a.ro.pap[c] ? pwf : 1.0f;
+                rbv[a.ro.region[c] * CPP + pc(c)] = bonus;
+            }
+            if (STAGE) asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();
         }
         for (int ti = 0; ti < a.tpi; ++ti) {
@@ -336,7 +362,7 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(Prefix
             int ef0 = 0, ef1 = 0, prev_mx = 0;
             if (R == 0) { for (int c = lane; c < C; c += 32) tally[c] = 0; }
             if (MODEL) {
-                for (int c = lane; c < CP; c += 32) bw[c] = 0.0f;
+                for (int c = lane; c < CPP; c += 32) bw[c] = 0.0f;
                 bwp[lane] = 0.0f;
             }
             __syncwarp();
@@ -344,14 +370,16 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(Prefix
             for (int r = 1; r <= R; ++r) {
                 rounds = r;
                 kx.nb = nbs[r - 1];
-                const float* Tr = (STAGE ? Ts : Tset) + (size_t)(r - 1) * round_pitch;
+                const int rt = min(r, a.Rt) - 1;                     // rounds beyond Rt are run-off rounds: no table
+                const uint32_t Tr_a = Ts_a + (uint32_t)((size_t)rt * round_pitch * 4);
+                const float* Tr_g = Tset + (size_t)rt * round_pitch;
                 if (MODEL && has_bw && have_prev && prev_mx > 0) {               // bandwagon, model.py:326-354
                     const float inv = 1.0f / (float)prev_mx;
-                    for (int c = lane; c < C; c += 32) bw[c] = (float)tally[c] * inv * bw_strength;   // tally = previous round's
+                    for (int c = lane; c < C; c += 32) bw[pc(c)] = (float)tally[c] * inv * bw_strength;   // tally = previous round's
                     __syncwarp();
                     float s = 0.f;                                               // bandwagon of chunk `lane`, then prefix over chunks
                     if (lane < nch) {
-                        const float4* b4 = reinterpret_cast<const float4*>(bw + (lane << Ls));
+                        const float4* b4 = reinterpret_cast<const float4*>(bw + lane * Lp);
                         for (int i = 0; i < (1 << (Ls - 2)); ++i) { const float4 v = b4[i]; s += (v.x + v.y) + (v.z + v.w); }
                     }
 #pragma unroll
@@ -370,17 +398,17 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(Prefix
                 if (!have_eff) {
                     // =============== full-field round ==============================================
                     for_each_elector(r, s_lo, s_hi, [&](int e, float u, int slot) {
-                        const int prev = sticky_live ? (int)votes[e] : -1;
-                        const int vote = prefix_draw<LC8, MODEL>(kx, Tr + (size_t)slot * a.stride, e, u, prev);
-                        atomicAdd(&tally[vote], 1);
-                        if (MODEL) votes[e] = (uint16_t)vote;        // read back only by this lane: in place is safe
+                        const int prev = sticky_live ? lds_u16(kx.votes + 2 * slot) : -1;
+                        const int vote = prefix_draw<LC8, MODEL, STAGE>(kx, Tr_a + (uint32_t)slot * stride4, Tr_g + (size_t)slot * a.stride, e, slot, u, prev);
+                        red_inc(kx.tally + 4 * vote);
+                        if (MODEL) sts_u16(kx.votes + 2 * slot, vote);   // read back only by this lane: in place is safe
                     });
                 } else {
                     // =============== run-off round: first k columns (simulate.py:144-154) ===========
                     for_each_elector(r, s_lo, s_hi, [&](int e, float u, int slot) {
-                        const float xe = xs[e];
-                        const int ge = reg[e];
-                        const int prev = sticky_live ? (int)votes[e] : -1;
+                        float xe; int ge;
+                        lds_xg(kx.xg + 8 * slot, xe, ge);
+                        const int prev = sticky_live ? lds_u16(kx.votes + 2 * slot) : -1;
                         int vote;
                         if (fast2) {
                             const float v0 = prefix_full_score<MODEL>(kx, e, 0, xe, ge, prev);
@@ -410,9 +438,9 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(Prefix
                             }
                             if (jsel >= k) jsel = k - 1;
                             vote = eff[jsel];
-                            atomicAdd(&tally[vote], 1);
+                            red_inc(kx.tally + 4 * vote);
                         }
-                        if (MODEL) votes[e] = (uint16_t)vote;
+                        if (MODEL) sts_u16(kx.votes + 2 * slot, vote);
                     });
                 }
                 int n0 = 0, n1 = 0;

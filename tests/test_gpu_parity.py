@@ -54,7 +54,7 @@ def upload(eng, roster):
     eng.upload_roster(roster.ideology, roster.region, roster.papabile)
 
 
-ENGINES = {"dense": 1, "table": 2}
+ENGINES = {"dense": 1, "table": 2, "prefix": 3}
 
 
 CFG2 = dict(initial_beta_weight=1.5, enable_dynamic_beta=True, beta_increment_amount=0.3,
@@ -539,8 +539,9 @@ def test_model_wiring_on_ragged_rosters(eng, E):
     ref = CO.run(roster, [(mp, ep)], O.WIRING_MODEL, n, seed=8, want_tallies=True)
     out = eng.run([to_params(mp, ep)], n, seed=8, wiring=O.WIRING_MODEL, precision=FP64, want_round_tallies=True)
     assert np.array_equal(out.winner, ref["winner"]) and np.array_equal(out.round_tallies, ref["round_tallies"])
-    o32 = eng.run([to_params(mp, ep)], n, seed=8, wiring=O.WIRING_MODEL, precision=FP32, want_round_tallies=True)
-    first = o32.round_tallies[:, 0, :]
-    assert (first.sum(axis=1) == E).all()
-    agree = np.mean((o32.winner == ref["winner"]) & (o32.rounds == ref["rounds"]))
-    assert agree > 0.85, (E, agree)
+    for en in (0, 1, 3):        # auto (= prefix when its preconditions hold), dense, prefix
+        o32 = eng.run([to_params(mp, ep)], n, seed=8, wiring=O.WIRING_MODEL, engine=en, precision=FP32, want_round_tallies=True)
+        first = o32.round_tallies[:, 0, :]
+        assert (first.sum(axis=1) == E).all()
+        agree = np.mean((o32.winner == ref["winner"]) & (o32.rounds == ref["rounds"]))
+        assert agree > 0.85, (E, en, agree)

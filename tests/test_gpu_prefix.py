@@ -1,0 +1,271 @@
+"""GPU parity tests of the PREFIX engine (CSIM_ENGINE_PREFIX, conclave_sim_b200/csrc/prefix.cuh), through the C ABI.
+
+The engine is fp32: the bar is the one the other fp32 engines meet — per-trial agreement with the fp64 oracle
+under the shared Philox stream (a draw flips only when u lands within fp32 rounding of a CDF boundary), the
+chi-square / KS gate against the reference's own sample, and size-independent properties at full size.
+Its tables are built in fp64 and rounded once, so in practice it agrees with the oracle more often than the
+dense fp32 engine does.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import conclave_oracle as O
+from oracle import c_oracle as CO
+import golden_util as G
+from test_gpu_parity import CFG2, EP2, to_params, upload, _chi2_homogeneity
+
+pytestmark = pytest.mark.gpu
+
+DENSE, TABLE, PREFIX = 1, 2, 3
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from conclave_sim_b200 import Engine
+    CO.build()
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def _same(out, ref):
+    return (out.winner == ref["winner"]) & (out.rounds == ref["rounds"]) & (out.final_votes == ref["final_votes"]).all(axis=1)
+
+
+@pytest.mark.parametrize("wiring,n", [(O.WIRING_REF_CLI, 20000), (O.WIRING_MODEL, 6000)])
+def test_prefix_agrees_with_oracle_per_trial(eng, wiring, n):
+    from conclave_sim_b200 import FP32
+    roster = G.real_roster()
+    upload(eng, roster)
+    mp = O.ModelParams(**CFG2)
+    out = eng.run([to_params(mp, EP2)], n, seed=5, wiring=wiring, engine=PREFIX, precision=FP32, want_final_votes=True)
+    ref = CO.run(roster, [(mp, EP2)], wiring, n, seed=5)
+    same = _same(out, ref)
+    assert same.mean() > 0.99, same.mean()
+    assert np.array_equal(out.winner_hist[0, :134], np.bincount(out.winner[out.winner >= 0], minlength=134))
+    assert out.totals[0, 0] == out.rounds.sum() and out.totals[0, 1] == n
+
+
+@pytest.mark.parametrize("kw", [
+    dict(stickiness_factor=0.0), dict(bandwagon_strength=0.0), dict(stickiness_factor=2.5, bandwagon_strength=0.0),
+    dict(regional_affinity_bonus=0.0, papabile_weight_factor=1.0), dict(enable_dynamic_beta=False, initial_beta_weight=0.0),
+    dict(initial_beta_weight=-1.0, enable_dynamic_beta=False), dict(initial_beta_weight=10.0, beta_increment_amount=5.0),
+    dict(bandwagon_strength=5.0, stickiness_factor=0.1),
+], ids=lambda d: ",".join(f"{k}={v}" for k, v in d.items()))
+def test_prefix_model_terms_one_by_one(eng, kw):
+    """Each term of the `model` wiring on and off (and betas outside the factorised-exponential range of dense32)."""
+    from conclave_sim_b200 import FP32
+    roster = G.real_roster()
+    upload(eng, roster)
+    mp = O.ModelParams(**dict(CFG2, **kw))
+    ep = O.EngineParams(max_rounds=12, supermajority_threshold=0.56, runoff_threshold_rounds=6)
+    n = 1500
+    ref = CO.run(roster, [(mp, ep)], O.WIRING_MODEL, n, seed=17)
+    out = eng.run([to_params(mp, ep)], n, seed=17, wiring=O.WIRING_MODEL, engine=PREFIX, precision=FP32, want_final_votes=True)
+    same = _same(out, ref)
+    assert same.mean() > 0.97, (kw, same.mean())
+
+
+def test_prefix_fp32_underflow_matches_dense32(eng):
+    """beta = 40 + 20 per round: exp(-beta |dx|) underflows fp32 in the run-off rounds (both run-off scores flush to zero ->
+    the uniform fallback of simulate.py:151), which fp64 does not do — a property of fp32, not of the engine: the
+    full-field rounds still follow the oracle, and the two fp32 engines agree with each other per trial."""
+    from conclave_sim_b200 import FP32
+    roster = G.real_roster()
+    upload(eng, roster)
+    mp = O.ModelParams(**dict(CFG2, initial_beta_weight=40.0, beta_increment_amount=20.0))
+    ep = O.EngineParams(max_rounds=12, supermajority_threshold=0.56, runoff_threshold_rounds=6)
+    n = 1500
+    for wiring in (O.WIRING_REF_CLI, O.WIRING_MODEL):
+        ref = CO.run(roster, [(mp, ep)], wiring, n, seed=17, want_tallies=True)
+        pf = eng.run([to_params(mp, ep)], n, seed=17, wiring=wiring, engine=PREFIX, precision=FP32, want_round_tallies=True)
+        dn = eng.run([to_params(mp, ep)], n, seed=17, wiring=wiring, engine=DENSE, precision=FP32, want_round_tallies=True)
+        for r in range(6):
+            assert np.mean((pf.round_tallies[:, r, :] == ref["round_tallies"][:, r, :]).all(axis=1)) > 0.99
+        assert np.mean((pf.winner == dn.winner) & (pf.rounds == dn.rounds)) > 0.97
+
+
+@pytest.mark.parametrize("E", [1, 2, 3, 9, 33, 127, 128, 129, 136, 137, 193, 200, 255, 256, 257, 300, 513])
+def test_prefix_ragged_rosters(eng, E):
+    """Roster sizes around every boundary of the lane dealing: 32-lane passes, 128-elector quad groups, a tail of more /
+    fewer than 64 electors (193: the tail is dealt as quads), 256 (chunks of 8 -> 16) and 512 (-> 32)."""
+    from conclave_sim_b200 import FP32
+    roster = O.synthetic_roster(E, seed=100 + E)
+    upload(eng, roster)
+    mp = O.ModelParams(**dict(CFG2, stickiness_factor=1.5, bandwagon_strength=1.0))
+    ep = O.EngineParams(max_rounds=9, supermajority_threshold=0.6, runoff_threshold_rounds=4)
+    n = 128 if E > 256 else 256
+    for wiring in (O.WIRING_REF_CLI, O.WIRING_MODEL):
+        ref = CO.run(roster, [(mp, ep)], wiring, n, seed=8, want_tallies=True)
+        out = eng.run([to_params(mp, ep)], n, seed=8, wiring=wiring, engine=PREFIX, precision=FP32, want_round_tallies=True,
+                      want_final_votes=True)
+        played = out.round_tallies[:, 0, :]
+        assert (played.sum(axis=1) == E).all()                        # every elector votes exactly once per round
+        live = out.round_tallies.reshape(n, -1, E).sum(axis=2)
+        for i in range(0, n, 17):
+            assert (live[i, :out.rounds[i]] == E).all() and (out.round_tallies[i, out.rounds[i]:] == -1).all()
+        agree = np.mean((out.winner == ref["winner"]) & (out.rounds == ref["rounds"]))
+        assert agree > 0.95, (E, wiring, agree)
+
+
+@pytest.mark.parametrize("ep_kw", [
+    dict(max_rounds=0), dict(max_rounds=1), dict(max_rounds=6, runoff_threshold_rounds=0), dict(max_rounds=6, runoff_threshold_rounds=-3),
+    dict(max_rounds=6, runoff_candidate_count=500), dict(max_rounds=6, runoff_candidate_count=1),
+    dict(max_rounds=5, supermajority_threshold=0.0), dict(max_rounds=5, supermajority_threshold=1.5),
+    dict(max_rounds=7, runoff_threshold_rounds=100), dict(max_rounds=9, runoff_threshold_rounds=2, runoff_candidate_count=3),
+    dict(max_rounds=30, runoff_candidate_count=0, supermajority_threshold=0.9),
+], ids=lambda d: ",".join(f"{k}={v}" for k, v in d.items()))
+def test_prefix_edge_engine_parameters(eng, ep_kw):
+    """Degenerate worker arguments the reference accepts (simulate.py:30-41)."""
+    from conclave_sim_b200 import FP32
+    roster = O.synthetic_roster(37, seed=11)
+    upload(eng, roster)
+    mp = O.ModelParams(**CFG2)
+    kw = dict(max_rounds=6, supermajority_threshold=0.56)
+    kw.update(ep_kw)
+    ep = O.EngineParams(**kw)
+    for wiring in (O.WIRING_REF_CLI, O.WIRING_MODEL):
+        ref = CO.run(roster, [(mp, ep)], wiring, 96, seed=2, want_tallies=True)
+        out = eng.run([to_params(mp, ep)], 96, seed=2, wiring=wiring, engine=PREFIX, precision=FP32, want_final_votes=True,
+                      want_round_tallies=True)
+        assert np.array_equal(out.reason, (out.winner >= 0).astype(np.uint8))
+        assert np.mean((out.rounds == ref["rounds"]) & (out.winner == ref["winner"])) > 0.9, wiring
+        if ep.max_rounds == 0:
+            assert (out.final_votes == 0).all() and (out.rounds == 0).all() and (out.winner == -1).all()
+        else:
+            assert np.mean((out.round_tallies == ref["round_tallies"]).all(axis=(1, 2))) > 0.9
+    assert eng.run([to_params(mp, ep)], 0, seed=2, engine=PREFIX).winner.shape == (0,)
+
+
+def test_prefix_heterogeneous_sets_and_wide_sim_ids(eng):
+    """One batch mixing run-off widths / start rounds / thresholds (so CTAs re-stage their tables per set);
+    sim ids beyond 2^32."""
+    from conclave_sim_b200 import FP32
+    roster = G.real_roster()
+    upload(eng, roster)
+    eps = [O.EngineParams(max_rounds=12, supermajority_threshold=0.56, runoff_threshold_rounds=5, runoff_candidate_count=2),
+           O.EngineParams(max_rounds=12, supermajority_threshold=0.50, runoff_threshold_rounds=3, runoff_candidate_count=3),
+           O.EngineParams(max_rounds=12, supermajority_threshold=0.60, runoff_threshold_rounds=4, runoff_candidate_count=0),
+           O.EngineParams(max_rounds=12, supermajority_threshold=0.45, runoff_threshold_rounds=1, runoff_candidate_count=5)]
+    mps = [O.ModelParams(**dict(CFG2, papabile_weight_factor=pw, regional_affinity_bonus=rb, initial_beta_weight=b0))
+           for pw, rb, b0 in ((2.0, 0.1, 1.5), (1.0, 0.0, 0.5), (3.0, 0.3, 2.0), (1.5, 0.05, 1.0))]
+    sets = list(zip(mps, eps))
+    base = 2**40 + 5
+    n = 300
+    for wiring in (O.WIRING_REF_CLI, O.WIRING_MODEL):
+        ref = CO.run(roster, sets, wiring, n, seed=2**63 + 11, sim_id_begin=base)
+        out = eng.run([to_params(*s) for s in sets], n, seed=2**63 + 11, sim_id_begin=base, wiring=wiring, engine=PREFIX,
+                      precision=FP32, want_final_votes=True)
+        same = _same(out, ref)
+        assert same.mean() > 0.98, (wiring, same.mean())
+        w = out.winner.reshape(4, n); r = out.rounds.reshape(4, n)
+        for s in range(4):
+            assert out.winner_hist[s, :134].sum() == (w[s] >= 0).sum() and out.winner_hist[s, 134] == (w[s] < 0).sum()
+            assert np.array_equal(out.rounds_hist[s], np.bincount(r[s][w[s] >= 0], minlength=13))
+            assert out.totals[s, 0] == r[s].sum() and out.totals[s, 1] == n
+
+
+def test_prefix_sweep_many_sets_and_sharding(eng):
+    """A 96-set sweep (BASELINE cfg-4 in miniature): every set's trials are the ones a single-set run gives, and
+    a shard of the sim-id range reproduces the whole (what multi-GPU sharding relies on)."""
+    import itertools
+    from conclave_sim_b200 import FP32
+    roster = O.synthetic_roster(135)
+    upload(eng, roster)
+    grid = list(itertools.product([0.5, 1.0, 1.5, 2.0], [0.0, 0.3], [1.0, 1.5, 3.0], [0.5, 0.56, 0.6, 2 / 3]))
+    sets = [(O.ModelParams(**dict(CFG2, initial_beta_weight=b0, beta_increment_amount=db, papabile_weight_factor=pw)),
+             O.EngineParams(max_rounds=20, supermajority_threshold=thr)) for b0, db, pw, thr in grid]
+    ps = [to_params(*s) for s in sets]
+    n = 700
+    for wiring in (O.WIRING_REF_CLI, O.WIRING_MODEL):
+        full = eng.run(ps, n, seed=4, wiring=wiring, engine=PREFIX, precision=FP32)
+        w = full.winner.reshape(len(ps), n); r = full.rounds.reshape(len(ps), n)
+        for s in (0, 37, 95):
+            solo = eng.run([ps[s]], n, seed=4, wiring=wiring, engine=PREFIX, precision=FP32)
+            assert np.array_equal(solo.winner, w[s]) and np.array_equal(solo.rounds, r[s])
+            assert np.array_equal(solo.winner_hist[0], full.winner_hist[s]) and np.array_equal(solo.totals[0], full.totals[s])
+            part = eng.run([ps[s]], 250, seed=4, sim_id_begin=300, wiring=wiring, engine=PREFIX, precision=FP32)
+            assert np.array_equal(part.winner, w[s][300:550]) and np.array_equal(part.rounds, r[s][300:550])
+        ref = CO.run(roster, [sets[37]], wiring, n, seed=4)
+        assert np.mean((w[37] == ref["winner"]) & (r[37] == ref["rounds"])) > 0.98
+
+
+def test_prefix_tables_in_global_memory(eng):
+    """Tables read through L2 instead of shared memory: forced on a small roster, natural on cfg-5's 1024 x 1024."""
+    from conclave_sim_b200 import FP32
+    roster = G.real_roster()
+    upload(eng, roster)
+    mp = O.ModelParams(**CFG2)
+    p = [to_params(mp, EP2)]
+    for wiring in (O.WIRING_REF_CLI, O.WIRING_MODEL):
+        staged = eng.run(p, 3000, seed=9, wiring=wiring, engine=PREFIX, precision=FP32, want_final_votes=True)
+        os.environ["CSIM_PREFIX_NOSTAGE"] = "1"
+        try:
+            glob = eng.run(p, 3000, seed=9, wiring=wiring, engine=PREFIX, precision=FP32, want_final_votes=True)
+        finally:
+            del os.environ["CSIM_PREFIX_NOSTAGE"]
+        assert np.array_equal(staged.winner, glob.winner) and np.array_equal(staged.final_votes, glob.final_votes)
+    roster = O.synthetic_roster(1024)
+    upload(eng, roster)
+    ep = O.EngineParams(max_rounds=50, supermajority_threshold=0.56)
+    p = [to_params(mp, ep)]
+    for wiring in (O.WIRING_REF_CLI, O.WIRING_MODEL):
+        n = 4000
+        out = eng.run(p, n, seed=5, wiring=wiring, engine=PREFIX, precision=FP32, want_final_votes=True)
+        d = eng.run(p, n, seed=5, wiring=wiring, engine=DENSE, precision=FP32, want_final_votes=True)
+        assert (out.final_votes.sum(axis=1) == 1024).all()
+        assert np.mean((out.winner == d.winner) & (out.rounds == d.rounds)) > 0.97
+        ref = CO.run(roster, [(mp, ep)], wiring, 48, seed=5)
+        assert np.mean((out.winner[:48] == ref["winner"]) & (out.rounds[:48] == ref["rounds"])) > 0.9
+
+
+def test_prefix_distribution_matches_reference_sample(eng):
+    """north_star's statistical gate (chi-square winners / rounds, KS rounds, p > 0.01) against the reference's own
+    20 000-trial CPU sample, 1e6 GPU trials."""
+    from scipy import stats
+    from conclave_sim_b200 import FP32
+    with open(os.path.join(G.GOLD, "dist_cfg2.json")) as f:
+        ref = json.load(f)
+    roster = G.real_roster()
+    upload(eng, roster)
+    n = 1_000_000
+    out = eng.run([to_params(O.ModelParams(**CFG2), EP2)], n, seed=987654321, precision=FP32, engine=PREFIX, want_reason=False)
+    gw = np.concatenate([out.winner_hist[0, :134], [out.winner_hist[0, 134]]])
+    rw = np.concatenate([ref["winner_hist"], [ref["no_winner"]]])
+    p_w = _chi2_homogeneity(gw, rw)
+    gr = np.concatenate([out.rounds_hist[0], [out.winner_hist[0, 134]]])
+    rr = np.concatenate([ref["rounds_hist_success"], [ref["no_winner"]]])
+    p_r = _chi2_homogeneity(gr, rr)
+    p_ks = stats.ks_2samp(np.repeat(np.arange(21), out.rounds_hist[0]), np.repeat(np.arange(21), ref["rounds_hist_success"])).pvalue
+    print(f"[prefix] chi2 winners p={p_w:.4f}  chi2 rounds p={p_r:.4f}  KS rounds p={p_ks:.4f}")
+    assert p_w > 0.01 and p_r > 0.01 and p_ks > 0.01
+
+
+def test_prefix_full_size_properties_model_wiring(eng):
+    """1.25 M trials (BASELINE cfg-3's per-GPU share) under the `model` wiring: conservation, independence from how the
+    sim-id range is cut, and per-trial agreement with the dense fp32 kernel (a different algorithm on the same stream)."""
+    from conclave_sim_b200 import FP32
+    roster = O.synthetic_roster(135)
+    upload(eng, roster)
+    p = [to_params(O.ModelParams(**CFG2), EP2)]
+    n = 1_250_000
+    for wiring in (O.WIRING_MODEL, O.WIRING_REF_CLI):
+        pf = eng.run(p, n, seed=31337, wiring=wiring, engine=PREFIX, precision=FP32)
+        dn = eng.run(p, n, seed=31337, wiring=wiring, engine=DENSE, precision=FP32)
+        w, rd = pf.winner, pf.rounds
+        assert pf.winner_hist.sum() == n and pf.totals[0, 1] == n and pf.totals[0, 0] == rd.astype(np.int64).sum()
+        assert np.array_equal(pf.winner_hist[0], np.bincount(np.where(w >= 0, w, 135), minlength=136))
+        assert np.array_equal(pf.rounds_hist[0], np.bincount(rd[w >= 0], minlength=21))
+        assert ((w >= 0) | (rd == 20)).all() and (rd >= 1).all() and (rd <= 20).all()
+        third = n // 3
+        a = eng.run(p, third, seed=31337, sim_id_begin=0, wiring=wiring, engine=PREFIX, precision=FP32)
+        b = eng.run(p, n - third, seed=31337, sim_id_begin=third, wiring=wiring, engine=PREFIX, precision=FP32)
+        assert np.array_equal(np.concatenate([a.winner, b.winner]), w) and np.array_equal(np.concatenate([a.rounds, b.rounds]), rd)
+        assert np.array_equal(a.winner_hist + b.winner_hist, pf.winner_hist)
+        same = np.mean((pf.winner == dn.winner) & (pf.rounds == dn.rounds))
+        print(f"prefix==dense on {same:.5f} of {n} trials (wiring {wiring})")
+        assert same > 0.995
+        assert _chi2_homogeneity(pf.winner_hist[0], dn.winner_hist[0]) > 1e-3
