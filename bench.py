@@ -175,7 +175,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from conclave_sim_b200 import Engine, make_params, FP32, WIRING_REF_CLI, ENGINE_DENSE, ENGINE_TABLE
+    from conclave_sim_b200 import Engine, make_params, FP32, WIRING_REF_CLI, WIRING_MODEL, ENGINE_DENSE, ENGINE_TABLE, ENGINE_PREFIX
     from conclave_sim_b200.dist import DeviceBatch, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -205,9 +205,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(i: int, reduce: bool = True, engine: int = ENGINE_DENSE):
+    def step(i: int, reduce: bool = True, engine: int = ENGINE_DENSE, wiring: int = WIRING_REF_CLI):
         begin, _ = shard_range(n_global, rank, world)
-        batch.run([params], sim_id_begin=i * n_global + begin, seed=SEED, wiring=WIRING_REF_CLI,
+        batch.run([params], sim_id_begin=i * n_global + begin, seed=SEED, wiring=wiring,
                   engine=engine, precision=FP32, reduce=reduce)
 
     for i in range(args.warmup):
@@ -274,30 +274,44 @@ def main():
                 "factorised_pair_body_peak_pairs_per_s": None if peak_fact is None else peak_fact / 2.5 * 1e9,
                 "hbm_writeback_gbs": out_bytes / kern_s * 1e-9}
 
-    # ---- the TABLE engine (trial-invariant per-round CDF tables; what ENGINE_AUTO picks for ref_cli), reported
-    #      SEPARATELY from the dense kernel's value / roofline (never mixed)
-    for i in range(2):
-        step(500 + i, engine=ENGINE_TABLE)
-    barrier()
-    tev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    t_rounds = 0
-    for i in range(args.steps):
-        flush.zero_()
-        tev[i][0].record()
-        step(502 + i, engine=ENGINE_TABLE)
-        tev[i][1].record()
-        tev[i][1].synchronize()
-        t_rounds += int(batch.totals[0].item())           # already summed over ranks by the step's all-reduce
-    barrier()
-    tt = torch.tensor([sum(a.elapsed_time(b) for a, b in tev)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    table_ms, table_rounds = tt[0].item(), float(t_rounds)
-    table_engine = {"value": table_rounds * E / (table_ms * 1e-3), "unit": "elector-rounds/s",
-                    "conclaves_per_sec": n_global * args.steps / (table_ms * 1e-3), "ms_per_step": table_ms / args.steps,
-                    "kernel": "k_trials_table<float> (+ k_base_scores64, k_cdf_tables64, k_f64_to_f32 per step)",
-                    "note": "ref_cli wiring only: the probability matrix is trial-invariant there, so CDF rows are built once per "
-                            "step and a draw is a binary search; NOT comparable with the dense roofline"}
+    # ---- the other engines on the same workload, reported SEPARATELY from the dense kernel's value / roofline
+    #      (never mixed): same steps, same L2 flush, CUDA events, max over ranks
+    def timed_engine(engine: int, wiring: int, base: int):
+        for i in range(2):
+            step(base + i, engine=engine, wiring=wiring)
+        barrier()
+        tev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        t_rounds, k_ms = 0, 0.0
+        for i in range(args.steps):
+            flush.zero_()
+            tev[i][0].record()
+            step(base + 2 + i, engine=engine, wiring=wiring)
+            tev[i][1].record()
+            tev[i][1].synchronize()
+            k_ms += eng.stats()[1]
+            t_rounds += int(batch.totals[0].item())       # already summed over ranks by the step's all-reduce
+        barrier()
+        tt = torch.tensor([sum(a.elapsed_time(b) for a, b in tev), k_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = tt[0].item()
+        return {"value": float(t_rounds) * E / (ms * 1e-3), "unit": "elector-rounds/s",
+                "conclaves_per_sec": n_global * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps,
+                "trial_kernel_ms_per_step": tt[1].item() / args.steps, "mean_rounds": float(t_rounds) / (n_global * args.steps)}
+
+    table_engine = timed_engine(ENGINE_TABLE, WIRING_REF_CLI, 500)
+    table_engine.update(kernel="k_trials_table<float> (+ k_base_scores64, k_cdf_tables64, k_f64_to_f32 per step)",
+                        note="ref_cli wiring only: the probability matrix is trial-invariant there, so CDF rows are built once per "
+                             "step and a draw is a binary search; NOT comparable with the dense roofline")
+    prefix_engine = {"ref_cli": timed_engine(ENGINE_PREFIX, WIRING_REF_CLI, 600),
+                     "model": timed_engine(ENGINE_PREFIX, WIRING_MODEL, 700),
+                     "kernel": "k_trials_prefix<LC8, MODEL, STAGE> (+ k_prefix_tables32 per step)",
+                     "note": "trial-invariant chunk-prefix tables + per-trial bandwagon / stickiness corrections: a draw is a binary "
+                             "search over 17 chunk prefixes and a re-scan of one chunk of 8 candidates; both wirings; what "
+                             "ENGINE_AUTO picks for the `model` wiring.  NOT comparable with the dense roofline"}
+    model_wiring_dense = timed_engine(ENGINE_DENSE, WIRING_MODEL, 800)
+    model_wiring_dense.update(kernel="k_trials_dense32<LC=8,MODEL=true,FACT=true>",
+                              note="`model` wiring (bandwagon + stickiness live, SURVEY 8f.1) on the dense kernel, for comparison")
 
     # ---- e2e: the host-buffer public API (roster + params uploaded, results copied back, every step)
     e2e_steps = max(2, min(args.steps, 3))
@@ -374,6 +388,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": "elector-rounds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "api": "conclave_sim_b200.Engine.run (host buffers; results land in page-locked arrays) -> csim_run"},
         "table_engine": table_engine,
+        "prefix_engine": prefix_engine,
+        "model_wiring_dense": model_wiring_dense,
         "gpu_launches": int(launches1 - launches0),
         "clocks": clocks,
         "mean_rounds": all_rounds / (n_global * args.steps),

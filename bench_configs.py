@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--full", action="store_true")
     a = ap.parse_args()
-    from conclave_sim_b200 import Engine, make_params, FP32, FP64, WIRING_REF_CLI, WIRING_MODEL, ENGINE_DENSE, ENGINE_TABLE
+    from conclave_sim_b200 import Engine, make_params, FP32, FP64, WIRING_REF_CLI, WIRING_MODEL, ENGINE_DENSE, ENGINE_TABLE, ENGINE_PREFIX
     eng = Engine(0)
     out = []
 
@@ -43,7 +43,7 @@ def main():
         trials = n * len(sets)
         rec = dict(config=name, E=E, param_sets=len(sets), trials=trials,
                    wiring="ref_cli" if wiring == WIRING_REF_CLI else "model",
-                   engine={ENGINE_DENSE: "dense", ENGINE_TABLE: "table"}[engine], precision="fp32" if precision == FP32 else "fp64",
+                   engine={ENGINE_DENSE: "dense", ENGINE_TABLE: "table", ENGINE_PREFIX: "prefix"}[engine], precision="fp32" if precision == FP32 else "fp64",
                    wall_s=best, kernel_ms=r.kernel_ms, conclaves_per_s=trials / best, elector_rounds_per_s=r.elector_rounds / best,
                    success_rate=float((r.winner >= 0).mean()), mean_rounds=float(r.rounds.mean()))
         out.append(rec)
@@ -53,23 +53,26 @@ def main():
                             stickiness_factor=0.5, regional_affinity_bonus=0.1, papabile_weight_factor=1.5),
                        max_rounds=20, supermajority_threshold=2 / 3)
     cfg2 = make_params(CFG2, max_rounds=20, supermajority_threshold=0.56)
-    for eng_id in (ENGINE_DENSE, ENGINE_TABLE):
+    for eng_id in (ENGINE_DENSE, ENGINE_TABLE, ENGINE_PREFIX):
         run("cfg1 defaults x100", 134, [cfg1], 100, WIRING_REF_CLI, eng_id, FP32)
         run("cfg2 README x1000", 134, [cfg2], 1000, WIRING_REF_CLI, eng_id, FP32)
         run("cfg3 README x1.25M (1/8 of 10M)", 134, [cfg2], 125_000 if a.quick else 1_250_000, WIRING_REF_CLI, eng_id, FP32)
     run("cfg2 README x1000 (fp64 exact)", 134, [cfg2], 1000, WIRING_REF_CLI, ENGINE_TABLE, FP64)
-    run("cfg3 model wiring x1.25M", 134, [cfg2], 125_000 if a.quick else 1_250_000, WIRING_MODEL, ENGINE_DENSE, FP32)
+    for eng_id in (ENGINE_DENSE, ENGINE_PREFIX):
+        run("cfg3 model wiring x1.25M", 134, [cfg2], 125_000 if a.quick else 1_250_000, WIRING_MODEL, eng_id, FP32)
     # cfg-4: SURVEY 8d grid
     grid = list(itertools.product([0.5, 1.0, 1.5, 2.0], [0.0, 0.1, 0.3, 0.5], [1.0, 1.5, 2.0, 3.0], [0.5, 0.56, 0.6, 2 / 3]))
     sets = [make_params(dict(CFG2, initial_beta_weight=b0, beta_increment_amount=db, papabile_weight_factor=pw),
                         max_rounds=20, supermajority_threshold=thr) for b0, db, pw, thr in grid]
-    for eng_id in (ENGINE_DENSE, ENGINE_TABLE):
+    for eng_id in (ENGINE_DENSE, ENGINE_TABLE, ENGINE_PREFIX):
         run("cfg4 sweep 256 sets x 100k", 134, sets, 10_000 if a.quick else 100_000, WIRING_REF_CLI, eng_id, FP32, reps=1)
     # cfg-5
     cfg5 = make_params(CFG2, max_rounds=50, supermajority_threshold=0.56)
     n5 = 10_000 if a.quick else (1_000_000 if a.full else 100_000)
-    for eng_id in (ENGINE_DENSE, ENGINE_TABLE):
+    run("cfg4 sweep 256 sets x 100k, model wiring", 134, sets, 10_000 if a.quick else 100_000, WIRING_MODEL, ENGINE_PREFIX, FP32, reps=1)
+    for eng_id in (ENGINE_DENSE, ENGINE_TABLE, ENGINE_PREFIX):
         run(f"cfg5 1024x1024 R=50 x{n5}", 1024, [cfg5], n5, WIRING_REF_CLI, eng_id, FP32, reps=1)
+    run(f"cfg5 1024x1024 R=50 x{n5}, model wiring", 1024, [cfg5], n5, WIRING_MODEL, ENGINE_PREFIX, FP32, reps=1)
 
 
 if __name__ == "__main__":

@@ -576,6 +576,7 @@ static csim_status launch_prefix(csim_ctx* c, const csim_run_args* ra, const std
     a.cta_smem = a.tab_smem + prefix_roster_smem(CPP, c->G, R, a.rows);
     a.warp_smem = prefix_warp_smem(E, CPP, kmax, a.rows, model);
     a.warps_per_cta = wpc;
+    prefix_layout(a, model);
     const size_t tbytes = a.set_pitch * 4 * (size_t)b.n_sets;
     if (tbytes > ((size_t)64 << 30)) return fail(CSIM_ERR_UNSUPPORTED, "prefix tables need %zu bytes", tbytes);
     CU_TRY(c->ptab.reserve(tbytes));
@@ -667,8 +668,8 @@ extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
     //   model wiring, fp32: the PREFIX engine (trial-invariant chunk-prefix tables + per-trial corrections) whenever its
     //     preconditions hold, else DENSE;
     //   ref_cli wiring: the TABLE engine when the batch fills the GPU with its 512-trial super-batches (or fp64); rosters
-    //     whose E x C rows do not fit in shared memory (E > 256) go to PREFIX; small fp32 batches (BASELINE configs 1-2:
-    //     100 / 1000 trials) finish sooner on the dense kernel's one-warp-per-trial grid.
+    //     whose E x C rows do not fit in shared memory (E > 256) go to PREFIX, and so do small fp32 batches (BASELINE
+    //     configs 1-2: 100 / 1000 trials finish in 0.06-0.08 ms on its one-warp-per-trial grid; DENSE if PREFIX cannot run).
     int engine = ra->engine;
     if (engine == CSIM_ENGINE_AUTO) {
         const bool pfx_ok = ra->precision == CSIM_FP32 && prefix_supported(c, ra, hs, R);
@@ -678,7 +679,7 @@ extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
             const uint64_t n_sb = ((ra->n_sims + (uint64_t)CSIM_TABLE_WPC * 32 - 1) / ((uint64_t)CSIM_TABLE_WPC * 32)) * ra->n_param_sets;
             if (ra->precision == CSIM_FP64) engine = CSIM_ENGINE_TABLE;
             else if (E > 256) engine = pfx_ok ? CSIM_ENGINE_PREFIX : CSIM_ENGINE_TABLE;
-            else engine = n_sb >= (uint64_t)c->prop.multiProcessorCount / 2 ? CSIM_ENGINE_TABLE : CSIM_ENGINE_DENSE;
+            else engine = n_sb >= (uint64_t)c->prop.multiProcessorCount / 2 ? CSIM_ENGINE_TABLE : (pfx_ok ? CSIM_ENGINE_PREFIX : CSIM_ENGINE_DENSE);
         }
     }
     csim_status s = engine == CSIM_ENGINE_PREFIX ? launch_prefix(c, ra, hs, b, out, st)

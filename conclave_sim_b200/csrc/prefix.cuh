@@ -37,6 +37,8 @@
 #define CSIM_PREFIX_THREADS 768        // 24 warps per CTA, 1 CTA per SM (<= 85 registers)
 #endif
 
+__host__ __device__ inline int prefix_cpp(int nch, int Ls);
+
 struct PrefixArgs {
     RosterDev ro;
     BatchDev b;
@@ -56,7 +58,35 @@ struct PrefixArgs {
     size_t tab_smem;        // bytes of the staged tables (0 when STAGE = false)
     size_t cta_smem;        // staged tables + roster tables
     size_t warp_smem;       // per-warp state
+    // shared-memory byte offsets, computed on the host (prefix_layout) so that the kernel reads them straight from the
+    // constant bank instead of keeping a dozen addresses in registers:
+    uint32_t o_xs, o_pw, o_rb, o_xg, o_nbs;            // from the start of dynamic shared memory
+    uint32_t w_bwp, w_tally, w_eff, w_votes, w_mark;   // from the warp's block (bandwagon f32[CPP] sits at 0)
+    uint32_t cp4;                                      // 4 * CPP: byte pitch of the per-candidate arrays
+    int nch4, step0_4;                                 // 4 nch; 4 x (largest power of two <= nch)
 };
+
+// fills the offsets above from (E, G, R, Ls, nch, rows, kmax, tab_smem); returns nothing the caller has to size by hand
+__host__ inline void prefix_layout(PrefixArgs& a, bool model) {
+    const uint32_t CPP = (uint32_t)prefix_cpp(a.nch, a.Ls), G = (uint32_t)a.ro.G;
+    const uint32_t Ei = ((uint32_t)a.ro.E + 7u) & ~7u, rows8 = ((uint32_t)a.rows + 7u) & ~7u;
+    a.cp4 = 4u * CPP;
+    uint32_t o = (uint32_t)a.tab_smem;
+    a.o_xs = o; o += a.cp4;
+    a.o_pw = o; o += a.cp4;
+    a.o_rb = o; o += a.cp4 * G;
+    a.o_xg = o; o += 8u * rows8;
+    a.o_nbs = o;
+    uint32_t w = 0;
+    if (model) { w += a.cp4; a.w_bwp = w; w += 128u; } else a.w_bwp = 0;
+    a.w_tally = w; w += 4u * Ei;
+    a.w_eff = w; w += 4u * (((uint32_t)a.kmax + 3u) & ~3u);
+    a.w_votes = w; if (model) w += 2u * rows8;
+    a.w_mark = w;
+    a.nch4 = 4 * a.nch;
+    a.step0_4 = 4;
+    while (a.step0_4 * 2 <= a.nch4) a.step0_4 *= 2;
+}
 
 // Row of elector e inside one round's table: quad-dealt electors (e = 4 (lane + 32 qi) + i) sit at
 // 128 qi + 32 i + lane, so one pass of the warp (fixed i) touches 32 consecutive rows.
@@ -125,22 +155,30 @@ __device__ __forceinline__ void lds_xg(uint32_t a, float& x, int& g) { asm volat
 __device__ __forceinline__ void sts_u16(uint32_t a, int v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
 __device__ __forceinline__ void red_inc(uint32_t a) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory"); }
 
-struct PrefixCtx {              // per-warp / per-round constants of a draw (shared-window byte addresses)
-    uint32_t xs, pw, rb, xg;    // CTA: ideology f32[CPP], papabile weight f32[CPP] (0 beyond C), bonus table f32[G][CPP] (padded
-                                //      candidate order, prefix_cpp);  {ideology, region} of the electors in slot order, 8 B each
-    uint32_t bw, bwp, votes, tally;   // warp: bandwagon f32[CPP], its chunk prefix f32[32], last votes u16[rows] (slot order), tally i32[E]
-    uint32_t cp4;               // CPP * 4 (row pitch of rb)
+// Shared arrays of a draw, as window addresses = one of two bases + an offset from the constant bank:
+//   CTA  (sb): xs f32[CPP] ideology, pw f32[CPP] papabile weight (0 = padding), rb f32[G][CPP] regional bonus of region g
+//              (all in padded candidate order, prefix_cpp), xg {ideology, region} of the electors in slot order (8 B each)
+//   warp (wb): bw f32[CPP] bandwagon, bwp f32[32] its prefix over chunks, tally i32[E], votes u16[rows] (slot order)
+struct PrefixCtx {
+    uint32_t sb, wb;
     float nb, st1p;
-    int C, Ls, nch4, step0_4;   // nch4 = 4 nch, step0_4 = 4 x (largest power of two <= nch)
 };
+#define PFX_XS(k, a)    ((k).sb + (a).o_xs)
+#define PFX_PW(k, a)    ((k).sb + (a).o_pw)
+#define PFX_RB(k, a)    ((k).sb + (a).o_rb)
+#define PFX_XG(k, a)    ((k).sb + (a).o_xg)
+#define PFX_BW(k, a)    ((k).wb)
+#define PFX_BWP(k, a)   ((k).wb + (a).w_bwp)
+#define PFX_TALLY(k, a) ((k).wb + (a).w_tally)
+#define PFX_VOTES(k, a) ((k).wb + (a).w_votes)
 
 // every term of one score, inline (run-off rounds; c is warp-uniform)
 template <bool MODEL>
-__device__ __forceinline__ float prefix_full_score(const PrefixCtx& k, int e, int c, float xe, int ge, int prev) {
-    const uint32_t o = 4u * (uint32_t)(c + ((c >> k.Ls) << 2));
-    float v = fmaf(ex2_approx(fabsf(xe - lds_f(k.xs + o)) * k.nb), lds_f(k.pw + o), lds_f(k.rb + ge * k.cp4 + o));
+__device__ __forceinline__ float prefix_full_score(const PrefixCtx& k, const PrefixArgs& a, int e, int c, float xe, int ge, int prev) {
+    const uint32_t o = 4u * (uint32_t)(c + ((c >> a.Ls) << 2));
+    float v = fmaf(ex2_approx(fabsf(xe - lds_f(PFX_XS(k, a) + o)) * k.nb), lds_f(PFX_PW(k, a) + o), lds_f(PFX_RB(k, a) + ge * a.cp4 + o));
     if (MODEL) {
-        v += lds_f(k.bw + o);
+        v += lds_f(PFX_BW(k, a) + o);
         if (c == prev) v *= k.st1p;
     }
     return c == e ? 0.0f : v;
@@ -149,29 +187,30 @@ __device__ __forceinline__ float prefix_full_score(const PrefixCtx& k, int e, in
 // One vote of a full-field round.  STAGE: trow = shared address of this elector's row of the round's chunk-prefix
 // table; else Tg = the row in global memory.
 template <bool LC8, bool MODEL, bool STAGE>
-__device__ __forceinline__ int prefix_draw(const PrefixCtx& k, uint32_t trow, const float* __restrict__ Tg, int e, int slot, float u, int prev) {
-    const int Ls = LC8 ? 3 : k.Ls, nch4 = k.nch4;
+__device__ __forceinline__ int prefix_draw(const PrefixCtx& k, const PrefixArgs& a, uint32_t trow, const float* __restrict__ Tg, int e, int slot,
+                                           float u, int prev) {
+    const int Ls = LC8 ? 3 : a.Ls, nch4 = a.nch4, C = a.ro.E;
     float xe; int ge;
-    lds_xg(k.xg + 8 * slot, xe, ge);
-    const uint32_t rbrow = k.rb + ge * k.cp4;
+    lds_xg(PFX_XG(k, a) + 8 * slot, xe, ge);
+    const uint32_t rbrow = PFX_RB(k, a) + ge * a.cp4;
     const float nb = k.nb;
     float selfbw = 0.f, sadd = 0.f;
     const int je4 = (e >> Ls) << 2;
     int jp4 = 0x7fffffff;
     if (MODEL) {
-        selfbw = lds_f(k.bw + 4 * (e + (je4 & ~3)));        // bwp counts e's own bandwagon term; its score is 0 (model.py:418-424)
+        selfbw = lds_f(PFX_BW(k, a) + 4 * (e + je4));        // bwp counts e's own bandwagon term; its score is 0 (model.py:418-424)
         if (prev >= 0 && prev != e) {                       // stickiness, model.py:357-367
             jp4 = (prev >> Ls) << 2;
             const uint32_t o = 4u * (uint32_t)(prev + jp4);
-            float b = fmaf(ex2_approx(fabsf(xe - lds_f(k.xs + o)) * nb), lds_f(k.pw + o), lds_f(rbrow + o));
-            b += lds_f(k.bw + o);
+            float b = fmaf(ex2_approx(fabsf(xe - lds_f(PFX_XS(k, a) + o)) * nb), lds_f(PFX_PW(k, a) + o), lds_f(rbrow + o));
+            b += lds_f(PFX_BW(k, a) + o);
             sadd = b * (k.st1p - 1.0f);
         }
     }
     auto F = [&](int j4) -> float {                         // prefix of the row over chunks 0..j  (j4 = 4 j)
         float v = STAGE ? lds_f(trow + j4) : __ldg(reinterpret_cast<const float*>(reinterpret_cast<const char*>(Tg) + j4));
         if (MODEL) {
-            v += lds_f(k.bwp + j4);
+            v += lds_f(PFX_BWP(k, a) + j4);
             v = (j4 >= je4) ? v - selfbw : v;
             v = (j4 >= jp4) ? v + sadd : v;
         }
@@ -179,13 +218,13 @@ __device__ __forceinline__ int prefix_draw(const PrefixCtx& k, uint32_t trow, co
     };
     const float S = F(nch4 - 4);
     if (!(S > 0.0f)) {            // all scores vanished: the reference makes the row uniform INCLUDING self (model.py:447-449)
-        const int j = (int)(u * (float)k.C);
-        return j < k.C ? j : k.C - 1;
+        const int j = (int)(u * (float)C);
+        return j < C ? j : C - 1;
     }
     const float tgt = u * S;
     int pos4 = 0;                 // 4 x number of chunks whose prefix is <= tgt
     float cum = 0.0f;             // prefix below the chunk the target falls into
-    for (int st = k.step0_4; st >= 4; st >>= 1) {
+    for (int st = a.step0_4; st >= 4; st >>= 1) {
         const int np4 = min(pos4 + st, nch4);               // probing the last entry twice is harmless
         const float f = F(np4 - 4);
         const bool le = f <= tgt;
@@ -202,11 +241,11 @@ __device__ __forceinline__ int prefix_draw(const PrefixCtx& k, uint32_t trow, co
     for (int bi = 0; bi < nb8; ++bi) {                      // blocks of 8 candidates of the chunk, in roster order
         const int cb = c0 + 8 * bi;
         const uint32_t o = 4u * (uint32_t)cb + 4u * (uint32_t)pos4;     // padded order: 4 extra floats per chunk before this one
-        const float4 xa = lds_f4(k.xs + o), xb = lds_f4(k.xs + o + 16);
-        const float4 pa = lds_f4(k.pw + o), pb = lds_f4(k.pw + o + 16);          // 0 beyond C: padding scores nothing
+        const float4 xa = lds_f4(PFX_XS(k, a) + o), xb = lds_f4(PFX_XS(k, a) + o + 16);
+        const float4 pa = lds_f4(PFX_PW(k, a) + o), pb = lds_f4(PFX_PW(k, a) + o + 16);     // 0 beyond C: padding scores nothing
         const float4 ra = lds_f4(rbrow + o), rb = lds_f4(rbrow + o + 16);        // regional bonus of e's region
         float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
-        if (MODEL) { ba = lds_f4(k.bw + o); bb = lds_f4(k.bw + o + 16); }
+        if (MODEL) { ba = lds_f4(PFX_BW(k, a) + o); bb = lds_f4(PFX_BW(k, a) + o + 16); }
         const int is = e - cb;                               // position of e itself / of prev inside this block (else outside 0..7)
         const int ip = MODEL ? prev - cb : -1;
 #define CSIM_PRESCAN(i, xv, pv, rv, bv)                                                  \
@@ -225,29 +264,27 @@ __device__ __forceinline__ int prefix_draw(const PrefixCtx& k, uint32_t trow, co
         if (cnt < 8 * (bi + 1)) break;                       // the crossing is inside this block
     }
     int vote = c0 + cnt;                                     // == first c with cum > tgt
-    const int maxc = min(c0 + (1 << Ls) - 1, k.C - 1);
+    const int maxc = min(c0 + (1 << Ls) - 1, C - 1);
     vote = vote > maxc ? maxc : vote;                        // rounding at the chunk's upper edge
-    if (vote == e) vote = e > 0 ? e - 1 : (k.C > 1 ? 1 : 0);
+    if (vote == e) vote = e > 0 ? e - 1 : (C > 1 ? 1 : 0);
     return vote;
 }
 
 template <bool LC8, bool MODEL, bool STAGE>
-__global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(PrefixArgs a) {
+__global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(const __grid_constant__ PrefixArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int E = a.ro.E, C = E, R = a.b.R, G = a.ro.G;
     const int Ls = LC8 ? 3 : a.Ls, nch = a.nch, Lp = (1 << Ls) + 4, CPP = nch * Lp;
-    const int Ei = (E + 7) & ~7, rows8 = (a.rows + 7) & ~7;
     auto pc = [&](int c) { return c + ((c >> Ls) << 2); };   // index of candidate c in the padded arrays
     const int wpc = a.warps_per_cta;
-    // ---- CTA-shared: staged tables of the current set, then roster tables --------------------------
+    // ---- CTA-shared: staged tables of the current set, then roster tables (offsets: prefix_layout) ---------
     float* Ts = (float*)smem_raw;
-    unsigned char* p = smem_raw + a.tab_smem;
-    float* xs = (float*)p;                      p += sizeof(float) * CPP;
-    float* pwv = (float*)p;                     p += sizeof(float) * CPP;           // papabile weight of the current set (0 = padding)
-    float* rbv = (float*)p;                     p += sizeof(float) * CPP * G;       // [g][c]: bonus if region_c == g else 0
-    int2* xg = (int2*)p;                        p += sizeof(int2) * rows8;          // {ideology bits, region} by elector slot
-    float* nbs = (float*)p;                                                         // [R] -beta_r log2 e of the current set
+    float* xs = (float*)(smem_raw + a.o_xs);
+    float* pwv = (float*)(smem_raw + a.o_pw);                                       // papabile weight of the current set (0 = padding)
+    float* rbv = (float*)(smem_raw + a.o_rb);                                       // [g][c]: bonus if region_c == g else 0
+    int2* xg = (int2*)(smem_raw + a.o_xg);                                          // {ideology bits, region} by elector slot
+    float* nbs = (float*)(smem_raw + a.o_nbs);                                      // [R] -beta_r log2 e of the current set
     for (int i = threadIdx.x; i < CPP; i += blockDim.x) { xs[i] = 0.0f; pwv[i] = 0.0f; }
     for (int i = threadIdx.x; i < CPP * G; i += blockDim.x) rbv[i] = 0.0f;
     __syncthreads();
@@ -257,16 +294,11 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(Prefix
     }
     // ---- per-warp state ----------------------------------------------------------------------------
     unsigned char* base = smem_raw + a.cta_smem + (size_t)wib * a.warp_smem;
-    float* bw = nullptr; float* bwp = nullptr;
-    if (MODEL) {
-        bw = (float*)base;                      base += sizeof(float) * CPP;
-        bwp = (float*)base;                     base += sizeof(float) * 32;
-    }
-    int32_t* tally = (int32_t*)base;            base += sizeof(int32_t) * Ei;
-    int32_t* eff = (int32_t*)base;              base += sizeof(int32_t) * ((a.kmax + 3) & ~3);
-    uint16_t* votes = nullptr;
-    if (MODEL) { votes = (uint16_t*)base;       base += sizeof(uint16_t) * rows8; }
-    uint8_t* mark = (uint8_t*)base;
+    float* bw = (float*)base;                                                       // MODEL only
+    float* bwp = (float*)(base + a.w_bwp);                                          // MODEL only
+    int32_t* tally = (int32_t*)(base + a.w_tally);
+    int32_t* eff = (int32_t*)(base + a.w_eff);
+    uint8_t* mark = base + a.w_mark;
 
     const int n_qit = a.e_quad_end >> 7;                     // quad iterations (128 electors each)
     const bool top2_ok = C >= 2 && C < 32768;
@@ -274,15 +306,10 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(Prefix
     const uint32_t stride4 = 4u * (uint32_t)a.stride;
 
     PrefixCtx kx;
-    kx.xs = (uint32_t)__cvta_generic_to_shared(xs); kx.xg = (uint32_t)__cvta_generic_to_shared(xg);
-    kx.pw = (uint32_t)__cvta_generic_to_shared(pwv); kx.rb = (uint32_t)__cvta_generic_to_shared(rbv);
-    kx.bw = MODEL ? (uint32_t)__cvta_generic_to_shared(bw) : 0u; kx.bwp = MODEL ? (uint32_t)__cvta_generic_to_shared(bwp) : 0u;
-    kx.votes = MODEL ? (uint32_t)__cvta_generic_to_shared(votes) : 0u; kx.tally = (uint32_t)__cvta_generic_to_shared(tally);
-    kx.cp4 = 4u * (uint32_t)CPP;
-    kx.C = C; kx.Ls = Ls; kx.nch4 = 4 * nch; kx.nb = 0.f; kx.st1p = 1.f;
-    kx.step0_4 = 4;
-    while (kx.step0_4 * 2 <= 4 * nch) kx.step0_4 *= 2;
-    const uint32_t Ts_a = (uint32_t)__cvta_generic_to_shared(Ts);
+    kx.sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    kx.wb = kx.sb + (uint32_t)a.cta_smem + (uint32_t)wib * (uint32_t)a.warp_smem;
+    kx.nb = 0.f; kx.st1p = 1.f;
+    const uint32_t Ts_a = kx.sb;
 
     // the electors of one round, each lane with its uniform: whole Philox quads per lane, then the tail one per lane
     auto for_each_elector = [&](int r, uint32_t s_lo, uint32_t s_hi, auto&& fn) {
@@ -312,7 +339,7 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(Prefix
     const uint64_t items_per_set = (a.b.n_sims + per_item - 1) / per_item;
     const uint64_t n_items = items_per_set * a.b.n_sets;
     int cur_set = -1;
-    float bw_strength = 0.f;
+    float bw_strength = 0.f, bonus_s = 0.f;
     int need = 0, k = 0, rr = 0;
     bool has_sticky = false, has_bw = false;
     unsigned long long acc_rounds = 0, acc_trials = 0;
@@ -328,7 +355,7 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(Prefix
             acc_rounds = acc_trials = 0;
             cur_set = set;
             const DevSet* S = &a.b.sets[set];
-            kx.st1p = S->f_st1p; bw_strength = S->f_bandwagon;
+            kx.st1p = S->f_st1p; bw_strength = S->f_bandwagon; bonus_s = S->f_bonus;
             need = S->need; k = S->k; rr = S->rr;
             has_sticky = MODEL && S->has_sticky; has_bw = MODEL && S->has_bw;
             const float pwf = S->f_pwf, bonus = S->f_bonus;
@@ -398,30 +425,46 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(Prefix
                 if (!have_eff) {
                     // =============== full-field round ==============================================
                     for_each_elector(r, s_lo, s_hi, [&](int e, float u, int slot) {
-                        const int prev = sticky_live ? lds_u16(kx.votes + 2 * slot) : -1;
-                        const int vote = prefix_draw<LC8, MODEL, STAGE>(kx, Tr_a + (uint32_t)slot * stride4, Tr_g + (size_t)slot * a.stride, e, slot, u, prev);
-                        red_inc(kx.tally + 4 * vote);
-                        if (MODEL) sts_u16(kx.votes + 2 * slot, vote);   // read back only by this lane: in place is safe
+                        const int prev = sticky_live ? lds_u16(PFX_VOTES(kx, a) + 2 * slot) : -1;
+                        const int vote = prefix_draw<LC8, MODEL, STAGE>(kx, a, Tr_a + (uint32_t)slot * stride4, Tr_g + (size_t)slot * a.stride, e, slot, u, prev);
+                        red_inc(PFX_TALLY(kx, a) + 4 * vote);
+                        if (MODEL) sts_u16(PFX_VOTES(kx, a) + 2 * slot, vote);   // read back only by this lane: in place is safe
                     });
                 } else {
                     // =============== run-off round: first k columns (simulate.py:144-154) ===========
-                    for_each_elector(r, s_lo, s_hi, [&](int e, float u, int slot) {
-                        float xe; int ge;
-                        lds_xg(kx.xg + 8 * slot, xe, ge);
-                        const int prev = sticky_live ? lds_u16(kx.votes + 2 * slot) : -1;
-                        int vote;
-                        if (fast2) {
-                            const float v0 = prefix_full_score<MODEL>(kx, e, 0, xe, ge, prev);
-                            const float v1 = prefix_full_score<MODEL>(kx, e, 1, xe, ge, prev);
+                    if (fast2) {
+                        // k = 2: columns 0 and 1 are the same two candidates for every elector: their constants live in registers
+                        const uint32_t o1 = 4u * (uint32_t)pc(1);
+                        const float x0 = lds_f(PFX_XS(kx, a)), x1 = lds_f(PFX_XS(kx, a) + o1);
+                        const float p0 = lds_f(PFX_PW(kx, a)), p1 = lds_f(PFX_PW(kx, a) + o1);
+                        const float b0 = MODEL ? lds_f(PFX_BW(kx, a)) : 0.0f, b1 = MODEL ? lds_f(PFX_BW(kx, a) + o1) : 0.0f;
+                        float xt; int g0, g1;
+                        lds_xg(PFX_XG(kx, a) + 8 * prefix_slot(0, a.e_quad_end), xt, g0);
+                        lds_xg(PFX_XG(kx, a) + 8 * prefix_slot(1, a.e_quad_end), xt, g1);
+                        const float nb = kx.nb;
+                        for_each_elector(r, s_lo, s_hi, [&](int e, float u, int slot) {
+                            float xe; int ge;
+                            lds_xg(PFX_XG(kx, a) + 8 * slot, xe, ge);
+                            const int prev = sticky_live ? lds_u16(PFX_VOTES(kx, a) + 2 * slot) : -1;
+                            float v0 = fmaf(ex2_approx(fabsf(xe - x0) * nb), p0, ge == g0 ? bonus_s : 0.0f) + b0;
+                            float v1 = fmaf(ex2_approx(fabsf(xe - x1) * nb), p1, ge == g1 ? bonus_s : 0.0f) + b1;
+                            if (MODEL) { if (prev == 0) v0 *= kx.st1p; if (prev == 1) v1 *= kx.st1p; }
+                            if (e == 0) v0 = 0.0f;
+                            if (e == 1) v1 = 0.0f;
                             const float sum = v0 + v1;
                             int j;
                             if (!(sum > 0.0f)) j = (u * 2.0f >= 1.0f) ? 1 : 0;       // simulate.py:151 uniform fallback
                             else j = (v0 > u * sum || !(v1 > 0.0f)) ? 0 : 1;
                             cnt0 += (j == 0);
-                            vote = j == 0 ? ef0 : ef1;
-                        } else {
+                            if (MODEL) sts_u16(PFX_VOTES(kx, a) + 2 * slot, j == 0 ? ef0 : ef1);
+                        });
+                    } else {
+                        for_each_elector(r, s_lo, s_hi, [&](int e, float u, int slot) {
+                            float xe; int ge;
+                            lds_xg(PFX_XG(kx, a) + 8 * slot, xe, ge);
+                            const int prev = sticky_live ? lds_u16(PFX_VOTES(kx, a) + 2 * slot) : -1;
                             float sum = 0.f;
-                            for (int j = 0; j < k; ++j) sum += prefix_full_score<MODEL>(kx, e, j, xe, ge, prev);
+                            for (int j = 0; j < k; ++j) sum += prefix_full_score<MODEL>(kx, a, e, j, xe, ge, prev);
                             int jsel;
                             if (!(sum > 0.0f)) {
                                 jsel = (int)(u * (float)k);
@@ -429,7 +472,7 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(Prefix
                                 const float tgt = u * sum;
                                 float cum = 0.f; jsel = -1; int lastpos = 0;
                                 for (int j = 0; j < k; ++j) {
-                                    const float v = prefix_full_score<MODEL>(kx, e, j, xe, ge, prev);
+                                    const float v = prefix_full_score<MODEL>(kx, a, e, j, xe, ge, prev);
                                     cum += v;
                                     if (v > 0.0f) lastpos = j;
                                     if (jsel < 0 && v > 0.0f && cum > tgt) jsel = j;
@@ -437,11 +480,11 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(Prefix
                                 if (jsel < 0) jsel = lastpos;
                             }
                             if (jsel >= k) jsel = k - 1;
-                            vote = eff[jsel];
-                            red_inc(kx.tally + 4 * vote);
-                        }
-                        if (MODEL) sts_u16(kx.votes + 2 * slot, vote);
-                    });
+                            const int vote = eff[jsel];
+                            red_inc(PFX_TALLY(kx, a) + 4 * vote);
+                            if (MODEL) sts_u16(PFX_VOTES(kx, a) + 2 * slot, vote);
+                        });
+                    }
                 }
                 int n0 = 0, n1 = 0;
                 if (have_eff && fast2) {

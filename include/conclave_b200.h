@@ -49,8 +49,9 @@ typedef enum csim_status {
 #define CSIM_WIRING_MODEL   1 /* bandwagon / stickiness / fatigue / stop-candidate live, fed per trial */
 
 /* engine */
-#define CSIM_ENGINE_AUTO  0   /* ref_cli: TABLE when the batch is large enough to fill the GPU (PREFIX beyond 256 electors),
-                                 else DENSE; model: PREFIX in fp32 when its preconditions hold, else DENSE */
+#define CSIM_ENGINE_AUTO  0   /* ref_cli: TABLE when the batch is large enough to fill the GPU and E <= 256 (or fp64), else
+                                 PREFIX; model: PREFIX; DENSE whenever PREFIX cannot run (fp64, fatigue / stop-candidate,
+                                 negative bonus / strength / papabile factor, > 64 regions) */
 #define CSIM_ENGINE_DENSE 1   /* every trial re-evaluates its E x C scores each round */
 #define CSIM_ENGINE_TABLE 2   /* ref_cli only: trial-invariant per-round CDF tables, built once */
 #define CSIM_ENGINE_PREFIX 3  /* fp32, both wirings: trial-invariant chunk-prefix tables + per-trial bandwagon /
