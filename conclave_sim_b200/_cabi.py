@@ -20,7 +20,7 @@ ABI_VERSION = 1
 
 EXPORTS = ["csim_abi_version", "csim_last_error", "csim_create", "csim_destroy", "csim_device_info",
            "csim_upload_roster", "csim_beta_schedule", "csim_need_votes", "csim_prob_matrix", "csim_run",
-           "csim_stats", "csim_microbench"]
+           "csim_stats", "csim_microbench", "csim_prefix_plan_query", "csim_prefix_slot"]
 
 
 class CsimError(RuntimeError):
@@ -56,6 +56,14 @@ class CsimRunArgs(C.Structure):
     ]
 
 
+class CsimPrefixPlan(C.Structure):
+    """struct csim_prefix_plan"""
+    _fields_ = [(n, C.c_int32) for n in ("staged", "chunk", "n_chunks", "row_pitch", "rows", "table_rounds", "warps_per_cta",
+                                         "e_quad_end")] + \
+               [(n, C.c_uint64) for n in ("table_bytes_per_set", "smem_tables", "smem_cta", "smem_per_warp", "smem_total")] + \
+               [("offsets", C.c_uint32 * 12)]
+
+
 _lib = None
 
 
@@ -82,6 +90,10 @@ def load_library() -> C.CDLL:
     lib.csim_run.argtypes = [C.c_void_p, C.POINTER(CsimRunArgs)]
     lib.csim_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_float)]
     lib.csim_microbench.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double)]
+    lib.csim_prefix_plan_query.argtypes = [C.c_int32] * 6 + [C.c_uint64, C.c_int32, C.POINTER(CsimPrefixPlan)]
+    lib.csim_prefix_plan_query.restype = C.c_int
+    lib.csim_prefix_slot.argtypes = [C.c_int32, C.c_int32]
+    lib.csim_prefix_slot.restype = C.c_int32
     for name in ("csim_create", "csim_destroy", "csim_device_info", "csim_upload_roster", "csim_beta_schedule",
                  "csim_prob_matrix", "csim_run", "csim_stats", "csim_microbench"):
         getattr(lib, name).restype = C.c_int

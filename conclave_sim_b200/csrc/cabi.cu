@@ -534,49 +534,16 @@ static csim_status launch_prefix(csim_ctx* c, const csim_run_args* ra, const std
     a.ro = roster_dev(c); a.b = b; a.out = out; a.nbeta = (const float*)c->nbeta.p;
     int kmax = 1;
     for (const DevSet& s : hs) kmax = std::max(kmax, s.k);
-    a.kmax = kmax;
-    // electors are dealt to lanes as whole Philox quads (128 per warp pass group); a tail of <= 64 electors goes one per lane
-    const int n_left = E & 127;
-    a.e_quad_end = (E & ~127) + (n_left > 64 ? 128 : 0);
-    a.rows = std::max(E, a.e_quad_end);
     // only rounds that can be full-field need tables: once a run-off exists (k > 0) every round after
     // max(runoff_threshold_rounds, 1) is a run-off round (simulate.py:183-186)
     int Rt = 1;
     for (const DevSet& s : hs) Rt = std::max(Rt, s.k > 0 ? std::min(R, std::max(s.rr, 1)) : R);
     Rt = std::max(1, std::min(Rt, std::max(R, 1)));
-    a.Rt = Rt;
-    const int max_wpc = CSIM_PREFIX_THREADS / 32;
-    const size_t budget = (size_t)c->prop.sharedMemPerBlockOptin;
-    // smallest chunk (fewest re-scanned candidates) whose tables fit in shared memory next to >= 8 warps
-    int Ls_min = 3;
-    while (((E + (1 << Ls_min) - 1) >> Ls_min) > 32) ++Ls_min;
-    int Ls = -1, wpc = 0;
-    bool stage = false;
-    const char* force = getenv("CSIM_PREFIX_NOSTAGE");
-    for (int l = Ls_min; l <= 4 && !force; ++l) {          // a chunk of more than 16 costs more to re-scan than L2 probes do
-        const int nch = (E + (1 << l) - 1) >> l, stride = nch | 1, CPP = prefix_cpp(nch, l);
-        const size_t tab = (((size_t)Rt * a.rows * stride * 4) + 15) & ~(size_t)15;
-        const size_t fixed = tab + prefix_roster_smem(CPP, c->G, R, a.rows), per_warp = prefix_warp_smem(E, CPP, kmax, a.rows, model);
-        if (fixed + 8 * per_warp > budget) continue;
-        Ls = l; stage = true;
-        wpc = (int)std::min<size_t>(max_wpc, (budget - fixed) / per_warp);
-        break;
-    }
-    if (!stage) {
-        Ls = Ls_min;
-        const int nch = (E + (1 << Ls) - 1) >> Ls, CPP = prefix_cpp(nch, Ls);
-        const size_t fixed = prefix_roster_smem(CPP, c->G, R, a.rows), per_warp = prefix_warp_smem(E, CPP, kmax, a.rows, model);
-        if (fixed + per_warp > budget) return fail(CSIM_ERR_UNSUPPORTED, "prefix engine: a roster of %d electors does not fit in shared memory", E);
-        wpc = (int)std::min<size_t>(max_wpc, (budget - fixed) / per_warp);
-    }
-    a.Ls = Ls; a.nch = (E + (1 << Ls) - 1) >> Ls; a.stride = a.nch | 1;
-    const int CPP = prefix_cpp(a.nch, Ls);
-    a.set_pitch = (((size_t)Rt * a.rows * a.stride) + 3) & ~(size_t)3;
-    a.tab_smem = stage ? a.set_pitch * 4 : 0;
-    a.cta_smem = a.tab_smem + prefix_roster_smem(CPP, c->G, R, a.rows);
-    a.warp_smem = prefix_warp_smem(E, CPP, kmax, a.rows, model);
-    a.warps_per_cta = wpc;
-    prefix_layout(a, model);
+    const bool stage_ok = getenv("CSIM_PREFIX_NOSTAGE") == nullptr;
+    if (!prefix_plan(a, E, c->G, R, Rt, kmax, model, (size_t)c->prop.sharedMemPerBlockOptin, stage_ok))
+        return fail(CSIM_ERR_UNSUPPORTED, "prefix engine: a roster of %d electors does not fit in shared memory", E);
+    const bool stage = a.tab_smem != 0;
+    const int Ls = a.Ls;
     const size_t tbytes = a.set_pitch * 4 * (size_t)b.n_sets;
     if (tbytes > ((size_t)64 << 30)) return fail(CSIM_ERR_UNSUPPORTED, "prefix tables need %zu bytes", tbytes);
     CU_TRY(c->ptab.reserve(tbytes));
@@ -595,6 +562,30 @@ static csim_status launch_prefix(csim_ctx* c, const csim_run_args* ra, const std
     if (stage) return lc8 ? launch_prefix_t<true, false, true>(c, a, st) : launch_prefix_t<false, false, true>(c, a, st);
     return lc8 ? launch_prefix_t<true, false, false>(c, a, st) : launch_prefix_t<false, false, false>(c, a, st);
 }
+
+extern "C" csim_status csim_prefix_plan_query(int32_t n_electors, int32_t n_regions, int32_t max_rounds, int32_t table_rounds, int32_t kmax,
+                                              int32_t wiring, uint64_t smem_budget, int32_t allow_stage, csim_prefix_plan* out) {
+    if (!out) return fail(CSIM_ERR_INVALID, "csim_prefix_plan_query: out is NULL");
+    if (n_electors < 1 || n_electors >= 32768 || n_regions < 1 || n_regions > 64 || max_rounds < 0 || kmax < 0)
+        return fail(CSIM_ERR_INVALID, "csim_prefix_plan_query: need 1 <= electors < 32768, 1 <= regions <= 64, rounds >= 0, kmax >= 0");
+    PrefixArgs a;
+    memset(&a, 0, sizeof a);
+    memset(out, 0, sizeof *out);
+    const bool model = wiring == CSIM_WIRING_MODEL;
+    if (!prefix_plan(a, n_electors, n_regions, max_rounds, std::max(1, std::min(table_rounds, std::max(max_rounds, 1))), std::max(kmax, 1), model,
+                     (size_t)smem_budget, allow_stage != 0))
+        return fail(CSIM_ERR_UNSUPPORTED, "prefix engine: a roster of %d electors does not fit in %llu bytes of shared memory", n_electors,
+                    (unsigned long long)smem_budget);
+    out->staged = a.tab_smem != 0; out->chunk = 1 << a.Ls; out->n_chunks = a.nch; out->row_pitch = a.stride; out->rows = a.rows;
+    out->table_rounds = a.Rt; out->warps_per_cta = a.warps_per_cta; out->e_quad_end = a.e_quad_end;
+    out->table_bytes_per_set = a.set_pitch * 4; out->smem_tables = a.tab_smem; out->smem_cta = a.cta_smem; out->smem_per_warp = a.warp_smem;
+    out->smem_total = a.cta_smem + a.warp_smem * (uint64_t)a.warps_per_cta;
+    const uint32_t off[12] = {a.o_xs, a.o_pw, a.o_rb, a.o_xg, a.o_nbs, a.w_bwp, a.w_tally, a.w_eff, a.w_votes, a.w_mark, a.cp4, (uint32_t)a.step0_4};
+    for (int i = 0; i < 12; ++i) out->offsets[i] = off[i];
+    return CSIM_OK;
+}
+
+extern "C" int32_t csim_prefix_slot(int32_t elector, int32_t e_quad_end) { return prefix_slot(elector, e_quad_end); }
 
 extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
     if (!c || !ra) return fail(CSIM_ERR_INVALID, "csim_run: NULL argument");

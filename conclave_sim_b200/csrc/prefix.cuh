@@ -107,6 +107,55 @@ __host__ __device__ inline size_t prefix_warp_smem(int E, int CPP, int kmax, int
     return (n + 15) & ~(size_t)15;
 }
 
+// Host-side plan of one launch: how electors are dealt to lanes, the chunk size, whether the tables are staged in
+// shared memory, warps per CTA and every shared-memory offset.  Pure arithmetic (no CUDA calls): csim_prefix_plan_query
+// exposes it so that the CPU test-suite can check the budgeting for any roster shape.
+//   budget       = opt-in shared memory per block of the device (232448 B on sm_100)
+//   allow_stage  = false forces the global-memory (L2) path
+// Returns false when even one warp does not fit.
+__host__ inline bool prefix_plan(PrefixArgs& a, int E, int G, int R, int Rt, int kmax, bool model, size_t budget, bool allow_stage) {
+    a.ro.E = E; a.ro.G = G; a.kmax = kmax;
+    // electors are dealt to lanes as whole Philox quads (128 per group of 4 passes); a tail of <= 64 electors goes one per lane
+    const int n_left = E & 127;
+    a.e_quad_end = (E & ~127) + (n_left > 64 ? 128 : 0);
+    a.rows = E > a.e_quad_end ? E : a.e_quad_end;
+    a.Rt = Rt < 1 ? 1 : Rt;
+    const int max_wpc = CSIM_PREFIX_THREADS / 32;
+    int Ls_min = 3;
+    while (((E + (1 << Ls_min) - 1) >> Ls_min) > 32) ++Ls_min;         // at most 32 chunks (one lane per chunk in the bandwagon scan)
+    int Ls = -1, wpc = 0;
+    bool stage = false;
+    // smallest chunk (fewest re-scanned candidates) whose tables fit in shared memory next to >= 8 warps; a chunk of more
+    // than 16 candidates costs more to re-scan than probing the tables through L2 does
+    for (int l = Ls_min; l <= 4 && allow_stage; ++l) {
+        const int nch = (E + (1 << l) - 1) >> l, stride = nch | 1, CPP = prefix_cpp(nch, l);
+        const size_t tab = (((size_t)a.Rt * a.rows * stride * 4) + 15) & ~(size_t)15;
+        const size_t fixed = tab + prefix_roster_smem(CPP, G, R, a.rows), per_warp = prefix_warp_smem(E, CPP, kmax, a.rows, model);
+        if (fixed + 8 * per_warp > budget) continue;
+        Ls = l; stage = true;
+        const size_t fit = (budget - fixed) / per_warp;
+        wpc = (int)(fit < (size_t)max_wpc ? fit : (size_t)max_wpc);
+        break;
+    }
+    if (!stage) {
+        Ls = Ls_min;
+        const int nch = (E + (1 << Ls) - 1) >> Ls, CPP = prefix_cpp(nch, Ls);
+        const size_t fixed = prefix_roster_smem(CPP, G, R, a.rows), per_warp = prefix_warp_smem(E, CPP, kmax, a.rows, model);
+        if (fixed + per_warp > budget) return false;
+        const size_t fit = (budget - fixed) / per_warp;
+        wpc = (int)(fit < (size_t)max_wpc ? fit : (size_t)max_wpc);
+    }
+    a.Ls = Ls; a.nch = (E + (1 << Ls) - 1) >> Ls; a.stride = a.nch | 1;
+    const int CPP = prefix_cpp(a.nch, Ls);
+    a.set_pitch = (((size_t)a.Rt * a.rows * a.stride) + 3) & ~(size_t)3;
+    a.tab_smem = stage ? a.set_pitch * 4 : 0;
+    a.cta_smem = a.tab_smem + prefix_roster_smem(CPP, G, R, a.rows);
+    a.warp_smem = prefix_warp_smem(E, CPP, kmax, a.rows, model);
+    a.warps_per_cta = wpc;
+    prefix_layout(a, model);
+    return true;
+}
+
 // K0: chunk-prefix tables.  One warp per (set, round, elector), lane j sums chunk j in fp64 (the order of the
 // terms is model.py:311-324: exp, papabile factor, regional bonus), an inclusive warp scan makes the prefixes.
 // grid = (ceil(E / 8), sets * Rt), block = 256.

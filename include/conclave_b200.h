@@ -173,6 +173,31 @@ csim_status csim_prob_matrix(csim_ctx* ctx, const csim_params* p, double beta,
 /* The hot path: a batch of independent trials. */
 csim_status csim_run(csim_ctx* ctx, const csim_run_args* args);
 
+/* How the PREFIX engine would lay one launch out (pure host arithmetic, no device needed): used by the CPU tests to
+ * check the shared-memory budgeting for any roster shape, and by callers that want to know whether a roster's tables
+ * are staged in shared memory or probed through L2.
+ *   table_rounds = rounds that can be full-field: min(max_rounds, max(runoff_threshold_rounds, 1)) when a run-off
+ *                  exists, else max_rounds;  smem_budget = opt-in shared memory per block (232448 on sm_100).
+ * offsets[] = {o_xs, o_pw, o_rb, o_xg, o_nbs (from the start of dynamic shared memory), w_bwp, w_tally, w_eff,
+ *              w_votes, w_mark (from the warp's block), candidate-array pitch in bytes, 4 x first search step}. */
+typedef struct csim_prefix_plan {
+    int32_t  staged;            /* 1: tables of all table_rounds live in shared memory */
+    int32_t  chunk;             /* candidates per chunk (8, 16, 32, ...) */
+    int32_t  n_chunks;          /* <= 32 */
+    int32_t  row_pitch;         /* floats per table row (odd) */
+    int32_t  rows;              /* table rows per round */
+    int32_t  table_rounds;
+    int32_t  warps_per_cta;
+    int32_t  e_quad_end;        /* electors below this are dealt as whole Philox quads per lane */
+    uint64_t table_bytes_per_set;
+    uint64_t smem_tables, smem_cta, smem_per_warp, smem_total;
+    uint32_t offsets[12];
+} csim_prefix_plan;
+csim_status csim_prefix_plan_query(int32_t n_electors, int32_t n_regions, int32_t max_rounds, int32_t table_rounds, int32_t kmax,
+                                   int32_t wiring, uint64_t smem_budget, int32_t allow_stage, csim_prefix_plan* out);
+/* table row of an elector inside one round's table (the order the lanes visit electors) */
+int32_t     csim_prefix_slot(int32_t elector, int32_t e_quad_end);
+
 /* Diagnostics for bench.py: number of kernel launches this context has issued,
  * and the device time (ms, CUDA events on the launch stream) of the last csim_run's trial kernel. */
 csim_status csim_stats(csim_ctx* ctx, int64_t* kernel_launches, float* last_trial_kernel_ms);
