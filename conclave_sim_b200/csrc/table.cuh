@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(CSIM_TABLE_WPC * 32, 1024 / (CSIM_TABLE_WPC * 
             }
 #pragma unroll
             for (int sl = 0; sl < 4; ++sl) {
+                if (128 * gi + 32 * sl >= E) break;               // warp-uniform: nobody left in this group (E = 135: 3 of 8 sub-passes)
                 const int e = 128 * gi + 32 * sl + lane;
                 const int src = 8 * sl + (lane >> 2), sel = lane & 3;
                 const uint32_t a0 = __shfl_sync(CSIM_FULL, w[0], src), a1 = __shfl_sync(CSIM_FULL, w[1], src);
