@@ -328,7 +328,6 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(const 
     auto pc = [&](int c) { return c + ((c >> Ls) << 2); };   // index of candidate c in the padded arrays
     const int wpc = a.warps_per_cta;
     // ---- CTA-shared: staged tables of the current set, then roster tables (offsets: prefix_layout) ---------
-    float* Ts = (float*)smem_raw;
     float* xs = (float*)(smem_raw + a.o_xs);
     float* pwv = (float*)(smem_raw + a.o_pw);                                       // papabile weight of the current set (0 = padding)
     float* rbv = (float*)(smem_raw + a.o_rb);                                       // [g][c]: bonus if region_c == g else 0
