@@ -171,6 +171,10 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
+    # stdout carries ONE JSON line: libraries that print banners to fd 1 (NCCL's version line) are sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     args.warmup = max(args.warmup, 3)
 
     import torch
@@ -222,7 +226,7 @@ def main():
     time.sleep(0.3)
     launches0, _ = eng.stats()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kernel_ms, tot_rounds, tot_pairs = [], 0, 0
+    kernel_ms, tot_rounds, tot_pairs, kept_rounds = [], 0, 0, []
     barrier()
     for i in range(args.steps):
         flush.zero_()
@@ -231,10 +235,13 @@ def main():
         ev[i][1].record()
         ev[i][1].synchronize()
         kernel_ms.append(eng.stats()[1])
-        rounds_host = batch.rounds.cpu().numpy()          # after the step's end event: not timed
+        kept_rounds.append(batch.rounds.clone())          # device-side copy after the step's end event: not timed, and no host
+                                                          # work between steps that would skew the ranks against each other
+    barrier()
+    for rd in kept_rounds:
+        rounds_host = rd.cpu().numpy()
         tot_rounds += int(rounds_host.astype(np.int64).sum())
         tot_pairs += pair_evals(rounds_host, E, rr, k)
-    barrier()
     launches1, _ = eng.stats()
     clocks = sampler.stop()
     ms_local = sum(a.elapsed_time(b) for a, b in ev)
@@ -408,6 +415,8 @@ def main():
                                 "table_optimised_value": tab_er,
                                 "python_reference_in_build_container": "38.2 conclaves/s, 58.7k elector-rounds/s on 8 cores "
                                                                        "(unmodified reference, 20000 trials; tests/golden/dist_cfg2.json)"}
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
