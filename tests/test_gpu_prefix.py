@@ -269,3 +269,24 @@ def test_prefix_full_size_properties_model_wiring(eng):
         print(f"prefix==dense on {same:.5f} of {n} trials (wiring {wiring})")
         assert same > 0.995
         assert _chi2_homogeneity(pf.winner_hist[0], dn.winner_hist[0]) > 1e-3
+
+
+def test_prefix_model_wiring_distribution_vs_independent_oracle_sample(eng):
+    """`model` wiring under the native RNG: winners / rounds of 1e6 GPU trials against an INDEPENDENTLY seeded sample of
+    the fp64 oracle (40 000 trials, other seed, other sim ids) — the analogue, for the wiring the reference's CLI never
+    reaches, of the chi-square / KS gate against the reference's own sample."""
+    from scipy import stats
+    from conclave_sim_b200 import FP32
+    roster = G.real_roster()
+    upload(eng, roster)
+    mp = O.ModelParams(**CFG2)
+    ref = CO.run(roster, [(mp, EP2)], O.WIRING_MODEL, 40000, seed=424242, sim_id_begin=7_000_000)
+    n = 1_000_000
+    out = eng.run([to_params(mp, EP2)], n, seed=99, wiring=O.WIRING_MODEL, precision=FP32, engine=PREFIX, want_reason=False)
+    p_w = _chi2_homogeneity(out.winner_hist[0], ref["winner_hist"][0])
+    gr = np.append(out.rounds_hist[0], out.winner_hist[0, 134])
+    rr = np.append(ref["rounds_hist"][0], ref["winner_hist"][0, 134])
+    p_r = _chi2_homogeneity(gr, rr)
+    p_ks = stats.ks_2samp(np.repeat(np.arange(21), out.rounds_hist[0]), np.repeat(np.arange(21), ref["rounds_hist"][0])).pvalue
+    print(f"[prefix/model] chi2 winners p={p_w:.4f}  chi2 rounds p={p_r:.4f}  KS rounds p={p_ks:.4f}")
+    assert p_w > 0.01 and p_r > 0.01 and p_ks > 0.01
