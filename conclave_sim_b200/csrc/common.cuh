@@ -153,3 +153,25 @@ __device__ __forceinline__ void warp_top2(const int32_t* tally, int C, int lane,
     k1 = a; k2 = b;
 }
 
+
+// ---------------------------------------------------------------------------
+// Bulk asynchronous copy global -> shared (the TMA engine's 1-D form, SASS UBLKCP) completing on an mbarrier:
+// ONE thread issues the copy of a whole table, every thread of the CTA waits on the barrier's phase.
+// Addresses are shared-window addresses; `bytes` must be a multiple of 16 and both ends 16-byte aligned.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // order earlier generic-proxy accesses of dst before the async write
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(bar), "r"(phase) : "memory");
+}

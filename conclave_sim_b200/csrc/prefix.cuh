@@ -23,7 +23,7 @@
 // the ref_cli wiring the bandwagon / stickiness terms vanish and F_e(j) is one load.
 //
 // The tables of ALL rounds of one parameter set are small (E x 17 floats per round, 182 KB for 20 rounds
-// at E = 134) and live in shared memory (1 CTA per SM, cp.async-staged once per set), so — unlike the
+// at E = 134) and live in shared memory (1 CTA per SM, staged once per set by TMA bulk copies on an mbarrier), so — unlike the
 // full-resolution CDF tables of table.cuh, which only fit one round at a time — trials stay independent:
 // one warp owns one trial from round 1 to its end, then takes the next.  When they do not fit (cfg-5:
 // 1024 electors x 50 rounds = 6.7 MB) the probes read them through L2 instead (STAGE = false).
@@ -319,6 +319,21 @@ __device__ __forceinline__ int prefix_draw(const PrefixCtx& k, const PrefixArgs&
     return vote;
 }
 
+// One thread: (re-)arm the CTA's mbarrier and issue the set's tables as bulk copies (TMA 1-D, UBLKCP) of <= 32 KB, all
+// completing on that barrier.  Kept out of line so that its registers do not weigh on the trial loop.
+__device__ __noinline__ void prefix_stage_tables(uint32_t dst, const float* src, uint32_t total, uint32_t bar, bool first) {
+    if (!first) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+    mbar_init(bar, 1);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+    const char* gbase = reinterpret_cast<const char*>(src);
+    for (uint32_t off = 0; off < total; off += 32768u) {
+        const uint32_t nbytes = min(32768u, total - off);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst + off), "l"(gbase + off), "r"(nbytes), "r"(bar) : "memory");
+    }
+}
+
 template <bool LC8, bool MODEL, bool STAGE>
 __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(const __grid_constant__ PrefixArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -358,6 +373,7 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(const 
     kx.wb = kx.sb + (uint32_t)a.cta_smem + (uint32_t)wib * (uint32_t)a.warp_smem;
     kx.nb = 0.f; kx.st1p = 1.f;
     const uint32_t Ts_a = kx.sb;
+    __shared__ __align__(8) unsigned long long stage_bar;                   // mbarrier of the staged tables (re-armed per set: phase 0)
 
     // the electors of one round, each lane with its uniform: whole Philox quads per lane, then the tail one per lane
     auto for_each_elector = [&](int r, uint32_t s_lo, uint32_t s_hi, auto&& fn) {
@@ -401,6 +417,7 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(const 
                 atomicAdd(&a.out.totals[2 * cur_set], acc_rounds); atomicAdd(&a.out.totals[2 * cur_set + 1], acc_trials);
             }
             acc_rounds = acc_trials = 0;
+            const bool first_set = cur_set < 0;
             cur_set = set;
             const DevSet* S = &a.b.sets[set];
             kx.st1p = S->f_st1p; bw_strength = S->f_bandwagon; bonus_s = S->f_bonus;
@@ -409,20 +426,15 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(const 
             const float pwf = S->f_pwf, bonus = S->f_bonus;
             Tset = a.T + (size_t)set * a.set_pitch;
             __syncthreads();                                    // readers of the previous set's tables are done
-            if (STAGE) {
-                // asynchronous 16-byte copies global -> shared (LDGSTS), all of a thread's chunks in flight at once
-                const uint32_t n16 = (uint32_t)(a.tab_smem / 16);
-                const char* gbase = reinterpret_cast<const char*>(Tset);
-                for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(Ts_a + i * 16), "l"(gbase + (size_t)i * 16) : "memory");
-                asm volatile("cp.async.commit_group;" ::: "memory");
-            }
+            if (STAGE && threadIdx.x == 0)
+                prefix_stage_tables(Ts_a, Tset, (uint32_t)a.tab_smem, (uint32_t)__cvta_generic_to_shared(&stage_bar), first_set);
             for (int r = threadIdx.x; r < R; r += blockDim.x) nbs[r] = a.nbeta[(size_t)set * R + r];
             for (int c = threadIdx.x; c < C; c += blockDim.x) {
                 pwv[pc(c)] = a.ro.pap[c] ? pwf : 1.0f;
                 rbv[a.ro.region[c] * CPP + pc(c)] = bonus;
             }
-            if (STAGE) asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();                                    // the re-armed barrier is visible to every waiter
+            if (STAGE) mbar_wait((uint32_t)__cvta_generic_to_shared(&stage_bar), 0u);
             __syncthreads();
         }
         for (int ti = 0; ti < a.tpi; ++ti) {

@@ -125,6 +125,13 @@ __global__ void __launch_bounds__(CSIM_TABLE_WPC * 32, 1024 / (CSIM_TABLE_WPC * 
     int32_t* eff = (int32_t*)base;              base += sizeof(int32_t) * ((kmax + 3) & ~3);
     uint8_t* mark = (uint8_t*)base;
 
+    __shared__ __align__(8) unsigned long long stage_bar;                   // mbarrier of the staged table
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&stage_bar);
+    uint32_t stage_phase = 0;
+    if (STAGE) {
+        if (threadIdx.x == 0) mbar_init(bar_a, 1);
+        __syncthreads();
+    }
     const int wpc = a.warps_per_cta;
     const uint64_t sb_trials = (uint64_t)wpc * 32;                           // trials per super-batch
     const uint64_t sb_per_set = (a.b.n_sims + sb_trials - 1) / sb_trials;
@@ -195,14 +202,11 @@ __global__ void __launch_bounds__(CSIM_TABLE_WPC * 32, 1024 / (CSIM_TABLE_WPC * 
             const Real* tab_g = a.cdf + ((size_t)set * R + (r - 1)) * cdf_round_stride(E);
             if (STAGE) {
                 __syncthreads();                                  // previous round's readers are done
-                // asynchronous 16-byte copies global -> shared (LDGSTS): all of a thread's ~18 chunks are in flight at once
-                const uint32_t n16 = (uint32_t)(cdf_round_stride(E) * sizeof(Real) / 16);
-                const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(tab_s);
-                const char* gbase = reinterpret_cast<const char*>(tab_g);
-                for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + i * 16), "l"(gbase + (size_t)i * 16) : "memory");
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                // one bulk copy (TMA 1-D, UBLKCP) of the round's whole E x C table, completing on the CTA's mbarrier
+                if (threadIdx.x == 0)
+                    bulk_load_g2s((uint32_t)__cvta_generic_to_shared(tab_s), tab_g, (uint32_t)(cdf_round_stride(E) * sizeof(Real)), bar_a);
+                mbar_wait(bar_a, stage_phase);
+                stage_phase ^= 1u;
             }
             __syncthreads();
             if (!__any_sync(CSIM_FULL, alive)) continue;
