@@ -290,3 +290,37 @@ def test_prefix_model_wiring_distribution_vs_independent_oracle_sample(eng):
     p_ks = stats.ks_2samp(np.repeat(np.arange(21), out.rounds_hist[0]), np.repeat(np.arange(21), ref["rounds_hist"][0])).pvalue
     print(f"[prefix/model] chi2 winners p={p_w:.4f}  chi2 rounds p={p_r:.4f}  KS rounds p={p_ks:.4f}")
     assert p_w > 0.01 and p_r > 0.01 and p_ks > 0.01
+
+
+def test_plain_c_client_matches_python(eng, tmp_path):
+    """The C ABI without Python in the loop: tests/c/c_client.c (C99, only include/conclave_b200.h) is compiled with gcc,
+    linked against the library and run as its own process; its per-trial output equals the Python host's for the same
+    roster, parameters, seed and sim ids — on every engine — and an unsupported request comes back as a status + message."""
+    import subprocess
+    from conclave_sim_b200 import FP32, FP64, make_params
+    from conclave_sim_b200._cabi import LIB_PATH
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "c_client"
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "c", "c_client.c"), LIB_PATH, "-Wl,-rpath," + os.path.dirname(LIB_PATH), "-o", str(exe)],
+                   check=True)
+    E, n, seed = 135, 3000, 20250507
+    s = 12345
+    x = np.zeros(E); g = np.zeros(E, np.int32); pap = np.zeros(E, np.uint8)
+    for i in range(E):                                   # the LCG of c_client.c
+        s = (s * 1664525 + 1013904223) & 0xFFFFFFFF; x[i] = (s >> 8) / 16777216.0
+        s = (s * 1664525 + 1013904223) & 0xFFFFFFFF; g[i] = (s >> 16) % 8
+        s = (s * 1664525 + 1013904223) & 0xFFFFFFFF; pap[i] = ((s >> 16) % 100) < 15
+    eng.upload_roster(x, g, pap)
+    p = make_params(CFG2, max_rounds=20, supermajority_threshold=0.56)
+    for engine, wiring, precision in ((PREFIX, 1, FP32), (PREFIX, 0, FP32), (DENSE, 1, FP32), (TABLE, 0, FP32), (TABLE, 0, FP64), (0, 1, FP32)):
+        r = subprocess.run([str(exe), str(E), str(n), str(engine), str(wiring), str(precision), str(seed)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        lines = r.stdout.strip().split("\n")
+        got = np.array([[int(v) for v in ln.split()] for ln in lines[:n]])
+        ref = eng.run([p], n, seed=seed, sim_id_begin=1000, wiring=wiring, engine=engine, precision=precision)
+        assert np.array_equal(got[:, 0], ref.winner) and np.array_equal(got[:, 1], ref.rounds), (engine, wiring, precision)
+        assert lines[n] == f"totals {int(ref.totals[0, 0])} {int(ref.totals[0, 1])}"
+        assert lines[n + 1] == "whist " + " ".join(str(int(v)) for v in ref.winner_hist[0])
+        assert lines[n + 2] == "rhist " + " ".join(str(int(v)) for v in ref.rounds_hist[0])
+        assert lines[n + 3].startswith("prefix+fp64 -> -4 (") and "fp32 engine" in lines[n + 3]

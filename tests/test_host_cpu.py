@@ -38,10 +38,11 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_struct_mirrors_match_header(tmp_path):
     """Compile a tiny C program printing sizeof/offsetof of the header's structs; compare with ctypes."""
-    from conclave_sim_b200._cabi import CsimParams, CsimRunArgs
+    from conclave_sim_b200._cabi import CsimParams, CsimRunArgs, CsimPrefixPlan
     from oracle.c_oracle import CParams
     fields_p = [f[0] for f in CsimParams._fields_]
     fields_r = [f[0] for f in CsimRunArgs._fields_]
+    fields_q = [f[0] for f in CsimPrefixPlan._fields_]
     prog = '#include <stdio.h>\n#include <stddef.h>\n#include "conclave_b200.h"\nint main(){\n'
     prog += 'printf("%zu\\n", sizeof(csim_params));\n'
     for f in fields_p:
@@ -49,14 +50,18 @@ def test_struct_mirrors_match_header(tmp_path):
     prog += 'printf("%zu\\n", sizeof(csim_run_args));\n'
     for f in fields_r:
         prog += f'printf("%zu\\n", offsetof(csim_run_args, {f}));\n'
+    prog += 'printf("%zu\\n", sizeof(csim_prefix_plan));\n'
+    for f in fields_q:
+        prog += f'printf("%zu\\n", offsetof(csim_prefix_plan, {f}));\n'
     prog += "return 0;}\n"
     c = tmp_path / "t.c"
     c.write_text(prog)
     exe = tmp_path / "t"
-    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)], check=True)
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)], check=True)
     nums = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     exp = [ctypes.sizeof(CsimParams)] + [getattr(CsimParams, f).offset for f in fields_p] + \
-          [ctypes.sizeof(CsimRunArgs)] + [getattr(CsimRunArgs, f).offset for f in fields_r]
+          [ctypes.sizeof(CsimRunArgs)] + [getattr(CsimRunArgs, f).offset for f in fields_r] + \
+          [ctypes.sizeof(CsimPrefixPlan)] + [getattr(CsimPrefixPlan, f).offset for f in fields_q]
     assert nums == exp
     assert ctypes.sizeof(CParams) == ctypes.sizeof(CsimParams)
     assert [f[0] for f in CParams._fields_] == fields_p
@@ -227,3 +232,14 @@ def test_legacy_shim_input_validation():
         S.run_monte_carlo_simulation(1, pd.DataFrame(columns=["elector_id", "ideology_score"]), {"beta_weight": 0.1})
     with pytest.raises(ValueError, match="must contain an 'elector_id' column"):
         S.run_monte_carlo_simulation(1, pd.DataFrame({"ideology_score": [0.1, 0.2]}), {"beta_weight": 0.1})
+
+
+def test_plain_c_client_compiles_and_links(tmp_path):
+    """tests/c/c_client.c — a C99 program using nothing but include/conclave_b200.h — compiles with -Wall -Werror -pedantic
+    and links against the shared library (it is RUN by the GPU test test_plain_c_client_matches_python)."""
+    from conclave_sim_b200._cabi import LIB_PATH
+    exe = tmp_path / "c_client"
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "c_client.c"), LIB_PATH, "-Wl,-rpath," + os.path.dirname(LIB_PATH), "-o", str(exe)],
+                   check=True)
+    assert exe.exists()
