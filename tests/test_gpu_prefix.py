@@ -324,3 +324,35 @@ def test_plain_c_client_matches_python(eng, tmp_path):
         assert lines[n + 1] == "whist " + " ".join(str(int(v)) for v in ref.winner_hist[0])
         assert lines[n + 2] == "rhist " + " ".join(str(int(v)) for v in ref.rounds_hist[0])
         assert lines[n + 3].startswith("prefix+fp64 -> -4 (") and "fp32 engine" in lines[n + 3]
+
+
+def test_cli_model_wiring_runs_on_the_prefix_engine(eng, tmp_path):
+    """`python -m conclave_sim_b200.simulate --wiring model` (bandwagon + stickiness live): the reference's CLI surface, CSV and
+    stats JSON contracts, on the engine AUTO picks for this wiring; the statistics match the oracle's for the same wiring."""
+    import pandas as pd
+    from conclave_sim_b200 import simulate as S
+    roster = G.real_roster()
+    df = pd.DataFrame({"ideology_score": roster.ideology, "region": [f"R{g}" for g in roster.region],
+                       "is_papabile": roster.papabile}, index=pd.Index(roster.ids, name="elector_id"))
+    csv = tmp_path / "roster.csv"
+    df.reset_index().to_csv(csv, index=False)
+    out_csv, out_json = tmp_path / "res.csv", tmp_path / "stats.json"
+    common = ["-n", "4000", "-r", "20", "-t", "0.56", "-f", str(csv), "-o", str(out_csv), "-s", str(out_json),
+              "--enable-dynamic-beta", "--beta-increment-amount", "0.3", "--beta-increment-interval-rounds", "1",
+              "--initial-beta-weight", "1.5", "--bandwagon-strength", "0.7", "--papabile-weight-factor", "2.0",
+              "--stickiness-factor", "0.8", "--seed", "42", "--wiring", "model"]
+    res = {}
+    for engine in ("auto", "prefix", "dense"):
+        S.main(common + ["--engine", engine])
+        got = pd.read_csv(out_csv)
+        assert list(got.columns) == ["sim_id", "winner", "rounds", "reason"] and len(got) == 4000
+        res[engine] = (got, json.load(open(out_json)))
+    assert res["auto"][0].equals(res["prefix"][0])                       # AUTO == PREFIX for this wiring
+    same = (res["prefix"][0]["rounds"] == res["dense"][0]["rounds"]).mean()
+    assert same > 0.99                                                    # two fp32 kernels, one Philox stream
+    ref = CO.run(roster, [(O.ModelParams(**CFG2), EP2)], O.WIRING_MODEL, 4000, seed=42)
+    js = res["prefix"][1]
+    assert js["total_simulations"] == 4000
+    assert abs(js["success_rate"] - float((ref["winner"] >= 0).mean())) < 0.005
+    assert abs(js["average_rounds_all"] - float(ref["rounds"].mean())) < 0.02
+    S.RUNTIME.update(wiring="ref_cli", engine="auto", seed=None)
