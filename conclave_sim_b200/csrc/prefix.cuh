@@ -460,7 +460,11 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(const 
                 const int rt = min(r, a.Rt) - 1;                     // rounds beyond Rt are run-off rounds: no table
                 const uint32_t Tr_a = Ts_a + (uint32_t)((size_t)rt * round_pitch * 4);
                 const float* Tr_g = Tset + (size_t)rt * round_pitch;
-                if (MODEL && has_bw && have_prev && prev_mx > 0) {               // bandwagon, model.py:326-354
+                float rb0 = 0.0f, rb1 = 0.0f;                        // bandwagon of candidates 0 / 1 (a k = 2 run-off round needs no more)
+                if (MODEL && has_bw && have_prev && prev_mx > 0 && have_eff && fast2) {
+                    const float inv = 1.0f / (float)prev_mx;
+                    rb0 = (float)tally[0] * inv * bw_strength; rb1 = (float)tally[1] * inv * bw_strength;
+                } else if (MODEL && has_bw && have_prev && prev_mx > 0) {        // bandwagon, model.py:326-354
                     const float inv = 1.0f / (float)prev_mx;
                     for (int c = lane; c < C; c += 32) bw[pc(c)] = (float)tally[c] * inv * bw_strength;   // tally = previous round's
                     __syncwarp();
@@ -497,7 +501,7 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(const 
                         const uint32_t o1 = 4u * (uint32_t)pc(1);
                         const float x0 = lds_f(PFX_XS(kx, a)), x1 = lds_f(PFX_XS(kx, a) + o1);
                         const float p0 = lds_f(PFX_PW(kx, a)), p1 = lds_f(PFX_PW(kx, a) + o1);
-                        const float b0 = MODEL ? lds_f(PFX_BW(kx, a)) : 0.0f, b1 = MODEL ? lds_f(PFX_BW(kx, a) + o1) : 0.0f;
+                        const float b0 = rb0, b1 = rb1;
                         float xt; int g0, g1;
                         lds_xg(PFX_XG(kx, a) + 8 * prefix_slot(0, a.e_quad_end), xt, g0);
                         lds_xg(PFX_XG(kx, a) + 8 * prefix_slot(1, a.e_quad_end), xt, g1);
