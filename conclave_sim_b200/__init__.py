@@ -11,10 +11,10 @@ Layout:
   ingest.py        ElectorDataIngester        (mirror of src/ingest.py:611-663)
   dist.py          trial sharding across GPUs + histogram all-reduce (torch.distributed)
 """
-from ._cabi import (CsimError, WIRING_REF_CLI, WIRING_MODEL, ENGINE_AUTO, ENGINE_DENSE, ENGINE_TABLE, ENGINE_PREFIX,
+from ._cabi import (CsimError, WIRING_REF_CLI, WIRING_MODEL, ENGINE_AUTO, ENGINE_DENSE, ENGINE_TABLE, ENGINE_PREFIX, ENGINE_FULL,
                     FP32, FP64, REASON_MAX_ROUNDS, REASON_WINNER, REASON_NO_PROBS)
 from .engine import Engine, get_engine, make_params, RunResult
 
 __all__ = ["Engine", "get_engine", "make_params", "RunResult", "CsimError",
-           "WIRING_REF_CLI", "WIRING_MODEL", "ENGINE_AUTO", "ENGINE_DENSE", "ENGINE_TABLE", "ENGINE_PREFIX", "FP32", "FP64",
+           "WIRING_REF_CLI", "WIRING_MODEL", "ENGINE_AUTO", "ENGINE_DENSE", "ENGINE_TABLE", "ENGINE_PREFIX", "ENGINE_FULL", "FP32", "FP64",
            "REASON_MAX_ROUNDS", "REASON_WINNER", "REASON_NO_PROBS"]

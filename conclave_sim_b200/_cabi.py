@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CSIM_LIB") or os.path.join(HERE, "libconclave_b200.so")   # CSIM_LIB: tuning builds only
 
 WIRING_REF_CLI, WIRING_MODEL = 0, 1
-ENGINE_AUTO, ENGINE_DENSE, ENGINE_TABLE, ENGINE_PREFIX = 0, 1, 2, 3
+ENGINE_AUTO, ENGINE_DENSE, ENGINE_TABLE, ENGINE_PREFIX, ENGINE_FULL = 0, 1, 2, 3, 4
 FP32, FP64 = 0, 1
 REASON_MAX_ROUNDS, REASON_WINNER, REASON_NO_PROBS = 0, 1, 2
 BETA_STEPPED, BETA_GROWTH = 0, 1

@@ -23,6 +23,7 @@
 #include "prob32.cuh"
 #include "table.cuh"
 #include "prefix.cuh"
+#include "full32.cuh"
 
 static thread_local std::string g_err;
 
@@ -563,6 +564,48 @@ static csim_status launch_prefix(csim_ctx* c, const csim_run_args* ra, const std
     return lc8 ? launch_prefix_t<true, false, false>(c, a, st) : launch_prefix_t<false, false, false>(c, a, st);
 }
 
+// ---------------------------------------------------------------------------------------------
+// FULL engine (full32.cuh): fp32, every model term inline, fatigue + stop-candidate included
+// ---------------------------------------------------------------------------------------------
+static csim_status launch_full32(csim_ctx* c, const csim_run_args* ra, const std::vector<DevSet>& hs, const BatchDev& b,
+                                 const TrialOut& out, cudaStream_t st) {
+    if (ra->precision != CSIM_FP32) return fail(CSIM_ERR_UNSUPPORTED, "the full engine is an fp32 engine (CSIM_FP64: use DENSE)");
+    for (int i = 0; i < ra->n_param_sets; ++i)
+        if (ra->params[i].regional_affinity_bonus < 0 || ra->params[i].bandwagon_strength < 0 || ra->params[i].papabile_weight_factor < 0 ||
+            ra->params[i].fatigue_penalty_factor < 0 || ra->params[i].stop_candidate_boost_factor < 0)
+            return fail(CSIM_ERR_UNSUPPORTED, "negative bonus / strength / papabile / fatigue / boost factor: use CSIM_FP64 precision");
+    const int E = c->E, R = b.R;
+    if (c->G > 64) return fail(CSIM_ERR_UNSUPPORTED, "%d distinct regions (> 64): use CSIM_FP64 precision", c->G);
+    if (E >= 32768) return fail(CSIM_ERR_UNSUPPORTED, "full engine: at most 32767 electors");
+    Full32Args a;
+    memset(&a, 0, sizeof a);
+    int kmax = 1, Fmax = 1;
+    for (const DevSet& s : hs) { kmax = std::max(kmax, s.k); Fmax = std::max(Fmax, s.fat_rounds); }
+    if (!full32_plan(a, E, c->G, R, kmax, Fmax, (size_t)c->prop.sharedMemPerBlockOptin))
+        return fail(CSIM_ERR_UNSUPPORTED, "full engine: a roster of %d electors (fatigue window %d) does not fit in shared memory", E, Fmax);
+    a.ro = roster_dev(c); a.b = b; a.out = out; a.nbeta = (const float*)c->nbeta.p;
+    const int wpc = a.warps_per_cta;
+    const size_t smem = a.cta_smem + a.warp_smem * wpc;
+    CU_TRY(cudaFuncSetAttribute(k_trials_full32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trials_full32, wpc * 32, smem));
+    if (per_sm < 1) return fail(CSIM_ERR_UNSUPPORTED, "full kernel does not fit on an SM (threads=%d, smem=%zu)", wpc * 32, smem);
+    const uint64_t ctas = (uint64_t)c->prop.multiProcessorCount * per_sm;
+    uint64_t tpi = a.b.n_sims / ((uint64_t)wpc * ctas * 8);
+    tpi = std::max<uint64_t>(1, std::min<uint64_t>(tpi, 64));
+    a.tpi = (int)tpi;
+    const uint64_t per_item = (uint64_t)wpc * tpi;
+    const uint64_t n_items = ((a.b.n_sims + per_item - 1) / per_item) * a.b.n_sets;
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_items, ctas));
+    CU_TRY(cudaEventRecord(c->ev0, st));
+    k_trials_full32<<<grid, wpc * 32, smem, st>>>(a);
+    CU_TRY(cudaEventRecord(c->ev1, st));
+    c->ev_valid = true;
+    ++c->launches;
+    CU_TRY(cudaGetLastError());
+    return CSIM_OK;
+}
+
 extern "C" csim_status csim_prefix_plan_query(int32_t n_electors, int32_t n_regions, int32_t max_rounds, int32_t table_rounds, int32_t kmax,
                                               int32_t wiring, uint64_t smem_budget, int32_t allow_stage, csim_prefix_plan* out) {
     if (!out) return fail(CSIM_ERR_INVALID, "csim_prefix_plan_query: out is NULL");
@@ -594,7 +637,7 @@ extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
     if (!ra->winner || !ra->rounds) return fail(CSIM_ERR_INVALID, "csim_run: winner and rounds outputs are required");
     if (ra->wiring != CSIM_WIRING_REF_CLI && ra->wiring != CSIM_WIRING_MODEL) return fail(CSIM_ERR_INVALID, "csim_run: bad wiring %d", ra->wiring);
     if (ra->precision != CSIM_FP32 && ra->precision != CSIM_FP64) return fail(CSIM_ERR_INVALID, "csim_run: bad precision %d", ra->precision);
-    if (ra->engine != CSIM_ENGINE_AUTO && ra->engine != CSIM_ENGINE_DENSE && ra->engine != CSIM_ENGINE_TABLE && ra->engine != CSIM_ENGINE_PREFIX)
+    if (ra->engine != CSIM_ENGINE_AUTO && ra->engine != CSIM_ENGINE_DENSE && ra->engine != CSIM_ENGINE_TABLE && ra->engine != CSIM_ENGINE_PREFIX && ra->engine != CSIM_ENGINE_FULL)
         return fail(CSIM_ERR_INVALID, "csim_run: bad engine %d", ra->engine);
     if (ra->uniform_tape && ra->precision != CSIM_FP64) return fail(CSIM_ERR_INVALID, "csim_run: a uniform tape requires CSIM_FP64 precision");
     const int R = ra->params[0].max_rounds;
@@ -657,15 +700,18 @@ extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
 
     // engine choice (CSIM_ENGINE_AUTO)
     //   model wiring, fp32: the PREFIX engine (trial-invariant chunk-prefix tables + per-trial corrections) whenever its
-    //     preconditions hold, else DENSE;
+    //     preconditions hold; with candidate fatigue / stop-candidate live the FULL engine (every term inline); else DENSE
+    //     (which reports what it cannot do);
     //   ref_cli wiring: the TABLE engine when the batch fills the GPU with its 512-trial super-batches (or fp64); rosters
     //     whose E x C rows do not fit in shared memory (E > 256) go to PREFIX, and so do small fp32 batches (BASELINE
     //     configs 1-2: 100 / 1000 trials finish in 0.06-0.08 ms on its one-warp-per-trial grid; DENSE if PREFIX cannot run).
     int engine = ra->engine;
     if (engine == CSIM_ENGINE_AUTO) {
         const bool pfx_ok = ra->precision == CSIM_FP32 && prefix_supported(c, ra, hs, R);
+        bool extras = false;                                     // candidate fatigue / stop-candidate live (model wiring only)
+        for (const DevSet& s : hs) extras = extras || s.en_fat || s.en_stop;
         if (ra->wiring == CSIM_WIRING_MODEL) {
-            engine = pfx_ok ? CSIM_ENGINE_PREFIX : CSIM_ENGINE_DENSE;
+            engine = pfx_ok ? CSIM_ENGINE_PREFIX : ((extras && ra->precision == CSIM_FP32) ? CSIM_ENGINE_FULL : CSIM_ENGINE_DENSE);
         } else {
             const uint64_t n_sb = ((ra->n_sims + (uint64_t)CSIM_TABLE_WPC * 32 - 1) / ((uint64_t)CSIM_TABLE_WPC * 32)) * ra->n_param_sets;
             if (ra->precision == CSIM_FP64) engine = CSIM_ENGINE_TABLE;
@@ -673,7 +719,8 @@ extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
             else engine = n_sb >= (uint64_t)c->prop.multiProcessorCount / 2 ? CSIM_ENGINE_TABLE : (pfx_ok ? CSIM_ENGINE_PREFIX : CSIM_ENGINE_DENSE);
         }
     }
-    csim_status s = engine == CSIM_ENGINE_PREFIX ? launch_prefix(c, ra, hs, b, out, st)
+    csim_status s = engine == CSIM_ENGINE_FULL ? launch_full32(c, ra, hs, b, out, st)
+                    : engine == CSIM_ENGINE_PREFIX ? launch_prefix(c, ra, hs, b, out, st)
                     : engine == CSIM_ENGINE_TABLE ? launch_table(c, ra, hs, b, out, st)
                     : (ra->precision == CSIM_FP64 ? launch_exact64(c, ra, hs, b, out, st) : launch_dense32(c, ra, hs, hb, b, out, st));
     if (s != CSIM_OK) return s;

@@ -46,7 +46,7 @@ DEFAULT_RUNOFF_CANDIDATE_COUNT = 2
 RUNTIME: Dict[str, Any] = dict(wiring="ref_cli", seed=None, device=0, precision="fp32", engine="auto")
 _WIRING = {"ref_cli": _cabi.WIRING_REF_CLI, "model": _cabi.WIRING_MODEL}
 _PRECISION = {"fp32": _cabi.FP32, "fp64": _cabi.FP64}
-_ENGINE = {"auto": _cabi.ENGINE_AUTO, "dense": _cabi.ENGINE_DENSE, "table": _cabi.ENGINE_TABLE, "prefix": _cabi.ENGINE_PREFIX}
+_ENGINE = {"auto": _cabi.ENGINE_AUTO, "dense": _cabi.ENGINE_DENSE, "table": _cabi.ENGINE_TABLE, "prefix": _cabi.ENGINE_PREFIX, "full": _cabi.ENGINE_FULL}
 
 
 def _seed() -> int:
@@ -89,8 +89,6 @@ def run_simulations(elector_data_full: pd.DataFrame, model_params: Dict[str, Any
     prec = _PRECISION[precision]
     if uniform_tapes is not None:
         prec = _cabi.FP64
-    elif prec == _cabi.FP32 and _WIRING[wiring] == _cabi.WIRING_MODEL and (enable_candidate_fatigue or enable_stop_candidate):
-        prec = _cabi.FP64      # those two terms exist in the fp64 kernel only
     return eng.run([params], num_simulations, sim_id_begin=sim_id_begin, seed=_seed() if seed is None else seed,
                    wiring=_WIRING[wiring], engine=_ENGINE[engine], precision=prec, tapes=uniform_tapes,
                    want_final_votes=want_final_votes, want_round_tallies=want_round_tallies)
@@ -178,7 +176,7 @@ def build_parser() -> argparse.ArgumentParser:
     gpu.add_argument("--seed", type=int, default=None, help="Philox key (default: fresh per process, like the reference's unseeded RNG).")
     gpu.add_argument("--device", type=int, default=0, help="CUDA device ordinal.")
     gpu.add_argument("--precision", choices=["fp32", "fp64"], default="fp32", help="fp32 fast path or fp64 exact path.")
-    gpu.add_argument("--engine", choices=["auto", "dense", "table", "prefix"], default="auto")
+    gpu.add_argument("--engine", choices=["auto", "dense", "table", "prefix", "full"], default="auto")
     return parser
 
 

@@ -50,12 +50,15 @@ typedef enum csim_status {
 
 /* engine */
 #define CSIM_ENGINE_AUTO  0   /* ref_cli: TABLE when the batch is large enough to fill the GPU and E <= 256 (or fp64), else
-                                 PREFIX; model: PREFIX; DENSE whenever PREFIX cannot run (fp64, fatigue / stop-candidate,
-                                 negative bonus / strength / papabile factor, > 64 regions) */
+                                 PREFIX; model: PREFIX, or FULL when candidate fatigue / stop-candidate is live in fp32; DENSE
+                                 whenever those cannot run (fp64, negative bonus / strength / papabile factor, > 64 regions) */
 #define CSIM_ENGINE_DENSE 1   /* every trial re-evaluates its E x C scores each round */
 #define CSIM_ENGINE_TABLE 2   /* ref_cli only: trial-invariant per-round CDF tables, built once */
 #define CSIM_ENGINE_PREFIX 3  /* fp32, both wirings: trial-invariant chunk-prefix tables + per-trial bandwagon /
                                  stickiness corrections, binary search over chunks, re-scan of one chunk */
+#define CSIM_ENGINE_FULL   4  /* fp32: every term of the model inline per (elector, candidate), candidate fatigue and
+                                 stop-candidate included (the fatigue set and the stop trigger are decided in fp64 exactly
+                                 as the exact engine decides them) */
 
 /* arithmetic */
 #define CSIM_FP32 0           /* fast path: fp32 scores, ex2.approx, 24-bit uniforms */

@@ -356,3 +356,90 @@ def test_cli_model_wiring_runs_on_the_prefix_engine(eng, tmp_path):
     assert abs(js["success_rate"] - float((ref["winner"] >= 0).mean())) < 0.005
     assert abs(js["average_rounds_all"] - float(ref["rounds"].mean())) < 0.02
     S.RUNTIME.update(wiring="ref_cli", engine="auto", seed=None)
+
+
+# ------------------------------------------------------------------ the FULL engine (fatigue + stop-candidate in fp32)
+FULL = 4
+
+
+def _extras_sets():
+    base = dict(CFG2)
+    mps = [O.ModelParams(**base, enable_candidate_fatigue=True, enable_stop_candidate=True, stop_candidate_threshold_unacceptable_distance=0.3),
+           O.ModelParams(**base, enable_candidate_fatigue=True, fatigue_penalty_factor=0.25),
+           O.ModelParams(**base, enable_stop_candidate=True, stop_candidate_threshold_unacceptable_distance=0.2,
+                         stop_candidate_threat_min_vote_share=0.08, stop_candidate_boost_factor=2.5),
+           O.ModelParams(**base)]
+    eps = [O.EngineParams(max_rounds=14, supermajority_threshold=0.56, runoff_threshold_rounds=7, enable_candidate_fatigue=True,
+                          fatigue_threshold_rounds=2, fatigue_vote_share_threshold=0.03, fatigue_top_n_immune=3, enable_stop_candidate=True),
+           O.EngineParams(max_rounds=14, supermajority_threshold=0.6, runoff_threshold_rounds=9, runoff_candidate_count=3,
+                          enable_candidate_fatigue=True, fatigue_threshold_rounds=3, fatigue_vote_share_threshold=0.05, fatigue_top_n_immune=0),
+           O.EngineParams(max_rounds=14, supermajority_threshold=0.56, runoff_threshold_rounds=5, enable_stop_candidate=True),
+           O.EngineParams(max_rounds=14, supermajority_threshold=0.56, runoff_threshold_rounds=5)]
+    return list(zip(mps, eps))
+
+
+def test_full_engine_fatigue_and_stop_vs_oracle(eng):
+    """fp32 with candidate fatigue and stop-candidate live: per-trial agreement with the fp64 oracle (the fatigue set and the
+    stop trigger are decided in fp64 on both sides, so a trial diverges only through an fp32 draw flip), per-round tallies,
+    histograms; the same batch through AUTO (which must pick this engine) and against the exact fp64 GPU engine."""
+    from conclave_sim_b200 import FP32, FP64
+    roster = G.real_roster()
+    upload(eng, roster)
+    sets = _extras_sets()
+    ps = [to_params(*s) for s in sets]
+    n = 600
+    ref = CO.run(roster, sets, O.WIRING_MODEL, n, seed=3, want_tallies=True)
+    out = eng.run(ps, n, seed=3, wiring=O.WIRING_MODEL, engine=FULL, precision=FP32, want_round_tallies=True, want_final_votes=True)
+    same = _same(out, ref).reshape(len(sets), n).mean(axis=1)
+    print("full32 vs oracle per set:", same)
+    assert (same > 0.97).all(), same
+    first = out.round_tallies[:, 0, :]
+    assert (first.sum(axis=1) == 134).all()
+    assert np.mean((out.round_tallies[:, :3, :] == ref["round_tallies"][:, :3, :]).all(axis=(1, 2))) > 0.99
+    w = out.winner.reshape(len(sets), n)
+    for s in range(len(sets)):
+        assert out.winner_hist[s, :134].sum() == (w[s] >= 0).sum() and out.totals[s, 1] == n
+    auto = eng.run(ps, n, seed=3, wiring=O.WIRING_MODEL, precision=FP32)              # AUTO: fatigue / stop live -> FULL
+    assert np.array_equal(auto.winner, out.winner) and np.array_equal(auto.rounds, out.rounds)
+    exact = eng.run(ps, n, seed=3, wiring=O.WIRING_MODEL, precision=FP64)
+    assert np.array_equal(exact.winner, ref["winner"]) and np.array_equal(exact.rounds, ref["rounds"])
+    # the extras change the outcome distribution: the test would be vacuous otherwise
+    plain = eng.run([ps[3]] * 1, n, seed=3, wiring=O.WIRING_MODEL, engine=PREFIX, precision=FP32)
+    assert np.array_equal(plain.winner, w[3])                                          # set 3 has no extras: FULL == PREFIX trial for trial
+    assert np.mean(w[0] != w[3]) > 0.2 and np.mean(w[2] != w[3]) > 0.05
+
+
+@pytest.mark.parametrize("E", [2, 9, 33, 129, 200, 300])
+def test_full_engine_on_ragged_rosters(eng, E):
+    from conclave_sim_b200 import FP32
+    roster = O.synthetic_roster(E, seed=300 + E)
+    upload(eng, roster)
+    mp = O.ModelParams(**dict(CFG2, stickiness_factor=1.2, bandwagon_strength=1.0), enable_candidate_fatigue=True, enable_stop_candidate=True,
+                       stop_candidate_threshold_unacceptable_distance=0.25, stop_candidate_threat_min_vote_share=0.1)
+    ep = O.EngineParams(max_rounds=10, supermajority_threshold=0.6, runoff_threshold_rounds=6, enable_candidate_fatigue=True,
+                        fatigue_threshold_rounds=2, fatigue_vote_share_threshold=0.04, fatigue_top_n_immune=2, enable_stop_candidate=True)
+    n = 128
+    ref = CO.run(roster, [(mp, ep)], O.WIRING_MODEL, n, seed=8, want_tallies=True)
+    out = eng.run([to_params(mp, ep)], n, seed=8, wiring=O.WIRING_MODEL, engine=FULL, precision=FP32, want_round_tallies=True)
+    assert (out.round_tallies[:, 0, :].sum(axis=1) == E).all()
+    agree = np.mean((out.winner == ref["winner"]) & (out.rounds == ref["rounds"]))
+    assert agree > 0.9, (E, agree)
+
+
+def test_full_engine_without_extras_equals_prefix_and_scales(eng):
+    """No fatigue / stop: the FULL kernel is a plain dense fp32 engine; on 200 000 trials it agrees with PREFIX per trial
+    (different kernels, one Philox stream), conserves votes and is independent of how the sim-id range is cut."""
+    from conclave_sim_b200 import FP32
+    roster = O.synthetic_roster(135)
+    upload(eng, roster)
+    p = [to_params(O.ModelParams(**CFG2), EP2)]
+    n = 200_000
+    for wiring in (O.WIRING_MODEL, O.WIRING_REF_CLI):
+        f = eng.run(p, n, seed=77, wiring=wiring, engine=FULL, precision=FP32)
+        q = eng.run(p, n, seed=77, wiring=wiring, engine=PREFIX, precision=FP32)
+        assert np.mean((f.winner == q.winner) & (f.rounds == q.rounds)) > 0.995
+        assert f.winner_hist.sum() == n and f.totals[0, 0] == f.rounds.astype(np.int64).sum()
+        a_ = eng.run(p, 70_000, seed=77, sim_id_begin=0, wiring=wiring, engine=FULL, precision=FP32)
+        b_ = eng.run(p, n - 70_000, seed=77, sim_id_begin=70_000, wiring=wiring, engine=FULL, precision=FP32)
+        assert np.array_equal(np.concatenate([a_.winner, b_.winner]), f.winner)
+        print(f"full32 wiring {wiring}: {n} trials in {f.kernel_ms:.2f} ms = {f.elector_rounds / (f.kernel_ms * 1e-3):.3e} elector-rounds/s")
