@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--full", action="store_true")
     a = ap.parse_args()
-    from conclave_sim_b200 import Engine, make_params, FP32, FP64, WIRING_REF_CLI, WIRING_MODEL, ENGINE_DENSE, ENGINE_TABLE, ENGINE_PREFIX
+    from conclave_sim_b200 import Engine, make_params, FP32, FP64, WIRING_REF_CLI, WIRING_MODEL, ENGINE_DENSE, ENGINE_TABLE, ENGINE_PREFIX, ENGINE_FULL
     eng = Engine(0)
     out = []
 
@@ -43,7 +43,7 @@ def main():
         trials = n * len(sets)
         rec = dict(config=name, E=E, param_sets=len(sets), trials=trials,
                    wiring="ref_cli" if wiring == WIRING_REF_CLI else "model",
-                   engine={ENGINE_DENSE: "dense", ENGINE_TABLE: "table", ENGINE_PREFIX: "prefix"}[engine], precision="fp32" if precision == FP32 else "fp64",
+                   engine={ENGINE_DENSE: "dense", ENGINE_TABLE: "table", ENGINE_PREFIX: "prefix", ENGINE_FULL: "full"}[engine], precision="fp32" if precision == FP32 else "fp64",
                    wall_s=best, kernel_ms=r.kernel_ms, conclaves_per_s=trials / best, elector_rounds_per_s=r.elector_rounds / best,
                    success_rate=float((r.winner >= 0).mean()), mean_rounds=float(r.rounds.mean()))
         out.append(rec)
@@ -60,6 +60,10 @@ def main():
     run("cfg2 README x1000 (fp64 exact)", 134, [cfg2], 1000, WIRING_REF_CLI, ENGINE_TABLE, FP64)
     for eng_id in (ENGINE_DENSE, ENGINE_PREFIX):
         run("cfg3 model wiring x1.25M", 134, [cfg2], 125_000 if a.quick else 1_250_000, WIRING_MODEL, eng_id, FP32)
+    cfg2x = make_params(dict(CFG2, stop_candidate_threshold_unacceptable_distance=0.3), max_rounds=20, supermajority_threshold=0.56,
+                        enable_candidate_fatigue=True, enable_stop_candidate=True)
+    run("cfg3 model wiring + fatigue + stop-candidate x250k", 134, [cfg2x], 25_000 if a.quick else 250_000, WIRING_MODEL, ENGINE_FULL, FP32)
+    run("cfg3 model wiring + fatigue + stop-candidate x25k (fp64 exact)", 134, [cfg2x], 25_000, WIRING_MODEL, ENGINE_DENSE, FP64, reps=1)
     # cfg-4: SURVEY 8d grid
     grid = list(itertools.product([0.5, 1.0, 1.5, 2.0], [0.0, 0.1, 0.3, 0.5], [1.0, 1.5, 2.0, 3.0], [0.5, 0.56, 0.6, 2 / 3]))
     sets = [make_params(dict(CFG2, initial_beta_weight=b0, beta_increment_amount=db, papabile_weight_factor=pw),
