@@ -511,9 +511,14 @@ static bool prefix_supported(const csim_ctx* c, const csim_run_args* ra, const s
     for (const DevSet& s : hs) if (s.en_fat || s.en_stop) return false;
     for (int i = 0; i < ra->n_param_sets; ++i)
         if (ra->params[i].regional_affinity_bonus < 0 || ra->params[i].bandwagon_strength < 0 || ra->params[i].papabile_weight_factor < 0) return false;
-    if (c->G > 64 || c->E >= 32768) return false;
+    if (c->E >= 32768) return false;
     if (R > 0 && (size_t)ra->n_param_sets * R > 65535) return false;
-    return true;
+    int kmax = 1;
+    for (const DevSet& s : hs) kmax = std::max(kmax, s.k);
+    PrefixArgs probe;                                        // does it fit at all? (many regions make the bonus table large)
+    memset(&probe, 0, sizeof probe);
+    return prefix_plan(probe, c->E, c->G, R, std::max(R, 1), kmax, ra->wiring == CSIM_WIRING_MODEL,
+                       (size_t)c->prop.sharedMemPerBlockOptin - 64, true);
 }
 
 static csim_status launch_prefix(csim_ctx* c, const csim_run_args* ra, const std::vector<DevSet>& hs, const BatchDev& b,
@@ -526,7 +531,6 @@ static csim_status launch_prefix(csim_ctx* c, const csim_run_args* ra, const std
             return fail(CSIM_ERR_UNSUPPORTED, "negative bonus / strength / papabile factor: use CSIM_FP64 precision");
     if (ra->precision != CSIM_FP32) return fail(CSIM_ERR_UNSUPPORTED, "the prefix engine is an fp32 engine (use DENSE or TABLE with CSIM_FP64)");
     const int E = c->E, R = b.R;
-    if (c->G > 64) return fail(CSIM_ERR_UNSUPPORTED, "%d distinct regions (> 64): use CSIM_FP64 precision", c->G);
     if (E >= 32768) return fail(CSIM_ERR_UNSUPPORTED, "prefix engine: at most 32767 electors");
     if (R > 0 && (size_t)b.n_sets * R > 65535) return fail(CSIM_ERR_UNSUPPORTED, "n_param_sets * max_rounds exceeds 65535");
     const bool model = ra->wiring == CSIM_WIRING_MODEL;
@@ -575,7 +579,6 @@ static csim_status launch_full32(csim_ctx* c, const csim_run_args* ra, const std
             ra->params[i].fatigue_penalty_factor < 0 || ra->params[i].stop_candidate_boost_factor < 0)
             return fail(CSIM_ERR_UNSUPPORTED, "negative bonus / strength / papabile / fatigue / boost factor: use CSIM_FP64 precision");
     const int E = c->E, R = b.R;
-    if (c->G > 64) return fail(CSIM_ERR_UNSUPPORTED, "%d distinct regions (> 64): use CSIM_FP64 precision", c->G);
     if (E >= 32768) return fail(CSIM_ERR_UNSUPPORTED, "full engine: at most 32767 electors");
     Full32Args a;
     memset(&a, 0, sizeof a);
@@ -609,8 +612,8 @@ static csim_status launch_full32(csim_ctx* c, const csim_run_args* ra, const std
 extern "C" csim_status csim_prefix_plan_query(int32_t n_electors, int32_t n_regions, int32_t max_rounds, int32_t table_rounds, int32_t kmax,
                                               int32_t wiring, uint64_t smem_budget, int32_t allow_stage, csim_prefix_plan* out) {
     if (!out) return fail(CSIM_ERR_INVALID, "csim_prefix_plan_query: out is NULL");
-    if (n_electors < 1 || n_electors >= 32768 || n_regions < 1 || n_regions > 64 || max_rounds < 0 || kmax < 0)
-        return fail(CSIM_ERR_INVALID, "csim_prefix_plan_query: need 1 <= electors < 32768, 1 <= regions <= 64, rounds >= 0, kmax >= 0");
+    if (n_electors < 1 || n_electors >= 32768 || n_regions < 1 || n_regions > n_electors || max_rounds < 0 || kmax < 0)
+        return fail(CSIM_ERR_INVALID, "csim_prefix_plan_query: need 1 <= electors < 32768, 1 <= regions <= electors, rounds >= 0, kmax >= 0");
     PrefixArgs a;
     memset(&a, 0, sizeof a);
     memset(out, 0, sizeof *out);
@@ -711,7 +714,8 @@ extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
         bool extras = false;                                     // candidate fatigue / stop-candidate live (model wiring only)
         for (const DevSet& s : hs) extras = extras || s.en_fat || s.en_stop;
         if (ra->wiring == CSIM_WIRING_MODEL) {
-            engine = pfx_ok ? CSIM_ENGINE_PREFIX : ((extras && ra->precision == CSIM_FP32) ? CSIM_ENGINE_FULL : CSIM_ENGINE_DENSE);
+            // (DENSE is the MUFU / factorised two-phase kernel: bandwagon + stickiness only, at most 64 regions)
+            engine = pfx_ok ? CSIM_ENGINE_PREFIX : ((ra->precision == CSIM_FP32 && (extras || c->G > 64)) ? CSIM_ENGINE_FULL : CSIM_ENGINE_DENSE);
         } else {
             const uint64_t n_sb = ((ra->n_sims + (uint64_t)CSIM_TABLE_WPC * 32 - 1) / ((uint64_t)CSIM_TABLE_WPC * 32)) * ra->n_param_sets;
             if (ra->precision == CSIM_FP64) engine = CSIM_ENGINE_TABLE;

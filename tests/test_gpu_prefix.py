@@ -443,3 +443,26 @@ def test_full_engine_without_extras_equals_prefix_and_scales(eng):
         b_ = eng.run(p, n - 70_000, seed=77, sim_id_begin=70_000, wiring=wiring, engine=FULL, precision=FP32)
         assert np.array_equal(np.concatenate([a_.winner, b_.winner]), f.winner)
         print(f"full32 wiring {wiring}: {n} trials in {f.kernel_ms:.2f} ms = {f.elector_rounds / (f.kernel_ms * 1e-3):.3e} elector-rounds/s")
+
+
+def test_many_regions(eng):
+    """More than 64 distinct regions (a roster keyed by country, say): the two-phase dense fp32 kernel does not take it,
+    the PREFIX / FULL engines (and AUTO, which must route around DENSE) do; checked against the oracle."""
+    from conclave_sim_b200 import FP32, CsimError
+    E = 120
+    base = O.synthetic_roster(E, seed=5)
+    region = (np.arange(E) * 7 % 97).astype(np.int32)            # 97 distinct codes among 120 electors
+    roster = O.Roster.from_arrays(base.ideology, region, base.papabile)
+    assert len(np.unique(roster.region)) == 97
+    upload(eng, roster)
+    mp = O.ModelParams(**CFG2)
+    ep = O.EngineParams(max_rounds=12, supermajority_threshold=0.56)
+    p = [to_params(mp, ep)]
+    n = 1000
+    for wiring in (O.WIRING_REF_CLI, O.WIRING_MODEL):
+        ref = CO.run(roster, [(mp, ep)], wiring, n, seed=6)
+        for en in (PREFIX, FULL, 0):
+            out = eng.run(p, n, seed=6, wiring=wiring, engine=en, precision=FP32)
+            assert np.mean((out.winner == ref["winner"]) & (out.rounds == ref["rounds"])) > 0.98, (wiring, en)
+        with pytest.raises(CsimError):
+            eng.run(p, n, seed=6, wiring=wiring, engine=DENSE, precision=FP32)
