@@ -574,10 +574,6 @@ static csim_status launch_prefix(csim_ctx* c, const csim_run_args* ra, const std
 static csim_status launch_full32(csim_ctx* c, const csim_run_args* ra, const std::vector<DevSet>& hs, const BatchDev& b,
                                  const TrialOut& out, cudaStream_t st) {
     if (ra->precision != CSIM_FP32) return fail(CSIM_ERR_UNSUPPORTED, "the full engine is an fp32 engine (CSIM_FP64: use DENSE)");
-    for (int i = 0; i < ra->n_param_sets; ++i)
-        if (ra->params[i].regional_affinity_bonus < 0 || ra->params[i].bandwagon_strength < 0 || ra->params[i].papabile_weight_factor < 0 ||
-            ra->params[i].fatigue_penalty_factor < 0 || ra->params[i].stop_candidate_boost_factor < 0)
-            return fail(CSIM_ERR_UNSUPPORTED, "negative bonus / strength / papabile / fatigue / boost factor: use CSIM_FP64 precision");
     const int E = c->E, R = b.R;
     if (E >= 32768) return fail(CSIM_ERR_UNSUPPORTED, "full engine: at most 32767 electors");
     Full32Args a;
@@ -714,13 +710,13 @@ extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
         bool extras = false;                                     // candidate fatigue / stop-candidate live (model wiring only)
         for (const DevSet& s : hs) extras = extras || s.en_fat || s.en_stop;
         if (ra->wiring == CSIM_WIRING_MODEL) {
-            // (DENSE is the MUFU / factorised two-phase kernel: bandwagon + stickiness only, at most 64 regions)
-            engine = pfx_ok ? CSIM_ENGINE_PREFIX : ((ra->precision == CSIM_FP32 && (extras || c->G > 64)) ? CSIM_ENGINE_FULL : CSIM_ENGINE_DENSE);
+            // (FULL takes everything PREFIX refuses: fatigue / stop-candidate, negative factors; DENSE in fp32 is explicit-only)
+            engine = pfx_ok ? CSIM_ENGINE_PREFIX : (ra->precision == CSIM_FP32 ? CSIM_ENGINE_FULL : CSIM_ENGINE_DENSE);
         } else {
             const uint64_t n_sb = ((ra->n_sims + (uint64_t)CSIM_TABLE_WPC * 32 - 1) / ((uint64_t)CSIM_TABLE_WPC * 32)) * ra->n_param_sets;
             if (ra->precision == CSIM_FP64) engine = CSIM_ENGINE_TABLE;
             else if (E > 256) engine = pfx_ok ? CSIM_ENGINE_PREFIX : CSIM_ENGINE_TABLE;
-            else engine = n_sb >= (uint64_t)c->prop.multiProcessorCount / 2 ? CSIM_ENGINE_TABLE : (pfx_ok ? CSIM_ENGINE_PREFIX : CSIM_ENGINE_DENSE);
+            else engine = n_sb >= (uint64_t)c->prop.multiProcessorCount / 2 ? CSIM_ENGINE_TABLE : (pfx_ok ? CSIM_ENGINE_PREFIX : CSIM_ENGINE_FULL);
         }
     }
     csim_status s = engine == CSIM_ENGINE_FULL ? launch_full32(c, ra, hs, b, out, st)

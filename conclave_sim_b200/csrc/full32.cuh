@@ -14,6 +14,9 @@
 //
 // The fatigue set and the stop-candidate trigger are decided in fp64 exactly as the exact engine decides them
 // (exact64.cuh), so both engines fatigue / boost the same candidates; only the scores themselves are fp32.
+// Both clamps of the model (max(s, 0) after stickiness and at the end, model.py:369,427) are applied, so negative
+// bonus / bandwagon / papabile / penalty / boost factors — which the table-based engines refuse — are taken too: this is
+// the fp32 engine of last resort.
 #pragma once
 #include "common.cuh"
 #include "prefix.cuh"      // prefix_slot: the same dealing of electors to lanes
@@ -113,7 +116,7 @@ __device__ __forceinline__ void full32_score8(const Full32Ctx& k, int blk, int e
         }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) if (is == i) v[i] = 0.0f;                                 // no self vote
+    for (int i = 0; i < 8; ++i) v[i] = (is == i) ? 0.0f : fmaxf(v[i], 0.0f);              // no self vote; final clamp (model.py:424-427)
 }
 
 __device__ __forceinline__ float full32_score1(const Full32Ctx& k, int c, int e, float xe, double xe64, const float* rbrow, int prev, bool trig) {
@@ -121,7 +124,7 @@ __device__ __forceinline__ float full32_score1(const Full32Ctx& k, int c, int e,
     if (c == prev) s *= k.st1p;
     s = fmaxf(s, 0.0f) * k.phi[c];
     if (trig && !(fabs(xe64 - k.x64[c]) > k.stop_D)) s *= k.boost;
-    return c == e ? 0.0f : s;
+    return c == e ? 0.0f : fmaxf(s, 0.0f);
 }
 
 __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const __grid_constant__ Full32Args a) {

@@ -466,3 +466,27 @@ def test_many_regions(eng):
             assert np.mean((out.winner == ref["winner"]) & (out.rounds == ref["rounds"])) > 0.98, (wiring, en)
         with pytest.raises(CsimError):
             eng.run(p, n, seed=6, wiring=wiring, engine=DENSE, precision=FP32)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(regional_affinity_bonus=-0.05), dict(bandwagon_strength=-0.4), dict(papabile_weight_factor=-1.0, regional_affinity_bonus=0.3),
+    dict(regional_affinity_bonus=-0.2, bandwagon_strength=-0.3, enable_candidate_fatigue=True, fatigue_penalty_factor=-0.5),
+], ids=lambda d: ",".join(f"{k}={v}" for k, v in d.items()))
+def test_negative_factors_go_to_the_full_engine(eng, kw):
+    """Negative bonus / bandwagon / papabile / penalty factors make scores negative before the model's clamps (model.py:369,427):
+    the table-based engines refuse them, AUTO sends them to FULL, which follows the fp64 oracle."""
+    from conclave_sim_b200 import FP32, CsimError
+    roster = G.real_roster()
+    upload(eng, roster)
+    mp = O.ModelParams(**dict(CFG2, **kw))
+    ep = O.EngineParams(max_rounds=12, supermajority_threshold=0.56, enable_candidate_fatigue=bool(kw.get("enable_candidate_fatigue")),
+                        fatigue_threshold_rounds=2)
+    n = 800
+    for wiring in (O.WIRING_MODEL, O.WIRING_REF_CLI):
+        ref = CO.run(roster, [(mp, ep)], wiring, n, seed=12)
+        out = eng.run([to_params(mp, ep)], n, seed=12, wiring=wiring, precision=FP32)          # AUTO
+        full = eng.run([to_params(mp, ep)], n, seed=12, wiring=wiring, engine=FULL, precision=FP32)
+        assert np.array_equal(out.winner, full.winner) and np.array_equal(out.rounds, full.rounds)
+        assert np.mean((full.winner == ref["winner"]) & (full.rounds == ref["rounds"])) > 0.97, (kw, wiring)
+        with pytest.raises(CsimError):
+            eng.run([to_params(mp, ep)], n, seed=12, wiring=wiring, engine=PREFIX, precision=FP32)
