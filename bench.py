@@ -179,7 +179,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from conclave_sim_b200 import Engine, make_params, FP32, WIRING_REF_CLI, WIRING_MODEL, ENGINE_DENSE, ENGINE_TABLE, ENGINE_PREFIX
+    from conclave_sim_b200 import Engine, make_params, FP32, WIRING_REF_CLI, WIRING_MODEL, ENGINE_DENSE, ENGINE_TABLE, ENGINE_PREFIX, ENGINE_FULL
     from conclave_sim_b200.dist import DeviceBatch, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -211,9 +211,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(i: int, reduce: bool = True, engine: int = ENGINE_DENSE, wiring: int = WIRING_REF_CLI):
+    def step(i: int, reduce: bool = True, engine: int = ENGINE_DENSE, wiring: int = WIRING_REF_CLI, p=None):
         begin, _ = shard_range(n_global, rank, world)
-        batch.run([params], sim_id_begin=i * n_global + begin, seed=SEED, wiring=wiring,
+        batch.run([params if p is None else p], sim_id_begin=i * n_global + begin, seed=SEED, wiring=wiring,
                   engine=engine, precision=FP32, reduce=reduce)
 
     for i in range(args.warmup):
@@ -285,16 +285,16 @@ def main():
 
     # ---- the other engines on the same workload, reported SEPARATELY from the dense kernel's value / roofline
     #      (never mixed): same steps, same L2 flush, CUDA events, max over ranks
-    def timed_engine(engine: int, wiring: int, base: int):
+    def timed_engine(engine: int, wiring: int, base: int, p=None):
         for i in range(2):
-            step(base + i, engine=engine, wiring=wiring)
+            step(base + i, engine=engine, wiring=wiring, p=p)
         barrier()
         tev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         t_rounds, k_ms = 0, 0.0
         for i in range(args.steps):
             flush.zero_()
             tev[i][0].record()
-            step(base + 2 + i, engine=engine, wiring=wiring)
+            step(base + 2 + i, engine=engine, wiring=wiring, p=p)
             tev[i][1].record()
             tev[i][1].synchronize()
             k_ms += eng.stats()[1]
@@ -318,6 +318,13 @@ def main():
                      "note": "trial-invariant chunk-prefix tables + per-trial bandwagon / stickiness corrections: a draw is a binary "
                              "search over 17 chunk prefixes and a re-scan of one chunk of 8 candidates; both wirings; what "
                              "ENGINE_AUTO picks for the `model` wiring.  NOT comparable with the dense roofline"}
+    params_x = make_params(dict(CFG2, stop_candidate_threshold_unacceptable_distance=0.3), enable_candidate_fatigue=True,
+                           enable_stop_candidate=True, **ENGINE_KW)
+    full_engine = timed_engine(ENGINE_FULL, WIRING_MODEL, 900, p=params_x)
+    full_engine.update(kernel="k_trials_full32",
+                       note="`model` wiring with EVERY term live: cfg-2 parameters + candidate fatigue (3 rounds below 5 %) + stop-candidate "
+                            "(unacceptable distance 0.3): all E x C scores inline per trial per round; the engine ENGINE_AUTO picks for what the "
+                            "table-based engines refuse (these terms used to run on the fp64 exact kernel only, 3.5e5 conclaves/s)")
     model_wiring_dense = timed_engine(ENGINE_DENSE, WIRING_MODEL, 800)
     model_wiring_dense.update(kernel="k_trials_dense32<LC=8,MODEL=true,FACT=true>",
                               note="`model` wiring (bandwagon + stickiness live, SURVEY 8f.1) on the dense kernel, for comparison")
@@ -398,6 +405,7 @@ def main():
                 "steps": e2e_steps, "api": "conclave_sim_b200.Engine.run (host buffers; results land in page-locked arrays) -> csim_run"},
         "table_engine": table_engine,
         "prefix_engine": prefix_engine,
+        "full_engine": full_engine,
         "model_wiring_dense": model_wiring_dense,
         "gpu_launches": int(launches1 - launches0),
         "clocks": clocks,
