@@ -585,9 +585,18 @@ static csim_status launch_full32(csim_ctx* c, const csim_run_args* ra, const std
     a.ro = roster_dev(c); a.b = b; a.out = out; a.nbeta = (const float*)c->nbeta.p;
     const int wpc = a.warps_per_cta;
     const size_t smem = a.cta_smem + a.warp_smem * wpc;
-    CU_TRY(cudaFuncSetAttribute(k_trials_full32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bool ext = false, neg = false;                            // which terms the batch needs decides the instantiation
+    for (const DevSet& s : hs) ext = ext || s.en_fat || s.en_stop;
+    for (int i = 0; i < ra->n_param_sets; ++i) {
+        const csim_params& q = ra->params[i];
+        neg = neg || q.regional_affinity_bonus < 0 || q.bandwagon_strength < 0 || q.papabile_weight_factor < 0 || q.stickiness_factor < -1 ||
+              q.fatigue_penalty_factor < 0 || q.stop_candidate_boost_factor < 0;
+    }
+    void (*kern)(Full32Args) = ext ? (neg ? k_trials_full32<true, true> : k_trials_full32<true, false>)
+                                   : (neg ? k_trials_full32<false, true> : k_trials_full32<false, false>);
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trials_full32, wpc * 32, smem));
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpc * 32, smem));
     if (per_sm < 1) return fail(CSIM_ERR_UNSUPPORTED, "full kernel does not fit on an SM (threads=%d, smem=%zu)", wpc * 32, smem);
     const uint64_t ctas = (uint64_t)c->prop.multiProcessorCount * per_sm;
     uint64_t tpi = a.b.n_sims / ((uint64_t)wpc * ctas * 8);
@@ -597,7 +606,7 @@ static csim_status launch_full32(csim_ctx* c, const csim_run_args* ra, const std
     const uint64_t n_items = ((a.b.n_sims + per_item - 1) / per_item) * a.b.n_sets;
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_items, ctas));
     CU_TRY(cudaEventRecord(c->ev0, st));
-    k_trials_full32<<<grid, wpc * 32, smem, st>>>(a);
+    kern<<<grid, wpc * 32, smem, st>>>(a);
     CU_TRY(cudaEventRecord(c->ev1, st));
     c->ev_valid = true;
     ++c->launches;

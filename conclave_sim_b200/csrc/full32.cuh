@@ -86,7 +86,11 @@ struct Full32Ctx {          // what one score needs (per warp / per round)
     int C;
 };
 
-// the 8 scores of block `blk` of elector e's row, every term inline in the order of model.py:311-424
+// The 8 scores of block `blk` of elector e's row, every term inline in the order of model.py:311-427.
+//   RAW  pass 1: stickiness and the self vote are NOT applied per candidate (two compares per pair saved); the caller fixes the
+//        running prefix at the chunks of prev and of e with the exact differences (full32_score1 with / without them)
+//   EXT  candidate fatigue / stop-candidate live for this batch;  NEG  some factor is negative: the model's clamps matter
+template <bool RAW, bool EXT, bool NEG>
 __device__ __forceinline__ void full32_score8(const Full32Ctx& k, int blk, int e, float xe, double xe64, const float* rbrow, int prev, bool trig,
                                               float (&v)[8]) {
     const int cb = blk << 3;
@@ -94,39 +98,54 @@ __device__ __forceinline__ void full32_score8(const Full32Ctx& k, int blk, int e
     const float4 pa = *reinterpret_cast<const float4*>(k.pw + cb), pb = *reinterpret_cast<const float4*>(k.pw + cb + 4);
     const float4 ra = *reinterpret_cast<const float4*>(rbrow + cb), rb = *reinterpret_cast<const float4*>(rbrow + cb + 4);
     const float4 ba = *reinterpret_cast<const float4*>(k.bw + cb), bb = *reinterpret_cast<const float4*>(k.bw + cb + 4);
-    const float4 fa = *reinterpret_cast<const float4*>(k.phi + cb), fb = *reinterpret_cast<const float4*>(k.phi + cb + 4);
     const float x8[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
     const float p8[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
     const float r8[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
     const float b8[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-    const float f8[8] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w};
     const int is = e - cb, ip = prev - cb;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         float s = fmaf(ex2_approx(fabsf(xe - x8[i]) * k.nb), p8[i], r8[i]) + b8[i];     // exp, papabile, regional, bandwagon
-        if (ip == i) s *= k.st1p;                                                         // stickiness
-        s = fmaxf(s, 0.0f) * f8[i];                                                       // clamp, fatigue
+        if (!RAW && ip == i) s *= k.st1p;                                                 // stickiness
+        if (NEG) s = fmaxf(s, 0.0f);                                                      // clamp (model.py:369)
         v[i] = s;
     }
-    if (trig) {                                                                           // stop-candidate: boost the acceptable ones
+    if (EXT) {
+        const float4 fa = *reinterpret_cast<const float4*>(k.phi + cb), fb = *reinterpret_cast<const float4*>(k.phi + cb + 4);
+        const float f8[8] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = min(cb + i, k.C - 1);
-            if (!(fabs(xe64 - k.x64[c]) > k.stop_D)) v[i] *= k.boost;
+        for (int i = 0; i < 8; ++i) v[i] *= f8[i];                                        // fatigue
+        if (trig) {                                                                       // stop-candidate: boost the acceptable ones
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int c = min(cb + i, k.C - 1);
+                if (!(fabs(xe64 - k.x64[c]) > k.stop_D)) v[i] *= k.boost;      // acceptable <=> not (|dx| > D), fp64 as model.py:390
+            }
         }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = (is == i) ? 0.0f : fmaxf(v[i], 0.0f);              // no self vote; final clamp (model.py:424-427)
+    for (int i = 0; i < 8; ++i) {
+        if (!RAW && is == i) v[i] = 0.0f;                                                 // no self vote
+        else if (NEG) v[i] = fmaxf(v[i], 0.0f);                                           // final clamp (model.py:427)
+    }
 }
 
-__device__ __forceinline__ float full32_score1(const Full32Ctx& k, int c, int e, float xe, double xe64, const float* rbrow, int prev, bool trig) {
+// one score; `sticky` / `self` say whether those two point rules are applied (pass 1 needs the difference they make)
+template <bool EXT, bool NEG>
+__device__ __forceinline__ float full32_score1(const Full32Ctx& k, int c, int e, float xe, double xe64, const float* rbrow, int prev, bool trig,
+                                               bool sticky = true, bool self = true) {
     float s = fmaf(ex2_approx(fabsf(xe - k.xs[c]) * k.nb), k.pw[c], rbrow[c]) + k.bw[c];
-    if (c == prev) s *= k.st1p;
-    s = fmaxf(s, 0.0f) * k.phi[c];
-    if (trig && !(fabs(xe64 - k.x64[c]) > k.stop_D)) s *= k.boost;
-    return c == e ? 0.0f : fmaxf(s, 0.0f);
+    if (sticky && c == prev) s *= k.st1p;
+    if (NEG) s = fmaxf(s, 0.0f);
+    if (EXT) {
+        s *= k.phi[c];
+        if (trig && !(fabs(xe64 - k.x64[c]) > k.stop_D)) s *= k.boost;
+    }
+    if (self && c == e) return 0.0f;
+    return NEG ? fmaxf(s, 0.0f) : s;
 }
 
+template <bool EXT, bool NEG>
 __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const __grid_constant__ Full32Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -312,16 +331,27 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
                     int vote;
                     if (!have_eff) {
                         // ---- pass 1: the whole row, running prefix per chunk into this lane's column ----------
+                        // the point rules enter the prefix at the chunks of e and of prev, as exact differences
+                        const int je = (e >> 3) / Lb;
+                        const float d_self = -full32_score1<EXT, NEG>(kx, e, e, xe, xe64, rbrow, -1, trig, false, false);
+                        int jp = -1;
+                        float d_prev = 0.0f;
+                        if (prev >= 0 && prev != e) {
+                            jp = (prev >> 3) / Lb;
+                            d_prev = full32_score1<EXT, NEG>(kx, prev, e, xe, xe64, rbrow, prev, trig, true, false) -
+                                     full32_score1<EXT, NEG>(kx, prev, e, xe, xe64, rbrow, prev, trig, false, false);
+                        }
                         float run = 0.0f;
                         for (int j = 0; j < nch; ++j) {
                             for (int b = 0; b < Lb; ++b) {
                                 const int blk = j * Lb + b;
                                 if (blk >= nblk) break;
                                 float v[8];
-                                full32_score8(kx, blk, e, xe, xe64, rbrow, prev, trig, v);
-#pragma unroll
-                                for (int q = 0; q < 8; ++q) run += v[q];
+                                full32_score8<true, EXT, NEG>(kx, blk, e, xe, xe64, rbrow, prev, trig, v);
+                                run += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
                             }
+                            if (j == je) run += d_self;
+                            if (j == jp) run += d_prev;
                             col[32 * j] = run;
                         }
                         const float Sm = run;
@@ -347,7 +377,7 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
                                 const int blk = blk0 + b;
                                 if (blk >= nblk) break;
                                 float v[8];
-                                full32_score8(kx, blk, e, xe, xe64, rbrow, prev, trig, v);
+                                full32_score8<false, EXT, NEG>(kx, blk, e, xe, xe64, rbrow, prev, trig, v);
 #pragma unroll
                                 for (int q = 0; q < 8; ++q) { cum += v[q]; cnt += (cum <= tgt) ? 1 : 0; }
                                 if (cnt < 8 * (b + 1)) break;
@@ -360,7 +390,7 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
                     } else {
                         // ---- run-off round: first k columns, renormalised (simulate.py:144-154) --------------
                         float sum = 0.f;
-                        for (int j = 0; j < k; ++j) sum += full32_score1(kx, j, e, xe, xe64, rbrow, prev, trig);
+                        for (int j = 0; j < k; ++j) sum += full32_score1<EXT, NEG>(kx, j, e, xe, xe64, rbrow, prev, trig);
                         int jsel;
                         if (!(sum > 0.0f)) {
                             jsel = (int)(u * (float)k);
@@ -368,7 +398,7 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
                             const float tgt = u * sum;
                             float cum = 0.f; jsel = -1; int lastpos = 0;
                             for (int j = 0; j < k; ++j) {
-                                const float v = full32_score1(kx, j, e, xe, xe64, rbrow, prev, trig);
+                                const float v = full32_score1<EXT, NEG>(kx, j, e, xe, xe64, rbrow, prev, trig);
                                 cum += v;
                                 if (v > 0.0f) lastpos = j;
                                 if (jsel < 0 && v > 0.0f && cum > tgt) jsel = j;
