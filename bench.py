@@ -366,28 +366,33 @@ def main():
     from conclave_sim_b200 import simulate as S
     df = pd.DataFrame({"ideology_score": ideology, "region": region, "is_papabile": pap},
                       index=pd.Index([str(i) for i in range(E)], name="elector_id"))
-    S.RUNTIME.update(seed=SEED, device=local_rank, precision="fp32", engine="auto", wiring="ref_cli")
     api_kw = dict(max_rounds=R, supermajority_threshold=ENGINE_KW["supermajority_threshold"], runoff_threshold_rounds=rr,
                   runoff_candidate_count=k)
-    S.run_simulations(df, CFG2, n_local, sim_id_begin=begin, **api_kw)
-    barrier()
-    t0 = time.perf_counter()
-    api_rounds = 0
-    for i in range(e2e_steps):
-        eng_api = S.get_engine(local_rank)
-        eng_api._roster_key = None
-        r = S.run_simulations(df, CFG2, n_local, sim_id_begin=(2000 + i) * n_global + begin, **api_kw)
-        api_rounds += int(r.totals[0, 0])
-    barrier()
-    api_s = time.perf_counter() - t0
-    ta = torch.tensor([api_s, float(api_rounds)], dtype=torch.float64, device=dev)
-    if world > 1:
-        a = ta.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
-        b = ta.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
-        api_s, api_rounds = a[0].item(), b[1].item()
-    table_engine["e2e_default_api"] = {"value": api_rounds * E / api_s, "unit": "elector-rounds/s",
-                                       "conclaves_per_sec": n_global * e2e_steps / api_s,
-                                       "api": "conclave_sim_b200.simulate.run_simulations(DataFrame, ...) with default engine"}
+
+    def api_e2e(wiring: str, base: int):
+        """run_simulations(DataFrame, ...) with the default engine, roster re-uploaded every step, results on the host"""
+        S.RUNTIME.update(seed=SEED, device=local_rank, precision="fp32", engine="auto", wiring=wiring)
+        S.run_simulations(df, CFG2, n_local, sim_id_begin=begin, **api_kw)
+        barrier()
+        t0 = time.perf_counter()
+        rounds_sum = 0
+        for i in range(e2e_steps):
+            S.get_engine(local_rank)._roster_key = None
+            r = S.run_simulations(df, CFG2, n_local, sim_id_begin=(base + i) * n_global + begin, **api_kw)
+            rounds_sum += int(r.totals[0, 0])
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt, float(rounds_sum)], dtype=torch.float64, device=dev)
+        if world > 1:
+            a = tt.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
+            b = tt.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
+            dt, rounds_sum = a[0].item(), b[1].item()
+        return {"value": rounds_sum * E / dt, "unit": "elector-rounds/s", "conclaves_per_sec": n_global * e2e_steps / dt,
+                "api": f"conclave_sim_b200.simulate.run_simulations(DataFrame, ..., wiring='{wiring}') with the default engine"}
+
+    table_engine["e2e_default_api"] = api_e2e("ref_cli", 2000)
+    prefix_engine["model"]["e2e_default_api"] = api_e2e("model", 3000)
+    S.RUNTIME.update(wiring="ref_cli")
     h2d = E * (8 + 4 + 1) + 152 + 20 * 12
     d2h = n_local * 9 + ((E + 1) + (R + 1) + 2) * 8
 

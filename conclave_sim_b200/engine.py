@@ -174,15 +174,15 @@ class Engine:
         def _take(name, dtype):
             a = None if out is None else out.get(name)
             if a is None:
-                return np.zeros(n, dtype)
+                return np.empty(n, dtype)          # every entry is written by the device-to-host copy
             if a.dtype != dtype or a.shape != (n,) or not a.flags.c_contiguous:
                 raise ValueError(f"out['{name}'] must be a contiguous {np.dtype(dtype).name} array of shape ({n},)")
             return a
         winner = _take("winner", np.int32)
         rounds = _take("rounds", np.int32)
         reason = _take("reason", np.uint8) if want_reason else None
-        final = np.zeros((n, E), np.int32) if want_final_votes else None
-        tall = np.zeros((n, R, E), np.int32) if want_round_tallies else None
+        final = np.empty((n, E), np.int32) if want_final_votes else None
+        tall = np.empty((n, R, E), np.int32) if want_round_tallies else None
         wh = np.zeros((len(param_sets), E + 1), np.int64)
         rh = np.zeros((len(param_sets), R + 1), np.int64)
         tot = np.zeros((len(param_sets), 2), np.int64)
