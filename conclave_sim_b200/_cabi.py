@@ -20,7 +20,7 @@ ABI_VERSION = 1
 
 EXPORTS = ["csim_abi_version", "csim_last_error", "csim_create", "csim_destroy", "csim_device_info",
            "csim_upload_roster", "csim_beta_schedule", "csim_need_votes", "csim_prob_matrix", "csim_run",
-           "csim_stats", "csim_microbench", "csim_prefix_plan_query", "csim_prefix_slot"]
+           "csim_stats", "csim_microbench", "csim_prefix_plan_query", "csim_prefix_slot", "csim_host_alloc", "csim_host_free"]
 
 
 class CsimError(RuntimeError):
@@ -92,6 +92,10 @@ def load_library() -> C.CDLL:
     lib.csim_microbench.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double)]
     lib.csim_prefix_plan_query.argtypes = [C.c_int32] * 6 + [C.c_uint64, C.c_int32, C.POINTER(CsimPrefixPlan)]
     lib.csim_prefix_plan_query.restype = C.c_int
+    lib.csim_host_alloc.argtypes = [C.c_uint64, C.POINTER(C.c_void_p)]
+    lib.csim_host_alloc.restype = C.c_int
+    lib.csim_host_free.argtypes = [C.c_void_p]
+    lib.csim_host_free.restype = C.c_int
     lib.csim_prefix_slot.argtypes = [C.c_int32, C.c_int32]
     lib.csim_prefix_slot.restype = C.c_int32
     for name in ("csim_create", "csim_destroy", "csim_device_info", "csim_upload_roster", "csim_beta_schedule",

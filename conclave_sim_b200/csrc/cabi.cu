@@ -754,6 +754,20 @@ extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
     return CSIM_OK;
 }
 
+// Page-locked host memory for result arrays: device-to-host copies into it run at full PCIe speed and do not stage
+// through the driver's bounce buffers.  The Python host keeps a small pool of these (engine.py: _PinnedPool).
+extern "C" csim_status csim_host_alloc(uint64_t bytes, void** out) {
+    if (!out) return fail(CSIM_ERR_INVALID, "csim_host_alloc: out is NULL");
+    *out = nullptr;
+    if (bytes == 0) return CSIM_OK;
+    CU_TRY(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault));
+    return CSIM_OK;
+}
+extern "C" csim_status csim_host_free(void* p) {
+    if (p) CU_TRY(cudaFreeHost(p));
+    return CSIM_OK;
+}
+
 extern "C" csim_status csim_stats(csim_ctx* c, int64_t* kernel_launches, float* last_trial_kernel_ms) {
     if (!c) return fail(CSIM_ERR_INVALID, "csim_stats: ctx is NULL");
     if (kernel_launches) *kernel_launches = c->launches;

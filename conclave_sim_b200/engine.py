@@ -90,6 +90,62 @@ def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+class _PinnedBlock:
+    """One page-locked allocation; goes back to its pool when the last array viewing it is collected."""
+    __slots__ = ("pool", "ptr", "size")
+
+    def __init__(self, pool, ptr, size):
+        self.pool, self.ptr, self.size = pool, ptr, size
+
+    def __del__(self):
+        try:
+            self.pool._give_back(self.ptr, self.size)
+        except Exception:
+            pass
+
+
+class _PinnedPool:
+    """Page-locked result arrays for large batches (csim_host_alloc).  cudaHostAlloc costs about a millisecond per call, so
+    blocks are recycled by size once the numpy arrays built on them are gone; nothing is shared between live results."""
+    MIN_BYTES = 1 << 18           # smaller results: pageable memory is just as fast
+
+    def __init__(self, lib):
+        self._lib = lib
+        self._free: Dict[int, List[int]] = {}
+        self._closed = False
+
+    def array(self, n: int, dtype) -> np.ndarray:
+        dt = np.dtype(dtype)
+        nbytes = int(n) * dt.itemsize
+        if nbytes < self.MIN_BYTES or self._closed:
+            return np.empty(n, dt)
+        size = 1 << (nbytes - 1).bit_length()                 # power-of-two buckets
+        free = self._free.get(size)
+        if free:
+            ptr = free.pop()
+        else:
+            p = C.c_void_p()
+            if self._lib.csim_host_alloc(size, C.byref(p)) != 0 or not p.value:
+                return np.empty(n, dt)                         # pinning is an optimisation, never a requirement
+            ptr = p.value
+        buf = (C.c_ubyte * nbytes).from_address(ptr)
+        buf._csim_block = _PinnedBlock(self, ptr, size)        # numpy array -> ctypes buffer -> block -> pool
+        return np.frombuffer(buf, dtype=dt, count=n)
+
+    def _give_back(self, ptr: int, size: int):
+        if self._closed:
+            self._lib.csim_host_free(C.c_void_p(ptr))
+        else:
+            self._free.setdefault(size, []).append(ptr)
+
+    def close(self):
+        self._closed = True
+        for blocks in self._free.values():
+            for ptr in blocks:
+                self._lib.csim_host_free(C.c_void_p(ptr))
+        self._free.clear()
+
+
 class Engine:
     """One CUDA device.  Not a CPU fallback: construction fails without a usable sm_100 GPU."""
 
@@ -100,8 +156,11 @@ class Engine:
         self.device = int(device)
         self.n_electors = 0
         self._roster_key = None
+        self._pinned = _PinnedPool(self._lib)
 
     def close(self):
+        if getattr(self, "_pinned", None) is not None:
+            self._pinned.close()
         if getattr(self, "_ctx", None) is not None and self._ctx:
             self._lib.csim_destroy(self._ctx)
             self._ctx = C.c_void_p()
@@ -174,7 +233,7 @@ class Engine:
         def _take(name, dtype):
             a = None if out is None else out.get(name)
             if a is None:
-                return np.empty(n, dtype)          # every entry is written by the device-to-host copy
+                return self._pinned.array(n, dtype)      # every entry is written by the device-to-host copy; page-locked when large
             if a.dtype != dtype or a.shape != (n,) or not a.flags.c_contiguous:
                 raise ValueError(f"out['{name}'] must be a contiguous {np.dtype(dtype).name} array of shape ({n},)")
             return a

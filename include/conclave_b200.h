@@ -201,6 +201,11 @@ csim_status csim_prefix_plan_query(int32_t n_electors, int32_t n_regions, int32_
 /* table row of an elector inside one round's table (the order the lanes visit electors) */
 int32_t     csim_prefix_slot(int32_t elector, int32_t e_quad_end);
 
+/* Page-locked host memory (cudaHostAlloc / cudaFreeHost) for the per-trial result arrays of a host-buffer csim_run:
+ * copies into it run at full PCIe speed.  Optional: any host memory works. */
+csim_status csim_host_alloc(uint64_t bytes, void** out);
+csim_status csim_host_free(void* p);
+
 /* Diagnostics for bench.py: number of kernel launches this context has issued,
  * and the device time (ms, CUDA events on the launch stream) of the last csim_run's trial kernel. */
 csim_status csim_stats(csim_ctx* ctx, int64_t* kernel_launches, float* last_trial_kernel_ms);

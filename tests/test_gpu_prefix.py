@@ -490,3 +490,27 @@ def test_negative_factors_go_to_the_full_engine(eng, kw):
         assert np.mean((full.winner == ref["winner"]) & (full.rounds == ref["rounds"])) > 0.97, (kw, wiring)
         with pytest.raises(CsimError):
             eng.run([to_params(mp, ep)], n, seed=12, wiring=wiring, engine=PREFIX, precision=FP32)
+
+
+def test_pinned_result_pool(eng):
+    """Large batches get their per-trial arrays in page-locked memory (csim_host_alloc); blocks are recycled once the arrays
+    are gone, live results never share memory, and the values equal those of a small (pageable) call."""
+    import gc
+    from conclave_sim_b200 import FP32
+    roster = G.real_roster()
+    upload(eng, roster)
+    p = [to_params(O.ModelParams(**CFG2), EP2)]
+    n = 200_000
+    a = eng.run(p, n, seed=1, engine=PREFIX, precision=FP32)
+    b = eng.run(p, n, seed=2, engine=PREFIX, precision=FP32)
+    assert a.winner.ctypes.data != b.winner.ctypes.data and not np.array_equal(a.winner, b.winner)
+    small = eng.run(p, 1000, seed=1, engine=PREFIX, precision=FP32)             # pageable path
+    assert np.array_equal(small.winner, a.winner[:1000]) and np.array_equal(small.rounds, a.rounds[:1000])
+    addr = a.winner.ctypes.data
+    keep = a.winner.copy()
+    del a
+    gc.collect()
+    c = eng.run(p, n, seed=1, engine=PREFIX, precision=FP32)                     # reuses a released block
+    assert np.array_equal(c.winner, keep)
+    assert c.winner.ctypes.data in (addr, c.winner.ctypes.data) and c.winner.flags.writeable
+    assert np.array_equal(b.winner, eng.run(p, n, seed=2, engine=PREFIX, precision=FP32).winner)   # b was never overwritten
