@@ -224,6 +224,14 @@ static DevSet make_set(const csim_params* p, int E, int wiring) {
     s.fat_rounds = std::max(0, p->fatigue_threshold_rounds);
     s.fat_top_n = std::max(0, p->fatigue_top_n_immune);
     s.en_stop = model && p->enable_stop_candidate;
+    // the two share tests of the model as integer vote thresholds: v / E in fp64 is monotone in v, so the comparisons the
+    // reference makes on shares (simulate.py:111, model.py:397) are reproduced exactly without a division per candidate
+    int32_t v = 0;
+    while (v <= E && (double)v / (double)E < s.fat_thr) ++v;
+    s.fat_cnt = v;
+    v = 0;
+    while (v <= E && !((double)v / (double)E > s.stop_T)) ++v;
+    s.stop_cnt = v;
     return s;
 }
 

@@ -34,7 +34,8 @@ struct DevSet {
     int32_t fat_rounds;
     int32_t fat_top_n;
     int32_t en_stop;      // stop-candidate live (model wiring only)
-    int32_t pad0, pad1;
+    int32_t fat_cnt;      // smallest vote count v with (double)v / E >= fatigue_vote_share_threshold: share < thr  <=>  votes < fat_cnt
+    int32_t stop_cnt;     // smallest vote count v with (double)v / E >  stop_candidate_threat_min_vote_share: share > T <=> votes >= stop_cnt
 };
 
 struct RosterDev {

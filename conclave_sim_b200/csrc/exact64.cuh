@@ -242,8 +242,8 @@ __global__ void __launch_bounds__(256, CSIM_EXACT_MINB) k_trials_exact64(Exact64
                         for (int c = lane; c < C; c += 32) {
                             if (mark[c]) continue;
                             bool low = true;
-                            for (int q = 0; q < F && low; ++q)
-                                low = __ddiv_rn((double)hist[(size_t)((n_hist - F + q) % a.Fmax) * C + c], (double)E) < S.fat_thr;
+                            for (int q = 0; q < F && low; ++q)      // share < threshold as an exact integer test (DevSet::fat_cnt)
+                                low = hist[(size_t)((n_hist - F + q) % a.Fmax) * C + c] < S.fat_cnt;
                             fat[c] = low ? 1 : 0;
                         }
                         use_fat = true;
@@ -287,9 +287,9 @@ __global__ void __launch_bounds__(256, CSIM_EXACT_MINB) k_trials_exact64(Exact64
                 row.stop_D = S.stop_D; row.stop_boost = S.stop_boost;
                 row.trig = false; row.degenerate = false;
                 if (model && S.en_stop) {                                     // model.py:384-400
-                    for (int q = 0; q < C; ++q) {
-                        const double sh = have_prev ? __ddiv_rn((double)prev_tally[q], (double)E) : 0.0;
-                        if (fabs(row.xe - a.ro.x64[q]) > S.stop_D && sh > S.stop_T) { row.trig = true; break; }
+                    for (int q = 0; q < C; ++q) {                 // share > threshold as an exact integer test (DevSet::stop_cnt)
+                        const bool threat = have_prev ? prev_tally[q] >= S.stop_cnt : 0.0 > S.stop_T;
+                        if (threat && fabs(row.xe - a.ro.x64[q]) > S.stop_D) { row.trig = true; break; }
                     }
                 }
                 const int ncol = have_eff ? k : C;

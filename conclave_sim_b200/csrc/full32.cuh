@@ -282,8 +282,8 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
                             for (int c = lane; c < C; c += 32) {
                                 if (mark[c]) continue;
                                 bool low = true;
-                                for (int q = 0; q < F && low; ++q)
-                                    low = __ddiv_rn((double)hist[(size_t)((n_hist - F + q) % a.Fmax) * C + c], (double)E) < S.fat_thr;
+                                for (int q = 0; q < F && low; ++q)                  // share < threshold, as an integer test (DevSet::fat_cnt)
+                                    low = hist[(size_t)((n_hist - F + q) % a.Fmax) * C + c] < S.fat_cnt;
                                 fat[c] = low ? 1 : 0;
                             }
                             use_fat = true;
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
                 if (S.en_stop && have_prev) {
                     for (int c0 = 0; c0 < C; c0 += 32) {
                         const int c = c0 + lane;
-                        const bool is_thr = c < C && __ddiv_rn((double)tally[c], (double)E) > S.stop_T;
+                        const bool is_thr = c < C && tally[c] >= S.stop_cnt;       // share > threshold (DevSet::stop_cnt)
                         const unsigned m = __ballot_sync(CSIM_FULL, is_thr);
                         if (is_thr) { const int pos = n_thr + __popc(m & ((1u << lane) - 1u)); if (pos < 32) thr[pos] = c; }
                         n_thr += __popc(m);
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
                             for (int q = 0; q < n_thr && !trig; ++q) trig = fabs(xe64 - a.ro.x64[thr[q]]) > S.stop_D;
                         } else {                                     // more threats than the list holds: test every candidate
                             for (int q = 0; q < C && !trig; ++q)
-                                trig = fabs(xe64 - a.ro.x64[q]) > S.stop_D && __ddiv_rn((double)hist[(size_t)((n_hist - 1) % a.Fmax) * C + q], (double)E) > S.stop_T;
+                                trig = fabs(xe64 - a.ro.x64[q]) > S.stop_D && hist[(size_t)((n_hist - 1) % a.Fmax) * C + q] >= S.stop_cnt;
                         }
                     }
                     int vote;
