@@ -20,7 +20,7 @@ ABI_VERSION = 1
 
 EXPORTS = ["csim_abi_version", "csim_last_error", "csim_create", "csim_destroy", "csim_device_info",
            "csim_upload_roster", "csim_beta_schedule", "csim_need_votes", "csim_prob_matrix", "csim_run",
-           "csim_stats", "csim_microbench", "csim_prefix_plan_query", "csim_prefix_slot", "csim_host_alloc", "csim_host_free"]
+           "csim_stats", "csim_microbench", "csim_prefix_plan_query", "csim_prefix_slot", "csim_host_alloc", "csim_host_free", "csim_vote_threshold"]
 
 
 class CsimError(RuntimeError):
@@ -85,6 +85,8 @@ def load_library() -> C.CDLL:
     lib.csim_beta_schedule.argtypes = [C.POINTER(CsimParams), C.c_int32, C.c_int32, C.c_void_p]
     lib.csim_need_votes.argtypes = [C.c_double, C.c_int32]
     lib.csim_need_votes.restype = C.c_int32
+    lib.csim_vote_threshold.argtypes = [C.c_double, C.c_int32, C.c_int32]
+    lib.csim_vote_threshold.restype = C.c_int32
     lib.csim_prob_matrix.argtypes = [C.c_void_p, C.POINTER(CsimParams), C.c_double, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     lib.csim_run.argtypes = [C.c_void_p, C.POINTER(CsimRunArgs)]

@@ -191,6 +191,17 @@ extern "C" int32_t csim_need_votes(double thr, int32_t E) {
     return v;
 }
 
+// smallest vote count v in [0, E + 1] with (double)v / E >= share (strict == 0) or > share (strict != 0): v / E is monotone
+// in v, so "share of the votes < threshold" (simulate.py:111) is exactly "votes < csim_vote_threshold(threshold, E, 0)" and
+// "share > threshold" (model.py:397) is exactly "votes >= csim_vote_threshold(threshold, E, 1)" — no division per candidate
+extern "C" int32_t csim_vote_threshold(double share, int32_t E, int32_t strict) {
+    if (E <= 0) return 0;
+    int32_t v = 0;
+    if (strict) { while (v <= E && !((double)v / (double)E > share)) ++v; }
+    else        { while (v <= E && (double)v / (double)E < share) ++v; }
+    return v;
+}
+
 static RosterDev roster_dev(const csim_ctx* c) {
     RosterDev r;
     r.E = c->E; r.Epad = c->Epad; r.G = c->G;
@@ -226,12 +237,8 @@ static DevSet make_set(const csim_params* p, int E, int wiring) {
     s.en_stop = model && p->enable_stop_candidate;
     // the two share tests of the model as integer vote thresholds: v / E in fp64 is monotone in v, so the comparisons the
     // reference makes on shares (simulate.py:111, model.py:397) are reproduced exactly without a division per candidate
-    int32_t v = 0;
-    while (v <= E && (double)v / (double)E < s.fat_thr) ++v;
-    s.fat_cnt = v;
-    v = 0;
-    while (v <= E && !((double)v / (double)E > s.stop_T)) ++v;
-    s.stop_cnt = v;
+    s.fat_cnt = csim_vote_threshold(s.fat_thr, E, 0);
+    s.stop_cnt = csim_vote_threshold(s.stop_T, E, 1);
     return s;
 }
 

@@ -156,6 +156,10 @@ csim_status csim_upload_roster(csim_ctx* ctx, int32_t n_electors, const double* 
 csim_status csim_beta_schedule(const csim_params* p, int32_t first_round, int32_t n_rounds, double* out);
 /* smallest integer v with (double)v >= threshold * n_electors */
 int32_t     csim_need_votes(double supermajority_threshold, int32_t n_electors);
+/* smallest vote count v in [0, n_electors + 1] with (double)v / n_electors >= share (strict == 0) or > share (strict != 0):
+ * the share tests of candidate fatigue (simulate.py:111: share < threshold) and stop-candidate (model.py:397: share >
+ * threshold) as exact integer tests on vote counts */
+int32_t     csim_vote_threshold(double share, int32_t n_electors, int32_t strict);
 
 /* P[E, n_cand] for one round with effective beta `beta` (host buffers in and out).
  * prev_vote[E]  : candidate index (roster order) each elector voted for last round, -1 = none (nullable -> stickiness off)

@@ -243,3 +243,19 @@ def test_plain_c_client_compiles_and_links(tmp_path):
                     os.path.join(ROOT, "tests", "c", "c_client.c"), LIB_PATH, "-Wl,-rpath," + os.path.dirname(LIB_PATH), "-o", str(exe)],
                    check=True)
     assert exe.exists()
+
+
+def test_vote_thresholds_reproduce_the_share_tests(lib):
+    """csim_vote_threshold: the reference compares SHARES (votes / E in fp64) with its thresholds (simulate.py:111 `<`,
+    model.py:397 `>`); the kernels compare vote COUNTS with these integers — the two must agree for every count, ties included."""
+    rng = np.random.default_rng(3)
+    for E in (1, 2, 7, 85, 134, 135, 1024):
+        shares = list(rng.random(40)) + [k / E for k in range(0, E + 1, max(1, E // 17))] + [0.0, 1.0, -0.1, 1.5, 0.05, 0.15, 0.03,
+                                                                                            np.nextafter(3 / E, 0), np.nextafter(3 / E, 1)]
+        v = np.arange(0, E + 1)
+        sh = v.astype(np.float64) / np.float64(E)
+        for s in shares:
+            lo = lib.csim_vote_threshold(float(s), E, 0)
+            hi = lib.csim_vote_threshold(float(s), E, 1)
+            assert np.array_equal(sh < s, v < lo), (E, s)
+            assert np.array_equal(sh > s, v >= hi), (E, s)
