@@ -560,7 +560,9 @@ static csim_status launch_prefix(csim_ctx* c, const csim_run_args* ra, const std
     for (const DevSet& s : hs) Rt = std::max(Rt, s.k > 0 ? std::min(R, std::max(s.rr, 1)) : R);
     Rt = std::max(1, std::min(Rt, std::max(R, 1)));
     const bool stage_ok = getenv("CSIM_PREFIX_NOSTAGE") == nullptr;
-    if (!prefix_plan(a, E, c->G, R, Rt, kmax, model, (size_t)c->prop.sharedMemPerBlockOptin - 64 /* static: the staging mbarrier */, stage_ok))
+    const char* ls_env = getenv("CSIM_PREFIX_LS");                  // tuning: force the chunk size (log2)
+    if (!prefix_plan(a, E, c->G, R, Rt, kmax, model, (size_t)c->prop.sharedMemPerBlockOptin - 64 /* static: the staging mbarrier */, stage_ok,
+                     ls_env ? atoi(ls_env) : 0))
         return fail(CSIM_ERR_UNSUPPORTED, "prefix engine: a roster of %d electors does not fit in shared memory", E);
     const bool stage = a.tab_smem != 0;
     const int Ls = a.Ls;

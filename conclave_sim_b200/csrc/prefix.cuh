@@ -15,7 +15,7 @@
 // with T_r[e][j] = sum of base[e,c] over c < (j+1) L, c != e — built ONCE per (parameter set, round) in
 // fp64 and rounded once (k_prefix_tables32) — and BWP the per-trial-round prefix of bw over chunks
 // (17 numbers at E = 134).  A draw is then
-//   1. S = F_e(last), target = u S, a binary search over the <= 32 chunk prefixes (<= 5 probes), and
+//   1. S = F_e(last), target = u S, a binary search over the chunk prefixes (17 at E = 134: 5 probes; at most 128: 7 probes), and
 //   2. a re-scan of the ONE chunk the target falls into, every term inline in roster order, to find the
 //      first c with cum > target  (== searchsorted(cumsum(p)/sum, u, 'right'), simulate.py:153).
 // That is the dense fp32 engine (dense32.cuh) with its phase 1 — the E x C exponentials every trial
@@ -33,6 +33,7 @@
 #pragma once
 #include "common.cuh"
 
+#define CSIM_PREFIX_MAX_CHUNKS 128     // chunk prefixes per row (the bandwagon scan walks them 32 at a time)
 #ifndef CSIM_PREFIX_THREADS
 #define CSIM_PREFIX_THREADS 768        // 24 warps per CTA, 1 CTA per SM (<= 85 registers)
 #endif
@@ -47,7 +48,7 @@ struct PrefixArgs {
     const float* T;         // [sets][Rt][rows][stride]  chunk-prefix tables of the full-field rounds
     int Rt;                 // rounds that can be full-field: min(R, max(runoff_threshold_rounds, 1)) when a run-off exists, else R
     int Ls;                 // log2(candidates per chunk); L = 1 << Ls >= 8
-    int nch;                // chunks, nch * L >= C, nch <= 32
+    int nch;                // chunks, nch * L >= C, nch <= CSIM_PREFIX_MAX_CHUNKS
     int stride;             // row pitch in floats (odd, >= nch)
     int rows;               // rows per round
     int e_quad_end;         // electors below this are dealt as whole Philox quads per lane, the rest one per lane
@@ -78,7 +79,7 @@ __host__ inline void prefix_layout(PrefixArgs& a, bool model) {
     a.o_xg = o; o += 8u * rows8;
     a.o_nbs = o;
     uint32_t w = 0;
-    if (model) { w += a.cp4; a.w_bwp = w; w += 128u; } else a.w_bwp = 0;
+    if (model) { w += a.cp4; a.w_bwp = w; w += 4u * CSIM_PREFIX_MAX_CHUNKS; } else a.w_bwp = 0;
     a.w_tally = w; w += 4u * Ei;
     a.w_eff = w; w += 4u * (((uint32_t)a.kmax + 3u) & ~3u);
     a.w_votes = w; if (model) w += 2u * rows8;
@@ -103,7 +104,7 @@ __host__ __device__ inline size_t prefix_roster_smem(int CPP, int G, int R, int 
 __host__ __device__ inline size_t prefix_warp_smem(int E, int CPP, int kmax, int rows, bool model) {
     const size_t Ei = ((size_t)E + 7) & ~(size_t)7, rows8 = ((size_t)rows + 7) & ~(size_t)7;
     size_t n = Ei * 4 /*tally*/ + (((size_t)kmax + 3) & ~(size_t)3) * 4 /*eff*/ + Ei /*mark*/;
-    if (model) n += (size_t)CPP * 4 /*bw*/ + 32 * 4 /*bwp*/ + rows8 * 2 /*votes*/;
+    if (model) n += (size_t)CPP * 4 /*bw*/ + CSIM_PREFIX_MAX_CHUNKS * 4 /*bwp*/ + rows8 * 2 /*votes*/;
     return (n + 15) & ~(size_t)15;
 }
 
@@ -113,7 +114,9 @@ __host__ __device__ inline size_t prefix_warp_smem(int E, int CPP, int kmax, int
 //   budget       = opt-in shared memory per block of the device (232448 B on sm_100)
 //   allow_stage  = false forces the global-memory (L2) path
 // Returns false when even one warp does not fit.
-__host__ inline bool prefix_plan(PrefixArgs& a, int E, int G, int R, int Rt, int kmax, bool model, size_t budget, bool allow_stage) {
+//   force_Ls     > 0: use chunks of 1 << force_Ls candidates (tuning / tests), else the rule below
+__host__ inline bool prefix_plan(PrefixArgs& a, int E, int G, int R, int Rt, int kmax, bool model, size_t budget, bool allow_stage,
+                                 int force_Ls = 0) {
     a.ro.E = E; a.ro.G = G; a.kmax = kmax;
     // electors are dealt to lanes as whole Philox quads (128 per group of 4 passes); a tail of <= 64 electors goes one per lane
     const int n_left = E & 127;
@@ -122,12 +125,17 @@ __host__ inline bool prefix_plan(PrefixArgs& a, int E, int G, int R, int Rt, int
     a.Rt = Rt < 1 ? 1 : Rt;
     const int max_wpc = CSIM_PREFIX_THREADS / 32;
     int Ls_min = 3;
-    while (((E + (1 << Ls_min) - 1) >> Ls_min) > 32) ++Ls_min;         // at most 32 chunks (one lane per chunk in the bandwagon scan)
+    while (((E + (1 << Ls_min) - 1) >> Ls_min) > CSIM_PREFIX_MAX_CHUNKS) ++Ls_min;
+    // tables probed through L2 (large rosters): re-scanning a chunk costs ~14 instructions per candidate, a probe one L2
+    // round trip.  Measured (100 k trials): E = 512 ref_cli 1.46e11 / 1.34e11 / 0.88e11 elector-rounds/s with chunks of
+    // 8 / 16 / 32, model 5.1e10 / 8.1e10 / 7.1e10; E = 1024 ref_cli 6.0e10 / 6.4e10 / 6.4e10, model 2.7e10 / 3.1e10 / 3.1e10
+    int Ls_pref = Ls_min > (E > 512 || (model && E > 256) ? 4 : 3) ? Ls_min : (E > 512 || (model && E > 256) ? 4 : 3);
+    if (force_Ls >= 3) { Ls_pref = force_Ls < Ls_min ? Ls_min : force_Ls; Ls_min = Ls_pref; }
     int Ls = -1, wpc = 0;
     bool stage = false;
     // smallest chunk (fewest re-scanned candidates) whose tables fit in shared memory next to >= 8 warps; a chunk of more
     // than 16 candidates costs more to re-scan than probing the tables through L2 does
-    for (int l = Ls_min; l <= 4 && allow_stage; ++l) {
+    for (int l = Ls_min; l <= (force_Ls >= 3 ? Ls_min : 4) && allow_stage; ++l) {
         const int nch = (E + (1 << l) - 1) >> l, stride = nch | 1, CPP = prefix_cpp(nch, l);
         const size_t tab = (((size_t)a.Rt * a.rows * stride * 4) + 15) & ~(size_t)15;
         const size_t fixed = tab + prefix_roster_smem(CPP, G, R, a.rows), per_warp = prefix_warp_smem(E, CPP, kmax, a.rows, model);
@@ -138,7 +146,7 @@ __host__ inline bool prefix_plan(PrefixArgs& a, int E, int G, int R, int Rt, int
         break;
     }
     if (!stage) {
-        Ls = Ls_min;
+        Ls = Ls_pref;
         const int nch = (E + (1 << Ls) - 1) >> Ls, CPP = prefix_cpp(nch, Ls);
         const size_t fixed = prefix_roster_smem(CPP, G, R, a.rows), per_warp = prefix_warp_smem(E, CPP, kmax, a.rows, model);
         if (fixed + per_warp > budget) return false;
@@ -168,26 +176,30 @@ __global__ void k_prefix_tables32(RosterDev ro, const DevSet* sets, const double
     const DevSet* S = &sets[set];
     const double beta = betas[(size_t)set * R + r0], xe = ro.x64[e], pwf = S->pwf, bonus = S->bonus;
     const int ge = ro.region[e];
-    double s = 0.0;
-    if (lane < nch) {
-        const int c1 = min(C, (lane + 1) << Ls);
-        for (int c = lane << Ls; c < c1; ++c) {
-            if (c == e) continue;                                            // model.py:418-424
-            double v = exp(-beta * fabs(xe - ro.x64[c]));
-            if (ro.pap[c]) v *= pwf;
-            if (ro.region[c] == ge) v += bonus;
-            s += fmax(v, 0.0);
-        }
-    }
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const double o = __shfl_up_sync(CSIM_FULL, s, off);
-        if (lane >= off) s += o;
-    }
-    const double last = __shfl_sync(CSIM_FULL, s, nch - 1);
     float* row = T + (size_t)set * set_pitch + ((size_t)r0 * rows + prefix_slot(e, e_quad_end)) * stride;
-    if (lane < stride) row[lane] = (float)(lane < nch ? s : last);
-    if (lane == 0 && stride > 32) row[32] = (float)last;
+    double carry = 0.0;                                              // prefix up to the previous group of 32 chunks
+    for (int j0 = 0; j0 < stride; j0 += 32) {
+        const int j = j0 + lane;
+        double s = 0.0;
+        if (j < nch) {
+            const int c1 = min(C, (j + 1) << Ls);
+            for (int c = j << Ls; c < c1; ++c) {
+                if (c == e) continue;                                        // model.py:418-424
+                double v = exp(-beta * fabs(xe - ro.x64[c]));
+                if (ro.pap[c]) v *= pwf;
+                if (ro.region[c] == ge) v += bonus;
+                s += fmax(v, 0.0);
+            }
+        }
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const double o = __shfl_up_sync(CSIM_FULL, s, off);
+            if (lane >= off) s += o;
+        }
+        s += carry;
+        if (j < stride) row[j] = (float)s;                           // entries beyond nch repeat the total (row pitch padding)
+        carry = __shfl_sync(CSIM_FULL, s, 31);
+    }
 }
 
 // ---- shared memory through 32-bit window addresses ---------------------------------------------------
@@ -450,7 +462,7 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(const 
             if (R == 0) { for (int c = lane; c < C; c += 32) tally[c] = 0; }
             if (MODEL) {
                 for (int c = lane; c < CPP; c += 32) bw[c] = 0.0f;
-                bwp[lane] = 0.0f;
+                for (int j = lane; j < nch; j += 32) bwp[j] = 0.0f;
             }
             __syncwarp();
 
@@ -468,17 +480,24 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(const 
                     const float inv = 1.0f / (float)prev_mx;
                     for (int c = lane; c < C; c += 32) bw[pc(c)] = (float)tally[c] * inv * bw_strength;   // tally = previous round's
                     __syncwarp();
-                    float s = 0.f;                                               // bandwagon of chunk `lane`, then prefix over chunks
-                    if (lane < nch) {
-                        const float4* b4 = reinterpret_cast<const float4*>(bw + lane * Lp);
-                        for (int i = 0; i < (1 << (Ls - 2)); ++i) { const float4 v = b4[i]; s += (v.x + v.y) + (v.z + v.w); }
-                    }
+                    float carry = 0.f;                                           // bandwagon per chunk, then prefix over chunks (32 at a time)
+#pragma unroll 1
+                    for (int j0 = 0; j0 < nch; j0 += 32) {
+                        const int j = j0 + lane;
+                        float s = 0.f;
+                        if (j < nch) {
+                            const float4* b4 = reinterpret_cast<const float4*>(bw + j * Lp);
+                            for (int i = 0; i < (1 << (Ls - 2)); ++i) { const float4 v = b4[i]; s += (v.x + v.y) + (v.z + v.w); }
+                        }
 #pragma unroll
-                    for (int off = 1; off < 32; off <<= 1) {
-                        const float o = __shfl_up_sync(CSIM_FULL, s, off);
-                        if (lane >= off) s += o;
+                        for (int off = 1; off < 32; off <<= 1) {
+                            const float o = __shfl_up_sync(CSIM_FULL, s, off);
+                            if (lane >= off) s += o;
+                        }
+                        s += carry;
+                        if (j < nch) bwp[j] = s;
+                        carry = __shfl_sync(CSIM_FULL, s, 31);
                     }
-                    bwp[lane] = s;
                 }
                 __syncwarp();
                 for (int c = lane; c < C; c += 32) tally[c] = 0;

@@ -31,7 +31,7 @@ def test_plan_invariants(E):
             assert E > 2000 or G >= 64
             continue
         L, nch = p.chunk, p.n_chunks
-        assert L >= 8 and L & (L - 1) == 0 and 1 <= nch <= 32 and nch * L >= E and (nch - 1) * L < E
+        assert L >= 8 and L & (L - 1) == 0 and 1 <= nch <= 128 and nch * L >= E and (nch - 1) * L < E
         assert p.row_pitch % 2 == 1 and p.row_pitch >= nch
         assert p.rows >= E and p.e_quad_end % 128 == 0 and p.rows == max(E, p.e_quad_end)
         assert (E - p.e_quad_end) <= 64                                    # the tail dealt one elector per lane is at most two passes
@@ -53,7 +53,7 @@ def test_plan_invariants(E):
         # warp arrays
         Ei = (E + 7) & ~7
         if wiring == 1:
-            assert w_bwp == cp4 and w_tally == w_bwp + 128 and w_votes >= w_eff + 4 * kmax and w_mark >= w_votes + 2 * p.rows
+            assert w_bwp == cp4 and w_tally == w_bwp + 4 * 128 and w_votes >= w_eff + 4 * kmax and w_mark >= w_votes + 2 * p.rows
         else:
             assert w_tally == 0 and w_mark == w_votes
         assert w_eff == w_tally + 4 * Ei and w_mark + E <= p.smem_per_warp
@@ -83,7 +83,7 @@ def test_cfg_shapes():
     st, p = plan(134, 8, 20, 20, 1, 1)          # no run-off: all 20 rounds can be full-field, 182 KB of tables still fit
     assert st == 0 and p.staged and p.smem_tables == 182240 and p.warps_per_cta >= 16
     st, p = plan(1024, 8, 50, 5, 2, 0)          # cfg-5: tables through L2
-    assert st == 0 and not p.staged and p.chunk == 32 and p.n_chunks == 32 and p.table_bytes_per_set == 675840
+    assert st == 0 and not p.staged and p.chunk == 16 and p.n_chunks == 64 and p.table_bytes_per_set == 5 * 1024 * 65 * 4
     st, p = plan(134, 8, 20, 5, 2, 1, budget=40000)
     assert st == 0 and not p.staged             # a small budget falls back to L2 tables
     st, p = plan(134, 8, 20, 5, 2, 1, budget=4000)
