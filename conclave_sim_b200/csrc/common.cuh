@@ -176,3 +176,36 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }"
                      : "=r"(ok) : "r"(bar), "r"(phase) : "memory");
 }
+
+// ---------------------------------------------------------------------------
+// Dealing the electors of one round to the 32 lanes of the warp that owns the trial (PREFIX and FULL engines), each with
+// its fp32 uniform: lane l owns whole Philox quads (electors 4q .. 4q+3, q = l + 32 qi: one Philox call, four uniforms) for
+// the electors below e_quad_end, then the tail goes one elector per lane.  fn(e, u, slot) — slot = the elector's row in
+// tables stored in lane-visiting order (prefix_slot) — must not contain warp collectives: lanes run out of electors
+// at different times.
+// ---------------------------------------------------------------------------
+template <class Fn>
+__device__ __forceinline__ void deal_electors(int lane, int E, int e_quad_end, int r, uint32_t s_lo, uint32_t s_hi, uint32_t seed_lo,
+                                              uint32_t seed_hi, Fn&& fn) {
+    const int n_qit = e_quad_end >> 7;                       // quad iterations (128 electors each)
+    for (int qi = 0; qi < n_qit; ++qi) {
+        const int q = lane + 32 * qi;
+        if (4 * q < E) {
+            uint32_t w[4];
+            philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)q, seed_lo, seed_hi, w);
+#pragma unroll 1
+            for (int i = 0; i < 4; ++i) {
+                const int e = 4 * q + i;
+                const uint32_t wa = i == 0 ? w[0] : (i == 1 ? w[1] : (i == 2 ? w[2] : w[3]));
+                if (e < E) fn(e, u24_from_word(wa), (qi << 7) + (i << 5) + lane);
+            }
+        }
+    }
+    for (int e = e_quad_end + lane; e < E; e += 32) {
+        uint32_t w[4];
+        philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)(e >> 2), seed_lo, seed_hi, w);
+        const int sel = e & 3;
+        const uint32_t wa = sel == 0 ? w[0] : (sel == 1 ? w[1] : (sel == 2 ? w[2] : w[3]));
+        fn(e, u24_from_word(wa), e);
+    }
+}

@@ -179,29 +179,9 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
     kx.nb = 0.f; kx.st1p = 1.f; kx.boost = 1.f; kx.stop_D = 0.0; kx.C = C;
     int step0 = 1;
     while (step0 * 2 <= nch) step0 *= 2;
-    const int n_qit = a.e_quad_end >> 7;
 
     auto for_each_elector = [&](int r, uint32_t s_lo, uint32_t s_hi, auto&& fn) {
-        for (int qi = 0; qi < n_qit; ++qi) {
-            const int q = lane + 32 * qi;
-            if (4 * q < E) {
-                uint32_t w[4];
-                philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)q, a.b.seed_lo, a.b.seed_hi, w);
-#pragma unroll 1
-                for (int i = 0; i < 4; ++i) {
-                    const int e = 4 * q + i;
-                    const uint32_t wa = i == 0 ? w[0] : (i == 1 ? w[1] : (i == 2 ? w[2] : w[3]));
-                    if (e < E) fn(e, u24_from_word(wa), (qi << 7) + (i << 5) + lane);
-                }
-            }
-        }
-        for (int e = a.e_quad_end + lane; e < E; e += 32) {
-            uint32_t w[4];
-            philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)(e >> 2), a.b.seed_lo, a.b.seed_hi, w);
-            const int sel = e & 3;
-            const uint32_t wa = sel == 0 ? w[0] : (sel == 1 ? w[1] : (sel == 2 ? w[2] : w[3]));
-            fn(e, u24_from_word(wa), e);
-        }
+        deal_electors(lane, E, a.e_quad_end, r, s_lo, s_hi, a.b.seed_lo, a.b.seed_hi, fn);
     };
 
     const uint64_t per_item = (uint64_t)wpc * a.tpi;

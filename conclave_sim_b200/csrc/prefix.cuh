@@ -375,7 +375,6 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(const 
     int32_t* eff = (int32_t*)(base + a.w_eff);
     uint8_t* mark = base + a.w_mark;
 
-    const int n_qit = a.e_quad_end >> 7;                     // quad iterations (128 electors each)
     const bool top2_ok = C >= 2 && C < 32768;
     const size_t round_pitch = (size_t)a.rows * a.stride;
     const uint32_t stride4 = 4u * (uint32_t)a.stride;
@@ -387,28 +386,9 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(const 
     const uint32_t Ts_a = kx.sb;
     __shared__ __align__(8) unsigned long long stage_bar;                   // mbarrier of the staged tables (re-armed per set: phase 0)
 
-    // the electors of one round, each lane with its uniform: whole Philox quads per lane, then the tail one per lane
+    // the electors of one round, each lane with its uniform (common.cuh: deal_electors)
     auto for_each_elector = [&](int r, uint32_t s_lo, uint32_t s_hi, auto&& fn) {
-        for (int qi = 0; qi < n_qit; ++qi) {
-            const int q = lane + 32 * qi;
-            if (4 * q < E) {
-                uint32_t w[4];
-                philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)q, a.b.seed_lo, a.b.seed_hi, w);
-#pragma unroll 1
-                for (int i = 0; i < 4; ++i) {
-                    const int e = 4 * q + i;
-                    const uint32_t wa = i == 0 ? w[0] : (i == 1 ? w[1] : (i == 2 ? w[2] : w[3]));
-                    if (e < E) fn(e, u24_from_word(wa), (qi << 7) + (i << 5) + lane);
-                }
-            }
-        }
-        for (int e = a.e_quad_end + lane; e < E; e += 32) {
-            uint32_t w[4];
-            philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)(e >> 2), a.b.seed_lo, a.b.seed_hi, w);
-            const int sel = e & 3;
-            const uint32_t wa = sel == 0 ? w[0] : (sel == 1 ? w[1] : (sel == 2 ? w[2] : w[3]));
-            fn(e, u24_from_word(wa), e);
-        }
+        deal_electors(lane, E, a.e_quad_end, r, s_lo, s_hi, a.b.seed_lo, a.b.seed_hi, fn);
     };
 
     const uint64_t per_item = (uint64_t)wpc * a.tpi;
