@@ -209,3 +209,18 @@ __device__ __forceinline__ void deal_electors(int lane, int E, int e_quad_end, i
         fn(e, u24_from_word(wa), e);
     }
 }
+
+// The per-trial outputs every warp-per-trial kernel writes when its trial ends (winner / rounds / reason rows, the last
+// tally, the -1 padding of the per-round tallies beyond `rounds`, the two histograms of simulate.py:356-387).
+__device__ __forceinline__ void write_trial_outputs(const TrialOut& out, uint64_t t, int set, int C, int R, int lane, const int32_t* tally,
+                                                    int winner, int rounds, int reason) {
+    if (out.final_votes) for (int c = lane; c < C; c += 32) out.final_votes[t * (uint64_t)C + c] = tally[c];
+    if (out.round_tallies)
+        for (size_t i = (size_t)rounds * C + lane; i < (size_t)R * C; i += 32) out.round_tallies[t * (uint64_t)R * C + i] = -1;
+    if (lane == 0) {
+        out.winner[t] = winner; out.rounds[t] = rounds;
+        if (out.reason) out.reason[t] = (uint8_t)reason;
+        if (out.winner_hist) atomicAdd(&out.winner_hist[(size_t)set * (C + 1) + (winner >= 0 ? winner : C)], 1ULL);
+        if (out.rounds_hist && winner >= 0) atomicAdd(&out.rounds_hist[(size_t)set * (R + 1) + rounds], 1ULL);
+    }
+}

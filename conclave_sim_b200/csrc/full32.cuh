@@ -406,15 +406,7 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
                 if (r >= rr && k > 0) { warp_top_k(tally, C, k, lane, eff, mark); have_eff = true; }   // simulate.py:183-186
                 __syncwarp();
             }
-            if (a.out.final_votes) for (int c = lane; c < C; c += 32) a.out.final_votes[t * (uint64_t)C + c] = tally[c];
-            if (a.out.round_tallies)
-                for (size_t i2 = (size_t)rounds * C + lane; i2 < (size_t)R * C; i2 += 32) a.out.round_tallies[t * (uint64_t)R * C + i2] = -1;
-            if (lane == 0) {
-                a.out.winner[t] = winner; a.out.rounds[t] = rounds;
-                if (a.out.reason) a.out.reason[t] = (uint8_t)reason;
-                if (a.out.winner_hist) atomicAdd(&a.out.winner_hist[(size_t)set * (C + 1) + (winner >= 0 ? winner : C)], 1ULL);
-                if (a.out.rounds_hist && winner >= 0) atomicAdd(&a.out.rounds_hist[(size_t)set * (R + 1) + rounds], 1ULL);
-            }
+            write_trial_outputs(a.out, t, set, C, R, lane, tally, winner, rounds, reason);
             acc_rounds += (unsigned long long)rounds; acc_trials += 1;
             __syncwarp();
         }
