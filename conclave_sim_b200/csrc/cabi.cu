@@ -573,7 +573,7 @@ static csim_status launch_prefix(csim_ctx* c, const csim_run_args* ra, const std
     if (R > 0) {
         dim3 g((E + 7) / 8, b.n_sets * Rt);
         k_prefix_tables32<<<g, 256, 0, st>>>(a.ro, b.sets, (const double*)c->betas.p, R, Rt, a.Ls, a.nch, a.stride, a.rows, a.e_quad_end,
-                                             a.set_pitch, (float*)c->ptab.p);
+                                             a.set_pitch, a.col_major, (float*)c->ptab.p);
         ++c->launches;
     }
     const bool lc8 = Ls == 3;

@@ -45,7 +45,10 @@ struct PrefixArgs {
     BatchDev b;
     TrialOut out;
     const float* nbeta;     // [sets][R]  -beta_r * log2(e)
-    const float* T;         // [sets][Rt][rows][stride]  chunk-prefix tables of the full-field rounds
+    const float* T;         // chunk-prefix tables of the full-field rounds: [sets][Rt][rows][stride] when staged in shared
+                            // memory (odd row pitch: conflict-free), [sets][Rt][stride][rows] (column-major) when probed through
+                            // L2: the 32 lanes of a pass own 32 consecutive rows, so a probe of one chunk column is one 128-byte line
+    int col_major;          // 1: the second layout
     int Rt;                 // rounds that can be full-field: min(R, max(runoff_threshold_rounds, 1)) when a run-off exists, else R
     int Ls;                 // log2(candidates per chunk); L = 1 << Ls >= 8
     int nch;                // chunks, nch * L >= C, nch <= CSIM_PREFIX_MAX_CHUNKS
@@ -126,10 +129,12 @@ __host__ inline bool prefix_plan(PrefixArgs& a, int E, int G, int R, int Rt, int
     const int max_wpc = CSIM_PREFIX_THREADS / 32;
     int Ls_min = 3;
     while (((E + (1 << Ls_min) - 1) >> Ls_min) > CSIM_PREFIX_MAX_CHUNKS) ++Ls_min;
-    // tables probed through L2 (large rosters): re-scanning a chunk costs ~14 instructions per candidate, a probe one L2
-    // round trip.  Measured (100 k trials): E = 512 ref_cli 1.46e11 / 1.34e11 / 0.88e11 elector-rounds/s with chunks of
-    // 8 / 16 / 32, model 5.1e10 / 8.1e10 / 7.1e10; E = 1024 ref_cli 6.0e10 / 6.4e10 / 6.4e10, model 2.7e10 / 3.1e10 / 3.1e10
-    int Ls_pref = Ls_min > (E > 512 || (model && E > 256) ? 4 : 3) ? Ls_min : (E > 512 || (model && E > 256) ? 4 : 3);
+    // tables probed through L1 / L2 (large rosters): re-scanning a chunk costs ~14 instructions per candidate, a probe one
+    // cache round trip.  Measured (100 k trials, elector-rounds/s, chunks of 8 / 16 / 32, best layout below):
+    //   E = 512   ref_cli 1.46e11 / 1.34e11 / 0.93e11     model 9.3e10 / 8.3e10 / 6.9e10
+    //   E = 1024  ref_cli 8.5e10 / 7.9e10 / 6.7e10        model 3.5e10 / 3.8e10 / 3.3e10
+    const int Ls_want = (model && E > 512) ? 4 : 3;
+    int Ls_pref = Ls_min > Ls_want ? Ls_min : Ls_want;
     if (force_Ls >= 3) { Ls_pref = force_Ls < Ls_min ? Ls_min : force_Ls; Ls_min = Ls_pref; }
     int Ls = -1, wpc = 0;
     bool stage = false;
@@ -160,6 +165,12 @@ __host__ inline bool prefix_plan(PrefixArgs& a, int E, int G, int R, int Rt, int
     a.cta_smem = a.tab_smem + prefix_roster_smem(CPP, G, R, a.rows);
     a.warp_smem = prefix_warp_smem(E, CPP, kmax, a.rows, model);
     a.warps_per_cta = wpc;
+    // layout of a table that stays in global memory: row-major keeps the 6-7 probes of one draw inside the 2-3 lines of its
+    // row — best while a round's table fits in what the shared-memory carve-out leaves of L1 (E = 512 ref_cli: 1.46e11 vs
+    // 1.32e11); beyond that column-major wins: a pass of 32 lanes owns 32 consecutive rows, so a probe of one chunk column
+    // is one 128-byte line (E = 1024 ref_cli: 8.5e10 vs 6.0e10; E = 512 model, where shared memory leaves little L1: 9.3e10 vs 5.1e10)
+    const size_t l1_left = (size_t)228 * 1024 > a.cta_smem + a.warp_smem * (size_t)wpc ? (size_t)228 * 1024 - (a.cta_smem + a.warp_smem * (size_t)wpc) : 0;
+    a.col_major = (!stage && (size_t)a.rows * a.stride * 4 > l1_left) ? 1 : 0;
     prefix_layout(a, model);
     return true;
 }
@@ -168,7 +179,7 @@ __host__ inline bool prefix_plan(PrefixArgs& a, int E, int G, int R, int Rt, int
 // terms is model.py:311-324: exp, papabile factor, regional bonus), an inclusive warp scan makes the prefixes.
 // grid = (ceil(E / 8), sets * Rt), block = 256.
 __global__ void k_prefix_tables32(RosterDev ro, const DevSet* sets, const double* betas, int R, int Rt, int Ls, int nch, int stride,
-                                  int rows, int e_quad_end, size_t set_pitch, float* T) {
+                                  int rows, int e_quad_end, size_t set_pitch, int col_major, float* T) {
     const int lane = threadIdx.x & 31, e = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int set = blockIdx.y / Rt, r0 = blockIdx.y - set * Rt;       // r0 = round - 1
     const int C = ro.E;
@@ -176,7 +187,9 @@ __global__ void k_prefix_tables32(RosterDev ro, const DevSet* sets, const double
     const DevSet* S = &sets[set];
     const double beta = betas[(size_t)set * R + r0], xe = ro.x64[e], pwf = S->pwf, bonus = S->bonus;
     const int ge = ro.region[e];
-    float* row = T + (size_t)set * set_pitch + ((size_t)r0 * rows + prefix_slot(e, e_quad_end)) * stride;
+    const int slot = prefix_slot(e, e_quad_end);
+    float* tab = T + (size_t)set * set_pitch + (size_t)r0 * rows * stride;        // this round's table
+    float* row = tab + (size_t)slot * stride;                                      // row-major
     double carry = 0.0;                                              // prefix up to the previous group of 32 chunks
     for (int j0 = 0; j0 < stride; j0 += 32) {
         const int j = j0 + lane;
@@ -197,7 +210,9 @@ __global__ void k_prefix_tables32(RosterDev ro, const DevSet* sets, const double
             if (lane >= off) s += o;
         }
         s += carry;
-        if (j < stride) row[j] = (float)s;                           // entries beyond nch repeat the total (row pitch padding)
+        if (j < stride) {                                            // entries beyond nch repeat the total (row pitch padding)
+            if (col_major) tab[(size_t)j * rows + slot] = (float)s; else row[j] = (float)s;
+        }
         carry = __shfl_sync(CSIM_FULL, s, 31);
     }
 }
@@ -246,11 +261,12 @@ __device__ __forceinline__ float prefix_full_score(const PrefixCtx& k, const Pre
 }
 
 // One vote of a full-field round.  STAGE: trow = shared address of this elector's row of the round's chunk-prefix
-// table; else Tg = the row in global memory.
+// table; else Tg = its first entry in the global table (row- or column-major, PrefixArgs::col_major).
 template <bool LC8, bool MODEL, bool STAGE>
 __device__ __forceinline__ int prefix_draw(const PrefixCtx& k, const PrefixArgs& a, uint32_t trow, const float* __restrict__ Tg, int e, int slot,
                                            float u, int prev) {
     const int Ls = LC8 ? 3 : a.Ls, nch4 = a.nch4, C = a.ro.E;
+    const uint32_t gstep = a.col_major ? (uint32_t)a.rows : 1u;       // column-major: consecutive chunks are `rows` floats apart
     float xe; int ge;
     lds_xg(PFX_XG(k, a) + 8 * slot, xe, ge);
     const uint32_t rbrow = PFX_RB(k, a) + ge * a.cp4;
@@ -269,7 +285,8 @@ __device__ __forceinline__ int prefix_draw(const PrefixCtx& k, const PrefixArgs&
         }
     }
     auto F = [&](int j4) -> float {                         // prefix of the row over chunks 0..j  (j4 = 4 j)
-        float v = STAGE ? lds_f(trow + j4) : __ldg(reinterpret_cast<const float*>(reinterpret_cast<const char*>(Tg) + j4));
+        // staged: this elector's row in shared memory; else Tg = its first entry in the global table, gstep floats per chunk
+        float v = STAGE ? lds_f(trow + j4) : __ldg(reinterpret_cast<const float*>(reinterpret_cast<const char*>(Tg) + (size_t)j4 * gstep));
         if (MODEL) {
             v += lds_f(PFX_BWP(k, a) + j4);
             v = (j4 >= je4) ? v - selfbw : v;
@@ -489,7 +506,7 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(const 
                     // =============== full-field round ==============================================
                     for_each_elector(r, s_lo, s_hi, [&](int e, float u, int slot) {
                         const int prev = sticky_live ? lds_u16(PFX_VOTES(kx, a) + 2 * slot) : -1;
-                        const int vote = prefix_draw<LC8, MODEL, STAGE>(kx, a, Tr_a + (uint32_t)slot * stride4, Tr_g + (size_t)slot * a.stride, e, slot, u, prev);
+                        const int vote = prefix_draw<LC8, MODEL, STAGE>(kx, a, Tr_a + (uint32_t)slot * stride4, Tr_g + (a.col_major ? (size_t)slot : (size_t)slot * a.stride), e, slot, u, prev);
                         red_inc(PFX_TALLY(kx, a) + 4 * vote);
                         if (MODEL) sts_u16(PFX_VOTES(kx, a) + 2 * slot, vote);   // read back only by this lane: in place is safe
                     });

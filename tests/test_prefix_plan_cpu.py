@@ -83,7 +83,7 @@ def test_cfg_shapes():
     st, p = plan(134, 8, 20, 20, 1, 1)          # no run-off: all 20 rounds can be full-field, 182 KB of tables still fit
     assert st == 0 and p.staged and p.smem_tables == 182240 and p.warps_per_cta >= 16
     st, p = plan(1024, 8, 50, 5, 2, 0)          # cfg-5: tables through L2
-    assert st == 0 and not p.staged and p.chunk == 16 and p.n_chunks == 64 and p.table_bytes_per_set == 5 * 1024 * 65 * 4
+    assert st == 0 and not p.staged and p.chunk == 8 and p.n_chunks == 128 and p.table_bytes_per_set == 5 * 1024 * 129 * 4
     st, p = plan(134, 8, 20, 5, 2, 1, budget=40000)
     assert st == 0 and not p.staged             # a small budget falls back to L2 tables
     st, p = plan(134, 8, 20, 5, 2, 1, budget=4000)
