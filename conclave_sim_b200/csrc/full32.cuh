@@ -148,7 +148,9 @@ __device__ __forceinline__ float full32_score1(const Full32Ctx& k, int c, int e,
 template <bool EXT, bool NEG>
 __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const __grid_constant__ Full32Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    asm volatile("" : "+r"(lane));       // opaque: kept in a register instead of being re-derived from %tid inside the loops
     const int E = a.ro.E, C = E, R = a.b.R, G = a.ro.G;
     const int nblk = a.nblk, CP = nblk << 3, Lb = a.Lb, nch = a.nch;
     const int wpc = a.warps_per_cta;

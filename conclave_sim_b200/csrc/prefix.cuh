@@ -366,7 +366,9 @@ __device__ __noinline__ void prefix_stage_tables(uint32_t dst, const float* src,
 template <bool LC8, bool MODEL, bool STAGE>
 __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(const __grid_constant__ PrefixArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    asm volatile("" : "+r"(lane));       // opaque: kept in a register instead of being re-derived from %tid in every pass
     const int E = a.ro.E, C = E, R = a.b.R, G = a.ro.G;
     const int Ls = LC8 ? 3 : a.Ls, nch = a.nch, Lp = (1 << Ls) + 4, CPP = nch * Lp;
     auto pc = [&](int c) { return c + ((c >> Ls) << 2); };   // index of candidate c in the padded arrays
@@ -399,6 +401,7 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(const 
     PrefixCtx kx;
     kx.sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
     kx.wb = kx.sb + (uint32_t)a.cta_smem + (uint32_t)wib * (uint32_t)a.warp_smem;
+    asm volatile("" : "+r"(kx.sb), "+r"(kx.wb));   // opaque for the same reason (the shared-window base needs an S2R)
     kx.nb = 0.f; kx.st1p = 1.f;
     const uint32_t Ts_a = kx.sb;
     __shared__ __align__(8) unsigned long long stage_bar;                   // mbarrier of the staged tables (re-armed per set: phase 0)
