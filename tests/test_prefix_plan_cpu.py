@@ -36,7 +36,7 @@ def test_plan_invariants(E):
         assert p.rows >= E and p.e_quad_end % 128 == 0 and p.rows == max(E, p.e_quad_end)
         assert (E - p.e_quad_end) <= 64                                    # the tail dealt one elector per lane is at most two passes
         assert 1 <= p.table_rounds <= max(R, 1)
-        assert 1 <= p.warps_per_cta <= 24
+        assert 1 <= p.warps_per_cta <= 32
         assert p.smem_total == p.smem_cta + p.smem_per_warp * p.warps_per_cta <= BUDGET
         if not stage:
             assert not p.staged
@@ -79,7 +79,7 @@ def test_slot_is_a_bijection_with_conflict_free_passes(E):
 def test_cfg_shapes():
     """The shapes DESIGN.md quotes."""
     st, p = plan(134, 8, 20, 5, 2, 1)
-    assert st == 0 and p.staged and p.chunk == 8 and p.n_chunks == 17 and p.warps_per_cta == 24 and p.smem_tables == 45568
+    assert st == 0 and p.staged and p.chunk == 8 and p.n_chunks == 17 and p.warps_per_cta == 32 and p.smem_tables == 45568
     st, p = plan(134, 8, 20, 20, 1, 1)          # no run-off: all 20 rounds can be full-field, 182 KB of tables still fit
     assert st == 0 and p.staged and p.smem_tables == 182240 and p.warps_per_cta >= 16
     st, p = plan(1024, 8, 50, 5, 2, 0)          # cfg-5: tables through L2
