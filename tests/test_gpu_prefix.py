@@ -514,3 +514,35 @@ def test_pinned_result_pool(eng):
     assert np.array_equal(c.winner, keep)
     assert c.winner.ctypes.data in (addr, c.winner.ctypes.data) and c.winner.flags.writeable
     assert np.array_equal(b.winner, eng.run(p, n, seed=2, engine=PREFIX, precision=FP32).winner)   # b was never overwritten
+
+
+def test_c_abi_error_paths_report_and_leave_the_context_usable(eng):
+    """Every refusal is a status + csim_last_error() message (the reference logs a failed worker and silently drops its trial,
+    simulate.py:350-351; nothing is dropped here), and the context keeps working afterwards."""
+    from conclave_sim_b200 import FP32, FP64, CsimError, make_params
+    roster = G.real_roster()
+    upload(eng, roster)
+    p = to_params(O.ModelParams(**CFG2), EP2)
+    cases = [
+        (dict(engine=9), "bad engine"),
+        (dict(precision=7), "bad precision"),
+        (dict(wiring=5), "bad wiring"),
+        (dict(engine=PREFIX, precision=FP64), "fp32 engine"),
+        (dict(engine=FULL, precision=FP64), "fp32 engine"),
+        (dict(engine=TABLE, wiring=O.WIRING_MODEL), "ref_cli wiring only"),
+        (dict(precision=FP32, tapes=np.zeros((10, 20 * 134))), "tape requires"),
+    ]
+    for kw, needle in cases:
+        with pytest.raises(CsimError) as ei:
+            eng.run([p], 10, seed=1, **kw)
+        assert needle in str(ei.value), (kw, str(ei.value))
+        ok = eng.run([p], 10, seed=1)                                  # the context survives every refusal
+        assert ok.winner.shape == (10,)
+    other = make_params(CFG2, max_rounds=7, supermajority_threshold=0.56)
+    with pytest.raises(CsimError) as ei:
+        eng.run([p, other], 10, seed=1)
+    assert "share max_rounds" in str(ei.value)
+    with pytest.raises(ValueError):
+        eng.run([p], 10, seed=1, precision=FP64, tapes=np.zeros((10, 5)))   # host-side shape check
+    with pytest.raises(TypeError):
+        make_params({"not_a_model_parameter": 1})
