@@ -548,7 +548,7 @@ def test_c_abi_error_paths_report_and_leave_the_context_usable(eng):
         make_params({"not_a_model_parameter": 1})
 
 
-@pytest.mark.parametrize("case_seed", list(range(48)))
+@pytest.mark.parametrize("case_seed", list(range(int(os.environ.get("CSIM_FUZZ_CASES", "48")))))   # CSIM_FUZZ_CASES=N: a longer campaign
 def test_fuzz_engines_vs_oracle(eng, case_seed):
     """Seeded differential fuzzing: random roster (1..220 electors, 1..E regions), random parameters of every kind (negative
     factors, fatigue, stop-candidate, run-off widths / start rounds, thresholds, beta schedules), both wirings.  The fp64
