@@ -592,6 +592,13 @@ def test_fuzz_engines_vs_oracle(eng, case_seed):
             tie = True      # the immune top-n under ties is the one behaviour without a defined reference: same rule both sides
         assert np.array_equal(ex.winner, ref["winner"]) and np.array_equal(ex.rounds, ref["rounds"]), (case_seed, wiring, tie)
         assert np.array_equal(ex.round_tallies, ref["round_tallies"]), (case_seed, wiring)
+        # the same under an injected uniform tape (the mode the reference's own draws are replayed in), dense and table engines
+        nt = 12
+        tape = rng.random((nt, ep.max_rounds * E))
+        ref_t = CO.run(roster, [(mp, ep)], wiring, nt, tapes=tape, want_tallies=True)
+        for en in ((DENSE, TABLE) if wiring == O.WIRING_REF_CLI else (DENSE,)):
+            ex_t = eng.run(p, nt, wiring=wiring, engine=en, precision=FP64, tapes=tape, want_round_tallies=True)
+            assert np.array_equal(ex_t.winner, ref_t["winner"]) and np.array_equal(ex_t.round_tallies, ref_t["round_tallies"]), (case_seed, wiring, en)
         for en in (0, PREFIX, FULL, DENSE, TABLE):
             try:
                 out = eng.run(p, n, seed=seed, wiring=wiring, engine=en, precision=FP32, want_round_tallies=True)
