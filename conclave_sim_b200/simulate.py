@@ -250,6 +250,39 @@ def results_from_batch(res: RunResult, candidate_ids: List[Any], supermajority_t
     return out
 
 
+def results_frame(res: RunResult, candidate_ids: List[Any], supermajority_threshold: float, sim_id_begin: int = 0) -> pd.DataFrame:
+    """The results table of src/simulate.py:395-412 (columns sim_id, winner, rounds, reason; winner None -> empty cell) built
+    column-wise from the batch arrays: the same rows results_from_batch yields one dict at a time, without a Python loop over
+    trials (a million trials: ~0.1 s instead of seconds)."""
+    n = len(res.winner)
+    w = np.asarray(res.winner)
+    ids = np.empty(len(candidate_ids) + 1, dtype=object)
+    ids[:-1] = [str(c) for c in candidate_ids]
+    ids[-1] = None                                                    # index -1 = no winner
+    code = np.asarray(res.reason) if res.reason is not None else np.where(w >= 0, _cabi.REASON_WINNER, _cabi.REASON_MAX_ROUNDS)
+    texts = np.empty(3, dtype=object)
+    for c in (_cabi.REASON_MAX_ROUNDS, _cabi.REASON_WINNER, _cabi.REASON_NO_PROBS):
+        texts[c] = reason_text(c, supermajority_threshold)
+    return pd.DataFrame({"sim_id": np.arange(sim_id_begin, sim_id_begin + n, dtype=np.int64), "winner": ids[w],
+                         "rounds": np.asarray(res.rounds).astype(np.int64), "reason": texts[code]})
+
+
+def _write_csv(results_df: pd.DataFrame, path: str) -> None:
+    """pandas' writer; for large tables pyarrow's (same text: header, minimal quoting, empty cell for a missing winner)."""
+    if len(results_df) >= 200_000:
+        try:
+            import pyarrow as pa
+            import pyarrow.csv as pacsv
+            table = pa.Table.from_pandas(results_df, preserve_index=False)
+            with open(path, "wb") as f:                               # pyarrow quotes header names whatever the style: write it here
+                f.write((",".join(results_df.columns) + "\n").encode())
+                pacsv.write_csv(table, f, write_options=pacsv.WriteOptions(include_header=False, quoting_style="none"))
+            return
+        except Exception:                                             # pyarrow missing or too old: pandas does the same, slower
+            pass
+    results_df.to_csv(path, index=False)
+
+
 def _json_default(x):
     if isinstance(x, np.integer):
         return int(x)
@@ -258,12 +291,15 @@ def _json_default(x):
     return x
 
 
-def write_outputs(results: List[Dict[str, Any]], aggregate_stats: Dict[str, Any], output_results: str, output_stats: str):
-    """src/simulate.py:395-426."""
-    rows = [{"sim_id": r["sim_id"], "winner": r["winner"], "rounds": r["rounds"], "reason": r["reason"]} for r in results]
-    results_df = pd.DataFrame(rows)
+def write_outputs(results, aggregate_stats: Dict[str, Any], output_results: str, output_stats: str):
+    """src/simulate.py:395-426.  `results` = the list of per-trial dicts of the reference, or the results_frame of a batch."""
+    if isinstance(results, pd.DataFrame):
+        results_df = results
+    else:
+        rows = [{"sim_id": r["sim_id"], "winner": r["winner"], "rounds": r["rounds"], "reason": r["reason"]} for r in results]
+        results_df = pd.DataFrame(rows)
     try:
-        results_df.to_csv(output_results, index=False)
+        _write_csv(results_df, output_results)
         log.info(f"Saving simulation results ({len(results_df)} rows) to: {output_results}")
     except Exception as exc:
         log.error(f"Failed to save results CSV: {exc}")
@@ -297,7 +333,8 @@ def main(argv: Optional[List[str]] = None):
     model_params = model_params_from_args(args)
 
     start = time.time()
-    results: List[Dict[str, Any]] = []
+    results: Any = []
+    aggregate_stats = None
     try:
         batch = run_simulations(
             elector_data_full, model_params, args.num_simulations, max_rounds=args.max_rounds,
@@ -306,12 +343,17 @@ def main(argv: Optional[List[str]] = None):
             fatigue_threshold_rounds=args.fatigue_threshold_rounds,
             fatigue_vote_share_threshold=args.fatigue_vote_share_threshold,
             fatigue_top_n_immune=args.fatigue_top_n_immune, enable_stop_candidate=args.enable_stop_candidate)
-        results = results_from_batch(batch, list(elector_data_full.index), args.supermajority_threshold)
+        ids = list(elector_data_full.index)
+        # the results table column-wise and the statistics straight from the device histograms: the same values as
+        # results_from_batch + aggregate_results (tests/test_gpu_parity.py::test_sweep_stats_and_legacy_shim), no per-trial Python
+        results = results_frame(batch, ids, args.supermajority_threshold)
+        aggregate_stats = stats_from_histograms(batch.winner_hist[0], batch.rounds_hist[0], batch.totals[0], ids, args.num_simulations)
     except Exception as exc:   # the reference logs worker errors and carries on with what it has (:350-351)
         log.error(f"Error in simulation worker: {exc}", exc_info=True)
     log.info(f"Simulation time: {time.time() - start:.2f} seconds")
 
-    aggregate_stats = aggregate_results(results, args.num_simulations)
+    if aggregate_stats is None:
+        aggregate_stats = aggregate_results([], args.num_simulations)
     log.info(f"Calculated aggregate stats: {aggregate_stats}")
     write_outputs(results, aggregate_stats, args.output_results, args.output_stats)
 

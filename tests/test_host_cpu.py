@@ -259,3 +259,33 @@ def test_vote_thresholds_reproduce_the_share_tests(lib):
             hi = lib.csim_vote_threshold(float(s), E, 1)
             assert np.array_equal(sh < s, v < lo), (E, s)
             assert np.array_equal(sh > s, v >= hi), (E, s)
+
+
+def test_results_frame_and_fast_csv_equal_the_row_by_row_path(tmp_path):
+    """The CLI builds its results table column-wise (results_frame) and writes large tables with pyarrow: both must give
+    exactly what the reference's row-by-row route gives (results_from_batch -> DataFrame(rows).to_csv, simulate.py:395-412)."""
+    import pandas as pd
+    from conclave_sim_b200 import simulate as S
+    from conclave_sim_b200.engine import RunResult
+    rng = np.random.default_rng(0)
+    E = 134
+    ids = [f"E{i:03d}" for i in range(E)]
+    for n, with_reason in ((1000, True), (250_000, True), (3000, False)):
+        w = rng.integers(-1, E, n).astype(np.int32)
+        r = rng.integers(1, 21, n).astype(np.int32)
+        reason = np.where(w >= 0, 1, rng.choice([0, 2], n)).astype(np.uint8) if with_reason else None
+        res = RunResult(w, r, reason, None, None, None, None, None, E)
+        df = S.results_frame(res, ids, 0.56, sim_id_begin=7)
+        rows = pd.DataFrame(S.results_from_batch(res, ids, 0.56, sim_id_begin=7))
+        assert list(df.columns) == ["sim_id", "winner", "rounds", "reason"] and len(df) == n
+        assert df["winner"].isna().sum() == int((w < 0).sum())
+        a, b = tmp_path / "fast.csv", tmp_path / "rows.csv"
+        S._write_csv(df, str(a))                      # pyarrow for n >= 200 000, pandas below
+        rows.to_csv(b, index=False)
+        assert a.read_bytes() == b.read_bytes()
+    # an elector id that needs CSV quoting: the fast writer must hand over to pandas, not mangle it
+    ids2 = list(ids); ids2[3] = 'Doe, John "JD"'
+    res = RunResult(np.full(200_001, 3, np.int32), np.ones(200_001, np.int32), np.ones(200_001, np.uint8), None, None, None, None, None, E)
+    df = S.results_frame(res, ids2, 0.56)
+    S._write_csv(df, str(tmp_path / "q.csv"))
+    assert pd.read_csv(tmp_path / "q.csv")["winner"].iloc[0] == ids2[3]
