@@ -334,6 +334,12 @@ def main():
                                "note": "the same canonical accounting as the dense roofline (10 FP32 + 1 MUFU per pair evaluation); this "
                                        "kernel is the MUFU form with every term inline, so the fraction is what the canonical formulation "
                                        "itself reaches here — the factorised dense kernel's fraction above is the optimised form of the same work"}
+    # what bounds those kernels, from the committed ncu captures (static evidence, not measured by this run)
+    table_engine["ncu"] = {"issue_slots_busy_pct_while_resident": 67, "bound": "shared-memory latency (serial 8-probe searches)",
+                           "source": "profiles/r01_ncu_table_r1b_summary.txt"}
+    prefix_engine["ncu"] = {"issue_slots_busy_pct": 76, "shared_wavefronts_pct_of_peak": 58, "bound": "issue slots, then shared-memory wavefronts",
+                            "source": "profiles/r01_ncu_prefix_model_final_summary.txt"}
+    full_engine["ncu"] = {"issue_slots_busy_pct": 54, "top_stall": "no_instruction", "source": "profiles/r01_ncu_full32_summary.txt"}
     model_wiring_dense = timed_engine(ENGINE_DENSE, WIRING_MODEL, 800)
     model_wiring_dense.update(kernel="k_trials_dense32<LC=8,MODEL=true,FACT=true>",
                               note="`model` wiring (bandwagon + stickiness live, SURVEY 8f.1) on the dense kernel, for comparison")
