@@ -250,8 +250,12 @@ def main():
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms_total, all_rounds, all_pairs, kern_ms_max = tmax[0].item(), tsum[1].item(), tsum[2].item(), tmax[3].item()
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        rank_ms = [round(x[0].item() / args.steps, 4) for x in every]     # per-rank step time: `value` uses the slowest
     else:
         ms_total, all_rounds, all_pairs, kern_ms_max = t[0].item(), t[1].item(), t[2].item(), t[3].item()
+        rank_ms = [round(ms_total / args.steps, 4)]
     value = all_rounds * E / (ms_total * 1e-3)
     conclaves = n_global * args.steps / (ms_total * 1e-3)
 
@@ -415,7 +419,7 @@ def main():
     line = {
         "metric": "elector_rounds_per_sec", "value": value, "unit": "elector-rounds/s",
         "conclaves_per_sec": conclaves, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_total / args.steps, "rank_ms_per_step": rank_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"cfg2 README params x {n_local} trials/GPU/step (cfg3 per-GPU share), synthetic E={E}, "
                                "ref_cli wiring, dense fp32 engine, Philox4x32-10",

@@ -749,6 +749,14 @@ extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
                     : engine == CSIM_ENGINE_PREFIX ? launch_prefix(c, ra, hs, b, out, st)
                     : engine == CSIM_ENGINE_TABLE ? launch_table(c, ra, hs, b, out, st)
                     : (ra->precision == CSIM_FP64 ? launch_exact64(c, ra, hs, b, out, st) : launch_dense32(c, ra, hs, hb, b, out, st));
+    if (s == CSIM_ERR_UNSUPPORTED && ra->engine == CSIM_ENGINE_AUTO) {
+        // AUTO does not refuse a shape one of the engines can run: what its first choice cannot hold in shared memory (e.g. FULL
+        // with 1024 electors x 60 regions of bonus rows) goes to the fp32 dense engine, and what that cannot express (fatigue /
+        // stop-candidate, negative factors, > 64 regions) to the fp64 exact engine, whose tables live in global memory.  The
+        // results are then of CSIM_FP64 quality whatever precision was asked for.  An explicit engine still reports UNSUPPORTED.
+        if (engine != CSIM_ENGINE_DENSE && ra->precision == CSIM_FP32) s = launch_dense32(c, ra, hs, hb, b, out, st);
+        if (s == CSIM_ERR_UNSUPPORTED && !(engine == CSIM_ENGINE_DENSE && ra->precision == CSIM_FP64)) s = launch_exact64(c, ra, hs, b, out, st);
+    }
     if (s != CSIM_OK) return s;
 
     if (!dev) {

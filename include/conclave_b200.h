@@ -51,7 +51,10 @@ typedef enum csim_status {
 /* engine */
 #define CSIM_ENGINE_AUTO  0   /* ref_cli: TABLE when the batch is large enough to fill the GPU and E <= 256 (or fp64), else
                                  PREFIX; model: PREFIX, or FULL for what PREFIX refuses in fp32 (candidate fatigue / stop-candidate
-                                 live, negative bonus / strength / papabile factors); fp64: TABLE (ref_cli) or DENSE (model) */
+                                 live, negative bonus / strength / papabile factors); fp64: TABLE (ref_cli) or DENSE (model).
+                                 A shape the chosen engine cannot hold in shared memory falls through to DENSE and then to
+                                 the fp64 exact engine (global-memory tables): AUTO returns CSIM_ERR_UNSUPPORTED only for
+                                 what no engine runs; an explicitly named engine reports its own limits */
 #define CSIM_ENGINE_DENSE 1   /* every trial re-evaluates its E x C scores each round */
 #define CSIM_ENGINE_TABLE 2   /* ref_cli only: trial-invariant per-round CDF tables, built once */
 #define CSIM_ENGINE_PREFIX 3  /* fp32, both wirings: trial-invariant chunk-prefix tables + per-trial bandwagon /

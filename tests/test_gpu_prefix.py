@@ -555,8 +555,9 @@ def test_fuzz_engines_vs_oracle(eng, case_seed):
     engines must equal the C oracle exactly; every fp32 engine that accepts the case must agree with it per trial up to the
     draws fp32 rounding can flip, and conserve votes."""
     from conclave_sim_b200 import FP32, FP64, CsimError
-    rng = np.random.default_rng(1000 + case_seed)
-    E = int(rng.choice([1, 2, 3, 5, 17, 31, 32, 33, 64, 100, 127, 128, 129, 134, 135, 160, 220]))
+    big = os.environ.get("CSIM_FUZZ_BIG", "0") == "1"       # CSIM_FUZZ_BIG=1: rosters past 256 / 512 electors (the prefix engine's
+    rng = np.random.default_rng((500000 if big else 1000) + case_seed)     # 16-wide chunks and global-memory tables), fewer trials each
+    E = int(rng.choice([257, 300, 511, 513, 640, 1024] if big else [1, 2, 3, 5, 17, 31, 32, 33, 64, 100, 127, 128, 129, 134, 135, 160, 220]))
     base = O.synthetic_roster(E, seed=int(rng.integers(1 << 30)))
     G_ = int(rng.integers(1, min(E, 80) + 1))
     region = rng.integers(0, G_, E).astype(np.int32)
@@ -582,7 +583,7 @@ def test_fuzz_engines_vs_oracle(eng, case_seed):
         fatigue_vote_share_threshold=float(rng.choice([0.02, 0.05, 0.1])), fatigue_top_n_immune=int(rng.choice([0, 1, 3])),
         enable_stop_candidate=mp.enable_stop_candidate)
     p = [to_params(mp, ep)]
-    n = 96
+    n = 24 if big else 96
     seed = int(rng.integers(1 << 40))
     for wiring in (O.WIRING_REF_CLI, O.WIRING_MODEL):
         ref = CO.run(roster, [(mp, ep)], wiring, n, seed=seed, want_tallies=True)
@@ -603,9 +604,36 @@ def test_fuzz_engines_vs_oracle(eng, case_seed):
             try:
                 out = eng.run(p, n, seed=seed, wiring=wiring, engine=en, precision=FP32, want_round_tallies=True)
             except CsimError:
-                assert en in (PREFIX, DENSE, TABLE), (case_seed, wiring, en)      # AUTO and FULL take everything in fp32
+                # AUTO takes everything; FULL everything whose region-bonus rows fit in shared memory (not 1024 electors x 60 regions)
+                assert en in (PREFIX, DENSE, TABLE) or (big and en == FULL and E * G_ > 40000), (case_seed, wiring, en)
                 continue
             played = out.round_tallies[:, 0, :]
             assert (played.sum(axis=1) == E).all(), (case_seed, wiring, en)
             agree = np.mean((out.winner == ref["winner"]) & (out.rounds == ref["rounds"]))
-            assert agree >= 0.85, (case_seed, wiring, en, agree)
+            assert agree >= (0.7 if big else 0.85), (case_seed, wiring, en, agree)
+
+
+def test_auto_falls_through_to_an_engine_that_fits(eng):
+    """1024 electors x 62 regions with candidate fatigue live: PREFIX refuses fatigue, FULL's bonus rows (E x G floats) do not fit
+    in shared memory, the fp32 dense engine has no fatigue -- AUTO must still answer, from the fp64 exact engine, and an
+    explicitly named FULL must say why it cannot."""
+    from conclave_sim_b200 import FP32, FP64, CsimError
+    E, G_ = 1024, 62
+    base = O.synthetic_roster(E, seed=5)
+    region = (np.arange(E) % G_).astype(np.int32)
+    roster = O.Roster.from_arrays(base.ideology, region, base.papabile)
+    upload(eng, roster)
+    mp = O.ModelParams(enable_candidate_fatigue=True, fatigue_penalty_factor=0.5, bandwagon_strength=0.7, stickiness_factor=0.3)
+    ep = O.EngineParams(max_rounds=4, enable_candidate_fatigue=True, fatigue_threshold_rounds=1, fatigue_vote_share_threshold=0.05)
+    p = [to_params(mp, ep)]
+    with pytest.raises(CsimError) as ei:
+        eng.run(p, 8, seed=3, wiring=O.WIRING_MODEL, engine=FULL, precision=FP32)
+    assert "does not fit in shared memory" in str(ei.value)
+    auto = eng.run(p, 8, seed=3, wiring=O.WIRING_MODEL, precision=FP32, want_round_tallies=True)
+    exact = eng.run(p, 8, seed=3, wiring=O.WIRING_MODEL, precision=FP64, want_round_tallies=True)
+    ref = CO.run(roster, [(mp, ep)], O.WIRING_MODEL, 8, seed=3, want_tallies=True)
+    assert np.array_equal(auto.winner, exact.winner) and np.array_equal(auto.round_tallies, exact.round_tallies)
+    assert np.array_equal(exact.winner, ref["winner"]) and np.array_equal(exact.round_tallies, ref["round_tallies"])
+    # ref_cli, same roster: fatigue is inert there and AUTO's first choice runs
+    out = eng.run(p, 8, seed=3, wiring=O.WIRING_REF_CLI, precision=FP32)
+    assert out.winner.shape == (8,)
