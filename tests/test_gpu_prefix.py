@@ -637,3 +637,23 @@ def test_auto_falls_through_to_an_engine_that_fits(eng):
     # ref_cli, same roster: fatigue is inert there and AUTO's first choice runs
     out = eng.run(p, 8, seed=3, wiring=O.WIRING_REF_CLI, precision=FP32)
     assert out.winner.shape == (8,)
+
+
+@pytest.mark.parametrize("E", [2048, 2500])
+def test_rosters_at_and_past_the_prefix_limit(eng, E):
+    """2048 electors is the PREFIX engine's limit (128 chunks of 16); 2500 is past it, where AUTO hands `model` trials to FULL
+    and `ref_cli` trials to whatever fits.  Votes are conserved, fp64 equals the oracle exactly, fp32 agrees per trial."""
+    from conclave_sim_b200 import FP32, FP64
+    roster = O.synthetic_roster(E, seed=E)
+    upload(eng, roster)
+    mp = O.ModelParams(initial_beta_weight=2.0, bandwagon_strength=0.7, stickiness_factor=0.3, regional_affinity_bonus=0.1)
+    ep = O.EngineParams(max_rounds=4, supermajority_threshold=0.5, runoff_threshold_rounds=2, runoff_candidate_count=2)
+    p = [to_params(mp, ep)]
+    n = 6
+    for wiring in (O.WIRING_REF_CLI, O.WIRING_MODEL):
+        ref = CO.run(roster, [(mp, ep)], wiring, n, seed=11, want_tallies=True)
+        ex = eng.run(p, n, seed=11, wiring=wiring, precision=FP64, want_round_tallies=True)
+        assert np.array_equal(ex.winner, ref["winner"]) and np.array_equal(ex.round_tallies, ref["round_tallies"])
+        out = eng.run(p, n, seed=11, wiring=wiring, precision=FP32, want_round_tallies=True)
+        assert (out.round_tallies[:, 0, :].sum(axis=1) == E).all()
+        assert np.mean((out.winner == ref["winner"]) & (out.rounds == ref["rounds"])) >= 0.8
