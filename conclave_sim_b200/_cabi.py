@@ -16,11 +16,17 @@ ENGINE_AUTO, ENGINE_DENSE, ENGINE_TABLE, ENGINE_PREFIX, ENGINE_FULL = 0, 1, 2, 3
 FP32, FP64 = 0, 1
 REASON_MAX_ROUNDS, REASON_WINNER, REASON_NO_PROBS = 0, 1, 2
 BETA_STEPPED, BETA_GROWTH = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
+NCCL_ID_BYTES = 128
+ENGINE_NAMES = {0: "auto", 1: "dense", 2: "table", 3: "prefix", 4: "full"}
 
 EXPORTS = ["csim_abi_version", "csim_last_error", "csim_create", "csim_destroy", "csim_device_info",
            "csim_upload_roster", "csim_beta_schedule", "csim_need_votes", "csim_prob_matrix", "csim_run",
-           "csim_stats", "csim_microbench", "csim_prefix_plan_query", "csim_prefix_slot", "csim_host_alloc", "csim_host_free", "csim_vote_threshold"]
+           "csim_stats", "csim_microbench", "csim_prefix_plan_query", "csim_prefix_slot", "csim_host_alloc", "csim_host_free", "csim_vote_threshold",
+           "csim_last_run_info", "csim_engine_probs", "csim_device_count",
+           "csim_nccl_load", "csim_nccl_version", "csim_nccl_unique_id", "csim_nccl_comm_create", "csim_nccl_comm_destroy",
+           "csim_allreduce_hists", "csim_shard_range",
+           "csim_group_create", "csim_group_destroy", "csim_group_size", "csim_group_ctx", "csim_group_upload_roster", "csim_group_run"]
 
 
 class CsimError(RuntimeError):
@@ -100,8 +106,31 @@ def load_library() -> C.CDLL:
     lib.csim_host_free.restype = C.c_int
     lib.csim_prefix_slot.argtypes = [C.c_int32, C.c_int32]
     lib.csim_prefix_slot.restype = C.c_int32
+    lib.csim_device_count.argtypes = [C.POINTER(C.c_int32)]
+    lib.csim_device_count.restype = C.c_int
+    lib.csim_last_run_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 3
+    lib.csim_engine_probs.argtypes = [C.c_void_p, C.POINTER(CsimParams), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.csim_nccl_load.argtypes = [C.c_char_p]
+    lib.csim_nccl_version.restype = C.c_int32
+    lib.csim_nccl_unique_id.argtypes = [C.c_void_p]
+    lib.csim_nccl_comm_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+    lib.csim_nccl_comm_destroy.argtypes = [C.c_void_p]
+    lib.csim_allreduce_hists.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    lib.csim_shard_range.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.csim_shard_range.restype = None
+    lib.csim_group_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32]
+    lib.csim_group_destroy.argtypes = [C.c_void_p]
+    lib.csim_group_size.argtypes = [C.c_void_p]
+    lib.csim_group_size.restype = C.c_int32
+    lib.csim_group_ctx.argtypes = [C.c_void_p, C.c_int32]
+    lib.csim_group_ctx.restype = C.c_void_p
+    lib.csim_group_upload_roster.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.csim_group_run.argtypes = [C.c_void_p, C.POINTER(CsimRunArgs), C.c_void_p]
     for name in ("csim_create", "csim_destroy", "csim_device_info", "csim_upload_roster", "csim_beta_schedule",
-                 "csim_prob_matrix", "csim_run", "csim_stats", "csim_microbench"):
+                 "csim_prob_matrix", "csim_run", "csim_stats", "csim_microbench", "csim_last_run_info", "csim_engine_probs",
+                 "csim_nccl_load", "csim_nccl_unique_id", "csim_nccl_comm_create", "csim_nccl_comm_destroy", "csim_allreduce_hists",
+                 "csim_group_create", "csim_group_destroy", "csim_group_upload_roster", "csim_group_run"):
         getattr(lib, name).restype = C.c_int
     v = lib.csim_abi_version()
     if v != ABI_VERSION:
@@ -114,3 +143,26 @@ def check(status: int):
     if status != 0:
         msg = load_library().csim_last_error()
         raise CsimError(status, msg.decode("utf-8", "replace") if msg else "")
+
+
+def nccl_library_path():
+    """The NCCL copy the process should bind: the wheel-bundled one next to torch (the copy torch itself loads, so one NCCL
+    per process), found WITHOUT importing torch; None -> csim_nccl_load falls back to the loader's search path."""
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+        cand = os.path.join(base, "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            return cand
+    return None
+
+
+def nccl_load() -> int:
+    """Bind NCCL (idempotent); returns its version code.  Raises CsimError when no NCCL can be loaded."""
+    lib = load_library()
+    path = os.environ.get("CSIM_NCCL_LIB") or nccl_library_path()
+    check(lib.csim_nccl_load(path.encode() if path else None))
+    return int(lib.csim_nccl_version())

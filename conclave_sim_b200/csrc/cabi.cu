@@ -27,6 +27,10 @@
 
 static thread_local std::string g_err;
 
+#ifndef CSIM_GRID_TILE
+#define CSIM_GRID_TILE 65535           // gridDim.y / .z limit: the table-build launches are tiled over (set, round)
+#endif
+
 static csim_status fail(csim_status st, const char* fmt, ...) {
     char buf[512];
     va_list ap;
@@ -60,7 +64,20 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// csim_engine_probs: while one is set on the context, the launchers pick the PROBE instantiation of their trial kernel
+struct ProbeReq {
+    int round = 1;
+    const int32_t* prev_vote = nullptr;     // device copies
+    const int32_t* prev_count = nullptr;
+    const uint8_t* fatigued = nullptr;
+    float* scores = nullptr;                // [E][E]
+    float* prefix = nullptr;                // [E][cap]
+    int cap = 0;
+    int nch = 0, chunk = 0;                 // filled by the launcher
+};
+
 struct csim_ctx {
+    ProbeReq* probe = nullptr;
     int device = 0;
     cudaDeviceProp prop{};
     int E = 0, Epad = 0, G = 0;
@@ -70,15 +87,45 @@ struct csim_ctx {
     // host-buffer mode staging
     DevBuf o_winner, o_rounds, o_reason, o_final, o_tallies, o_whist, o_rhist, o_totals, i_tape;
     // prob-matrix staging
-    DevBuf p_prev, p_cnt, p_fat, p_shares, p_bw, p_out, p_cand;
+    DevBuf p_prev, p_cnt, p_fat, p_shares, p_bw, p_out, p_cand, p_pref;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool ev_valid = false;
+    cudaEvent_t ev_busy = nullptr;      // recorded behind the last work a call enqueued: the next call's stream waits on it
+    bool ev_valid = false, busy_valid = false;
     int64_t launches = 0;
     float last_ms = -1.f;
+    int last_engine = CSIM_ENGINE_AUTO, last_precision = CSIM_FP32, last_fell = 0;
 };
+
+// Entry points switch to the context's device; the caller's current device is restored on every exit path.
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// A context serves one stream at a time (its per-batch scratch is overwritten by the next call): every call makes its
+// stream wait on what the previous call enqueued, and leaves its own marker behind.
+static cudaError_t ctx_wait_prev(csim_ctx* c, cudaStream_t st) {
+    return c->busy_valid ? cudaStreamWaitEvent(st, c->ev_busy, 0) : cudaSuccess;
+}
+static cudaError_t ctx_mark_busy(csim_ctx* c, cudaStream_t st) {
+    cudaError_t e = cudaEventRecord(c->ev_busy, st);
+    if (e == cudaSuccess) c->busy_valid = true;
+    return e;
+}
 
 extern "C" int csim_abi_version(void) { return CSIM_ABI_VERSION; }
 extern "C" const char* csim_last_error(void) { return g_err.c_str(); }
+
+extern "C" csim_status csim_device_count(int32_t* n_out) {
+    if (!n_out) return fail(CSIM_ERR_INVALID, "csim_device_count: n is NULL");
+    *n_out = 0;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(CSIM_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    *n_out = n;
+    return CSIM_OK;
+}
 
 extern "C" csim_status csim_create(csim_ctx** out, int device) {
     if (!out) return fail(CSIM_ERR_INVALID, "csim_create: out is NULL");
@@ -89,6 +136,7 @@ extern "C" csim_status csim_create(csim_ctx** out, int device) {
         return fail(CSIM_ERR_CUDA, "csim_create: no usable CUDA device (%s); this engine has no CPU fallback",
                     e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
     if (device < 0 || device >= n) return fail(CSIM_ERR_INVALID, "csim_create: device %d out of range [0,%d)", device, n);
+    DeviceGuard guard;
     CU_TRY(cudaSetDevice(device));
     csim_ctx* c = new csim_ctx();
     c->device = device;
@@ -101,19 +149,23 @@ extern "C" csim_status csim_create(csim_ctx** out, int device) {
     }
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
+    cudaEventCreateWithFlags(&c->ev_busy, cudaEventDisableTiming);
     *out = c;
     return CSIM_OK;
 }
 
 extern "C" csim_status csim_destroy(csim_ctx* c) {
     if (!c) return CSIM_OK;
+    DeviceGuard guard;
     cudaSetDevice(c->device);
+    cudaDeviceSynchronize();             // nothing of this context may still be in flight when its buffers go
     for (DevBuf* b : {&c->x64, &c->x32, &c->region, &c->pap, &c->sets, &c->betas, &c->nbeta, &c->W, &c->tab, &c->cdf64, &c->cdfk64, &c->cdf32, &c->cdfk32, &c->ptab, &c->o_winner, &c->o_rounds,
                       &c->o_reason, &c->o_final, &c->o_tallies, &c->o_whist, &c->o_rhist, &c->o_totals, &c->i_tape,
-                      &c->p_prev, &c->p_cnt, &c->p_fat, &c->p_shares, &c->p_bw, &c->p_out, &c->p_cand})
+                      &c->p_prev, &c->p_cnt, &c->p_fat, &c->p_shares, &c->p_bw, &c->p_out, &c->p_cand, &c->p_pref})
         b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_busy) cudaEventDestroy(c->ev_busy);
     delete c;
     return CSIM_OK;
 }
@@ -130,7 +182,9 @@ extern "C" csim_status csim_device_info(csim_ctx* c, int* sm_count, int* cc_majo
 extern "C" csim_status csim_upload_roster(csim_ctx* c, int32_t E, const double* x, const int32_t* region, const uint8_t* pap) {
     if (!c) return fail(CSIM_ERR_INVALID, "csim_upload_roster: ctx is NULL");
     if (E <= 0 || !x || !region || !pap) return fail(CSIM_ERR_INVALID, "csim_upload_roster: need E > 0 and non-NULL columns (E=%d)", E);
+    DeviceGuard guard;
     CU_TRY(cudaSetDevice(c->device));
+    if (c->busy_valid) CU_TRY(cudaEventSynchronize(c->ev_busy));      // a run still in flight reads the old roster
     // dense region codes (equal code == same region), order of first appearance
     std::map<int32_t, int32_t> code;
     std::vector<int32_t> dense(E);
@@ -251,7 +305,9 @@ extern "C" csim_status csim_prob_matrix(csim_ctx* c, const csim_params* p, doubl
     if (!c || !p || !P_out) return fail(CSIM_ERR_INVALID, "csim_prob_matrix: NULL argument");
     if (c->E <= 0) return fail(CSIM_ERR_STATE, "csim_prob_matrix: roster not uploaded");
     if (precision != CSIM_FP32 && precision != CSIM_FP64) return fail(CSIM_ERR_INVALID, "csim_prob_matrix: bad precision %d", precision);
+    DeviceGuard guard;
     CU_TRY(cudaSetDevice(c->device));
+    if (c->busy_valid) CU_TRY(cudaEventSynchronize(c->ev_busy));      // shares sets / betas / W with csim_run (see header: one stream at a time)
     const int E = c->E;
     const int NC = cand_index ? n_cand : E;
     if (cand_index) {
@@ -277,7 +333,7 @@ extern "C" csim_status csim_prob_matrix(csim_ctx* c, const csim_params* p, doubl
         CU_TRY(c->p_bw.reserve(8 * E));
         CU_TRY(c->p_out.reserve(sizeof(double) * (size_t)E * NC));
         dim3 g((c->Epad + 127) / 128, E, 1);
-        k_base_scores64<<<g, 128>>>(ro, (const DevSet*)c->sets.p, (const double*)c->betas.p, 1, (double*)c->W.p);
+        k_base_scores64<<<g, 128>>>(ro, (const DevSet*)c->sets.p, (const double*)c->betas.p, 1, (double*)c->W.p, 0);
         ++c->launches;
         ProbArgs a;
         a.ro = ro; a.S = S; a.W = (const double*)c->W.p; a.prev_vote = d_prev; a.prev_count = d_cnt; a.fatigued = d_fat;
@@ -327,9 +383,11 @@ static csim_status launch_exact64(csim_ctx* c, const csim_run_args* ra, const st
     if (wbytes > ((size_t)96 << 30)) return fail(CSIM_ERR_UNSUPPORTED, "fp64 base-score tables need %zu bytes", wbytes);
     CU_TRY(c->W.reserve(wbytes));
     RosterDev ro = roster_dev(c);
-    dim3 g((c->Epad + 127) / 128, E, b.n_sets * R);
-    if (g.z > 65535) return fail(CSIM_ERR_UNSUPPORTED, "n_param_sets * max_rounds = %u exceeds 65535 in fp64 mode", g.z);
-    if (R > 0) { k_base_scores64<<<g, 128, 0, st>>>(ro, b.sets, (const double*)c->betas.p, R, (double*)c->W.p); ++c->launches; }
+    for (int sr0 = 0; sr0 < b.n_sets * R; sr0 += CSIM_GRID_TILE) {       // tiled over the 65535 limit of gridDim.z
+        dim3 g((c->Epad + 127) / 128, E, std::min(CSIM_GRID_TILE, b.n_sets * R - sr0));
+        k_base_scores64<<<g, 128, 0, st>>>(ro, b.sets, (const double*)c->betas.p, R, (double*)c->W.p, sr0);
+        ++c->launches;
+    }
     Exact64Args a;
     a.ro = ro; a.b = b; a.out = out; a.W = (const double*)c->W.p; a.wiring = ra->wiring;
     int Fmax = 1, kmax = 1;
@@ -364,7 +422,13 @@ static csim_status launch_dense32_t(csim_ctx* c, Dense32Args& a, cudaStream_t st
     a.warps_per_cta = wpc;
     const size_t smem = a.cta_smem + a.warp_smem * wpc;
     int grid = 1;
-    auto kern = k_trials_dense32<LC, MODEL, FACT>;
+    void (*kern)(Dense32Args) = k_trials_dense32<LC, MODEL, FACT, false>;
+    if (c->probe) {
+        kern = k_trials_dense32<LC, MODEL, FACT, true>;
+        a.probe_round = c->probe->round; a.probe_prev_vote = c->probe->prev_vote; a.probe_prev_count = c->probe->prev_count;
+        a.probe_scores = c->probe->scores; a.probe_prefix = c->probe->prefix; a.probe_cap = c->probe->cap;
+        c->probe->nch = a.nch; c->probe->chunk = a.L;
+    }
     csim_status s = persistent_grid(c, kern, wpc * 32, smem, (uint64_t)a.b.n_sets * a.b.n_sims, wpc, &grid);
     if (s != CSIM_OK) return s;
     if (FACT && a.b.R > 0) {
@@ -372,9 +436,11 @@ static csim_status launch_dense32_t(csim_ctx* c, Dense32Args& a, cudaStream_t st
         const size_t tb = sizeof(float) * (size_t)a.b.n_sets * a.b.R * 4 * CP;
         CU_TRY(c->tab.reserve(tb));
         a.tab = (const float*)c->tab.p;
-        dim3 g((CP + 127) / 128, a.b.n_sets * a.b.R);
-        k_round_tables32<<<g, 128, 0, st>>>(a.ro, a.b.sets, (const double*)c->betas.p, a.b.R, CP, c->x_mid, (float*)c->tab.p);
-        ++c->launches;
+        for (int sr0 = 0; sr0 < a.b.n_sets * a.b.R; sr0 += CSIM_GRID_TILE) {
+            dim3 g((CP + 127) / 128, std::min(CSIM_GRID_TILE, a.b.n_sets * a.b.R - sr0));
+            k_round_tables32<<<g, 128, 0, st>>>(a.ro, a.b.sets, (const double*)c->betas.p, a.b.R, CP, c->x_mid, (float*)c->tab.p, sr0);
+            ++c->launches;
+        }
     }
     CU_TRY(cudaEventRecord(c->ev0, st));
     kern<<<grid, wpc * 32, smem, st>>>(a);
@@ -400,9 +466,9 @@ static csim_status launch_dense32(csim_ctx* c, const csim_run_args* ra, const st
         if (ra->params[i].regional_affinity_bonus < 0 || ra->params[i].bandwagon_strength < 0 || ra->params[i].papabile_weight_factor < 0)
             return fail(CSIM_ERR_UNSUPPORTED, "negative bonus / strength / papabile factor: use CSIM_FP64 precision");
     if (c->G > 64) return fail(CSIM_ERR_UNSUPPORTED, "%d distinct regions (> 64): use CSIM_FP64 precision", c->G);
-    if (b.R > 0 && (size_t)b.n_sets * b.R > 65535) return fail(CSIM_ERR_UNSUPPORTED, "n_param_sets * max_rounds exceeds 65535");
     Dense32Args a;
     a.ro = roster_dev(c); a.b = b; a.out = out; a.nbeta = (const float*)c->nbeta.p; a.wiring = ra->wiring; a.tab = nullptr;
+    a.probe_round = 0; a.probe_prev_vote = nullptr; a.probe_prev_count = nullptr; a.probe_scores = nullptr; a.probe_prefix = nullptr; a.probe_cap = 0;
     int kmax = 1;
     for (const DevSet& s : hs) kmax = std::max(kmax, s.k);
     a.kmax = kmax;
@@ -461,7 +527,6 @@ static csim_status launch_table(csim_ctx* c, const csim_run_args* ra, const std:
     if (ra->wiring != CSIM_WIRING_REF_CLI)
         return fail(CSIM_ERR_UNSUPPORTED, "the table engine exists for the ref_cli wiring only (under `model` the matrix depends on the trial)");
     const int E = c->E, R = b.R;
-    if ((size_t)b.n_sets * R > 65535) return fail(CSIM_ERR_UNSUPPORTED, "n_param_sets * max_rounds exceeds 65535");
     int kmax = 1;
     for (const DevSet& s : hs) kmax = std::max(kmax, s.k);
     const size_t rows = (size_t)b.n_sets * R * E;
@@ -472,11 +537,12 @@ static csim_status launch_table(csim_ctx* c, const csim_run_args* ra, const std:
     CU_TRY(c->cdf64.reserve(sizeof(double) * cdf_elems));
     CU_TRY(c->cdfk64.reserve(sizeof(double) * rows * kmax));
     RosterDev ro = roster_dev(c);
-    dim3 g((c->Epad + 127) / 128, E, b.n_sets * R);
-    if (R > 0) {
-        k_base_scores64<<<g, 128, 0, st>>>(ro, b.sets, (const double*)c->betas.p, R, (double*)c->W.p);
-        dim3 g2((E + 63) / 64, b.n_sets * R);
-        k_cdf_tables64<<<g2, 64, 0, st>>>(ro, b.sets, (const double*)c->W.p, R, kmax, (double*)c->cdf64.p, (double*)c->cdfk64.p);
+    for (int sr0 = 0; sr0 < b.n_sets * R; sr0 += CSIM_GRID_TILE) {       // tiled over the 65535 limit of gridDim.y / .z
+        const int nt = std::min(CSIM_GRID_TILE, b.n_sets * R - sr0);
+        dim3 g((c->Epad + 127) / 128, E, nt);
+        k_base_scores64<<<g, 128, 0, st>>>(ro, b.sets, (const double*)c->betas.p, R, (double*)c->W.p, sr0);
+        dim3 g2((E + 63) / 64, nt);
+        k_cdf_tables64<<<g2, 64, 0, st>>>(ro, b.sets, (const double*)c->W.p, R, kmax, (double*)c->cdf64.p, (double*)c->cdfk64.p, sr0);
         c->launches += 2;
     }
     if (ra->precision == CSIM_FP64)
@@ -496,7 +562,14 @@ static csim_status launch_table(csim_ctx* c, const csim_run_args* ra, const std:
 // ---------------------------------------------------------------------------------------------
 template <bool LC8, bool MODEL, bool STAGE>
 static csim_status launch_prefix_t(csim_ctx* c, PrefixArgs& a, cudaStream_t st) {
-    auto kern = k_trials_prefix<LC8, MODEL, STAGE>;
+    void (*kern)(const PrefixArgs) = k_trials_prefix<LC8, MODEL, STAGE, false>;
+    if (c->probe) {
+        if (STAGE) return fail(CSIM_ERR_STATE, "prefix probe: tables must be read through global memory");
+        kern = k_trials_prefix<LC8, MODEL, false, true>;
+        a.probe_round = c->probe->round; a.probe_prev_vote = c->probe->prev_vote; a.probe_prev_count = c->probe->prev_count;
+        a.probe_scores = c->probe->scores; a.probe_prefix = c->probe->prefix; a.probe_cap = c->probe->cap;
+        c->probe->nch = a.nch; c->probe->chunk = 1 << a.Ls;
+    }
     const int wpc = a.warps_per_cta;
     const size_t smem = a.cta_smem + a.warp_smem * wpc;
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -527,7 +600,6 @@ static bool prefix_supported(const csim_ctx* c, const csim_run_args* ra, const s
     for (int i = 0; i < ra->n_param_sets; ++i)
         if (ra->params[i].regional_affinity_bonus < 0 || ra->params[i].bandwagon_strength < 0 || ra->params[i].papabile_weight_factor < 0) return false;
     if (c->E >= 32768) return false;
-    if (R > 0 && (size_t)ra->n_param_sets * R > 65535) return false;
     int kmax = 1;
     for (const DevSet& s : hs) kmax = std::max(kmax, s.k);
     PrefixArgs probe;                                        // does it fit at all? (many regions make the bonus table large)
@@ -547,7 +619,6 @@ static csim_status launch_prefix(csim_ctx* c, const csim_run_args* ra, const std
     if (ra->precision != CSIM_FP32) return fail(CSIM_ERR_UNSUPPORTED, "the prefix engine is an fp32 engine (use DENSE or TABLE with CSIM_FP64)");
     const int E = c->E, R = b.R;
     if (E >= 32768) return fail(CSIM_ERR_UNSUPPORTED, "prefix engine: at most 32767 electors");
-    if (R > 0 && (size_t)b.n_sets * R > 65535) return fail(CSIM_ERR_UNSUPPORTED, "n_param_sets * max_rounds exceeds 65535");
     const bool model = ra->wiring == CSIM_WIRING_MODEL;
     PrefixArgs a;
     memset(&a, 0, sizeof a);
@@ -559,7 +630,7 @@ static csim_status launch_prefix(csim_ctx* c, const csim_run_args* ra, const std
     int Rt = 1;
     for (const DevSet& s : hs) Rt = std::max(Rt, s.k > 0 ? std::min(R, std::max(s.rr, 1)) : R);
     Rt = std::max(1, std::min(Rt, std::max(R, 1)));
-    const bool stage_ok = getenv("CSIM_PREFIX_NOSTAGE") == nullptr;
+    const bool stage_ok = getenv("CSIM_PREFIX_NOSTAGE") == nullptr && !c->probe;    // a probe reads the same tables through global memory
     const char* ls_env = getenv("CSIM_PREFIX_LS");                  // tuning: force the chunk size (log2)
     if (!prefix_plan(a, E, c->G, R, Rt, kmax, model, (size_t)c->prop.sharedMemPerBlockOptin - 64 /* static: the staging mbarrier */, stage_ok,
                      ls_env ? atoi(ls_env) : 0))
@@ -570,10 +641,10 @@ static csim_status launch_prefix(csim_ctx* c, const csim_run_args* ra, const std
     if (tbytes > ((size_t)64 << 30)) return fail(CSIM_ERR_UNSUPPORTED, "prefix tables need %zu bytes", tbytes);
     CU_TRY(c->ptab.reserve(tbytes));
     a.T = (const float*)c->ptab.p;
-    if (R > 0) {
-        dim3 g((E + 7) / 8, b.n_sets * Rt);
+    for (int sr0 = 0; R > 0 && sr0 < b.n_sets * Rt; sr0 += CSIM_GRID_TILE) {
+        dim3 g((E + 7) / 8, std::min(CSIM_GRID_TILE, b.n_sets * Rt - sr0));
         k_prefix_tables32<<<g, 256, 0, st>>>(a.ro, b.sets, (const double*)c->betas.p, R, Rt, a.Ls, a.nch, a.stride, a.rows, a.e_quad_end,
-                                             a.set_pitch, a.col_major, (float*)c->ptab.p);
+                                             a.set_pitch, a.col_major, (float*)c->ptab.p, sr0);
         ++c->launches;
     }
     const bool lc8 = Ls == 3;
@@ -609,8 +680,16 @@ static csim_status launch_full32(csim_ctx* c, const csim_run_args* ra, const std
         neg = neg || q.regional_affinity_bonus < 0 || q.bandwagon_strength < 0 || q.papabile_weight_factor < 0 || q.stickiness_factor < -1 ||
               q.fatigue_penalty_factor < 0 || q.stop_candidate_boost_factor < 0;
     }
-    void (*kern)(Full32Args) = ext ? (neg ? k_trials_full32<true, true> : k_trials_full32<true, false>)
-                                   : (neg ? k_trials_full32<false, true> : k_trials_full32<false, false>);
+    void (*kern)(const Full32Args) = ext ? (neg ? k_trials_full32<true, true, false> : k_trials_full32<true, false, false>)
+                                         : (neg ? k_trials_full32<false, true, false> : k_trials_full32<false, false, false>);
+    if (c->probe) {
+        kern = ext ? (neg ? k_trials_full32<true, true, true> : k_trials_full32<true, false, true>)
+                   : (neg ? k_trials_full32<false, true, true> : k_trials_full32<false, false, true>);
+        a.probe_round = c->probe->round; a.probe_prev_vote = c->probe->prev_vote; a.probe_prev_count = c->probe->prev_count;
+        a.probe_fatigued = c->probe->fatigued;
+        a.probe_scores = c->probe->scores; a.probe_prefix = c->probe->prefix; a.probe_cap = c->probe->cap;
+        c->probe->nch = a.nch; c->probe->chunk = 8 * a.Lb;
+    }
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpc * 32, smem));
@@ -658,7 +737,9 @@ extern "C" int32_t csim_prefix_slot(int32_t elector, int32_t e_quad_end) { retur
 extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
     if (!c || !ra) return fail(CSIM_ERR_INVALID, "csim_run: NULL argument");
     if (c->E <= 0) return fail(CSIM_ERR_STATE, "csim_run: roster not uploaded");
-    if (!ra->params || ra->n_param_sets < 1) return fail(CSIM_ERR_INVALID, "csim_run: need at least one parameter set");
+    if (ra->n_param_sets < 0) return fail(CSIM_ERR_INVALID, "csim_run: n_param_sets < 0");
+    if ((uint64_t)ra->n_param_sets * ra->n_sims == 0) return CSIM_OK;      // an empty batch (e.g. a rank whose shard is empty) touches nothing
+    if (!ra->params) return fail(CSIM_ERR_INVALID, "csim_run: params is NULL");
     if (!ra->winner || !ra->rounds) return fail(CSIM_ERR_INVALID, "csim_run: winner and rounds outputs are required");
     if (ra->wiring != CSIM_WIRING_REF_CLI && ra->wiring != CSIM_WIRING_MODEL) return fail(CSIM_ERR_INVALID, "csim_run: bad wiring %d", ra->wiring);
     if (ra->precision != CSIM_FP32 && ra->precision != CSIM_FP64) return fail(CSIM_ERR_INVALID, "csim_run: bad precision %d", ra->precision);
@@ -669,10 +750,12 @@ extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
     if (R < 0) return fail(CSIM_ERR_INVALID, "csim_run: max_rounds < 0");
     for (int i = 0; i < ra->n_param_sets; ++i)
         if (ra->params[i].max_rounds != R) return fail(CSIM_ERR_INVALID, "csim_run: every parameter set of a batch must share max_rounds");
+    if ((uint64_t)ra->n_param_sets * (uint64_t)std::max(R, 1) > (1ull << 30)) return fail(CSIM_ERR_INVALID, "csim_run: n_param_sets * max_rounds too large");
     const uint64_t n = (uint64_t)ra->n_param_sets * ra->n_sims;
-    if (n == 0) return CSIM_OK;
+    DeviceGuard guard;
     CU_TRY(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)ra->stream;
+    CU_TRY(ctx_wait_prev(c, st));          // the previous call's kernels still read the scratch this call overwrites
     const int E = c->E;
     const bool dev = ra->buffers_on_device != 0;
 
@@ -749,15 +832,29 @@ extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
                     : engine == CSIM_ENGINE_PREFIX ? launch_prefix(c, ra, hs, b, out, st)
                     : engine == CSIM_ENGINE_TABLE ? launch_table(c, ra, hs, b, out, st)
                     : (ra->precision == CSIM_FP64 ? launch_exact64(c, ra, hs, b, out, st) : launch_dense32(c, ra, hs, hb, b, out, st));
+    int ran_engine = engine, ran_precision = (engine == CSIM_ENGINE_DENSE || engine == CSIM_ENGINE_TABLE) ? ra->precision : CSIM_FP32;
+    int fell = 0;
     if (s == CSIM_ERR_UNSUPPORTED && ra->engine == CSIM_ENGINE_AUTO) {
-        // AUTO does not refuse a shape one of the engines can run: what its first choice cannot hold in shared memory (e.g. FULL
-        // with 1024 electors x 60 regions of bonus rows) goes to the fp32 dense engine, and what that cannot express (fatigue /
-        // stop-candidate, negative factors, > 64 regions) to the fp64 exact engine, whose tables live in global memory.  The
-        // results are then of CSIM_FP64 quality whatever precision was asked for.  An explicit engine still reports UNSUPPORTED.
-        if (engine != CSIM_ENGINE_DENSE && ra->precision == CSIM_FP32) s = launch_dense32(c, ra, hs, hb, b, out, st);
-        if (s == CSIM_ERR_UNSUPPORTED && !(engine == CSIM_ENGINE_DENSE && ra->precision == CSIM_FP64)) s = launch_exact64(c, ra, hs, b, out, st);
+        // AUTO does not refuse a shape one of the engines can run.  What its first choice cannot hold or express goes, in fp32, to
+        // the FULL engine (every term inline, no table-size limits), then to the fp32 dense engine (FULL with 1024 electors x 60
+        // regions of bonus rows does not fit in shared memory), and what that cannot express either (fatigue / stop-candidate,
+        // negative factors, > 64 regions) to the fp64 exact engine, whose tables live in global memory.  In that last case the
+        // results are of CSIM_FP64 quality — and cost — whatever precision was asked for: csim_last_run_info reports it and the
+        // Python host warns.  An explicitly named engine still reports UNSUPPORTED.
+        fell = 1;
+        if (ra->precision == CSIM_FP32 && engine != CSIM_ENGINE_FULL) {
+            s = launch_full32(c, ra, hs, b, out, st); ran_engine = CSIM_ENGINE_FULL; ran_precision = CSIM_FP32;
+        }
+        if (s == CSIM_ERR_UNSUPPORTED && ra->precision == CSIM_FP32 && engine != CSIM_ENGINE_DENSE) {
+            s = launch_dense32(c, ra, hs, hb, b, out, st); ran_engine = CSIM_ENGINE_DENSE; ran_precision = CSIM_FP32;
+        }
+        if (s == CSIM_ERR_UNSUPPORTED && !(engine == CSIM_ENGINE_DENSE && ra->precision == CSIM_FP64)) {
+            s = launch_exact64(c, ra, hs, b, out, st); ran_engine = CSIM_ENGINE_DENSE; ran_precision = CSIM_FP64;
+        }
     }
     if (s != CSIM_OK) return s;
+    c->last_engine = ran_engine; c->last_precision = ran_precision; c->last_fell = fell;
+    CU_TRY(ctx_mark_busy(c, st));
 
     if (!dev) {
         CU_TRY(cudaMemcpyAsync(ra->winner, out.winner, 4 * n, cudaMemcpyDeviceToHost, st));
@@ -793,6 +890,78 @@ extern "C" csim_status csim_host_free(void* p) {
     return CSIM_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// csim_engine_probs: the parity probe (header).  Runs ONE trial of the named engine through its PROBE instantiation.
+// ---------------------------------------------------------------------------------------------
+extern "C" csim_status csim_engine_probs(csim_ctx* c, const csim_params* p, int32_t wiring, int32_t engine, int32_t round,
+                                         const int32_t* prev_vote, const int32_t* prev_count, const uint8_t* fatigued,
+                                         float* scores_out, float* prefix_out, int32_t prefix_capacity, int32_t* n_chunks_out, int32_t* chunk_out) {
+    if (!c || !p || !scores_out || !prefix_out || !n_chunks_out || !chunk_out) return fail(CSIM_ERR_INVALID, "csim_engine_probs: NULL argument");
+    if (c->E <= 0) return fail(CSIM_ERR_STATE, "csim_engine_probs: roster not uploaded");
+    if (round < 1) return fail(CSIM_ERR_INVALID, "csim_engine_probs: round must be >= 1");
+    if (engine != CSIM_ENGINE_DENSE && engine != CSIM_ENGINE_TABLE && engine != CSIM_ENGINE_PREFIX && engine != CSIM_ENGINE_FULL)
+        return fail(CSIM_ERR_INVALID, "csim_engine_probs: name one engine (not AUTO)");
+    if (wiring != CSIM_WIRING_REF_CLI && wiring != CSIM_WIRING_MODEL) return fail(CSIM_ERR_INVALID, "csim_engine_probs: bad wiring %d", wiring);
+    if (engine == CSIM_ENGINE_TABLE && (prev_vote || prev_count || wiring != CSIM_WIRING_REF_CLI))
+        return fail(CSIM_ERR_INVALID, "csim_engine_probs: the table engine exists for the ref_cli wiring only (no previous-round inputs)");
+    const int E = c->E;
+    DeviceGuard guard;
+    CU_TRY(cudaSetDevice(c->device));
+    if (c->busy_valid) CU_TRY(cudaEventSynchronize(c->ev_busy));
+    csim_params q = *p;
+    q.max_rounds = round;
+    q.runoff_candidate_count = 0;                    // no run-off: round `round` is a full-field round
+    int32_t w1 = -1, r1 = 0;
+    csim_run_args ra;
+    memset(&ra, 0, sizeof ra);
+    ra.params = &q; ra.n_param_sets = 1; ra.wiring = wiring; ra.engine = engine; ra.precision = CSIM_FP32;
+    ra.sim_id_begin = 0; ra.n_sims = 1; ra.seed = 1; ra.winner = &w1; ra.rounds = &r1;
+    if (engine == CSIM_ENGINE_TABLE) {
+        if (prefix_capacity < E) return fail(CSIM_ERR_INVALID, "csim_engine_probs: prefix_capacity %d < E = %d (the table engine's rows are whole CDFs)", prefix_capacity, E);
+        csim_status s = csim_run(c, &ra);            // builds cdf32 for rounds 1..round exactly as a batch does
+        if (s != CSIM_OK) return s;
+        std::vector<float> cdf((size_t)E * E);
+        CU_TRY(cudaMemcpy(cdf.data(), (const float*)c->cdf32.p + (size_t)(round - 1) * cdf_round_stride(E), sizeof(float) * (size_t)E * E, cudaMemcpyDeviceToHost));
+        for (int e = 0; e < E; ++e)
+            for (int j = 0; j < E; ++j) {
+                const float v = cdf[(size_t)e * E + j];
+                prefix_out[(size_t)e * prefix_capacity + j] = v;
+                scores_out[(size_t)e * E + j] = j == 0 ? v : v - cdf[(size_t)e * E + j - 1];
+            }
+        *n_chunks_out = E; *chunk_out = 1;
+        return CSIM_OK;
+    }
+    if (prefix_capacity < (E + 7) / 8) return fail(CSIM_ERR_INVALID, "csim_engine_probs: prefix_capacity %d < ceil(E / 8) = %d", prefix_capacity, (E + 7) / 8);
+    ProbeReq req;
+    req.round = round; req.cap = prefix_capacity;
+    if (prev_vote) { CU_TRY(c->p_prev.reserve(4 * E)); CU_TRY(cudaMemcpy(c->p_prev.p, prev_vote, 4 * E, cudaMemcpyHostToDevice)); req.prev_vote = (const int32_t*)c->p_prev.p; }
+    if (prev_count) { CU_TRY(c->p_cnt.reserve(4 * E)); CU_TRY(cudaMemcpy(c->p_cnt.p, prev_count, 4 * E, cudaMemcpyHostToDevice)); req.prev_count = (const int32_t*)c->p_cnt.p; }
+    if (fatigued) { CU_TRY(c->p_fat.reserve(E)); CU_TRY(cudaMemcpy(c->p_fat.p, fatigued, E, cudaMemcpyHostToDevice)); req.fatigued = (const uint8_t*)c->p_fat.p; }
+    CU_TRY(c->p_out.reserve(sizeof(float) * (size_t)E * E));
+    CU_TRY(c->p_pref.reserve(sizeof(float) * (size_t)E * prefix_capacity));
+    CU_TRY(cudaMemset(c->p_out.p, 0, sizeof(float) * (size_t)E * E));
+    CU_TRY(cudaMemset(c->p_pref.p, 0, sizeof(float) * (size_t)E * prefix_capacity));
+    req.scores = (float*)c->p_out.p; req.prefix = (float*)c->p_pref.p;
+    c->probe = &req;
+    csim_status s = csim_run(c, &ra);
+    c->probe = nullptr;
+    if (s != CSIM_OK) return s;
+    if (req.nch > prefix_capacity) return fail(CSIM_ERR_INVALID, "csim_engine_probs: prefix_capacity %d < %d chunks", prefix_capacity, req.nch);
+    CU_TRY(cudaMemcpy(scores_out, c->p_out.p, sizeof(float) * (size_t)E * E, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(prefix_out, c->p_pref.p, sizeof(float) * (size_t)E * prefix_capacity, cudaMemcpyDeviceToHost));
+    *n_chunks_out = req.nch; *chunk_out = req.chunk;
+    return CSIM_OK;
+}
+
+extern "C" csim_status csim_last_run_info(csim_ctx* c, int32_t* engine, int32_t* precision, int32_t* fell_through) {
+    if (!c) return fail(CSIM_ERR_INVALID, "csim_last_run_info: ctx is NULL");
+    if (c->last_engine == CSIM_ENGINE_AUTO) return fail(CSIM_ERR_STATE, "csim_last_run_info: no csim_run has completed on this context");
+    if (engine) *engine = c->last_engine;
+    if (precision) *precision = c->last_precision;
+    if (fell_through) *fell_through = c->last_fell;
+    return CSIM_OK;
+}
+
 extern "C" csim_status csim_stats(csim_ctx* c, int64_t* kernel_launches, float* last_trial_kernel_ms) {
     if (!c) return fail(CSIM_ERR_INVALID, "csim_stats: ctx is NULL");
     if (kernel_launches) *kernel_launches = c->launches;
@@ -810,6 +979,7 @@ extern "C" csim_status csim_stats(csim_ctx* c, int64_t* kernel_launches, float* 
 extern "C" csim_status csim_microbench(csim_ctx* c, int32_t kind, double* ginstr_per_s) {
     if (!c || !ginstr_per_s) return fail(CSIM_ERR_INVALID, "csim_microbench: NULL argument");
     if (kind < 0 || kind > 3) return fail(CSIM_ERR_INVALID, "csim_microbench: kind %d", kind);
+    DeviceGuard guard;
     CU_TRY(cudaSetDevice(c->device));
     float* sink = nullptr;
     CU_TRY(cudaMalloc(&sink, 4));
@@ -839,3 +1009,6 @@ extern "C" csim_status csim_microbench(csim_ctx* c, int32_t kind, double* ginstr
     *ginstr_per_s = best;
     return CSIM_OK;
 }
+
+// the multi-GPU entry points (NCCL bound at run time, csim_group_*)
+#include "multigpu.cuh"

@@ -54,6 +54,15 @@ struct Dense32Args {
     int warps_per_cta;
     size_t cta_smem;        // bytes of CTA-shared tables
     size_t warp_smem;       // bytes per warp
+    // PROBE instantiation only (csim_engine_probs): one trial is started AT round probe_round from the given previous-round
+    // state, and every draw of that round also dumps what it computes with: the chunk prefixes its search probes and the
+    // re-scan scores of every chunk
+    int probe_round;
+    const int32_t* probe_prev_vote;     // [E] or null
+    const int32_t* probe_prev_count;    // [E] or null
+    float* probe_scores;                // [E][C]
+    float* probe_prefix;                // [E][probe_cap]
+    int probe_cap;
 };
 
 #ifndef CSIM_NE
@@ -90,9 +99,9 @@ __device__ __forceinline__ float f2_hi(unsigned long long v) { return __uint_as_
 
 // K0 (FACT): per (set, round) vectors of the factorised exponential, fp64 exp rounded once to fp32.
 // grid = (ceil(CP/128), sets*R), block = 128.
-__global__ void k_round_tables32(RosterDev ro, const DevSet* sets, const double* betas, int R, int CP, double xm, float* tab) {
+__global__ void k_round_tables32(RosterDev ro, const DevSet* sets, const double* betas, int R, int CP, double xm, float* tab, int sr0) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const int sr = blockIdx.y;
+    const int sr = sr0 + blockIdx.y;
     if (c >= CP) return;
     float A = 0.f, Ap = 0.f, BP = 0.f, BPp = 0.f;
     if (c < ro.E) {
@@ -111,6 +120,7 @@ struct LaneCtx32 {              // per-warp / per-round constants of the draw
     float nb, bonus, st1p;
     int C, G, L, nch, step0;
     bool use_bw;
+    float* dbg_scores; float* dbg_prefix; int dbg_cap;      // PROBE only
 };
 
 // One elector's scalars.  FACT: score(e,c) = A * min(BP_c, R * BQ_c);  else A = 1 and x is the ideology.
@@ -198,11 +208,54 @@ __device__ __forceinline__ float probe32(const LaneCtx32& k, const float* pref, 
     return v;
 }
 
+// The 8 scores of chunk jstar of elector e's row with every term inline (LC == 8): what the re-scan of finish_draw sums.
+template <bool MODEL, bool FACT>
+__device__ __forceinline__ void rescan8_scores(const LaneCtx32& k, int jstar, int e, const Elector32& el, float (&v)[8]) {
+    const int c0 = jstar * 8;
+    // vectorised re-scan.  FACT: (xa, xb) hold BQ, (pa, pb) hold BP;  else x and pw
+    const float* src_x = FACT ? k.bq : k.xs;
+    const float4 xa = *reinterpret_cast<const float4*>(src_x + c0), xb = *reinterpret_cast<const float4*>(src_x + c0 + 4);
+    const float4 pa = *reinterpret_cast<const float4*>(k.pw + c0), pb = *reinterpret_cast<const float4*>(k.pw + c0 + 4);
+    const uint32_t rm = k.regmask[jstar * k.G + el.g];                   // bit i: candidate c0+i is of e's region
+    const uint32_t dm = (jstar == (e >> 3)) ? (1u << (e & 7)) : 0u;      // bit i: candidate c0+i is e itself
+    uint32_t pm = 0;
+    float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
+    if (MODEL) {
+        if (el.prev >= 0 && (el.prev >> 3) == jstar) pm = 1u << (el.prev & 7);
+        if (k.use_bw) { ba = *reinterpret_cast<const float4*>(k.bw + c0); bb = *reinterpret_cast<const float4*>(k.bw + c0 + 4); }
+    }
+    const float nb = k.nb;
+#define CSIM_RESCAN(i, xv, pv, bv)                                              \
+    {                                                                       \
+        const float m = FACT ? fminf((pv), el.R * (xv)) : ex2_approx(fabsf(el.x - (xv)) * nb) * (pv); \
+        float s = fmaf(el.A, m, ((rm >> (i)) & 1u) ? k.bonus : 0.0f);       \
+        if (MODEL) { s += (bv); if ((pm >> (i)) & 1u) s *= k.st1p; }        \
+        if ((dm >> (i)) & 1u) s = 0.0f;                                     \
+        v[i] = s;                                                           \
+    }
+    CSIM_RESCAN(0, xa.x, pa.x, ba.x) CSIM_RESCAN(1, xa.y, pa.y, ba.y) CSIM_RESCAN(2, xa.z, pa.z, ba.z) CSIM_RESCAN(3, xa.w, pa.w, ba.w)
+    CSIM_RESCAN(4, xb.x, pb.x, bb.x) CSIM_RESCAN(5, xb.y, pb.y, bb.y) CSIM_RESCAN(6, xb.z, pb.z, bb.z) CSIM_RESCAN(7, xb.w, pb.w, bb.w)
+#undef CSIM_RESCAN
+}
+
 // Phase 2: given the exponential-part prefix over chunks (pref[j * pstride], m units), draw the vote.
-template <int LC, bool MODEL, bool FACT>
+template <int LC, bool MODEL, bool FACT, bool PROBE = false>
 __device__ __forceinline__ int finish_draw(const LaneCtx32& k, const float* pref, int pstride, int e, float u, const Elector32& el) {
     const int C = k.C, L = LC > 0 ? LC : k.L, nch = k.nch;
     const float* rbrow = k.rbp + el.g * nch;
+    if (PROBE) {            // csim_engine_probs: the numbers this draw is made from
+        for (int j = 0; j < nch; ++j) k.dbg_prefix[(size_t)e * k.dbg_cap + j] = probe32<MODEL>(k, pref, pstride, rbrow, el.A, j);
+        for (int js = 0; js < nch; ++js) {
+            if (LC == 8) {
+                float v[8];
+                rescan8_scores<MODEL, FACT>(k, js, e, el, v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) if (js * 8 + i < C) k.dbg_scores[(size_t)e * C + js * 8 + i] = v[i];
+            } else {
+                for (int i = 0; i < L; ++i) if (js * L + i < C) k.dbg_scores[(size_t)e * C + js * L + i] = full_score32<MODEL, FACT>(k, e, js * L + i, el);
+            }
+        }
+    }
     const float S = probe32<MODEL>(k, pref, pstride, rbrow, el.A, nch - 1);
     if (!(S > 0.0f)) {            // all scores vanished: the reference makes the row uniform INCLUDING self (model.py:447-449)
         const int j = (int)(u * (float)C);
@@ -221,31 +274,10 @@ __device__ __forceinline__ int finish_draw(const LaneCtx32& k, const float* pref
     float cum = below;
     int cnt = 0;
     if (LC == 8) {
-        // vectorised re-scan.  FACT: (xa, xb) hold BQ, (pa, pb) hold BP;  else x and pw
-        const float* src_x = FACT ? k.bq : k.xs;
-        const float4 xa = *reinterpret_cast<const float4*>(src_x + c0), xb = *reinterpret_cast<const float4*>(src_x + c0 + 4);
-        const float4 pa = *reinterpret_cast<const float4*>(k.pw + c0), pb = *reinterpret_cast<const float4*>(k.pw + c0 + 4);
-        const uint32_t rm = k.regmask[jstar * k.G + el.g];                   // bit i: candidate c0+i is of e's region
-        const uint32_t dm = (jstar == (e >> 3)) ? (1u << (e & 7)) : 0u;      // bit i: candidate c0+i is e itself
-        uint32_t pm = 0;
-        float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
-        if (MODEL) {
-            if (el.prev >= 0 && (el.prev >> 3) == jstar) pm = 1u << (el.prev & 7);
-            if (k.use_bw) { ba = *reinterpret_cast<const float4*>(k.bw + c0); bb = *reinterpret_cast<const float4*>(k.bw + c0 + 4); }
-        }
-        const float nb = k.nb;
-#define CSIM_RESCAN(i, xv, pv, bv)                                              \
-        {                                                                       \
-            const float m = FACT ? fminf((pv), el.R * (xv)) : ex2_approx(fabsf(el.x - (xv)) * nb) * (pv); \
-            float v = fmaf(el.A, m, ((rm >> (i)) & 1u) ? k.bonus : 0.0f);       \
-            if (MODEL) { v += (bv); if ((pm >> (i)) & 1u) v *= k.st1p; }        \
-            if ((dm >> (i)) & 1u) v = 0.0f;                                     \
-            cum += v;                                                           \
-            cnt += (cum <= tgt) ? 1 : 0;                                        \
-        }
-        CSIM_RESCAN(0, xa.x, pa.x, ba.x) CSIM_RESCAN(1, xa.y, pa.y, ba.y) CSIM_RESCAN(2, xa.z, pa.z, ba.z) CSIM_RESCAN(3, xa.w, pa.w, ba.w)
-        CSIM_RESCAN(4, xb.x, pb.x, bb.x) CSIM_RESCAN(5, xb.y, pb.y, bb.y) CSIM_RESCAN(6, xb.z, pb.z, bb.z) CSIM_RESCAN(7, xb.w, pb.w, bb.w)
-#undef CSIM_RESCAN
+        float v[8];
+        rescan8_scores<MODEL, FACT>(k, jstar, e, el, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { cum += v[i]; cnt += (cum <= tgt) ? 1 : 0; }
     } else {
         for (int i = 0; i < L; ++i) {
             const int c = c0 + i;
@@ -261,7 +293,7 @@ __device__ __forceinline__ int finish_draw(const LaneCtx32& k, const float* pref
     return vote;
 }
 
-template <int LC, bool MODEL, bool FACT>
+template <int LC, bool MODEL, bool FACT, bool PROBE = false>
 __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a) {
     constexpr int NE = CSIM_NE;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -326,6 +358,7 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
     kx.C = C; kx.G = G; kx.L = L; kx.nch = nch; kx.use_bw = false; kx.nb = 0.f; kx.bonus = 0.f; kx.st1p = 1.f;
     kx.step0 = 1;
     while (kx.step0 * 2 <= nch) kx.step0 *= 2;
+    kx.dbg_scores = a.probe_scores; kx.dbg_prefix = a.probe_prefix; kx.dbg_cap = a.probe_cap;
 
     int cur_set = -1;
     float bw_strength = 0.f;
@@ -370,8 +403,16 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
         int winner = -1, rounds = 0, reason = CSIM_REASON_MAX_ROUNDS;
         int ef0 = 0, ef1 = 0;                                    // run-off pair when fast2
         if (R == 0) { for (int c = lane; c < C; c += 32) tally[c] = 0; __syncwarp(); }
+        if (PROBE && MODEL && (a.probe_prev_vote || a.probe_prev_count)) {      // start from the given previous-round state
+            for (int c = lane; c < C; c += 32) {
+                prev_tally[c] = a.probe_prev_count ? a.probe_prev_count[c] : 0;
+                votes[c] = a.probe_prev_vote ? a.probe_prev_vote[c] : -1;
+            }
+            have_prev = true;
+            __syncwarp();
+        }
 
-        for (int r = 1; r <= R; ++r) {
+        for (int r = PROBE ? a.probe_round : 1; r <= R; ++r) {
             rounds = r;
             kx.nb = __ldg(&nbeta[r - 1]);
             kx.use_bw = false;
@@ -450,8 +491,8 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                             Elector32 ei = el[0];
 #pragma unroll
                             for (int m = 1; m < NE; ++m) if (i == m) ei = el[m];
-                            const int vote = finish_draw<LC, MODEL, FACT>(kx, pref + (size_t)i * nch * 32 + lane, 32, e0 + i,
-                                                                          u24_from_word(wa), ei);
+                            const int vote = finish_draw<LC, MODEL, FACT, PROBE>(kx, pref + (size_t)i * nch * 32 + lane, 32, e0 + i,
+                                                                                 u24_from_word(wa), ei);
                             atomicAdd(&tally[vote], 1);
                             if (MODEL) votes[e0 + i] = vote;   // read only by this lane for its own electors: in-place is safe
                         }
@@ -488,7 +529,7 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                     if (act && sub == 0) {
                         float run = 0.f;
                         for (int j = 0; j < nch; ++j) { run += cl[j]; cl[j] = run; }
-                        const int vote = finish_draw<LC, MODEL, FACT>(kx, cl, 1, e, u24_from_word(wa), el);
+                        const int vote = finish_draw<LC, MODEL, FACT, PROBE>(kx, cl, 1, e, u24_from_word(wa), el);
                         atomicAdd(&tally[vote], 1);
                         if (MODEL) votes[e] = vote;
                     }
@@ -549,6 +590,7 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                 if (lane == 0) { tally[ef0] = n0; tally[ef1] = n1; }
             }
             __syncwarp();
+            if (PROBE) break;                                    // one round is all a probe plays
             // ---------------- close the round -----------------------------------------------------
             if (a.out.round_tallies)
                 for (int c = lane; c < C; c += 32)

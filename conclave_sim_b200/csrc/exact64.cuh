@@ -15,12 +15,12 @@
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------
-// K0: base scores.  grid = (ceil(Epad/128), C, sets*R), block = 128 (threads over e).
+// K0: base scores.  grid = (ceil(Epad/128), C, <= 65535 of the sets*R tables from sr0), block = 128 (threads over e).
 // ---------------------------------------------------------------------------
-__global__ void k_base_scores64(RosterDev ro, const DevSet* sets, const double* betas /*[sets][R]*/, int R, double* W) {
+__global__ void k_base_scores64(RosterDev ro, const DevSet* sets, const double* betas /*[sets][R]*/, int R, double* W, int sr0) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const int c = blockIdx.y;
-    const int sr = blockIdx.z;                 // set * R + (round - 1)
+    const int sr = sr0 + blockIdx.z;           // set * R + (round - 1); sr0: launches are tiled over the 65535 grid limit
     if (e >= ro.Epad) return;
     const int set = sr / R;
     double v = 0.0;

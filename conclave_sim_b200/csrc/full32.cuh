@@ -40,6 +40,14 @@ struct Full32Args {
     // byte offsets (host-computed, full32_layout)
     uint32_t o_xs, o_pw, o_rb, o_xg, o_nbs;                                                  // CTA part
     uint32_t w_bw, w_phi, w_col, w_tally, w_eff, w_votes, w_hist, w_avg, w_fat, w_mark, w_thr; // warp part
+    // PROBE instantiation only (csim_engine_probs): see Dense32Args; probe_fatigued = the fatigue mask to apply (or null)
+    int probe_round;
+    const int32_t* probe_prev_vote;
+    const int32_t* probe_prev_count;
+    const uint8_t* probe_fatigued;
+    float* probe_scores;
+    float* probe_prefix;
+    int probe_cap;
 };
 
 __host__ inline bool full32_plan(Full32Args& a, int E, int G, int R, int kmax, int Fmax, size_t budget) {
@@ -145,7 +153,7 @@ __device__ __forceinline__ float full32_score1(const Full32Ctx& k, int c, int e,
     return NEG ? fmaxf(s, 0.0f) : s;
 }
 
-template <bool EXT, bool NEG>
+template <bool EXT, bool NEG, bool PROBE = false>
 __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const __grid_constant__ Full32Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int lane = threadIdx.x & 31;
@@ -225,8 +233,20 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
             for (int c = lane; c < CP; c += 32) { bw[c] = 0.0f; phi[c] = c < C ? 1.0f : 0.0f; }
             if (R == 0) for (int c = lane; c < C; c += 32) tally[c] = 0;
             __syncwarp();
+            if (PROBE && (a.probe_prev_vote || a.probe_prev_count)) {          // start from the given previous-round state
+                int m = 0;
+                for (int c = lane; c < C; c += 32) {
+                    const int v = a.probe_prev_count ? a.probe_prev_count[c] : 0;
+                    tally[c] = v; hist[c] = v; m = max(m, v);
+                    votes[prefix_slot(c, a.e_quad_end)] = (uint16_t)(a.probe_prev_vote ? a.probe_prev_vote[c] : 0xFFFF);
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_xor_sync(CSIM_FULL, m, off));
+                prev_mx = m; have_prev = true; n_hist = 1;
+                __syncwarp();
+            }
 
-            for (int r = 1; r <= R; ++r) {
+            for (int r = PROBE ? a.probe_round : 1; r <= R; ++r) {
                 rounds = r;
                 kx.nb = nbs[r - 1];
                 // ---- per-round state from round r-1 (tally still holds it) ---------------------------------
@@ -273,9 +293,14 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
                         __syncwarp();
                     }
                     for (int c = lane; c < C; c += 32) phi[c] = (use_fat && fat[c]) ? S.f_fat_pen : 1.0f;
+                    if (PROBE && a.probe_fatigued) for (int c = lane; c < C; c += 32) phi[c] = a.probe_fatigued[c] ? S.f_fat_pen : 1.0f;
                 }
                 // stop-candidate threats, model.py:384-400: candidates whose last share exceeds the threshold
                 int n_thr = 0;
+                // round 1 has no previous shares: the reference tests 0.0 > threshold against every candidate (simulate.py:73,
+                // model.py:397), so with a NEGATIVE threat share every candidate is a threat already then
+                const bool all_thr = S.en_stop && !have_prev && 0.0 > S.stop_T;
+                if (all_thr) n_thr = 33;                                       // more than the list holds: the per-candidate branch below
                 if (S.en_stop && have_prev) {
                     for (int c0 = 0; c0 < C; c0 += 32) {
                         const int c = c0 + lane;
@@ -299,7 +324,8 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
                     const int2 g2 = xg[slot];
                     const float xe = __int_as_float(g2.x);
                     const float* rbrow = rbv + g2.y * CP;
-                    const int prev = sticky_live ? (int)votes[slot] : -1;
+                    int prev = sticky_live ? (int)votes[slot] : -1;
+                    if (PROBE && prev == 0xFFFF) prev = -1;              // probe input: this elector had no previous vote
                     const double xe64 = a.ro.x64[e];
                     bool trig = false;
                     if (n_thr > 0) {
@@ -307,7 +333,7 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
                             for (int q = 0; q < n_thr && !trig; ++q) trig = fabs(xe64 - a.ro.x64[thr[q]]) > S.stop_D;
                         } else {                                     // more threats than the list holds: test every candidate
                             for (int q = 0; q < C && !trig; ++q)
-                                trig = fabs(xe64 - a.ro.x64[q]) > S.stop_D && hist[(size_t)((n_hist - 1) % a.Fmax) * C + q] >= S.stop_cnt;
+                                trig = fabs(xe64 - a.ro.x64[q]) > S.stop_D && (all_thr || hist[(size_t)((n_hist - 1) % a.Fmax) * C + q] >= S.stop_cnt);
                         }
                     }
                     int vote;
@@ -335,6 +361,15 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
                             if (j == je) run += d_self;
                             if (j == jp) run += d_prev;
                             col[32 * j] = run;
+                        }
+                        if (PROBE) {                                  // csim_engine_probs: the numbers this draw is made from
+                            for (int j = 0; j < nch; ++j) a.probe_prefix[(size_t)e * a.probe_cap + j] = col[32 * j];
+                            for (int blk = 0; blk < nblk; ++blk) {
+                                float v[8];
+                                full32_score8<false, EXT, NEG>(kx, blk, e, xe, xe64, rbrow, prev, trig, v);
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) if (8 * blk + q < C) a.probe_scores[(size_t)e * C + 8 * blk + q] = v[q];
+                            }
                         }
                         const float Sm = run;
                         if (!(Sm > 0.0f)) {                           // model.py:447-449: uniform row INCLUDING self
@@ -394,6 +429,7 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
                     votes[slot] = (uint16_t)vote;                    // read back only by this lane: in place is safe
                 });
                 __syncwarp();
+                if (PROBE) break;                                    // one round is all a probe plays
                 // ---- close the round ---------------------------------------------------------------------
                 if (a.out.round_tallies)
                     for (int c = lane; c < C; c += 32)

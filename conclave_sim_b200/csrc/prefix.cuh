@@ -69,6 +69,13 @@ struct PrefixArgs {
     uint32_t w_bwp, w_tally, w_eff, w_votes, w_mark;   // from the warp's block (bandwagon f32[CPP] sits at 0)
     uint32_t cp4;                                      // 4 * CPP: byte pitch of the per-candidate arrays
     int nch4, step0_4;                                 // 4 nch; 4 x (largest power of two <= nch)
+    // PROBE instantiation only (csim_engine_probs): see Dense32Args
+    int probe_round;
+    const int32_t* probe_prev_vote;
+    const int32_t* probe_prev_count;
+    float* probe_scores;
+    float* probe_prefix;
+    int probe_cap;
 };
 
 // fills the offsets above from (E, G, R, Ls, nch, rows, kmax, tab_smem); returns nothing the caller has to size by hand
@@ -180,9 +187,10 @@ __host__ inline bool prefix_plan(PrefixArgs& a, int E, int G, int R, int Rt, int
 // terms is model.py:311-324: exp, papabile factor, regional bonus), an inclusive warp scan makes the prefixes.
 // grid = (ceil(E / 8), sets * Rt), block = 256.
 __global__ void k_prefix_tables32(RosterDev ro, const DevSet* sets, const double* betas, int R, int Rt, int Ls, int nch, int stride,
-                                  int rows, int e_quad_end, size_t set_pitch, int col_major, float* T) {
+                                  int rows, int e_quad_end, size_t set_pitch, int col_major, float* T, int sr0) {
     const int lane = threadIdx.x & 31, e = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int set = blockIdx.y / Rt, r0 = blockIdx.y - set * Rt;       // r0 = round - 1
+    const int sr = sr0 + blockIdx.y;
+    const int set = sr / Rt, r0 = sr - set * Rt;                        // r0 = round - 1
     const int C = ro.E;
     if (e >= C) return;
     const DevSet* S = &sets[set];
@@ -261,9 +269,34 @@ __device__ __forceinline__ float prefix_full_score(const PrefixCtx& k, const Pre
     return c == e ? 0.0f : v;
 }
 
+// The 8 re-scan scores of the block of 8 candidates starting at cb (padded offset o), every term inline in roster order.
+template <bool MODEL>
+__device__ __forceinline__ void prefix_scores8(const PrefixCtx& k, const PrefixArgs& a, uint32_t rbrow, float xe, float nb, int e, int prev, int cb,
+                                               uint32_t o, float (&v)[8]) {
+    const float4 xa = lds_f4(PFX_XS(k, a) + o), xb = lds_f4(PFX_XS(k, a) + o + 16);
+    const float4 pa = lds_f4(PFX_PW(k, a) + o), pb = lds_f4(PFX_PW(k, a) + o + 16);     // 0 beyond C: padding scores nothing
+    const float4 ra = lds_f4(rbrow + o), rb = lds_f4(rbrow + o + 16);        // regional bonus of e's region
+    float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
+    if (MODEL) { ba = lds_f4(PFX_BW(k, a) + o); bb = lds_f4(PFX_BW(k, a) + o + 16); }
+    const int is = e - cb;                               // position of e itself / of prev inside this block (else outside 0..7)
+    const int ip = MODEL ? prev - cb : -1;
+#define CSIM_PRESCAN(i, xv, pv, rv, bv)                                                  \
+    {                                                                                \
+        float s = fmaf(ex2_approx(fabsf(xe - (xv)) * nb), (pv), (rv));               \
+        if (MODEL) { s += (bv); if (ip == (i)) s *= k.st1p; }                        \
+        if (is == (i)) s = 0.0f;                                                     \
+        v[i] = s;                                                                    \
+    }
+    CSIM_PRESCAN(0, xa.x, pa.x, ra.x, ba.x) CSIM_PRESCAN(1, xa.y, pa.y, ra.y, ba.y)
+    CSIM_PRESCAN(2, xa.z, pa.z, ra.z, ba.z) CSIM_PRESCAN(3, xa.w, pa.w, ra.w, ba.w)
+    CSIM_PRESCAN(4, xb.x, pb.x, rb.x, bb.x) CSIM_PRESCAN(5, xb.y, pb.y, rb.y, bb.y)
+    CSIM_PRESCAN(6, xb.z, pb.z, rb.z, bb.z) CSIM_PRESCAN(7, xb.w, pb.w, rb.w, bb.w)
+#undef CSIM_PRESCAN
+}
+
 // One vote of a full-field round.  STAGE: trow = shared address of this elector's row of the round's chunk-prefix
 // table; else Tg = its first entry in the global table (row- or column-major, PrefixArgs::col_major).
-template <bool LC8, bool MODEL, bool STAGE>
+template <bool LC8, bool MODEL, bool STAGE, bool PROBE = false>
 __device__ __forceinline__ int prefix_draw(const PrefixCtx& k, const PrefixArgs& a, uint32_t trow, const float* __restrict__ Tg, int e, int slot,
                                            float u, int prev) {
     const int Ls = LC8 ? 3 : a.Ls, nch4 = a.nch4, C = a.ro.E;
@@ -295,6 +328,15 @@ __device__ __forceinline__ int prefix_draw(const PrefixCtx& k, const PrefixArgs&
         }
         return v;
     };
+    if (PROBE) {                  // csim_engine_probs: the numbers this draw is made from
+        for (int j4 = 0; j4 < nch4; j4 += 4) a.probe_prefix[(size_t)e * a.probe_cap + (j4 >> 2)] = F(j4);
+        for (int cb = 0; cb < C; cb += 8) {
+            float v[8];
+            prefix_scores8<MODEL>(k, a, rbrow, xe, nb, e, prev, cb, 4u * (uint32_t)cb + 4u * (uint32_t)((cb >> Ls) << 2), v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (cb + i < C) a.probe_scores[(size_t)e * C + cb + i] = v[i];
+        }
+    }
     const float S = F(nch4 - 4);
     if (!(S > 0.0f)) {            // all scores vanished: the reference makes the row uniform INCLUDING self (model.py:447-449)
         const int j = (int)(u * (float)C);
@@ -320,26 +362,10 @@ __device__ __forceinline__ int prefix_draw(const PrefixCtx& k, const PrefixArgs&
     for (int bi = 0; bi < nb8; ++bi) {                      // blocks of 8 candidates of the chunk, in roster order
         const int cb = c0 + 8 * bi;
         const uint32_t o = 4u * (uint32_t)cb + 4u * (uint32_t)pos4;     // padded order: 4 extra floats per chunk before this one
-        const float4 xa = lds_f4(PFX_XS(k, a) + o), xb = lds_f4(PFX_XS(k, a) + o + 16);
-        const float4 pa = lds_f4(PFX_PW(k, a) + o), pb = lds_f4(PFX_PW(k, a) + o + 16);     // 0 beyond C: padding scores nothing
-        const float4 ra = lds_f4(rbrow + o), rb = lds_f4(rbrow + o + 16);        // regional bonus of e's region
-        float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
-        if (MODEL) { ba = lds_f4(PFX_BW(k, a) + o); bb = lds_f4(PFX_BW(k, a) + o + 16); }
-        const int is = e - cb;                               // position of e itself / of prev inside this block (else outside 0..7)
-        const int ip = MODEL ? prev - cb : -1;
-#define CSIM_PRESCAN(i, xv, pv, rv, bv)                                                  \
-        {                                                                                \
-            float v = fmaf(ex2_approx(fabsf(xe - (xv)) * nb), (pv), (rv));               \
-            if (MODEL) { v += (bv); if (ip == (i)) v *= k.st1p; }                        \
-            if (is == (i)) v = 0.0f;                                                     \
-            cum += v;                                                                    \
-            cnt += (cum <= tgt) ? 1 : 0;                                                 \
-        }
-        CSIM_PRESCAN(0, xa.x, pa.x, ra.x, ba.x) CSIM_PRESCAN(1, xa.y, pa.y, ra.y, ba.y)
-        CSIM_PRESCAN(2, xa.z, pa.z, ra.z, ba.z) CSIM_PRESCAN(3, xa.w, pa.w, ra.w, ba.w)
-        CSIM_PRESCAN(4, xb.x, pb.x, rb.x, bb.x) CSIM_PRESCAN(5, xb.y, pb.y, rb.y, bb.y)
-        CSIM_PRESCAN(6, xb.z, pb.z, rb.z, bb.z) CSIM_PRESCAN(7, xb.w, pb.w, rb.w, bb.w)
-#undef CSIM_PRESCAN
+        float v[8];
+        prefix_scores8<MODEL>(k, a, rbrow, xe, nb, e, prev, cb, o, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { cum += v[i]; cnt += (cum <= tgt) ? 1 : 0; }
         if (cnt < 8 * (bi + 1)) break;                       // the crossing is inside this block
     }
     int vote = c0 + cnt;                                     // == first c with cum > tgt
@@ -364,7 +390,7 @@ __device__ __noinline__ void prefix_stage_tables(uint32_t dst, const float* src,
     }
 }
 
-template <bool LC8, bool MODEL, bool STAGE>
+template <bool LC8, bool MODEL, bool STAGE, bool PROBE = false>
 __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(const __grid_constant__ PrefixArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int lane = threadIdx.x & 31;
@@ -466,8 +492,20 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(const 
                 for (int j = lane; j < nch; j += 32) bwp[j] = 0.0f;
             }
             __syncwarp();
+            if (PROBE && MODEL && (a.probe_prev_vote || a.probe_prev_count)) {   // start from the given previous-round state
+                int m = 0;
+                for (int c = lane; c < C; c += 32) {
+                    const int v = a.probe_prev_count ? a.probe_prev_count[c] : 0;
+                    tally[c] = v; m = max(m, v);
+                    sts_u16(PFX_VOTES(kx, a) + 2 * prefix_slot(c, a.e_quad_end), a.probe_prev_vote ? a.probe_prev_vote[c] : 0xFFFF);
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_xor_sync(CSIM_FULL, m, off));
+                prev_mx = m; have_prev = true;
+                __syncwarp();
+            }
 
-            for (int r = 1; r <= R; ++r) {
+            for (int r = PROBE ? a.probe_round : 1; r <= R; ++r) {
                 rounds = r;
                 kx.nb = nbs[r - 1];
                 const int rt = min(r, a.Rt) - 1;                     // rounds beyond Rt are run-off rounds: no table
@@ -509,8 +547,9 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(const 
                 if (!have_eff) {
                     // =============== full-field round ==============================================
                     for_each_elector(r, s_lo, s_hi, [&](int e, float u, int slot) {
-                        const int prev = sticky_live ? lds_u16(PFX_VOTES(kx, a) + 2 * slot) : -1;
-                        const int vote = prefix_draw<LC8, MODEL, STAGE>(kx, a, Tr_a + (uint32_t)slot * stride4, Tr_g + (a.col_major ? (size_t)slot : (size_t)slot * a.stride), e, slot, u, prev);
+                        int prev = sticky_live ? lds_u16(PFX_VOTES(kx, a) + 2 * slot) : -1;
+                        if (PROBE && prev == 0xFFFF) prev = -1;              // probe input: this elector had no previous vote
+                        const int vote = prefix_draw<LC8, MODEL, STAGE, PROBE>(kx, a, Tr_a + (uint32_t)slot * stride4, Tr_g + (a.col_major ? (size_t)slot : (size_t)slot * a.stride), e, slot, u, prev);
                         red_inc(PFX_TALLY(kx, a) + 4 * vote);
                         if (MODEL) sts_u16(PFX_VOTES(kx, a) + 2 * slot, vote);   // read back only by this lane: in place is safe
                     });
@@ -578,6 +617,7 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(const 
                     if (lane == 0) { tally[ef0] = n0; tally[ef1] = n1; }
                 }
                 __syncwarp();
+                if (PROBE) break;                                    // one round is all a probe plays
                 // ---------------- close the round -------------------------------------------------
                 if (a.out.round_tallies)
                     for (int c = lane; c < C; c += 32)

@@ -49,9 +49,9 @@ __device__ __forceinline__ void cdf_row_exact64(F& prob, int ncol, double* out) 
 __host__ __device__ inline size_t cdf_round_stride(int E) { return ((size_t)E * E + 3) & ~(size_t)3; }
 
 __global__ void k_cdf_tables64(RosterDev ro, const DevSet* sets, const double* W, int R, int kmax,
-                               double* cdf, double* cdfk) {
+                               double* cdf, double* cdfk, int sr0) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    const int sr = blockIdx.y;                   // set * R + (round - 1)
+    const int sr = sr0 + blockIdx.y;             // set * R + (round - 1)
     const int E = ro.E, C = E;
     if (e >= E) return;
     const DevSet S = sets[sr / R];

@@ -1,9 +1,12 @@
-"""Multi-GPU: trials shard by disjoint sim-id ranges, one process per GPU; the only exchange is
+"""Multi-GPU, one process per GPU (torchrun): trials shard by disjoint sim-id ranges; the only exchange is
 ONE all-reduce (sum, int64) of the concatenated winner / rounds histograms and totals
 (replaces the Counter / mean aggregation of src/simulate.py:356-387 across processes).
 
 Because a trial's Philox stream is keyed by its global sim_id, results are independent of the
-number of ranks.  torch.distributed is plumbing only (NCCL over NVLink on GPUs, gloo in CPU tests).
+number of ranks.  On GPUs the all-reduce is issued through the C ABI (csim_allreduce_hists, NCCL bound by
+the library at run time) on a communicator whose 128-byte id travels through torch.distributed — which is
+plumbing only here (rendezvous, the id broadcast, gloo in the CPU tests).  The single-process form
+(`--devices N`, csim_group_run) lives in engine.EngineGroup.
 """
 from __future__ import annotations
 
@@ -51,14 +54,35 @@ def run_sharded(run_shard: Callable[[int, int], Dict[str, np.ndarray]], n_sims: 
     return dict(winner_hist=wh, rounds_hist=rh, totals=tot, begin=begin, count=count, local=local)
 
 
+_comms: Dict[int, int] = {}
+
+
+def csim_comm(engine) -> Optional[int]:
+    """This rank's ncclComm_t for `engine`'s device (created once per process through the C ABI: rank 0 makes the NCCL id,
+    torch.distributed broadcasts its 128 bytes).  None outside a multi-rank job."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return None
+    if engine.device in _comms:
+        return _comms[engine.device]
+    from .engine import nccl_unique_id
+    box = [nccl_unique_id() if dist.get_rank() == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    comm = engine.nccl_comm_create(box[0], dist.get_world_size(), dist.get_rank())
+    _comms[engine.device] = comm
+    return comm
+
+
 class DeviceBatch:
     """Device-resident buffers of one rank's shard + the stream-ordered run / all-reduce pair
-    (kernel, then NCCL all-reduce of the histogram tensor on the same stream)."""
+    (kernel, then ONE NCCL all-reduce of the packed histogram tensor on the same stream: csim_allreduce_hists on `comm`
+    when one is given, else torch.distributed's)."""
 
-    def __init__(self, engine, n_sets: int, n_sims_local: int, R: int, want_reason: bool = False):
+    def __init__(self, engine, n_sets: int, n_sims_local: int, R: int, want_reason: bool = False, comm: Optional[int] = None):
         import torch
         self.torch = torch
         self.engine = engine
+        self.comm = comm
         E = engine.n_electors
         dev = torch.device("cuda", engine.device)
         n = n_sets * n_sims_local
@@ -75,12 +99,16 @@ class DeviceBatch:
         torch = self.torch
         self.hist.zero_()
         stream = torch.cuda.current_stream(self.winner.device).cuda_stream
-        self.engine.run_device(param_sets, self.n_sims_local, winner=self.winner, rounds=self.rounds, reason=self.reason,
-                               winner_hist=self.winner_hist, rounds_hist=self.rounds_hist, totals=self.totals,
-                               sim_id_begin=sim_id_begin, seed=seed, wiring=wiring, engine=engine, precision=precision,
-                               stream=stream)
+        if self.n_sims_local > 0:          # a rank whose shard is empty (fewer trials than ranks) still joins the all-reduce
+            self.engine.run_device(param_sets, self.n_sims_local, winner=self.winner, rounds=self.rounds, reason=self.reason,
+                                   winner_hist=self.winner_hist, rounds_hist=self.rounds_hist, totals=self.totals,
+                                   sim_id_begin=sim_id_begin, seed=seed, wiring=wiring, engine=engine, precision=precision,
+                                   stream=stream)
         if reduce:
-            allreduce_sum_(self.hist)
+            if self.comm is not None:
+                self.engine.allreduce_hists(self.comm, self.winner_hist, self.rounds_hist, self.totals, self.n_sets, self.R, stream)
+            else:
+                allreduce_sum_(self.hist)
 
     def hists(self):
         flat = self.hist.cpu().numpy()

@@ -7,8 +7,9 @@ whole batch of trials on the GPU.  All numerics happen in the CUDA library behin
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass
-from typing import Any, Dict, List, Optional, Sequence
+import warnings
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -80,6 +81,12 @@ class RunResult:
     totals: np.ndarray                  # int64 [sets, 2]    (sum of rounds played, trials)
     n_electors: int
     kernel_ms: float = -1.0
+    engine: str = ""                    # the engine that ran ("dense" | "table" | "prefix" | "full"): what AUTO resolved to
+    precision: str = ""                 # the arithmetic it ran in ("fp32" | "fp64"); differs from the request only when AUTO
+                                        # fell through to the fp64 exact engine
+    fell_through: bool = False          # AUTO's first choice refused the shape
+    devices: Tuple[int, ...] = ()       # CUDA devices the trials were sharded over
+    kernel_ms_per_device: Tuple[float, ...] = ()
 
     @property
     def elector_rounds(self) -> int:
@@ -259,7 +266,9 @@ class Engine:
         a.winner_hist = _ptr(wh); a.rounds_hist = _ptr(rh); a.totals = _ptr(tot)
         a.buffers_on_device = 0; a.stream = None
         check(self._lib.csim_run(self._ctx, C.byref(a)))
-        return RunResult(winner, rounds, reason, final, tall, wh, rh, tot, E, self.stats()[1])
+        eng_name, prec_name, fell = self.last_run_info(requested_precision=precision) if n else ("", "", False)
+        ms = self.stats()[1]
+        return RunResult(winner, rounds, reason, final, tall, wh, rh, tot, E, ms, eng_name, prec_name, fell, (self.device,), (ms,))
 
     def run_device(self, param_sets: Sequence[CsimParams], n_sims: int, *, winner, rounds, winner_hist=None,
                    rounds_hist=None, totals=None, reason=None, final_votes=None, round_tallies=None,
@@ -280,6 +289,43 @@ class Engine:
         a.buffers_on_device = 1; a.stream = C.c_void_p(int(stream)) if stream else None
         check(self._lib.csim_run(self._ctx, C.byref(a)))
 
+    def last_run_info(self, requested_precision: Optional[int] = None):
+        """(engine name, precision name, fell_through) of the last csim_run: what CSIM_ENGINE_AUTO resolved to.  Warns when the
+        fall-through changed the arithmetic (an fp32 request served by the fp64 exact engine, ~100x slower)."""
+        return _run_info(self._lib, self._ctx, requested_precision)
+
+    def engine_probs(self, params: CsimParams, *, wiring: int, engine: int, round: int = 1, prev_vote=None, prev_count=None,
+                     fatigued=None):
+        """Parity probe (csim_engine_probs): the scores and chunk prefixes the named fp32 TRIAL engine uses in its hot loop for one
+        full-field round.  Returns (scores[E, E] float32, prefix[E, n_chunks] float32, chunk)."""
+        E = self.n_electors
+        pv = None if prev_vote is None else np.ascontiguousarray(prev_vote, np.int32)
+        pc = None if prev_count is None else np.ascontiguousarray(prev_count, np.int32)
+        ft = None if fatigued is None else np.ascontiguousarray(np.asarray(fatigued).astype(bool), np.uint8)
+        scores = np.zeros((E, E), np.float32)
+        cap = max(E, 32)
+        prefix = np.zeros((E, cap), np.float32)
+        nch, chunk = C.c_int32(), C.c_int32()
+        check(self._lib.csim_engine_probs(self._ctx, C.byref(params), int(wiring), int(engine), int(round), _ptr(pv), _ptr(pc), _ptr(ft),
+                                          _ptr(scores), _ptr(prefix), cap, C.byref(nch), C.byref(chunk)))
+        return scores, prefix.reshape(-1)[:E * nch.value].reshape(E, nch.value).copy(), chunk.value
+
+    # ------------------------------------------------------------------ multi-process NCCL (one process per GPU)
+    def nccl_comm_create(self, unique_id: bytes, n_ranks: int, rank: int) -> int:
+        """ncclComm_t (as an int) of this rank on this engine's device; `unique_id` = the 128 bytes rank 0 got from
+        nccl_unique_id() and broadcast to every rank."""
+        _cabi.nccl_load()
+        buf = (C.c_uint8 * _cabi.NCCL_ID_BYTES).from_buffer_copy(unique_id)
+        comm = C.c_void_p()
+        check(self._lib.csim_nccl_comm_create(self._ctx, buf, int(n_ranks), int(rank), C.byref(comm)))
+        return comm.value
+
+    def allreduce_hists(self, comm: int, winner_hist, rounds_hist, totals, n_sets: int, max_rounds: int, stream: int = 0) -> None:
+        """csim_allreduce_hists: in-place NCCL sum of this rank's DEVICE histograms (anything with data_ptr()), enqueued on `stream`."""
+        dp = lambda t: None if t is None else C.c_void_p(int(t.data_ptr()))
+        check(self._lib.csim_allreduce_hists(self._ctx, C.c_void_p(comm), dp(winner_hist), dp(rounds_hist), dp(totals), int(n_sets),
+                                             int(max_rounds), C.c_void_p(int(stream)) if stream else None))
+
     # ------------------------------------------------------------------ diagnostics
     def stats(self):
         n, ms = C.c_int64(), C.c_float()
@@ -292,7 +338,136 @@ class Engine:
         return g.value
 
 
+def _run_info(lib, ctx, requested_precision: Optional[int]):
+    e, p, f = C.c_int32(), C.c_int32(), C.c_int32()
+    check(lib.csim_last_run_info(ctx, C.byref(e), C.byref(p), C.byref(f)))
+    if requested_precision is not None and p.value != requested_precision:
+        warnings.warn(f"conclave_sim_b200: no fp32 engine runs this batch (shape / parameters); CSIM_ENGINE_AUTO fell through to the "
+                      f"fp64 exact engine '{_cabi.ENGINE_NAMES[e.value]}' — results are of fp64 quality but ~100x slower", RuntimeWarning,
+                      stacklevel=3)
+    return _cabi.ENGINE_NAMES[e.value], "fp64" if p.value == FP64 else "fp32", bool(f.value)
+
+
+def nccl_unique_id() -> bytes:
+    """128-byte NCCL id (rank 0 calls this and broadcasts it; see Engine.nccl_comm_create)."""
+    _cabi.nccl_load()
+    buf = (C.c_uint8 * _cabi.NCCL_ID_BYTES)()
+    check(_cabi.load_library().csim_nccl_unique_id(buf))
+    return bytes(buf)
+
+
+def nccl_comm_destroy(comm: int) -> None:
+    check(_cabi.load_library().csim_nccl_comm_destroy(C.c_void_p(comm)))
+
+
+class EngineGroup:
+    """Several CUDA devices driven from ONE process (csim_group_*): the trials of a call are sharded over the devices by disjoint
+    sim-id ranges, the histograms are combined by one NCCL all-reduce and the per-trial rows land in one host array — the
+    replacement of the reference's `-w/--workers` process pool (src/simulate.py:231,330-351).  Same `run` as Engine; results
+    are bit-identical to a single-device run."""
+
+    def __init__(self, devices: Sequence[int]):
+        self._lib = _cabi.load_library()
+        self.devices = tuple(int(d) for d in devices)
+        if len(self.devices) > 1:
+            _cabi.nccl_load()
+        arr = (C.c_int32 * len(self.devices))(*self.devices)
+        self._grp = C.c_void_p()
+        check(self._lib.csim_group_create(C.byref(self._grp), arr, len(self.devices)))
+        self.n_electors = 0
+        self._roster_key = None
+        self._pinned = _PinnedPool(self._lib)
+
+    def close(self):
+        if getattr(self, "_pinned", None) is not None:
+            self._pinned.close()
+        if getattr(self, "_grp", None) is not None and self._grp:
+            self._lib.csim_group_destroy(self._grp)
+            self._grp = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload_roster(self, ideology_score, region_code, is_papabile) -> None:
+        x = np.ascontiguousarray(ideology_score, dtype=np.float64)
+        g = np.ascontiguousarray(region_code, dtype=np.int32)
+        p = np.ascontiguousarray(np.asarray(is_papabile).astype(bool), dtype=np.uint8)
+        if not (x.ndim == g.ndim == p.ndim == 1 and len(x) == len(g) == len(p)):
+            raise ValueError("roster columns must be 1-D and of equal length")
+        key = (x.tobytes(), g.tobytes(), p.tobytes())
+        if key == self._roster_key:
+            return
+        check(self._lib.csim_group_upload_roster(self._grp, len(x), _ptr(x), _ptr(g), _ptr(p)))
+        self.n_electors = len(x)
+        self._roster_key = key
+
+    def run(self, param_sets: Sequence[CsimParams], n_sims: int, *, sim_id_begin: int = 0, seed: int = 0,
+            wiring: int = WIRING_REF_CLI, engine: int = ENGINE_AUTO, precision: int = FP32,
+            tapes: Optional[np.ndarray] = None, want_reason: bool = True, want_final_votes: bool = False,
+            want_round_tallies: bool = False) -> RunResult:
+        E = self.n_electors
+        sets = (CsimParams * len(param_sets))(*param_sets)
+        R = int(sets[0].max_rounds)
+        n = len(param_sets) * int(n_sims)
+        winner = self._pinned.array(n, np.int32)
+        rounds = self._pinned.array(n, np.int32)
+        reason = self._pinned.array(n, np.uint8) if want_reason else None
+        final = np.empty((n, E), np.int32) if want_final_votes else None
+        tall = np.empty((n, R, E), np.int32) if want_round_tallies else None
+        wh = np.zeros((len(param_sets), E + 1), np.int64)
+        rh = np.zeros((len(param_sets), R + 1), np.int64)
+        tot = np.zeros((len(param_sets), 2), np.int64)
+        tp = None
+        if tapes is not None:
+            tp = np.ascontiguousarray(tapes, np.float64)
+            if tp.shape != (n, R * E):
+                raise ValueError(f"uniform tape must have shape ({n}, {R * E}), got {tp.shape}")
+        a = CsimRunArgs()
+        a.params = sets; a.n_param_sets = len(param_sets); a.wiring = wiring; a.engine = engine; a.precision = precision
+        a.sim_id_begin = int(sim_id_begin); a.n_sims = int(n_sims); a.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        a.uniform_tape = _ptr(tp)
+        a.winner = _ptr(winner); a.rounds = _ptr(rounds); a.reason = _ptr(reason)
+        a.final_votes = _ptr(final); a.round_tallies = _ptr(tall)
+        a.winner_hist = _ptr(wh); a.rounds_hist = _ptr(rh); a.totals = _ptr(tot)
+        a.buffers_on_device = 0; a.stream = None
+        kms = (C.c_float * len(self.devices))()
+        check(self._lib.csim_group_run(self._grp, C.byref(a), kms))
+        eng_name = prec_name = ""
+        fell = False
+        if n:
+            # every device resolves AUTO the same way unless its shard is much smaller; report the first device that ran
+            for i in range(len(self.devices)):
+                try:
+                    eng_name, prec_name, fell = _run_info(self._lib, self._lib.csim_group_ctx(self._grp, i), precision)
+                    break
+                except _cabi.CsimError:
+                    continue
+        ms = tuple(float(v) for v in kms)
+        return RunResult(winner, rounds, reason, final, tall, wh, rh, tot, E, max(ms) if ms else -1.0, eng_name, prec_name, fell,
+                         self.devices, ms)
+
+
 _engines: Dict[int, Engine] = {}
+_groups: Dict[Tuple[int, ...], EngineGroup] = {}
+
+
+def get_group(devices: Sequence[int]) -> EngineGroup:
+    """Process-wide engine group per device tuple."""
+    key = tuple(int(d) for d in devices)
+    if key not in _groups:
+        _groups[key] = EngineGroup(key)
+    return _groups[key]
+
+
+def device_count() -> int:
+    """Visible CUDA devices (csim_device_count; 0 when the driver reports none)."""
+    n = C.c_int32(0)
+    if _cabi.load_library().csim_device_count(C.byref(n)) != 0:
+        return 0
+    return int(n.value)
 
 
 def get_engine(device: int = 0) -> Engine:

@@ -6,8 +6,12 @@ result dict), the results CSV (`sim_id,winner,rounds,reason`, :395-412) and the 
 (:374-387,423) that viz.py / generate_visualizations.py consume.
 
 What replaces the reference's ProcessPoolExecutor fan-out (:330-351): ONE batched call into the
-CUDA library for all trials (`run_simulations`).  New, opt-in flags only: --wiring, --seed,
---device, --precision, --engine.
+CUDA library for all trials (`run_simulations`), sharded over the GPUs of the box by disjoint sim-id
+ranges when more than one device is asked for (`--devices N`, or the reference's own `-w/--workers`
+knob read as a device count; also under torchrun, one process per GPU): the per-device histograms are
+combined by ONE NCCL all-reduce and the per-trial rows are concatenated on the host, so the CSV / JSON
+are the same bytes whatever the device count.  New, opt-in flags only: --wiring, --seed, --device,
+--devices, --precision, --engine, --tape.
 
 Wiring: `ref_cli` (default) reproduces what the reference's CLI computes — the
 previous round's votes never reach the model, so bandwagon / stickiness / fatigue /
@@ -28,7 +32,7 @@ import numpy as np
 import pandas as pd
 
 from . import _cabi
-from .engine import Engine, get_engine, make_params, RunResult
+from .engine import Engine, EngineGroup, get_engine, get_group, device_count, make_params, RunResult
 from .ingest import ElectorDataIngester, roster_arrays
 
 logging.basicConfig(level=logging.INFO, format="%(asctime)s - %(name)s - %(levelname)s - %(message)s")
@@ -43,7 +47,7 @@ DEFAULT_RUNOFF_CANDIDATE_COUNT = 2
 
 # Process-wide defaults of the opt-in knobs (the reference draws from an unseeded global RNG, so
 # every process sees a different stream; we draw a fresh Philox key per process unless told).
-RUNTIME: Dict[str, Any] = dict(wiring="ref_cli", seed=None, device=0, precision="fp32", engine="auto")
+RUNTIME: Dict[str, Any] = dict(wiring="ref_cli", seed=None, device=0, devices=None, precision="fp32", engine="auto")
 _WIRING = {"ref_cli": _cabi.WIRING_REF_CLI, "model": _cabi.WIRING_MODEL}
 _PRECISION = {"fp32": _cabi.FP32, "fp64": _cabi.FP64}
 _ENGINE = {"auto": _cabi.ENGINE_AUTO, "dense": _cabi.ENGINE_DENSE, "table": _cabi.ENGINE_TABLE, "prefix": _cabi.ENGINE_PREFIX, "full": _cabi.ENGINE_FULL}
@@ -53,6 +57,50 @@ def _seed() -> int:
     if RUNTIME["seed"] is None:
         RUNTIME["seed"] = int.from_bytes(os.urandom(8), "little")
     return int(RUNTIME["seed"])
+
+
+def resolve_devices(devices=None, device: Optional[int] = None, workers: Optional[int] = None) -> tuple:
+    """The CUDA devices one call shards its trials over.
+    `devices`: None, a count (int or digit string: the first N visible devices), "all", a comma list "0,2,3" or a sequence of
+    ordinals.  With `devices` None the reference's own parallelism knob applies: `workers` (-w/--workers, src/simulate.py:231)
+    is read as a device count, clamped to what the box has; with neither, the single `device`."""
+    first = RUNTIME["device"] if device is None else int(device)
+    if devices is None:
+        if workers is None or int(workers) <= 1:
+            return (first,)
+        n = max(1, min(int(workers), device_count()))
+        return tuple(range(n)) if n > 1 else (first,)
+    if isinstance(devices, str):
+        d = devices.strip().lower()
+        if d == "all":
+            return tuple(range(max(1, device_count())))
+        if "," in d:
+            devices = [int(v) for v in d.split(",") if v.strip() != ""]
+        else:
+            devices = int(d)
+    if isinstance(devices, (int, np.integer)):
+        n = int(devices)
+        if n < 1:
+            raise ValueError("devices must be >= 1")
+        have = device_count()
+        if n > have:
+            raise ValueError(f"{n} devices requested, {have} visible")
+        return tuple(range(n))
+    out = tuple(int(v) for v in devices)
+    if not out or len(set(out)) != len(out):
+        raise ValueError(f"bad device list {devices!r}")
+    return out
+
+
+def _torchrun_world():
+    """(rank, world, local_rank) when this process is one rank of an initialised torch.distributed job, else None."""
+    try:
+        import torch.distributed as dist
+    except Exception:
+        return None
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return None
+    return dist.get_rank(), dist.get_world_size(), int(os.environ.get("LOCAL_RANK", dist.get_rank()))
 
 
 def reason_text(code: int, supermajority_threshold: float) -> str:
@@ -72,12 +120,32 @@ def run_simulations(elector_data_full: pd.DataFrame, model_params: Dict[str, Any
                     sim_id_begin: int = 0, seed: Optional[int] = None, wiring: Optional[str] = None,
                     device: Optional[int] = None, precision: Optional[str] = None, engine: Optional[str] = None,
                     want_final_votes: bool = False, want_round_tallies: bool = False,
-                    uniform_tapes: Optional[np.ndarray] = None) -> RunResult:
-    """All trials of one parameter set in one GPU batch (replaces src/simulate.py:330-351)."""
+                    uniform_tapes: Optional[np.ndarray] = None, devices=None, workers: Optional[int] = None,
+                    distributed: Optional[bool] = None) -> RunResult:
+    """All trials of one parameter set in one batch (replaces src/simulate.py:330-351).
+
+    One device: one launch.  `devices` (count / list / "all", or `workers` read as a device count — resolve_devices): the trials are
+    sharded over the devices by disjoint sim-id ranges from this ONE process (csim_group_run: one NCCL all-reduce of the
+    histograms, rows concatenated on the host).  Inside an initialised torch.distributed job (torchrun, one process per GPU;
+    `distributed` None = detect): this rank runs its shard on its LOCAL_RANK device, the histograms are all-reduced over NCCL
+    through the C ABI (csim_allreduce_hists) and rank 0 receives every rank's rows; the other ranks get their own rows and the
+    global histograms.  Whatever the split, the results equal a single-device run with the same seed."""
     wiring = wiring or RUNTIME["wiring"]
     precision = precision or RUNTIME["precision"]
     engine = engine or RUNTIME["engine"]
-    eng = get_engine(RUNTIME["device"] if device is None else device)
+    tr = _torchrun_world() if distributed in (None, True) else None
+    if distributed is True and tr is None:
+        raise RuntimeError("distributed=True needs an initialised torch.distributed process group with more than one rank")
+    if tr is not None and devices is None and RUNTIME["devices"] is None:
+        return _run_simulations_torchrun(tr, elector_data_full, model_params, num_simulations, max_rounds=max_rounds,
+                                         supermajority_threshold=supermajority_threshold, runoff_threshold_rounds=runoff_threshold_rounds,
+                                         runoff_candidate_count=runoff_candidate_count, enable_candidate_fatigue=enable_candidate_fatigue,
+                                         fatigue_threshold_rounds=fatigue_threshold_rounds,
+                                         fatigue_vote_share_threshold=fatigue_vote_share_threshold, fatigue_top_n_immune=fatigue_top_n_immune,
+                                         enable_stop_candidate=enable_stop_candidate, sim_id_begin=sim_id_begin, seed=seed, wiring=wiring,
+                                         precision=precision, engine=engine)
+    devs = resolve_devices(RUNTIME["devices"] if devices is None else devices, device, workers)
+    eng = get_group(devs) if len(devs) > 1 else get_engine(devs[0])
     x, g, pap = roster_arrays(elector_data_full)
     eng.upload_roster(x, g, pap)
     params = make_params(model_params, max_rounds=max_rounds, supermajority_threshold=supermajority_threshold,
@@ -92,6 +160,66 @@ def run_simulations(elector_data_full: pd.DataFrame, model_params: Dict[str, Any
     return eng.run([params], num_simulations, sim_id_begin=sim_id_begin, seed=_seed() if seed is None else seed,
                    wiring=_WIRING[wiring], engine=_ENGINE[engine], precision=prec, tapes=uniform_tapes,
                    want_final_votes=want_final_votes, want_round_tallies=want_round_tallies)
+
+
+def load_tapes(path: str, num_simulations: int, max_rounds: int, n_electors: int) -> np.ndarray:
+    """--tape FILE: uniform draws exported from the reference (`.npy`, or `.npz` with an array named `tapes`), one row of
+    max_rounds * E uniforms per trial in elector order per round — e.g. np.random.seed(s); np.random.random_sample(R * E) per
+    trial, the reference's own MT19937 stream.  The fp64 exact engine then reproduces the reference bit for bit."""
+    a = np.load(path)
+    if hasattr(a, "files"):
+        a = a["tapes"]
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if a.ndim == 1:
+        a = a.reshape(1, -1)
+    want = (int(num_simulations), int(max_rounds) * int(n_electors))
+    if a.shape[0] < want[0] or a.shape[1] != want[1]:
+        raise ValueError(f"--tape: {path} has shape {a.shape}, need at least {want[0]} rows of {want[1]} uniforms "
+                         f"(max_rounds {max_rounds} x {n_electors} electors)")
+    return a[:want[0]]
+
+
+_torchrun_state: Dict[str, Any] = {}
+
+
+def _run_simulations_torchrun(tr, elector_data_full, model_params, num_simulations, *, sim_id_begin, seed, wiring, precision, engine,
+                              **engine_kw) -> RunResult:
+    """One rank of a torchrun job: its contiguous shard of the sim ids on its LOCAL_RANK device, ONE NCCL all-reduce of the
+    histograms through the C ABI, every rank's rows gathered on rank 0 (the rank that writes the CSV)."""
+    import torch
+    import torch.distributed as tdist
+    from .dist import DeviceBatch, shard_range, csim_comm
+    rank, world, local_rank = tr
+    eng = get_engine(local_rank)
+    x, g, pap = roster_arrays(elector_data_full)
+    eng.upload_roster(x, g, pap)
+    params = make_params(model_params, **engine_kw)
+    if seed is None:                        # every rank must draw from the SAME Philox key: rank 0's
+        box = [_seed() if rank == 0 else None]
+        tdist.broadcast_object_list(box, src=0)
+        seed = int(box[0])
+    begin, count = shard_range(num_simulations, rank, world)
+    torch.cuda.set_device(local_rank)
+    R = int(params.max_rounds)
+    batch = DeviceBatch(eng, 1, count, R, want_reason=True, comm=csim_comm(eng))
+    batch.run([params], sim_id_begin=int(sim_id_begin) + begin, seed=seed, wiring=_WIRING[wiring], engine=_ENGINE[engine],
+              precision=_PRECISION[precision])
+    wh, rh, tot = batch.hists()
+    # rows: every rank's (winner, rounds, reason) to rank 0, in sim-id order
+    counts = [shard_range(num_simulations, r, world)[1] for r in range(world)]
+    mx = max(counts)
+    pack = torch.zeros(mx, 3, dtype=torch.int32, device=batch.winner.device)
+    if count:
+        pack[:count, 0] = batch.winner; pack[:count, 1] = batch.rounds; pack[:count, 2] = batch.reason.to(torch.int32)
+    got = [torch.empty_like(pack) for _ in range(world)] if rank == 0 else None
+    tdist.gather(pack, got, dst=0)
+    if rank == 0:
+        rows = torch.cat([t[:c] for t, c in zip(got, counts)]).cpu().numpy()
+    else:
+        rows = pack[:count].cpu().numpy()
+    name, prec, fell = eng.last_run_info(requested_precision=_PRECISION[precision]) if count else ("", "", False)
+    return RunResult(np.ascontiguousarray(rows[:, 0]), np.ascontiguousarray(rows[:, 1]), rows[:, 2].astype(np.uint8), None, None,
+                     wh.copy(), rh.copy(), tot.copy(), eng.n_electors, eng.stats()[1], name, prec, fell, (local_rank,), (eng.stats()[1],))
 
 
 def _run_single_simulation_worker(sim_id: int, elector_data_full: pd.DataFrame, model_params: Dict[str, Any],
@@ -146,7 +274,7 @@ def build_parser() -> argparse.ArgumentParser:
     parser.add_argument("-o", "--output-results", type=str, default="data/simulation_results.csv", help="Path to save detailed simulation results.")
     parser.add_argument("-s", "--output-stats", type=str, default="data/simulation_stats.json", help="Path to save aggregate simulation statistics.")
     parser.add_argument("-v", "--verbose", action="store_true", help="Enable verbose logging for simulation workers.")
-    parser.add_argument("-w", "--workers", type=int, default=None, help="Number of worker processes (accepted for compatibility; trials run as one GPU batch).")
+    parser.add_argument("-w", "--workers", type=int, default=None, help="Number of worker processes. Here: the number of GPUs the trials are sharded over (clamped to the visible devices; --devices overrides).")
 
     model_group = parser.add_argument_group("Transition Model Parameters")
     model_group.add_argument("--initial-beta-weight", type=float, default=1.0, help="Initial weight for ideological distance sensitivity.")
@@ -175,6 +303,8 @@ def build_parser() -> argparse.ArgumentParser:
     gpu.add_argument("--wiring", choices=["ref_cli", "model"], default="ref_cli", help="ref_cli: what the reference CLI computes; model: bandwagon/stickiness/fatigue/stop-candidate live.")
     gpu.add_argument("--seed", type=int, default=None, help="Philox key (default: fresh per process, like the reference's unseeded RNG).")
     gpu.add_argument("--device", type=int, default=0, help="CUDA device ordinal.")
+    gpu.add_argument("--devices", type=str, default=None, help="GPUs to shard the trials over: a count (8), a list (0,1,2,3) or 'all'. One NCCL all-reduce of the histograms; same CSV/JSON as one device.")
+    gpu.add_argument("--tape", type=str, default=None, help=".npy/.npz of uniform draws exported from the reference, [num_simulations, max_rounds*E]; forces the fp64 exact engine (bit-exact replay).")
     gpu.add_argument("--precision", choices=["fp32", "fp64"], default="fp32", help="fp32 fast path or fp64 exact path.")
     gpu.add_argument("--engine", choices=["auto", "dense", "table", "prefix", "full"], default="auto")
     return parser
@@ -316,7 +446,20 @@ def write_outputs(results, aggregate_stats: Dict[str, Any], output_results: str,
 def main(argv: Optional[List[str]] = None):
     args = parse_args(argv)
     log.setLevel(logging.DEBUG if args.verbose else logging.INFO)
-    RUNTIME.update(wiring=args.wiring, seed=args.seed, device=args.device, precision=args.precision, engine=args.engine)
+    RUNTIME.update(wiring=args.wiring, seed=args.seed, device=args.device, precision=args.precision, engine=args.engine, devices=None)
+    # torchrun (one process per GPU): join the job; rank 0 writes the outputs
+    owns_pg = False
+    rank = 0
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.devices is None:
+        import torch
+        import torch.distributed as tdist
+        if not tdist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+            torch.cuda.set_device(local_rank)
+            tdist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            owns_pg = True
+        rank = tdist.get_rank()
 
     log.info(f"Starting Conclave simulation with {args.num_simulations} simulations.")
     log.info(f"Parameters: Max Rounds={args.max_rounds}, Supermajority={args.supermajority_threshold*100:.0f}%"
@@ -336,13 +479,17 @@ def main(argv: Optional[List[str]] = None):
     results: Any = []
     aggregate_stats = None
     try:
+        tapes = load_tapes(args.tape, args.num_simulations, args.max_rounds, len(elector_data_full)) if args.tape else None
         batch = run_simulations(
             elector_data_full, model_params, args.num_simulations, max_rounds=args.max_rounds,
             supermajority_threshold=args.supermajority_threshold, runoff_threshold_rounds=args.runoff_rounds,
             runoff_candidate_count=args.runoff_candidates, enable_candidate_fatigue=args.enable_candidate_fatigue,
             fatigue_threshold_rounds=args.fatigue_threshold_rounds,
             fatigue_vote_share_threshold=args.fatigue_vote_share_threshold,
-            fatigue_top_n_immune=args.fatigue_top_n_immune, enable_stop_candidate=args.enable_stop_candidate)
+            fatigue_top_n_immune=args.fatigue_top_n_immune, enable_stop_candidate=args.enable_stop_candidate,
+            uniform_tapes=tapes, devices=args.devices, workers=args.workers)
+        log.info(f"Engine: {batch.engine} ({batch.precision}) on CUDA device(s) {list(batch.devices)}"
+                 + (" [AUTO fell through from its first choice]" if batch.fell_through else ""))
         ids = list(elector_data_full.index)
         # the results table column-wise and the statistics straight from the device histograms: the same values as
         # results_from_batch + aggregate_results (tests/test_gpu_parity.py::test_sweep_stats_and_legacy_shim), no per-trial Python
@@ -354,8 +501,16 @@ def main(argv: Optional[List[str]] = None):
 
     if aggregate_stats is None:
         aggregate_stats = aggregate_results([], args.num_simulations)
+    if rank != 0:                       # torchrun: the rows and the reduced histograms are on rank 0, which writes the outputs
+        if owns_pg:
+            import torch.distributed as tdist
+            tdist.destroy_process_group()
+        return aggregate_stats
     log.info(f"Calculated aggregate stats: {aggregate_stats}")
     write_outputs(results, aggregate_stats, args.output_results, args.output_stats)
+    if owns_pg:
+        import torch.distributed as tdist
+        tdist.destroy_process_group()
 
     sr = aggregate_stats["success_rate"]
     avg = aggregate_stats["average_rounds_successful"]
@@ -416,12 +571,15 @@ def stats_from_histograms(winner_hist: np.ndarray, rounds_hist: np.ndarray, tota
 
 def run_sweep(elector_data_full: pd.DataFrame, param_sets: List[Dict[str, Any]], num_simulations: int, *,
               seed: Optional[int] = None, wiring: Optional[str] = None, device: Optional[int] = None,
-              precision: Optional[str] = None, engine: Optional[str] = None) -> List[Dict[str, Any]]:
+              precision: Optional[str] = None, engine: Optional[str] = None, devices=None) -> List[Dict[str, Any]]:
     """Parameter sweep (BASELINE config 4): every entry of `param_sets` is a dict with the keys of
     make_params (a 'model_params' dict plus max_rounds / supermajority_threshold / runoff_* ...); all sets run in
-    ONE launch with per-CTA parameters and each gets its stats dict from the device histograms."""
+    ONE launch with per-CTA parameters (per device when `devices` names several: every device runs its share of the trials
+    of EVERY set) and each gets its stats dict from the device histograms.  Every set of one sweep must share max_rounds
+    (csim_run's batch limit); sweep max_rounds with one call per value."""
     wiring = wiring or RUNTIME["wiring"]
-    eng = get_engine(RUNTIME["device"] if device is None else device)
+    devs = resolve_devices(RUNTIME["devices"] if devices is None else devices, device)
+    eng = get_group(devs) if len(devs) > 1 else get_engine(devs[0])
     x, g, pap = roster_arrays(elector_data_full)
     eng.upload_roster(x, g, pap)
     sets = []

@@ -15,14 +15,25 @@
  *                           fanned out over trials like         src/simulate.py:330-351
  *                           + the histograms the aggregation    src/simulate.py:356-387
  *                           needs
+ *   csim_group_run       <- the ProcessPoolExecutor fan-out     src/simulate.py:330-351
+ *                           (`-w/--workers`, :231): the trials of one call sharded over the
+ *                           GPUs of one box by disjoint sim-id ranges, histograms combined by
+ *                           ONE NCCL all-reduce (csim_allreduce_hists)
+ *   csim_engine_probs    <- the same model.py:269-560 matrix, but computed with the arithmetic
+ *                           each TRIAL engine uses in its hot loop (parity probe: 1e-5 gate)
  *
  * Conventions: plain pointers and sizes, caller owns every buffer, no
  * exceptions cross the boundary.  Every call returns CSIM_OK (0) or a negative
  * csim_status; csim_last_error() gives the message of the calling thread's
  * last failure.  A context is bound to one CUDA device and owns staging
  * buffers that successive calls reuse: calls on ONE context must be issued
- * from one thread at a time and are ordered on the stream they are given;
- * use one context per host thread (contexts are independent).  There is NO CPU
+ * from one thread at a time; use one context per host thread (contexts are
+ * independent).  A context serves ONE stream at a time: its per-batch scratch
+ * (parameter sets, beta tables, CDF / prefix tables) is overwritten by the next
+ * call, so every call first makes its stream wait (cudaStreamWaitEvent) on the
+ * work the previous call of the same context enqueued — calls on different
+ * streams are therefore serialised, never racing.  Every entry point restores
+ * the calling thread's current CUDA device before it returns.  There is NO CPU
  * fallback: with no usable CUDA device csim_create fails with CSIM_ERR_CUDA.
  */
 #ifndef CONCLAVE_B200_H
@@ -34,7 +45,7 @@
 extern "C" {
 #endif
 
-#define CSIM_ABI_VERSION 1
+#define CSIM_ABI_VERSION 2
 
 typedef enum csim_status {
     CSIM_OK = 0,
@@ -52,9 +63,10 @@ typedef enum csim_status {
 #define CSIM_ENGINE_AUTO  0   /* ref_cli: TABLE when the batch is large enough to fill the GPU and E <= 256 (or fp64), else
                                  PREFIX; model: PREFIX, or FULL for what PREFIX refuses in fp32 (candidate fatigue / stop-candidate
                                  live, negative bonus / strength / papabile factors); fp64: TABLE (ref_cli) or DENSE (model).
-                                 A shape the chosen engine cannot hold in shared memory falls through to DENSE and then to
-                                 the fp64 exact engine (global-memory tables): AUTO returns CSIM_ERR_UNSUPPORTED only for
-                                 what no engine runs; an explicitly named engine reports its own limits */
+                                 A shape the chosen engine cannot hold in shared memory falls through to FULL, then DENSE,
+                                 then the fp64 exact engine (global-memory tables; results are then of CSIM_FP64 quality and
+                                 ~100x slower): AUTO returns CSIM_ERR_UNSUPPORTED only for what no engine runs; an explicitly
+                                 named engine reports its own limits.  csim_last_run_info says which engine / precision ran */
 #define CSIM_ENGINE_DENSE 1   /* every trial re-evaluates its E x C scores each round */
 #define CSIM_ENGINE_TABLE 2   /* ref_cli only: trial-invariant per-round CDF tables, built once */
 #define CSIM_ENGINE_PREFIX 3  /* fp32, both wirings: trial-invariant chunk-prefix tables + per-trial bandwagon /
@@ -113,7 +125,12 @@ typedef struct csim_ctx csim_ctx;
  * trial t = set * n_sims + i simulates parameter set `set` with
  * sim_id = sim_id_begin + i.  Under the native RNG (uniform_tape == NULL) the
  * votes of a trial depend only on (seed, sim_id, params): results do not
- * depend on batching, sharding or device. */
+ * depend on batching, sharding or device.
+ * Limit of a batch: every parameter set must have the same max_rounds (the per-trial
+ * outputs and rounds_hist are dense [.., max_rounds, ..] arrays); a sweep over
+ * max_rounds is one csim_run per distinct value (CSIM_ERR_INVALID otherwise).
+ * n_param_sets * n_sims == 0 is a valid empty batch: the call returns CSIM_OK
+ * without touching any buffer (pointers may then be NULL). */
 typedef struct csim_run_args {
     const csim_params* params;      /* [n_param_sets] (host memory, always) */
     int32_t  n_param_sets;
@@ -146,6 +163,8 @@ typedef struct csim_run_args {
 int         csim_abi_version(void);
 const char* csim_last_error(void);
 
+/* number of CUDA devices visible to the process (0 and CSIM_ERR_CUDA when the driver reports none) */
+csim_status csim_device_count(int32_t* n);
 csim_status csim_create(csim_ctx** out, int device);
 csim_status csim_destroy(csim_ctx* ctx);
 csim_status csim_device_info(csim_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int* clock_khz);
@@ -212,6 +231,72 @@ int32_t     csim_prefix_slot(int32_t elector, int32_t e_quad_end);
  * copies into it run at full PCIe speed.  Optional: any host memory works. */
 csim_status csim_host_alloc(uint64_t bytes, void** out);
 csim_status csim_host_free(void* p);
+
+/* Which engine the last successful csim_run of this context launched (CSIM_ENGINE_DENSE ... CSIM_ENGINE_FULL, never AUTO),
+ * the precision it computed in (CSIM_FP64 when AUTO fell through to the exact engine although CSIM_FP32 was asked for), and
+ * whether AUTO's first choice was refused (fell_through != 0).  Any pointer may be NULL. */
+csim_status csim_last_run_info(csim_ctx* ctx, int32_t* engine, int32_t* precision, int32_t* fell_through);
+
+/* ---------------------------------------------------------------------------------------------
+ * Parity probe: the probabilities a TRIAL engine uses in its hot loop (not the standalone csim_prob_matrix kernels).
+ * One full-field round of one parameter set, computed by a probe kernel that calls the engine's own __device__ routines
+ * (dense: chunk_acc / probe32 / the re-scan of finish_draw on the k_round_tables32 vectors; prefix: k_prefix_tables32 rows +
+ * the re-scan of prefix_draw; full: full32_score8; table: the fp32 CDF rows k_trials_table searches).
+ *   engine      CSIM_ENGINE_DENSE / TABLE / PREFIX / FULL (not AUTO); precision must be CSIM_FP32
+ *   round       1-based: the beta in effect is csim_beta_schedule(p, round, 1)
+ *   prev_vote / prev_count   as csim_prob_matrix (model wiring; NULL = first round).  TABLE: must be NULL (ref_cli only).
+ *                            Stop-candidate (FULL) takes last round's shares as prev_count / E, exactly as a trial does
+ *   fatigued                 FULL only: the candidate-fatigue mask to apply (used iff p->enable_candidate_fatigue), else NULL
+ *   scores_out  [E, E]   float: the per-(elector, candidate) score of the engine's re-scan (TABLE: cdf[e][c] - cdf[e][c-1])
+ *   prefix_out  [E, n_chunks] float: the chunk prefixes the engine's binary search probes, in score units; the last one is
+ *               the row sum S_e the target u*S_e is formed from (TABLE: n_chunks == E, the CDF row itself, S_e == last == 1)
+ *   n_chunks_out, chunk_out  chunks per row and candidates per chunk of that layout
+ * P[e][c] = scores_out[e][c] / prefix_out[e][n_chunks - 1]. */
+csim_status csim_engine_probs(csim_ctx* ctx, const csim_params* p, int32_t wiring, int32_t engine, int32_t round,
+                              const int32_t* prev_vote, const int32_t* prev_count, const uint8_t* fatigued,
+                              float* scores_out, float* prefix_out, int32_t prefix_capacity, int32_t* n_chunks_out, int32_t* chunk_out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU (replaces the process pool of src/simulate.py:330-351).  Trials shard by disjoint sim-id ranges;
+ * the only exchange is ONE all-reduce (sum, int64) of the winner / rounds histograms and totals.
+ * NCCL is bound at RUN time (dlopen), so the library loads and every single-GPU call works on a box without NCCL. */
+
+/* dlopen NCCL: `path` (e.g. the wheel-bundled .../nvidia/nccl/lib/libnccl.so.2) or NULL -> "libnccl.so.2" by the loader's
+ * search path ($CSIM_NCCL_LIB first).  Idempotent; the multi-GPU calls below load it on first use. */
+csim_status csim_nccl_load(const char* path);
+/* NCCL_VERSION_CODE of the bound library, 0 when not loaded */
+int32_t     csim_nccl_version(void);
+
+/* One process per GPU (torchrun / MPI style): rank 0 makes an id, the host program broadcasts its 128 bytes by whatever
+ * means it has, every rank creates its communicator on its context's device.  `comm` is an ncclComm_t. */
+#define CSIM_NCCL_ID_BYTES 128
+csim_status csim_nccl_unique_id(uint8_t id[CSIM_NCCL_ID_BYTES]);
+csim_status csim_nccl_comm_create(csim_ctx* ctx, const uint8_t id[CSIM_NCCL_ID_BYTES], int32_t n_ranks, int32_t rank, void** comm);
+csim_status csim_nccl_comm_destroy(void* comm);
+/* In-place sum over the ranks of `comm` (any ncclComm_t of ctx's device — one made above or the host program's own) of this
+ * rank's histograms (DEVICE buffers, the ones a device-buffer csim_run accumulated into), enqueued on `stream` after the
+ * trial kernel.  ONE ncclAllReduce when the three buffers are contiguous in the order winner_hist | rounds_hist | totals
+ * (pass the first pointer and the other two where they lie), otherwise one grouped call.  rounds_hist / totals may be NULL. */
+csim_status csim_allreduce_hists(csim_ctx* ctx, void* comm, int64_t* winner_hist, int64_t* rounds_hist, int64_t* totals,
+                                 int32_t n_param_sets, int32_t max_rounds, void* stream);
+
+/* One process, several GPUs: a group owns one context (and one stream, one NCCL communicator) per device. */
+typedef struct csim_group csim_group;
+csim_status csim_group_create(csim_group** out, const int32_t* devices, int32_t n_devices);
+csim_status csim_group_destroy(csim_group* g);
+int32_t     csim_group_size(const csim_group* g);
+csim_ctx*   csim_group_ctx(csim_group* g, int32_t i);                       /* the i-th device's context (borrowed) */
+csim_status csim_group_upload_roster(csim_group* g, int32_t n_electors, const double* ideology_score,
+                                     const int32_t* region_code, const uint8_t* is_papabile);
+/* [begin, begin + count) of shard `rank` of `n` trials split over `n_ranks` contiguous, balanced ranges */
+void        csim_shard_range(uint64_t n, int32_t rank, int32_t n_ranks, uint64_t* begin, uint64_t* count);
+/* csim_run over every device of the group.  HOST buffers only (args->buffers_on_device must be 0; args->stream is ignored).
+ * Device i simulates sims [begin_i, begin_i + count_i) of args->n_sims (csim_shard_range) of EVERY parameter set, all devices
+ * concurrently; the per-device histograms are summed by one NCCL all-reduce enqueued behind each device's trial kernel; the
+ * per-trial rows are copied straight into the caller's [set][sim] arrays (page-locked arrays make those copies asynchronous).
+ * Results are bit-identical to csim_run on one device with the same arguments (a trial's stream is keyed by its sim id).
+ * kernel_ms (nullable, [n_devices]): device time of each device's trial kernel. */
+csim_status csim_group_run(csim_group* g, const csim_run_args* args, float* kernel_ms);
 
 /* Diagnostics for bench.py: number of kernel launches this context has issued,
  * and the device time (ms, CUDA events on the launch stream) of the last csim_run's trial kernel. */

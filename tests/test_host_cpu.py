@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(EXPORTS), declared ^ set(EXPORTS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.csim_abi_version() == 1
+    assert lib.csim_abi_version() == 2
 
 
 def test_struct_mirrors_match_header(tmp_path):
