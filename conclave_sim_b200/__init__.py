@@ -9,12 +9,13 @@ Layout:
   simulate.py      parse_args / model_params_from_args / _run_single_simulation_worker / main
                    (mirror of src/simulate.py)
   ingest.py        ElectorDataIngester        (mirror of src/ingest.py:611-663)
-  dist.py          trial sharding across GPUs + histogram all-reduce (torch.distributed)
+  dist.py          one process per GPU (torchrun): trial sharding + the histogram all-reduce through the C ABI
+                   (engine.EngineGroup = the single-process form, csim_group_run)
 """
 from ._cabi import (CsimError, WIRING_REF_CLI, WIRING_MODEL, ENGINE_AUTO, ENGINE_DENSE, ENGINE_TABLE, ENGINE_PREFIX, ENGINE_FULL,
                     FP32, FP64, REASON_MAX_ROUNDS, REASON_WINNER, REASON_NO_PROBS)
-from .engine import Engine, get_engine, make_params, RunResult
+from .engine import Engine, EngineGroup, get_engine, get_group, device_count, make_params, RunResult
 
-__all__ = ["Engine", "get_engine", "make_params", "RunResult", "CsimError",
+__all__ = ["Engine", "EngineGroup", "get_engine", "get_group", "device_count", "make_params", "RunResult", "CsimError",
            "WIRING_REF_CLI", "WIRING_MODEL", "ENGINE_AUTO", "ENGINE_DENSE", "ENGINE_TABLE", "ENGINE_PREFIX", "ENGINE_FULL", "FP32", "FP64",
            "REASON_MAX_ROUNDS", "REASON_WINNER", "REASON_NO_PROBS"]

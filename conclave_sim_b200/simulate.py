@@ -363,7 +363,7 @@ def aggregate_results(results: List[Dict[str, Any]], num_simulations: int) -> Di
         "winner_counts": dict(winner_counts),
         "most_frequent_winner": top[0][0] if top else None,
         "most_frequent_winner_count": top[0][1] if top else 0,
-        "most_frequent_winner_percentage": (top[0][1] / num_simulations if num_simulations > 0 else 0) if top else 0,
+        "most_frequent_winner_percentage": (top[0][1] if top else 0) / num_simulations if num_simulations > 0 else 0,
         "average_rounds_all": np.mean([r["rounds"] for r in results]) if results else 0,
     }
 
@@ -385,6 +385,8 @@ def results_frame(res: RunResult, candidate_ids: List[Any], supermajority_thresh
     column-wise from the batch arrays: the same rows results_from_batch yields one dict at a time, without a Python loop over
     trials (a million trials: ~0.1 s instead of seconds)."""
     n = len(res.winner)
+    if n == 0:
+        return pd.DataFrame([])                                       # what the reference builds from an empty result list (:412): no columns
     w = np.asarray(res.winner)
     ids = np.empty(len(candidate_ids) + 1, dtype=object)
     ids[:-1] = [str(c) for c in candidate_ids]
@@ -494,7 +496,8 @@ def main(argv: Optional[List[str]] = None):
         # the results table column-wise and the statistics straight from the device histograms: the same values as
         # results_from_batch + aggregate_results (tests/test_gpu_parity.py::test_sweep_stats_and_legacy_shim), no per-trial Python
         results = results_frame(batch, ids, args.supermajority_threshold)
-        aggregate_stats = stats_from_histograms(batch.winner_hist[0], batch.rounds_hist[0], batch.totals[0], ids, args.num_simulations)
+        aggregate_stats = stats_from_histograms(batch.winner_hist[0], batch.rounds_hist[0], batch.totals[0], ids, args.num_simulations,
+                                                winners_in_order=batch.winner)
     except Exception as exc:   # the reference logs worker errors and carries on with what it has (:350-351)
         log.error(f"Error in simulation worker: {exc}", exc_info=True)
     log.info(f"Simulation time: {time.time() - start:.2f} seconds")
@@ -527,11 +530,14 @@ def main(argv: Optional[List[str]] = None):
 # set of a sweep, without touching the per-trial rows.
 # ---------------------------------------------------------------------------------------------
 def stats_from_histograms(winner_hist: np.ndarray, rounds_hist: np.ndarray, totals: np.ndarray,
-                          candidate_ids: List[Any], num_simulations: Optional[int] = None) -> Dict[str, Any]:
+                          candidate_ids: List[Any], num_simulations: Optional[int] = None,
+                          winners_in_order: Optional[np.ndarray] = None) -> Dict[str, Any]:
     """Same keys / values as aggregate_results (src/simulate.py:356-387) from
     winner_hist[E+1] (slot E = no winner), rounds_hist[R+1] (winning trials) and totals = (sum of rounds, trials).
-    `most_frequent_winner` breaks count ties by roster order (the reference's tie-break is its
-    completion order, i.e. unspecified)."""
+    The reference's `winner_counts` is a Counter filled in completion order and `most_frequent_winner` is the FIRST-inserted
+    among equal counts (:367-370).  `winners_in_order` (the per-trial winner indices in sim-id order, -1 = none) reproduces
+    exactly that for a pool that completes in order — byte-identical JSON (tests/golden/main/*.json); without it keys and ties
+    go by roster order (a sweep has no per-trial rows on the host)."""
     winner_hist = np.asarray(winner_hist, dtype=np.int64)
     rounds_hist = np.asarray(rounds_hist, dtype=np.int64)
     E = len(winner_hist) - 1
@@ -547,9 +553,15 @@ def stats_from_histograms(winner_hist: np.ndarray, rounds_hist: np.ndarray, tota
         rmin, rmax = int(rvals[0]), int(rvals[-1])
     else:
         avg = median = rmin = rmax = None
-    counts = {str(candidate_ids[i]): int(c) for i, c in enumerate(winner_hist[:E]) if c > 0}
+    order = np.nonzero(winner_hist[:E] > 0)[0]
+    if winners_in_order is not None and len(order):
+        w = np.asarray(winners_in_order)
+        first = pd.unique(w[w >= 0])                                   # hash-based, keeps the order of first appearance
+        if len(first) == len(order):
+            order = first
+    counts = {str(candidate_ids[i]): int(winner_hist[i]) for i in order}
     if counts:
-        best = int(np.argmax(winner_hist[:E]))
+        best = int(order[int(np.argmax(winner_hist[order]))])          # the first of the equal maxima in that order
         mf, mfc = str(candidate_ids[best]), int(winner_hist[best])
     else:
         mf, mfc = None, 0

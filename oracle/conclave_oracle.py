@@ -512,7 +512,7 @@ def aggregate(winners: Sequence[Optional[str]], rounds: Sequence[int], num_simul
         "winner_counts": dict(wc),
         "most_frequent_winner": top[0][0] if top else None,
         "most_frequent_winner_count": top[0][1] if top else 0,
-        "most_frequent_winner_percentage": (top[0][1] / num_simulations) if (top and num_simulations > 0) else 0,
+        "most_frequent_winner_percentage": ((top[0][1] if top else 0) / num_simulations) if num_simulations > 0 else 0,   # :371: 0 / n = 0.0 when nobody wins
         "average_rounds_all": float(np.mean([int(r) for r in rounds])) if len(rounds) else 0,
     }
 

@@ -289,3 +289,148 @@ def test_results_frame_and_fast_csv_equal_the_row_by_row_path(tmp_path):
     df = S.results_frame(res, ids2, 0.56)
     S._write_csv(df, str(tmp_path / "q.csv"))
     assert pd.read_csv(tmp_path / "q.csv")["winner"].iloc[0] == ids2[3]
+
+
+# ---------------------------------------------------------------------------------------------
+# Round 2: the writers against the bytes the UNMODIFIED reference's main() wrote (tests/golden/main, oracle/gen_golden_main.py),
+# the multi-GPU host logic, the new CLI flags
+# ---------------------------------------------------------------------------------------------
+MAIN_GOLD = os.path.join(ROOT, "tests", "golden", "main")
+
+
+def _main_cases():
+    with open(os.path.join(MAIN_GOLD, "main_cases.json")) as f:
+        return json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("case", _main_cases(), ids=lambda c: c["name"])
+def test_writers_reproduce_the_reference_main_bytes(tmp_path, case):
+    """src/simulate.py:356-431 — the rows the reference's main() aggregated are fed to our aggregation / writers in all three
+    forms (row dicts -> aggregate_results; batch arrays -> results_frame + stats_from_histograms); CSV and JSON must be the same
+    BYTES the reference wrote."""
+    import pandas as pd
+    import golden_util as G
+    from conclave_sim_b200 import simulate as S
+    from conclave_sim_b200.engine import RunResult
+    want_csv = open(os.path.join(MAIN_GOLD, case["name"] + ".csv"), "rb").read()
+    want_json = open(os.path.join(MAIN_GOLD, case["name"] + ".json"), "rb").read()
+    ids = G.real_roster().ids
+    n = case["n"]
+    args = S.parse_args(["-n", str(n)] + case["args"])
+    thr = args.supermajority_threshold
+    if n:
+        ref = pd.read_csv(os.path.join(MAIN_GOLD, case["name"] + ".csv"), dtype={"winner": str}, keep_default_na=True)
+        winners = [None if pd.isna(w) else w for w in ref["winner"]]
+        results = [dict(sim_id=int(s), winner=w, rounds=int(r), reason=str(t)) for s, w, r, t in zip(ref["sim_id"], winners, ref["rounds"], ref["reason"])]
+    else:
+        winners, results = [], []
+    # 1. the reference's own row-by-row form
+    agg = S.aggregate_results(results, n)
+    S.write_outputs(results, agg, str(tmp_path / "a.csv"), str(tmp_path / "a.json"))
+    assert open(tmp_path / "a.csv", "rb").read() == want_csv
+    assert open(tmp_path / "a.json", "rb").read() == want_json
+    # 2. what main() does with a GPU batch: arrays -> column-wise frame, histograms -> stats
+    E, R = len(ids), args.max_rounds
+    widx = np.array([ids.index(w) if w is not None else -1 for w in winners], np.int32)
+    rounds = np.array([r["rounds"] for r in results], np.int32)
+    reason = np.array([1 if r["reason"].startswith("Winner") else 0 for r in results], np.uint8)
+    wh = np.bincount(np.where(widx >= 0, widx, E), minlength=E + 1).astype(np.int64)
+    rh = np.bincount(rounds[widx >= 0], minlength=R + 1).astype(np.int64)
+    tot = np.array([rounds.sum(), n], np.int64)
+    batch = RunResult(widx, rounds, reason, None, None, wh[None], rh[None], tot[None], E)
+    frame = S.results_frame(batch, ids, thr)
+    stats = S.stats_from_histograms(wh, rh, tot, ids, n, winners_in_order=widx)
+    S.write_outputs(frame, stats, str(tmp_path / "b.csv"), str(tmp_path / "b.json"))
+    assert open(tmp_path / "b.csv", "rb").read() == want_csv
+    assert open(tmp_path / "b.json", "rb").read() == want_json
+
+
+def test_shard_range_c_abi_equals_python(lib):
+    import ctypes as C
+    from conclave_sim_b200.dist import shard_range
+    for n in (0, 1, 2, 7, 8, 9, 1000, 10_000_000, 2**40 + 3):
+        for world in (1, 2, 3, 8, 16):
+            covered = 0
+            for rank in range(world):
+                b, c = C.c_uint64(), C.c_uint64()
+                lib.csim_shard_range(n, rank, world, C.byref(b), C.byref(c))
+                assert (b.value, c.value) == shard_range(n, rank, world)
+                assert b.value == covered
+                covered += c.value
+            assert covered == n
+
+
+def test_resolve_devices_and_new_cli_flags(monkeypatch):
+    from conclave_sim_b200 import simulate as S
+    monkeypatch.setattr(S, "device_count", lambda: 8)
+    assert S.resolve_devices(None, 0) == (0,)
+    assert S.resolve_devices(None, 3) == (3,)
+    assert S.resolve_devices(None, 0, workers=1) == (0,)
+    assert S.resolve_devices(None, 0, workers=4) == (0, 1, 2, 3)
+    assert S.resolve_devices(None, 0, workers=64) == tuple(range(8))          # -w clamps to the box
+    assert S.resolve_devices(2) == (0, 1) and S.resolve_devices("2") == (0, 1)
+    assert S.resolve_devices("all") == tuple(range(8))
+    assert S.resolve_devices("3,1") == (3, 1) and S.resolve_devices([5, 6]) == (5, 6)
+    for bad in (0, "0", 9, [1, 1], []):
+        with pytest.raises(ValueError):
+            S.resolve_devices(bad)
+    monkeypatch.setattr(S, "device_count", lambda: 1)
+    assert S.resolve_devices(None, 0, workers=16) == (0,)
+    a = S.parse_args("--devices 4 --tape t.npy -w 2".split())
+    assert (a.devices, a.tape, a.workers) == ("4", "t.npy", 2)
+    a = S.parse_args([])
+    assert a.devices is None and a.tape is None
+
+
+def test_load_tapes(tmp_path):
+    from conclave_sim_b200 import simulate as S
+    t = np.random.default_rng(0).random((5, 3 * 7))
+    np.save(tmp_path / "t.npy", t)
+    np.savez(tmp_path / "t.npz", tapes=t)
+    for f in ("t.npy", "t.npz"):
+        got = S.load_tapes(str(tmp_path / f), 4, 3, 7)
+        assert got.shape == (4, 21) and np.array_equal(got, t[:4]) and got.flags.c_contiguous
+    with pytest.raises(ValueError):
+        S.load_tapes(str(tmp_path / "t.npy"), 6, 3, 7)           # not enough rows
+    with pytest.raises(ValueError):
+        S.load_tapes(str(tmp_path / "t.npy"), 4, 4, 7)           # wrong row length
+
+
+def test_multi_gpu_entry_points_without_a_device(lib):
+    """No GPU here: the group / NCCL entry points must fail with a status and a message, never crash or compute."""
+    import ctypes as C
+    from conclave_sim_b200 import _cabi
+    g = C.c_void_p()
+    devs = (C.c_int32 * 2)(0, 1)
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a CUDA device is present")
+    except ImportError:
+        pass
+    assert lib.csim_group_create(C.byref(g), devs, 2) != 0 and not g.value
+    assert b"" != lib.csim_last_error()
+    assert lib.csim_group_create(C.byref(g), None, 0) == -1
+    n = C.c_int32(7)
+    assert lib.csim_device_count(C.byref(n)) != 0 and n.value == 0
+    assert lib.csim_group_size(None) == 0
+    assert lib.csim_allreduce_hists(None, None, None, None, None, 1, 1, None) == -1
+    # NCCL binds at run time: loading it needs no GPU (skip when the box has no NCCL at all)
+    try:
+        v = _cabi.nccl_load()
+    except _cabi.CsimError:
+        pytest.skip("no libnccl on this box")
+    assert v >= 21800 and lib.csim_nccl_version() == v
+
+
+def test_stats_first_appearance_order_and_ties():
+    from conclave_sim_b200 import simulate as S
+    ids = ["a", "b", "c", "d"]
+    w = np.array([2, -1, 0, 2, 0, 3])
+    wh = np.bincount(np.where(w >= 0, w, 4), minlength=5)
+    rh = np.bincount(np.array([3, 4, 3, 5, 6]), minlength=8)
+    got = S.stats_from_histograms(wh, rh, np.array([30, 6]), ids, 6, winners_in_order=w)
+    assert list(got["winner_counts"].items()) == [("c", 2), ("a", 2), ("d", 1)]
+    assert got["most_frequent_winner"] == "c"                     # the reference's Counter.most_common: first inserted of the equal counts
+    got = S.stats_from_histograms(wh, rh, np.array([30, 6]), ids, 6)
+    assert list(got["winner_counts"].items()) == [("a", 2), ("c", 2), ("d", 1)] and got["most_frequent_winner"] == "a"

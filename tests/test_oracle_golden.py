@@ -2,6 +2,8 @@
 unmodified reference (oracle/gen_golden.py), and against the closed-form known answers the
 reference's own tests/test_model.py states (papabile :552-632, regional :635-705, bandwagon
 :708-792, stickiness :795-874, combined :879-1000, dynamic beta :1006-1079)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -156,3 +158,26 @@ def test_prob_matrix_candidate_subset_matches_reference(case):
     P = O.prob_matrix(case["roster"], case["mp"], case["beta"], prev_vote=case["prev_vote"], fatigued=case["fatigued"],
                       shares=case["shares"], cand_index=case["cand"])
     assert P.shape == case["P"].shape and np.array_equal(P, case["P"])
+
+
+def test_oracle_aggregate_equals_the_reference_main_json():
+    """oracle.aggregate (src/simulate.py:356-387) against the stats JSON the unmodified reference's main() wrote
+    (tests/golden/main, oracle/gen_golden_main.py)."""
+    import json
+    import pandas as pd
+    gold = os.path.join(G.GOLD, "main")
+    with open(os.path.join(gold, "main_cases.json")) as f:
+        cases = json.load(f)["cases"]
+    assert len(cases) >= 4
+    for c in cases:
+        with open(os.path.join(gold, c["name"] + ".json")) as f:
+            want = json.load(f)
+        if c["n"]:
+            ref = pd.read_csv(os.path.join(gold, c["name"] + ".csv"), dtype={"winner": str})
+            winners = [None if pd.isna(w) else w for w in ref["winner"]]
+            rounds = ref["rounds"].tolist()
+        else:
+            winners, rounds = [], []
+        got = O.aggregate(winners, rounds, c["n"])
+        assert json.loads(json.dumps(got)) == want, c["name"]
+        assert list(got) == list(want) and list(got["winner_counts"]) == list(want["winner_counts"])
