@@ -16,6 +16,7 @@ import pytest
 from oracle import conclave_oracle as O
 from oracle import c_oracle as CO
 import golden_util as G
+from parity_util import assert_agree, first_difference_is_one_flipped_vote
 
 pytestmark = pytest.mark.gpu
 
@@ -200,10 +201,19 @@ def test_fp32_agrees_with_oracle_per_trial(eng, wiring, n, engine):
     mp = O.ModelParams(**CFG2)
     out = eng.run([to_params(mp, EP2)], n, seed=5, wiring=wiring, engine=ENGINES[engine], precision=FP32, want_final_votes=True)
     ref = CO.run(roster, [(mp, EP2)], wiring, n, seed=5)
-    same = (out.winner == ref["winner"]) & (out.rounds == ref["rounds"]) & (out.final_votes == ref["final_votes"]).all(axis=1)
-    # 24-bit uniforms + fp32 sums flip ~1e-5 of the draws; a flipped draw may change the trial
-    assert same.mean() > 0.95, same.mean()
-    assert abs(out.rounds.mean() - ref["rounds"].mean()) < 0.05
+    same = (out.winner == ref["winner"]) & (out.rounds == ref["rounds"])
+    # 24-bit uniforms + fp32 sums move a vote to the neighbouring candidate in ~1e-6 of the draws; such a vote rarely changes the
+    # outcome: the gate is the measured rate (parity_util.RATE), and every trial that does differ must show exactly that signature
+    assert_agree(same, engine, ref["rounds"].sum() * roster.E, what=f"fp32 {engine} wiring {wiring}")
+    assert abs(out.rounds.mean() - ref["rounds"].mean()) < 0.01
+    votes_same = (out.final_votes == ref["final_votes"]).all(axis=1)
+    assert votes_same[same].mean() > 0.99                         # a flip in the last round leaves winner / rounds alone
+    p = to_params(mp, EP2)
+    for i in np.nonzero(~same)[0][:8]:
+        g1 = eng.run([p], 1, seed=5, sim_id_begin=int(i), wiring=wiring, engine=ENGINES[engine], precision=FP32, want_round_tallies=True)
+        r1 = CO.run(roster, [(mp, EP2)], wiring, 1, seed=5, sim_id_begin=int(i), want_tallies=True)
+        assert g1.winner[0] == out.winner[i] and r1["winner"][0] == ref["winner"][i]
+        first_difference_is_one_flipped_vote(g1.round_tallies[0], r1["round_tallies"][0])
 
 
 def _chi2_homogeneity(a, b, min_expected=5.0):
@@ -265,7 +275,7 @@ def test_edge_rosters(eng):
             played = o32.round_tallies[:, 0, :]
             assert (played.sum(axis=1) == E).all()                 # every elector votes exactly once per round
             if E > 1:
-                assert np.mean(o32.winner == r32["winner"]) > 0.85, (E, en, np.mean(o32.winner == r32["winner"]))
+                assert_agree((o32.winner == r32["winner"]) & (o32.rounds == r32["rounds"]), en, r32["rounds"].sum() * E, what=f"edge roster E={E} engine {en}")
 
 
 def test_large_roster_cfg5_shape(eng):
@@ -341,7 +351,7 @@ def test_table_engine_without_shared_memory_staging(eng):
     assert np.array_equal(out.winner, ref["winner"]) and np.array_equal(out.rounds, ref["rounds"])
     assert np.array_equal(out.round_tallies, ref["round_tallies"])
     o32 = eng.run([to_params(mp, ep)], 40, seed=21, precision=FP32, engine=ENGINES["table"])
-    assert np.mean(o32.rounds == ref["rounds"]) > 0.8
+    assert_agree((o32.rounds == ref["rounds"]) & (o32.winner == ref["winner"]), "table", ref["rounds"].sum() * 300, what="table engine without staging")
 
 
 def test_sweep_stats_and_legacy_shim(eng):
@@ -444,7 +454,7 @@ def test_edge_engine_parameters(eng, ep_kw):
             else:
                 assert (out.final_votes == 0).all()
             o32 = eng.run([to_params(mp, ep)], 48, seed=2, wiring=wiring, engine=en, precision=FP32, want_final_votes=True)
-            assert np.mean(o32.rounds == ref["rounds"]) > 0.8, (wiring, en)
+            assert_agree((o32.rounds == ref["rounds"]) & (o32.winner == ref["winner"]), en, max(1, ref["rounds"].sum()) * roster.E, what=f"edge parameters {kw} wiring {wiring} engine {en}")
             if ep.max_rounds == 0:
                 assert (o32.final_votes == 0).all() and (o32.rounds == 0).all()
     assert eng.run([to_params(mp, ep)], 0, seed=2).winner.shape == (0,)
@@ -471,7 +481,7 @@ def test_heterogeneous_parameter_sets_and_wide_sim_ids(eng):
             assert np.array_equal(out.round_tallies, ref["round_tallies"]), (wiring, en)
             assert np.array_equal(out.winner_hist, ref["winner_hist"]) and np.array_equal(out.totals, ref["totals"])
             o32 = eng.run([to_params(*s) for s in sets], 40, seed=2**63 + 11, sim_id_begin=base, wiring=wiring, engine=en, precision=FP32)
-            assert np.mean(o32.rounds == ref["rounds"]) > 0.85, (wiring, en)
+            assert_agree((o32.rounds == ref["rounds"]) & (o32.winner == ref["winner"]), en, ref["rounds"].sum() * roster.E, what=f"heterogeneous sets wiring {wiring} engine {en}")
 
 
 def test_full_size_properties_cfg3_share(eng):
@@ -505,7 +515,7 @@ def test_full_size_properties_cfg3_share(eng):
     same_dt = np.mean((dense.winner == table.winner) & (dense.rounds == table.rounds))
     same_te = np.mean((table.winner == exact.winner) & (table.rounds == exact.rounds))
     print(f"dense==table on {same_dt:.5f}, table32==table64 on {same_te:.5f} of {n} trials")
-    assert same_dt > 0.99 and same_te > 0.99
+    assert same_dt > 0.9995 and same_te > 0.9998                # measured 0.99996 / 0.99998 (a corrupted per-mille of trials fails)
     for x, y in ((dense, table), (dense, exact)):
         assert _chi2_homogeneity(x.winner_hist[0], y.winner_hist[0]) > 1e-3
         assert _chi2_homogeneity(np.append(x.rounds_hist[0], x.winner_hist[0, 135]), np.append(y.rounds_hist[0], y.winner_hist[0, 135])) > 1e-3
@@ -522,9 +532,9 @@ def test_cfg5_shape_at_scale(eng):
     d = eng.run(p, n, seed=5, engine=ENGINES["dense"], precision=FP32, want_final_votes=True)
     t = eng.run(p, n, seed=5, engine=ENGINES["table"], precision=FP32, want_final_votes=True)
     assert (d.final_votes.sum(axis=1) == 1024).all() and (t.final_votes.sum(axis=1) == 1024).all()
-    assert np.mean((d.winner == t.winner) & (d.rounds == t.rounds)) > 0.97
+    assert_agree((d.winner == t.winner) & (d.rounds == t.rounds), "dense", d.totals[0, 0] * 1024, what="cfg5 shape dense32 vs table32", slack=2.0)
     ref = CO.run(roster, [(O.ModelParams(**CFG2), ep)], O.WIRING_REF_CLI, 64, seed=5)
-    assert np.mean(t.winner[:64] == ref["winner"]) > 0.9
+    assert_agree((t.winner[:64] == ref["winner"]) & (t.rounds[:64] == ref["rounds"]), "table", ref["rounds"].sum() * 1024, what="cfg5 shape table32 vs oracle")
 
 
 @pytest.mark.parametrize("E", [2, 33, 129, 200, 300])
@@ -543,5 +553,4 @@ def test_model_wiring_on_ragged_rosters(eng, E):
         o32 = eng.run([to_params(mp, ep)], n, seed=8, wiring=O.WIRING_MODEL, engine=en, precision=FP32, want_round_tallies=True)
         first = o32.round_tallies[:, 0, :]
         assert (first.sum(axis=1) == E).all()
-        agree = np.mean((o32.winner == ref["winner"]) & (o32.rounds == ref["rounds"]))
-        assert agree > 0.85, (E, en, agree)
+        assert_agree((o32.winner == ref["winner"]) & (o32.rounds == ref["rounds"]), en, ref["rounds"].sum() * E, what=f"model wiring ragged E={E} engine {en}")

@@ -15,6 +15,7 @@ import pytest
 from oracle import conclave_oracle as O
 from oracle import c_oracle as CO
 import golden_util as G
+from parity_util import assert_agree
 from test_gpu_parity import CFG2, EP2, to_params, upload, _chi2_homogeneity
 
 pytestmark = pytest.mark.gpu
@@ -44,7 +45,7 @@ def test_prefix_agrees_with_oracle_per_trial(eng, wiring, n):
     out = eng.run([to_params(mp, EP2)], n, seed=5, wiring=wiring, engine=PREFIX, precision=FP32, want_final_votes=True)
     ref = CO.run(roster, [(mp, EP2)], wiring, n, seed=5)
     same = _same(out, ref)
-    assert same.mean() > 0.99, same.mean()
+    assert_agree(same, "prefix", ref["rounds"].sum() * 134, what=f"prefix wiring {wiring}")
     assert np.array_equal(out.winner_hist[0, :134], np.bincount(out.winner[out.winner >= 0], minlength=134))
     assert out.totals[0, 0] == out.rounds.sum() and out.totals[0, 1] == n
 
@@ -66,7 +67,7 @@ def test_prefix_model_terms_one_by_one(eng, kw):
     ref = CO.run(roster, [(mp, ep)], O.WIRING_MODEL, n, seed=17)
     out = eng.run([to_params(mp, ep)], n, seed=17, wiring=O.WIRING_MODEL, engine=PREFIX, precision=FP32, want_final_votes=True)
     same = _same(out, ref)
-    assert same.mean() > 0.97, (kw, same.mean())
+    assert_agree(same, "prefix", ref["rounds"].sum() * 134, what=f"prefix model terms {kw}")
 
 
 def test_prefix_fp32_underflow_matches_dense32(eng):
@@ -85,7 +86,7 @@ def test_prefix_fp32_underflow_matches_dense32(eng):
         dn = eng.run([to_params(mp, ep)], n, seed=17, wiring=wiring, engine=DENSE, precision=FP32, want_round_tallies=True)
         for r in range(6):
             assert np.mean((pf.round_tallies[:, r, :] == ref["round_tallies"][:, r, :]).all(axis=1)) > 0.99
-        assert np.mean((pf.winner == dn.winner) & (pf.rounds == dn.rounds)) > 0.97
+        assert_agree((pf.winner == dn.winner) & (pf.rounds == dn.rounds), "dense", pf.rounds.sum() * 134, what=f"underflow prefix vs dense32 wiring {wiring}", slack=2.0)
 
 
 @pytest.mark.parametrize("E", [1, 2, 3, 9, 33, 127, 128, 129, 136, 137, 193, 200, 255, 256, 257, 300, 513])
@@ -107,8 +108,7 @@ def test_prefix_ragged_rosters(eng, E):
         live = out.round_tallies.reshape(n, -1, E).sum(axis=2)
         for i in range(0, n, 17):
             assert (live[i, :out.rounds[i]] == E).all() and (out.round_tallies[i, out.rounds[i]:] == -1).all()
-        agree = np.mean((out.winner == ref["winner"]) & (out.rounds == ref["rounds"]))
-        assert agree > 0.95, (E, wiring, agree)
+        assert_agree((out.winner == ref["winner"]) & (out.rounds == ref["rounds"]), "prefix", ref["rounds"].sum() * E, what=f"prefix ragged E={E} wiring {wiring}")
 
 
 @pytest.mark.parametrize("ep_kw", [
@@ -132,11 +132,11 @@ def test_prefix_edge_engine_parameters(eng, ep_kw):
         out = eng.run([to_params(mp, ep)], 96, seed=2, wiring=wiring, engine=PREFIX, precision=FP32, want_final_votes=True,
                       want_round_tallies=True)
         assert np.array_equal(out.reason, (out.winner >= 0).astype(np.uint8))
-        assert np.mean((out.rounds == ref["rounds"]) & (out.winner == ref["winner"])) > 0.9, wiring
+        assert_agree((out.rounds == ref["rounds"]) & (out.winner == ref["winner"]), "prefix", max(1, ref["rounds"].sum()) * roster.E, what=f"prefix edge parameters {ep_kw} wiring {wiring}")
         if ep.max_rounds == 0:
             assert (out.final_votes == 0).all() and (out.rounds == 0).all() and (out.winner == -1).all()
         else:
-            assert np.mean((out.round_tallies == ref["round_tallies"]).all(axis=(1, 2))) > 0.9
+            assert np.mean((out.round_tallies == ref["round_tallies"]).all(axis=(1, 2))) > 0.95    # vote-level: a moved vote that leaves the outcome alone still shows here
     assert eng.run([to_params(mp, ep)], 0, seed=2, engine=PREFIX).winner.shape == (0,)
 
 
@@ -160,7 +160,7 @@ def test_prefix_heterogeneous_sets_and_wide_sim_ids(eng):
         out = eng.run([to_params(*s) for s in sets], n, seed=2**63 + 11, sim_id_begin=base, wiring=wiring, engine=PREFIX,
                       precision=FP32, want_final_votes=True)
         same = _same(out, ref)
-        assert same.mean() > 0.98, (wiring, same.mean())
+        assert_agree(same, "prefix", ref["rounds"].sum() * 134, what=f"prefix heterogeneous sets wiring {wiring}")
         w = out.winner.reshape(4, n); r = out.rounds.reshape(4, n)
         for s in range(4):
             assert out.winner_hist[s, :134].sum() == (w[s] >= 0).sum() and out.winner_hist[s, 134] == (w[s] < 0).sum()
@@ -190,7 +190,7 @@ def test_prefix_sweep_many_sets_and_sharding(eng):
             part = eng.run([ps[s]], 250, seed=4, sim_id_begin=300, wiring=wiring, engine=PREFIX, precision=FP32)
             assert np.array_equal(part.winner, w[s][300:550]) and np.array_equal(part.rounds, r[s][300:550])
         ref = CO.run(roster, [sets[37]], wiring, n, seed=4)
-        assert np.mean((w[37] == ref["winner"]) & (r[37] == ref["rounds"])) > 0.98
+        assert_agree((w[37] == ref["winner"]) & (r[37] == ref["rounds"]), "prefix", ref["rounds"].sum() * roster.E, what=f"prefix 96-set sweep wiring {wiring}")
 
 
 def test_prefix_tables_in_global_memory(eng):
@@ -217,9 +217,9 @@ def test_prefix_tables_in_global_memory(eng):
         out = eng.run(p, n, seed=5, wiring=wiring, engine=PREFIX, precision=FP32, want_final_votes=True)
         d = eng.run(p, n, seed=5, wiring=wiring, engine=DENSE, precision=FP32, want_final_votes=True)
         assert (out.final_votes.sum(axis=1) == 1024).all()
-        assert np.mean((out.winner == d.winner) & (out.rounds == d.rounds)) > 0.97
+        assert_agree((out.winner == d.winner) & (out.rounds == d.rounds), "dense", out.totals[0, 0] * 1024, what=f"cfg5 prefix vs dense32 wiring {wiring}", slack=2.0)
         ref = CO.run(roster, [(mp, ep)], wiring, 48, seed=5)
-        assert np.mean((out.winner[:48] == ref["winner"]) & (out.rounds[:48] == ref["rounds"])) > 0.9
+        assert_agree((out.winner[:48] == ref["winner"]) & (out.rounds[:48] == ref["rounds"]), "prefix", ref["rounds"].sum() * 1024, what=f"cfg5 prefix vs oracle wiring {wiring}")
 
 
 def test_prefix_distribution_matches_reference_sample(eng):
@@ -267,7 +267,7 @@ def test_prefix_full_size_properties_model_wiring(eng):
         assert np.array_equal(a.winner_hist + b.winner_hist, pf.winner_hist)
         same = np.mean((pf.winner == dn.winner) & (pf.rounds == dn.rounds))
         print(f"prefix==dense on {same:.5f} of {n} trials (wiring {wiring})")
-        assert same > 0.995
+        assert same > 0.9995                                          # measured 0.9998 (dense32's own rate)
         assert _chi2_homogeneity(pf.winner_hist[0], dn.winner_hist[0]) > 1e-3
 
 
@@ -392,7 +392,8 @@ def test_full_engine_fatigue_and_stop_vs_oracle(eng):
     out = eng.run(ps, n, seed=3, wiring=O.WIRING_MODEL, engine=FULL, precision=FP32, want_round_tallies=True, want_final_votes=True)
     same = _same(out, ref).reshape(len(sets), n).mean(axis=1)
     print("full32 vs oracle per set:", same)
-    assert (same > 0.97).all(), same
+    for si in range(len(sets)):
+        assert_agree(_same(out, ref).reshape(len(sets), n)[si], "full", ref["rounds"].reshape(len(sets), n)[si].sum() * 134, what=f"full32 fatigue+stop set {si}")
     first = out.round_tallies[:, 0, :]
     assert (first.sum(axis=1) == 134).all()
     assert np.mean((out.round_tallies[:, :3, :] == ref["round_tallies"][:, :3, :]).all(axis=(1, 2))) > 0.99
@@ -422,8 +423,7 @@ def test_full_engine_on_ragged_rosters(eng, E):
     ref = CO.run(roster, [(mp, ep)], O.WIRING_MODEL, n, seed=8, want_tallies=True)
     out = eng.run([to_params(mp, ep)], n, seed=8, wiring=O.WIRING_MODEL, engine=FULL, precision=FP32, want_round_tallies=True)
     assert (out.round_tallies[:, 0, :].sum(axis=1) == E).all()
-    agree = np.mean((out.winner == ref["winner"]) & (out.rounds == ref["rounds"]))
-    assert agree > 0.9, (E, agree)
+    assert_agree((out.winner == ref["winner"]) & (out.rounds == ref["rounds"]), "full", ref["rounds"].sum() * E, what=f"full32 ragged E={E}")
 
 
 def test_full_engine_without_extras_equals_prefix_and_scales(eng):
@@ -437,7 +437,7 @@ def test_full_engine_without_extras_equals_prefix_and_scales(eng):
     for wiring in (O.WIRING_MODEL, O.WIRING_REF_CLI):
         f = eng.run(p, n, seed=77, wiring=wiring, engine=FULL, precision=FP32)
         q = eng.run(p, n, seed=77, wiring=wiring, engine=PREFIX, precision=FP32)
-        assert np.mean((f.winner == q.winner) & (f.rounds == q.rounds)) > 0.995
+        assert_agree((f.winner == q.winner) & (f.rounds == q.rounds), "full", f.totals[0, 0] * 135, what=f"full32 vs prefix wiring {wiring}")
         assert f.winner_hist.sum() == n and f.totals[0, 0] == f.rounds.astype(np.int64).sum()
         a_ = eng.run(p, 70_000, seed=77, sim_id_begin=0, wiring=wiring, engine=FULL, precision=FP32)
         b_ = eng.run(p, n - 70_000, seed=77, sim_id_begin=70_000, wiring=wiring, engine=FULL, precision=FP32)
@@ -463,7 +463,7 @@ def test_many_regions(eng):
         ref = CO.run(roster, [(mp, ep)], wiring, n, seed=6)
         for en in (PREFIX, FULL, 0):
             out = eng.run(p, n, seed=6, wiring=wiring, engine=en, precision=FP32)
-            assert np.mean((out.winner == ref["winner"]) & (out.rounds == ref["rounds"])) > 0.98, (wiring, en)
+            assert_agree((out.winner == ref["winner"]) & (out.rounds == ref["rounds"]), "full" if en == FULL else "prefix", ref["rounds"].sum() * roster.E, what=f"many regions wiring {wiring} engine {en}")
         with pytest.raises(CsimError):
             eng.run(p, n, seed=6, wiring=wiring, engine=DENSE, precision=FP32)
 
@@ -487,7 +487,7 @@ def test_negative_factors_go_to_the_full_engine(eng, kw):
         out = eng.run([to_params(mp, ep)], n, seed=12, wiring=wiring, precision=FP32)          # AUTO
         full = eng.run([to_params(mp, ep)], n, seed=12, wiring=wiring, engine=FULL, precision=FP32)
         assert np.array_equal(out.winner, full.winner) and np.array_equal(out.rounds, full.rounds)
-        assert np.mean((full.winner == ref["winner"]) & (full.rounds == ref["rounds"])) > 0.97, (kw, wiring)
+        assert_agree((full.winner == ref["winner"]) & (full.rounds == ref["rounds"]), "full", ref["rounds"].sum() * roster.E, what=f"negative factors {kw} wiring {wiring}")
         with pytest.raises(CsimError):
             eng.run([to_params(mp, ep)], n, seed=12, wiring=wiring, engine=PREFIX, precision=FP32)
 
@@ -609,8 +609,13 @@ def test_fuzz_engines_vs_oracle(eng, case_seed):
                 continue
             played = out.round_tallies[:, 0, :]
             assert (played.sum(axis=1) == E).all(), (case_seed, wiring, en)
-            agree = np.mean((out.winner == ref["winner"]) & (out.rounds == ref["rounds"]))
-            assert agree >= (0.7 if big else 0.85), (case_seed, wiring, en, agree)
+            same = (out.winner == ref["winner"]) & (out.rounds == ref["rounds"])
+            if out.precision == "fp64":                               # AUTO fell through to the exact engine: no tolerance at all
+                assert same.all(), (case_seed, wiring, en)
+            else:
+                # random parameters include knife-edge elections (beta = 0: every candidate equally likely), where one moved vote
+                # changes the outcome far more often than on cfg-2: four times the engine's cfg-2 rate, never "most trials"
+                assert_agree(same, out.engine, max(1, ref["rounds"].sum()) * E, what=f"fuzz {case_seed} wiring {wiring} engine {en}", slack=4.0)
 
 
 def test_auto_falls_through_to_an_engine_that_fits(eng):
@@ -656,4 +661,7 @@ def test_rosters_at_and_past_the_prefix_limit(eng, E):
         assert np.array_equal(ex.winner, ref["winner"]) and np.array_equal(ex.round_tallies, ref["round_tallies"])
         out = eng.run(p, n, seed=11, wiring=wiring, precision=FP32, want_round_tallies=True)
         assert (out.round_tallies[:, 0, :].sum(axis=1) == E).all()
-        assert np.mean((out.winner == ref["winner"]) & (out.rounds == ref["rounds"])) >= 0.8
+        if out.precision == "fp64":
+            assert np.array_equal(out.winner, ref["winner"]) and np.array_equal(out.rounds, ref["rounds"])
+        else:
+            assert_agree((out.winner == ref["winner"]) & (out.rounds == ref["rounds"]), out.engine, ref["rounds"].sum() * E, what=f"auto fall-through wiring {wiring}")
