@@ -59,6 +59,7 @@ class CsimRunArgs(C.Structure):
         ("final_votes", C.c_void_p), ("round_tallies", C.c_void_p),
         ("winner_hist", C.c_void_p), ("rounds_hist", C.c_void_p), ("totals", C.c_void_p),
         ("buffers_on_device", C.c_int32), ("reserved", C.c_int32), ("stream", C.c_void_p),
+        ("auto_batch_sims", C.c_uint64),
     ]
 
 

@@ -822,7 +822,8 @@ extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
             // (FULL takes everything PREFIX refuses: fatigue / stop-candidate, negative factors; DENSE in fp32 is explicit-only)
             engine = pfx_ok ? CSIM_ENGINE_PREFIX : (ra->precision == CSIM_FP32 ? CSIM_ENGINE_FULL : CSIM_ENGINE_DENSE);
         } else {
-            const uint64_t n_sb = ((ra->n_sims + (uint64_t)CSIM_TABLE_WPC * 32 - 1) / ((uint64_t)CSIM_TABLE_WPC * 32)) * ra->n_param_sets;
+            const uint64_t job_sims = ra->auto_batch_sims ? ra->auto_batch_sims : ra->n_sims;      // the whole job's size when this is a shard
+            const uint64_t n_sb = ((job_sims + (uint64_t)CSIM_TABLE_WPC * 32 - 1) / ((uint64_t)CSIM_TABLE_WPC * 32)) * ra->n_param_sets;
             if (ra->precision == CSIM_FP64) engine = CSIM_ENGINE_TABLE;
             else if (E > 256) engine = pfx_ok ? CSIM_ENGINE_PREFIX : CSIM_ENGINE_TABLE;
             else engine = n_sb >= (uint64_t)c->prop.multiProcessorCount / 2 ? CSIM_ENGINE_TABLE : (pfx_ok ? CSIM_ENGINE_PREFIX : CSIM_ENGINE_FULL);

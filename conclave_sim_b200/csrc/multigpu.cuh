@@ -265,6 +265,7 @@ extern "C" csim_status csim_group_run(csim_group* g, const csim_run_args* ra, fl
         csim_run_args a = *ra;
         a.buffers_on_device = 1; a.stream = st;
         a.sim_id_begin = ra->sim_id_begin + beg[i]; a.n_sims = cnt[i];
+        a.auto_batch_sims = ra->auto_batch_sims ? ra->auto_batch_sims : ra->n_sims;      // AUTO chooses for the whole job, not for the shard
         CU_TRY(c->o_winner.reserve(4 * nl)); a.winner = (int32_t*)c->o_winner.p;
         CU_TRY(c->o_rounds.reserve(4 * nl)); a.rounds = (int32_t*)c->o_rounds.p;
         a.reason = nullptr; a.final_votes = nullptr; a.round_tallies = nullptr; a.uniform_tape = nullptr;

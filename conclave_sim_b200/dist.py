@@ -95,7 +95,10 @@ class DeviceBatch:
         b = a + n_sets * (R + 1)
         self.winner_hist, self.rounds_hist, self.totals = self.hist[:a], self.hist[a:b], self.hist[b:]
 
-    def run(self, param_sets, *, sim_id_begin: int, seed: int, wiring: int, engine: int, precision: int, reduce: bool = True):
+    def run(self, param_sets, *, sim_id_begin: int, seed: int, wiring: int, engine: int, precision: int, reduce: bool = True,
+            job_sims: int = 0):
+        """job_sims: trials per set of the whole job over all ranks (so that CSIM_ENGINE_AUTO chooses the same engine on every
+        rank as a single-device run of the job would); 0 = this shard's own size."""
         torch = self.torch
         self.hist.zero_()
         stream = torch.cuda.current_stream(self.winner.device).cuda_stream
@@ -103,7 +106,7 @@ class DeviceBatch:
             self.engine.run_device(param_sets, self.n_sims_local, winner=self.winner, rounds=self.rounds, reason=self.reason,
                                    winner_hist=self.winner_hist, rounds_hist=self.rounds_hist, totals=self.totals,
                                    sim_id_begin=sim_id_begin, seed=seed, wiring=wiring, engine=engine, precision=precision,
-                                   stream=stream)
+                                   stream=stream, auto_batch_sims=job_sims)
         if reduce:
             if self.comm is not None:
                 self.engine.allreduce_hists(self.comm, self.winner_hist, self.rounds_hist, self.totals, self.n_sets, self.R, stream)

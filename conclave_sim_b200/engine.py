@@ -273,7 +273,7 @@ class Engine:
     def run_device(self, param_sets: Sequence[CsimParams], n_sims: int, *, winner, rounds, winner_hist=None,
                    rounds_hist=None, totals=None, reason=None, final_votes=None, round_tallies=None,
                    uniform_tape=None, sim_id_begin: int = 0, seed: int = 0, wiring: int = WIRING_REF_CLI,
-                   engine: int = ENGINE_AUTO, precision: int = FP32, stream: int = 0) -> None:
+                   engine: int = ENGINE_AUTO, precision: int = FP32, stream: int = 0, auto_batch_sims: int = 0) -> None:
         """Device-buffer call: every array argument is a torch CUDA tensor (or anything with
         data_ptr()) on this engine's device; work is only ENQUEUED on `stream` (a raw cudaStream_t
         handle, e.g. torch.cuda.current_stream().cuda_stream).  Histograms are accumulated into."""
@@ -287,6 +287,7 @@ class Engine:
         a.final_votes = dp(final_votes); a.round_tallies = dp(round_tallies)
         a.winner_hist = dp(winner_hist); a.rounds_hist = dp(rounds_hist); a.totals = dp(totals)
         a.buffers_on_device = 1; a.stream = C.c_void_p(int(stream)) if stream else None
+        a.auto_batch_sims = int(auto_batch_sims)       # the whole job's trials per set when this batch is one rank's shard (AUTO's choice)
         check(self._lib.csim_run(self._ctx, C.byref(a)))
 
     def last_run_info(self, requested_precision: Optional[int] = None):
@@ -308,7 +309,7 @@ class Engine:
         nch, chunk = C.c_int32(), C.c_int32()
         check(self._lib.csim_engine_probs(self._ctx, C.byref(params), int(wiring), int(engine), int(round), _ptr(pv), _ptr(pc), _ptr(ft),
                                           _ptr(scores), _ptr(prefix), cap, C.byref(nch), C.byref(chunk)))
-        return scores, prefix.reshape(-1)[:E * nch.value].reshape(E, nch.value).copy(), chunk.value
+        return scores, prefix[:, :nch.value].copy(), chunk.value
 
     # ------------------------------------------------------------------ multi-process NCCL (one process per GPU)
     def nccl_comm_create(self, unique_id: bytes, n_ranks: int, rank: int) -> int:

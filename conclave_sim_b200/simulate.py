@@ -203,7 +203,7 @@ def _run_simulations_torchrun(tr, elector_data_full, model_params, num_simulatio
     R = int(params.max_rounds)
     batch = DeviceBatch(eng, 1, count, R, want_reason=True, comm=csim_comm(eng))
     batch.run([params], sim_id_begin=int(sim_id_begin) + begin, seed=seed, wiring=_WIRING[wiring], engine=_ENGINE[engine],
-              precision=_PRECISION[precision])
+              precision=_PRECISION[precision], job_sims=int(num_simulations))
     wh, rh, tot = batch.hists()
     # rows: every rank's (winner, rounds, reason) to rank 0, in sim-id order
     counts = [shard_range(num_simulations, r, world)[1] for r in range(world)]

@@ -158,6 +158,10 @@ typedef struct csim_run_args {
                                           enqueues work on `stream` (uniform_tape included). */
     int32_t  reserved;
     void*    stream;                /* cudaStream_t, NULL = default stream */
+    uint64_t auto_batch_sims;       /* 0, or the trials per parameter set of the WHOLE job this batch is one shard of:
+                                       CSIM_ENGINE_AUTO then chooses as it would for the whole job, so that every shard of a
+                                       multi-GPU run — and the single-device run it must reproduce — use the same engine
+                                       (AUTO's choice depends on the batch size).  csim_group_run sets it for its devices. */
 } csim_run_args;
 
 int         csim_abi_version(void);

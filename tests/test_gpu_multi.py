@@ -80,6 +80,12 @@ def group_vs_single(eng, devices, n=3001):
         # empty batch
         z = grp.run([p1], 0)
         assert z.winner.shape == (0,) and z.totals.sum() == 0
+        # AUTO must not depend on the split: 60 001 ref_cli trials are a TABLE job on one device, and each device of the group — whose
+        # own shard alone would be a PREFIX job — must run TABLE too (csim_run_args.auto_batch_sims), or the rows would differ
+        a = eng.run([p1], 60001, seed=21, wiring=REF_CLI)
+        b = grp.run([p1], 60001, seed=21, wiring=REF_CLI)
+        assert a.engine == "table" and b.engine == "table"
+        same(a, b)
     finally:
         grp.close()
 
@@ -239,6 +245,16 @@ def test_auto_reports_engine_and_warns_on_precision_change(eng):
     assert eng.run([p], 100000, wiring=REF_CLI).engine == "table"
     assert eng.run([p], 100, wiring=REF_CLI).engine == "prefix"
     assert eng.run([p], 100, wiring=MODEL).engine == "prefix"
+    # a shard of a larger job: AUTO chooses for the whole job (auto_batch_sims), here TABLE although 1000 trials alone mean PREFIX
+    import torch
+    from conclave_sim_b200.dist import DeviceBatch
+    b = DeviceBatch(eng, 1, 1000, 20, want_reason=True)
+    b.run([p], sim_id_begin=0, seed=1, wiring=REF_CLI, engine=0, precision=FP32, reduce=False, job_sims=100000)
+    torch.cuda.synchronize()
+    assert eng.last_run_info()[0] == "table"
+    b.run([p], sim_id_begin=0, seed=1, wiring=REF_CLI, engine=0, precision=FP32, reduce=False)
+    torch.cuda.synchronize()
+    assert eng.last_run_info()[0] == "prefix"
     r = eng.run([p], 64, wiring=MODEL, precision=FP64)
     assert (r.engine, r.precision) == ("dense", "fp64")
     px = to_params(O.ModelParams(**{**CFG2, "enable_candidate_fatigue": True}), O.EngineParams(max_rounds=20, supermajority_threshold=0.56, enable_candidate_fatigue=True))
