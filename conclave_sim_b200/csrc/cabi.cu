@@ -4,34 +4,14 @@
 // reference derives them in fp64 (beta schedule model.py:562-580, vote threshold
 // simulate.py:175), size grids as multiples of the SM count, and move buffers when the caller
 // hands host memory.  There is no CPU implementation of the hot path in this file.
-#include <cuda_runtime.h>
-#include <math.h>
-#include <stdarg.h>
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
-
-#include <algorithm>
-#include <map>
-#include <string>
-#include <vector>
-
-#include "conclave_b200.h"
-#include "common.cuh"
-#include "exact64.cuh"
-#include "dense32.cuh"
+#include "internal.cuh"
+#include "exact64.cuh"      // k_base_scores64 / k_prob_matrix64 of csim_prob_matrix
 #include "prob32.cuh"
-#include "table.cuh"
-#include "prefix.cuh"
-#include "full32.cuh"
+#include "table.cuh"        // cdf_round_stride (csim_engine_probs reads the table engine's fp32 CDF rows back)
 
 static thread_local std::string g_err;
 
-#ifndef CSIM_GRID_TILE
-#define CSIM_GRID_TILE 65535           // gridDim.y / .z limit: the table-build launches are tiled over (set, round)
-#endif
-
-static csim_status fail(csim_status st, const char* fmt, ...) {
+csim_status fail(csim_status st, const char* fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
@@ -39,79 +19,6 @@ static csim_status fail(csim_status st, const char* fmt, ...) {
     va_end(ap);
     g_err = buf;
     return st;
-}
-
-#define CU_TRY(expr)                                                                                   \
-    do {                                                                                               \
-        cudaError_t _e = (expr);                                                                       \
-        if (_e != cudaSuccess)                                                                         \
-            return fail(CSIM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
-    } while (0)
-
-// grow-only device buffer
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t n) {
-        if (n == 0) n = 16;
-        if (n <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        cudaError_t e = cudaMalloc(&p, n);
-        if (e == cudaSuccess) cap = n;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
-// csim_engine_probs: while one is set on the context, the launchers pick the PROBE instantiation of their trial kernel
-struct ProbeReq {
-    int round = 1;
-    const int32_t* prev_vote = nullptr;     // device copies
-    const int32_t* prev_count = nullptr;
-    const uint8_t* fatigued = nullptr;
-    float* scores = nullptr;                // [E][E]
-    float* prefix = nullptr;                // [E][cap]
-    int cap = 0;
-    int nch = 0, chunk = 0;                 // filled by the launcher
-};
-
-struct csim_ctx {
-    ProbeReq* probe = nullptr;
-    int device = 0;
-    cudaDeviceProp prop{};
-    int E = 0, Epad = 0, G = 0;
-    DevBuf x64, x32, region, pap;
-    DevBuf sets, betas, nbeta, W, tab, cdf64, cdfk64, cdf32, cdfk32, ptab;
-    double x_mid = 0.0, x_half = 0.0;   // centre and half-range of ideology_score (factorised exp)
-    // host-buffer mode staging
-    DevBuf o_winner, o_rounds, o_reason, o_final, o_tallies, o_whist, o_rhist, o_totals, i_tape;
-    // prob-matrix staging
-    DevBuf p_prev, p_cnt, p_fat, p_shares, p_bw, p_out, p_cand, p_pref;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEvent_t ev_busy = nullptr;      // recorded behind the last work a call enqueued: the next call's stream waits on it
-    bool ev_valid = false, busy_valid = false;
-    int64_t launches = 0;
-    float last_ms = -1.f;
-    int last_engine = CSIM_ENGINE_AUTO, last_precision = CSIM_FP32, last_fell = 0;
-};
-
-// Entry points switch to the context's device; the caller's current device is restored on every exit path.
-struct DeviceGuard {
-    int prev = -1;
-    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
-
-// A context serves one stream at a time (its per-batch scratch is overwritten by the next call): every call makes its
-// stream wait on what the previous call enqueued, and leaves its own marker behind.
-static cudaError_t ctx_wait_prev(csim_ctx* c, cudaStream_t st) {
-    return c->busy_valid ? cudaStreamWaitEvent(st, c->ev_busy, 0) : cudaSuccess;
-}
-static cudaError_t ctx_mark_busy(csim_ctx* c, cudaStream_t st) {
-    cudaError_t e = cudaEventRecord(c->ev_busy, st);
-    if (e == cudaSuccess) c->busy_valid = true;
-    return e;
 }
 
 extern "C" int csim_abi_version(void) { return CSIM_ABI_VERSION; }
@@ -256,14 +163,6 @@ extern "C" int32_t csim_vote_threshold(double share, int32_t E, int32_t strict) 
     return v;
 }
 
-static RosterDev roster_dev(const csim_ctx* c) {
-    RosterDev r;
-    r.E = c->E; r.Epad = c->Epad; r.G = c->G;
-    r.x64 = (const double*)c->x64.p; r.x32 = (const float*)c->x32.p;
-    r.region = (const int32_t*)c->region.p; r.pap = (const uint8_t*)c->pap.p;
-    return r;
-}
-
 static DevSet make_set(const csim_params* p, int E, int wiring) {
     DevSet s;
     memset(&s, 0, sizeof s);
@@ -364,376 +263,6 @@ extern "C" csim_status csim_prob_matrix(csim_ctx* c, const csim_params* p, doubl
 // ---------------------------------------------------------------------------------------------
 // csim_run
 // ---------------------------------------------------------------------------------------------
-template <class K>
-static csim_status persistent_grid(csim_ctx* c, K kernel, int threads, size_t smem, uint64_t n_trials, int warps_per_cta, int* grid) {
-    CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
-    if (per_sm < 1) return fail(CSIM_ERR_UNSUPPORTED, "kernel does not fit on an SM (threads=%d, smem=%zu)", threads, smem);
-    const uint64_t want = (n_trials + warps_per_cta - 1) / warps_per_cta;
-    const uint64_t full = (uint64_t)c->prop.multiProcessorCount * per_sm;     // a multiple of the SM count
-    *grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, full));
-    return CSIM_OK;
-}
-
-static csim_status launch_exact64(csim_ctx* c, const csim_run_args* ra, const std::vector<DevSet>& hs, const BatchDev& b,
-                                  const TrialOut& out, cudaStream_t st) {
-    const int E = c->E, R = b.R;
-    const size_t wbytes = sizeof(double) * (size_t)b.n_sets * R * E * c->Epad;
-    if (wbytes > ((size_t)96 << 30)) return fail(CSIM_ERR_UNSUPPORTED, "fp64 base-score tables need %zu bytes", wbytes);
-    CU_TRY(c->W.reserve(wbytes));
-    RosterDev ro = roster_dev(c);
-    for (int sr0 = 0; sr0 < b.n_sets * R; sr0 += CSIM_GRID_TILE) {       // tiled over the 65535 limit of gridDim.z
-        dim3 g((c->Epad + 127) / 128, E, std::min(CSIM_GRID_TILE, b.n_sets * R - sr0));
-        k_base_scores64<<<g, 128, 0, st>>>(ro, b.sets, (const double*)c->betas.p, R, (double*)c->W.p, sr0);
-        ++c->launches;
-    }
-    Exact64Args a;
-    a.ro = ro; a.b = b; a.out = out; a.W = (const double*)c->W.p; a.wiring = ra->wiring;
-    int Fmax = 1, kmax = 1;
-    for (const DevSet& s : hs) { Fmax = std::max(Fmax, s.fat_rounds); kmax = std::max(kmax, s.k); }
-    a.Fmax = Fmax; a.kmax = kmax;
-    a.warp_smem = exact64_warp_smem(E, Fmax, kmax);
-    int wpc = (int)std::min<size_t>(8, (200 * 1024) / a.warp_smem);
-    if (wpc < 1) return fail(CSIM_ERR_UNSUPPORTED, "roster of %d electors needs %zu B of shared memory per trial", E, a.warp_smem);
-    a.warps_per_cta = wpc;
-    const size_t smem = a.warp_smem * wpc;
-    int grid = 1;
-    csim_status s = persistent_grid(c, k_trials_exact64, wpc * 32, smem, (uint64_t)b.n_sets * b.n_sims, wpc, &grid);
-    if (s != CSIM_OK) return s;
-    CU_TRY(cudaEventRecord(c->ev0, st));
-    k_trials_exact64<<<grid, wpc * 32, smem, st>>>(a);
-    CU_TRY(cudaEventRecord(c->ev1, st));
-    c->ev_valid = true;
-    ++c->launches;
-    CU_TRY(cudaGetLastError());
-    return CSIM_OK;
-}
-
-template <int LC, bool MODEL, bool FACT>
-static csim_status launch_dense32_t(csim_ctx* c, Dense32Args& a, cudaStream_t st) {
-    a.cta_smem = dense32_cta_smem(a.nch, a.L, a.ro.G);
-    a.warp_smem = dense32_warp_smem(a.ro.E, a.nch, a.L, a.kmax, MODEL);
-    int wpc = 8;
-    const size_t budget = (size_t)(220 * 1024) / CSIM_MINB;                        // CSIM_MINB CTAs per SM
-    while (wpc > 1 && a.cta_smem + a.warp_smem * wpc > budget) --wpc;
-    if (a.cta_smem + a.warp_smem * wpc > 220 * 1024)
-        return fail(CSIM_ERR_UNSUPPORTED, "roster of %d electors / %d regions needs %zu B of shared memory", a.ro.E, a.ro.G, a.cta_smem + a.warp_smem);
-    a.warps_per_cta = wpc;
-    const size_t smem = a.cta_smem + a.warp_smem * wpc;
-    int grid = 1;
-    void (*kern)(Dense32Args) = k_trials_dense32<LC, MODEL, FACT, false>;
-    if (c->probe) {
-        kern = k_trials_dense32<LC, MODEL, FACT, true>;
-        a.probe_round = c->probe->round; a.probe_prev_vote = c->probe->prev_vote; a.probe_prev_count = c->probe->prev_count;
-        a.probe_scores = c->probe->scores; a.probe_prefix = c->probe->prefix; a.probe_cap = c->probe->cap;
-        c->probe->nch = a.nch; c->probe->chunk = a.L;
-    }
-    csim_status s = persistent_grid(c, kern, wpc * 32, smem, (uint64_t)a.b.n_sets * a.b.n_sims, wpc, &grid);
-    if (s != CSIM_OK) return s;
-    if (FACT && a.b.R > 0) {
-        const int CP = a.nch * a.L;
-        const size_t tb = sizeof(float) * (size_t)a.b.n_sets * a.b.R * 4 * CP;
-        CU_TRY(c->tab.reserve(tb));
-        a.tab = (const float*)c->tab.p;
-        for (int sr0 = 0; sr0 < a.b.n_sets * a.b.R; sr0 += CSIM_GRID_TILE) {
-            dim3 g((CP + 127) / 128, std::min(CSIM_GRID_TILE, a.b.n_sets * a.b.R - sr0));
-            k_round_tables32<<<g, 128, 0, st>>>(a.ro, a.b.sets, (const double*)c->betas.p, a.b.R, CP, c->x_mid, (float*)c->tab.p, sr0);
-            ++c->launches;
-        }
-    }
-    CU_TRY(cudaEventRecord(c->ev0, st));
-    kern<<<grid, wpc * 32, smem, st>>>(a);
-    CU_TRY(cudaEventRecord(c->ev1, st));
-    c->ev_valid = true;
-    ++c->launches;
-    CU_TRY(cudaGetLastError());
-    return CSIM_OK;
-}
-
-template <int LC>
-static csim_status launch_dense32_d(csim_ctx* c, Dense32Args& a, bool model, bool fact, cudaStream_t st) {
-    if (model) return fact ? launch_dense32_t<LC, true, true>(c, a, st) : launch_dense32_t<LC, true, false>(c, a, st);
-    return fact ? launch_dense32_t<LC, false, true>(c, a, st) : launch_dense32_t<LC, false, false>(c, a, st);
-}
-
-static csim_status launch_dense32(csim_ctx* c, const csim_run_args* ra, const std::vector<DevSet>& hs, const std::vector<double>& hb,
-                                  const BatchDev& b, const TrialOut& out, cudaStream_t st) {
-    for (const DevSet& s : hs)
-        if (s.en_fat || s.en_stop)
-            return fail(CSIM_ERR_UNSUPPORTED, "candidate fatigue / stop-candidate are implemented in CSIM_FP64 precision only");
-    for (int i = 0; i < ra->n_param_sets; ++i)
-        if (ra->params[i].regional_affinity_bonus < 0 || ra->params[i].bandwagon_strength < 0 || ra->params[i].papabile_weight_factor < 0)
-            return fail(CSIM_ERR_UNSUPPORTED, "negative bonus / strength / papabile factor: use CSIM_FP64 precision");
-    if (c->G > 64) return fail(CSIM_ERR_UNSUPPORTED, "%d distinct regions (> 64): use CSIM_FP64 precision", c->G);
-    Dense32Args a;
-    a.ro = roster_dev(c); a.b = b; a.out = out; a.nbeta = (const float*)c->nbeta.p; a.wiring = ra->wiring; a.tab = nullptr;
-    a.probe_round = 0; a.probe_prev_vote = nullptr; a.probe_prev_count = nullptr; a.probe_scores = nullptr; a.probe_prefix = nullptr; a.probe_cap = 0;
-    int kmax = 1;
-    for (const DevSet& s : hs) kmax = std::max(kmax, s.k);
-    a.kmax = kmax;
-    // factorised exponential: needs beta >= 0 and e^{+-beta x'} comfortably inside fp32 range
-    bool fact = getenv("CSIM_DENSE_MUFU") == nullptr;
-    for (double be : hb) if (!(be >= 0.0) || !(be * c->x_half <= 26.0)) fact = false;   // e^{3 beta x'} must stay finite in fp32
-    const bool model = ra->wiring == CSIM_WIRING_MODEL;
-    const int E = c->E;
-    if (E <= 256) {                       // chunks of 8 candidates, at most 32 chunks
-        a.L = 8; a.nch = (E + 7) / 8;
-        return launch_dense32_d<8>(c, a, model, fact, st);
-    }
-    a.L = (((E + 31) / 32) + 3) & ~3;     // at most 32 chunks of L candidates
-    a.nch = (E + a.L - 1) / a.L;
-    return launch_dense32_d<0>(c, a, model, fact, st);
-}
-
-template <class Real>
-static csim_status launch_table_t(csim_ctx* c, const BatchDev& b, const TrialOut& out, int kmax, const Real* cdf, const Real* cdfk,
-                                  cudaStream_t st) {
-    TableArgs<Real> a;
-    a.ro = roster_dev(c); a.b = b; a.out = out; a.cdf = cdf; a.cdfk = cdfk; a.kmax = kmax;
-    const int E = c->E;
-    const size_t Ei = ((size_t)E + 3) & ~(size_t)3;
-    a.warp_smem = (Ei * 4 + (((size_t)kmax + 3) & ~(size_t)3) * 4 + Ei + 15) & ~(size_t)15;
-    const size_t qtab = (((size_t)b.R * E * sizeof(Real)) + 15) & ~(size_t)15;
-    const size_t full = (cdf_round_stride(E) * sizeof(Real) + 15) & ~(size_t)15;
-    int wpc = CSIM_TABLE_WPC;
-    a.stage_q = (qtab + a.warp_smem * wpc <= 64 * 1024) ? 1 : 0;
-    a.stage = (a.stage_q && full + qtab + a.warp_smem * wpc <= 200 * 1024) ? 1 : 0;
-    a.cta_smem = (a.stage ? full : 0) + (a.stage_q ? qtab : 0);
-    while (wpc > 1 && a.cta_smem + a.warp_smem * wpc > 220 * 1024) --wpc;
-    if (a.cta_smem + a.warp_smem * wpc > 220 * 1024)
-        return fail(CSIM_ERR_UNSUPPORTED, "table engine: a roster of %d electors does not fit in shared memory", E);
-    a.warps_per_cta = wpc;
-    const size_t smem = a.cta_smem + a.warp_smem * wpc;
-    void (*kern)(TableArgs<Real>) = a.stage ? k_trials_table<Real, true> : k_trials_table<Real, false>;
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpc * 32, smem));
-    if (per_sm < 1) return fail(CSIM_ERR_UNSUPPORTED, "table kernel does not fit on an SM (smem=%zu)", smem);
-    const uint64_t sb_trials = (uint64_t)wpc * 32;
-    const uint64_t n_sb = ((b.n_sims + sb_trials - 1) / sb_trials) * b.n_sets;
-    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_sb, (uint64_t)c->prop.multiProcessorCount * per_sm));
-    CU_TRY(cudaEventRecord(c->ev0, st));
-    kern<<<grid, wpc * 32, smem, st>>>(a);
-    CU_TRY(cudaEventRecord(c->ev1, st));
-    c->ev_valid = true;
-    ++c->launches;
-    CU_TRY(cudaGetLastError());
-    return CSIM_OK;
-}
-
-static csim_status launch_table(csim_ctx* c, const csim_run_args* ra, const std::vector<DevSet>& hs, const BatchDev& b,
-                                const TrialOut& out, cudaStream_t st) {
-    if (ra->wiring != CSIM_WIRING_REF_CLI)
-        return fail(CSIM_ERR_UNSUPPORTED, "the table engine exists for the ref_cli wiring only (under `model` the matrix depends on the trial)");
-    const int E = c->E, R = b.R;
-    int kmax = 1;
-    for (const DevSet& s : hs) kmax = std::max(kmax, s.k);
-    const size_t rows = (size_t)b.n_sets * R * E;
-    const size_t cdf_elems = (size_t)b.n_sets * R * cdf_round_stride(E);
-    const size_t wbytes = sizeof(double) * (size_t)b.n_sets * R * E * c->Epad;
-    if (wbytes + rows * E * 12 > ((size_t)120 << 30)) return fail(CSIM_ERR_UNSUPPORTED, "CDF tables need more than 120 GB");
-    CU_TRY(c->W.reserve(wbytes));
-    CU_TRY(c->cdf64.reserve(sizeof(double) * cdf_elems));
-    CU_TRY(c->cdfk64.reserve(sizeof(double) * rows * kmax));
-    RosterDev ro = roster_dev(c);
-    for (int sr0 = 0; sr0 < b.n_sets * R; sr0 += CSIM_GRID_TILE) {       // tiled over the 65535 limit of gridDim.y / .z
-        const int nt = std::min(CSIM_GRID_TILE, b.n_sets * R - sr0);
-        dim3 g((c->Epad + 127) / 128, E, nt);
-        k_base_scores64<<<g, 128, 0, st>>>(ro, b.sets, (const double*)c->betas.p, R, (double*)c->W.p, sr0);
-        dim3 g2((E + 63) / 64, nt);
-        k_cdf_tables64<<<g2, 64, 0, st>>>(ro, b.sets, (const double*)c->W.p, R, kmax, (double*)c->cdf64.p, (double*)c->cdfk64.p, sr0);
-        c->launches += 2;
-    }
-    if (ra->precision == CSIM_FP64)
-        return launch_table_t<double>(c, b, out, kmax, (const double*)c->cdf64.p, (const double*)c->cdfk64.p, st);
-    CU_TRY(c->cdf32.reserve(sizeof(float) * cdf_elems));
-    CU_TRY(c->cdfk32.reserve(sizeof(float) * rows * kmax));
-    if (R > 0) {
-        k_f64_to_f32<<<c->prop.multiProcessorCount * 4, 256, 0, st>>>((const double*)c->cdf64.p, (float*)c->cdf32.p, cdf_elems);
-        k_f64_to_f32<<<c->prop.multiProcessorCount, 256, 0, st>>>((const double*)c->cdfk64.p, (float*)c->cdfk32.p, rows * kmax);
-        c->launches += 2;
-    }
-    return launch_table_t<float>(c, b, out, kmax, (const float*)c->cdf32.p, (const float*)c->cdfk32.p, st);
-}
-
-// ---------------------------------------------------------------------------------------------
-// PREFIX engine (prefix.cuh)
-// ---------------------------------------------------------------------------------------------
-template <bool LC8, bool MODEL, bool STAGE>
-static csim_status launch_prefix_t(csim_ctx* c, PrefixArgs& a, cudaStream_t st) {
-    void (*kern)(const PrefixArgs) = k_trials_prefix<LC8, MODEL, STAGE, false>;
-    if (c->probe) {
-        if (STAGE) return fail(CSIM_ERR_STATE, "prefix probe: tables must be read through global memory");
-        kern = k_trials_prefix<LC8, MODEL, false, true>;
-        a.probe_round = c->probe->round; a.probe_prev_vote = c->probe->prev_vote; a.probe_prev_count = c->probe->prev_count;
-        a.probe_scores = c->probe->scores; a.probe_prefix = c->probe->prefix; a.probe_cap = c->probe->cap;
-        c->probe->nch = a.nch; c->probe->chunk = 1 << a.Ls;
-    }
-    const int wpc = a.warps_per_cta;
-    const size_t smem = a.cta_smem + a.warp_smem * wpc;
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpc * 32, smem));
-    if (per_sm < 1) return fail(CSIM_ERR_UNSUPPORTED, "prefix kernel does not fit on an SM (threads=%d, smem=%zu)", wpc * 32, smem);
-    const uint64_t ctas = (uint64_t)c->prop.multiProcessorCount * per_sm;      // persistent: a multiple of the SM count
-    // work item = warps_per_cta x tpi trials of one set; ~8 items per CTA keeps the tail short while a CTA
-    // that stays inside one parameter set never re-stages its tables
-    uint64_t tpi = a.b.n_sims / ((uint64_t)wpc * ctas * 8);
-    tpi = std::max<uint64_t>(1, std::min<uint64_t>(tpi, 64));
-    a.tpi = (int)tpi;
-    const uint64_t per_item = (uint64_t)wpc * tpi;
-    const uint64_t n_items = ((a.b.n_sims + per_item - 1) / per_item) * a.b.n_sets;
-    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_items, ctas));
-    CU_TRY(cudaEventRecord(c->ev0, st));
-    kern<<<grid, wpc * 32, smem, st>>>(a);
-    CU_TRY(cudaEventRecord(c->ev1, st));
-    c->ev_valid = true;
-    ++c->launches;
-    CU_TRY(cudaGetLastError());
-    return CSIM_OK;
-}
-
-// preconditions of the fp32 PREFIX engine (launch_prefix reports the same conditions as errors)
-static bool prefix_supported(const csim_ctx* c, const csim_run_args* ra, const std::vector<DevSet>& hs, int R) {
-    for (const DevSet& s : hs) if (s.en_fat || s.en_stop) return false;
-    for (int i = 0; i < ra->n_param_sets; ++i)
-        if (ra->params[i].regional_affinity_bonus < 0 || ra->params[i].bandwagon_strength < 0 || ra->params[i].papabile_weight_factor < 0) return false;
-    if (c->E >= 32768) return false;
-    int kmax = 1;
-    for (const DevSet& s : hs) kmax = std::max(kmax, s.k);
-    PrefixArgs probe;                                        // does it fit at all? (many regions make the bonus table large)
-    memset(&probe, 0, sizeof probe);
-    return prefix_plan(probe, c->E, c->G, R, std::max(R, 1), kmax, ra->wiring == CSIM_WIRING_MODEL,
-                       (size_t)c->prop.sharedMemPerBlockOptin - 64, true);
-}
-
-static csim_status launch_prefix(csim_ctx* c, const csim_run_args* ra, const std::vector<DevSet>& hs, const BatchDev& b,
-                                 const TrialOut& out, cudaStream_t st) {
-    for (const DevSet& s : hs)
-        if (s.en_fat || s.en_stop)
-            return fail(CSIM_ERR_UNSUPPORTED, "candidate fatigue / stop-candidate are implemented in CSIM_FP64 precision only");
-    for (int i = 0; i < ra->n_param_sets; ++i)
-        if (ra->params[i].regional_affinity_bonus < 0 || ra->params[i].bandwagon_strength < 0 || ra->params[i].papabile_weight_factor < 0)
-            return fail(CSIM_ERR_UNSUPPORTED, "negative bonus / strength / papabile factor: use CSIM_FP64 precision");
-    if (ra->precision != CSIM_FP32) return fail(CSIM_ERR_UNSUPPORTED, "the prefix engine is an fp32 engine (use DENSE or TABLE with CSIM_FP64)");
-    const int E = c->E, R = b.R;
-    if (E >= 32768) return fail(CSIM_ERR_UNSUPPORTED, "prefix engine: at most 32767 electors");
-    const bool model = ra->wiring == CSIM_WIRING_MODEL;
-    PrefixArgs a;
-    memset(&a, 0, sizeof a);
-    a.ro = roster_dev(c); a.b = b; a.out = out; a.nbeta = (const float*)c->nbeta.p;
-    int kmax = 1;
-    for (const DevSet& s : hs) kmax = std::max(kmax, s.k);
-    // only rounds that can be full-field need tables: once a run-off exists (k > 0) every round after
-    // max(runoff_threshold_rounds, 1) is a run-off round (simulate.py:183-186)
-    int Rt = 1;
-    for (const DevSet& s : hs) Rt = std::max(Rt, s.k > 0 ? std::min(R, std::max(s.rr, 1)) : R);
-    Rt = std::max(1, std::min(Rt, std::max(R, 1)));
-    const bool stage_ok = getenv("CSIM_PREFIX_NOSTAGE") == nullptr && !c->probe;    // a probe reads the same tables through global memory
-    const char* ls_env = getenv("CSIM_PREFIX_LS");                  // tuning: force the chunk size (log2)
-    if (!prefix_plan(a, E, c->G, R, Rt, kmax, model, (size_t)c->prop.sharedMemPerBlockOptin - 64 /* static: the staging mbarrier */, stage_ok,
-                     ls_env ? atoi(ls_env) : 0))
-        return fail(CSIM_ERR_UNSUPPORTED, "prefix engine: a roster of %d electors does not fit in shared memory", E);
-    const bool stage = a.tab_smem != 0;
-    const int Ls = a.Ls;
-    const size_t tbytes = a.set_pitch * 4 * (size_t)b.n_sets;
-    if (tbytes > ((size_t)64 << 30)) return fail(CSIM_ERR_UNSUPPORTED, "prefix tables need %zu bytes", tbytes);
-    CU_TRY(c->ptab.reserve(tbytes));
-    a.T = (const float*)c->ptab.p;
-    for (int sr0 = 0; R > 0 && sr0 < b.n_sets * Rt; sr0 += CSIM_GRID_TILE) {
-        dim3 g((E + 7) / 8, std::min(CSIM_GRID_TILE, b.n_sets * Rt - sr0));
-        k_prefix_tables32<<<g, 256, 0, st>>>(a.ro, b.sets, (const double*)c->betas.p, R, Rt, a.Ls, a.nch, a.stride, a.rows, a.e_quad_end,
-                                             a.set_pitch, a.col_major, (float*)c->ptab.p, sr0);
-        ++c->launches;
-    }
-    const bool lc8 = Ls == 3;
-    if (model) {
-        if (stage) return lc8 ? launch_prefix_t<true, true, true>(c, a, st) : launch_prefix_t<false, true, true>(c, a, st);
-        return lc8 ? launch_prefix_t<true, true, false>(c, a, st) : launch_prefix_t<false, true, false>(c, a, st);
-    }
-    if (stage) return lc8 ? launch_prefix_t<true, false, true>(c, a, st) : launch_prefix_t<false, false, true>(c, a, st);
-    return lc8 ? launch_prefix_t<true, false, false>(c, a, st) : launch_prefix_t<false, false, false>(c, a, st);
-}
-
-// ---------------------------------------------------------------------------------------------
-// FULL engine (full32.cuh): fp32, every model term inline, fatigue + stop-candidate included
-// ---------------------------------------------------------------------------------------------
-static csim_status launch_full32(csim_ctx* c, const csim_run_args* ra, const std::vector<DevSet>& hs, const BatchDev& b,
-                                 const TrialOut& out, cudaStream_t st) {
-    if (ra->precision != CSIM_FP32) return fail(CSIM_ERR_UNSUPPORTED, "the full engine is an fp32 engine (CSIM_FP64: use DENSE)");
-    const int E = c->E, R = b.R;
-    if (E >= 32768) return fail(CSIM_ERR_UNSUPPORTED, "full engine: at most 32767 electors");
-    Full32Args a;
-    memset(&a, 0, sizeof a);
-    int kmax = 1, Fmax = 1;
-    for (const DevSet& s : hs) { kmax = std::max(kmax, s.k); Fmax = std::max(Fmax, s.fat_rounds); }
-    if (!full32_plan(a, E, c->G, R, kmax, Fmax, (size_t)c->prop.sharedMemPerBlockOptin))
-        return fail(CSIM_ERR_UNSUPPORTED, "full engine: a roster of %d electors (fatigue window %d) does not fit in shared memory", E, Fmax);
-    a.ro = roster_dev(c); a.b = b; a.out = out; a.nbeta = (const float*)c->nbeta.p;
-    const int wpc = a.warps_per_cta;
-    const size_t smem = a.cta_smem + a.warp_smem * wpc;
-    bool ext = false, neg = false;                            // which terms the batch needs decides the instantiation
-    for (const DevSet& s : hs) ext = ext || s.en_fat || s.en_stop;
-    for (int i = 0; i < ra->n_param_sets; ++i) {
-        const csim_params& q = ra->params[i];
-        neg = neg || q.regional_affinity_bonus < 0 || q.bandwagon_strength < 0 || q.papabile_weight_factor < 0 || q.stickiness_factor < -1 ||
-              q.fatigue_penalty_factor < 0 || q.stop_candidate_boost_factor < 0;
-    }
-    void (*kern)(const Full32Args) = ext ? (neg ? k_trials_full32<true, true, false> : k_trials_full32<true, false, false>)
-                                         : (neg ? k_trials_full32<false, true, false> : k_trials_full32<false, false, false>);
-    if (c->probe) {
-        kern = ext ? (neg ? k_trials_full32<true, true, true> : k_trials_full32<true, false, true>)
-                   : (neg ? k_trials_full32<false, true, true> : k_trials_full32<false, false, true>);
-        a.probe_round = c->probe->round; a.probe_prev_vote = c->probe->prev_vote; a.probe_prev_count = c->probe->prev_count;
-        a.probe_fatigued = c->probe->fatigued;
-        a.probe_scores = c->probe->scores; a.probe_prefix = c->probe->prefix; a.probe_cap = c->probe->cap;
-        c->probe->nch = a.nch; c->probe->chunk = 8 * a.Lb;
-    }
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpc * 32, smem));
-    if (per_sm < 1) return fail(CSIM_ERR_UNSUPPORTED, "full kernel does not fit on an SM (threads=%d, smem=%zu)", wpc * 32, smem);
-    const uint64_t ctas = (uint64_t)c->prop.multiProcessorCount * per_sm;
-    uint64_t tpi = a.b.n_sims / ((uint64_t)wpc * ctas * 8);
-    tpi = std::max<uint64_t>(1, std::min<uint64_t>(tpi, 64));
-    a.tpi = (int)tpi;
-    const uint64_t per_item = (uint64_t)wpc * tpi;
-    const uint64_t n_items = ((a.b.n_sims + per_item - 1) / per_item) * a.b.n_sets;
-    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_items, ctas));
-    CU_TRY(cudaEventRecord(c->ev0, st));
-    kern<<<grid, wpc * 32, smem, st>>>(a);
-    CU_TRY(cudaEventRecord(c->ev1, st));
-    c->ev_valid = true;
-    ++c->launches;
-    CU_TRY(cudaGetLastError());
-    return CSIM_OK;
-}
-
-extern "C" csim_status csim_prefix_plan_query(int32_t n_electors, int32_t n_regions, int32_t max_rounds, int32_t table_rounds, int32_t kmax,
-                                              int32_t wiring, uint64_t smem_budget, int32_t allow_stage, csim_prefix_plan* out) {
-    if (!out) return fail(CSIM_ERR_INVALID, "csim_prefix_plan_query: out is NULL");
-    if (n_electors < 1 || n_electors >= 32768 || n_regions < 1 || n_regions > n_electors || max_rounds < 0 || kmax < 0)
-        return fail(CSIM_ERR_INVALID, "csim_prefix_plan_query: need 1 <= electors < 32768, 1 <= regions <= electors, rounds >= 0, kmax >= 0");
-    PrefixArgs a;
-    memset(&a, 0, sizeof a);
-    memset(out, 0, sizeof *out);
-    const bool model = wiring == CSIM_WIRING_MODEL;
-    if (!prefix_plan(a, n_electors, n_regions, max_rounds, std::max(1, std::min(table_rounds, std::max(max_rounds, 1))), std::max(kmax, 1), model,
-                     (size_t)smem_budget, allow_stage != 0))
-        return fail(CSIM_ERR_UNSUPPORTED, "prefix engine: a roster of %d electors does not fit in %llu bytes of shared memory", n_electors,
-                    (unsigned long long)smem_budget);
-    out->staged = a.tab_smem != 0; out->chunk = 1 << a.Ls; out->n_chunks = a.nch; out->row_pitch = a.stride; out->rows = a.rows;
-    out->table_rounds = a.Rt; out->warps_per_cta = a.warps_per_cta; out->e_quad_end = a.e_quad_end;
-    out->table_bytes_per_set = a.set_pitch * 4; out->smem_tables = a.tab_smem; out->smem_cta = a.cta_smem; out->smem_per_warp = a.warp_smem;
-    out->smem_total = a.cta_smem + a.warp_smem * (uint64_t)a.warps_per_cta;
-    const uint32_t off[12] = {a.o_xs, a.o_pw, a.o_rb, a.o_xg, a.o_nbs, a.w_bwp, a.w_tally, a.w_eff, a.w_votes, a.w_mark, a.cp4, (uint32_t)a.step0_4};
-    for (int i = 0; i < 12; ++i) out->offsets[i] = off[i];
-    return CSIM_OK;
-}
-
-extern "C" int32_t csim_prefix_slot(int32_t elector, int32_t e_quad_end) { return prefix_slot(elector, e_quad_end); }
-
 extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
     if (!c || !ra) return fail(CSIM_ERR_INVALID, "csim_run: NULL argument");
     if (c->E <= 0) return fail(CSIM_ERR_STATE, "csim_run: roster not uploaded");

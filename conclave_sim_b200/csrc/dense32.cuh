@@ -99,7 +99,7 @@ __device__ __forceinline__ float f2_hi(unsigned long long v) { return __uint_as_
 
 // K0 (FACT): per (set, round) vectors of the factorised exponential, fp64 exp rounded once to fp32.
 // grid = (ceil(CP/128), sets*R), block = 128.
-__global__ void k_round_tables32(RosterDev ro, const DevSet* sets, const double* betas, int R, int CP, double xm, float* tab, int sr0) {
+static __global__ void k_round_tables32(RosterDev ro, const DevSet* sets, const double* betas, int R, int CP, double xm, float* tab, int sr0) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int sr = sr0 + blockIdx.y;
     if (c >= CP) return;

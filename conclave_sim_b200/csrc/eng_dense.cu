@@ -1,0 +1,80 @@
+// eng_dense.cu — the fp32 DENSE engine: launcher of k_trials_dense32 (dense32.cuh), the roofline kernel
+#include "internal.cuh"
+#include "dense32.cuh"
+
+template <int LC, bool MODEL, bool FACT>
+static csim_status launch_dense32_t(csim_ctx* c, Dense32Args& a, cudaStream_t st) {
+    a.cta_smem = dense32_cta_smem(a.nch, a.L, a.ro.G);
+    a.warp_smem = dense32_warp_smem(a.ro.E, a.nch, a.L, a.kmax, MODEL);
+    int wpc = 8;
+    const size_t budget = (size_t)(220 * 1024) / CSIM_MINB;                        // CSIM_MINB CTAs per SM
+    while (wpc > 1 && a.cta_smem + a.warp_smem * wpc > budget) --wpc;
+    if (a.cta_smem + a.warp_smem * wpc > 220 * 1024)
+        return fail(CSIM_ERR_UNSUPPORTED, "roster of %d electors / %d regions needs %zu B of shared memory", a.ro.E, a.ro.G, a.cta_smem + a.warp_smem);
+    a.warps_per_cta = wpc;
+    const size_t smem = a.cta_smem + a.warp_smem * wpc;
+    int grid = 1;
+    void (*kern)(Dense32Args) = k_trials_dense32<LC, MODEL, FACT, false>;
+    if (c->probe) {
+        kern = k_trials_dense32<LC, MODEL, FACT, true>;
+        a.probe_round = c->probe->round; a.probe_prev_vote = c->probe->prev_vote; a.probe_prev_count = c->probe->prev_count;
+        a.probe_scores = c->probe->scores; a.probe_prefix = c->probe->prefix; a.probe_cap = c->probe->cap;
+        c->probe->nch = a.nch; c->probe->chunk = a.L;
+    }
+    csim_status s = persistent_grid(c, kern, wpc * 32, smem, (uint64_t)a.b.n_sets * a.b.n_sims, wpc, &grid);
+    if (s != CSIM_OK) return s;
+    if (FACT && a.b.R > 0) {
+        const int CP = a.nch * a.L;
+        const size_t tb = sizeof(float) * (size_t)a.b.n_sets * a.b.R * 4 * CP;
+        CU_TRY(c->tab.reserve(tb));
+        a.tab = (const float*)c->tab.p;
+        for (int sr0 = 0; sr0 < a.b.n_sets * a.b.R; sr0 += CSIM_GRID_TILE) {
+            dim3 g((CP + 127) / 128, std::min(CSIM_GRID_TILE, a.b.n_sets * a.b.R - sr0));
+            k_round_tables32<<<g, 128, 0, st>>>(a.ro, a.b.sets, (const double*)c->betas.p, a.b.R, CP, c->x_mid, (float*)c->tab.p, sr0);
+            ++c->launches;
+        }
+    }
+    CU_TRY(cudaEventRecord(c->ev0, st));
+    kern<<<grid, wpc * 32, smem, st>>>(a);
+    CU_TRY(cudaEventRecord(c->ev1, st));
+    c->ev_valid = true;
+    ++c->launches;
+    CU_TRY(cudaGetLastError());
+    return CSIM_OK;
+}
+
+template <int LC>
+static csim_status launch_dense32_d(csim_ctx* c, Dense32Args& a, bool model, bool fact, cudaStream_t st) {
+    if (model) return fact ? launch_dense32_t<LC, true, true>(c, a, st) : launch_dense32_t<LC, true, false>(c, a, st);
+    return fact ? launch_dense32_t<LC, false, true>(c, a, st) : launch_dense32_t<LC, false, false>(c, a, st);
+}
+
+csim_status launch_dense32(csim_ctx* c, const csim_run_args* ra, const std::vector<DevSet>& hs, const std::vector<double>& hb,
+                                  const BatchDev& b, const TrialOut& out, cudaStream_t st) {
+    for (const DevSet& s : hs)
+        if (s.en_fat || s.en_stop)
+            return fail(CSIM_ERR_UNSUPPORTED, "candidate fatigue / stop-candidate are implemented in CSIM_FP64 precision only");
+    for (int i = 0; i < ra->n_param_sets; ++i)
+        if (ra->params[i].regional_affinity_bonus < 0 || ra->params[i].bandwagon_strength < 0 || ra->params[i].papabile_weight_factor < 0)
+            return fail(CSIM_ERR_UNSUPPORTED, "negative bonus / strength / papabile factor: use CSIM_FP64 precision");
+    if (c->G > 64) return fail(CSIM_ERR_UNSUPPORTED, "%d distinct regions (> 64): use CSIM_FP64 precision", c->G);
+    Dense32Args a;
+    a.ro = roster_dev(c); a.b = b; a.out = out; a.nbeta = (const float*)c->nbeta.p; a.wiring = ra->wiring; a.tab = nullptr;
+    a.probe_round = 0; a.probe_prev_vote = nullptr; a.probe_prev_count = nullptr; a.probe_scores = nullptr; a.probe_prefix = nullptr; a.probe_cap = 0;
+    int kmax = 1;
+    for (const DevSet& s : hs) kmax = std::max(kmax, s.k);
+    a.kmax = kmax;
+    // factorised exponential: needs beta >= 0 and e^{+-beta x'} comfortably inside fp32 range
+    bool fact = getenv("CSIM_DENSE_MUFU") == nullptr;
+    for (double be : hb) if (!(be >= 0.0) || !(be * c->x_half <= 26.0)) fact = false;   // e^{3 beta x'} must stay finite in fp32
+    const bool model = ra->wiring == CSIM_WIRING_MODEL;
+    const int E = c->E;
+    if (E <= 256) {                       // chunks of 8 candidates, at most 32 chunks
+        a.L = 8; a.nch = (E + 7) / 8;
+        return launch_dense32_d<8>(c, a, model, fact, st);
+    }
+    a.L = (((E + 31) / 32) + 3) & ~3;     // at most 32 chunks of L candidates
+    a.nch = (E + a.L - 1) / a.L;
+    return launch_dense32_d<0>(c, a, model, fact, st);
+}
+

@@ -17,7 +17,7 @@
 // ---------------------------------------------------------------------------
 // K0: base scores.  grid = (ceil(Epad/128), C, <= 65535 of the sets*R tables from sr0), block = 128 (threads over e).
 // ---------------------------------------------------------------------------
-__global__ void k_base_scores64(RosterDev ro, const DevSet* sets, const double* betas /*[sets][R]*/, int R, double* W, int sr0) {
+static __global__ void k_base_scores64(RosterDev ro, const DevSet* sets, const double* betas /*[sets][R]*/, int R, double* W, int sr0) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const int c = blockIdx.y;
     const int sr = sr0 + blockIdx.z;           // set * R + (round - 1); sr0: launches are tiled over the 65535 grid limit
@@ -172,7 +172,7 @@ __host__ __device__ inline size_t exact64_warp_smem(int E, int Fmax, int kmax) {
 #ifndef CSIM_EXACT_MINB
 #define CSIM_EXACT_MINB 3      // 80 registers: the fp64 engine is latency-bound, three CTAs per SM nearly halve its time
 #endif
-__global__ void __launch_bounds__(256, CSIM_EXACT_MINB) k_trials_exact64(Exact64Args a) {
+static __global__ void __launch_bounds__(256, CSIM_EXACT_MINB) k_trials_exact64(Exact64Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int E = a.ro.E, C = E, R = a.b.R;
@@ -352,7 +352,7 @@ struct ProbArgs {
     double* P;                // [E][ncand] out
 };
 
-__global__ void k_prob_bw64(ProbArgs a) {       // single block: bandwagon bonuses (model.py:326-354)
+static __global__ void k_prob_bw64(ProbArgs a) {       // single block: bandwagon bonuses (model.py:326-354)
     __shared__ int smx;
     const int C = a.ro.E;
     if (threadIdx.x == 0) smx = 0;
@@ -366,7 +366,7 @@ __global__ void k_prob_bw64(ProbArgs a) {       // single block: bandwagon bonus
         a.bw[c] = (mx > 0 && a.prev_count[c] > 0) ? __dmul_rn(__ddiv_rn((double)a.prev_count[c], (double)mx), a.S.bandwagon) : 0.0;
 }
 
-__global__ void k_prob_matrix64(ProbArgs a, int use_bw) {
+static __global__ void k_prob_matrix64(ProbArgs a, int use_bw) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const int E = a.ro.E, C = E;
     if (e >= E) return;

@@ -186,7 +186,7 @@ __host__ inline bool prefix_plan(PrefixArgs& a, int E, int G, int R, int Rt, int
 // K0: chunk-prefix tables.  One warp per (set, round, elector), lane j sums chunk j in fp64 (the order of the
 // terms is model.py:311-324: exp, papabile factor, regional bonus), an inclusive warp scan makes the prefixes.
 // grid = (ceil(E / 8), sets * Rt), block = 256.
-__global__ void k_prefix_tables32(RosterDev ro, const DevSet* sets, const double* betas, int R, int Rt, int Ls, int nch, int stride,
+static __global__ void k_prefix_tables32(RosterDev ro, const DevSet* sets, const double* betas, int R, int Rt, int Ls, int nch, int stride,
                                   int rows, int e_quad_end, size_t set_pitch, int col_major, float* T, int sr0) {
     const int lane = threadIdx.x & 31, e = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int sr = sr0 + blockIdx.y;
@@ -377,7 +377,7 @@ __device__ __forceinline__ int prefix_draw(const PrefixCtx& k, const PrefixArgs&
 
 // One thread: (re-)arm the CTA's mbarrier and issue the set's tables as bulk copies (TMA 1-D, UBLKCP) of <= 32 KB, all
 // completing on that barrier.  Kept out of line so that its registers do not weigh on the trial loop.
-__device__ __noinline__ void prefix_stage_tables(uint32_t dst, const float* src, uint32_t total, uint32_t bar, bool first) {
+static __device__ __noinline__ void prefix_stage_tables(uint32_t dst, const float* src, uint32_t total, uint32_t bar, bool first) {
     if (!first) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
     mbar_init(bar, 1);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

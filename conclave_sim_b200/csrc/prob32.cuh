@@ -18,7 +18,7 @@ struct Prob32Args {
 };
 
 // One warp per elector row; lanes stride over candidates (model.py:311-486 in fp32).
-__global__ void k_prob_matrix32(Prob32Args a) {
+static __global__ void k_prob_matrix32(Prob32Args a) {
     const int lane = threadIdx.x & 31;
     const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int E = a.ro.E, C = E;

@@ -48,7 +48,7 @@ __device__ __forceinline__ void cdf_row_exact64(F& prob, int ncol, double* out) 
 
 __host__ __device__ inline size_t cdf_round_stride(int E) { return ((size_t)E * E + 3) & ~(size_t)3; }
 
-__global__ void k_cdf_tables64(RosterDev ro, const DevSet* sets, const double* W, int R, int kmax,
+static __global__ void k_cdf_tables64(RosterDev ro, const DevSet* sets, const double* W, int R, int kmax,
                                double* cdf, double* cdfk, int sr0) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const int sr = sr0 + blockIdx.y;             // set * R + (round - 1)
@@ -67,7 +67,7 @@ __global__ void k_cdf_tables64(RosterDev ro, const DevSet* sets, const double* W
     if (S.k > 0) cdf_row_exact64(p, S.k, cdfk + ((size_t)sr * E + e) * kmax);
 }
 
-__global__ void k_f64_to_f32(const double* in, float* out, size_t n) {
+static __global__ void k_f64_to_f32(const double* in, float* out, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = (float)in[i];
 }
 

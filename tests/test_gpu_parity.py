@@ -258,6 +258,56 @@ def test_distribution_matches_reference_sample(eng, precision, engine):
     assert p_w > 0.01 and p_r > 0.01 and p_ks > 0.01
 
 
+DIST_CASES = {
+    "cfg1": dict(roster="real", E=134, R=20, thr=2 / 3, n=400_000, engines=[("fp32", 0), ("fp32", 1), ("fp64", 2)]),
+    "cfg4a": dict(roster="real", E=134, R=20, thr=0.5, n=400_000, engines=[("fp32", 0), ("fp32", 1), ("fp64", 2)]),
+    "cfg5": dict(roster=1024, E=1024, R=50, thr=0.56, n=60_000, engines=[("fp32", 0), ("fp32", 2)]),
+}
+
+
+@pytest.mark.parametrize("name", list(DIST_CASES))
+def test_distribution_matches_reference_sample_other_configs(eng, name):
+    """The same gate on BASELINE configs[0] (CLI defaults: almost nobody wins — the informative distributions are the plurality
+    leader of the last round and its vote count), one set of the cfg-4 sweep grid and the cfg-5 shape (1024 x 1024, R = 50),
+    each against an independently seeded sample of the UNMODIFIED reference (tests/golden/dist_<name>.json,
+    oracle/gen_golden_dist.py): chi-square on winners, rounds and last-round leader, KS on rounds and leader votes; p > 0.01."""
+    from scipy import stats
+    from conclave_sim_b200 import FP32, FP64
+    c = DIST_CASES[name]
+    with open(os.path.join(G.GOLD, f"dist_{name}.json")) as f:
+        ref = json.load(f)
+    roster = G.real_roster() if c["roster"] == "real" else O.synthetic_roster(c["roster"])
+    upload(eng, roster)
+    E, R, n = c["E"], c["R"], c["n"]
+    assert ref["max_rounds"] == R and abs(ref["threshold"] - c["thr"]) < 1e-12 and len(ref["winner_hist"]) == E
+    p = to_params(O.ModelParams(**ref["model_params"]), O.EngineParams(max_rounds=R, supermajority_threshold=c["thr"]))
+    for precision, engine in c["engines"]:
+        out = eng.run([p], n, seed=24681357, precision=FP32 if precision == "fp32" else FP64, engine=engine, want_reason=False)
+        pvals = {}
+        gw = np.concatenate([out.winner_hist[0, :E], [out.winner_hist[0, E]]])
+        rw = np.concatenate([ref["winner_hist"], [ref["no_winner"]]])
+        pvals["chi2 winners"] = _chi2_homogeneity(gw, rw)
+        gr = np.concatenate([out.rounds_hist[0], [out.winner_hist[0, E]]])
+        rr_ = np.concatenate([ref["rounds_hist_success"], [ref["no_winner"]]])
+        if (gr > 0).sum() > 1 or (rr_ > 0).sum() > 1:
+            pvals["chi2 rounds"] = _chi2_homogeneity(gr, rr_)
+        else:
+            assert np.array_equal(gr > 0, rr_ > 0)                 # degenerate on both sides (cfg4a: every trial ends in round 6)
+        if ref["n"] - ref["no_winner"] > 20 and len(set(np.nonzero(ref["rounds_hist_success"])[0])) > 1:
+            pvals["KS rounds"] = stats.ks_2samp(np.repeat(np.arange(R + 1), out.rounds_hist[0]),
+                                                np.repeat(np.arange(R + 1), ref["rounds_hist_success"])).pvalue
+        # last round's plurality leader and its votes (needs the per-trial final votes: a smaller batch)
+        m = 100_000 if E <= 256 else 20_000
+        fv = eng.run([p], m, seed=97531, precision=FP32 if precision == "fp32" else FP64, engine=engine, want_reason=False,
+                     want_final_votes=True).final_votes
+        leader = fv.argmax(axis=1)
+        pvals["chi2 leader"] = _chi2_homogeneity(np.bincount(leader, minlength=E), ref["final_leader_hist"])
+        pvals["KS leader votes"] = stats.ks_2samp(fv.max(axis=1), np.repeat(np.arange(E + 1), ref["final_leader_votes_hist"])).pvalue
+        print(f"[{name} {precision}/{out.engine}] " + "  ".join(f"{k} p={v:.4f}" for k, v in pvals.items()) +
+              f"  success gpu={1 - gw[-1] / n:.5f} ref={1 - ref['no_winner'] / ref['n']:.5f}")
+        assert all(v > 0.01 for v in pvals.values()), (name, precision, engine, pvals)
+
+
 def test_edge_rosters(eng):
     from conclave_sim_b200 import FP32, FP64
     from oracle.gen_golden import CFG1
