@@ -11,16 +11,25 @@ reference CLI computes).  configs[1] names 1000 trials, which a B200 finishes in
 millisecond; one STEP here is therefore one batch of --trials-per-gpu trials per GPU (default
 1,250,000 = configs[2]'s 10M-trial job split over 8 GPUs, so --gpus 8 IS configs[2]; weak scaling).
 
-One step = one launch of the fp32 DENSE trial kernel (every trial re-evaluates its E x C scores
-each round) + one NCCL all-reduce of the winner / rounds histograms.  `value` is whole-job
-elector-rounds/s with inputs resident in HBM; `e2e` is the same metric through the host-buffer
-public API (roster + parameters uploaded, results copied back, every step).
+`value` / `roofline`: one step = one launch of the fp32 DENSE trial kernel (every trial re-evaluates its E x C scores each
+  round: the canonical per-trial formulation north_star describes and SURVEY 8d puts the roofline on) + ONE NCCL all-reduce
+  of the winner / rounds histograms issued through the C ABI (csim_allreduce_hists); inputs resident in HBM.
+`e2e`: the same engine through the PUBLIC call a user makes — conclave_sim_b200.simulate.run_simulations(DataFrame, ...) — with
+  host buffers: roster + parameters uploaded and the per-trial rows + histograms copied back inside every timed step; under
+  torchrun that one call shards the sim ids over the ranks, all-reduces the histograms and gathers the rows on rank 0.
+`engines`: every other engine on the same workload, each with its own timed steps (never mixed into value / roofline):
+  `auto` = what CSIM_ENGINE_AUTO — the default of the public API — runs for this workload (the TABLE engine), first-class with
+  its own e2e; prefix (both wirings), full (fatigue + stop-candidate live), dense under the `model` wiring.
+`configs` (N = 1 only): the remaining BASELINE configurations and the bit-exact fp64 engines, each timed with CUDA events:
+  fp64 table (bit-exact) at the full step size, exact64 under the `model` wiring, cfg-4 (256 sets x 100 k), cfg-5
+  (1 M x 1024^2, R = 50), and the literal cfg-1 / cfg-2 sizes through the host API.
 
 The oracle (oracle/) is only ever executed here for the cpu_baseline leg and for --impl reference.
 """
 from __future__ import annotations
 
 import argparse
+import itertools
 import json
 import os
 import subprocess
@@ -37,12 +46,17 @@ E_HEADLINE = 135
 CFG2 = dict(initial_beta_weight=1.5, enable_dynamic_beta=True, beta_increment_amount=0.3,
             beta_increment_interval_rounds=1, stickiness_factor=0.8, bandwagon_strength=0.7,
             regional_affinity_bonus=0.1, papabile_weight_factor=2.0)
+CFG1 = dict(initial_beta_weight=1.0, beta_increment_amount=0.05, beta_increment_interval_rounds=10,
+            stickiness_factor=0.5, regional_affinity_bonus=0.1, papabile_weight_factor=1.5)        # the CLI defaults (src/simulate.py:236-244)
 ENGINE_KW = dict(max_rounds=20, supermajority_threshold=0.56, runoff_threshold_rounds=5, runoff_candidate_count=2)
 SEED = 20250507
 # canonical dense work per (elector, candidate) pair
 FP32_PER_PAIR, MUFU_PER_PAIR = 10, 1
+# what the factorised kernel EXECUTES per pair in its inner loop: one packed multiply, two mins, one packed add per TWO pairs
+FACT_ISSUE_SLOTS_PER_PAIR = 2.0
 FALLBACK_FP32_GINSTR = 148 * 128 * 1.965     # architectural: SMs x FP32 lanes x GHz (used only if the microbench fails)
 FALLBACK_MUFU_GINSTR = 148 * 16 * 1.965
+NCU_DIGEST = os.path.join(ROOT, "profiles", "r02_ncu_digest.json")      # machine-readable digest of the committed ncu captures
 
 
 def synthetic_roster(E: int, seed: int = 20250507):
@@ -53,6 +67,11 @@ def synthetic_roster(E: int, seed: int = 20250507):
     region = rng.choice(8, size=E, p=p / p.sum()).astype(np.int32)
     pap = rng.random(E) < 0.15
     return ideology, region, pap
+
+
+def cfg4_grid():
+    """4 x 4 x 4 x 4 = 256 parameter sets (beta0, beta increment, papabile factor, threshold), cfg-2 otherwise."""
+    return list(itertools.product([0.5, 1.0, 1.5, 2.0], [0.0, 0.1, 0.3, 0.5], [1.0, 1.5, 2.0, 3.0], [0.5, 0.56, 0.6, 2 / 3]))
 
 
 class ClockSampler(threading.Thread):
@@ -104,7 +123,21 @@ def pair_evals(rounds: np.ndarray, E: int, rr: int, k: int) -> int:
     return int(full.sum()) * E * E + int((rounds - full).sum()) * E * k
 
 
-def cpu_oracle_rate(trials: int, threads: int, E: int, faithful: bool = True):
+def ncu_digest(kernel_key: str):
+    """The committed ncu evidence for one kernel (profiles/r02_ncu_digest.json, written by profiles/ncu_summary.py --digest from the
+    .ncu-rep captures of this round): a pointer + the few numbers, read from the file — nothing is hard-coded here."""
+    try:
+        with open(NCU_DIGEST) as f:
+            d = json.load(f)
+        rec = d.get(kernel_key)
+        if rec is not None:
+            rec = dict(rec, source=f"profiles/{os.path.basename(NCU_DIGEST)}")
+        return rec
+    except Exception:
+        return None
+
+
+def cpu_oracle_rate(trials: int, threads: int, E: int, faithful: bool = True, model_kw=None, engine_kw=None):
     """Times the C oracle (oracle/conclave_oracle.c, OpenMP) on `trials` trials of the workload.
     faithful=True: the whole E x C matrix (exp included) is re-evaluated per trial per round, as the
     reference does (src/simulate.py:121, src/model.py:311-486) -- the like-for-like baseline of the
@@ -114,13 +147,19 @@ def cpu_oracle_rate(trials: int, threads: int, E: int, faithful: bool = True):
     CO.build()
     CO.set_faithful(faithful)
     roster = O.synthetic_roster(E)
-    mp = O.ModelParams(**CFG2)
-    ep = O.EngineParams(max_rounds=20, supermajority_threshold=0.56)
+    mp = O.ModelParams(**(model_kw or CFG2))
+    ep = O.EngineParams(**(engine_kw or dict(max_rounds=20, supermajority_threshold=0.56)))
     t0 = time.perf_counter()
     out = CO.run(roster, [(mp, ep)], O.WIRING_REF_CLI, trials, seed=SEED, want_final=False, threads=threads)
     dt = time.perf_counter() - t0
     er = int(out["totals"][0, 0]) * E
     return er / dt, trials / dt, dt
+
+
+PYTHON_REFERENCE_NOTE = ("the UNMODIFIED Python reference cannot travel to the GPU box (/root/reference exists only in the build container); "
+                         "measured THERE on 8 cores, not on this box: 38.2 conclaves/s = 5.87e4 elector-rounds/s on cfg-2 "
+                         "(20 000 independently seeded trials, tests/golden/dist_cfg2.json), 31.7 conclaves/s on cfg-1 defaults, "
+                         "4.8 conclaves/s on the cfg-5 shape (tests/golden/dist_cfg1.json, dist_cfg5.json)")
 
 
 def reference_arm(args):
@@ -154,7 +193,7 @@ def reference_arm(args):
         "cpu_baseline": {"value": value, "unit": "elector-rounds/s", "cores": cores, "kind": "port",
                          "sample": f"{per_step} trials per step x {args.steps} steps, C oracle (dense per-trial matrix like the "
                                    f"reference), OpenMP on {cores} threads",
-                         "table_optimised_value": tab_er},
+                         "table_optimised_value": tab_er, "python_reference": PYTHON_REFERENCE_NOTE},
         "e2e": {"value": value, "unit": "elector-rounds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -168,6 +207,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--trials-per-gpu", type=int, default=1_250_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the N = 1 `configs` block (cfg-4 / cfg-5 / fp64 engines)")
+    ap.add_argument("--only", default=None, help="profiling aid: run only the timed steps of ONE engine (dense|auto|table|prefix|prefix_model|full) and exit")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -179,8 +220,9 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from conclave_sim_b200 import Engine, make_params, FP32, WIRING_REF_CLI, WIRING_MODEL, ENGINE_DENSE, ENGINE_TABLE, ENGINE_PREFIX, ENGINE_FULL
-    from conclave_sim_b200.dist import DeviceBatch, shard_range
+    from conclave_sim_b200 import (Engine, make_params, FP32, FP64, WIRING_REF_CLI, WIRING_MODEL, ENGINE_AUTO, ENGINE_DENSE, ENGINE_TABLE,
+                                   ENGINE_PREFIX, ENGINE_FULL)
+    from conclave_sim_b200.dist import DeviceBatch, shard_range, csim_comm
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -203,7 +245,8 @@ def main():
     R, rr, k = ENGINE_KW["max_rounds"], ENGINE_KW["runoff_threshold_rounds"], ENGINE_KW["runoff_candidate_count"]
     n_local = args.trials_per_gpu
     n_global = n_local * world
-    batch = DeviceBatch(eng, 1, n_local, R, want_reason=True)
+    comm = csim_comm(eng)                                 # ncclComm_t made through the C ABI (None on one GPU): the data path's only collective
+    batch = DeviceBatch(eng, 1, n_local, R, want_reason=True, comm=comm)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     def barrier():
@@ -211,10 +254,58 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(i: int, reduce: bool = True, engine: int = ENGINE_DENSE, wiring: int = WIRING_REF_CLI, p=None):
+    def step(i: int, reduce: bool = True, engine: int = ENGINE_DENSE, wiring: int = WIRING_REF_CLI, p=None, precision: int = FP32, b=None,
+             sets=None):
+        b = batch if b is None else b
         begin, _ = shard_range(n_global, rank, world)
-        batch.run([params if p is None else p], sim_id_begin=i * n_global + begin, seed=SEED, wiring=wiring,
-                  engine=engine, precision=FP32, reduce=reduce)
+        b.run(sets if sets is not None else [params if p is None else p], sim_id_begin=i * n_global + begin, seed=SEED, wiring=wiring,
+              engine=engine, precision=precision, reduce=reduce, job_sims=b.n_sims_local * world)
+
+    def timed(engine: int, wiring: int, base: int, p=None, precision: int = FP32, b=None, sets=None, steps=None, warm: int = 2):
+        """`steps` timed steps of one engine: L2 flushed between steps (untimed), CUDA events on the launch stream, max over ranks."""
+        b = batch if b is None else b
+        steps = args.steps if steps is None else steps
+        n_sets = 1 if sets is None else len(sets)
+        for i in range(warm):
+            step(base + i, engine=engine, wiring=wiring, p=p, precision=precision, b=b, sets=sets)
+        barrier()
+        name = eng.last_run_info()[0:2]
+        l0 = eng.stats()[0]
+        tev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t_rounds, k_ms = 0, 0.0
+        for i in range(steps):
+            flush.zero_()
+            tev[i][0].record()
+            step(base + warm + i, engine=engine, wiring=wiring, p=p, precision=precision, b=b, sets=sets)
+            tev[i][1].record()
+            tev[i][1].synchronize()
+            k_ms += eng.stats()[1]
+            t_rounds += int(b.totals.view(n_sets, 2)[:, 0].sum().item())       # already summed over ranks by the step's all-reduce
+        l1 = eng.stats()[0]
+        barrier()
+        tt = torch.tensor([sum(a.elapsed_time(c) for a, c in tev), k_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = tt[0].item()
+        trials = b.n_sims_local * world * n_sets * steps
+        Eb = eng.n_electors
+        return {"value": float(t_rounds) * Eb / (ms * 1e-3), "unit": "elector-rounds/s", "conclaves_per_sec": trials / (ms * 1e-3),
+                "ms_per_step": ms / steps, "trial_kernel_ms_per_step": tt[1].item() / steps, "steps": steps,
+                "trials_per_step": trials // steps, "mean_rounds": float(t_rounds) / trials, "engine_ran": name[0], "precision_ran": name[1],
+                "gpu_launches": int(l1 - l0)}
+
+    if args.only:
+        sel = {"dense": (ENGINE_DENSE, WIRING_REF_CLI, None), "auto": (ENGINE_AUTO, WIRING_REF_CLI, None), "table": (ENGINE_TABLE, WIRING_REF_CLI, None),
+               "prefix": (ENGINE_PREFIX, WIRING_REF_CLI, None), "prefix_model": (ENGINE_PREFIX, WIRING_MODEL, None),
+               "full": (ENGINE_FULL, WIRING_MODEL, make_params(dict(CFG2, stop_candidate_threshold_unacceptable_distance=0.3),
+                                                               enable_candidate_fatigue=True, enable_stop_candidate=True, **ENGINE_KW))}[args.only]
+        r = timed(sel[0], sel[1], 100, p=sel[2], warm=args.warmup)
+        os.dup2(real_stdout, 1)
+        if rank == 0:
+            print(json.dumps({"only": args.only, **r}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     for i in range(args.warmup):
         step(i)
@@ -242,6 +333,7 @@ def main():
         rounds_host = rd.cpu().numpy()
         tot_rounds += int(rounds_host.astype(np.int64).sum())
         tot_pairs += pair_evals(rounds_host, E, rr, k)
+    del kept_rounds
     launches1, _ = eng.stats()
     clocks = sampler.stop()
     ms_local = sum(a.elapsed_time(b) for a, b in ev)
@@ -259,128 +351,70 @@ def main():
     value = all_rounds * E / (ms_total * 1e-3)
     conclaves = n_global * args.steps / (ms_total * 1e-3)
 
-    # ---- roofline of the dominant kernel (k_trials_dense32), per launch, this rank
+    # ---- roofline of the dominant kernel (k_trials_dense32), per launch, this rank.
+    # frac = EXECUTED work against the measured peak of the same instruction mix: pair evaluations per second over the rate at
+    # which this GPU retires the kernel's own inner-loop pair body (csim_microbench(3): packed FMUL2 / FMNMX / FADD2).  The
+    # canonical SURVEY-8d accounting (10 FP32 + 1 MUFU per pair, which the factorised kernel does NOT execute) is kept beside it
+    # as `algorithmic_equivalent_frac` so that rounds stay comparable.
     try:
         peak_fp32 = eng.microbench(0); peak_mufu = eng.microbench(1); peak_mix = eng.microbench(2); peak_fact = eng.microbench(3)
-        peak_src = "measured (csim_microbench on this GPU)"
+        peak_src = "measured on this GPU by csim_microbench (k_microbench<0..3>); MEASURED_PEAKS.json has only HBM / bf16 entries, which do not bound this kernel"
     except Exception:
-        peak_fp32, peak_mufu, peak_mix, peak_fact, peak_src = FALLBACK_FP32_GINSTR, FALLBACK_MUFU_GINSTR, None, None, "architectural fallback"
+        peak_fp32, peak_mufu, peak_mix, peak_fact, peak_src = FALLBACK_FP32_GINSTR, FALLBACK_MUFU_GINSTR, None, None, "architectural fallback (148 SMs x 128 lanes x 1.965 GHz)"
     pairs_per_launch = tot_pairs / args.steps
     kern_s = (sum(kernel_ms) / args.steps) * 1e-3
-    ach_fp32 = pairs_per_launch * FP32_PER_PAIR / kern_s * 1e-9
-    ach_mufu = pairs_per_launch * MUFU_PER_PAIR / kern_s * 1e-9
+    pair_rate = pairs_per_launch / kern_s
+    fact_peak_pairs = (peak_fact / 2.5 * 1e9) if peak_fact else FALLBACK_FP32_GINSTR * 1e9 / 2.5     # microbench body = 2.5 thread-instr per pair
     out_bytes = n_local * 9 + (E + 1 + R + 1 + 2) * 8
-    roofline = {"bound": "fp32", "kernel": "k_trials_dense32<LC=8,MODEL=false,FACT=true>", "achieved": ach_fp32, "peak": peak_fp32,
-                "unit": "G thread-instr/s", "frac": ach_fp32 / peak_fp32, "traffic": 111872,
-                "traffic_note": "ncu dram__bytes_read+write of one launch at 250k trials (profiles/r01_ncu_dense32_v5_summary.txt); "
-                                "the kernel is compute-bound, HBM only sees the 9 B/trial result writeback",
-                "algorithmic": f"{FP32_PER_PAIR} FP32-pipe instr per (elector,candidate) pair evaluation (SURVEY 8d); "
-                               f"{pairs_per_launch:.4g} pair evaluations per launch (E*C in full-field rounds, E*k in run-off rounds)",
+    dig = ncu_digest("k_trials_dense32")
+    roofline = {"bound": "fp32", "kernel": "k_trials_dense32<LC=8,MODEL=false,FACT=true>",
+                "achieved": pair_rate * 1e-9, "peak": fact_peak_pairs * 1e-9, "unit": "G pair-evaluations/s", "frac": pair_rate / fact_peak_pairs,
+                "algorithmic": f"{pairs_per_launch:.4g} (elector, candidate) pair evaluations per launch (E*C in full-field rounds, E*k in run-off "
+                               f"rounds; SURVEY 8d) over the kernel's CUDA-event duration; peak = the rate at which this GPU retires the kernel's own "
+                               f"inner-loop pair body (2 FMUL2 + 2 FMNMX + FADD2 per two pairs, k_microbench<3>)",
                 "peak_source": peak_src, "kernel_ms_per_launch": kern_s * 1e3,
-                "sfu": {"achieved": ach_mufu, "peak": peak_mufu, "unit": "G MUFU/s", "frac": ach_mufu / peak_mufu,
-                        "note": "canonical 1 MUFU.EX2 per pair; the factorised kernel (FACT) issues none per pair"},
-                "note": "achieved uses the CANONICAL 10 FP32 instr/pair of SURVEY 8d so that rounds are comparable; the factorised "
-                        "kernel executes ~2.5 issue slots per pair in phase 1 (FMUL2/FMNMX/FADD2), see DESIGN.md 5 and "
-                        "profiles/*ncu_dense32*summary.txt for executed-instruction pipe utilisation",
-                "pair_evals_per_s": pairs_per_launch / kern_s,
-                "mufu_pair_body_peak_pairs_per_s": None if peak_mix is None else peak_mix / 4 * 1e9,
-                "factorised_pair_body_peak_pairs_per_s": None if peak_fact is None else peak_fact / 2.5 * 1e9,
-                "hbm_writeback_gbs": out_bytes / kern_s * 1e-9}
+                "algorithmic_equivalent_frac": pairs_per_launch * FP32_PER_PAIR / kern_s * 1e-9 / peak_fp32,
+                "algorithmic_equivalent_note": f"the canonical accounting of SURVEY 8d ({FP32_PER_PAIR} FP32 + {MUFU_PER_PAIR} MUFU per pair) against the measured "
+                                               f"FFMA rate ({peak_fp32:.4g} G thread-instr/s); the factorised kernel issues ~{FACT_ISSUE_SLOTS_PER_PAIR:g} slots per "
+                                               "pair and no MUFU, so this is NOT pipe utilisation — kept only so that rounds stay comparable",
+                "measured_peaks_ginstr": {"ffma": peak_fp32, "mufu_ex2": peak_mufu, "mufu_pair_body": peak_mix, "factorised_pair_body": peak_fact},
+                "traffic": None if dig is None else dig.get("dram_bytes_per_launch"),
+                "traffic_note": "dram__bytes_read + dram__bytes_write of ONE launch of this kernel at this step size from the committed ncu --set full "
+                                "capture (read from profiles/r02_ncu_digest.json at run time; null when the digest is absent); algorithmic HBM bytes per "
+                                f"launch = {out_bytes} (9 B/trial result rows + histograms): the kernel is compute-bound",
+                "hbm_writeback_gbs": out_bytes / kern_s * 1e-9, "ncu": dig}
 
     # ---- the other engines on the same workload, reported SEPARATELY from the dense kernel's value / roofline
-    #      (never mixed): same steps, same L2 flush, CUDA events, max over ranks
-    def timed_engine(engine: int, wiring: int, base: int, p=None):
-        for i in range(2):
-            step(base + i, engine=engine, wiring=wiring, p=p)
-        barrier()
-        tev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        t_rounds, k_ms = 0, 0.0
-        for i in range(args.steps):
-            flush.zero_()
-            tev[i][0].record()
-            step(base + 2 + i, engine=engine, wiring=wiring, p=p)
-            tev[i][1].record()
-            tev[i][1].synchronize()
-            k_ms += eng.stats()[1]
-            t_rounds += int(batch.totals[0].item())       # already summed over ranks by the step's all-reduce
-        barrier()
-        tt = torch.tensor([sum(a.elapsed_time(b) for a, b in tev), k_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = tt[0].item()
-        return {"value": float(t_rounds) * E / (ms * 1e-3), "unit": "elector-rounds/s",
-                "conclaves_per_sec": n_global * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps,
-                "trial_kernel_ms_per_step": tt[1].item() / args.steps, "mean_rounds": float(t_rounds) / (n_global * args.steps)}
-
-    table_engine = timed_engine(ENGINE_TABLE, WIRING_REF_CLI, 500)
-    table_engine.update(kernel="k_trials_table<float> (+ k_base_scores64, k_cdf_tables64, k_f64_to_f32 per step)",
-                        note="ref_cli wiring only: the probability matrix is trial-invariant there, so CDF rows are built once per "
-                             "step and a draw is a binary search; NOT comparable with the dense roofline")
-    prefix_engine = {"ref_cli": timed_engine(ENGINE_PREFIX, WIRING_REF_CLI, 600),
-                     "model": timed_engine(ENGINE_PREFIX, WIRING_MODEL, 700),
+    auto_engine = timed(ENGINE_AUTO, WIRING_REF_CLI, 500)
+    auto_engine.update(kernel="k_trials_table<float> (+ k_base_scores64, k_cdf_tables64, k_f64_to_f32 per step)",
+                       note="what CSIM_ENGINE_AUTO — the default of run_simulations / the CLI — runs for this workload: under ref_cli the probability "
+                            "matrix is trial-invariant, so CDF rows are built once per step and a draw is an 8-probe binary search in shared memory; "
+                            "NOT comparable with the dense roofline",
+                       bound={"kind": "issue slots / shared-memory latency (dependent 8-probe searches)", "ncu": ncu_digest("k_trials_table")})
+    prefix_engine = {"ref_cli": timed(ENGINE_PREFIX, WIRING_REF_CLI, 600), "model": timed(ENGINE_PREFIX, WIRING_MODEL, 700),
                      "kernel": "k_trials_prefix<LC8, MODEL, STAGE> (+ k_prefix_tables32 per step)",
-                     "note": "trial-invariant chunk-prefix tables + per-trial bandwagon / stickiness corrections: a draw is a binary "
-                             "search over 17 chunk prefixes and a re-scan of one chunk of 8 candidates; both wirings; what "
-                             "ENGINE_AUTO picks for the `model` wiring.  NOT comparable with the dense roofline"}
+                     "note": "trial-invariant chunk-prefix tables + per-trial bandwagon / stickiness corrections: a draw is a binary search over 17 chunk "
+                             "prefixes and a re-scan of one chunk of 8 candidates; both wirings; what ENGINE_AUTO picks for the `model` wiring",
+                     "bound": {"kind": "issue slots, then shared-memory wavefronts", "ncu": ncu_digest("k_trials_prefix")}}
     params_x = make_params(dict(CFG2, stop_candidate_threshold_unacceptable_distance=0.3), enable_candidate_fatigue=True,
                            enable_stop_candidate=True, **ENGINE_KW)
-    full_engine = timed_engine(ENGINE_FULL, WIRING_MODEL, 900, p=params_x)
+    full_engine = timed(ENGINE_FULL, WIRING_MODEL, 900, p=params_x)
     full_pairs = pair_evals(batch.rounds.cpu().numpy(), E, rr, k)             # this rank's last step (every step is the same size)
     full_kern_s = full_engine["trial_kernel_ms_per_step"] * 1e-3
-    full_engine.update(kernel="k_trials_full32",
+    full_engine.update(kernel="k_trials_full32<EXT=true,NEG=false>",
                        note="`model` wiring with EVERY term live: cfg-2 parameters + candidate fatigue (3 rounds below 5 %) + stop-candidate "
-                            "(unacceptable distance 0.3): all E x C scores inline per trial per round; the engine ENGINE_AUTO picks for what the "
-                            "table-based engines refuse (these terms used to run on the fp64 exact kernel only, 3.5e5 conclaves/s)")
-    full_engine["roofline"] = {"bound": "fp32", "kernel": "k_trials_full32<EXT=true,NEG=false>", "unit": "G thread-instr/s",
-                               "achieved": full_pairs * FP32_PER_PAIR / full_kern_s * 1e-9, "peak": peak_fp32,
-                               "frac": full_pairs * FP32_PER_PAIR / full_kern_s * 1e-9 / peak_fp32,
-                               "sfu_frac": full_pairs * MUFU_PER_PAIR / full_kern_s * 1e-9 / peak_mufu,
-                               "note": "the same canonical accounting as the dense roofline (10 FP32 + 1 MUFU per pair evaluation); this "
-                                       "kernel is the MUFU form with every term inline, so the fraction is what the canonical formulation "
-                                       "itself reaches here — the factorised dense kernel's fraction above is the optimised form of the same work"}
-    # what bounds those kernels, from the committed ncu captures (static evidence, not measured by this run)
-    table_engine["ncu"] = {"issue_slots_busy_pct_while_resident": 67, "bound": "shared-memory latency (serial 8-probe searches)",
-                           "source": "profiles/r01_ncu_table_r1b_summary.txt"}
-    prefix_engine["ncu"] = {"issue_slots_busy_pct": 76, "shared_wavefronts_pct_of_peak": 58, "bound": "issue slots, then shared-memory wavefronts",
-                            "source": "profiles/r01_ncu_prefix_model_final_summary.txt"}
-    full_engine["ncu"] = {"issue_slots_busy_pct": 54, "top_stall": "no_instruction", "source": "profiles/r01_ncu_full32_summary.txt"}
-    model_wiring_dense = timed_engine(ENGINE_DENSE, WIRING_MODEL, 800)
+                            "(unacceptable distance 0.3): all E x C scores inline per trial per round (MUFU form)",
+                       roofline={"bound": "fp32", "unit": "G thread-instr/s", "achieved": full_pairs * FP32_PER_PAIR / full_kern_s * 1e-9, "peak": peak_fp32,
+                                 "frac": full_pairs * FP32_PER_PAIR / full_kern_s * 1e-9 / peak_fp32,
+                                 "sfu_frac": full_pairs * MUFU_PER_PAIR / full_kern_s * 1e-9 / peak_mufu,
+                                 "note": "this kernel IS the canonical formulation (FADD, FMUL, MUFU.EX2, FFMA + the model's terms per pair), so the SURVEY-8d "
+                                         "accounting (10 FP32 + 1 MUFU per pair) is the executed one here",
+                                 "ncu": ncu_digest("k_trials_full32")})
+    model_wiring_dense = timed(ENGINE_DENSE, WIRING_MODEL, 800)
     model_wiring_dense.update(kernel="k_trials_dense32<LC=8,MODEL=true,FACT=true>",
                               note="`model` wiring (bandwagon + stickiness live, SURVEY 8f.1) on the dense kernel, for comparison")
 
-    # ---- e2e: the host-buffer public API (roster + params uploaded, results copied back, every step)
-    e2e_steps = max(2, min(args.steps, 3))
-    begin, _ = shard_range(n_global, rank, world)
-    hist_dev = torch.zeros((E + 1) + (R + 1) + 2, dtype=torch.int64, device=dev)
-    pinned = {"winner": torch.empty(n_local, dtype=torch.int32).pin_memory().numpy(),
-              "rounds": torch.empty(n_local, dtype=torch.int32).pin_memory().numpy(),
-              "reason": torch.empty(n_local, dtype=torch.uint8).pin_memory().numpy()}
-    def e2e_step(i):
-        eng._roster_key = None                      # force the roster upload inside the timed region
-        eng.upload_roster(ideology, region, pap)
-        r = eng.run([params], n_local, sim_id_begin=(1000 + i) * n_global + begin, seed=SEED, wiring=WIRING_REF_CLI,
-                    engine=ENGINE_DENSE, precision=FP32, want_reason=True, out=pinned)
-        if world > 1:
-            h = torch.from_numpy(np.concatenate([r.winner_hist.ravel(), r.rounds_hist.ravel(), r.totals.ravel()])).to(dev)
-            dist.all_reduce(h)
-            h.cpu()
-        return r
-    e2e_step(-1)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_rounds = 0
-    for i in range(e2e_steps):
-        r = e2e_step(i)
-        e2e_rounds += int(r.totals[0, 0])
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s, float(e2e_rounds)], dtype=torch.float64, device=dev)
-    if world > 1:
-        a = te.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
-        b = te.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
-        e2e_s, e2e_rounds = a[0].item(), b[1].item()
-    e2e_value = e2e_rounds * E / e2e_s
-    # the same through the reference-facing Python call (DataFrame roster, default engine = table for ref_cli)
+    # ---- e2e: the PUBLIC call (simulate.run_simulations), host buffers, every step: roster + parameters up, rows + histograms back
     import pandas as pd
     from conclave_sim_b200 import simulate as S
     df = pd.DataFrame({"ideology_score": ideology, "region": region, "is_papabile": pap},
@@ -388,32 +422,40 @@ def main():
     api_kw = dict(max_rounds=R, supermajority_threshold=ENGINE_KW["supermajority_threshold"], runoff_threshold_rounds=rr,
                   runoff_candidate_count=k)
 
-    def api_e2e(wiring: str, base: int):
-        """run_simulations(DataFrame, ...) with the default engine, roster re-uploaded every step, results on the host"""
-        S.RUNTIME.update(seed=SEED, device=local_rank, precision="fp32", engine="auto", wiring=wiring)
-        warm = [S.run_simulations(df, CFG2, n_local, sim_id_begin=begin + j, **api_kw) for j in range(2)]   # two live results: the
+    def api_e2e(wiring: str, engine: str, base: int):
+        """run_simulations(DataFrame, ...): the roster is re-uploaded every step, results land on the host (rank 0 receives every rank's
+        rows under torchrun).  CUDA events around the call on this rank's stream + the wall clock; max over ranks."""
+        S.RUNTIME.update(seed=SEED, device=local_rank, precision="fp32", engine=engine, wiring=wiring)
+        warm = [S.run_simulations(df, CFG2, n_global, sim_id_begin=j, **api_kw) for j in range(2)]   # two live results: the
         del warm                                                  # page-locked pool reaches its steady-state size before the clock starts
         barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
-        rounds_sum = 0
-        for i in range(e2e_steps):
-            S.get_engine(local_rank)._roster_key = None
-            r = S.run_simulations(df, CFG2, n_local, sim_id_begin=(base + i) * n_global + begin, **api_kw)
-            rounds_sum += int(r.totals[0, 0])
+        e0.record()
+        rounds_sum, ran = 0, None
+        for i in range(args.steps):
+            S.get_engine(local_rank)._roster_key = None           # force the roster upload inside the timed region
+            r = S.run_simulations(df, CFG2, n_global, sim_id_begin=(base + i) * n_global, **api_kw)
+            rounds_sum += int(r.totals[0, 0])                     # the reduced histograms: the whole job's rounds on every rank
+            ran = (r.engine, r.precision)
+        e1.record()
         barrier()
         dt = time.perf_counter() - t0
-        tt = torch.tensor([dt, float(rounds_sum)], dtype=torch.float64, device=dev)
+        tt = torch.tensor([dt, e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
         if world > 1:
-            a = tt.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
-            b = tt.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
-            dt, rounds_sum = a[0].item(), b[1].item()
-        return {"value": rounds_sum * E / dt, "unit": "elector-rounds/s", "conclaves_per_sec": n_global * e2e_steps / dt,
-                "api": f"conclave_sim_b200.simulate.run_simulations(DataFrame, ..., wiring='{wiring}') with the default engine"}
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt_wall, dt_dev = tt[0].item(), tt[1].item()
+        return {"value": rounds_sum * E / dt_wall, "unit": "elector-rounds/s", "conclaves_per_sec": n_global * args.steps / dt_wall, "steps": args.steps,
+                "ms_per_step": 1e3 * dt_wall / args.steps, "ms_per_step_cuda_events": 1e3 * dt_dev / args.steps, "engine_ran": ran[0], "precision_ran": ran[1],
+                "api": f"conclave_sim_b200.simulate.run_simulations(DataFrame, cfg2, {n_global} trials, wiring='{wiring}', engine='{engine}')"
+                       + (f" inside the {world}-rank torchrun job: sim ids sharded over the ranks, ONE NCCL all-reduce of the histograms through "
+                          "csim_allreduce_hists, every rank's rows gathered on rank 0" if world > 1 else "")}
 
-    table_engine["e2e_default_api"] = api_e2e("ref_cli", 2000)
-    prefix_engine["model"]["e2e_default_api"] = api_e2e("model", 3000)
-    S.RUNTIME.update(wiring="ref_cli")
-    h2d = E * (8 + 4 + 1) + 152 + 20 * 12
+    e2e_dense = api_e2e("ref_cli", "dense", 1000)
+    auto_engine["e2e"] = api_e2e("ref_cli", "auto", 2000)
+    prefix_engine["model"]["e2e"] = api_e2e("model", "auto", 3000)
+    S.RUNTIME.update(wiring="ref_cli", engine="auto")
+    h2d = E * (8 + 4 + 1) + 152 + R * 12
     d2h = n_local * 9 + ((E + 1) + (R + 1) + 2) * 8
 
     line = {
@@ -424,30 +466,83 @@ def main():
         "config": {"workload": f"cfg2 README params x {n_local} trials/GPU/step (cfg3 per-GPU share), synthetic E={E}, "
                                "ref_cli wiring, dense fp32 engine, Philox4x32-10",
                    "trials_per_step_global": n_global, "max_rounds": R, "l2": "flushed between steps (256 MiB memset, untimed)",
-                   "collective": "1 NCCL all-reduce (int64 sum) of winner/rounds histograms per step" if world > 1 else "none (1 GPU)"},
+                   "collective": "1 NCCL all-reduce (int64 sum) of winner/rounds histograms per step, issued through the C ABI (csim_allreduce_hists)"
+                                 if world > 1 else "none (1 GPU)"},
         "roofline": roofline,
-        "e2e": {"value": e2e_value, "unit": "elector-rounds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "conclave_sim_b200.Engine.run (host buffers; results land in page-locked arrays) -> csim_run"},
-        "table_engine": table_engine,
-        "prefix_engine": prefix_engine,
-        "full_engine": full_engine,
-        "model_wiring_dense": model_wiring_dense,
+        "e2e": {"value": e2e_dense["value"], "unit": "elector-rounds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                **{kk: vv for kk, vv in e2e_dense.items() if kk not in ("value", "unit")}},
+        "engines": {"auto": auto_engine, "prefix": prefix_engine, "full": full_engine, "dense_model_wiring": model_wiring_dense},
         "gpu_launches": int(launches1 - launches0),
         "clocks": clocks,
         "mean_rounds": all_rounds / (n_global * args.steps),
     }
+
+    # ---- N = 1: the remaining BASELINE configurations and the bit-exact fp64 engines, each with CUDA-event time
+    if world == 1 and not args.no_configs:
+        cfgs = {}
+        cfgs["table_fp64_bit_exact"] = dict(timed(ENGINE_TABLE, WIRING_REF_CLI, 4000, precision=FP64, steps=min(args.steps, 3), warm=1),
+                                            note="fp64 CDF tables + 53-bit uniforms: bit-identical to the oracle / the reference under shared draws "
+                                                 "(tests: 100 000 trials); same workload and step size as `value`")
+        small = DeviceBatch(eng, 1, 100_000, R, want_reason=True)
+        cfgs["exact64_model_wiring"] = dict(timed(ENGINE_DENSE, WIRING_MODEL, 4100, precision=FP64, b=small, steps=min(args.steps, 3), warm=1),
+                                            note="fp64 exact DENSE engine, `model` wiring (bandwagon + stickiness live): the parity workhorse, 100 000 trials per step")
+        cfgs["exact64_model_wiring_fatigue_stop"] = dict(timed(ENGINE_DENSE, WIRING_MODEL, 4200, p=params_x, precision=FP64, b=small, steps=min(args.steps, 3), warm=1),
+                                                         note="the same with candidate fatigue + stop-candidate live (what FULL replaces in fp32)")
+        del small
+        # cfg-4: 256 parameter sets x 100 000 trials, ONE launch with per-CTA parameters
+        sets4 = [make_params(dict(CFG2, initial_beta_weight=b0, beta_increment_amount=db, papabile_weight_factor=pw), max_rounds=20,
+                             supermajority_threshold=thr) for b0, db, pw, thr in cfg4_grid()]
+        b4 = DeviceBatch(eng, len(sets4), 100_000, R, want_reason=False)
+        cfgs["cfg4_sweep_256x100k"] = {"auto_ref_cli": timed(ENGINE_AUTO, WIRING_REF_CLI, 5000, b=b4, sets=sets4, steps=min(args.steps, 3), warm=1),
+                                       "auto_model": timed(ENGINE_AUTO, WIRING_MODEL, 5100, b=b4, sets=sets4, steps=min(args.steps, 3), warm=1),
+                                       "dense_ref_cli": timed(ENGINE_DENSE, WIRING_REF_CLI, 5200, b=b4, sets=sets4, steps=1, warm=1),
+                                       "note": "BASELINE configs[3]: SURVEY 8d grid (beta0 x increment x papabile x threshold), 25.6 M trials per step, "
+                                               "per-set histograms on the device"}
+        del b4
+        # cfg-5: synthetic 1024 x 1024 roster, R = 50, 1 M trials
+        x5, g5, p5 = synthetic_roster(1024)
+        eng.upload_roster(x5, g5, p5)
+        p5r = make_params(CFG2, max_rounds=50, supermajority_threshold=0.56)
+        b5 = DeviceBatch(eng, 1, 1_000_000, 50, want_reason=False)
+        cfgs["cfg5_1024x1024_R50_1M"] = {"auto_ref_cli": timed(ENGINE_AUTO, WIRING_REF_CLI, 6000, p=p5r, b=b5, steps=min(args.steps, 3), warm=1),
+                                         "auto_model": timed(ENGINE_AUTO, WIRING_MODEL, 6100, p=p5r, b=b5, steps=min(args.steps, 3), warm=1),
+                                         "table_ref_cli": timed(ENGINE_TABLE, WIRING_REF_CLI, 6200, p=p5r, b=b5, steps=1, warm=1),
+                                         "note": "BASELINE configs[4] at full size: 1 M trials of 1024 electors x 1024 candidates, 50 rounds"}
+        del b5
+        eng.upload_roster(ideology, region, pap)
+        # the literal cfg-1 / cfg-2 sizes through the host API (too short for events to mean much: wall clock, best of 5)
+        x134, g134, p134 = synthetic_roster(134)
+        eng.upload_roster(x134, g134, p134)
+        lit = {}
+        for nm, mp_kw, thr, nn in (("cfg1_defaults_x100", CFG1, 2 / 3, 100), ("cfg2_readme_x1000", CFG2, 0.56, 1000)):
+            pp = make_params(mp_kw, max_rounds=20, supermajority_threshold=thr)
+            eng.run([pp], nn, seed=SEED)
+            best = None
+            for _ in range(5):
+                t0 = time.perf_counter()
+                rr_ = eng.run([pp], nn, seed=SEED)
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            lit[nm] = {"wall_ms": best * 1e3, "conclaves_per_sec": nn / best, "value": rr_.elector_rounds / best, "unit": "elector-rounds/s", "engine_ran": rr_.engine}
+        cfgs["literal_small_configs_host_api"] = lit
+        eng.upload_roster(ideology, region, pap)
+        line["configs"] = cfgs
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = len(os.sched_getaffinity(0))
         probe_er, probe_c, _ = cpu_oracle_rate(2000, cores, E)
         n_cpu = max(2000, int(probe_c * 12.0))       # ~12 s of CPU work
         er, c, dt = cpu_oracle_rate(n_cpu, cores, E)
         tab_er, _, _ = cpu_oracle_rate(max(20000, int(probe_c * 40)), cores, E, faithful=False)
+        # the as-shipped command line of BASELINE configs[0] (CLI defaults, 100 trials, 20 rounds), same port, same cores
+        s_er, s_c, s_dt = cpu_oracle_rate(100, cores, 134, model_kw=CFG1, engine_kw=dict(max_rounds=20, supermajority_threshold=2 / 3))
         line["cpu_baseline"] = {"value": er, "unit": "elector-rounds/s", "conclaves_per_sec": c, "cores": cores, "kind": "port",
                                 "sample": f"{n_cpu} trials of the same workload, C oracle re-evaluating the E x C matrix per trial "
                                           f"per round like the reference (OpenMP, {cores} threads), {dt:.1f} s",
                                 "table_optimised_value": tab_er,
-                                "python_reference_in_build_container": "38.2 conclaves/s, 58.7k elector-rounds/s on 8 cores "
-                                                                       "(unmodified reference, 20000 trials; tests/golden/dist_cfg2.json)"}
+                                "as_shipped_cfg1_x100": {"value": s_er, "conclaves_per_sec": s_c, "seconds": s_dt,
+                                                         "what": "BASELINE configs[0] (`--num-simulations 100 --max-rounds 20`, CLI defaults) on the same port and cores"},
+                                "python_reference": PYTHON_REFERENCE_NOTE}
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     if rank == 0:
