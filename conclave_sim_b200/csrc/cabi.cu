@@ -450,14 +450,16 @@ extern "C" csim_status csim_engine_probs(csim_ctx* c, const csim_params* p, int3
         if (prefix_capacity < E) return fail(CSIM_ERR_INVALID, "csim_engine_probs: prefix_capacity %d < E = %d (the table engine's rows are whole CDFs)", prefix_capacity, E);
         csim_status s = csim_run(c, &ra);            // builds cdf32 for rounds 1..round exactly as a batch does
         if (s != CSIM_OK) return s;
-        std::vector<float> cdf((size_t)E * E);
-        CU_TRY(cudaMemcpy(cdf.data(), (const float*)c->cdf32.p + (size_t)(round - 1) * cdf_round_stride(E), sizeof(float) * (size_t)E * E, cudaMemcpyDeviceToHost));
-        for (int e = 0; e < E; ++e)
+        std::vector<float> cdf(cdf_round_stride(E));
+        CU_TRY(cudaMemcpy(cdf.data(), (const float*)c->cdf32.p + (size_t)(round - 1) * cdf_round_stride(E), sizeof(float) * cdf_round_stride(E), cudaMemcpyDeviceToHost));
+        const int eqe = table_e_quad_end(E);
+        for (int e = 0; e < E; ++e) {
+            const float* row = cdf.data() + (size_t)table_slot(e, eqe) * E;     // rows are stored in lane-visiting order
             for (int j = 0; j < E; ++j) {
-                const float v = cdf[(size_t)e * E + j];
-                prefix_out[(size_t)e * prefix_capacity + j] = v;
-                scores_out[(size_t)e * E + j] = j == 0 ? v : v - cdf[(size_t)e * E + j - 1];
+                prefix_out[(size_t)e * prefix_capacity + j] = row[j];
+                scores_out[(size_t)e * E + j] = j == 0 ? row[j] : row[j] - row[j - 1];
             }
+        }
         *n_chunks_out = E; *chunk_out = 1;
         return CSIM_OK;
     }

@@ -262,14 +262,20 @@ __device__ __forceinline__ int finish_draw(const LaneCtx32& k, const float* pref
         return j < C ? j : C - 1;
     }
     const float tgt = u * S;
-    int pos = 0;                  // number of chunks whose prefix is <= tgt
-    for (int step = k.step0; step > 0; step >>= 1) {
-        const int np = pos + step;
-        if (np <= nch && probe32<MODEL>(k, pref, pstride, rbrow, el.A, np - 1) <= tgt) pos = np;
+    // Bound-free search for the number of chunks whose prefix is <= tgt, in [0, nch - 1] (see prefix.cuh / table.cuh): with
+    // P = step0 = the largest power of two <= nch, one first probe picks between the windows [0, P) and [nch - P, nch); the
+    // halving steps stay inside the window, and the last probe taken IS the prefix below the chosen chunk.
+    int pos = 0;
+    float below = 0.0f;
+    if (nch > k.step0) {
+        const float f = probe32<MODEL>(k, pref, pstride, rbrow, el.A, nch - k.step0 - 1);
+        if (f <= tgt) { pos = nch - k.step0; below = f; }
     }
-    const int last_chunk = (C - 1) / L;
-    const int jstar = pos > last_chunk ? last_chunk : pos;
-    const float below = jstar > 0 ? probe32<MODEL>(k, pref, pstride, rbrow, el.A, jstar - 1) : 0.0f;
+    for (int step = k.step0 >> 1; step > 0; step >>= 1) {
+        const float f = probe32<MODEL>(k, pref, pstride, rbrow, el.A, pos + step - 1);
+        if (f <= tgt) { pos += step; below = f; }
+    }
+    const int jstar = pos;
     const int c0 = jstar * L;
     float cum = below;
     int cnt = 0;

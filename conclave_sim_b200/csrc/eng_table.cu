@@ -10,7 +10,7 @@ static csim_status launch_table_t(csim_ctx* c, const BatchDev& b, const TrialOut
     const int E = c->E;
     const size_t Ei = ((size_t)E + 3) & ~(size_t)3;
     a.warp_smem = (Ei * 4 + (((size_t)kmax + 3) & ~(size_t)3) * 4 + Ei + 15) & ~(size_t)15;
-    const size_t qtab = (((size_t)b.R * E * sizeof(Real)) + 15) & ~(size_t)15;
+    const size_t qtab = (((size_t)b.R * table_rows(E) * sizeof(Real)) + 15) & ~(size_t)15;
     const size_t full = (cdf_round_stride(E) * sizeof(Real) + 15) & ~(size_t)15;
     int wpc = CSIM_TABLE_WPC;
     a.stage_q = (qtab + a.warp_smem * wpc <= 64 * 1024) ? 1 : 0;
@@ -26,9 +26,24 @@ static csim_status launch_table_t(csim_ctx* c, const BatchDev& b, const TrialOut
     int per_sm = 0;
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpc * 32, smem));
     if (per_sm < 1) return fail(CSIM_ERR_UNSUPPORTED, "table kernel does not fit on an SM (smem=%zu)", smem);
-    const uint64_t sb_trials = (uint64_t)wpc * 32;
+    // trials per warp per super-batch: a CTA's cost is proportional to it, the kernel's duration to waves x tpw — choose the
+    // tpw in [20, 32] that wastes least in the last wave of the persistent grid (1.25 M trials, 296 CTAs: tpw 32 = 8.25 waves,
+    // i.e. 9 x 32 = 288 trial-slots per warp; tpw 30 = 8.8 waves, 9 x 30 = 270)
+    const uint64_t ctas = (uint64_t)c->prop.multiProcessorCount * per_sm;
+    int tpw = 32;
+    if (const char* e = getenv("CSIM_TABLE_TPW")) tpw = std::max(1, std::min(32, atoi(e)));
+    else {
+        uint64_t best = ~0ull;
+        for (int t = 32; t >= 20; --t) {
+            const uint64_t nsb = ((b.n_sims + (uint64_t)wpc * t - 1) / ((uint64_t)wpc * t)) * b.n_sets;
+            const uint64_t cost = ((nsb + ctas - 1) / ctas) * (uint64_t)t;
+            if (cost < best) { best = cost; tpw = t; }
+        }
+    }
+    a.tpw = tpw;
+    const uint64_t sb_trials = (uint64_t)wpc * tpw;
     const uint64_t n_sb = ((b.n_sims + sb_trials - 1) / sb_trials) * b.n_sets;
-    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_sb, (uint64_t)c->prop.multiProcessorCount * per_sm));
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_sb, ctas));
     CU_TRY(cudaEventRecord(c->ev0, st));
     kern<<<grid, wpc * 32, smem, st>>>(a);
     CU_TRY(cudaEventRecord(c->ev1, st));

@@ -378,16 +378,20 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
                         } else {
                             // ---- pass 2: chunk search + re-scan ---------------------------------------------
                             const float tgt = u * Sm;
-                            int pos = 0;
+                            int pos = 0;               // bound-free search (table.cuh): windows [0, P) / [nch - P, nch), P = step0
                             float cum = 0.0f;
-                            for (int st = step0; st > 0; st >>= 1) {
-                                const int np = min(pos + st, nch);
-                                const float f = col[32 * (np - 1)];
+                            if (nch > step0) {
+                                const float f = col[32 * (nch - step0 - 1)];
                                 const bool le = f <= tgt;
-                                pos = le ? np : pos;
+                                pos = le ? nch - step0 : 0;
+                                cum = le ? f : 0.0f;
+                            }
+                            for (int st = step0 >> 1; st > 0; st >>= 1) {
+                                const float f = col[32 * (pos + st - 1)];
+                                const bool le = f <= tgt;
+                                pos = le ? pos + st : pos;
                                 cum = le ? f : cum;
                             }
-                            if (pos >= nch) { pos = nch - 1; cum = pos > 0 ? col[32 * (pos - 1)] : 0.0f; }
                             int cnt = 0;
                             const int blk0 = pos * Lb;
                             for (int b = 0; b < Lb; ++b) {

@@ -343,18 +343,23 @@ __device__ __forceinline__ int prefix_draw(const PrefixCtx& k, const PrefixArgs&
         return j < C ? j : C - 1;
     }
     const float tgt = u * S;
+    // Bound-free search for the number of chunks whose prefix is <= tgt, in [0, nch - 1] (the last prefix is S itself; should
+    // u S round up to S the vote belongs to the last chunk).  With P = the largest power of two <= nch, one first probe picks
+    // between the overlapping windows [0, P) and [nch - P, nch); the halving steps then never leave the window: no clamps.
     int pos4 = 0;                 // 4 x number of chunks whose prefix is <= tgt
     float cum = 0.0f;             // prefix below the chunk the target falls into
-    for (int st = a.step0_4; st >= 4; st >>= 1) {
-        const int np4 = min(pos4 + st, nch4);               // probing the last entry twice is harmless
-        const float f = F(np4 - 4);
+    const int P4 = a.step0_4;
+    if (nch4 > P4) {
+        const float f = F(nch4 - P4 - 4);
         const bool le = f <= tgt;
-        pos4 = le ? np4 : pos4;
-        cum = le ? f : cum;
+        pos4 = le ? nch4 - P4 : 0;
+        cum = le ? f : 0.0f;
     }
-    if (pos4 >= nch4) {           // u S rounded up to S: the vote is in the last chunk
-        pos4 = nch4 - 4;
-        cum = pos4 > 0 ? F(pos4 - 4) : 0.0f;
+    for (int st = P4 >> 1; st >= 4; st >>= 1) {
+        const float f = F(pos4 + st - 4);
+        const bool le = f <= tgt;
+        pos4 = le ? pos4 + st : pos4;
+        cum = le ? f : cum;
     }
     const int c0 = (pos4 >> 2) << Ls;
     int cnt = 0;

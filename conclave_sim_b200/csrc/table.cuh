@@ -46,7 +46,18 @@ __device__ __forceinline__ void cdf_row_exact64(F& prob, int ncol, double* out) 
     for (int i = 0; i < ncol; ++i) out[i] = __ddiv_rn(out[i], last);  // cdf /= cdf[-1]
 }
 
-__host__ __device__ inline size_t cdf_round_stride(int E) { return ((size_t)E * E + 3) & ~(size_t)3; }
+__host__ __device__ inline size_t cdf_round_stride(int E);
+
+// How the trial kernel deals electors to lanes, and hence the order of the table rows.  Electors below e_quad_end go to lanes as
+// whole Philox quads (lane l owns electors 4 (l + 32 qi) .. + 3: one Philox call yields its four uniforms, no shuffles); the tail
+// of at most 64 goes one elector per lane.  So that the 32 lanes of a pass (fixed word index i) probe 32 CONSECUTIVE rows — same
+// column, odd pitch: conflict-free — the row of elector e is stored at table_slot(e): 128 qi + 32 i + lane.
+__host__ __device__ inline int table_e_quad_end(int E) { return (E & ~127) + ((E & 127) > 64 ? 128 : 0); }
+__host__ __device__ inline int table_slot(int e, int e_quad_end) {
+    return e < e_quad_end ? ((e >> 7) << 7) + ((e & 3) << 5) + ((e >> 2) & 31) : e;
+}
+__host__ __device__ inline int table_rows(int E) { const int q = table_e_quad_end(E); return E > q ? E : q; }
+__host__ __device__ inline size_t cdf_round_stride(int E) { return ((size_t)table_rows(E) * E + 3) & ~(size_t)3; }
 
 static __global__ void k_cdf_tables64(RosterDev ro, const DevSet* sets, const double* W, int R, int kmax,
                                double* cdf, double* cdfk, int sr0) {
@@ -62,8 +73,16 @@ static __global__ void k_cdf_tables64(RosterDev ro, const DevSet* sets, const do
     double rs = np_pairwise(row, C);                                  // model.py:451
     if (rs == 0.0) { row.degenerate = true; rs = np_pairwise(row, C); }
     Prob64 p{&row, rs};
-    cdf_row_exact64(p, C, cdf + (size_t)sr * cdf_round_stride(E) + (size_t)e * C);
-    if (e == 0) for (size_t i = (size_t)E * C; i < cdf_round_stride(E); ++i) cdf[(size_t)sr * cdf_round_stride(E) + i] = 1.0;   // pad
+    const int eqe = table_e_quad_end(E);
+    cdf_row_exact64(p, C, cdf + (size_t)sr * cdf_round_stride(E) + (size_t)table_slot(e, eqe) * C);     // rows in lane-visiting order
+    if (e == 0) {                                                    // rows no elector owns (a partly filled quad group) and the padding
+        for (int sl = 0; eqe > E && sl < table_rows(E); ++sl) {      // (eqe <= E: the slots are a permutation of the electors)
+            bool used = false;
+            for (int q = 0; q < E && !used; ++q) used = table_slot(q, eqe) == sl;
+            if (!used) for (int i = 0; i < C; ++i) cdf[(size_t)sr * cdf_round_stride(E) + (size_t)sl * C + i] = 1.0;
+        }
+        for (size_t i = (size_t)table_rows(E) * C; i < cdf_round_stride(E); ++i) cdf[(size_t)sr * cdf_round_stride(E) + i] = 1.0;
+    }
     if (S.k > 0) cdf_row_exact64(p, S.k, cdfk + ((size_t)sr * E + e) * kmax);
 }
 
@@ -83,29 +102,57 @@ struct TableArgs {
     const Real* cdfk;       // [sets][R][E][kmax]
     int kmax;
     int warps_per_cta;
+    int tpw;                // trials per warp per super-batch (<= 32: lane i holds trial i); chosen by the launcher so that the
+                            // super-batches fill whole waves of the persistent grid (a partly filled last wave idles the GPU)
     int stage;              // 1: E x C rows fit in shared memory and are staged per round
     int stage_q;            // 1: the [R][E] run-off first-column table is staged too
     size_t cta_smem;        // staged table + run-off table
     size_t warp_smem;
 };
 
+// #{i : row[i] <= u}  == searchsorted(row, u, 'right'), for a row whose last entry is > u (a CDF row ends in 1.0 and u < 1).
+// Bound-free form: with P = step0 = the largest power of two <= n, ONE first probe decides between the two overlapping windows
+// [0, P) and [n - P, n) — the answer is >= n - P exactly when row[n - P - 1] <= u — and log2(P) halving steps then stay inside
+// the chosen window by construction, so no probe needs a bound check or an index clamp.  Per probe: one load at a
+// compile-time offset from a running pointer, one compare, one predicated add (the clamped form cost 8 instructions, 6 of them
+// on the half-rate ALU pipe).  Same probe count as before (1 + log2 P).
 template <class Real>
 __device__ __forceinline__ int upper_bound_row(const Real* row, int n, int step0, Real u) {
-    int pos = 0;                                       // #{i : row[i] <= u}  == searchsorted(row, u, 'right')
     if (step0 == 128) {                                // 128 <= n <= 255: eight probes, fully unrolled
+        const Real* p = row;
+        if (n > 128) p += (row[n - 129] <= u) ? (n - 128) : 0;
 #pragma unroll
-        for (int step = 128; step > 0; step >>= 1) {
-            const int np = pos + step;
-            const Real v = row[min(np, n) - 1];
-            pos = (np <= n && v <= u) ? np : pos;
-        }
-        return pos;
+        for (int step = 64; step > 0; step >>= 1) p += (p[step - 1] <= u) ? step : 0;
+        return (int)(p - row);
     }
-    for (int step = step0; step > 0; step >>= 1) {
-        const int np = pos + step;
-        if (np <= n && row[np - 1] <= u) pos = np;
-    }
+    int pos = (n > step0 && row[n - step0 - 1] <= u) ? n - step0 : 0;
+    for (int step = step0 >> 1; step > 0; step >>= 1)
+        if (row[pos + step - 1] <= u) pos += step;
     return pos;
+}
+
+// The same search on a row staged in shared memory, on a 32-bit shared-window byte address: every probe is ONE ld.shared at an
+// immediate offset from the running address, one compare and one select-add (the generic-pointer form above makes the
+// compiler re-derive an index and a LEA per probe).  128 <= n <= 255 only (the caller checks step0 == 128).
+template <int OFF> __device__ __forceinline__ float lds_at(uint32_t a, float) {
+    float v; asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF)); return v;
+}
+template <int OFF> __device__ __forceinline__ double lds_at(uint32_t a, double) {
+    double v; asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF)); return v;
+}
+template <class Real>
+__device__ __forceinline__ int upper_bound_row_smem128(uint32_t row_a, int n, Real u) {
+    constexpr int W = (int)sizeof(Real);
+    uint32_t a = row_a;
+    if (n > 128) {                                     // window [n - 128, n) iff the (n - 128)-th entry is <= u
+        const uint32_t d = (uint32_t)(n - 128) * W;
+        const Real v = lds_at<-W>(a + d, Real(0));
+        a += (v <= u) ? d : 0u;
+    }
+#define CSIM_TSTEP(S) { const Real v = lds_at<((S) - 1) * W>(a, Real(0)); a += (v <= u) ? (uint32_t)((S) * W) : 0u; }
+    CSIM_TSTEP(64) CSIM_TSTEP(32) CSIM_TSTEP(16) CSIM_TSTEP(8) CSIM_TSTEP(4) CSIM_TSTEP(2) CSIM_TSTEP(1)
+#undef CSIM_TSTEP
+    return (int)((a - row_a) / W);
 }
 
 #ifndef CSIM_TABLE_WPC
@@ -119,7 +166,7 @@ __global__ void __launch_bounds__(CSIM_TABLE_WPC * 32, 1024 / (CSIM_TABLE_WPC * 
     const int E = a.ro.E, C = E, R = a.b.R, kmax = a.kmax;
     const int Ei = (E + 3) & ~3;
     Real* tab_s = (Real*)smem_raw;                               // staged cdf_r  [E][C]   (stage == 1)
-    Real* q_s = tab_s + (STAGE ? cdf_round_stride(E) : 0);       // run-off first-column table [R][E]
+    Real* q_s = tab_s + (STAGE ? cdf_round_stride(E) : 0);       // run-off first-column table [R][table_rows(E)], slot order
     unsigned char* base = smem_raw + a.cta_smem + (size_t)wib * a.warp_smem;
     int32_t* tally = (int32_t*)base;            base += sizeof(int32_t) * Ei;
     int32_t* eff = (int32_t*)base;              base += sizeof(int32_t) * ((kmax + 3) & ~3);
@@ -127,75 +174,86 @@ __global__ void __launch_bounds__(CSIM_TABLE_WPC * 32, 1024 / (CSIM_TABLE_WPC * 
 
     __shared__ __align__(8) unsigned long long stage_bar;                   // mbarrier of the staged table
     const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&stage_bar);
+    const uint32_t tab_a = (uint32_t)__cvta_generic_to_shared(tab_s);
     uint32_t stage_phase = 0;
     if (STAGE) {
         if (threadIdx.x == 0) mbar_init(bar_a, 1);
         __syncthreads();
     }
     const int wpc = a.warps_per_cta;
-    const uint64_t sb_trials = (uint64_t)wpc * 32;                           // trials per super-batch
+    const int tpw = a.tpw;
+    const uint64_t sb_trials = (uint64_t)wpc * tpw;                          // trials per super-batch
     const uint64_t sb_per_set = (a.b.n_sims + sb_trials - 1) / sb_trials;
     const uint64_t n_sb = sb_per_set * a.b.n_sets;
     int step0 = 1;
     while (step0 * 2 <= C) step0 *= 2;
     const bool top2_ok = C >= 2 && C < 32768;
 
-    // Electors are dealt lane-major (e = 128 g + 32 s + lane) so that the 32 lanes probe 32 different rows at
-    // the same column without bank conflicts (row pitch C is odd at E = 135; the first probes of a binary search
-    // all hit the same column).  Lane l computes the Philox call of quad 32 g + l; the word of elector e lives
-    // in lane (e >> 2) & 31 and is fetched with four shuffles.
-    const int n_groups = (E + 127) >> 7;
+    // Electors are dealt to lanes as whole Philox quads (table_slot above): lane l draws for electors 4 l .. 4 l + 3 with the
+    // four words of ONE Philox call — no shuffles, no word selection — and the rows of a pass are 32 consecutive table rows.
+    // fn(e, u, slot): slot = the elector's table row.  The tail (at most 64 electors) goes one elector per lane.
+    const int eqe = table_e_quad_end(E);
+    const int n_qit = eqe >> 7;
+    const int q_rows = table_rows(E);                            // pitch of the staged run-off table (slot order)
     auto for_each_elector = [&](int r, uint64_t t, uint32_t s_lo, uint32_t s_hi, auto&& fn) {
         const bool use_tape = F64 && a.b.tape != nullptr;
-        for (int gi = 0; gi < n_groups; ++gi) {
+        const double* tp = use_tape ? a.b.tape + (t * (uint64_t)R + (uint64_t)(r - 1)) * (uint64_t)E : nullptr;
+        for (int qi = 0; qi < n_qit; ++qi) {
+            const int q = lane + 32 * qi;
+            if (4 * q >= E) continue;
             uint32_t w[4] = {0, 0, 0, 0}, wb[4] = {0, 0, 0, 0};
             if (!use_tape) {
-                const uint32_t q = (uint32_t)(32 * gi + lane);
-                philox4x32_10(s_lo, s_hi, (uint32_t)r, q, a.b.seed_lo, a.b.seed_hi, w);
-                if (F64) philox4x32_10(s_lo, s_hi, (uint32_t)r, q | 0x80000000u, a.b.seed_lo, a.b.seed_hi, wb);
+                philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)q, a.b.seed_lo, a.b.seed_hi, w);
+                if (F64) philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)q | 0x80000000u, a.b.seed_lo, a.b.seed_hi, wb);
             }
 #pragma unroll
-            for (int sl = 0; sl < 4; ++sl) {
-                if (128 * gi + 32 * sl >= E) break;               // warp-uniform: nobody left in this group (E = 135: 3 of 8 sub-passes)
-                const int e = 128 * gi + 32 * sl + lane;
-                const int src = 8 * sl + (lane >> 2), sel = lane & 3;
-                const uint32_t a0 = __shfl_sync(CSIM_FULL, w[0], src), a1 = __shfl_sync(CSIM_FULL, w[1], src);
-                const uint32_t a2 = __shfl_sync(CSIM_FULL, w[2], src), a3 = __shfl_sync(CSIM_FULL, w[3], src);
-                const uint32_t wa = sel == 0 ? a0 : (sel == 1 ? a1 : (sel == 2 ? a2 : a3));
-                uint32_t wbb = 0;
-                if (F64) {
-                    const uint32_t b0 = __shfl_sync(CSIM_FULL, wb[0], src), b1 = __shfl_sync(CSIM_FULL, wb[1], src);
-                    const uint32_t b2 = __shfl_sync(CSIM_FULL, wb[2], src), b3 = __shfl_sync(CSIM_FULL, wb[3], src);
-                    wbb = sel == 0 ? b0 : (sel == 1 ? b1 : (sel == 2 ? b2 : b3));
-                }
+            for (int i = 0; i < 4; ++i) {
+                const int e = 4 * q + i;
                 if (e < E) {
                     Real u;
-                    if (use_tape) u = (Real)a.b.tape[(t * (uint64_t)R + (uint64_t)(r - 1)) * (uint64_t)E + e];
-                    else u = F64 ? (Real)u53_from_words(wa, wbb) : (Real)u24_from_word(wa);
-                    fn(e, u);
+                    if (use_tape) u = (Real)tp[e];
+                    else u = F64 ? (Real)u53_from_words(w[i], wb[i]) : (Real)u24_from_word(w[i]);
+                    fn(e, u, (qi << 7) + (i << 5) + lane);
                 }
             }
+        }
+        for (int e = eqe + lane; e < E; e += 32) {
+            Real u;
+            if (use_tape) u = (Real)tp[e];
+            else {
+                uint32_t w[4], wb[4] = {0, 0, 0, 0};
+                philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)(e >> 2), a.b.seed_lo, a.b.seed_hi, w);
+                if (F64) philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)(e >> 2) | 0x80000000u, a.b.seed_lo, a.b.seed_hi, wb);
+                const int sel = e & 3;
+                const uint32_t wa = sel == 0 ? w[0] : (sel == 1 ? w[1] : (sel == 2 ? w[2] : w[3]));
+                const uint32_t wbb = sel == 0 ? wb[0] : (sel == 1 ? wb[1] : (sel == 2 ? wb[2] : wb[3]));
+                u = F64 ? (Real)u53_from_words(wa, wbb) : (Real)u24_from_word(wa);
+            }
+            fn(e, u, e);
         }
     };
 
     for (uint64_t sb = blockIdx.x; sb < n_sb; sb += gridDim.x) {
         const int set = (int)(sb / sb_per_set);
-        const uint64_t i0 = (sb % sb_per_set) * sb_trials + (uint64_t)wib * 32;     // first sim index of this warp's batch
+        const uint64_t i0 = (sb % sb_per_set) * sb_trials + (uint64_t)wib * tpw;    // first sim index of this warp's batch
         const DevSet S = a.b.sets[set];
         const int k = S.k, need = S.need, rr = S.rr;
         const int r_full = k > 0 ? min(R, max(rr, 1)) : R;       // rounds 1..r_full are full-field (round 1 always is)
         const bool fast2 = (k == 2) && top2_ok;
         // lane i holds the state of trial i0 + i
         const uint64_t my_i = i0 + lane;
-        bool alive = my_i < a.b.n_sims;
+        bool alive = lane < tpw && my_i < a.b.n_sims;
         const bool exists = alive;
         int winner = -1, rounds = 0, ef0 = 0, ef1 = 0;
         const uint64_t my_t = (uint64_t)set * a.b.n_sims + my_i;
 
         // stage the run-off first-column table (k == 2 fast path) once per super-batch
         __syncthreads();
-        if (fast2 && a.stage_q)
-            for (int i = threadIdx.x; i < R * E; i += blockDim.x) q_s[i] = a.cdfk[(((size_t)set * R) * E + i) * kmax];
+        if (fast2 && a.stage_q)                                  // [R][E] in slot order: a pass reads 32 consecutive entries
+            for (int i = threadIdx.x; i < R * E; i += blockDim.x) {
+                const int rq = i / E, eq = i - rq * E;
+                q_s[rq * q_rows + table_slot(eq, eqe)] = a.cdfk[(((size_t)set * R) * E + i) * kmax];
+            }
 
         // =============== full-field rounds, round-major ===========================================
         for (int r = 1; r <= r_full; ++r) {
@@ -210,17 +268,19 @@ __global__ void __launch_bounds__(CSIM_TABLE_WPC * 32, 1024 / (CSIM_TABLE_WPC * 
             }
             __syncthreads();
             if (!__any_sync(CSIM_FULL, alive)) continue;
-            for (int ti = 0; ti < 32; ++ti) {
+            for (int ti = 0; ti < tpw; ++ti) {
                 if (!__shfl_sync(CSIM_FULL, alive ? 1 : 0, ti)) continue;
                 const uint64_t sim = a.b.sim_id_begin + i0 + ti;
                 const uint64_t t = (uint64_t)set * a.b.n_sims + i0 + ti;
                 const uint32_t s_lo = (uint32_t)sim, s_hi = (uint32_t)(sim >> 32);
                 for (int c = lane; c < C; c += 32) tally[c] = 0;
                 __syncwarp();
-                for_each_elector(r, t, s_lo, s_hi, [&](int e, Real u) {
+                for_each_elector(r, t, s_lo, s_hi, [&](int e, Real u, int slot) {
                     // STAGE: the row lives in shared memory (a typed pointer keeps these LDS, not generic loads)
-                    int vote = STAGE ? upper_bound_row<Real>(tab_s + (size_t)e * C, C, step0, u)
-                                     : upper_bound_row<Real>(tab_g + (size_t)e * C, C, step0, u);
+                    int vote;
+                    if (STAGE && step0 == 128) vote = upper_bound_row_smem128<Real>(tab_a + (uint32_t)(slot * C) * (uint32_t)sizeof(Real), C, u);
+                    else vote = STAGE ? upper_bound_row<Real>(tab_s + (size_t)slot * C, C, step0, u)
+                                      : upper_bound_row<Real>(tab_g + (size_t)slot * C, C, step0, u);
                     vote = vote < C ? vote : C - 1;
                     atomicAdd(&tally[vote], 1);
                 });
@@ -250,7 +310,7 @@ __global__ void __launch_bounds__(CSIM_TABLE_WPC * 32, 1024 / (CSIM_TABLE_WPC * 
         }
         // =============== run-off rounds, per trial =================================================
         if (k > 0 && r_full < R) {
-            for (int ti = 0; ti < 32; ++ti) {
+            for (int ti = 0; ti < tpw; ++ti) {
                 if (!__shfl_sync(CSIM_FULL, alive ? 1 : 0, ti)) continue;
                 const uint64_t sim = a.b.sim_id_begin + i0 + ti;
                 const uint64_t t = (uint64_t)set * a.b.n_sims + i0 + ti;
@@ -263,8 +323,8 @@ __global__ void __launch_bounds__(CSIM_TABLE_WPC * 32, 1024 / (CSIM_TABLE_WPC * 
                     const Real* tab_g = a.cdf + ((size_t)set * R + (r_full - 1)) * cdf_round_stride(E);
                     for (int c = lane; c < C; c += 32) tally[c] = 0;
                     __syncwarp();
-                    for_each_elector(r_full, t, s_lo, s_hi, [&](int e, Real u) {
-                        const int vote = upper_bound_row<Real>(tab_g + (size_t)e * C, C, step0, u);
+                    for_each_elector(r_full, t, s_lo, s_hi, [&](int e, Real u, int slot) {
+                        const int vote = upper_bound_row<Real>(tab_g + (size_t)slot * C, C, step0, u);
                         atomicAdd(&tally[vote < C ? vote : C - 1], 1);
                     });
                     __syncwarp();
@@ -275,9 +335,9 @@ __global__ void __launch_bounds__(CSIM_TABLE_WPC * 32, 1024 / (CSIM_TABLE_WPC * 
                     rnd = r;
                     int cnt0 = 0;
                     if (!fast2) { for (int c = lane; c < C; c += 32) tally[c] = 0; __syncwarp(); }
-                    for_each_elector(r, t, s_lo, s_hi, [&](int e, Real u) {
+                    for_each_elector(r, t, s_lo, s_hi, [&](int e, Real u, int slot) {
                         if (fast2) {
-                            const Real q0 = a.stage_q ? q_s[(r - 1) * E + e] : a.cdfk[(((size_t)set * R + (r - 1)) * E + e) * kmax];
+                            const Real q0 = a.stage_q ? q_s[(r - 1) * q_rows + slot] : a.cdfk[(((size_t)set * R + (r - 1)) * E + e) * kmax];
                             cnt0 += (q0 <= u) ? 0 : 1;                               // j = #{cdf_j <= u}; vote eff[0] iff cdf_0 > u
                         } else {
                             const Real* rowk = a.cdfk + (((size_t)set * R + (r - 1)) * E + e) * kmax;
