@@ -9,7 +9,16 @@ static csim_status launch_table_t(csim_ctx* c, const BatchDev& b, const TrialOut
     a.ro = roster_dev(c); a.b = b; a.out = out; a.cdf = cdf; a.cdfk = cdfk; a.kmax = kmax;
     const int E = c->E;
     const size_t Ei = ((size_t)E + 3) & ~(size_t)3;
-    a.warp_smem = (Ei * 4 + (((size_t)kmax + 3) & ~(size_t)3) * 4 + Ei + 15) & ~(size_t)15;
+    // fp32: the tail electors' Philox words of a round are computed once for the warp's 32 trials (table.cuh: tailbuf)
+    const int n_tail = E - table_e_quad_end(E);
+    a.tail_words = (sizeof(Real) == 4 && n_tail > 0 && n_tail <= 16 && getenv("CSIM_TABLE_NOTAIL") == nullptr) ? 4 * ((n_tail + 3) / 4) : 0;
+    auto warp_bytes = [&](int tail_words) { return (Ei * 4 + (((size_t)kmax + 3) & ~(size_t)3) * 4 + ((Ei + 15) & ~(size_t)15) + (size_t)tail_words * 32 * 4 + 15) & ~(size_t)15; };
+    {   // the tail buffer must not cost the second resident CTA (2 x 16 warps per SM is what hides the search latency)
+        const size_t fixed = ((cdf_round_stride(E) * sizeof(Real) + 15) & ~(size_t)15) + ((((size_t)b.R * table_rows(E) * sizeof(Real)) + 15) & ~(size_t)15);
+        const size_t half = ((size_t)c->prop.sharedMemPerMultiprocessor - 2 * 1024) / 2;
+        if (a.tail_words && fixed + warp_bytes(0) * CSIM_TABLE_WPC <= half && fixed + warp_bytes(a.tail_words) * CSIM_TABLE_WPC > half) a.tail_words = 0;
+    }
+    a.warp_smem = warp_bytes(a.tail_words);
     const size_t qtab = (((size_t)b.R * table_rows(E) * sizeof(Real)) + 15) & ~(size_t)15;
     const size_t full = (cdf_round_stride(E) * sizeof(Real) + 15) & ~(size_t)15;
     int wpc = CSIM_TABLE_WPC;

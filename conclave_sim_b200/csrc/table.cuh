@@ -106,6 +106,9 @@ struct TableArgs {
                             // super-batches fill whole waves of the persistent grid (a partly filled last wave idles the GPU)
     int stage;              // 1: E x C rows fit in shared memory and are staged per round
     int stage_q;            // 1: the [R][E] run-off first-column table is staged too
+    int tail_words;         // fp32 only, 0 = off: Philox words kept per trial for the tail electors (4 per tail quad, <= 16).  The
+                            // round-major order lets lane i compute the tail quads of trial i for the round ONCE for the whole
+                            // warp (tail_words / 4 Philox calls per round instead of one per trial): see tailbuf in the kernel
     size_t cta_smem;        // staged table + run-off table
     size_t warp_smem;
 };
@@ -170,7 +173,8 @@ __global__ void __launch_bounds__(CSIM_TABLE_WPC * 32, 1024 / (CSIM_TABLE_WPC * 
     unsigned char* base = smem_raw + a.cta_smem + (size_t)wib * a.warp_smem;
     int32_t* tally = (int32_t*)base;            base += sizeof(int32_t) * Ei;
     int32_t* eff = (int32_t*)base;              base += sizeof(int32_t) * ((kmax + 3) & ~3);
-    uint8_t* mark = (uint8_t*)base;
+    uint8_t* mark = (uint8_t*)base;             base += (Ei + 15) & ~15;
+    uint32_t* tailbuf = (uint32_t*)base;                                    // [32 trials][tail_words] (tail_words > 0 only)
 
     __shared__ __align__(8) unsigned long long stage_bar;                   // mbarrier of the staged table
     const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&stage_bar);
@@ -195,7 +199,16 @@ __global__ void __launch_bounds__(CSIM_TABLE_WPC * 32, 1024 / (CSIM_TABLE_WPC * 
     const int eqe = table_e_quad_end(E);
     const int n_qit = eqe >> 7;
     const int q_rows = table_rows(E);                            // pitch of the staged run-off table (slot order)
-    auto for_each_elector = [&](int r, uint64_t t, uint32_t s_lo, uint32_t s_hi, auto&& fn) {
+    const int tw = F64 ? 0 : a.tail_words;
+    // the tail quads of THIS lane's trial for round r -> tailbuf[lane][...]: one call per tail quad for the whole warp
+    auto stage_tail_words = [&](int r, uint64_t my_sim) {
+        for (int j = 0; j < (tw >> 2); ++j) {
+            uint32_t w[4];
+            philox4x32_10((uint32_t)my_sim, (uint32_t)(my_sim >> 32), (uint32_t)r, (uint32_t)((eqe >> 2) + j), a.b.seed_lo, a.b.seed_hi, w);
+            *reinterpret_cast<uint4*>(tailbuf + lane * tw + 4 * j) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    };
+    auto for_each_elector = [&](int r, uint64_t t, uint32_t s_lo, uint32_t s_hi, const uint32_t* tail, auto&& fn) {
         const bool use_tape = F64 && a.b.tape != nullptr;
         const double* tp = use_tape ? a.b.tape + (t * (uint64_t)R + (uint64_t)(r - 1)) * (uint64_t)E : nullptr;
         for (int qi = 0; qi < n_qit; ++qi) {
@@ -220,6 +233,7 @@ __global__ void __launch_bounds__(CSIM_TABLE_WPC * 32, 1024 / (CSIM_TABLE_WPC * 
         for (int e = eqe + lane; e < E; e += 32) {
             Real u;
             if (use_tape) u = (Real)tp[e];
+            else if (!F64 && tail) u = (Real)u24_from_word(tail[e - eqe]);       // staged for the whole warp by stage_tail_words
             else {
                 uint32_t w[4], wb[4] = {0, 0, 0, 0};
                 philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)(e >> 2), a.b.seed_lo, a.b.seed_hi, w);
@@ -268,6 +282,7 @@ __global__ void __launch_bounds__(CSIM_TABLE_WPC * 32, 1024 / (CSIM_TABLE_WPC * 
             }
             __syncthreads();
             if (!__any_sync(CSIM_FULL, alive)) continue;
+            if (tw) { __syncwarp(); if (alive) stage_tail_words(r, a.b.sim_id_begin + my_i); __syncwarp(); }
             for (int ti = 0; ti < tpw; ++ti) {
                 if (!__shfl_sync(CSIM_FULL, alive ? 1 : 0, ti)) continue;
                 const uint64_t sim = a.b.sim_id_begin + i0 + ti;
@@ -275,7 +290,7 @@ __global__ void __launch_bounds__(CSIM_TABLE_WPC * 32, 1024 / (CSIM_TABLE_WPC * 
                 const uint32_t s_lo = (uint32_t)sim, s_hi = (uint32_t)(sim >> 32);
                 for (int c = lane; c < C; c += 32) tally[c] = 0;
                 __syncwarp();
-                for_each_elector(r, t, s_lo, s_hi, [&](int e, Real u, int slot) {
+                for_each_elector(r, t, s_lo, s_hi, tw ? tailbuf + ti * tw : nullptr, [&](int e, Real u, int slot) {
                     // STAGE: the row lives in shared memory (a typed pointer keeps these LDS, not generic loads)
                     int vote;
                     if (STAGE && step0 == 128) vote = upper_bound_row_smem128<Real>(tab_a + (uint32_t)(slot * C) * (uint32_t)sizeof(Real), C, u);
@@ -308,8 +323,61 @@ __global__ void __launch_bounds__(CSIM_TABLE_WPC * 32, 1024 / (CSIM_TABLE_WPC * 
                 __syncwarp();
             }
         }
-        // =============== run-off rounds, per trial =================================================
-        if (k > 0 && r_full < R) {
+        // =============== run-off rounds, k == 2: round-major like the full-field rounds ================
+        // (lane i keeps the run-off pair of trial i; the tail quads of a round are computed once for the whole warp)
+        if (fast2 && r_full < R) {
+            for (int r = r_full + 1; r <= R; ++r) {
+                if (!__any_sync(CSIM_FULL, alive)) break;
+                if (tw) { __syncwarp(); if (alive) stage_tail_words(r, a.b.sim_id_begin + my_i); __syncwarp(); }
+                for (int ti = 0; ti < tpw; ++ti) {
+                    if (!__shfl_sync(CSIM_FULL, alive ? 1 : 0, ti)) continue;
+                    const uint64_t sim = a.b.sim_id_begin + i0 + ti;
+                    const uint64_t t = (uint64_t)set * a.b.n_sims + i0 + ti;
+                    const int e0 = __shfl_sync(CSIM_FULL, ef0, ti), e1 = __shfl_sync(CSIM_FULL, ef1, ti);
+                    int cnt0 = 0;
+                    for_each_elector(r, t, (uint32_t)sim, (uint32_t)(sim >> 32), tw ? tailbuf + ti * tw : nullptr, [&](int e, Real u, int slot) {
+                        const Real q0 = a.stage_q ? q_s[(r - 1) * q_rows + slot] : a.cdfk[(((size_t)set * R + (r - 1)) * E + e) * kmax];
+                        cnt0 += (q0 <= u) ? 0 : 1;                                   // j = #{cdf_j <= u}; vote eff[0] iff cdf_0 > u
+                    });
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) cnt0 += __shfl_xor_sync(CSIM_FULL, cnt0, off);
+                    const int n0 = cnt0, n1 = E - cnt0;
+                    int mx, arg, second;
+                    const bool need_tally = a.out.round_tallies || a.out.final_votes || !(n0 > 0 && n1 > 0);
+                    if (need_tally) {
+                        __syncwarp();
+                        for (int c = lane; c < C; c += 32) tally[c] = 0;
+                        __syncwarp();
+                        if (lane == 0) { tally[e0] = n0; tally[e1] = n1; }
+                        __syncwarp();
+                    }
+                    if (n0 > 0 && n1 > 0) {
+                        const bool first0 = n0 > n1 || (n0 == n1 && e0 < e1);
+                        mx = first0 ? n0 : n1; arg = first0 ? e0 : e1; second = first0 ? e1 : e0;
+                    } else {
+                        // one of the pair got nothing: the second place is the lowest-index zero-tally candidate
+                        uint32_t k1, k2;
+                        warp_top2(tally, C, lane, k1, k2);
+                        mx = (int)(k1 >> 16); arg = 0xFFFF - (int)(k1 & 0xFFFFu); second = 0xFFFF - (int)(k2 & 0xFFFFu);
+                    }
+                    if (a.out.round_tallies)
+                        for (int c = lane; c < C; c += 32)
+                            a.out.round_tallies[(t * (uint64_t)R + (uint64_t)(r - 1)) * (uint64_t)C + c] = tally[c];
+                    const bool won = mx >= need;
+                    if ((won || r == R) && a.out.final_votes)
+                        for (int c = lane; c < C; c += 32) a.out.final_votes[t * (uint64_t)C + c] = tally[c];
+                    if (lane == ti) {
+                        rounds = r;
+                        if (won) { winner = arg; alive = false; }
+                        else if (r == R) { alive = false; }
+                        else { ef0 = arg; ef1 = second; }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        // =============== run-off rounds, generic k: per trial =======================================
+        if (k > 0 && !fast2 && r_full < R) {
             for (int ti = 0; ti < tpw; ++ti) {
                 if (!__shfl_sync(CSIM_FULL, alive ? 1 : 0, ti)) continue;
                 const uint64_t sim = a.b.sim_id_begin + i0 + ti;
@@ -323,7 +391,7 @@ __global__ void __launch_bounds__(CSIM_TABLE_WPC * 32, 1024 / (CSIM_TABLE_WPC * 
                     const Real* tab_g = a.cdf + ((size_t)set * R + (r_full - 1)) * cdf_round_stride(E);
                     for (int c = lane; c < C; c += 32) tally[c] = 0;
                     __syncwarp();
-                    for_each_elector(r_full, t, s_lo, s_hi, [&](int e, Real u, int slot) {
+                    for_each_elector(r_full, t, s_lo, s_hi, nullptr, [&](int e, Real u, int slot) {
                         const int vote = upper_bound_row<Real>(tab_g + (size_t)slot * C, C, step0, u);
                         atomicAdd(&tally[vote < C ? vote : C - 1], 1);
                     });
@@ -335,7 +403,7 @@ __global__ void __launch_bounds__(CSIM_TABLE_WPC * 32, 1024 / (CSIM_TABLE_WPC * 
                     rnd = r;
                     int cnt0 = 0;
                     if (!fast2) { for (int c = lane; c < C; c += 32) tally[c] = 0; __syncwarp(); }
-                    for_each_elector(r, t, s_lo, s_hi, [&](int e, Real u, int slot) {
+                    for_each_elector(r, t, s_lo, s_hi, nullptr, [&](int e, Real u, int slot) {
                         if (fast2) {
                             const Real q0 = a.stage_q ? q_s[(r - 1) * q_rows + slot] : a.cdfk[(((size_t)set * R + (r - 1)) * E + e) * kmax];
                             cnt0 += (q0 <= u) ? 0 : 1;                               // j = #{cdf_j <= u}; vote eff[0] iff cdf_0 > u
