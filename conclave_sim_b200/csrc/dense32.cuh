@@ -2,30 +2,31 @@
 //
 // This is the kernel the roofline is quoted on (SURVEY §8d "canonical dense per-trial
 // formulation").  One warp owns one trial and walks it from round 1 to its end, then takes the
-// next trial (static stride over trials: results never depend on the schedule).  No block-level
-// barrier exists after the roster tables are staged; only __syncwarp.
+// next trial of its CTA's work item (a CTA walks items of ONE parameter set at a time, so the
+// per-set tables below are CTA-shared; results never depend on the schedule).  After the tables
+// of a set are staged there is no block-level barrier; only __syncwarp.
 //
 // Full-field round, for every elector e (candidates are cut into chunks of L, L = 8 up to E = 256):
 //
 //   phase 1   chunk_sum[j] = sum over c in chunk j of  exp(-beta_r |x_e - x_c|) * pw_c
 //             evaluated for NE (= 2) electors of a lane at once, so every candidate operand fetched
-//             from shared memory (a warp-uniform 128-bit load) feeds NE x 4 pair evaluations.  The terms that need no exponential are added per CHUNK:
-//               self vote       = - s_ee  in e's chunk            (model.py:418-424)
-//               stickiness      = + st * s_e,prev  in prev's chunk (model.py:357-367)
-//             and the running prefix over chunks goes to a per-lane column of shared memory.
-//             The terms that are sums of per-candidate constants are not accumulated at all: they are
-//             read from prefix tables when a prefix is probed:
+//             from shared memory (a warp-uniform 128-bit load) feeds NE x 4 pair evaluations; the running
+//             prefix over chunks goes to a per-lane column of shared memory.  Nothing else happens in
+//             this loop — 36 of its 44 instructions are the pair arithmetic and its operand loads.
+//             The terms that need no exponential enter when a prefix is PROBED:
+//               self vote       = - s_ee  from e's chunk on           (model.py:418-424)     one compare + add
+//               stickiness      = + st * s_e,prev  from prev's chunk on (model.py:357-367)   one compare + add
 //               regional bonus  = bonus * #{c <= chunk j : region_c == region_e}   (roster table RBp)
 //               bandwagon       = sum of bw_c over chunks <= j                     (per trial-round BWp)
-//   phase 2   t = u * S; a 5-probe binary search over the prefix column finds the chunk that t falls
-//             into; ONLY that chunk's L candidates are re-evaluated with every term inline, in
-//             roster order, to find the first c with cum > t
+//   phase 2   t = u * S; a bound-free binary search over the prefix column (1 + log2 P probes) finds the
+//             chunk that t falls into; ONLY that chunk's L candidates are re-evaluated with every term
+//             inline, in roster order, to find the first c with cum > t
 //             (== searchsorted(cumsum(p)/sum, u, 'right'), simulate.py:153).
 //   The E mod 128 electors that do not fill a quad per lane are split P lanes per elector (P = 4 at
 //   E = 135), each lane summing every P-th chunk, so the leftover costs ~1/4 of a full pass.
 //
 // Factorised evaluation (template flag FACT, the default whenever beta_r >= 0 and
-// beta_r * half-range(x) <= 40): with x' = x - x_mid,
+// beta_r * half-range(x) <= 26): with x' = x - x_mid,
 //     exp(-beta |x_e - x_c|) = min( e^{-beta x'_e} e^{+beta x'_c} ,  e^{+beta x'_e} e^{-beta x'_c} )
 //                            = A_e * min( BP_c , R_e * BQ_c ) / pw_c     with A = e^{-beta x'}, R = e^{+2 beta x'},
 //                                                                        BP = e^{+beta x'} pw, BQ = e^{-beta x'} pw
@@ -34,6 +35,12 @@
 // per pair.  The factor A_e multiplies the chunk prefix once, when it is probed.  The per-round vectors
 // come from k_round_tables32 (fp64 exp, rounded once).  FACT = false keeps the MUFU.EX2 form (any roster,
 // any beta).
+//
+// Candidate operands of one round ("round table" T, shared memory).  Two operands per candidate: P (BP, or the papabile
+// weight in the MUFU form) and X (BQ, or the ideology).  L = 8: interleaved per chunk, [P0..3 | X0..3 | P4..7 | X4..7],
+// so ONE pointer that advances 64 bytes per chunk serves the four 128-bit loads of a chunk at immediate offsets; generic
+// L: two planes [CP] + [CP].  FACT: the tables of ALL R rounds of the current parameter set are staged once per CTA
+// (R x 2 CP floats: 21.8 KB at E = 135, R = 20) when they fit, else each warp stages the round it plays.
 //
 // Run-off rounds (simulate.py:144-154,183-186) only need the first k columns of the row
 // (P[e, :k] renormalised), so they cost k pair evaluations per elector; with k = 2 the tally is a
@@ -46,12 +53,15 @@ struct Dense32Args {
     BatchDev b;
     TrialOut out;
     const float* nbeta;     // [sets][R]  -beta_r * log2(e)
-    const float* tab;       // [sets][R][4][nch*L]  A, A', BP, BP' (FACT only)
+    const float* tab;       // [sets][R][4][nch*L]  A, 1/A, BP, BQ (FACT only; k_round_tables32)
     int wiring;
     int L;                  // candidates per chunk (multiple of 4)
     int nch;                // number of chunks, nch * L >= C, nch <= 32
     int kmax;
     int warps_per_cta;
+    int tpi;                // trials per warp per work item
+    int cta_tabs;           // 1: the round tables of the whole parameter set are CTA-shared (n_tab rounds); 0: per warp, per round
+    int n_tab;              // rounds staged per set when cta_tabs (FACT: R; MUFU form: 1 — its operands do not depend on the round)
     size_t cta_smem;        // bytes of CTA-shared tables
     size_t warp_smem;       // bytes per warp
     // PROBE instantiation only (csim_engine_probs): one trial is started AT round probe_round from the given previous-round
@@ -72,13 +82,18 @@ struct Dense32Args {
 #define CSIM_MINB 3        // resident CTAs per SM the register allocation is bounded for
 #endif
 #define DENSE32_PREF_COLS (CSIM_NE > 1 ? CSIM_NE : 1)
-__host__ __device__ inline size_t dense32_cta_smem(int nch, int L, int G) {
-    const size_t CP = (size_t)nch * L;
-    return ((CP * 4 /*xs*/ + CP * 4 /*reg*/ + (size_t)nch * G * 4 * 2 /*RBp, regmask*/) + 15) & ~(size_t)15;
+// pitch of the per-region regional-bonus rows (floats): CP + 4 spreads the rows of 8 regions over all banks for the 128-bit loads
+__host__ __device__ inline int dense32_rb_pitch(int CP) { return CP + 4; }
+// byte offsets of the CTA-shared arrays: reg i32[CP] | RBp f32[G][nch] | RBf f32[G][pitch] | round tables f32[n_tab][2 CP]; all 16-byte aligned
+__host__ __device__ inline size_t dense32_o_rbp(int nch, int L) { return (size_t)nch * L * 4; }
+__host__ __device__ inline size_t dense32_o_rbf(int nch, int L, int G) { return dense32_o_rbp(nch, L) + (((size_t)nch * G * 4 + 15) & ~(size_t)15); }
+__host__ __device__ inline size_t dense32_o_tabs(int nch, int L, int G) { return dense32_o_rbf(nch, L, G) + (size_t)G * dense32_rb_pitch(nch * L) * 4; }
+__host__ __device__ inline size_t dense32_cta_smem(int nch, int L, int G, int n_tab_rounds) {
+    return dense32_o_tabs(nch, L, G) + (size_t)n_tab_rounds * 2 * nch * L * 4;
 }
-__host__ __device__ inline size_t dense32_warp_smem(int E, int nch, int L, int kmax, bool model) {
+__host__ __device__ inline size_t dense32_warp_smem(int E, int nch, int L, int kmax, bool model, bool warp_tab) {
     const size_t CP = (size_t)nch * L, Ei = ((size_t)E + 3) & ~(size_t)3, n4 = ((size_t)nch + 3) & ~(size_t)3;
-    size_t n = CP * 4 * 2 /*pw | BP, BQ*/ + (size_t)DENSE32_PREF_COLS * nch * 32 * 4 /*prefix columns*/ + Ei * 4 /*tally*/ +
+    size_t n = (warp_tab ? CP * 4 * 2 : 0) /*own round table*/ + (size_t)DENSE32_PREF_COLS * nch * 32 * 4 /*prefix columns*/ + Ei * 4 /*tally*/ +
                (((size_t)kmax + 3) & ~(size_t)3) * 4 /*eff*/ + Ei /*mark*/;
     if (model) n += CP * 4 /*bw*/ + n4 * 4 /*bwp*/ + Ei * 4 * 2 /*prev_tally, votes*/;
     return (n + 15) & ~(size_t)15;
@@ -114,9 +129,14 @@ static __global__ void k_round_tables32(RosterDev ro, const DevSet* sets, const 
     t[c] = A; t[CP + c] = Ap; t[2 * CP + c] = BP; t[3 * CP + c] = BPp;
 }
 
+// index of candidate c's P operand inside a round table; its X operand sits XOFF floats further
+template <int LC> __device__ __forceinline__ int tab_off(int c) { return LC == 8 ? ((c >> 3) << 4) + ((c & 4) << 1) + (c & 3) : c; }
+
 struct LaneCtx32 {              // per-warp / per-round constants of the draw
-    const float* xs; const int32_t* reg; const float* rbp; const uint32_t* regmask;
-    const float* pw; const float* bq; const float* bw; const float* bwp;   // FACT: pw = BP, bq = BQ;  bwp = prefix of bw over chunks
+    const float* T;             // this round's table (see the header): P = BP | pw, X = BQ | x
+    int xoff;                   // floats from a candidate's P operand to its X operand (4 when L = 8, else CP)
+    const int32_t* reg; const float* rbp; const float* rbf; int rb_pitch;
+    const float* bw; const float* bwp;   // bandwagon per candidate / its prefix over chunks (MODEL)
     float nb, bonus, st1p;
     int C, G, L, nch, step0;
     bool use_bw;
@@ -126,16 +146,21 @@ struct LaneCtx32 {              // per-warp / per-round constants of the draw
 // One elector's scalars.  FACT: score(e,c) = A * min(BP_c, R * BQ_c);  else A = 1 and x is the ideology.
 struct Elector32 { float x, A, Ainv, R; int g, prev; };
 
+// The two point rules of a row as corrections of its chunk prefixes, in m units (score = A * m): the self score leaves from
+// chunk je on (model.py:418-424), stickiness adds from chunk jp on (model.py:357-367).  Applied when a prefix is probed.
+struct Corr32 { float see, sadd; int je, jp; };
+
 // the exponential part of one score in "m" units (score = A * m)
-template <bool FACT>
+template <int LC, bool FACT>
 __device__ __forceinline__ float pair_m32(const LaneCtx32& k, int c, const Elector32& el) {
-    return FACT ? fminf(k.pw[c], el.R * k.bq[c]) : ex2_approx(fabsf(el.x - k.xs[c]) * k.nb) * k.pw[c];
+    const int o = tab_off<LC>(c);
+    return FACT ? fminf(k.T[o], el.R * k.T[o + k.xoff]) : ex2_approx(fabsf(el.x - k.T[o + k.xoff]) * k.nb) * k.T[o];
 }
 
 // every term of one score, inline (run-off rounds and the generic re-scan)
-template <bool MODEL, bool FACT>
+template <int LC, bool MODEL, bool FACT>
 __device__ __forceinline__ float full_score32(const LaneCtx32& k, int e, int c, const Elector32& el) {
-    float v = el.A * pair_m32<FACT>(k, c, el);
+    float v = el.A * pair_m32<LC, FACT>(k, c, el);
     if (k.reg[c] == el.g) v += k.bonus;
     if (MODEL) {
         if (k.use_bw) v += k.bw[c];
@@ -146,64 +171,94 @@ __device__ __forceinline__ float full_score32(const LaneCtx32& k, int e, int c, 
 
 // Phase 1 of one chunk for NE electors of a lane: acc (packed pair of partial sums, m units) += chunk j.
 // The candidate operands are loaded once (warp-uniform 128-bit loads) and reused by all NE electors.
+// LC == 8: tc points at the chunk's 16 interleaved floats; generic L: the chunk's P plane, X plane xoff floats further.
 template <int NE, int LC, bool FACT>
-__device__ __forceinline__ void chunk_acc(const LaneCtx32& k, int j, const float (&xe)[NE], const unsigned long long (&r2)[NE],
+__device__ __forceinline__ void chunk_acc(const LaneCtx32& k, const float* tc, const float (&xe)[NE], const float (&Re)[NE],
                                           unsigned long long (&acc)[NE]) {
-    const int L = LC > 0 ? LC : k.L;
-    if (FACT) {
-        const ulonglong2* b4 = reinterpret_cast<const ulonglong2*>(k.pw) + j * (L >> 2);
-        const ulonglong2* c4 = reinterpret_cast<const ulonglong2*>(k.bq) + j * (L >> 2);
-#pragma unroll 2
-        for (int i = 0; i < (L >> 2); ++i) {
-            const ulonglong2 b = b4[i], c = c4[i];
+    if (LC == 8) {
+        const ulonglong2* t4 = reinterpret_cast<const ulonglong2*>(tc);
+        if (FACT) {
 #pragma unroll
-            for (int t = 0; t < NE; ++t) {
-                unsigned long long t2 = f2_mul(r2[t], c.x);
-                acc[t] = f2_add(acc[t], f2_pack(fminf(f2_lo(b.x), f2_lo(t2)), fminf(f2_hi(b.x), f2_hi(t2))));
-                t2 = f2_mul(r2[t], c.y);
-                acc[t] = f2_add(acc[t], f2_pack(fminf(f2_lo(b.y), f2_lo(t2)), fminf(f2_hi(b.y), f2_hi(t2))));
+            for (int h = 0; h < 2; ++h) {
+                const ulonglong2 b = t4[2 * h], c = t4[2 * h + 1];            // BP, BQ of four candidates
+#pragma unroll
+                for (int t = 0; t < NE; ++t) {
+                    const unsigned long long r2 = f2_pack(Re[t], Re[t]);
+                    unsigned long long t2 = f2_mul(r2, c.x);
+                    acc[t] = f2_add(acc[t], f2_pack(fminf(f2_lo(b.x), f2_lo(t2)), fminf(f2_hi(b.x), f2_hi(t2))));
+                    t2 = f2_mul(r2, c.y);
+                    acc[t] = f2_add(acc[t], f2_pack(fminf(f2_lo(b.y), f2_lo(t2)), fminf(f2_hi(b.y), f2_hi(t2))));
+                }
+            }
+        } else {
+            const float4* f4 = reinterpret_cast<const float4*>(tc);
+            const float nb = k.nb;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float4 pv = f4[2 * h], xv = f4[2 * h + 1];
+#pragma unroll
+                for (int t = 0; t < NE; ++t) {
+                    float a0 = f2_lo(acc[t]), a1 = f2_hi(acc[t]);
+                    a0 = fmaf(ex2_approx(fabsf(xe[t] - xv.x) * nb), pv.x, a0);
+                    a1 = fmaf(ex2_approx(fabsf(xe[t] - xv.y) * nb), pv.y, a1);
+                    a0 = fmaf(ex2_approx(fabsf(xe[t] - xv.z) * nb), pv.z, a0);
+                    a1 = fmaf(ex2_approx(fabsf(xe[t] - xv.w) * nb), pv.w, a1);
+                    acc[t] = f2_pack(a0, a1);
+                }
             }
         }
     } else {
-        const float4* x4 = reinterpret_cast<const float4*>(k.xs + j * L);
-        const float4* p4 = reinterpret_cast<const float4*>(k.pw + j * L);
+        const int L = k.L;
+        const float4* p4 = reinterpret_cast<const float4*>(tc);
+        const float4* x4 = reinterpret_cast<const float4*>(tc + k.xoff);
         const float nb = k.nb;
 #pragma unroll 2
         for (int i = 0; i < (L >> 2); ++i) {
-            const float4 xv = x4[i], pv = p4[i];
+            const float4 pv = p4[i], xv = x4[i];
 #pragma unroll
             for (int t = 0; t < NE; ++t) {
                 float a0 = f2_lo(acc[t]), a1 = f2_hi(acc[t]);
-                a0 = fmaf(ex2_approx(fabsf(xe[t] - xv.x) * nb), pv.x, a0);
-                a1 = fmaf(ex2_approx(fabsf(xe[t] - xv.y) * nb), pv.y, a1);
-                a0 = fmaf(ex2_approx(fabsf(xe[t] - xv.z) * nb), pv.z, a0);
-                a1 = fmaf(ex2_approx(fabsf(xe[t] - xv.w) * nb), pv.w, a1);
+                if (FACT) {
+                    a0 += fminf(pv.x, Re[t] * xv.x); a1 += fminf(pv.y, Re[t] * xv.y);
+                    a0 += fminf(pv.z, Re[t] * xv.z); a1 += fminf(pv.w, Re[t] * xv.w);
+                } else {
+                    a0 = fmaf(ex2_approx(fabsf(xe[t] - xv.x) * nb), pv.x, a0);
+                    a1 = fmaf(ex2_approx(fabsf(xe[t] - xv.y) * nb), pv.y, a1);
+                    a0 = fmaf(ex2_approx(fabsf(xe[t] - xv.z) * nb), pv.z, a0);
+                    a1 = fmaf(ex2_approx(fabsf(xe[t] - xv.w) * nb), pv.w, a1);
+                }
                 acc[t] = f2_pack(a0, a1);
             }
         }
     }
 }
 
-// Per-elector corrections to the exponential-part prefix, in m units: the self score (removed at e's
-// chunk, model.py:418-424) and stickiness (added at prev's chunk, model.py:357-367).
-template <bool MODEL, bool FACT>
-__device__ __forceinline__ void corrections32(const LaneCtx32& k, int e, const Elector32& el, float& see_m, float& sadd_m, int& jp) {
+// Per-elector corrections to the exponential-part prefix, in m units: the self score (removed from e's
+// chunk on, model.py:418-424) and stickiness (added from prev's chunk on, model.py:357-367).
+template <int LC, bool MODEL, bool FACT>
+__device__ __forceinline__ Corr32 corrections32(const LaneCtx32& k, int e, const Elector32& el) {
+    Corr32 cr;
     float flat = k.bonus;                                  // the self pair is of e's own region
     if (MODEL && k.use_bw) flat += k.bw[e];
-    see_m = pair_m32<FACT>(k, e, el) + flat * el.Ainv;     // same expression as phase 1, so it cancels
-    jp = -1; sadd_m = 0.f;
+    cr.see = pair_m32<LC, FACT>(k, e, el) + flat * el.Ainv;   // same expression as phase 1, so it cancels
+    cr.je = e / k.L;
+    cr.jp = 0x7fffffff; cr.sadd = 0.f;
     if (MODEL && el.prev >= 0 && el.prev != e) {
         float fl = (k.reg[el.prev] == el.g) ? k.bonus : 0.f;
         if (k.use_bw) fl += k.bw[el.prev];
-        sadd_m = (pair_m32<FACT>(k, el.prev, el) + fl * el.Ainv) * (k.st1p - 1.0f);
-        jp = el.prev / k.L;
+        cr.sadd = (pair_m32<LC, FACT>(k, el.prev, el) + fl * el.Ainv) * (k.st1p - 1.0f);
+        cr.jp = el.prev / k.L;
     }
+    return cr;
 }
 
-// prefix of the scores over chunks 0..j:  A * (exponential part) + regional bonus + bandwagon
+// prefix of the scores over chunks 0..j:  A * (exponential part + point rules) + regional bonus + bandwagon
 template <bool MODEL>
-__device__ __forceinline__ float probe32(const LaneCtx32& k, const float* pref, int pstride, const float* rbrow, float A, int j) {
-    float v = fmaf(k.bonus, rbrow[j], A * pref[j * pstride]);
+__device__ __forceinline__ float probe32(const LaneCtx32& k, const float* pref, int pstride, const float* rbrow, float A, const Corr32& cr, int j) {
+    float m = pref[j * pstride];
+    m = j >= cr.je ? m - cr.see : m;
+    if (MODEL) m = j >= cr.jp ? m + cr.sadd : m;
+    float v = fmaf(k.bonus, rbrow[j], A * m);
     if (MODEL && k.use_bw) v += k.bwp[j];
     return v;
 }
@@ -212,39 +267,38 @@ __device__ __forceinline__ float probe32(const LaneCtx32& k, const float* pref, 
 template <bool MODEL, bool FACT>
 __device__ __forceinline__ void rescan8_scores(const LaneCtx32& k, int jstar, int e, const Elector32& el, float (&v)[8]) {
     const int c0 = jstar * 8;
-    // vectorised re-scan.  FACT: (xa, xb) hold BQ, (pa, pb) hold BP;  else x and pw
-    const float* src_x = FACT ? k.bq : k.xs;
-    const float4 xa = *reinterpret_cast<const float4*>(src_x + c0), xb = *reinterpret_cast<const float4*>(src_x + c0 + 4);
-    const float4 pa = *reinterpret_cast<const float4*>(k.pw + c0), pb = *reinterpret_cast<const float4*>(k.pw + c0 + 4);
-    const uint32_t rm = k.regmask[jstar * k.G + el.g];                   // bit i: candidate c0+i is of e's region
-    const uint32_t dm = (jstar == (e >> 3)) ? (1u << (e & 7)) : 0u;      // bit i: candidate c0+i is e itself
-    uint32_t pm = 0;
+    const float4* t4 = reinterpret_cast<const float4*>(k.T + 16 * jstar);
+    const float4 pa = t4[0], xa = t4[1], pb = t4[2], xb = t4[3];           // P = BP | pw, X = BQ | x
+    const float* rbrow = k.rbf + el.g * k.rb_pitch + c0;                   // bonus where candidate c0+i is of e's region, else 0
+    const float4 ra = *reinterpret_cast<const float4*>(rbrow), rb = *reinterpret_cast<const float4*>(rbrow + 4);
     float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
+    const int is = e - c0;                                                 // position of e itself / of prev inside this chunk (else outside 0..7)
+    int ip = -1;
     if (MODEL) {
-        if (el.prev >= 0 && (el.prev >> 3) == jstar) pm = 1u << (el.prev & 7);
+        ip = el.prev - c0;
         if (k.use_bw) { ba = *reinterpret_cast<const float4*>(k.bw + c0); bb = *reinterpret_cast<const float4*>(k.bw + c0 + 4); }
     }
     const float nb = k.nb;
-#define CSIM_RESCAN(i, xv, pv, bv)                                              \
+#define CSIM_RESCAN(i, xv, pv, rv, bv)                                          \
     {                                                                       \
         const float m = FACT ? fminf((pv), el.R * (xv)) : ex2_approx(fabsf(el.x - (xv)) * nb) * (pv); \
-        float s = fmaf(el.A, m, ((rm >> (i)) & 1u) ? k.bonus : 0.0f);       \
-        if (MODEL) { s += (bv); if ((pm >> (i)) & 1u) s *= k.st1p; }        \
-        if ((dm >> (i)) & 1u) s = 0.0f;                                     \
+        float s = fmaf(el.A, m, (rv));                                      \
+        if (MODEL) { s += (bv); if (ip == (i)) s *= k.st1p; }               \
+        if (is == (i)) s = 0.0f;                                            \
         v[i] = s;                                                           \
     }
-    CSIM_RESCAN(0, xa.x, pa.x, ba.x) CSIM_RESCAN(1, xa.y, pa.y, ba.y) CSIM_RESCAN(2, xa.z, pa.z, ba.z) CSIM_RESCAN(3, xa.w, pa.w, ba.w)
-    CSIM_RESCAN(4, xb.x, pb.x, bb.x) CSIM_RESCAN(5, xb.y, pb.y, bb.y) CSIM_RESCAN(6, xb.z, pb.z, bb.z) CSIM_RESCAN(7, xb.w, pb.w, bb.w)
+    CSIM_RESCAN(0, xa.x, pa.x, ra.x, ba.x) CSIM_RESCAN(1, xa.y, pa.y, ra.y, ba.y) CSIM_RESCAN(2, xa.z, pa.z, ra.z, ba.z) CSIM_RESCAN(3, xa.w, pa.w, ra.w, ba.w)
+    CSIM_RESCAN(4, xb.x, pb.x, rb.x, bb.x) CSIM_RESCAN(5, xb.y, pb.y, rb.y, bb.y) CSIM_RESCAN(6, xb.z, pb.z, rb.z, bb.z) CSIM_RESCAN(7, xb.w, pb.w, rb.w, bb.w)
 #undef CSIM_RESCAN
 }
 
 // Phase 2: given the exponential-part prefix over chunks (pref[j * pstride], m units), draw the vote.
 template <int LC, bool MODEL, bool FACT, bool PROBE = false>
-__device__ __forceinline__ int finish_draw(const LaneCtx32& k, const float* pref, int pstride, int e, float u, const Elector32& el) {
+__device__ __forceinline__ int finish_draw(const LaneCtx32& k, const float* pref, int pstride, int e, float u, const Elector32& el, const Corr32& cr) {
     const int C = k.C, L = LC > 0 ? LC : k.L, nch = k.nch;
     const float* rbrow = k.rbp + el.g * nch;
     if (PROBE) {            // csim_engine_probs: the numbers this draw is made from
-        for (int j = 0; j < nch; ++j) k.dbg_prefix[(size_t)e * k.dbg_cap + j] = probe32<MODEL>(k, pref, pstride, rbrow, el.A, j);
+        for (int j = 0; j < nch; ++j) k.dbg_prefix[(size_t)e * k.dbg_cap + j] = probe32<MODEL>(k, pref, pstride, rbrow, el.A, cr, j);
         for (int js = 0; js < nch; ++js) {
             if (LC == 8) {
                 float v[8];
@@ -252,11 +306,11 @@ __device__ __forceinline__ int finish_draw(const LaneCtx32& k, const float* pref
 #pragma unroll
                 for (int i = 0; i < 8; ++i) if (js * 8 + i < C) k.dbg_scores[(size_t)e * C + js * 8 + i] = v[i];
             } else {
-                for (int i = 0; i < L; ++i) if (js * L + i < C) k.dbg_scores[(size_t)e * C + js * L + i] = full_score32<MODEL, FACT>(k, e, js * L + i, el);
+                for (int i = 0; i < L; ++i) if (js * L + i < C) k.dbg_scores[(size_t)e * C + js * L + i] = full_score32<LC, MODEL, FACT>(k, e, js * L + i, el);
             }
         }
     }
-    const float S = probe32<MODEL>(k, pref, pstride, rbrow, el.A, nch - 1);
+    const float S = probe32<MODEL>(k, pref, pstride, rbrow, el.A, cr, nch - 1);
     if (!(S > 0.0f)) {            // all scores vanished: the reference makes the row uniform INCLUDING self (model.py:447-449)
         const int j = (int)(u * (float)C);
         return j < C ? j : C - 1;
@@ -268,11 +322,11 @@ __device__ __forceinline__ int finish_draw(const LaneCtx32& k, const float* pref
     int pos = 0;
     float below = 0.0f;
     if (nch > k.step0) {
-        const float f = probe32<MODEL>(k, pref, pstride, rbrow, el.A, nch - k.step0 - 1);
+        const float f = probe32<MODEL>(k, pref, pstride, rbrow, el.A, cr, nch - k.step0 - 1);
         if (f <= tgt) { pos = nch - k.step0; below = f; }
     }
     for (int step = k.step0 >> 1; step > 0; step >>= 1) {
-        const float f = probe32<MODEL>(k, pref, pstride, rbrow, el.A, pos + step - 1);
+        const float f = probe32<MODEL>(k, pref, pstride, rbrow, el.A, cr, pos + step - 1);
         if (f <= tgt) { pos += step; below = f; }
     }
     const int jstar = pos;
@@ -287,7 +341,7 @@ __device__ __forceinline__ int finish_draw(const LaneCtx32& k, const float* pref
     } else {
         for (int i = 0; i < L; ++i) {
             const int c = c0 + i;
-            const float v = c < C ? full_score32<MODEL, FACT>(k, e, c, el) : 0.0f;
+            const float v = c < C ? full_score32<LC, MODEL, FACT>(k, e, c, el) : 0.0f;
             cum += v;
             cnt += (cum <= tgt) ? 1 : 0;
         }
@@ -297,6 +351,20 @@ __device__ __forceinline__ int finish_draw(const LaneCtx32& k, const float* pref
     vote = vote > maxc ? maxc : vote;                    // rounding at the chunk's upper edge
     if (vote == e) vote = e > 0 ? e - 1 : (C > 1 ? 1 : 0);
     return vote;
+}
+
+// One round's table from its source into shared memory, by `nthr` threads of which this is number `tid`:
+// FACT: src = the round's [4][CP] block of Dense32Args::tab (planes 2, 3 = BP, BQ);  MUFU form: P = papabile weight, X = ideology.
+template <int LC, bool FACT>
+__device__ __forceinline__ void stage_round_table(float* dst, const Dense32Args& a, const float* src, float pwf, int CP, int C, int tid, int nthr) {
+    const int xoff = LC == 8 ? 4 : CP;
+    for (int c = tid; c < CP; c += nthr) {
+        float P, X;
+        if (FACT) { P = __ldg(src + 2 * CP + c); X = __ldg(src + 3 * CP + c); }
+        else { P = c < C ? (a.ro.pap[c] ? pwf : 1.0f) : 0.0f; X = c < C ? a.ro.x32[c] : 0.0f; }
+        const int o = tab_off<LC>(c);
+        dst[o] = P; dst[o + xoff] = X;
+    }
 }
 
 template <int LC, bool MODEL, bool FACT, bool PROBE = false>
@@ -309,29 +377,25 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
     const int nch = a.nch;
     const int CP = nch * L;
     const int Ei = (E + 3) & ~3;
+    const int wpc = a.warps_per_cta;
+    const int rbpitch = dense32_rb_pitch(CP);
     // ---- CTA-shared roster tables ------------------------------------------------------------
-    float* xs = (float*)smem_raw;
-    int32_t* reg = (int32_t*)(xs + CP);
-    float* rbp = (float*)(reg + CP);                         // [G][nch]: #{c in chunks 0..j : region_c == g}
-    uint32_t* regmask = (uint32_t*)(rbp + nch * G);          // [nch][G]: bit i <-> candidate j*L+i is of region g
-    for (int c = threadIdx.x; c < CP; c += blockDim.x) {
-        xs[c] = c < C ? a.ro.x32[c] : 0.0f;
-        reg[c] = c < C ? a.ro.region[c] : -1;
-    }
+    int32_t* reg = (int32_t*)smem_raw;
+    float* rbp = (float*)(smem_raw + dense32_o_rbp(nch, L));           // [G][nch]: #{c in chunks 0..j : region_c == g}
+    float* rbf = (float*)(smem_raw + dense32_o_rbf(nch, L, G));        // [G][rbpitch]: the current set's bonus where region_c == g, else 0
+    float* tabs = (float*)(smem_raw + dense32_o_tabs(nch, L, G));      // [n_tab][2 CP] round tables of the current set (cta_tabs)
+    for (int c = threadIdx.x; c < CP; c += blockDim.x) reg[c] = c < C ? a.ro.region[c] : -1;
     for (int i = threadIdx.x; i < nch * G; i += blockDim.x) {
         const int j = i / G, g = i - j * G;
-        int n = 0; uint32_t m = 0;
-        for (int c = 0; c < (j + 1) * L && c < C; ++c)
-            if (a.ro.region[c] == g) { ++n; if (c >= j * L && c - j * L < 32) m |= 1u << (c - j * L); }
+        int n = 0;
+        for (int c = 0; c < (j + 1) * L && c < C; ++c) n += a.ro.region[c] == g;
         rbp[g * nch + j] = (float)n;
-        regmask[i] = m;
     }
     // ---- per-warp state ----------------------------------------------------------------------
     unsigned char* base = smem_raw + a.cta_smem + (size_t)wib * a.warp_smem;
     // 16-byte aligned float arrays first (they are read with 128-bit loads), then the int arrays
-    float* pw = (float*)base;                   base += sizeof(float) * CP;      // FACT: BP of the current round
-    float* bq = (float*)base;                   base += sizeof(float) * CP;      // FACT: BQ
-    float* pref = (float*)base;                 base += sizeof(float) * DENSE32_PREF_COLS * nch * 32;   // prefix columns [t][j][lane]
+    float* wtab = (float*)base;                 if (!a.cta_tabs) base += sizeof(float) * 2 * CP;          // own round table (fallback)
+    float* pref = (float*)base;                 base += sizeof(float) * DENSE32_PREF_COLS * nch * 32;   // prefix columns [j][t][lane]
     float* bw = nullptr; float* bwp = nullptr;
     if (MODEL) {
         bw = (float*)base;                      base += sizeof(float) * CP;
@@ -345,11 +409,7 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
     }
     int32_t* eff = (int32_t*)base;              base += sizeof(int32_t) * ((a.kmax + 3) & ~3);
     uint8_t* mark = (uint8_t*)base;
-    __syncthreads();   // the only block barrier: roster tables are read-only from here on
 
-    const uint64_t n_trials = (uint64_t)a.b.n_sets * a.b.n_sims;
-    const uint64_t warp_global = (uint64_t)blockIdx.x * a.warps_per_cta + wib;
-    const uint64_t n_warps = (uint64_t)gridDim.x * a.warps_per_cta;
     const int m_quads = E >> 7;                              // whole Philox quads per lane
     const int n_main = 4 * m_quads;
     const int e_left0 = 128 * m_quads;                       // first elector that does not fill a quad per lane
@@ -360,14 +420,15 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
     const bool top2_ok = C >= 2 && C < 32768;
 
     LaneCtx32 kx;
-    kx.xs = xs; kx.reg = reg; kx.rbp = rbp; kx.regmask = regmask; kx.pw = pw; kx.bq = bq; kx.bw = bw; kx.bwp = bwp;
+    kx.T = tabs; kx.xoff = LC == 8 ? 4 : CP;
+    kx.reg = reg; kx.rbp = rbp; kx.rbf = rbf; kx.rb_pitch = rbpitch; kx.bw = bw; kx.bwp = bwp;
     kx.C = C; kx.G = G; kx.L = L; kx.nch = nch; kx.use_bw = false; kx.nb = 0.f; kx.bonus = 0.f; kx.st1p = 1.f;
     kx.step0 = 1;
     while (kx.step0 * 2 <= nch) kx.step0 *= 2;
     kx.dbg_scores = a.probe_scores; kx.dbg_prefix = a.probe_prefix; kx.dbg_cap = a.probe_cap;
 
     int cur_set = -1;
-    float bw_strength = 0.f;
+    float bw_strength = 0.f, pwf = 1.f;
     int need = 0, k = 0, rr = 0;
     bool has_sticky = false, has_bw = false;
     unsigned long long acc_rounds = 0, acc_trials = 0;
@@ -377,258 +438,268 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
     auto load_elector = [&](int e, bool sticky_live) {
         Elector32 el;
         if (FACT) { el.A = __ldg(tabA + e); el.Ainv = __ldg(tabA + CP + e); el.R = el.Ainv * el.Ainv; el.x = 0.f; }
-        else { el.A = 1.f; el.Ainv = 1.f; el.R = 1.f; el.x = xs[e]; }
+        else { el.A = 1.f; el.Ainv = 1.f; el.R = 1.f; el.x = __ldg(a.ro.x32 + e); }
         el.g = reg[e];
         el.prev = (MODEL && sticky_live) ? votes[e] : -1;
         return el;
     };
 
-    for (uint64_t t = warp_global; t < n_trials; t += n_warps) {
-        const int set = (int)(t / a.b.n_sims);
-        const uint64_t sim = a.b.sim_id_begin + (t % a.b.n_sims);
-        if (set != cur_set) {
-            if (cur_set >= 0 && lane == 0 && a.out.totals) {
+    const uint64_t per_item = (uint64_t)wpc * a.tpi;
+    const uint64_t items_per_set = (a.b.n_sims + per_item - 1) / per_item;
+    const uint64_t n_items = items_per_set * a.b.n_sets;
+
+    for (uint64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int set = (int)(it / items_per_set);
+        const uint64_t i0 = (it % items_per_set) * per_item;
+        if (set != cur_set) {                                   // uniform over the CTA: every warp walks the same items
+            if (cur_set >= 0 && lane == 0 && a.out.totals && acc_trials) {
                 atomicAdd(&a.out.totals[2 * cur_set], acc_rounds); atomicAdd(&a.out.totals[2 * cur_set + 1], acc_trials);
             }
             acc_rounds = acc_trials = 0;
             cur_set = set;
             const DevSet* S = &a.b.sets[set];
-            kx.bonus = S->f_bonus; kx.st1p = S->f_st1p; bw_strength = S->f_bandwagon;
+            kx.bonus = S->f_bonus; kx.st1p = S->f_st1p; bw_strength = S->f_bandwagon; pwf = S->f_pwf;
             need = S->need; k = S->k; rr = S->rr;
             has_sticky = MODEL && S->has_sticky; has_bw = MODEL && S->has_bw;
-            const float pwf = S->f_pwf;
-            __syncwarp();
-            if (!FACT) for (int c = lane; c < CP; c += 32) pw[c] = c < C ? (a.ro.pap[c] ? pwf : 1.0f) : 0.0f;
+            __syncthreads();                                    // readers of the previous set's tables are done
+            for (int i = threadIdx.x; i < G * rbpitch; i += blockDim.x) {
+                const int g = i / rbpitch, c = i - g * rbpitch;
+                rbf[i] = (c < C && a.ro.region[c] == g) ? kx.bonus : 0.0f;
+            }
+            if (a.cta_tabs)
+                for (int rt = 0; rt < a.n_tab; ++rt)
+                    stage_round_table<LC, FACT>(tabs + (size_t)rt * 2 * CP, a, FACT ? a.tab + ((size_t)set * R + rt) * 4 * CP : nullptr, pwf, CP, C,
+                                                threadIdx.x, blockDim.x);
             if (MODEL) for (int c = lane; c < CP; c += 32) bw[c] = 0.0f;
-            __syncwarp();
+            __syncthreads();
         }
         const float* nbeta = a.nbeta + (size_t)set * R;
-        const uint32_t s_lo = (uint32_t)sim, s_hi = (uint32_t)(sim >> 32);
-        const bool fast2 = (k == 2) && top2_ok;                  // two-candidate run-off: O(1) closing
-        bool have_eff = false, have_prev = false;
-        int winner = -1, rounds = 0, reason = CSIM_REASON_MAX_ROUNDS;
-        int ef0 = 0, ef1 = 0;                                    // run-off pair when fast2
-        if (R == 0) { for (int c = lane; c < C; c += 32) tally[c] = 0; __syncwarp(); }
-        if (PROBE && MODEL && (a.probe_prev_vote || a.probe_prev_count)) {      // start from the given previous-round state
-            for (int c = lane; c < C; c += 32) {
-                prev_tally[c] = a.probe_prev_count ? a.probe_prev_count[c] : 0;
-                votes[c] = a.probe_prev_vote ? a.probe_prev_vote[c] : -1;
-            }
-            have_prev = true;
-            __syncwarp();
-        }
-
-        for (int r = PROBE ? a.probe_round : 1; r <= R; ++r) {
-            rounds = r;
-            kx.nb = __ldg(&nbeta[r - 1]);
-            kx.use_bw = false;
-            if (FACT) {                                          // stage this round's BP / BQ (trial-invariant vectors)
-                tabA = a.tab + ((size_t)set * R + (r - 1)) * 4 * CP;
+        for (int ti = 0; ti < a.tpi; ++ti) {
+            const uint64_t i = i0 + (uint64_t)ti * wpc + wib;
+            if (i >= a.b.n_sims) break;
+            const uint64_t t = (uint64_t)set * a.b.n_sims + i;
+            const uint64_t sim = a.b.sim_id_begin + i;
+            const uint32_t s_lo = (uint32_t)sim, s_hi = (uint32_t)(sim >> 32);
+            const bool fast2 = (k == 2) && top2_ok;                  // two-candidate run-off: O(1) closing
+            bool have_eff = false, have_prev = false;
+            int winner = -1, rounds = 0, reason = CSIM_REASON_MAX_ROUNDS;
+            int ef0 = 0, ef1 = 0;                                    // run-off pair when fast2
+            if (R == 0) { for (int c = lane; c < C; c += 32) tally[c] = 0; __syncwarp(); }
+            if (PROBE && MODEL && (a.probe_prev_vote || a.probe_prev_count)) {      // start from the given previous-round state
+                for (int c = lane; c < C; c += 32) {
+                    prev_tally[c] = a.probe_prev_count ? a.probe_prev_count[c] : 0;
+                    votes[c] = a.probe_prev_vote ? a.probe_prev_vote[c] : -1;
+                }
+                have_prev = true;
                 __syncwarp();
-                for (int c = lane; c < CP; c += 32) { pw[c] = __ldg(tabA + 2 * CP + c); bq[c] = __ldg(tabA + 3 * CP + c); }
             }
-            if (MODEL) {
-                if (has_bw && have_prev) {                                   // model.py:326-354
-                    int mx, arg;
-                    warp_argmax_first(prev_tally, C, lane, mx, arg);
-                    if (mx > 0) {
-                        kx.use_bw = true;
-                        const float inv = 1.0f / (float)mx;
-                        for (int c = lane; c < C; c += 32) bw[c] = (float)prev_tally[c] * inv * bw_strength;
-                        __syncwarp();
-                        float s = 0.f;                                       // bandwagon of chunk `lane`, then prefix over chunks
-                        if (lane < nch) for (int c = lane * L; c < (lane + 1) * L; ++c) s += bw[c];
+
+            for (int r = PROBE ? a.probe_round : 1; r <= R; ++r) {
+                rounds = r;
+                kx.nb = __ldg(&nbeta[r - 1]);
+                kx.use_bw = false;
+                if (FACT) tabA = a.tab + ((size_t)set * R + (r - 1)) * 4 * CP;
+                if (a.cta_tabs) {
+                    kx.T = tabs + (size_t)(FACT ? r - 1 : 0) * 2 * CP;
+                } else {                                             // stage this round's table (trial-invariant vectors) for this warp
+                    __syncwarp();
+                    stage_round_table<LC, FACT>(wtab, a, tabA, pwf, CP, C, lane, 32);
+                    kx.T = wtab;
+                }
+                if (MODEL) {
+                    if (has_bw && have_prev) {                                   // model.py:326-354
+                        int mx, arg;
+                        warp_argmax_first(prev_tally, C, lane, mx, arg);
+                        if (mx > 0) {
+                            kx.use_bw = true;
+                            const float inv = 1.0f / (float)mx;
+                            for (int c = lane; c < C; c += 32) bw[c] = (float)prev_tally[c] * inv * bw_strength;
+                            __syncwarp();
+                            float s = 0.f;                                       // bandwagon of chunk `lane`, then prefix over chunks
+                            if (lane < nch) for (int c = lane * L; c < (lane + 1) * L; ++c) s += bw[c];
 #pragma unroll
-                        for (int off = 1; off < 32; off <<= 1) {
-                            const float o = __shfl_up_sync(CSIM_FULL, s, off);
-                            if (lane >= off) s += o;
+                            for (int off = 1; off < 32; off <<= 1) {
+                                const float o = __shfl_up_sync(CSIM_FULL, s, off);
+                                if (lane >= off) s += o;
+                            }
+                            if (lane < nch) bwp[lane] = s;
                         }
-                        if (lane < nch) bwp[lane] = s;
                     }
                 }
-            }
-            for (int c = lane; c < C; c += 32) tally[c] = 0;
-            __syncwarp();
-            const bool sticky_live = have_prev && has_sticky;
+                for (int c = lane; c < C; c += 32) tally[c] = 0;
+                __syncwarp();
+                const bool sticky_live = have_prev && has_sticky;
 
-            int cnt0 = 0;                                        // run-off (fast2): this lane's votes for ef0
-            if (!have_eff) {
-                // =============== full-field round: NE electors of a lane at once =====================
-                for (int qi = 0; qi < m_quads; ++qi) {
-                    const int q = lane + 32 * qi;
-                    uint32_t w[4];
-                    philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)q, a.b.seed_lo, a.b.seed_hi, w);
+                int cnt0 = 0;                                        // run-off (fast2): this lane's votes for ef0
+                if (!have_eff) {
+                    // =============== full-field round: NE electors of a lane at once =====================
+                    for (int qi = 0; qi < m_quads; ++qi) {
+                        const int q = lane + 32 * qi;
+                        uint32_t w[4];
+                        philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)q, a.b.seed_lo, a.b.seed_hi, w);
 #pragma unroll 1
-                    for (int g = 0; g < 4 / NE; ++g) {
-                        const int e0 = 4 * q + NE * g;
-                        Elector32 el[NE];
-                        float xe[NE], see[NE], sadd[NE];
-                        int jp[NE];
-                        unsigned long long r2[NE], acc[NE];
-#pragma unroll
-                        for (int i = 0; i < NE; ++i) {
-                            el[i] = load_elector(e0 + i, sticky_live);
-                            corrections32<MODEL, FACT>(kx, e0 + i, el[i], see[i], sadd[i], jp[i]);
-                            xe[i] = el[i].x;
-                            r2[i] = f2_pack(el[i].R, el[i].R);
-                            acc[i] = 0ull;
-                        }
-                        const int je = e0 / L;                   // the electors of a group share their chunk (L % 4 == 0)
-                        float* pc[NE];
-                        float corr[NE];                           // running self-vote / stickiness correction of the prefix
-#pragma unroll
-                        for (int i = 0; i < NE; ++i) { pc[i] = pref + (size_t)i * nch * 32 + lane; corr[i] = 0.f; }
-#pragma unroll 1
-                        for (int j = 0; j < nch; ++j) {
-                            chunk_acc<NE, LC, FACT>(kx, j, xe, r2, acc);
-                            const bool at_self = j == je;
+                        for (int g = 0; g < 4 / NE; ++g) {
+                            const int e0 = 4 * q + NE * g;
+                            Elector32 el[NE];
+                            Corr32 cr[NE];
+                            float xe[NE], Re[NE];
+                            unsigned long long acc[NE];
 #pragma unroll
                             for (int i = 0; i < NE; ++i) {
-                                if (at_self) corr[i] -= see[i];
-                                if (MODEL && j == jp[i]) corr[i] += sadd[i];
-                                *pc[i] = (f2_lo(acc[i]) + f2_hi(acc[i])) + corr[i];     // running prefix, m units
-                                pc[i] += 32;
+                                el[i] = load_elector(e0 + i, sticky_live);
+                                cr[i] = corrections32<LC, MODEL, FACT>(kx, e0 + i, el[i]);
+                                xe[i] = el[i].x; Re[i] = el[i].R;
+                                acc[i] = 0ull;
+                            }
+                            // phase 1: nothing but the pair arithmetic, its operand loads and one prefix store per elector
+                            const float* tc = kx.T;
+                            const int tstep = LC == 8 ? 16 : L;
+                            float* pc = pref + lane;                                    // [j][t][lane]
+#pragma unroll 2
+                            for (int j = 0; j < nch; ++j) {
+                                chunk_acc<NE, LC, FACT>(kx, tc, xe, Re, acc);
+#pragma unroll
+                                for (int i = 0; i < NE; ++i) pc[i * 32] = f2_lo(acc[i]) + f2_hi(acc[i]);   // running prefix, m units
+                                tc += tstep; pc += NE * 32;
+                            }
+#pragma unroll 1
+                            for (int i = 0; i < NE; ++i) {
+                                const int wi = NE * g + i;
+                                const uint32_t wa = wi == 0 ? w[0] : (wi == 1 ? w[1] : (wi == 2 ? w[2] : w[3]));
+                                Elector32 ei = el[0];
+                                Corr32 ci = cr[0];
+#pragma unroll
+                                for (int m = 1; m < NE; ++m) if (i == m) { ei = el[m]; ci = cr[m]; }
+                                const int vote = finish_draw<LC, MODEL, FACT, PROBE>(kx, pref + i * 32 + lane, NE * 32, e0 + i, u24_from_word(wa), ei, ci);
+                                atomicAdd(&tally[vote], 1);
+                                if (MODEL) votes[e0 + i] = vote;   // read only by this lane for its own electors: in-place is safe
                             }
                         }
-#pragma unroll 1
-                        for (int i = 0; i < NE; ++i) {
-                            const int wi = NE * g + i;
-                            const uint32_t wa = wi == 0 ? w[0] : (wi == 1 ? w[1] : (wi == 2 ? w[2] : w[3]));
-                            Elector32 ei = el[0];
-#pragma unroll
-                            for (int m = 1; m < NE; ++m) if (i == m) ei = el[m];
-                            const int vote = finish_draw<LC, MODEL, FACT, PROBE>(kx, pref + (size_t)i * nch * 32 + lane, 32, e0 + i,
-                                                                                 u24_from_word(wa), ei);
+                    }
+                    // =============== leftover electors: P lanes per elector, every P-th chunk each ========
+                    for (int gb = 0; gb < n_left; gb += 32) {
+                        const int n_it = min(32, n_left - gb);
+                        int P = 1;
+                        while (P * 2 * n_it <= 32) P *= 2;
+                        const int eli = lane / P, sub = lane - eli * P;
+                        const bool act = eli < n_it;
+                        const int e = e_left0 + gb + (act ? eli : 0);
+                        uint32_t w[4];
+                        philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)(e >> 2), a.b.seed_lo, a.b.seed_hi, w);
+                        const int sel = e & 3;
+                        const uint32_t wa = sel == 0 ? w[0] : (sel == 1 ? w[1] : (sel == 2 ? w[2] : w[3]));
+                        const Elector32 el = load_elector(e, sticky_live);
+                        const Corr32 cr = corrections32<LC, MODEL, FACT>(kx, e, el);
+                        const float xe1[1] = {el.x}, Re1[1] = {el.R};
+                        const int tstep = LC == 8 ? 16 : L;
+                        float* cl = pref + eli * nch;                // this elector's chunk sums, then prefixes (m units)
+                        __syncwarp();
+                        if (act) {
+                            for (int j = sub; j < nch; j += P) {
+                                unsigned long long acc[1] = {0ull};
+                                chunk_acc<1, LC, FACT>(kx, kx.T + j * tstep, xe1, Re1, acc);
+                                cl[j] = f2_lo(acc[0]) + f2_hi(acc[0]);
+                            }
+                        }
+                        __syncwarp();
+                        if (act && sub == 0) {
+                            float run = 0.f;
+                            for (int j = 0; j < nch; ++j) { run += cl[j]; cl[j] = run; }
+                            const int vote = finish_draw<LC, MODEL, FACT, PROBE>(kx, cl, 1, e, u24_from_word(wa), el, cr);
                             atomicAdd(&tally[vote], 1);
-                            if (MODEL) votes[e0 + i] = vote;   // read only by this lane for its own electors: in-place is safe
+                            if (MODEL) votes[e] = vote;
                         }
+                        __syncwarp();
                     }
-                }
-                // =============== leftover electors: P lanes per elector, every P-th chunk each ========
-                for (int gb = 0; gb < n_left; gb += 32) {
-                    const int n_it = min(32, n_left - gb);
-                    int P = 1;
-                    while (P * 2 * n_it <= 32) P *= 2;
-                    const int eli = lane / P, sub = lane - eli * P;
-                    const bool act = eli < n_it;
-                    const int e = e_left0 + gb + (act ? eli : 0);
-                    uint32_t w[4];
-                    philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)(e >> 2), a.b.seed_lo, a.b.seed_hi, w);
-                    const int sel = e & 3;
-                    const uint32_t wa = sel == 0 ? w[0] : (sel == 1 ? w[1] : (sel == 2 ? w[2] : w[3]));
-                    const Elector32 el = load_elector(e, sticky_live);
-                    float see, sadd; int jp;
-                    corrections32<MODEL, FACT>(kx, e, el, see, sadd, jp);
-                    const float xe1[1] = {el.x};
-                    const unsigned long long r2[1] = {f2_pack(el.R, el.R)};
-                    const int je = e / L;
-                    float* cl = pref + eli * nch;                // this elector's chunk sums, then prefixes (m units)
-                    __syncwarp();
-                    if (act) {
-                        for (int j = sub; j < nch; j += P) {
-                            unsigned long long acc[1] = {f2_pack((j == je) ? -see : 0.f, (MODEL && j == jp) ? sadd : 0.f)};
-                            chunk_acc<1, LC, FACT>(kx, j, xe1, r2, acc);
-                            cl[j] = f2_lo(acc[0]) + f2_hi(acc[0]);
+                } else {
+                    // =============== run-off round: one elector per slot, first k columns ==================
+                    uint32_t w[4] = {0, 0, 0, 0};
+                    for (int n = 0; n < n_slots; ++n) {
+                        int e, q; bool gen;
+                        if (n < n_main) { q = lane + 32 * (n >> 2); e = 4 * q + (n & 3); gen = (n & 3) == 0; }
+                        else { e = e_single0 + 32 * (n - n_main); q = e >> 2; gen = true; }
+                        if (gen) philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)q, a.b.seed_lo, a.b.seed_hi, w);
+                        const int sel = e & 3;
+                        const uint32_t wa = sel == 0 ? w[0] : (sel == 1 ? w[1] : (sel == 2 ? w[2] : w[3]));
+                        const float u = u24_from_word(wa);
+                        const Elector32 el = load_elector(e, sticky_live);
+                        int vote;
+                        if (fast2) {
+                            // two-candidate run-off: columns 0 and 1, renormalised (simulate.py:144-154)
+                            const float v0 = full_score32<LC, MODEL, FACT>(kx, e, 0, el);
+                            const float v1 = full_score32<LC, MODEL, FACT>(kx, e, 1, el);
+                            const float sum = v0 + v1;
+                            int j;
+                            if (!(sum > 0.0f)) j = (u * 2.0f >= 1.0f) ? 1 : 0;       // simulate.py:151 uniform fallback
+                            else j = (v0 > u * sum || !(v1 > 0.0f)) ? 0 : 1;
+                            cnt0 += (j == 0);
+                            vote = j == 0 ? ef0 : ef1;
+                        } else {
+                            float sum = 0.f;
+                            for (int j = 0; j < k; ++j) sum += full_score32<LC, MODEL, FACT>(kx, e, j, el);
+                            int jsel;
+                            if (!(sum > 0.0f)) {
+                                jsel = (int)(u * (float)k);
+                            } else {
+                                const float tgt = u * sum;
+                                float cum = 0.f; jsel = -1; int lastpos = 0;
+                                for (int j = 0; j < k; ++j) {
+                                    const float v = full_score32<LC, MODEL, FACT>(kx, e, j, el);
+                                    cum += v;
+                                    if (v > 0.0f) lastpos = j;
+                                    if (jsel < 0 && v > 0.0f && cum > tgt) jsel = j;
+                                }
+                                if (jsel < 0) jsel = lastpos;
+                            }
+                            if (jsel >= k) jsel = k - 1;
+                            vote = eff[jsel];
+                            atomicAdd(&tally[vote], 1);
                         }
-                    }
-                    __syncwarp();
-                    if (act && sub == 0) {
-                        float run = 0.f;
-                        for (int j = 0; j < nch; ++j) { run += cl[j]; cl[j] = run; }
-                        const int vote = finish_draw<LC, MODEL, FACT, PROBE>(kx, cl, 1, e, u24_from_word(wa), el);
-                        atomicAdd(&tally[vote], 1);
                         if (MODEL) votes[e] = vote;
                     }
-                    __syncwarp();
                 }
-            } else {
-                // =============== run-off round: one elector per slot, first k columns ==================
-                uint32_t w[4] = {0, 0, 0, 0};
-                for (int n = 0; n < n_slots; ++n) {
-                    int e, q; bool gen;
-                    if (n < n_main) { q = lane + 32 * (n >> 2); e = 4 * q + (n & 3); gen = (n & 3) == 0; }
-                    else { e = e_single0 + 32 * (n - n_main); q = e >> 2; gen = true; }
-                    if (gen) philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)q, a.b.seed_lo, a.b.seed_hi, w);
-                    const int sel = e & 3;
-                    const uint32_t wa = sel == 0 ? w[0] : (sel == 1 ? w[1] : (sel == 2 ? w[2] : w[3]));
-                    const float u = u24_from_word(wa);
-                    const Elector32 el = load_elector(e, sticky_live);
-                    int vote;
-                    if (fast2) {
-                        // two-candidate run-off: columns 0 and 1, renormalised (simulate.py:144-154)
-                        const float v0 = full_score32<MODEL, FACT>(kx, e, 0, el);
-                        const float v1 = full_score32<MODEL, FACT>(kx, e, 1, el);
-                        const float sum = v0 + v1;
-                        int j;
-                        if (!(sum > 0.0f)) j = (u * 2.0f >= 1.0f) ? 1 : 0;       // simulate.py:151 uniform fallback
-                        else j = (v0 > u * sum || !(v1 > 0.0f)) ? 0 : 1;
-                        cnt0 += (j == 0);
-                        vote = j == 0 ? ef0 : ef1;
-                    } else {
-                        float sum = 0.f;
-                        for (int j = 0; j < k; ++j) sum += full_score32<MODEL, FACT>(kx, e, j, el);
-                        int jsel;
-                        if (!(sum > 0.0f)) {
-                            jsel = (int)(u * (float)k);
-                        } else {
-                            const float tgt = u * sum;
-                            float cum = 0.f; jsel = -1; int lastpos = 0;
-                            for (int j = 0; j < k; ++j) {
-                                const float v = full_score32<MODEL, FACT>(kx, e, j, el);
-                                cum += v;
-                                if (v > 0.0f) lastpos = j;
-                                if (jsel < 0 && v > 0.0f && cum > tgt) jsel = j;
-                            }
-                            if (jsel < 0) jsel = lastpos;
-                        }
-                        if (jsel >= k) jsel = k - 1;
-                        vote = eff[jsel];
-                        atomicAdd(&tally[vote], 1);
-                    }
-                    if (MODEL) votes[e] = vote;
-                }
-            }
-            int n0 = 0, n1 = 0;
-            if (have_eff && fast2) {
+                int n0 = 0, n1 = 0;
+                if (have_eff && fast2) {
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) cnt0 += __shfl_xor_sync(CSIM_FULL, cnt0, off);
-                n0 = cnt0; n1 = E - cnt0;
-                if (lane == 0) { tally[ef0] = n0; tally[ef1] = n1; }
-            }
-            __syncwarp();
-            if (PROBE) break;                                    // one round is all a probe plays
-            // ---------------- close the round -----------------------------------------------------
-            if (a.out.round_tallies)
-                for (int c = lane; c < C; c += 32)
-                    a.out.round_tallies[(t * (uint64_t)R + (uint64_t)(r - 1)) * (uint64_t)C + c] = tally[c];
-            if (MODEL) for (int c = lane; c < C; c += 32) prev_tally[c] = tally[c];
-            have_prev = true;
-            if (fast2) {
-                int mx, arg, second;
-                if (have_eff && n0 > 0 && n1 > 0) {
-                    const bool first0 = n0 > n1 || (n0 == n1 && ef0 < ef1);
-                    mx = first0 ? n0 : n1; arg = first0 ? ef0 : ef1; second = first0 ? ef1 : ef0;
-                } else {
-                    uint32_t k1, k2;
-                    warp_top2(tally, C, lane, k1, k2);
-                    mx = (int)(k1 >> 16); arg = 0xFFFF - (int)(k1 & 0xFFFFu); second = 0xFFFF - (int)(k2 & 0xFFFFu);
+                    for (int off = 16; off > 0; off >>= 1) cnt0 += __shfl_xor_sync(CSIM_FULL, cnt0, off);
+                    n0 = cnt0; n1 = E - cnt0;
+                    if (lane == 0) { tally[ef0] = n0; tally[ef1] = n1; }
                 }
-                if (mx >= need) { winner = arg; reason = CSIM_REASON_WINNER; break; }        // simulate.py:174-180
-                if (r >= rr) { ef0 = arg; ef1 = second; have_eff = true; }                   // simulate.py:183-186
-            } else {
-                int mx, arg;
-                warp_argmax_first(tally, C, lane, mx, arg);
-                if (mx >= need) { winner = arg; reason = CSIM_REASON_WINNER; break; }
-                if (r >= rr && k > 0) { warp_top_k(tally, C, k, lane, eff, mark); have_eff = true; }
+                __syncwarp();
+                if (PROBE) break;                                    // one round is all a probe plays
+                // ---------------- close the round -----------------------------------------------------
+                if (a.out.round_tallies)
+                    for (int c = lane; c < C; c += 32)
+                        a.out.round_tallies[(t * (uint64_t)R + (uint64_t)(r - 1)) * (uint64_t)C + c] = tally[c];
+                if (MODEL) for (int c = lane; c < C; c += 32) prev_tally[c] = tally[c];
+                have_prev = true;
+                if (fast2) {
+                    int mx, arg, second;
+                    if (have_eff && n0 > 0 && n1 > 0) {
+                        const bool first0 = n0 > n1 || (n0 == n1 && ef0 < ef1);
+                        mx = first0 ? n0 : n1; arg = first0 ? ef0 : ef1; second = first0 ? ef1 : ef0;
+                    } else {
+                        uint32_t k1, k2;
+                        warp_top2(tally, C, lane, k1, k2);
+                        mx = (int)(k1 >> 16); arg = 0xFFFF - (int)(k1 & 0xFFFFu); second = 0xFFFF - (int)(k2 & 0xFFFFu);
+                    }
+                    if (mx >= need) { winner = arg; reason = CSIM_REASON_WINNER; break; }        // simulate.py:174-180
+                    if (r >= rr) { ef0 = arg; ef1 = second; have_eff = true; }                   // simulate.py:183-186
+                } else {
+                    int mx, arg;
+                    warp_argmax_first(tally, C, lane, mx, arg);
+                    if (mx >= need) { winner = arg; reason = CSIM_REASON_WINNER; break; }
+                    if (r >= rr && k > 0) { warp_top_k(tally, C, k, lane, eff, mark); have_eff = true; }
+                }
+                __syncwarp();
             }
+            // ---------------- trial outputs -----------------------------------------------------------
+            write_trial_outputs(a.out, t, set, C, R, lane, tally, winner, rounds, reason);
+            acc_rounds += (unsigned long long)rounds; acc_trials += 1;
             __syncwarp();
         }
-        // ---------------- trial outputs -----------------------------------------------------------
-        write_trial_outputs(a.out, t, set, C, R, lane, tally, winner, rounds, reason);
-        acc_rounds += (unsigned long long)rounds; acc_trials += 1;
-        __syncwarp();
     }
-    if (cur_set >= 0 && lane == 0 && a.out.totals) {
+    if (cur_set >= 0 && lane == 0 && a.out.totals && acc_trials) {
         atomicAdd(&a.out.totals[2 * cur_set], acc_rounds); atomicAdd(&a.out.totals[2 * cur_set + 1], acc_trials);
     }
 }

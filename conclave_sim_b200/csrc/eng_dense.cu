@@ -4,16 +4,37 @@
 
 template <int LC, bool MODEL, bool FACT>
 static csim_status launch_dense32_t(csim_ctx* c, Dense32Args& a, cudaStream_t st) {
-    a.cta_smem = dense32_cta_smem(a.nch, a.L, a.ro.G);
-    a.warp_smem = dense32_warp_smem(a.ro.E, a.nch, a.L, a.kmax, MODEL);
-    int wpc = 8;
+    const int E = a.ro.E, G = a.ro.G, R = a.b.R;
+    // Where the round tables live.  FACT: the tables of all R rounds of a set CTA-shared (staged once per set) when that leaves
+    // at least as many warps per CTA as per-warp tables would (a warp then stages the round it plays, as in round 1 of this
+    // repo); the MUFU form has ONE table per set (ideology, papabile weight) and always shares it.
     const size_t budget = (size_t)(220 * 1024) / CSIM_MINB;                        // CSIM_MINB CTAs per SM
-    while (wpc > 1 && a.cta_smem + a.warp_smem * wpc > budget) --wpc;
-    if (a.cta_smem + a.warp_smem * wpc > 220 * 1024)
-        return fail(CSIM_ERR_UNSUPPORTED, "roster of %d electors / %d regions needs %zu B of shared memory", a.ro.E, a.ro.G, a.cta_smem + a.warp_smem);
+    auto fit = [&](size_t cta, size_t warp) { int w = 8; while (w > 0 && cta + warp * w > budget) --w; return w; };
+    const int n_tab_shared = FACT ? R : 1;                                        // (R == 0: no round is ever played, nothing to stage)
+    const size_t ctaA = dense32_cta_smem(a.nch, a.L, G, n_tab_shared), warpA = dense32_warp_smem(E, a.nch, a.L, a.kmax, MODEL, false);
+    const size_t ctaB = dense32_cta_smem(a.nch, a.L, G, 0), warpB = dense32_warp_smem(E, a.nch, a.L, a.kmax, MODEL, true);
+    const int wA = fit(ctaA, warpA), wB = FACT ? fit(ctaB, warpB) : 0;
+    const bool shared_tabs = getenv("CSIM_DENSE_WARPTAB") == nullptr ? (wA >= wB && wA > 0) : !(FACT && wB > 0);
+    a.cta_tabs = shared_tabs ? 1 : 0;
+    a.n_tab = shared_tabs ? n_tab_shared : 0;
+    a.cta_smem = shared_tabs ? ctaA : ctaB;
+    a.warp_smem = shared_tabs ? warpA : warpB;
+    int wpc = shared_tabs ? wA : wB;
+    if (wpc < 1) {                                                               // not at CSIM_MINB CTAs per SM: one CTA, as many warps as fit
+        wpc = 8;
+        while (wpc > 1 && a.cta_smem + a.warp_smem * wpc > 220 * 1024) --wpc;
+        if (a.cta_smem + a.warp_smem * wpc > 220 * 1024) {
+            if (shared_tabs && FACT) {                                           // the shared tables themselves are too large: per-warp tables
+                a.cta_tabs = 0; a.n_tab = 0; a.cta_smem = ctaB; a.warp_smem = warpB;
+                wpc = 8;
+                while (wpc > 1 && a.cta_smem + a.warp_smem * wpc > 220 * 1024) --wpc;
+            }
+            if (a.cta_smem + a.warp_smem * wpc > 220 * 1024)
+                return fail(CSIM_ERR_UNSUPPORTED, "roster of %d electors / %d regions needs %zu B of shared memory", E, G, a.cta_smem + a.warp_smem);
+        }
+    }
     a.warps_per_cta = wpc;
     const size_t smem = a.cta_smem + a.warp_smem * wpc;
-    int grid = 1;
     void (*kern)(Dense32Args) = k_trials_dense32<LC, MODEL, FACT, false>;
     if (c->probe) {
         kern = k_trials_dense32<LC, MODEL, FACT, true>;
@@ -21,16 +42,27 @@ static csim_status launch_dense32_t(csim_ctx* c, Dense32Args& a, cudaStream_t st
         a.probe_scores = c->probe->scores; a.probe_prefix = c->probe->prefix; a.probe_cap = c->probe->cap;
         c->probe->nch = a.nch; c->probe->chunk = a.L;
     }
-    csim_status s = persistent_grid(c, kern, wpc * 32, smem, (uint64_t)a.b.n_sets * a.b.n_sims, wpc, &grid);
-    if (s != CSIM_OK) return s;
-    if (FACT && a.b.R > 0) {
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpc * 32, smem));
+    if (per_sm < 1) return fail(CSIM_ERR_UNSUPPORTED, "dense kernel does not fit on an SM (threads=%d, smem=%zu)", wpc * 32, smem);
+    const uint64_t ctas = (uint64_t)c->prop.multiProcessorCount * per_sm;      // persistent: a multiple of the SM count
+    // work item = warps_per_cta x tpi trials of one set; ~8 items per CTA keeps the tail short while a CTA that stays inside one
+    // parameter set never re-stages its tables
+    uint64_t tpi = a.b.n_sims / ((uint64_t)wpc * ctas * 8);
+    tpi = std::max<uint64_t>(1, std::min<uint64_t>(tpi, 64));
+    a.tpi = (int)tpi;
+    const uint64_t per_item = (uint64_t)wpc * tpi;
+    const uint64_t n_items = ((a.b.n_sims + per_item - 1) / per_item) * a.b.n_sets;
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_items, ctas));
+    if (FACT && R > 0) {
         const int CP = a.nch * a.L;
-        const size_t tb = sizeof(float) * (size_t)a.b.n_sets * a.b.R * 4 * CP;
+        const size_t tb = sizeof(float) * (size_t)a.b.n_sets * R * 4 * CP;
         CU_TRY(c->tab.reserve(tb));
         a.tab = (const float*)c->tab.p;
-        for (int sr0 = 0; sr0 < a.b.n_sets * a.b.R; sr0 += CSIM_GRID_TILE) {
-            dim3 g((CP + 127) / 128, std::min(CSIM_GRID_TILE, a.b.n_sets * a.b.R - sr0));
-            k_round_tables32<<<g, 128, 0, st>>>(a.ro, a.b.sets, (const double*)c->betas.p, a.b.R, CP, c->x_mid, (float*)c->tab.p, sr0);
+        for (int sr0 = 0; sr0 < a.b.n_sets * R; sr0 += CSIM_GRID_TILE) {
+            dim3 g((CP + 127) / 128, std::min(CSIM_GRID_TILE, a.b.n_sets * R - sr0));
+            k_round_tables32<<<g, 128, 0, st>>>(a.ro, a.b.sets, (const double*)c->betas.p, R, CP, c->x_mid, (float*)c->tab.p, sr0);
             ++c->launches;
         }
     }
