@@ -81,6 +81,9 @@ struct Dense32Args {
 #ifndef CSIM_MINB
 #define CSIM_MINB 3        // resident CTAs per SM the register allocation is bounded for
 #endif
+#ifndef CSIM_DENSE_PIPELINE
+#define CSIM_DENSE_PIPELINE 1   // software-pipeline the operand loads of the pair loop (L = 8, factorised form)
+#endif
 #define DENSE32_PREF_COLS (CSIM_NE > 1 ? CSIM_NE : 1)
 // pitch of the per-region regional-bonus rows (floats): CP + 4 spreads the rows of 8 regions over all banks for the 128-bit loads
 __host__ __device__ inline int dense32_rb_pitch(int CP) { return CP + 4; }
@@ -230,6 +233,25 @@ __device__ __forceinline__ void chunk_acc(const LaneCtx32& k, const float* tc, c
                 acc[t] = f2_pack(a0, a1);
             }
         }
+    }
+}
+
+// The factorised pair arithmetic of one chunk of 8 candidates on operands already in registers (b = BP, c = BQ of candidates
+// 0-3 and 4-7): the software-pipelined form of the loop loads the NEXT chunk's operands while this one is evaluated.
+template <int NE>
+__device__ __forceinline__ void chunk_math8(const ulonglong2& b0, const ulonglong2& c0, const ulonglong2& b1, const ulonglong2& c1,
+                                            const float (&Re)[NE], unsigned long long (&acc)[NE]) {
+#pragma unroll
+    for (int t = 0; t < NE; ++t) {
+        const unsigned long long r2 = f2_pack(Re[t], Re[t]);
+        unsigned long long t2 = f2_mul(r2, c0.x);
+        acc[t] = f2_add(acc[t], f2_pack(fminf(f2_lo(b0.x), f2_lo(t2)), fminf(f2_hi(b0.x), f2_hi(t2))));
+        t2 = f2_mul(r2, c0.y);
+        acc[t] = f2_add(acc[t], f2_pack(fminf(f2_lo(b0.y), f2_lo(t2)), fminf(f2_hi(b0.y), f2_hi(t2))));
+        t2 = f2_mul(r2, c1.x);
+        acc[t] = f2_add(acc[t], f2_pack(fminf(f2_lo(b1.x), f2_lo(t2)), fminf(f2_hi(b1.x), f2_hi(t2))));
+        t2 = f2_mul(r2, c1.y);
+        acc[t] = f2_add(acc[t], f2_pack(fminf(f2_lo(b1.y), f2_lo(t2)), fminf(f2_hi(b1.y), f2_hi(t2))));
     }
 }
 
@@ -555,12 +577,29 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                             const float* tc = kx.T;
                             const int tstep = LC == 8 ? 16 : L;
                             float* pc = pref + lane;                                    // [j][t][lane]
+                            if (LC == 8 && FACT && CSIM_DENSE_PIPELINE) {
+                                // software-pipelined: chunk j + 1's operands are in flight while chunk j is evaluated (the load past the
+                                // last chunk reads the next table / the warp's own arrays: inside the allocation, never used)
+                                const ulonglong2* t4 = reinterpret_cast<const ulonglong2*>(tc);
+                                ulonglong2 nb0 = t4[0], nc0 = t4[1], nb1 = t4[2], nc1 = t4[3];
 #pragma unroll 2
-                            for (int j = 0; j < nch; ++j) {
-                                chunk_acc<NE, LC, FACT>(kx, tc, xe, Re, acc);
+                                for (int j = 0; j < nch; ++j) {
+                                    const ulonglong2 b0 = nb0, c0 = nc0, b1 = nb1, c1 = nc1;
+                                    t4 += 4;
+                                    nb0 = t4[0]; nc0 = t4[1]; nb1 = t4[2]; nc1 = t4[3];
+                                    chunk_math8<NE>(b0, c0, b1, c1, Re, acc);
 #pragma unroll
-                                for (int i = 0; i < NE; ++i) pc[i * 32] = f2_lo(acc[i]) + f2_hi(acc[i]);   // running prefix, m units
-                                tc += tstep; pc += NE * 32;
+                                    for (int i = 0; i < NE; ++i) pc[i * 32] = f2_lo(acc[i]) + f2_hi(acc[i]);   // running prefix, m units
+                                    pc += NE * 32;
+                                }
+                            } else {
+#pragma unroll 2
+                                for (int j = 0; j < nch; ++j) {
+                                    chunk_acc<NE, LC, FACT>(kx, tc, xe, Re, acc);
+#pragma unroll
+                                    for (int i = 0; i < NE; ++i) pc[i * 32] = f2_lo(acc[i]) + f2_hi(acc[i]);   // running prefix, m units
+                                    tc += tstep; pc += NE * 32;
+                                }
                             }
 #pragma unroll 1
                             for (int i = 0; i < NE; ++i) {
@@ -612,29 +651,69 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                         __syncwarp();
                     }
                 } else {
-                    // =============== run-off round: one elector per slot, first k columns ==================
-                    uint32_t w[4] = {0, 0, 0, 0};
-                    for (int n = 0; n < n_slots; ++n) {
-                        int e, q; bool gen;
-                        if (n < n_main) { q = lane + 32 * (n >> 2); e = 4 * q + (n & 3); gen = (n & 3) == 0; }
-                        else { e = e_single0 + 32 * (n - n_main); q = e >> 2; gen = true; }
-                        if (gen) philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)q, a.b.seed_lo, a.b.seed_hi, w);
-                        const int sel = e & 3;
-                        const uint32_t wa = sel == 0 ? w[0] : (sel == 1 ? w[1] : (sel == 2 ? w[2] : w[3]));
-                        const float u = u24_from_word(wa);
-                        const Elector32 el = load_elector(e, sticky_live);
-                        int vote;
-                        if (fast2) {
-                            // two-candidate run-off: columns 0 and 1, renormalised (simulate.py:144-154)
-                            const float v0 = full_score32<LC, MODEL, FACT>(kx, e, 0, el);
-                            const float v1 = full_score32<LC, MODEL, FACT>(kx, e, 1, el);
-                            const float sum = v0 + v1;
+                    // =============== run-off round: first k columns (simulate.py:144-154) ==================
+                    if (fast2) {
+                        // k = 2: columns 0 and 1 are the same two candidates for every elector; their operands of this round, their
+                        // regions and bandwagon terms live in registers, and a vote is decided in m units (score / A_e: the
+                        // comparison v0 > u (v0 + v1) does not depend on the positive factor A_e), so an elector costs one load.
+                        const int o0 = tab_off<LC>(0), o1 = tab_off<LC>(1);
+                        const float P0 = kx.T[o0], X0 = kx.T[o0 + kx.xoff], P1 = kx.T[o1], X1 = kx.T[o1 + kx.xoff];
+                        const int g0 = reg[0], g1 = reg[1];
+                        float f0 = 0.f, f1 = 0.f;
+                        if (MODEL && kx.use_bw) { f0 = bw[0]; f1 = bw[1]; }
+                        const float bonus = kx.bonus, nb = kx.nb, st1p = kx.st1p;
+                        auto play = [&](int e, uint32_t wa) {
+                            const float u = u24_from_word(wa);
+                            const int g = reg[e];
+                            const float b0 = (g == g0 ? bonus : 0.0f) + f0, b1 = (g == g1 ? bonus : 0.0f) + f1;
+                            float w0, w1;
+                            if (FACT) {
+                                const float Ainv = __ldg(tabA + CP + e), Rr = Ainv * Ainv;
+                                w0 = fmaf(b0, Ainv, fminf(P0, Rr * X0));
+                                w1 = fmaf(b1, Ainv, fminf(P1, Rr * X1));
+                            } else {
+                                const float xe = __ldg(a.ro.x32 + e);
+                                w0 = fmaf(ex2_approx(fabsf(xe - X0) * nb), P0, b0);
+                                w1 = fmaf(ex2_approx(fabsf(xe - X1) * nb), P1, b1);
+                            }
+                            if (MODEL && sticky_live) {
+                                const int prev = votes[e];
+                                if (prev == 0) w0 *= st1p;
+                                if (prev == 1) w1 *= st1p;
+                            }
+                            if (e == 0) w0 = 0.0f;
+                            if (e == 1) w1 = 0.0f;
+                            const float sum = w0 + w1;
                             int j;
                             if (!(sum > 0.0f)) j = (u * 2.0f >= 1.0f) ? 1 : 0;       // simulate.py:151 uniform fallback
-                            else j = (v0 > u * sum || !(v1 > 0.0f)) ? 0 : 1;
+                            else j = (w0 > u * sum || !(w1 > 0.0f)) ? 0 : 1;
                             cnt0 += (j == 0);
-                            vote = j == 0 ? ef0 : ef1;
-                        } else {
+                            if (MODEL) votes[e] = j == 0 ? ef0 : ef1;
+                        };
+                        for (int qi = 0; qi < m_quads; ++qi) {
+                            const int q = lane + 32 * qi;
+                            uint32_t w[4];
+                            philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)q, a.b.seed_lo, a.b.seed_hi, w);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) play(4 * q + i, w[i]);
+                        }
+                        for (int e = e_single0; e < E; e += 32) {
+                            uint32_t w[4];
+                            philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)(e >> 2), a.b.seed_lo, a.b.seed_hi, w);
+                            const int sel = e & 3;
+                            play(e, sel == 0 ? w[0] : (sel == 1 ? w[1] : (sel == 2 ? w[2] : w[3])));
+                        }
+                    } else {
+                        uint32_t w[4] = {0, 0, 0, 0};
+                        for (int n = 0; n < n_slots; ++n) {
+                            int e, q; bool gen;
+                            if (n < n_main) { q = lane + 32 * (n >> 2); e = 4 * q + (n & 3); gen = (n & 3) == 0; }
+                            else { e = e_single0 + 32 * (n - n_main); q = e >> 2; gen = true; }
+                            if (gen) philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)q, a.b.seed_lo, a.b.seed_hi, w);
+                            const int sel = e & 3;
+                            const uint32_t wa = sel == 0 ? w[0] : (sel == 1 ? w[1] : (sel == 2 ? w[2] : w[3]));
+                            const float u = u24_from_word(wa);
+                            const Elector32 el = load_elector(e, sticky_live);
                             float sum = 0.f;
                             for (int j = 0; j < k; ++j) sum += full_score32<LC, MODEL, FACT>(kx, e, j, el);
                             int jsel;
@@ -652,10 +731,10 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                                 if (jsel < 0) jsel = lastpos;
                             }
                             if (jsel >= k) jsel = k - 1;
-                            vote = eff[jsel];
+                            const int vote = eff[jsel];
                             atomicAdd(&tally[vote], 1);
+                            if (MODEL) votes[e] = vote;
                         }
-                        if (MODEL) votes[e] = vote;
                     }
                 }
                 int n0 = 0, n1 = 0;
