@@ -210,6 +210,33 @@ __device__ __forceinline__ void deal_electors(int lane, int E, int e_quad_end, i
     }
 }
 
+// The same dealing as ONE loop over the lane's elector slots, so that the caller's body is instantiated once (deal_electors
+// inlines it twice: the FULL engine's body is ~25 KB of code and two copies thrash the 32 KB instruction cache).
+template <class Fn>
+__device__ __forceinline__ void deal_electors_once(int lane, int E, int e_quad_end, int r, uint32_t s_lo, uint32_t s_hi, uint32_t seed_lo,
+                                                   uint32_t seed_hi, Fn&& fn) {
+    const int n_q = (e_quad_end >> 7) << 2;                  // quad slots of a lane
+    const int n_tail = E > e_quad_end + lane ? (E - e_quad_end - lane + 31) >> 5 : 0;
+    uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll 1
+    for (int n = 0; n < n_q + n_tail; ++n) {
+        int e, slot, sel;
+        if (n < n_q) {
+            const int qi = n >> 2, q = lane + 32 * qi;
+            sel = n & 3;
+            e = 4 * q + sel;
+            slot = (qi << 7) + (sel << 5) + lane;
+            if (sel == 0 && e < E) philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)q, seed_lo, seed_hi, w);
+        } else {
+            e = e_quad_end + lane + 32 * (n - n_q);
+            slot = e; sel = e & 3;
+            philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)(e >> 2), seed_lo, seed_hi, w);
+        }
+        const uint32_t wa = sel == 0 ? w[0] : (sel == 1 ? w[1] : (sel == 2 ? w[2] : w[3]));
+        if (e < E) fn(e, u24_from_word(wa), slot);
+    }
+}
+
 // The per-trial outputs every warp-per-trial kernel writes when its trial ends (winner / rounds / reason rows, the last
 // tally, the -1 padding of the per-round tallies beyond `rounds`, the two histograms of simulate.py:356-387).
 __device__ __forceinline__ void write_trial_outputs(const TrialOut& out, uint64_t t, int set, int C, int R, int lane, const int32_t* tally,

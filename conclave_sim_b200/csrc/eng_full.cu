@@ -17,6 +17,18 @@ csim_status launch_full32(csim_ctx* c, const csim_run_args* ra, const std::vecto
     if (!full32_plan(a, E, c->G, R, kmax, Fmax, (size_t)c->prop.sharedMemPerBlockOptin))
         return fail(CSIM_ERR_UNSUPPORTED, "full engine: a roster of %d electors (fatigue window %d) does not fit in shared memory", E, Fmax);
     a.ro = roster_dev(c); a.b = b; a.out = out; a.nbeta = (const float*)c->nbeta.p;
+    a.accw = (E + 31) / 32; a.accmask = nullptr;
+    bool any_stop = false;
+    for (const DevSet& s : hs) any_stop = any_stop || s.en_stop;
+    if (any_stop) {                                           // acceptable(e, c) bits, fp64-exact, once per batch
+        CU_TRY(c->accm.reserve(sizeof(uint32_t) * (size_t)b.n_sets * E * a.accw));
+        a.accmask = (const uint32_t*)c->accm.p;
+        for (int s0 = 0; s0 < b.n_sets; s0 += CSIM_GRID_TILE) {
+            dim3 g((E * a.accw + 127) / 128, std::min(CSIM_GRID_TILE, b.n_sets - s0));
+            k_full_accmask<<<g, 128, 0, st>>>(a.ro, b.sets + s0, a.accw, (uint32_t*)c->accm.p + (size_t)s0 * E * a.accw);
+            ++c->launches;
+        }
+    }
     const int wpc = a.warps_per_cta;
     const size_t smem = a.cta_smem + a.warp_smem * wpc;
     bool ext = false, neg = false;                            // which terms the batch needs decides the instantiation

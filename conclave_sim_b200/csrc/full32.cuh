@@ -30,6 +30,10 @@ struct Full32Args {
     BatchDev b;
     TrialOut out;
     const float* nbeta;     // [sets][R]  -beta_r * log2(e)
+    const uint32_t* accmask;// [sets][E][accw]: bit c of row e <=> candidate c is ACCEPTABLE to elector e for that set's stop-candidate
+                            // distance: !(|x_e - x_c| > D) decided in fp64 exactly as model.py:390 (k_full_accmask, once per batch);
+                            // null when no set has stop-candidate enabled.  The hot loop tests bits instead of fp64 distances.
+    int accw;               // words per row
     int nblk;               // blocks of 8 candidates, 8 nblk >= C
     int Lb;                 // blocks per chunk
     int nch;                // chunks, nch * Lb >= nblk, nch <= 32
@@ -86,11 +90,24 @@ __host__ inline bool full32_plan(Full32Args& a, int E, int G, int R, int kmax, i
     return true;
 }
 
+// acceptable(e, c) for every set with stop-candidate enabled (model.py:384-415): grid = (ceil(E * W / 128), sets), block = 128
+static __global__ void k_full_accmask(RosterDev ro, const DevSet* sets, int W, uint32_t* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, set = blockIdx.y;
+    const int E = ro.E;
+    if (i >= E * W) return;
+    const int e = i / W, wd = i - e * W;
+    const double xe = ro.x64[e], D = sets[set].stop_D;
+    uint32_t m = 0;
+    for (int b = 0; b < 32; ++b) {
+        const int c = 32 * wd + b;
+        if (c < E && !(fabs(xe - ro.x64[c]) > D)) m |= 1u << b;
+    }
+    out[((size_t)set * E + e) * W + wd] = m;
+}
+
 struct Full32Ctx {          // what one score needs (per warp / per round)
     const float* xs; const float* pw; const float* rb; const float* bw; const float* phi;
-    const double* x64;
     float nb, st1p, boost;
-    double stop_D;
     int C;
 };
 
@@ -99,7 +116,7 @@ struct Full32Ctx {          // what one score needs (per warp / per round)
 //        running prefix at the chunks of prev and of e with the exact differences (full32_score1 with / without them)
 //   EXT  candidate fatigue / stop-candidate live for this batch;  NEG  some factor is negative: the model's clamps matter
 template <bool RAW, bool EXT, bool NEG>
-__device__ __forceinline__ void full32_score8(const Full32Ctx& k, int blk, int e, float xe, double xe64, const float* rbrow, int prev, bool trig,
+__device__ __forceinline__ void full32_score8(const Full32Ctx& k, int blk, int e, float xe, const uint32_t* arow, const float* rbrow, int prev, bool trig,
                                               float (&v)[8]) {
     const int cb = blk << 3;
     const float4 xa = *reinterpret_cast<const float4*>(k.xs + cb), xb = *reinterpret_cast<const float4*>(k.xs + cb + 4);
@@ -124,11 +141,9 @@ __device__ __forceinline__ void full32_score8(const Full32Ctx& k, int blk, int e
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] *= f8[i];                                        // fatigue
         if (trig) {                                                                       // stop-candidate: boost the acceptable ones
+            const uint32_t m8 = __ldg(arow + (cb >> 5)) >> (cb & 31);          // this block's 8 "acceptable" bits (model.py:390, k_full_accmask)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int c = min(cb + i, k.C - 1);
-                if (!(fabs(xe64 - k.x64[c]) > k.stop_D)) v[i] *= k.boost;      // acceptable <=> not (|dx| > D), fp64 as model.py:390
-            }
+            for (int i = 0; i < 8; ++i) if ((m8 >> i) & 1u) v[i] *= k.boost;
         }
     }
 #pragma unroll
@@ -140,14 +155,14 @@ __device__ __forceinline__ void full32_score8(const Full32Ctx& k, int blk, int e
 
 // one score; `sticky` / `self` say whether those two point rules are applied (pass 1 needs the difference they make)
 template <bool EXT, bool NEG>
-__device__ __forceinline__ float full32_score1(const Full32Ctx& k, int c, int e, float xe, double xe64, const float* rbrow, int prev, bool trig,
+__device__ __forceinline__ float full32_score1(const Full32Ctx& k, int c, int e, float xe, const uint32_t* arow, const float* rbrow, int prev, bool trig,
                                                bool sticky = true, bool self = true) {
     float s = fmaf(ex2_approx(fabsf(xe - k.xs[c]) * k.nb), k.pw[c], rbrow[c]) + k.bw[c];
     if (sticky && c == prev) s *= k.st1p;
     if (NEG) s = fmaxf(s, 0.0f);
     if (EXT) {
         s *= k.phi[c];
-        if (trig && !(fabs(xe64 - k.x64[c]) > k.stop_D)) s *= k.boost;
+        if (trig && ((__ldg(arow + (c >> 5)) >> (c & 31)) & 1u)) s *= k.boost;
     }
     if (self && c == e) return 0.0f;
     return NEG ? fmaxf(s, 0.0f) : s;
@@ -185,13 +200,13 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
     uint8_t* mark = base + a.w_mark;
 
     Full32Ctx kx;
-    kx.xs = xs; kx.pw = pwv; kx.rb = rbv; kx.bw = bw; kx.phi = phi; kx.x64 = a.ro.x64;
-    kx.nb = 0.f; kx.st1p = 1.f; kx.boost = 1.f; kx.stop_D = 0.0; kx.C = C;
+    kx.xs = xs; kx.pw = pwv; kx.rb = rbv; kx.bw = bw; kx.phi = phi;
+    kx.nb = 0.f; kx.st1p = 1.f; kx.boost = 1.f; kx.C = C;
     int step0 = 1;
     while (step0 * 2 <= nch) step0 *= 2;
 
     auto for_each_elector = [&](int r, uint32_t s_lo, uint32_t s_hi, auto&& fn) {
-        deal_electors(lane, E, a.e_quad_end, r, s_lo, s_hi, a.b.seed_lo, a.b.seed_hi, fn);
+        deal_electors_once(lane, E, a.e_quad_end, r, s_lo, s_hi, a.b.seed_lo, a.b.seed_hi, fn);
     };
 
     const uint64_t per_item = (uint64_t)wpc * a.tpi;
@@ -212,7 +227,7 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
             acc_rounds = acc_trials = 0;
             cur_set = set;
             S = a.b.sets[set];
-            kx.st1p = S.f_st1p; kx.boost = S.f_stop_boost; kx.stop_D = S.stop_D;
+            kx.st1p = S.f_st1p; kx.boost = S.f_stop_boost;
             __syncthreads();                                    // readers of the previous set's tables are done
             for (int r = threadIdx.x; r < R; r += blockDim.x) nbs[r] = a.nbeta[(size_t)set * R + r];
             for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -326,14 +341,14 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
                     const float* rbrow = rbv + g2.y * CP;
                     int prev = sticky_live ? (int)votes[slot] : -1;
                     if (PROBE && prev == 0xFFFF) prev = -1;              // probe input: this elector had no previous vote
-                    const double xe64 = a.ro.x64[e];
+                    const uint32_t* arow = a.accmask + ((size_t)set * E + e) * a.accw;      // dereferenced only when stop-candidate is live
                     bool trig = false;
                     if (n_thr > 0) {
                         if (n_thr <= 32) {
-                            for (int q = 0; q < n_thr && !trig; ++q) trig = fabs(xe64 - a.ro.x64[thr[q]]) > S.stop_D;
+                            for (int q = 0; q < n_thr && !trig; ++q) { const int c = thr[q]; trig = !((__ldg(arow + (c >> 5)) >> (c & 31)) & 1u); }   // an UNacceptable threat
                         } else {                                     // more threats than the list holds: test every candidate
                             for (int q = 0; q < C && !trig; ++q)
-                                trig = fabs(xe64 - a.ro.x64[q]) > S.stop_D && (all_thr || hist[(size_t)((n_hist - 1) % a.Fmax) * C + q] >= S.stop_cnt);
+                                trig = !((__ldg(arow + (q >> 5)) >> (q & 31)) & 1u) && (all_thr || hist[(size_t)((n_hist - 1) % a.Fmax) * C + q] >= S.stop_cnt);
                         }
                     }
                     int vote;
@@ -341,13 +356,13 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
                         // ---- pass 1: the whole row, running prefix per chunk into this lane's column ----------
                         // the point rules enter the prefix at the chunks of e and of prev, as exact differences
                         const int je = (e >> 3) / Lb;
-                        const float d_self = -full32_score1<EXT, NEG>(kx, e, e, xe, xe64, rbrow, -1, trig, false, false);
+                        const float d_self = -full32_score1<EXT, NEG>(kx, e, e, xe, arow, rbrow, -1, trig, false, false);
                         int jp = -1;
                         float d_prev = 0.0f;
                         if (prev >= 0 && prev != e) {
                             jp = (prev >> 3) / Lb;
-                            d_prev = full32_score1<EXT, NEG>(kx, prev, e, xe, xe64, rbrow, prev, trig, true, false) -
-                                     full32_score1<EXT, NEG>(kx, prev, e, xe, xe64, rbrow, prev, trig, false, false);
+                            d_prev = full32_score1<EXT, NEG>(kx, prev, e, xe, arow, rbrow, prev, trig, true, false) -
+                                     full32_score1<EXT, NEG>(kx, prev, e, xe, arow, rbrow, prev, trig, false, false);
                         }
                         float run = 0.0f;
                         for (int j = 0; j < nch; ++j) {
@@ -355,7 +370,7 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
                                 const int blk = j * Lb + b;
                                 if (blk >= nblk) break;
                                 float v[8];
-                                full32_score8<true, EXT, NEG>(kx, blk, e, xe, xe64, rbrow, prev, trig, v);
+                                full32_score8<true, EXT, NEG>(kx, blk, e, xe, arow, rbrow, prev, trig, v);
                                 run += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
                             }
                             if (j == je) run += d_self;
@@ -366,7 +381,7 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
                             for (int j = 0; j < nch; ++j) a.probe_prefix[(size_t)e * a.probe_cap + j] = col[32 * j];
                             for (int blk = 0; blk < nblk; ++blk) {
                                 float v[8];
-                                full32_score8<false, EXT, NEG>(kx, blk, e, xe, xe64, rbrow, prev, trig, v);
+                                full32_score8<false, EXT, NEG>(kx, blk, e, xe, arow, rbrow, prev, trig, v);
 #pragma unroll
                                 for (int q = 0; q < 8; ++q) if (8 * blk + q < C) a.probe_scores[(size_t)e * C + 8 * blk + q] = v[q];
                             }
@@ -398,7 +413,7 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
                                 const int blk = blk0 + b;
                                 if (blk >= nblk) break;
                                 float v[8];
-                                full32_score8<false, EXT, NEG>(kx, blk, e, xe, xe64, rbrow, prev, trig, v);
+                                full32_score8<false, EXT, NEG>(kx, blk, e, xe, arow, rbrow, prev, trig, v);
 #pragma unroll
                                 for (int q = 0; q < 8; ++q) { cum += v[q]; cnt += (cum <= tgt) ? 1 : 0; }
                                 if (cnt < 8 * (b + 1)) break;
@@ -411,7 +426,7 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
                     } else {
                         // ---- run-off round: first k columns, renormalised (simulate.py:144-154) --------------
                         float sum = 0.f;
-                        for (int j = 0; j < k; ++j) sum += full32_score1<EXT, NEG>(kx, j, e, xe, xe64, rbrow, prev, trig);
+                        for (int j = 0; j < k; ++j) sum += full32_score1<EXT, NEG>(kx, j, e, xe, arow, rbrow, prev, trig);
                         int jsel;
                         if (!(sum > 0.0f)) {
                             jsel = (int)(u * (float)k);
@@ -419,7 +434,7 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
                             const float tgt = u * sum;
                             float cum = 0.f; jsel = -1; int lastpos = 0;
                             for (int j = 0; j < k; ++j) {
-                                const float v = full32_score1<EXT, NEG>(kx, j, e, xe, xe64, rbrow, prev, trig);
+                                const float v = full32_score1<EXT, NEG>(kx, j, e, xe, arow, rbrow, prev, trig);
                                 cum += v;
                                 if (v > 0.0f) lastpos = j;
                                 if (jsel < 0 && v > 0.0f && cum > tgt) jsel = j;
