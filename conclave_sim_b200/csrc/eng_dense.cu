@@ -89,7 +89,6 @@ csim_status launch_dense32(csim_ctx* c, const csim_run_args* ra, const std::vect
     for (int i = 0; i < ra->n_param_sets; ++i)
         if (ra->params[i].regional_affinity_bonus < 0 || ra->params[i].bandwagon_strength < 0 || ra->params[i].papabile_weight_factor < 0)
             return fail(CSIM_ERR_UNSUPPORTED, "negative bonus / strength / papabile factor: use CSIM_FP64 precision");
-    if (c->G > 64) return fail(CSIM_ERR_UNSUPPORTED, "%d distinct regions (> 64): use CSIM_FP64 precision", c->G);
     Dense32Args a;
     a.ro = roster_dev(c); a.b = b; a.out = out; a.nbeta = (const float*)c->nbeta.p; a.wiring = ra->wiring; a.tab = nullptr;
     a.probe_round = 0; a.probe_prev_vote = nullptr; a.probe_prev_count = nullptr; a.probe_scores = nullptr; a.probe_prefix = nullptr; a.probe_cap = 0;
