@@ -37,8 +37,8 @@
 // any beta).
 //
 // Candidate operands of one round ("round table" T, shared memory).  Two operands per candidate: P (BP, or the papabile
-// weight in the MUFU form) and X (BQ, or the ideology).  L = 8: interleaved per chunk, [P0..3 | X0..3 | P4..7 | X4..7],
-// so ONE pointer that advances 64 bytes per chunk serves the four 128-bit loads of a chunk at immediate offsets; generic
+// weight in the MUFU form) and X (BQ, or the ideology).  L = 8: interleaved per chunk, [P0..3 | X0..3 | P4..7 | X4..7 | pad],
+// so ONE pointer that advances 80 bytes per chunk serves the four 128-bit loads of a chunk at immediate offsets; generic
 // L: two planes [CP] + [CP].  FACT: the tables of ALL R rounds of the current parameter set are staged once per CTA
 // (R x 2 CP floats: 21.8 KB at E = 135, R = 20) when they fit, else each warp stages the round it plays.
 //
@@ -62,6 +62,9 @@ struct Dense32Args {
     int tpi;                // trials per warp per work item
     int cta_tabs;           // 1: the round tables of the whole parameter set are CTA-shared (n_tab rounds); 0: per warp, per round
     int n_tab;              // rounds staged per set when cta_tabs (FACT: R; MUFU form: 1 — its operands do not depend on the round)
+    int n_tab_full;         // of those, the first n_tab_full are whole tables (the rounds that can be full-field); the later ones are
+                            // run-off rounds, which only ever read the first kmax candidates: nk_chunks chunks each (L = 8 only)
+    int nk_chunks;
     size_t cta_smem;        // bytes of CTA-shared tables
     size_t warp_smem;       // bytes per warp
     // PROBE instantiation only (csim_engine_probs): one trial is started AT round probe_round from the given previous-round
@@ -85,20 +88,27 @@ struct Dense32Args {
 #define CSIM_DENSE_PIPELINE 1   // software-pipeline the operand loads of the pair loop (L = 8, factorised form)
 #endif
 #define DENSE32_PREF_COLS (CSIM_NE > 1 ? CSIM_NE : 1)
-// pitch of the per-region regional-bonus rows (floats): CP + 4 spreads the rows of 8 regions over all banks for the 128-bit loads
-__host__ __device__ inline int dense32_rb_pitch(int CP) { return CP + 4; }
+// Shared-memory layouts whose chunks are GATHERED per lane by the re-scan (each lane re-reads the chunk ITS target fell into, with
+// 128-bit loads): with L = 8 a chunk is padded so that consecutive chunks start in different 16-byte bank groups — a round table
+// chunk holds 16 operands + 4 floats of padding (stride 80 B: 5 j mod 8 walks all eight groups; at 64 B every chunk started in
+// group 0 or 4 and the gathers serialised four-fold: 37 % of the kernel's shared wavefronts were conflicts), the per-candidate
+// arrays (regional rows, bandwagon) 8 + 4 floats (3 j mod 8).  Generic L: plain arrays.
+__host__ __device__ inline int dense32_tab_floats(int nch, int L) { return L == 8 ? nch * 20 : 2 * nch * L; }      // one round table
+__host__ __device__ inline int dense32_cpp(int nch, int L) { return L == 8 ? nch * 12 : nch * L; }                  // padded per-candidate array
+__host__ __device__ inline int dense32_rb_pitch(int nch, int L) { return dense32_cpp(nch, L) + 4; }
 // byte offsets of the CTA-shared arrays: reg i32[CP] | RBp f32[G][nch] | RBf f32[G][pitch] | round tables f32[n_tab][2 CP]; all 16-byte aligned
 __host__ __device__ inline size_t dense32_o_rbp(int nch, int L) { return (size_t)nch * L * 4; }
 __host__ __device__ inline size_t dense32_o_rbf(int nch, int L, int G) { return dense32_o_rbp(nch, L) + (((size_t)nch * G * 4 + 15) & ~(size_t)15); }
-__host__ __device__ inline size_t dense32_o_tabs(int nch, int L, int G) { return dense32_o_rbf(nch, L, G) + (size_t)G * dense32_rb_pitch(nch * L) * 4; }
-__host__ __device__ inline size_t dense32_cta_smem(int nch, int L, int G, int n_tab_rounds) {
-    return dense32_o_tabs(nch, L, G) + (size_t)n_tab_rounds * 2 * nch * L * 4;
+__host__ __device__ inline size_t dense32_o_tabs(int nch, int L, int G) { return dense32_o_rbf(nch, L, G) + (size_t)G * dense32_rb_pitch(nch, L) * 4; }
+__host__ __device__ inline size_t dense32_cta_smem(int nch, int L, int G, int n_tab_full, int n_tab_short = 0, int nk_chunks = 0) {
+    return dense32_o_tabs(nch, L, G) + ((size_t)n_tab_full * dense32_tab_floats(nch, L) + (size_t)n_tab_short * dense32_tab_floats(nk_chunks, L)) * 4;
 }
 __host__ __device__ inline size_t dense32_warp_smem(int E, int nch, int L, int kmax, bool model, bool warp_tab) {
     const size_t CP = (size_t)nch * L, Ei = ((size_t)E + 3) & ~(size_t)3, n4 = ((size_t)nch + 3) & ~(size_t)3;
-    size_t n = (warp_tab ? CP * 4 * 2 : 0) /*own round table*/ + (size_t)DENSE32_PREF_COLS * nch * 32 * 4 /*prefix columns*/ + Ei * 4 /*tally*/ +
-               (((size_t)kmax + 3) & ~(size_t)3) * 4 /*eff*/ + Ei /*mark*/;
-    if (model) n += CP * 4 /*bw*/ + n4 * 4 /*bwp*/ + Ei * 4 * 2 /*prev_tally, votes*/;
+    size_t n = (warp_tab ? (size_t)dense32_tab_floats(nch, L) * 4 : 0) /*own round table*/ + (size_t)DENSE32_PREF_COLS * nch * 32 * 4 /*prefix columns*/ +
+               Ei * 4 /*tally*/ + (((size_t)kmax + 3) & ~(size_t)3) * 4 /*eff*/ + Ei /*mark*/;
+    if (model) n += (size_t)dense32_cpp(nch, L) * 4 /*bw*/ + n4 * 4 /*bwp*/ + Ei * 4 * 2 /*prev_tally, votes*/;
+    (void)CP;
     return (n + 15) & ~(size_t)15;
 }
 
@@ -133,7 +143,9 @@ static __global__ void k_round_tables32(RosterDev ro, const DevSet* sets, const 
 }
 
 // index of candidate c's P operand inside a round table; its X operand sits XOFF floats further
-template <int LC> __device__ __forceinline__ int tab_off(int c) { return LC == 8 ? ((c >> 3) << 4) + ((c & 4) << 1) + (c & 3) : c; }
+template <int LC> __device__ __forceinline__ int tab_off(int c) { return LC == 8 ? (c >> 3) * 20 + ((c & 4) << 1) + (c & 3) : c; }
+// index of candidate c in the padded per-candidate arrays (regional rows, bandwagon)
+template <int LC> __device__ __forceinline__ int pad_c(int c) { return LC == 8 ? c + ((c >> 3) << 2) : c; }
 
 struct LaneCtx32 {              // per-warp / per-round constants of the draw
     const float* T;             // this round's table (see the header): P = BP | pw, X = BQ | x
@@ -166,7 +178,7 @@ __device__ __forceinline__ float full_score32(const LaneCtx32& k, int e, int c, 
     float v = el.A * pair_m32<LC, FACT>(k, c, el);
     if (k.reg[c] == el.g) v += k.bonus;
     if (MODEL) {
-        if (k.use_bw) v += k.bw[c];
+        if (k.use_bw) v += k.bw[pad_c<LC>(c)];
         if (c == el.prev) v *= k.st1p;
     }
     return c == e ? 0.0f : v;
@@ -261,13 +273,13 @@ template <int LC, bool MODEL, bool FACT>
 __device__ __forceinline__ Corr32 corrections32(const LaneCtx32& k, int e, const Elector32& el) {
     Corr32 cr;
     float flat = k.bonus;                                  // the self pair is of e's own region
-    if (MODEL && k.use_bw) flat += k.bw[e];
+    if (MODEL && k.use_bw) flat += k.bw[pad_c<LC>(e)];
     cr.see = pair_m32<LC, FACT>(k, e, el) + flat * el.Ainv;   // same expression as phase 1, so it cancels
     cr.je = e / k.L;
     cr.jp = 0x7fffffff; cr.sadd = 0.f;
     if (MODEL && el.prev >= 0 && el.prev != e) {
         float fl = (k.reg[el.prev] == el.g) ? k.bonus : 0.f;
-        if (k.use_bw) fl += k.bw[el.prev];
+        if (k.use_bw) fl += k.bw[pad_c<LC>(el.prev)];
         cr.sadd = (pair_m32<LC, FACT>(k, el.prev, el) + fl * el.Ainv) * (k.st1p - 1.0f);
         cr.jp = el.prev / k.L;
     }
@@ -289,16 +301,16 @@ __device__ __forceinline__ float probe32(const LaneCtx32& k, const float* pref, 
 template <bool MODEL, bool FACT>
 __device__ __forceinline__ void rescan8_scores(const LaneCtx32& k, int jstar, int e, const Elector32& el, float (&v)[8]) {
     const int c0 = jstar * 8;
-    const float4* t4 = reinterpret_cast<const float4*>(k.T + 16 * jstar);
+    const float4* t4 = reinterpret_cast<const float4*>(k.T + 20 * jstar);
     const float4 pa = t4[0], xa = t4[1], pb = t4[2], xb = t4[3];           // P = BP | pw, X = BQ | x
-    const float* rbrow = k.rbf + el.g * k.rb_pitch + c0;                   // bonus where candidate c0+i is of e's region, else 0
+    const float* rbrow = k.rbf + el.g * k.rb_pitch + 12 * jstar;           // bonus where candidate c0+i is of e's region, else 0 (padded chunks)
     const float4 ra = *reinterpret_cast<const float4*>(rbrow), rb = *reinterpret_cast<const float4*>(rbrow + 4);
     float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;
     const int is = e - c0;                                                 // position of e itself / of prev inside this chunk (else outside 0..7)
     int ip = -1;
     if (MODEL) {
         ip = el.prev - c0;
-        if (k.use_bw) { ba = *reinterpret_cast<const float4*>(k.bw + c0); bb = *reinterpret_cast<const float4*>(k.bw + c0 + 4); }
+        if (k.use_bw) { ba = *reinterpret_cast<const float4*>(k.bw + 12 * jstar); bb = *reinterpret_cast<const float4*>(k.bw + 12 * jstar + 4); }
     }
     const float nb = k.nb;
 #define CSIM_RESCAN(i, xv, pv, rv, bv)                                          \
@@ -378,9 +390,11 @@ __device__ __forceinline__ int finish_draw(const LaneCtx32& k, const float* pref
 // One round's table from its source into shared memory, by `nthr` threads of which this is number `tid`:
 // FACT: src = the round's [4][CP] block of Dense32Args::tab (planes 2, 3 = BP, BQ);  MUFU form: P = papabile weight, X = ideology.
 template <int LC, bool FACT>
-__device__ __forceinline__ void stage_round_table(float* dst, const Dense32Args& a, const float* src, float pwf, int CP, int C, int tid, int nthr) {
+__device__ __forceinline__ void stage_round_table(float* dst, const Dense32Args& a, const float* src, float pwf, int CP, int C, int tid, int nthr,
+                                                  int n_cand = 0x7fffffff) {
     const int xoff = LC == 8 ? 4 : CP;
-    for (int c = tid; c < CP; c += nthr) {
+    const int n = n_cand < CP ? n_cand : CP;                 // run-off rounds: only the first chunks are ever read
+    for (int c = tid; c < n; c += nthr) {
         float P, X;
         if (FACT) { P = __ldg(src + 2 * CP + c); X = __ldg(src + 3 * CP + c); }
         else { P = c < C ? (a.ro.pap[c] ? pwf : 1.0f) : 0.0f; X = c < C ? a.ro.x32[c] : 0.0f; }
@@ -400,7 +414,9 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
     const int CP = nch * L;
     const int Ei = (E + 3) & ~3;
     const int wpc = a.warps_per_cta;
-    const int rbpitch = dense32_rb_pitch(CP);
+    const int rbpitch = dense32_rb_pitch(nch, L);
+    const int TF = dense32_tab_floats(nch, L), CPP = dense32_cpp(nch, L);
+    const int TK = dense32_tab_floats(a.nk_chunks, L);       // a run-off round's short table (cta_tabs)
     // ---- CTA-shared roster tables ------------------------------------------------------------
     int32_t* reg = (int32_t*)smem_raw;
     float* rbp = (float*)(smem_raw + dense32_o_rbp(nch, L));           // [G][nch]: #{c in chunks 0..j : region_c == g}
@@ -416,11 +432,11 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
     // ---- per-warp state ----------------------------------------------------------------------
     unsigned char* base = smem_raw + a.cta_smem + (size_t)wib * a.warp_smem;
     // 16-byte aligned float arrays first (they are read with 128-bit loads), then the int arrays
-    float* wtab = (float*)base;                 if (!a.cta_tabs) base += sizeof(float) * 2 * CP;          // own round table (fallback)
+    float* wtab = (float*)base;                 if (!a.cta_tabs) base += sizeof(float) * TF;              // own round table (fallback)
     float* pref = (float*)base;                 base += sizeof(float) * DENSE32_PREF_COLS * nch * 32;   // prefix columns [j][t][lane]
     float* bw = nullptr; float* bwp = nullptr;
     if (MODEL) {
-        bw = (float*)base;                      base += sizeof(float) * CP;
+        bw = (float*)base;                      base += sizeof(float) * CPP;
         bwp = (float*)base;                     base += sizeof(float) * ((nch + 3) & ~3);
     }
     int32_t* tally = (int32_t*)base;            base += sizeof(int32_t) * Ei;
@@ -484,15 +500,18 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
             need = S->need; k = S->k; rr = S->rr;
             has_sticky = MODEL && S->has_sticky; has_bw = MODEL && S->has_bw;
             __syncthreads();                                    // readers of the previous set's tables are done
-            for (int i = threadIdx.x; i < G * rbpitch; i += blockDim.x) {
-                const int g = i / rbpitch, c = i - g * rbpitch;
-                rbf[i] = (c < C && a.ro.region[c] == g) ? kx.bonus : 0.0f;
+            for (int i = threadIdx.x; i < G * CP; i += blockDim.x) {
+                const int g = i / CP, c = i - g * CP;
+                rbf[g * rbpitch + pad_c<LC>(c)] = (c < C && a.ro.region[c] == g) ? kx.bonus : 0.0f;
             }
             if (a.cta_tabs)
-                for (int rt = 0; rt < a.n_tab; ++rt)
-                    stage_round_table<LC, FACT>(tabs + (size_t)rt * 2 * CP, a, FACT ? a.tab + ((size_t)set * R + rt) * 4 * CP : nullptr, pwf, CP, C,
-                                                threadIdx.x, blockDim.x);
-            if (MODEL) for (int c = lane; c < CP; c += 32) bw[c] = 0.0f;
+                for (int rt = 0; rt < a.n_tab; ++rt) {
+                    const bool whole = rt < a.n_tab_full;
+                    float* dst = whole ? tabs + (size_t)rt * TF : tabs + (size_t)a.n_tab_full * TF + (size_t)(rt - a.n_tab_full) * TK;
+                    stage_round_table<LC, FACT>(dst, a, FACT ? a.tab + ((size_t)set * R + rt) * 4 * CP : nullptr, pwf, CP, C, threadIdx.x, blockDim.x,
+                                                whole ? CP : a.nk_chunks * L);
+                }
+            if (MODEL) for (int c = lane; c < CPP; c += 32) bw[c] = 0.0f;
             __syncthreads();
         }
         const float* nbeta = a.nbeta + (size_t)set * R;
@@ -522,7 +541,8 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                 kx.use_bw = false;
                 if (FACT) tabA = a.tab + ((size_t)set * R + (r - 1)) * 4 * CP;
                 if (a.cta_tabs) {
-                    kx.T = tabs + (size_t)(FACT ? r - 1 : 0) * 2 * CP;
+                    const int rt = FACT ? r - 1 : 0;
+                    kx.T = rt < a.n_tab_full ? tabs + (size_t)rt * TF : tabs + (size_t)a.n_tab_full * TF + (size_t)(rt - a.n_tab_full) * TK;
                 } else {                                             // stage this round's table (trial-invariant vectors) for this warp
                     __syncwarp();
                     stage_round_table<LC, FACT>(wtab, a, tabA, pwf, CP, C, lane, 32);
@@ -535,10 +555,10 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                         if (mx > 0) {
                             kx.use_bw = true;
                             const float inv = 1.0f / (float)mx;
-                            for (int c = lane; c < C; c += 32) bw[c] = (float)prev_tally[c] * inv * bw_strength;
+                            for (int c = lane; c < C; c += 32) bw[pad_c<LC>(c)] = (float)prev_tally[c] * inv * bw_strength;
                             __syncwarp();
                             float s = 0.f;                                       // bandwagon of chunk `lane`, then prefix over chunks
-                            if (lane < nch) for (int c = lane * L; c < (lane + 1) * L; ++c) s += bw[c];
+                            if (lane < nch) for (int c = lane * L; c < (lane + 1) * L; ++c) s += bw[pad_c<LC>(c)];
 #pragma unroll
                             for (int off = 1; off < 32; off <<= 1) {
                                 const float o = __shfl_up_sync(CSIM_FULL, s, off);
@@ -575,7 +595,7 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                             }
                             // phase 1: nothing but the pair arithmetic, its operand loads and one prefix store per elector
                             const float* tc = kx.T;
-                            const int tstep = LC == 8 ? 16 : L;
+                            const int tstep = LC == 8 ? 20 : L;
                             float* pc = pref + lane;                                    // [j][t][lane]
                             if (LC == 8 && FACT && CSIM_DENSE_PIPELINE) {
                                 // software-pipelined: chunk j + 1's operands are in flight while chunk j is evaluated (the load past the
@@ -585,7 +605,7 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
 #pragma unroll 2
                                 for (int j = 0; j < nch; ++j) {
                                     const ulonglong2 b0 = nb0, c0 = nc0, b1 = nb1, c1 = nc1;
-                                    t4 += 4;
+                                    t4 += 5;                                                     // 80 bytes per chunk
                                     nb0 = t4[0]; nc0 = t4[1]; nb1 = t4[2]; nc1 = t4[3];
                                     chunk_math8<NE>(b0, c0, b1, c1, Re, acc);
 #pragma unroll
@@ -630,7 +650,7 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                         const Elector32 el = load_elector(e, sticky_live);
                         const Corr32 cr = corrections32<LC, MODEL, FACT>(kx, e, el);
                         const float xe1[1] = {el.x}, Re1[1] = {el.R};
-                        const int tstep = LC == 8 ? 16 : L;
+                        const int tstep = LC == 8 ? 20 : L;
                         float* cl = pref + eli * nch;                // this elector's chunk sums, then prefixes (m units)
                         __syncwarp();
                         if (act) {
@@ -660,7 +680,7 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                         const float P0 = kx.T[o0], X0 = kx.T[o0 + kx.xoff], P1 = kx.T[o1], X1 = kx.T[o1 + kx.xoff];
                         const int g0 = reg[0], g1 = reg[1];
                         float f0 = 0.f, f1 = 0.f;
-                        if (MODEL && kx.use_bw) { f0 = bw[0]; f1 = bw[1]; }
+                        if (MODEL && kx.use_bw) { f0 = bw[pad_c<LC>(0)]; f1 = bw[pad_c<LC>(1)]; }
                         const float bonus = kx.bonus, nb = kx.nb, st1p = kx.st1p;
                         auto play = [&](int e, uint32_t wa) {
                             const float u = u24_from_word(wa);

@@ -11,12 +11,17 @@ static csim_status launch_dense32_t(csim_ctx* c, Dense32Args& a, cudaStream_t st
     const size_t budget = (size_t)(220 * 1024) / CSIM_MINB;                        // CSIM_MINB CTAs per SM
     auto fit = [&](size_t cta, size_t warp) { int w = 8; while (w > 0 && cta + warp * w > budget) --w; return w; };
     const int n_tab_shared = FACT ? R : 1;                                        // (R == 0: no round is ever played, nothing to stage)
-    const size_t ctaA = dense32_cta_smem(a.nch, a.L, G, n_tab_shared), warpA = dense32_warp_smem(E, a.nch, a.L, a.kmax, MODEL, false);
+    // rounds beyond a.n_tab_full are run-off rounds in every set of the batch: they only read the first kmax candidates
+    const int n_full = (FACT && LC == 8) ? std::min(a.n_tab_full, n_tab_shared) : n_tab_shared;
+    const int nk = (a.kmax + 7) / 8;
+    const size_t ctaA = dense32_cta_smem(a.nch, a.L, G, n_full, n_tab_shared - n_full, nk), warpA = dense32_warp_smem(E, a.nch, a.L, a.kmax, MODEL, false);
     const size_t ctaB = dense32_cta_smem(a.nch, a.L, G, 0), warpB = dense32_warp_smem(E, a.nch, a.L, a.kmax, MODEL, true);
     const int wA = fit(ctaA, warpA), wB = FACT ? fit(ctaB, warpB) : 0;
     const bool shared_tabs = getenv("CSIM_DENSE_WARPTAB") == nullptr ? (wA >= wB && wA > 0) : !(FACT && wB > 0);
     a.cta_tabs = shared_tabs ? 1 : 0;
     a.n_tab = shared_tabs ? n_tab_shared : 0;
+    a.n_tab_full = shared_tabs ? n_full : 0;
+    a.nk_chunks = nk;
     a.cta_smem = shared_tabs ? ctaA : ctaB;
     a.warp_smem = shared_tabs ? warpA : warpB;
     int wpc = shared_tabs ? wA : wB;
@@ -25,7 +30,7 @@ static csim_status launch_dense32_t(csim_ctx* c, Dense32Args& a, cudaStream_t st
         while (wpc > 1 && a.cta_smem + a.warp_smem * wpc > 220 * 1024) --wpc;
         if (a.cta_smem + a.warp_smem * wpc > 220 * 1024) {
             if (shared_tabs && FACT) {                                           // the shared tables themselves are too large: per-warp tables
-                a.cta_tabs = 0; a.n_tab = 0; a.cta_smem = ctaB; a.warp_smem = warpB;
+                a.cta_tabs = 0; a.n_tab = 0; a.n_tab_full = 0; a.cta_smem = ctaB; a.warp_smem = warpB;
                 wpc = 8;
                 while (wpc > 1 && a.cta_smem + a.warp_smem * wpc > 220 * 1024) --wpc;
             }
@@ -95,6 +100,11 @@ csim_status launch_dense32(csim_ctx* c, const csim_run_args* ra, const std::vect
     int kmax = 1;
     for (const DevSet& s : hs) kmax = std::max(kmax, s.k);
     a.kmax = kmax;
+    // the rounds that can be full-field in SOME set of the batch: once a run-off exists (k > 0) every round after
+    // max(runoff_threshold_rounds, 1) is a run-off round (simulate.py:183-186)
+    a.n_tab_full = 1;
+    for (const DevSet& s : hs) a.n_tab_full = std::max(a.n_tab_full, s.k > 0 ? std::min(b.R, std::max(s.rr, 1)) : b.R);
+    a.nk_chunks = 1;
     // factorised exponential: needs beta >= 0 and e^{+-beta x'} comfortably inside fp32 range
     bool fact = getenv("CSIM_DENSE_MUFU") == nullptr;
     for (double be : hb) if (!(be >= 0.0) || !(be * c->x_half <= 26.0)) fact = false;   // e^{3 beta x'} must stay finite in fp32
