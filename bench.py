@@ -272,19 +272,23 @@ def main():
         name = eng.last_run_info()[0:2]
         l0 = eng.stats()[0]
         tev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        t_rounds, k_ms = 0, 0.0
-        for i in range(steps):
-            flush.zero_()
-            tev[i][0].record()
+        rounds_dev = torch.zeros((), dtype=torch.int64, device=dev)
+        for i in range(steps):                 # all steps are ENQUEUED back to back: no host round trip between them (a per-step
+            flush.zero_()                      # host sync lets the ranks drift apart by their launch latencies, which the all-reduce
+            tev[i][0].record()                 # then bills to the faster rank: 2.5 ms per 8 ms step at 2 GPUs)
             step(base + warm + i, engine=engine, wiring=wiring, p=p, precision=precision, b=b, sets=sets)
             tev[i][1].record()
-            tev[i][1].synchronize()
-            k_ms += eng.stats()[1]
-            t_rounds += int(b.totals.view(n_sets, 2)[:, 0].sum().item())       # already summed over ranks by the step's all-reduce
-        l1 = eng.stats()[0]
+            rounds_dev += b.totals.view(n_sets, 2)[:, 0].sum()                 # already summed over ranks by the step's all-reduce
         barrier()
+        k_ms = eng.stats()[1] * steps                                          # the trial kernel of the last step (every step is the same size)
+        t_rounds = int(rounds_dev.item())
+        l1 = eng.stats()[0]
         tt = torch.tensor([sum(a.elapsed_time(c) for a, c in tev), k_ms], dtype=torch.float64, device=dev)
+        per_rank = [round(tt[0].item() / steps, 4)]
         if world > 1:
+            every = [torch.zeros_like(tt) for _ in range(world)]
+            dist.all_gather(every, tt)
+            per_rank = [round(x[0].item() / steps, 4) for x in every]
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = tt[0].item()
         trials = b.n_sims_local * world * n_sets * steps
@@ -292,7 +296,7 @@ def main():
         return {"value": float(t_rounds) * Eb / (ms * 1e-3), "unit": "elector-rounds/s", "conclaves_per_sec": trials / (ms * 1e-3),
                 "ms_per_step": ms / steps, "trial_kernel_ms_per_step": tt[1].item() / steps, "steps": steps,
                 "trials_per_step": trials // steps, "mean_rounds": float(t_rounds) / trials, "engine_ran": name[0], "precision_ran": name[1],
-                "gpu_launches": int(l1 - l0)}
+                "gpu_launches": int(l1 - l0), "rank_ms_per_step": per_rank}
 
     if args.only:
         sel = {"dense": (ENGINE_DENSE, WIRING_REF_CLI, None), "auto": (ENGINE_AUTO, WIRING_REF_CLI, None), "table": (ENGINE_TABLE, WIRING_REF_CLI, None),

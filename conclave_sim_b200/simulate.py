@@ -121,15 +121,16 @@ def run_simulations(elector_data_full: pd.DataFrame, model_params: Dict[str, Any
                     device: Optional[int] = None, precision: Optional[str] = None, engine: Optional[str] = None,
                     want_final_votes: bool = False, want_round_tallies: bool = False,
                     uniform_tapes: Optional[np.ndarray] = None, devices=None, workers: Optional[int] = None,
-                    distributed: Optional[bool] = None) -> RunResult:
+                    distributed: Optional[bool] = None, gather_rows: bool = True) -> RunResult:
     """All trials of one parameter set in one batch (replaces src/simulate.py:330-351).
 
     One device: one launch.  `devices` (count / list / "all", or `workers` read as a device count — resolve_devices): the trials are
     sharded over the devices by disjoint sim-id ranges from this ONE process (csim_group_run: one NCCL all-reduce of the
     histograms, rows concatenated on the host).  Inside an initialised torch.distributed job (torchrun, one process per GPU;
     `distributed` None = detect): this rank runs its shard on its LOCAL_RANK device, the histograms are all-reduced over NCCL
-    through the C ABI (csim_allreduce_hists) and rank 0 receives every rank's rows; the other ranks get their own rows and the
-    global histograms.  Whatever the split, the results equal a single-device run with the same seed."""
+    through the C ABI (csim_allreduce_hists) and rank 0 receives every rank's rows (gather_rows=False: every rank keeps only its
+    own rows); the other ranks get their own rows and the global histograms.  Whatever the split, the results equal a
+    single-device run with the same seed."""
     wiring = wiring or RUNTIME["wiring"]
     precision = precision or RUNTIME["precision"]
     engine = engine or RUNTIME["engine"]
@@ -143,7 +144,7 @@ def run_simulations(elector_data_full: pd.DataFrame, model_params: Dict[str, Any
                                          fatigue_threshold_rounds=fatigue_threshold_rounds,
                                          fatigue_vote_share_threshold=fatigue_vote_share_threshold, fatigue_top_n_immune=fatigue_top_n_immune,
                                          enable_stop_candidate=enable_stop_candidate, sim_id_begin=sim_id_begin, seed=seed, wiring=wiring,
-                                         precision=precision, engine=engine)
+                                         precision=precision, engine=engine, gather_rows=gather_rows)
     devs = resolve_devices(RUNTIME["devices"] if devices is None else devices, device, workers)
     eng = get_group(devs) if len(devs) > 1 else get_engine(devs[0])
     x, g, pap = roster_arrays(elector_data_full)
@@ -179,13 +180,14 @@ def load_tapes(path: str, num_simulations: int, max_rounds: int, n_electors: int
     return a[:want[0]]
 
 
-_torchrun_state: Dict[str, Any] = {}
+_torchrun_state: Dict[Any, Any] = {}
 
 
 def _run_simulations_torchrun(tr, elector_data_full, model_params, num_simulations, *, sim_id_begin, seed, wiring, precision, engine,
-                              **engine_kw) -> RunResult:
+                              gather_rows: bool = True, **engine_kw) -> RunResult:
     """One rank of a torchrun job: its contiguous shard of the sim ids on its LOCAL_RANK device, ONE NCCL all-reduce of the
-    histograms through the C ABI, every rank's rows gathered on rank 0 (the rank that writes the CSV)."""
+    histograms through the C ABI, and (gather_rows) every rank's per-trial rows gathered over NVLink on rank 0 — the rank that
+    writes the CSV — which copies them to page-locked host arrays in one pass.  Device buffers are kept between calls."""
     import torch
     import torch.distributed as tdist
     from .dist import DeviceBatch, shard_range, csim_comm
@@ -198,28 +200,59 @@ def _run_simulations_torchrun(tr, elector_data_full, model_params, num_simulatio
         box = [_seed() if rank == 0 else None]
         tdist.broadcast_object_list(box, src=0)
         seed = int(box[0])
-    begin, count = shard_range(num_simulations, rank, world)
+    n = int(num_simulations)
+    begin, count = shard_range(n, rank, world)
     torch.cuda.set_device(local_rank)
     R = int(params.max_rounds)
-    batch = DeviceBatch(eng, 1, count, R, want_reason=True, comm=csim_comm(eng))
+    mx = shard_range(n, 0, world)[1]                                   # the largest shard (ranks differ by at most one trial)
+    key = (local_rank, n, world, R)
+    st = _torchrun_state.get(key)
+    if st is None:
+        _torchrun_state.clear()                                         # one job shape at a time: release the previous buffers
+        batch = DeviceBatch(eng, 1, mx, R, want_reason=True, comm=csim_comm(eng))     # padded to the largest shard: equal-size gathers
+        dev = batch.winner.device
+        recv = None
+        if rank == 0 and gather_rows:
+            recv = {"winner": torch.empty(world * mx, dtype=torch.int32, device=dev), "rounds": torch.empty(world * mx, dtype=torch.int32, device=dev),
+                    "reason": torch.empty(world * mx, dtype=torch.uint8, device=dev)}
+        st = _torchrun_state[key] = (batch, recv)
+    batch, recv = st
+    batch.n_sims_local = count                                          # this rank plays `count` of the mx slots
     batch.run([params], sim_id_begin=int(sim_id_begin) + begin, seed=seed, wiring=_WIRING[wiring], engine=_ENGINE[engine],
-              precision=_PRECISION[precision], job_sims=int(num_simulations))
+              precision=_PRECISION[precision], job_sims=n)
+    batch.n_sims_local = mx
     wh, rh, tot = batch.hists()
-    # rows: every rank's (winner, rounds, reason) to rank 0, in sim-id order
-    counts = [shard_range(num_simulations, r, world)[1] for r in range(world)]
-    mx = max(counts)
-    pack = torch.zeros(mx, 3, dtype=torch.int32, device=batch.winner.device)
-    if count:
-        pack[:count, 0] = batch.winner; pack[:count, 1] = batch.rounds; pack[:count, 2] = batch.reason.to(torch.int32)
-    got = [torch.empty_like(pack) for _ in range(world)] if rank == 0 else None
-    tdist.gather(pack, got, dst=0)
-    if rank == 0:
-        rows = torch.cat([t[:c] for t, c in zip(got, counts)]).cpu().numpy()
-    else:
-        rows = pack[:count].cpu().numpy()
     name, prec, fell = eng.last_run_info(requested_precision=_PRECISION[precision]) if count else ("", "", False)
-    return RunResult(np.ascontiguousarray(rows[:, 0]), np.ascontiguousarray(rows[:, 1]), rows[:, 2].astype(np.uint8), None, None,
-                     wh.copy(), rh.copy(), tot.copy(), eng.n_electors, eng.stats()[1], name, prec, fell, (local_rank,), (eng.stats()[1],))
+    counts = [shard_range(n, r, world)[1] for r in range(world)]
+    out = {}
+    if gather_rows:
+        for nm, t in (("winner", batch.winner), ("rounds", batch.rounds), ("reason", batch.reason)):
+            if recv is not None and rank == 0:
+                tdist.gather(t, [recv[nm][r * mx:(r + 1) * mx] for r in range(world)], dst=0)
+            else:
+                tdist.gather(t, None, dst=0)
+    if rank == 0 and gather_rows:
+        for nm, dt in (("winner", np.int32), ("rounds", np.int32), ("reason", np.uint8)):
+            host = eng._pinned.array(n, dt)                             # page-locked: the copies below run at full PCIe speed
+            ht = torch.from_numpy(host) if n else None
+            pos = 0
+            if n and all(c == mx for c in counts):
+                ht.copy_(recv[nm][:n])
+            else:
+                for r, c in enumerate(counts):
+                    if c:
+                        ht[pos:pos + c].copy_(recv[nm][r * mx:r * mx + c])
+                    pos += c
+            out[nm] = host
+    else:                                                               # this rank's own rows
+        for nm, t, dt in (("winner", batch.winner, np.int32), ("rounds", batch.rounds, np.int32), ("reason", batch.reason, np.uint8)):
+            host = eng._pinned.array(count, dt)
+            if count:
+                torch.from_numpy(host).copy_(t[:count])
+            out[nm] = host
+    ms = eng.stats()[1]
+    return RunResult(out["winner"], out["rounds"], out["reason"], None, None, wh.copy(), rh.copy(), tot.copy(), eng.n_electors, ms, name, prec, fell,
+                     (local_rank,), (ms,))
 
 
 def _run_single_simulation_worker(sim_id: int, elector_data_full: pd.DataFrame, model_params: Dict[str, Any],
