@@ -2,7 +2,7 @@
 
 Only tests/, __graft_entry__ (build, smoke) and bench.py's cpu_baseline / --impl reference
 legs may import this.  The struct mirror below is deliberately independent of the product's
-own binding (conclave_sim_b200/_cabi.py); tests/test_cabi_symbols.py checks both against the header.
+own binding (conclave_sim_b200/_cabi.py); tests/test_host_cpu.py::test_library_exports_every_declared_symbol checks both against the header.
 """
 from __future__ import annotations
 
