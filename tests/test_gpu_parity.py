@@ -427,6 +427,19 @@ def test_sweep_stats_and_legacy_shim(eng):
     rdf, st = S.run_monte_carlo_simulation(16, legacy, {"beta_weight": 0.1}, max_rounds=30)
     assert list(rdf.columns) == ["simulation_id", "winner_id", "rounds_taken", "status"] and len(rdf) == 16
     assert "success_rate" in st and "avg_rounds_success" in st
+    # the shim is the new engine behind the old schema (tests/test_simulate.py:51-68 of the reference): same trials as
+    # run_simulations under the same Philox key, winner ids in the caller's id type, status as the old code named it
+    S.RUNTIME.update(seed=4242)
+    rdf, st = S.run_monte_carlo_simulation(200, legacy, {"beta_weight": 0.1}, max_rounds=30)
+    df3 = legacy.assign(elector_id=legacy["elector_id"].astype(str)).set_index("elector_id").assign(region=["_r0", "_r1", "_r2"])
+    ref3 = S.run_simulations(df3, {"initial_beta_weight": 0.1}, 200, max_rounds=30, supermajority_threshold=S.REQUIRED_MAJORITY_FRACTION,
+                             runoff_threshold_rounds=5, runoff_candidate_count=2, seed=4242)
+    assert rdf["rounds_taken"].tolist() == ref3.rounds.tolist()
+    assert [(-1 if w is None or w != w else ["1", "2", "3"].index(str(w))) for w in rdf["winner_id"]] == ref3.winner.tolist()
+    assert (rdf["status"] == np.where(ref3.winner >= 0, "Success", "Max rounds reached")).all()
+    assert st["success_rate"] == float((ref3.winner >= 0).mean()) and st["num_simulations"] == 200
+    assert st["winner_counts"] == {str(i + 1): int(c) for i, c in enumerate(ref3.winner_hist[0, :3]) if c > 0}
+    S.RUNTIME.update(seed=None)
 
 
 @pytest.mark.parametrize("case", list(G.subset_cases()), ids=lambda c: c["name"])
