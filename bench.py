@@ -208,6 +208,7 @@ def main():
     ap.add_argument("--trials-per-gpu", type=int, default=1_250_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the N = 1 `configs` block (cfg-4 / cfg-5 / fp64 engines)")
+    ap.add_argument("--no-reduce", action="store_true", help="diagnostic: skip the histogram all-reduce in --only mode (each rank's own step time)")
     ap.add_argument("--only", default=None, help="profiling aid: run only the timed steps of ONE engine (dense|auto|table|prefix|prefix_model|full) and exit")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -246,6 +247,8 @@ def main():
     n_local = args.trials_per_gpu
     n_global = n_local * world
     comm = csim_comm(eng)                                 # ncclComm_t made through the C ABI (None on one GPU): the data path's only collective
+    if os.environ.get("CSIM_BENCH_TORCH_ALLREDUCE"):      # diagnostic: torch.distributed's all_reduce instead
+        comm = None
     batch = DeviceBatch(eng, 1, n_local, R, want_reason=True, comm=comm)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
@@ -273,22 +276,31 @@ def main():
         l0 = eng.stats()[0]
         tev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         rounds_dev = torch.zeros((), dtype=torch.int64, device=dev)
-        for i in range(steps):                 # all steps are ENQUEUED back to back: no host round trip between them (a per-step
-            flush.zero_()                      # host sync lets the ranks drift apart by their launch latencies, which the all-reduce
-            tev[i][0].record()                 # then bills to the faster rank: 2.5 ms per 8 ms step at 2 GPUs)
-            step(base + warm + i, engine=engine, wiring=wiring, p=p, precision=precision, b=b, sets=sets)
+        t_host0 = time.perf_counter()
+        for i in range(steps):
+            flush.zero_()
+            if world > 1:                      # untimed, like the flush: every rank starts the step together.  Without it rank 0 enters
+                barrier()                      # each step ~2 ms late (its host-side gap between steps, rank_untimed_gap_ms) and the
+            tev[i][0].record()                 # all-reduce bills that wait to every other rank's step (8.5 vs 10.3 ms at 2 and 8 GPUs)
+            step(base + warm + i, engine=engine, wiring=wiring, p=p, precision=precision, b=b, sets=sets, reduce=not args.no_reduce)
             tev[i][1].record()
             rounds_dev += b.totals.view(n_sets, 2)[:, 0].sum()                 # already summed over ranks by the step's all-reduce
+        host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / steps            # host time to ENQUEUE a step (it runs ahead of the GPU)
         barrier()
         k_ms = eng.stats()[1] * steps                                          # the trial kernel of the last step (every step is the same size)
         t_rounds = int(rounds_dev.item())
         l1 = eng.stats()[0]
-        tt = torch.tensor([sum(a.elapsed_time(c) for a, c in tev), k_ms], dtype=torch.float64, device=dev)
+        gap = sum(tev[i][1].elapsed_time(tev[i + 1][0]) for i in range(steps - 1)) / max(1, steps - 1)     # untimed: L2 flush + bookkeeping
+        tt = torch.tensor([sum(a.elapsed_time(c) for a, c in tev), k_ms, gap, host_enqueue_ms], dtype=torch.float64, device=dev)
         per_rank = [round(tt[0].item() / steps, 4)]
+        per_rank_gap = [round(gap, 4)]
+        per_rank_host = [round(host_enqueue_ms, 4)]
         if world > 1:
             every = [torch.zeros_like(tt) for _ in range(world)]
             dist.all_gather(every, tt)
             per_rank = [round(x[0].item() / steps, 4) for x in every]
+            per_rank_gap = [round(x[2].item(), 4) for x in every]
+            per_rank_host = [round(x[3].item(), 4) for x in every]
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = tt[0].item()
         trials = b.n_sims_local * world * n_sets * steps
@@ -296,7 +308,7 @@ def main():
         return {"value": float(t_rounds) * Eb / (ms * 1e-3), "unit": "elector-rounds/s", "conclaves_per_sec": trials / (ms * 1e-3),
                 "ms_per_step": ms / steps, "trial_kernel_ms_per_step": tt[1].item() / steps, "steps": steps,
                 "trials_per_step": trials // steps, "mean_rounds": float(t_rounds) / trials, "engine_ran": name[0], "precision_ran": name[1],
-                "gpu_launches": int(l1 - l0), "rank_ms_per_step": per_rank}
+                "gpu_launches": int(l1 - l0), "rank_ms_per_step": per_rank, "rank_untimed_gap_ms": per_rank_gap, "rank_host_enqueue_ms_per_step": per_rank_host}
 
     if args.only:
         sel = {"dense": (ENGINE_DENSE, WIRING_REF_CLI, None), "auto": (ENGINE_AUTO, WIRING_REF_CLI, None), "table": (ENGINE_TABLE, WIRING_REF_CLI, None),

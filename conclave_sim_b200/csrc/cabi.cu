@@ -57,6 +57,7 @@ extern "C" csim_status csim_create(csim_ctx** out, int device) {
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
     cudaEventCreateWithFlags(&c->ev_busy, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming);
     *out = c;
     return CSIM_OK;
 }
@@ -73,6 +74,8 @@ extern "C" csim_status csim_destroy(csim_ctx* c) {
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_busy) cudaEventDestroy(c->ev_busy);
+    if (c->ev_stage) cudaEventDestroy(c->ev_stage);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
     delete c;
     return CSIM_OK;
 }
@@ -300,10 +303,26 @@ extern "C" csim_status csim_run(csim_ctx* c, const csim_run_args* ra) {
     CU_TRY(c->sets.reserve(sizeof(DevSet) * hs.size()));
     CU_TRY(c->betas.reserve(sizeof(double) * hb.size()));
     CU_TRY(c->nbeta.reserve(sizeof(float) * hnb.size()));
-    CU_TRY(cudaMemcpyAsync(c->sets.p, hs.data(), sizeof(DevSet) * hs.size(), cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemcpyAsync(c->betas.p, hb.data(), sizeof(double) * hb.size(), cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemcpyAsync(c->nbeta.p, hnb.data(), sizeof(float) * hnb.size(), cudaMemcpyHostToDevice, st));
-    // the vectors above are pageable: the async copies have completed their host read on return
+    {   // through page-locked staging (see csim_ctx::h_stage): wait only for the PREVIOUS call's copies out of it, never for its kernels
+        const size_t b_sets = (sizeof(DevSet) * hs.size() + 15) & ~(size_t)15, b_betas = (sizeof(double) * hb.size() + 15) & ~(size_t)15;
+        const size_t b_nb = sizeof(float) * hnb.size(), need = b_sets + b_betas + b_nb;
+        if (c->stage_valid) CU_TRY(cudaEventSynchronize(c->ev_stage));
+        if (need > c->h_stage_cap) {
+            if (c->h_stage) cudaFreeHost(c->h_stage);
+            c->h_stage = nullptr; c->h_stage_cap = 0;
+            CU_TRY(cudaHostAlloc(&c->h_stage, need * 2, cudaHostAllocDefault));
+            c->h_stage_cap = need * 2;
+        }
+        char* hp = (char*)c->h_stage;
+        memcpy(hp, hs.data(), sizeof(DevSet) * hs.size());
+        memcpy(hp + b_sets, hb.data(), sizeof(double) * hb.size());
+        memcpy(hp + b_sets + b_betas, hnb.data(), b_nb);
+        CU_TRY(cudaMemcpyAsync(c->sets.p, hp, sizeof(DevSet) * hs.size(), cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(c->betas.p, hp + b_sets, sizeof(double) * hb.size(), cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(c->nbeta.p, hp + b_sets + b_betas, b_nb, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaEventRecord(c->ev_stage, st));
+        c->stage_valid = true;
+    }
 
     BatchDev b;
     b.sets = (const DevSet*)c->sets.p; b.n_sets = ra->n_param_sets; b.R = R; b.n_sims = ra->n_sims;

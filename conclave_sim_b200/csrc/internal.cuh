@@ -73,6 +73,11 @@ struct csim_ctx {
     DevBuf o_winner, o_rounds, o_reason, o_final, o_tallies, o_whist, o_rhist, o_totals, i_tape;
     // prob-matrix staging
     DevBuf p_prev, p_cnt, p_fat, p_shares, p_bw, p_out, p_cand, p_pref;
+    // page-locked staging of the per-batch parameter tables: the copies to the device are then truly asynchronous, so a
+    // device-buffer csim_run returns as soon as its work is enqueued and the host can run ahead of the GPU (copies from
+    // pageable memory block until everything earlier in the stream has finished)
+    void* h_stage = nullptr; size_t h_stage_cap = 0;
+    cudaEvent_t ev_stage = nullptr; bool stage_valid = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_busy = nullptr;      // recorded behind the last work a call enqueued: the next call's stream waits on it
     bool ev_valid = false, busy_valid = false;
