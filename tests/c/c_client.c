@@ -1,7 +1,9 @@
 /* A plain C99 client of include/conclave_b200.h — no Python, no torch: what a maintainer binding the library from C
  * (or through cgo / JNI / any FFI) would write.  Uploads a synthetic roster, runs one batch of trials on the engine
  * given on the command line and prints "winner rounds" per trial followed by the histograms.
- * usage: c_client <n_electors> <n_trials> <engine 0..3> <wiring 0|1> <precision 0|1> <seed> */
+ * With a 7th argument (a device count) the same batch goes through csim_group_*: one process, that many GPUs, trials sharded
+ * by sim id, histograms summed by NCCL — and the output must be identical to the single-context run.
+ * usage: c_client <n_electors> <n_trials> <engine 0..3> <wiring 0|1> <precision 0|1> <seed> [n_devices] */
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -18,11 +20,12 @@
     } while (0)
 
 int main(int argc, char** argv) {
-    if (argc != 7) { fprintf(stderr, "usage: %s E n engine wiring precision seed\n", argv[0]); return 1; }
+    if (argc != 7 && argc != 8) { fprintf(stderr, "usage: %s E n engine wiring precision seed [n_devices]\n", argv[0]); return 1; }
     const int E = atoi(argv[1]);
     const uint64_t n = strtoull(argv[2], NULL, 10);
     const int engine = atoi(argv[3]), wiring = atoi(argv[4]), precision = atoi(argv[5]);
     const uint64_t seed = strtoull(argv[6], NULL, 10);
+    const int n_devices = argc == 8 ? atoi(argv[7]) : 0;          /* 0: one context on device 0, no group */
 
     /* deterministic synthetic roster (a tiny LCG: the Python side of the test regenerates the same numbers) */
     double* x = malloc(sizeof(double) * E);
@@ -36,8 +39,22 @@ int main(int argc, char** argv) {
     }
 
     csim_ctx* ctx = NULL;
-    CHECK(csim_create(&ctx, 0));
-    CHECK(csim_upload_roster(ctx, E, x, region, pap));
+    csim_group* grp = NULL;
+    if (n_devices > 0) {
+        int32_t devs[64], visible = 0;
+        CHECK(csim_device_count(&visible));
+        if (n_devices > 64 || n_devices > visible) {
+            fprintf(stderr, "%d devices asked, %d visible\n", n_devices, (int)visible);
+            return 3;
+        }
+        for (int i = 0; i < n_devices; ++i) devs[i] = i;
+        CHECK(csim_group_create(&grp, devs, n_devices));
+        CHECK(csim_group_upload_roster(grp, E, x, region, pap));
+        if (csim_group_size(grp) != n_devices) { fprintf(stderr, "group size %d\n", (int)csim_group_size(grp)); return 3; }
+    } else {
+        CHECK(csim_create(&ctx, 0));
+        CHECK(csim_upload_roster(ctx, E, x, region, pap));
+    }
 
     csim_params p;
     memset(&p, 0, sizeof p);                       /* README parameters (BASELINE config 2) */
@@ -60,7 +77,14 @@ int main(int argc, char** argv) {
     a.sim_id_begin = 1000; a.n_sims = n; a.seed = seed;
     a.winner = winner; a.rounds = rounds; a.winner_hist = whist; a.rounds_hist = rhist; a.totals = totals;
     a.buffers_on_device = 0; a.stream = NULL;
-    CHECK(csim_run(ctx, &a));
+    if (grp) {
+        float ms[64];
+        CHECK(csim_group_run(grp, &a, ms));
+        for (int i = 0; i < n_devices; ++i)
+            if (!(ms[i] >= 0.0f)) { fprintf(stderr, "device %d kernel time %f\n", i, ms[i]); return 3; }
+    } else {
+        CHECK(csim_run(ctx, &a));
+    }
 
     for (uint64_t i = 0; i < n; ++i) printf("%d %d\n", (int)winner[i], (int)rounds[i]);
     printf("totals %lld %lld\n", (long long)totals[0], (long long)totals[1]);
@@ -72,10 +96,11 @@ int main(int argc, char** argv) {
 
     /* an unsupported request must come back as a status + message, never as a silent fallback */
     a.precision = CSIM_FP64; a.engine = CSIM_ENGINE_PREFIX;
-    csim_status st = csim_run(ctx, &a);
+    csim_status st = grp ? csim_group_run(grp, &a, NULL) : csim_run(ctx, &a);
     printf("prefix+fp64 -> %d (%s)\n", (int)st, st == CSIM_OK ? "" : csim_last_error());
 
-    CHECK(csim_destroy(ctx));
+    if (grp) CHECK(csim_group_destroy(grp));
+    else CHECK(csim_destroy(ctx));
     free(x); free(region); free(pap); free(winner); free(rounds); free(whist); free(rhist);
     return 0;
 }

@@ -338,3 +338,56 @@ def test_cli_end_to_end_equals_the_reference_main(tmp_path, case):
     _cli(args)
     assert open(tmp_path / "o.csv", "rb").read() == open(os.path.join(gold, case["name"] + ".csv"), "rb").read()
     assert open(tmp_path / "o.json", "rb").read() == open(os.path.join(gold, case["name"] + ".json"), "rb").read()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# a C host over the group entry points (no Python, no torch in the process that drives the GPUs)
+# ---------------------------------------------------------------------------------------------------------------------
+def _c_client(tmp_path):
+    from conclave_sim_b200._cabi import LIB_PATH
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "c_client"
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "c", "c_client.c"), LIB_PATH, "-Wl,-rpath," + os.path.dirname(LIB_PATH), "-o", str(exe)],
+                   check=True)
+    return str(exe)
+
+
+def _c_client_group_equals_single(tmp_path, n_devices, n=3001):
+    """tests/c/c_client.c with a device count drives csim_group_create / upload_roster / run / destroy from plain C; its whole
+    output (per-trial rows, totals, both histograms, the status of an unsupported request) is the single-context run's."""
+    from conclave_sim_b200._cabi import nccl_library_path
+    exe = _c_client(tmp_path)
+    env = {k: v for k, v in os.environ.items() if k != "NCCL_DEBUG"}       # (NCCL's version banner goes to stdout otherwise)
+    lib = nccl_library_path()
+    if lib:
+        env["CSIM_NCCL_LIB"] = lib                    # the NCCL this image's torch ships; the system copy works as well
+    for engine, wiring, precision in ((0, 0, 0), (1, 1, 0), (2, 0, 0), (2, 0, 1), (3, 1, 0), (4, 1, 0)):
+        base = [exe, "135", str(n), str(engine), str(wiring), str(precision), "20250507"]
+        one = subprocess.run(base, capture_output=True, text=True, env=env, timeout=600)
+        grp = subprocess.run(base + [str(n_devices)], capture_output=True, text=True, env=env, timeout=600)
+        assert one.returncode == 0, one.stderr
+        assert grp.returncode == 0, grp.stderr
+        a = one.stdout.strip().split("\n")
+        b = [ln for ln in grp.stdout.strip().split("\n") if not ln.startswith("NCCL version")]
+        assert len(a) == n + 4 and a == b, (engine, wiring, precision, [i for i, (u, v) in enumerate(zip(a, b)) if u != v][:5])
+
+
+def test_c_host_group_of_one_device(tmp_path):
+    _c_client_group_equals_single(tmp_path, 1)
+
+
+@need2
+def test_c_host_group_of_two_devices(tmp_path):
+    _c_client_group_equals_single(tmp_path, 2)
+
+
+@need2
+def test_c_host_group_of_all_devices(tmp_path):
+    _c_client_group_equals_single(tmp_path, n_gpus(), n=10007)
+
+
+def test_c_host_group_asks_for_too_many_devices(tmp_path):
+    exe = _c_client(tmp_path)
+    r = subprocess.run([exe, "135", "100", "0", "0", "0", "1", str(n_gpus() + 1)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 3 and "visible" in r.stderr
