@@ -380,14 +380,15 @@ def main():
     pairs_per_launch = tot_pairs / args.steps
     kern_s = (sum(kernel_ms) / args.steps) * 1e-3
     pair_rate = pairs_per_launch / kern_s
-    fact_peak_pairs = (peak_fact / 2.5 * 1e9) if peak_fact else FALLBACK_FP32_GINSTR * 1e9 / 2.5     # microbench body = 2.5 thread-instr per pair
+    fact_peak_pairs = (peak_fact / 2.0 * 1e9) if peak_fact else FALLBACK_FP32_GINSTR * 1e9 / 2.0     # pair body = 2 thread-instr per pair (1 FMUL2 + 2 FMNMX + 1 FADD2 per two pairs)
     out_bytes = n_local * 9 + (E + 1 + R + 1 + 2) * 8
     dig = ncu_digest("k_trials_dense32")
     roofline = {"bound": "fp32", "kernel": "k_trials_dense32<LC=8,MODEL=false,FACT=true>",
                 "achieved": pair_rate * 1e-9, "peak": fact_peak_pairs * 1e-9, "unit": "G pair-evaluations/s", "frac": pair_rate / fact_peak_pairs,
                 "algorithmic": f"{pairs_per_launch:.4g} (elector, candidate) pair evaluations per launch (E*C in full-field rounds, E*k in run-off "
                                f"rounds; SURVEY 8d) over the kernel's CUDA-event duration; peak = the rate at which this GPU retires the kernel's own "
-                               f"inner-loop pair body (2 FMUL2 + 2 FMNMX + FADD2 per two pairs, k_microbench<3>)",
+                               f"inner-loop pair body exactly as its SASS has it (1 FMUL2 + 2 FMNMX + 1 FADD2 per two pairs, k_microbench<3>; the round-1 "
+                               f"body with two FMUL2 — 1.007e13 pairs/s — was heavier than what the round-2 kernel executes and is no longer the denominator)",
                 "peak_source": peak_src, "kernel_ms_per_launch": kern_s * 1e3,
                 "algorithmic_equivalent_frac": pairs_per_launch * FP32_PER_PAIR / kern_s * 1e-9 / peak_fp32,
                 "algorithmic_equivalent_note": f"the canonical accounting of SURVEY 8d ({FP32_PER_PAIR} FP32 + {MUFU_PER_PAIR} MUFU per pair) against the measured "

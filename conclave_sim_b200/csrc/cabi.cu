@@ -67,7 +67,7 @@ extern "C" csim_status csim_destroy(csim_ctx* c) {
     DeviceGuard guard;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();             // nothing of this context may still be in flight when its buffers go
-    for (DevBuf* b : {&c->x64, &c->x32, &c->region, &c->pap, &c->sets, &c->betas, &c->nbeta, &c->W, &c->tab, &c->cdf64, &c->cdfk64, &c->cdf32, &c->cdfk32, &c->ptab, &c->accm, &c->o_winner, &c->o_rounds,
+    for (DevBuf* b : {&c->x64, &c->x32, &c->region, &c->pap, &c->sets, &c->betas, &c->nbeta, &c->W, &c->tab, &c->cdf64, &c->cdfk64, &c->cdf32, &c->cdfk32, &c->ptab, &c->accm, &c->work, &c->o_winner, &c->o_rounds,
                       &c->o_reason, &c->o_final, &c->o_tallies, &c->o_whist, &c->o_rhist, &c->o_totals, &c->i_tape,
                       &c->p_prev, &c->p_cnt, &c->p_fat, &c->p_shares, &c->p_bw, &c->p_out, &c->p_cand, &c->p_pref})
         b->release();
@@ -550,8 +550,8 @@ extern "C" csim_status csim_microbench(csim_ctx* c, int32_t kind, double* ginstr
         if (e != cudaSuccess) { cudaFree(sink); return fail(CSIM_ERR_CUDA, "microbench: %s", cudaGetErrorString(e)); }
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
-        // thread-instructions per loop iteration (kind 2: 8 pairs x {FADD,FMUL,MUFU,FFMA}; kind 3: 8 pairs = 4 x {2 FMUL2, 2 FMNMX, FADD2})
-        const double per_iter = kind == 2 ? 32.0 : (kind == 3 ? 20.0 : 8.0);
+        // thread-instructions per loop iteration (kind 2: 8 pairs x {FADD,FMUL,MUFU,FFMA}; kind 3: 8 pairs = 4 x {FMUL2, 2 FMNMX, FADD2})
+        const double per_iter = kind == 2 ? 32.0 : (kind == 3 ? 16.0 : 8.0);
         const double g = (double)grid * threads * iters * per_iter / (ms * 1e-3) * 1e-9;
         if (rep > 0) best = std::max(best, g);
     }

@@ -237,6 +237,36 @@ __device__ __forceinline__ void deal_electors_once(int lane, int E, int e_quad_e
     }
 }
 
+// ---------------------------------------------------------------------------
+// Dynamic trial scheduling of the warp-per-trial kernels.  Trials differ in length (6 ... max_rounds rounds), so a static
+// split leaves most SMs idle while the unluckiest warps finish (12 % of the warp slots of the round-2 dense kernel were
+// empty over its duration).  Instead: one 64-bit counter per parameter set in global memory (zeroed before the launch); a
+// warp takes the next `chunk` trials of the set its CTA is on with ONE atomicAdd by lane 0; a CTA walks the sets in a
+// rotated order (so that CTAs start on different sets), stages a set's tables once, and moves on when the set's counter has
+// run out.  Results never depend on the schedule: a trial's random stream is keyed by its sim id.
+// ---------------------------------------------------------------------------
+struct WorkQueue {
+    unsigned long long* next;   // [n_sets] next unclaimed trial of each set
+    int chunk;                  // trials a warp claims per fetch
+};
+
+__device__ __forceinline__ uint64_t warp_claim_trials(const WorkQueue& wq, int set, int lane) {
+    unsigned long long v = 0;
+    if (lane == 0) v = atomicAdd(wq.next + set, (unsigned long long)wq.chunk);
+    return __shfl_sync(CSIM_FULL, v, 0);
+}
+
+// the set a CTA visits in its si-th step, and whether that set still has unclaimed trials (thread 0 peeks; the caller
+// publishes the answer through shared memory around its own __syncthreads)
+__device__ __forceinline__ int cta_set_of_step(int si, int n_sets) {
+    const int set0 = (int)(((uint64_t)blockIdx.x * (uint64_t)n_sets) / gridDim.x);
+    const int set = set0 + si;
+    return set >= n_sets ? set - n_sets : set;
+}
+__device__ __forceinline__ bool set_exhausted(const WorkQueue& wq, int set, uint64_t n_sims) {
+    return *reinterpret_cast<volatile unsigned long long*>(wq.next + set) >= n_sims;
+}
+
 // The per-trial outputs every warp-per-trial kernel writes when its trial ends (winner / rounds / reason rows, the last
 // tally, the -1 padding of the per-round tallies beyond `rounds`, the two histograms of simulate.py:356-387).
 __device__ __forceinline__ void write_trial_outputs(const TrialOut& out, uint64_t t, int set, int C, int R, int lane, const int32_t* tally,

@@ -59,7 +59,7 @@ struct Dense32Args {
     int nch;                // number of chunks, nch * L >= C, nch <= 32
     int kmax;
     int warps_per_cta;
-    int tpi;                // trials per warp per work item
+    WorkQueue wq;           // dynamic trial scheduling (common.cuh)
     int cta_tabs;           // 1: the round tables of the whole parameter set are CTA-shared (n_tab rounds); 0: per warp, per round
     int n_tab;              // rounds staged per set when cta_tabs (FACT: R; MUFU form: 1 — its operands do not depend on the round)
     int n_tab_full;         // of those, the first n_tab_full are whole tables (the rounds that can be full-field); the later ones are
@@ -106,7 +106,7 @@ __host__ __device__ inline size_t dense32_cta_smem(int nch, int L, int G, int n_
 __host__ __device__ inline size_t dense32_warp_smem(int E, int nch, int L, int kmax, bool model, bool warp_tab) {
     const size_t CP = (size_t)nch * L, Ei = ((size_t)E + 3) & ~(size_t)3, n4 = ((size_t)nch + 3) & ~(size_t)3;
     size_t n = (warp_tab ? (size_t)dense32_tab_floats(nch, L) * 4 : 0) /*own round table*/ + (size_t)DENSE32_PREF_COLS * nch * 32 * 4 /*prefix columns*/ +
-               Ei * 4 /*tally*/ + (((size_t)kmax + 3) & ~(size_t)3) * 4 /*eff*/ + Ei /*mark*/;
+               Ei * 4 /*tally*/ + (((size_t)kmax + 3) & ~(size_t)3) * 4 /*eff*/ + Ei /*mark*/ + 16 + 2 * 32 * 16 /*wq, tailw: Philox words (16-byte aligned)*/;
     if (model) n += (size_t)dense32_cpp(nch, L) * 4 /*bw*/ + n4 * 4 /*bwp*/ + Ei * 4 * 2 /*prev_tally, votes*/;
     (void)CP;
     return (n + 15) & ~(size_t)15;
@@ -326,6 +326,13 @@ __device__ __forceinline__ void rescan8_scores(const LaneCtx32& k, int jstar, in
 #undef CSIM_RESCAN
 }
 
+// The draw of a row whose scores all vanished (model.py:447-449: the row becomes uniform INCLUDING self) — out of line, it is
+// (almost) never taken and its instructions should not sit in every draw.
+static __device__ __noinline__ int uniform_row_vote(float u, int C) {
+    const int j = (int)(u * (float)C);
+    return j < C ? j : C - 1;
+}
+
 // Phase 2: given the exponential-part prefix over chunks (pref[j * pstride], m units), draw the vote.
 template <int LC, bool MODEL, bool FACT, bool PROBE = false>
 __device__ __forceinline__ int finish_draw(const LaneCtx32& k, const float* pref, int pstride, int e, float u, const Elector32& el, const Corr32& cr) {
@@ -345,23 +352,25 @@ __device__ __forceinline__ int finish_draw(const LaneCtx32& k, const float* pref
         }
     }
     const float S = probe32<MODEL>(k, pref, pstride, rbrow, el.A, cr, nch - 1);
-    if (!(S > 0.0f)) {            // all scores vanished: the reference makes the row uniform INCLUDING self (model.py:447-449)
-        const int j = (int)(u * (float)C);
-        return j < C ? j : C - 1;
-    }
+    if (__builtin_expect(!(S > 0.0f), 0))          // all scores vanished: the reference makes the row uniform INCLUDING self (model.py:447-449)
+        return uniform_row_vote(u, C);
     const float tgt = u * S;
     // Bound-free search for the number of chunks whose prefix is <= tgt, in [0, nch - 1] (see prefix.cuh / table.cuh): with
     // P = step0 = the largest power of two <= nch, one first probe picks between the windows [0, P) and [nch - P, nch); the
-    // halving steps stay inside the window, and the last probe taken IS the prefix below the chosen chunk.
+    // halving steps stay inside the window, and the last probe taken IS the prefix below the chosen chunk.  nch <= 32, so the
+    // halving steps are 16, 8, 4, 2, 1 at most: unrolled with compile-time offsets, the ones >= step0 skipped (uniform branch).
     int pos = 0;
     float below = 0.0f;
     if (nch > k.step0) {
         const float f = probe32<MODEL>(k, pref, pstride, rbrow, el.A, cr, nch - k.step0 - 1);
         if (f <= tgt) { pos = nch - k.step0; below = f; }
     }
-    for (int step = k.step0 >> 1; step > 0; step >>= 1) {
-        const float f = probe32<MODEL>(k, pref, pstride, rbrow, el.A, cr, pos + step - 1);
-        if (f <= tgt) { pos += step; below = f; }
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+        if (step < k.step0) {
+            const float f = probe32<MODEL>(k, pref, pstride, rbrow, el.A, cr, pos + step - 1);
+            if (f <= tgt) { pos += step; below = f; }
+        }
     }
     const int jstar = pos;
     const int c0 = jstar * L;
@@ -413,7 +422,6 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
     const int nch = a.nch;
     const int CP = nch * L;
     const int Ei = (E + 3) & ~3;
-    const int wpc = a.warps_per_cta;
     const int rbpitch = dense32_rb_pitch(nch, L);
     const int TF = dense32_tab_floats(nch, L), CPP = dense32_cpp(nch, L);
     const int TK = dense32_tab_floats(a.nk_chunks, L);       // a run-off round's short table (cta_tabs)
@@ -446,7 +454,10 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
         votes = (int32_t*)base;                 base += sizeof(int32_t) * Ei;
     }
     int32_t* eff = (int32_t*)base;              base += sizeof(int32_t) * ((a.kmax + 3) & ~3);
-    uint8_t* mark = (uint8_t*)base;
+    uint8_t* mark = (uint8_t*)base;               base += Ei;
+    // Philox words (16-byte slots; Ei is a multiple of 4, so this is 4-byte aligned — rounded up to 16 below)
+    uint32_t* wq = (uint32_t*)(((uintptr_t)base + 15) & ~(uintptr_t)15);     // [32][4]: the quad of words of each lane's current four electors
+    uint32_t* tailw = wq + 32 * 4;                // [32][4]: the quads of the electors beyond the last whole 128, for several rounds ahead
 
     const int m_quads = E >> 7;                              // whole Philox quads per lane
     const int n_main = 4 * m_quads;
@@ -482,14 +493,19 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
         return el;
     };
 
-    const uint64_t per_item = (uint64_t)wpc * a.tpi;
-    const uint64_t items_per_set = (a.b.n_sims + per_item - 1) / per_item;
-    const uint64_t n_items = items_per_set * a.b.n_sets;
+    // The electors beyond the last whole 128 (n_left of them, nlq quads of Philox words per round): ONE Philox call per lane stashes
+    // their words for rpf = 32 / nlq rounds ahead (the counter is (sim, round, quad), so any lane can compute any round's quad).
+    const int nlq = (n_left + 3) >> 2;
+    const int rpf = nlq > 0 ? 32 / nlq : 0;          // rounds per fill (n_left <= 127 -> nlq <= 32 -> rpf >= 1)
+    const int q_left0 = e_left0 >> 2;
 
-    for (uint64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const int set = (int)(it / items_per_set);
-        const uint64_t i0 = (it % items_per_set) * per_item;
-        if (set != cur_set) {                                   // uniform over the CTA: every warp walks the same items
+    __shared__ int s_skip[2];
+    for (int si = 0; si < a.b.n_sets; ++si) {
+        const int set = cta_set_of_step(si, a.b.n_sets);         // uniform over the CTA
+        if (threadIdx.x == 0) s_skip[si & 1] = set_exhausted(a.wq, set, a.b.n_sims) ? 1 : 0;
+        __syncthreads();                                        // the answer is published; readers of the previous set's tables are done
+        if (s_skip[si & 1]) continue;
+        {
             if (cur_set >= 0 && lane == 0 && a.out.totals && acc_trials) {
                 atomicAdd(&a.out.totals[2 * cur_set], acc_rounds); atomicAdd(&a.out.totals[2 * cur_set + 1], acc_trials);
             }
@@ -499,7 +515,6 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
             kx.bonus = S->f_bonus; kx.st1p = S->f_st1p; bw_strength = S->f_bandwagon; pwf = S->f_pwf;
             need = S->need; k = S->k; rr = S->rr;
             has_sticky = MODEL && S->has_sticky; has_bw = MODEL && S->has_bw;
-            __syncthreads();                                    // readers of the previous set's tables are done
             for (int i = threadIdx.x; i < G * CP; i += blockDim.x) {
                 const int g = i / CP, c = i - g * CP;
                 rbf[g * rbpitch + pad_c<LC>(c)] = (c < C && a.ro.region[c] == g) ? kx.bonus : 0.0f;
@@ -515,8 +530,9 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
             __syncthreads();
         }
         const float* nbeta = a.nbeta + (size_t)set * R;
-        for (int ti = 0; ti < a.tpi; ++ti) {
-            const uint64_t i = i0 + (uint64_t)ti * wpc + wib;
+        for (uint64_t i0 = warp_claim_trials(a.wq, set, lane); i0 < a.b.n_sims; i0 = warp_claim_trials(a.wq, set, lane))
+        for (int ti = 0; ti < a.wq.chunk; ++ti) {
+            const uint64_t i = i0 + (uint64_t)ti;
             if (i >= a.b.n_sims) break;
             const uint64_t t = (uint64_t)set * a.b.n_sims + i;
             const uint64_t sim = a.b.sim_id_begin + i;
@@ -525,6 +541,7 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
             bool have_eff = false, have_prev = false;
             int winner = -1, rounds = 0, reason = CSIM_REASON_MAX_ROUNDS;
             int ef0 = 0, ef1 = 0;                                    // run-off pair when fast2
+            int tail_r0 = -(1 << 30);                                // first round of the current tail stash (none yet)
             if (R == 0) { for (int c = lane; c < C; c += 32) tally[c] = 0; __syncwarp(); }
             if (PROBE && MODEL && (a.probe_prev_vote || a.probe_prev_count)) {      // start from the given previous-round state
                 for (int c = lane; c < C; c += 32) {
@@ -568,8 +585,18 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                         }
                     }
                 }
-                for (int c = lane; c < C; c += 32) tally[c] = 0;
+                for (int c4 = lane; c4 < (Ei >> 2); c4 += 32) reinterpret_cast<int4*>(tally)[c4] = make_int4(0, 0, 0, 0);
+                if (nlq > 0 && (unsigned)(r - tail_r0) >= (unsigned)rpf) {         // (re)fill the tail stash: rounds r .. r + rpf - 1
+                    tail_r0 = r;
+                    const int rd = lane / nlq, tq = lane - rd * nlq;
+                    if (rd < rpf) {
+                        uint32_t w[4];
+                        philox4x32_10(s_lo, s_hi, (uint32_t)(r + rd), (uint32_t)(q_left0 + tq), a.b.seed_lo, a.b.seed_hi, w);
+                        *reinterpret_cast<uint4*>(tailw + 4 * lane) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
                 __syncwarp();
+                const uint32_t* tail_r = tailw + 4 * (r - tail_r0) * nlq - e_left0;  // word of leftover elector e this round: tail_r[e]
                 const bool sticky_live = have_prev && has_sticky;
 
                 int cnt0 = 0;                                        // run-off (fast2): this lane's votes for ef0
@@ -577,20 +604,20 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                     // =============== full-field round: NE electors of a lane at once =====================
                     for (int qi = 0; qi < m_quads; ++qi) {
                         const int q = lane + 32 * qi;
-                        uint32_t w[4];
-                        philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)q, a.b.seed_lo, a.b.seed_hi, w);
+                        {   // this lane's four words go to its own slot of shared memory: nothing of them stays live across the pair loop
+                            uint32_t w[4];
+                            philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)q, a.b.seed_lo, a.b.seed_hi, w);
+                            *reinterpret_cast<uint4*>(wq + 4 * lane) = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
 #pragma unroll 1
                         for (int g = 0; g < 4 / NE; ++g) {
                             const int e0 = 4 * q + NE * g;
-                            Elector32 el[NE];
-                            Corr32 cr[NE];
                             float xe[NE], Re[NE];
                             unsigned long long acc[NE];
 #pragma unroll
-                            for (int i = 0; i < NE; ++i) {
-                                el[i] = load_elector(e0 + i, sticky_live);
-                                cr[i] = corrections32<LC, MODEL, FACT>(kx, e0 + i, el[i]);
-                                xe[i] = el[i].x; Re[i] = el[i].R;
+                            for (int i = 0; i < NE; ++i) {          // all the pair loop needs of an elector: R_e (or its ideology)
+                                if (FACT) { const float Ainv = __ldg(tabA + CP + e0 + i); Re[i] = Ainv * Ainv; xe[i] = 0.f; }
+                                else { Re[i] = 1.f; xe[i] = __ldg(a.ro.x32 + e0 + i); }
                                 acc[i] = 0ull;
                             }
                             // phase 1: nothing but the pair arithmetic, its operand loads and one prefix store per elector
@@ -621,17 +648,16 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                                     tc += tstep; pc += NE * 32;
                                 }
                             }
+                            // phase 2: the elector's scalars and point-rule corrections are only needed here
 #pragma unroll 1
                             for (int i = 0; i < NE; ++i) {
-                                const int wi = NE * g + i;
-                                const uint32_t wa = wi == 0 ? w[0] : (wi == 1 ? w[1] : (wi == 2 ? w[2] : w[3]));
-                                Elector32 ei = el[0];
-                                Corr32 ci = cr[0];
-#pragma unroll
-                                for (int m = 1; m < NE; ++m) if (i == m) { ei = el[m]; ci = cr[m]; }
-                                const int vote = finish_draw<LC, MODEL, FACT, PROBE>(kx, pref + i * 32 + lane, NE * 32, e0 + i, u24_from_word(wa), ei, ci);
+                                const int e = e0 + i;
+                                const Elector32 el = load_elector(e, sticky_live);
+                                const Corr32 cr = corrections32<LC, MODEL, FACT>(kx, e, el);
+                                const uint32_t wa = wq[4 * lane + NE * g + i];
+                                const int vote = finish_draw<LC, MODEL, FACT, PROBE>(kx, pref + i * 32 + lane, NE * 32, e, u24_from_word(wa), el, cr);
                                 atomicAdd(&tally[vote], 1);
-                                if (MODEL) votes[e0 + i] = vote;   // read only by this lane for its own electors: in-place is safe
+                                if (MODEL) votes[e] = vote;        // read only by this lane for its own electors: in-place is safe
                             }
                         }
                     }
@@ -643,28 +669,35 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                         const int eli = lane / P, sub = lane - eli * P;
                         const bool act = eli < n_it;
                         const int e = e_left0 + gb + (act ? eli : 0);
-                        uint32_t w[4];
-                        philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)(e >> 2), a.b.seed_lo, a.b.seed_hi, w);
-                        const int sel = e & 3;
-                        const uint32_t wa = sel == 0 ? w[0] : (sel == 1 ? w[1] : (sel == 2 ? w[2] : w[3]));
                         const Elector32 el = load_elector(e, sticky_live);
-                        const Corr32 cr = corrections32<LC, MODEL, FACT>(kx, e, el);
                         const float xe1[1] = {el.x}, Re1[1] = {el.R};
                         const int tstep = LC == 8 ? 20 : L;
-                        float* cl = pref + eli * nch;                // this elector's chunk sums, then prefixes (m units)
+                        float* cl = pref + eli * nch;                // this elector's chunk prefixes (m units)
+                        // lane `sub` of an elector sums a contiguous range of its chunks (running prefix inside the range), the P range
+                        // totals are scanned with shuffles, and every lane adds the total of the ranges before its own
+                        const int per = (nch + P - 1) / P;
+                        const int j_lo = min(nch, sub * per), j_hi = min(nch, j_lo + per);
+                        float run = 0.f;
                         __syncwarp();
                         if (act) {
-                            for (int j = sub; j < nch; j += P) {
+                            for (int j = j_lo; j < j_hi; ++j) {
                                 unsigned long long acc[1] = {0ull};
                                 chunk_acc<1, LC, FACT>(kx, kx.T + j * tstep, xe1, Re1, acc);
-                                cl[j] = f2_lo(acc[0]) + f2_hi(acc[0]);
+                                run += f2_lo(acc[0]) + f2_hi(acc[0]);
+                                cl[j] = run;
                             }
                         }
+                        float off = run;                             // inclusive scan over the P lanes of an elector, then exclusive
+                        for (int d = 1; d < P; d <<= 1) {
+                            const float o = __shfl_up_sync(CSIM_FULL, off, d);
+                            if (sub >= d) off += o;
+                        }
+                        off -= run;
+                        if (act && sub > 0) for (int j = j_lo; j < j_hi; ++j) cl[j] += off;
                         __syncwarp();
                         if (act && sub == 0) {
-                            float run = 0.f;
-                            for (int j = 0; j < nch; ++j) { run += cl[j]; cl[j] = run; }
-                            const int vote = finish_draw<LC, MODEL, FACT, PROBE>(kx, cl, 1, e, u24_from_word(wa), el, cr);
+                            const Corr32 cr = corrections32<LC, MODEL, FACT>(kx, e, el);
+                            const int vote = finish_draw<LC, MODEL, FACT, PROBE>(kx, cl, 1, e, u24_from_word(tail_r[e]), el, cr);
                             atomicAdd(&tally[vote], 1);
                             if (MODEL) votes[e] = vote;
                         }
@@ -717,21 +750,16 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
 #pragma unroll
                             for (int i = 0; i < 4; ++i) play(4 * q + i, w[i]);
                         }
-                        for (int e = e_single0; e < E; e += 32) {
-                            uint32_t w[4];
-                            philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)(e >> 2), a.b.seed_lo, a.b.seed_hi, w);
-                            const int sel = e & 3;
-                            play(e, sel == 0 ? w[0] : (sel == 1 ? w[1] : (sel == 2 ? w[2] : w[3])));
-                        }
+                        for (int e = e_single0; e < E; e += 32) play(e, tail_r[e]);
                     } else {
                         uint32_t w[4] = {0, 0, 0, 0};
                         for (int n = 0; n < n_slots; ++n) {
                             int e, q; bool gen;
                             if (n < n_main) { q = lane + 32 * (n >> 2); e = 4 * q + (n & 3); gen = (n & 3) == 0; }
-                            else { e = e_single0 + 32 * (n - n_main); q = e >> 2; gen = true; }
+                            else { e = e_single0 + 32 * (n - n_main); q = e >> 2; gen = false; }
                             if (gen) philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)q, a.b.seed_lo, a.b.seed_hi, w);
                             const int sel = e & 3;
-                            const uint32_t wa = sel == 0 ? w[0] : (sel == 1 ? w[1] : (sel == 2 ? w[2] : w[3]));
+                            const uint32_t wa = n >= n_main ? tail_r[e] : (sel == 0 ? w[0] : (sel == 1 ? w[1] : (sel == 2 ? w[2] : w[3])));
                             const float u = u24_from_word(wa);
                             const Elector32 el = load_elector(e, sticky_live);
                             float sum = 0.f;

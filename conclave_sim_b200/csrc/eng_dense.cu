@@ -52,14 +52,11 @@ static csim_status launch_dense32_t(csim_ctx* c, Dense32Args& a, cudaStream_t st
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpc * 32, smem));
     if (per_sm < 1) return fail(CSIM_ERR_UNSUPPORTED, "dense kernel does not fit on an SM (threads=%d, smem=%zu)", wpc * 32, smem);
     const uint64_t ctas = (uint64_t)c->prop.multiProcessorCount * per_sm;      // persistent: a multiple of the SM count
-    // work item = warps_per_cta x tpi trials of one set; ~8 items per CTA keeps the tail short while a CTA that stays inside one
-    // parameter set never re-stages its tables
-    uint64_t tpi = a.b.n_sims / ((uint64_t)wpc * ctas * 8);
-    tpi = std::max<uint64_t>(1, std::min<uint64_t>(tpi, 64));
-    a.tpi = (int)tpi;
-    const uint64_t per_item = (uint64_t)wpc * tpi;
-    const uint64_t n_items = ((a.b.n_sims + per_item - 1) / per_item) * a.b.n_sets;
-    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_items, ctas));
+    // trials are claimed dynamically, `chunk` at a time per warp (common.cuh: WorkQueue); no more CTAs than there are warps' worth of trials
+    const uint64_t want = (a.b.n_sims * (uint64_t)std::max(a.b.n_sets, 1) + wpc - 1) / wpc;
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, ctas));
+    csim_status qs = work_queue(c, a.b.n_sets, a.b.n_sims, (uint64_t)grid * wpc, st, &a.wq);
+    if (qs != CSIM_OK) return qs;
     if (FACT && R > 0) {
         const int CP = a.nch * a.L;
         const size_t tb = sizeof(float) * (size_t)a.b.n_sets * R * 4 * CP;

@@ -39,7 +39,8 @@ struct Full32Args {
     int nch;                // chunks, nch * Lb >= nblk, nch <= 32
     int e_quad_end, rows;   // lane dealing (prefix_slot)
     int kmax, Fmax;
-    int warps_per_cta, tpi;
+    int warps_per_cta;
+    WorkQueue wq;           // dynamic trial scheduling (common.cuh)
     size_t cta_smem, warp_smem;
     // byte offsets (host-computed, full32_layout)
     uint32_t o_xs, o_pw, o_rb, o_xg, o_nbs;                                                  // CTA part
@@ -176,7 +177,6 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
     asm volatile("" : "+r"(lane));       // opaque: kept in a register instead of being re-derived from %tid inside the loops
     const int E = a.ro.E, C = E, R = a.b.R, G = a.ro.G;
     const int nblk = a.nblk, CP = nblk << 3, Lb = a.Lb, nch = a.nch;
-    const int wpc = a.warps_per_cta;
     float* xs = (float*)(smem_raw + a.o_xs);
     float* pwv = (float*)(smem_raw + a.o_pw);
     float* rbv = (float*)(smem_raw + a.o_rb);
@@ -209,18 +209,18 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
         deal_electors_once(lane, E, a.e_quad_end, r, s_lo, s_hi, a.b.seed_lo, a.b.seed_hi, fn);
     };
 
-    const uint64_t per_item = (uint64_t)wpc * a.tpi;
-    const uint64_t items_per_set = (a.b.n_sims + per_item - 1) / per_item;
-    const uint64_t n_items = items_per_set * a.b.n_sets;
     int cur_set = -1;
     unsigned long long acc_rounds = 0, acc_trials = 0;
     DevSet S;
     memset(&S, 0, sizeof S);
 
-    for (uint64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const int set = (int)(it / items_per_set);
-        const uint64_t i0 = (it % items_per_set) * per_item;
-        if (set != cur_set) {                                   // uniform over the CTA
+    __shared__ int s_skip[2];
+    for (int si = 0; si < a.b.n_sets; ++si) {
+        const int set = cta_set_of_step(si, a.b.n_sets);         // uniform over the CTA
+        if (threadIdx.x == 0) s_skip[si & 1] = set_exhausted(a.wq, set, a.b.n_sims) ? 1 : 0;
+        __syncthreads();
+        if (s_skip[si & 1]) continue;
+        {
             if (cur_set >= 0 && lane == 0 && a.out.totals && acc_trials) {
                 atomicAdd(&a.out.totals[2 * cur_set], acc_rounds); atomicAdd(&a.out.totals[2 * cur_set + 1], acc_trials);
             }
@@ -237,8 +237,9 @@ __global__ void __launch_bounds__(CSIM_FULL32_THREADS, 1) k_trials_full32(const 
             __syncthreads();
         }
         const int k = S.k, need = S.need, rr = S.rr, F = S.fat_rounds;
-        for (int ti = 0; ti < a.tpi; ++ti) {
-            const uint64_t i = i0 + (uint64_t)ti * wpc + wib;
+        for (uint64_t i0 = warp_claim_trials(a.wq, set, lane); i0 < a.b.n_sims; i0 = warp_claim_trials(a.wq, set, lane))
+        for (int ti = 0; ti < a.wq.chunk; ++ti) {
+            const uint64_t i = i0 + (uint64_t)ti;
             if (i >= a.b.n_sims) break;
             const uint64_t t = (uint64_t)set * a.b.n_sims + i;
             const uint64_t sim = a.b.sim_id_begin + i;

@@ -68,6 +68,7 @@ struct csim_ctx {
     int E = 0, Epad = 0, G = 0;
     DevBuf x64, x32, region, pap;
     DevBuf sets, betas, nbeta, W, tab, cdf64, cdfk64, cdf32, cdfk32, ptab, accm;
+    DevBuf work;                        // per-set trial counters of the dynamically scheduled kernels (WorkQueue)
     double x_mid = 0.0, x_half = 0.0;   // centre and half-range of ideology_score (factorised exp)
     // host-buffer mode staging
     DevBuf o_winner, o_rounds, o_reason, o_final, o_tallies, o_whist, o_rhist, o_totals, i_tape;
@@ -110,6 +111,20 @@ static inline RosterDev roster_dev(const csim_ctx* c) {
     r.x64 = (const double*)c->x64.p; r.x32 = (const float*)c->x32.p;
     r.region = (const int32_t*)c->region.p; r.pap = (const uint8_t*)c->pap.p;
     return r;
+}
+
+// Zeroed per-set trial counters for one launch of a dynamically scheduled kernel (enqueued on `st` ahead of the kernel), and
+// the number of trials a warp claims per fetch: small enough that the last claims end together (<= 1/128 of a warp's share, at most 4),
+// large enough that the atomics are noise.
+static inline csim_status work_queue(csim_ctx* c, int n_sets, uint64_t n_sims, uint64_t n_warps, cudaStream_t st, WorkQueue* wq) {
+    const size_t bytes = sizeof(unsigned long long) * (size_t)std::max(n_sets, 1);
+    CU_TRY(c->work.reserve(bytes));
+    CU_TRY(cudaMemsetAsync(c->work.p, 0, bytes, st));
+    wq->next = (unsigned long long*)c->work.p;
+    const uint64_t per_warp = n_sims * (uint64_t)std::max(n_sets, 1) / std::max<uint64_t>(n_warps, 1);
+    wq->chunk = (int)std::max<uint64_t>(1, std::min<uint64_t>(per_warp / 128, 4));
+    if (const char* e = getenv("CSIM_CHUNK")) wq->chunk = std::max(1, atoi(e));
+    return CSIM_OK;
 }
 
 template <class K>

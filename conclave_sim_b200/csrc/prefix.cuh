@@ -58,7 +58,7 @@ struct PrefixArgs {
     int e_quad_end;         // electors below this are dealt as whole Philox quads per lane, the rest one per lane
     int kmax;
     int warps_per_cta;
-    int tpi;                // trials per warp per work item
+    WorkQueue wq;           // dynamic trial scheduling (common.cuh)
     size_t set_pitch;       // floats between the tables of consecutive sets (16-byte multiple)
     size_t tab_smem;        // bytes of the staged tables (0 when STAGE = false)
     size_t cta_smem;        // staged tables + roster tables
@@ -380,12 +380,11 @@ __device__ __forceinline__ int prefix_draw(const PrefixCtx& k, const PrefixArgs&
     return vote;
 }
 
-// One thread: (re-)arm the CTA's mbarrier and issue the set's tables as bulk copies (TMA 1-D, UBLKCP) of <= 32 KB, all
-// completing on that barrier.  Kept out of line so that its registers do not weigh on the trial loop.
-static __device__ __noinline__ void prefix_stage_tables(uint32_t dst, const float* src, uint32_t total, uint32_t bar, bool first) {
-    if (!first) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-    mbar_init(bar, 1);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+// One thread: issue the set's tables as bulk copies (TMA 1-D, UBLKCP) of <= 32 KB, all completing on the CTA's mbarrier (armed
+// once at kernel start; every staging is one phase of it and the waiters track the parity).  Kept out of line so that its
+// registers do not weigh on the trial loop.
+static __device__ __noinline__ void prefix_stage_tables(uint32_t dst, const float* src, uint32_t total, uint32_t bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // earlier generic-proxy accesses of dst are ordered before the async writes
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
     const char* gbase = reinterpret_cast<const char*>(src);
     for (uint32_t off = 0; off < total; off += 32768u) {
@@ -404,7 +403,6 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(const 
     const int E = a.ro.E, C = E, R = a.b.R, G = a.ro.G;
     const int Ls = LC8 ? 3 : a.Ls, nch = a.nch, Lp = (1 << Ls) + 4, CPP = nch * Lp;
     auto pc = [&](int c) { return c + ((c >> Ls) << 2); };   // index of candidate c in the padded arrays
-    const int wpc = a.warps_per_cta;
     // ---- CTA-shared: staged tables of the current set, then roster tables (offsets: prefix_layout) ---------
     float* xs = (float*)(smem_raw + a.o_xs);
     float* pwv = (float*)(smem_raw + a.o_pw);                                       // papabile weight of the current set (0 = padding)
@@ -413,6 +411,9 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(const 
     float* nbs = (float*)(smem_raw + a.o_nbs);                                      // [R] -beta_r log2 e of the current set
     for (int i = threadIdx.x; i < CPP; i += blockDim.x) { xs[i] = 0.0f; pwv[i] = 0.0f; }
     for (int i = threadIdx.x; i < CPP * G; i += blockDim.x) rbv[i] = 0.0f;
+    __shared__ __align__(8) unsigned long long stage_bar;                   // mbarrier of the staged tables: one phase per staged set
+    uint32_t stage_phase = 0;
+    if (STAGE && threadIdx.x == 0) mbar_init((uint32_t)__cvta_generic_to_shared(&stage_bar), 1);
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         xs[pc(c)] = a.ro.x32[c];
@@ -436,16 +437,12 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(const 
     asm volatile("" : "+r"(kx.sb), "+r"(kx.wb));   // opaque for the same reason (the shared-window base needs an S2R)
     kx.nb = 0.f; kx.st1p = 1.f;
     const uint32_t Ts_a = kx.sb;
-    __shared__ __align__(8) unsigned long long stage_bar;                   // mbarrier of the staged tables (re-armed per set: phase 0)
 
     // the electors of one round, each lane with its uniform (common.cuh: deal_electors)
     auto for_each_elector = [&](int r, uint32_t s_lo, uint32_t s_hi, auto&& fn) {
         deal_electors(lane, E, a.e_quad_end, r, s_lo, s_hi, a.b.seed_lo, a.b.seed_hi, fn);
     };
 
-    const uint64_t per_item = (uint64_t)wpc * a.tpi;
-    const uint64_t items_per_set = (a.b.n_sims + per_item - 1) / per_item;
-    const uint64_t n_items = items_per_set * a.b.n_sets;
     int cur_set = -1;
     float bw_strength = 0.f, bonus_s = 0.f;
     int need = 0, k = 0, rr = 0;
@@ -453,15 +450,17 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(const 
     unsigned long long acc_rounds = 0, acc_trials = 0;
     const float* Tset = a.T;
 
-    for (uint64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const int set = (int)(it / items_per_set);
-        const uint64_t i0 = (it % items_per_set) * per_item;
-        if (set != cur_set) {                                   // uniform over the CTA: every warp walks the same items
+    __shared__ int s_skip[2];
+    for (int si = 0; si < a.b.n_sets; ++si) {
+        const int set = cta_set_of_step(si, a.b.n_sets);         // uniform over the CTA
+        if (threadIdx.x == 0) s_skip[si & 1] = set_exhausted(a.wq, set, a.b.n_sims) ? 1 : 0;
+        __syncthreads();
+        if (s_skip[si & 1]) continue;
+        {
             if (cur_set >= 0 && lane == 0 && a.out.totals && acc_trials) {
                 atomicAdd(&a.out.totals[2 * cur_set], acc_rounds); atomicAdd(&a.out.totals[2 * cur_set + 1], acc_trials);
             }
             acc_rounds = acc_trials = 0;
-            const bool first_set = cur_set < 0;
             cur_set = set;
             const DevSet* S = &a.b.sets[set];
             kx.st1p = S->f_st1p; bw_strength = S->f_bandwagon; bonus_s = S->f_bonus;
@@ -471,18 +470,18 @@ __global__ void __launch_bounds__(CSIM_PREFIX_THREADS, 1) k_trials_prefix(const 
             Tset = a.T + (size_t)set * a.set_pitch;
             __syncthreads();                                    // readers of the previous set's tables are done
             if (STAGE && threadIdx.x == 0)
-                prefix_stage_tables(Ts_a, Tset, (uint32_t)a.tab_smem, (uint32_t)__cvta_generic_to_shared(&stage_bar), first_set);
+                prefix_stage_tables(Ts_a, Tset, (uint32_t)a.tab_smem, (uint32_t)__cvta_generic_to_shared(&stage_bar));
             for (int r = threadIdx.x; r < R; r += blockDim.x) nbs[r] = a.nbeta[(size_t)set * R + r];
             for (int c = threadIdx.x; c < C; c += blockDim.x) {
                 pwv[pc(c)] = a.ro.pap[c] ? pwf : 1.0f;
                 rbv[a.ro.region[c] * CPP + pc(c)] = bonus;
             }
-            __syncthreads();                                    // the re-armed barrier is visible to every waiter
-            if (STAGE) mbar_wait((uint32_t)__cvta_generic_to_shared(&stage_bar), 0u);
-            __syncthreads();
+            if (STAGE) { mbar_wait((uint32_t)__cvta_generic_to_shared(&stage_bar), stage_phase); stage_phase ^= 1u; }
+            __syncthreads();                                    // tables landed, roster arrays of the set written
         }
-        for (int ti = 0; ti < a.tpi; ++ti) {
-            const uint64_t i = i0 + (uint64_t)ti * wpc + wib;
+        for (uint64_t i0 = warp_claim_trials(a.wq, set, lane); i0 < a.b.n_sims; i0 = warp_claim_trials(a.wq, set, lane))
+        for (int ti = 0; ti < a.wq.chunk; ++ti) {
+            const uint64_t i = i0 + (uint64_t)ti;
             if (i >= a.b.n_sims) break;
             const uint64_t t = (uint64_t)set * a.b.n_sims + i;
             const uint64_t sim = a.b.sim_id_begin + i;
