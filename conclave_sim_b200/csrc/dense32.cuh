@@ -454,9 +454,8 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
         votes = (int32_t*)base;                 base += sizeof(int32_t) * Ei;
     }
     int32_t* eff = (int32_t*)base;              base += sizeof(int32_t) * ((a.kmax + 3) & ~3);
-    uint8_t* mark = (uint8_t*)base;               base += Ei;
-    // Philox words (16-byte slots; Ei is a multiple of 4, so this is 4-byte aligned — rounded up to 16 below)
-    uint32_t* wq = (uint32_t*)(((uintptr_t)base + 15) & ~(uintptr_t)15);     // [32][4]: the quad of words of each lane's current four electors
+    uint8_t* mark = (uint8_t*)base;               base += (Ei + 15) & ~15;
+    uint32_t* wq = (uint32_t*)base;               // [32][4]: the quad of Philox words of each lane's current four electors (16-byte slots)
     uint32_t* tailw = wq + 32 * 4;                // [32][4]: the quads of the electors beyond the last whole 128, for several rounds ahead
 
     const int m_quads = E >> 7;                              // whole Philox quads per lane
@@ -481,12 +480,12 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
     int need = 0, k = 0, rr = 0;
     bool has_sticky = false, has_bw = false;
     unsigned long long acc_rounds = 0, acc_trials = 0;
-    const float* tabA = nullptr;
+    uint32_t tabA = 0;                        // element offset of this round's A | 1/A | BP | BQ block inside a.tab (32-bit: the launcher checks the size)
 
     // one elector's scalars for this round
     auto load_elector = [&](int e, bool sticky_live) {
         Elector32 el;
-        if (FACT) { el.A = __ldg(tabA + e); el.Ainv = __ldg(tabA + CP + e); el.R = el.Ainv * el.Ainv; el.x = 0.f; }
+        if (FACT) { el.A = __ldg(a.tab + (tabA + (uint32_t)e)); el.Ainv = __ldg(a.tab + (tabA + (uint32_t)(CP + e))); el.R = el.Ainv * el.Ainv; el.x = 0.f; }
         else { el.A = 1.f; el.Ainv = 1.f; el.R = 1.f; el.x = __ldg(a.ro.x32 + e); }
         el.g = reg[e];
         el.prev = (MODEL && sticky_live) ? votes[e] : -1;
@@ -556,13 +555,13 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                 rounds = r;
                 kx.nb = __ldg(&nbeta[r - 1]);
                 kx.use_bw = false;
-                if (FACT) tabA = a.tab + ((size_t)set * R + (r - 1)) * 4 * CP;
+                if (FACT) tabA = (uint32_t)(set * R + (r - 1)) * (uint32_t)(4 * CP);
                 if (a.cta_tabs) {
                     const int rt = FACT ? r - 1 : 0;
                     kx.T = rt < a.n_tab_full ? tabs + (size_t)rt * TF : tabs + (size_t)a.n_tab_full * TF + (size_t)(rt - a.n_tab_full) * TK;
                 } else {                                             // stage this round's table (trial-invariant vectors) for this warp
                     __syncwarp();
-                    stage_round_table<LC, FACT>(wtab, a, tabA, pwf, CP, C, lane, 32);
+                    stage_round_table<LC, FACT>(wtab, a, FACT ? a.tab + tabA : nullptr, pwf, CP, C, lane, 32);
                     kx.T = wtab;
                 }
                 if (MODEL) {
@@ -616,7 +615,7 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                             unsigned long long acc[NE];
 #pragma unroll
                             for (int i = 0; i < NE; ++i) {          // all the pair loop needs of an elector: R_e (or its ideology)
-                                if (FACT) { const float Ainv = __ldg(tabA + CP + e0 + i); Re[i] = Ainv * Ainv; xe[i] = 0.f; }
+                                if (FACT) { const float Ainv = __ldg(a.tab + (tabA + (uint32_t)(CP + e0 + i))); Re[i] = Ainv * Ainv; xe[i] = 0.f; }
                                 else { Re[i] = 1.f; xe[i] = __ldg(a.ro.x32 + e0 + i); }
                                 acc[i] = 0ull;
                             }
@@ -721,7 +720,7 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                             const float b0 = (g == g0 ? bonus : 0.0f) + f0, b1 = (g == g1 ? bonus : 0.0f) + f1;
                             float w0, w1;
                             if (FACT) {
-                                const float Ainv = __ldg(tabA + CP + e), Rr = Ainv * Ainv;
+                                const float Ainv = __ldg(a.tab + (tabA + (uint32_t)(CP + e))), Rr = Ainv * Ainv;
                                 w0 = fmaf(b0, Ainv, fminf(P0, Rr * X0));
                                 w1 = fmaf(b1, Ainv, fminf(P1, Rr * X1));
                             } else {

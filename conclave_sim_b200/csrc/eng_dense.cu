@@ -60,6 +60,7 @@ static csim_status launch_dense32_t(csim_ctx* c, Dense32Args& a, cudaStream_t st
     if (FACT && R > 0) {
         const int CP = a.nch * a.L;
         const size_t tb = sizeof(float) * (size_t)a.b.n_sets * R * 4 * CP;
+        if (tb / sizeof(float) > 0xffffffffull) return fail(CSIM_ERR_UNSUPPORTED, "dense engine: %d sets x %d rounds of round tables exceed 2^32 entries", a.b.n_sets, R);
         CU_TRY(c->tab.reserve(tb));
         a.tab = (const float*)c->tab.p;
         for (int sr0 = 0; sr0 < a.b.n_sets * R; sr0 += CSIM_GRID_TILE) {

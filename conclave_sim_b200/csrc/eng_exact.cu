@@ -27,6 +27,8 @@ csim_status launch_exact64(csim_ctx* c, const csim_run_args* ra, const std::vect
     int grid = 1;
     csim_status s = persistent_grid(c, k_trials_exact64, wpc * 32, smem, (uint64_t)b.n_sets * b.n_sims, wpc, &grid);
     if (s != CSIM_OK) return s;
+    s = work_queue(c, 1, (uint64_t)b.n_sets * b.n_sims, (uint64_t)grid * wpc, st, &a.wq);
+    if (s != CSIM_OK) return s;
     CU_TRY(cudaEventRecord(c->ev0, st));
     k_trials_exact64<<<grid, wpc * 32, smem, st>>>(a);
     CU_TRY(cudaEventRecord(c->ev1, st));

@@ -35,24 +35,24 @@ static csim_status launch_table_t(csim_ctx* c, const BatchDev& b, const TrialOut
     int per_sm = 0;
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpc * 32, smem));
     if (per_sm < 1) return fail(CSIM_ERR_UNSUPPORTED, "table kernel does not fit on an SM (smem=%zu)", smem);
-    // trials per warp per super-batch: a CTA's cost is proportional to it, the kernel's duration to waves x tpw — choose the
-    // tpw in [20, 32] that wastes least in the last wave of the persistent grid (1.25 M trials, 296 CTAs: tpw 32 = 8.25 waves,
-    // i.e. 9 x 32 = 288 trial-slots per warp; tpw 30 = 8.8 waves, 9 x 30 = 270)
+    // Super-batches are claimed dynamically (one global counter).  Big ones of wpc x 32 trials amortise the per-round staging; the
+    // last ~one-big-batch-per-CTA's worth of the job is cut into small ones (16 trials per warp) so that the CTAs finish within
+    // one small batch of each other instead of one big one (1.25 M trials on 296 CTAs: 8.25 big batches per CTA).
     const uint64_t ctas = (uint64_t)c->prop.multiProcessorCount * per_sm;
-    int tpw = 32;
+    int tpw = 32, tpw_tail = 16;
     if (const char* e = getenv("CSIM_TABLE_TPW")) tpw = std::max(1, std::min(32, atoi(e)));
-    else {
-        uint64_t best = ~0ull;
-        for (int t = 32; t >= 20; --t) {
-            const uint64_t nsb = ((b.n_sims + (uint64_t)wpc * t - 1) / ((uint64_t)wpc * t)) * b.n_sets;
-            const uint64_t cost = ((nsb + ctas - 1) / ctas) * (uint64_t)t;
-            if (cost < best) { best = cost; tpw = t; }
-        }
-    }
-    a.tpw = tpw;
-    const uint64_t sb_trials = (uint64_t)wpc * tpw;
-    const uint64_t n_sb = ((b.n_sims + sb_trials - 1) / sb_trials) * b.n_sets;
+    if (const char* e = getenv("CSIM_TABLE_TPW_TAIL")) tpw_tail = std::max(1, std::min(32, atoi(e)));
+    tpw_tail = std::min(tpw_tail, tpw);
+    a.tpw = tpw; a.tpw_tail = tpw_tail;
+    const uint64_t big_trials = (uint64_t)wpc * tpw, small_trials = (uint64_t)wpc * tpw_tail;
+    uint64_t tail_sims = std::min<uint64_t>(b.n_sims, ctas * big_trials);
+    if (const char* e = getenv("CSIM_TABLE_TAIL_BATCHES")) tail_sims = std::min<uint64_t>(b.n_sims, (uint64_t)atoll(e) * big_trials);
+    a.n_big_last = (b.n_sims - tail_sims) / big_trials;
+    const uint64_t sb_per_set = (b.n_sims + big_trials - 1) / big_trials;
+    const uint64_t n_sb = sb_per_set * (uint64_t)(b.n_sets - 1) + a.n_big_last + (b.n_sims - a.n_big_last * big_trials + small_trials - 1) / small_trials;
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_sb, ctas));
+    csim_status qs = work_queue(c, 1, n_sb, (uint64_t)grid, st, &a.wq);
+    if (qs != CSIM_OK) return qs;
     CU_TRY(cudaEventRecord(c->ev0, st));
     kern<<<grid, wpc * 32, smem, st>>>(a);
     CU_TRY(cudaEventRecord(c->ev1, st));

@@ -157,6 +157,7 @@ struct Exact64Args {
     int Fmax;               // ring size of the tally history (>= 1)
     int kmax;               // max k over sets (>= 1)
     int warps_per_cta;
+    WorkQueue wq;           // dynamic trial scheduling (common.cuh), one counter over all (set, sim) pairs
     size_t warp_smem;       // bytes of shared memory per warp
 };
 
@@ -189,11 +190,13 @@ static __global__ void __launch_bounds__(256, CSIM_EXACT_MINB) k_trials_exact64(
     uint8_t* mark = (uint8_t*)base;
 
     const uint64_t n_trials = (uint64_t)a.b.n_sets * a.b.n_sims;
-    const uint64_t warp_global = (uint64_t)blockIdx.x * a.warps_per_cta + wib;
-    const uint64_t n_warps = (uint64_t)gridDim.x * a.warps_per_cta;
     const bool model = a.wiring == CSIM_WIRING_MODEL;
 
-    for (uint64_t t = warp_global; t < n_trials; t += n_warps) {
+    // trials are claimed dynamically from ONE counter over the flat (set, sim) index (common.cuh: WorkQueue; no per-set state is CTA-shared here)
+    for (uint64_t t0 = warp_claim_trials(a.wq, 0, lane); t0 < n_trials; t0 = warp_claim_trials(a.wq, 0, lane))
+    for (int ti = 0; ti < a.wq.chunk; ++ti) {
+        const uint64_t t = t0 + (uint64_t)ti;
+        if (t >= n_trials) break;
         const int set = (int)(t / a.b.n_sims);
         const uint64_t sim = a.b.sim_id_begin + (t % a.b.n_sims);
         const DevSet S = a.b.sets[set];

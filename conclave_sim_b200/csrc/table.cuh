@@ -102,8 +102,11 @@ struct TableArgs {
     const Real* cdfk;       // [sets][R][E][kmax]
     int kmax;
     int warps_per_cta;
-    int tpw;                // trials per warp per super-batch (<= 32: lane i holds trial i); chosen by the launcher so that the
-                            // super-batches fill whole waves of the persistent grid (a partly filled last wave idles the GPU)
+    int tpw;                // trials per warp per super-batch (<= 32: lane i holds trial i)
+    int tpw_tail;           // ... of the small super-batches that the END of the job is cut into, so that the CTAs — which claim
+                            // super-batches dynamically (wq.next[0] counts them) — run out of work within one small batch of each other
+    uint64_t n_big_last;    // big super-batches of the LAST parameter set; the rest of its trials go in small ones
+    WorkQueue wq;
     int stage;              // 1: E x C rows fit in shared memory and are staged per round
     int stage_q;            // 1: the [R][E] run-off first-column table is staged too
     int tail_words;         // fp32 only, 0 = off: Philox words kept per trial for the tail electors (4 per tail quad, <= 16).  The
@@ -185,10 +188,14 @@ __global__ void __launch_bounds__(CSIM_TABLE_WPC * 32, 1024 / (CSIM_TABLE_WPC * 
         __syncthreads();
     }
     const int wpc = a.warps_per_cta;
-    const int tpw = a.tpw;
-    const uint64_t sb_trials = (uint64_t)wpc * tpw;                          // trials per super-batch
-    const uint64_t sb_per_set = (a.b.n_sims + sb_trials - 1) / sb_trials;
-    const uint64_t n_sb = sb_per_set * a.b.n_sets;
+    // super-batches: every set but the last in big ones (tpw trials per warp); the last set in n_big_last big ones and then small
+    // ones (tpw_tail), so the job ends on short work items.  Claimed in order from one global counter.
+    const uint64_t big_trials = (uint64_t)wpc * a.tpw, small_trials = (uint64_t)wpc * a.tpw_tail;
+    const uint64_t sb_per_set = (a.b.n_sims + big_trials - 1) / big_trials;
+    const uint64_t sb_before_last = sb_per_set * (uint64_t)(a.b.n_sets - 1);
+    const uint64_t last_big_sims = a.n_big_last * big_trials;              // <= n_sims
+    const uint64_t n_sb = sb_before_last + a.n_big_last + (a.b.n_sims - last_big_sims + small_trials - 1) / small_trials;
+    __shared__ unsigned long long s_sb[2];
     int step0 = 1;
     while (step0 * 2 <= C) step0 *= 2;
     const bool top2_ok = C >= 2 && C < 32768;
@@ -247,9 +254,22 @@ __global__ void __launch_bounds__(CSIM_TABLE_WPC * 32, 1024 / (CSIM_TABLE_WPC * 
         }
     };
 
-    for (uint64_t sb = blockIdx.x; sb < n_sb; sb += gridDim.x) {
-        const int set = (int)(sb / sb_per_set);
-        const uint64_t i0 = (sb % sb_per_set) * sb_trials + (uint64_t)wib * tpw;    // first sim index of this warp's batch
+    for (int it = 0;; ++it) {
+        if (threadIdx.x == 0) s_sb[it & 1] = atomicAdd(a.wq.next, 1ULL);
+        __syncthreads();                                         // (slot it & 1 is rewritten two barriers from now at the earliest)
+        const uint64_t sb = s_sb[it & 1];
+        if (sb >= n_sb) break;
+        int set, tpw;
+        uint64_t i0;                                             // first sim index of this warp's batch
+        if (sb < sb_before_last) {
+            set = (int)(sb / sb_per_set); tpw = a.tpw;
+            i0 = (sb % sb_per_set) * big_trials + (uint64_t)wib * tpw;
+        } else {
+            const uint64_t j = sb - sb_before_last;
+            set = a.b.n_sets - 1;
+            if (j < a.n_big_last) { tpw = a.tpw; i0 = j * big_trials + (uint64_t)wib * tpw; }
+            else { tpw = a.tpw_tail; i0 = last_big_sims + (j - a.n_big_last) * small_trials + (uint64_t)wib * tpw; }
+        }
         const DevSet S = a.b.sets[set];
         const int k = S.k, need = S.need, rr = S.rr;
         const int r_full = k > 0 ? min(R, max(rr, 1)) : R;       // rounds 1..r_full are full-field (round 1 always is)
