@@ -67,7 +67,7 @@ extern "C" csim_status csim_destroy(csim_ctx* c) {
     DeviceGuard guard;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();             // nothing of this context may still be in flight when its buffers go
-    for (DevBuf* b : {&c->x64, &c->x32, &c->region, &c->pap, &c->sets, &c->betas, &c->nbeta, &c->W, &c->tab, &c->cdf64, &c->cdfk64, &c->cdf32, &c->cdfk32, &c->ptab, &c->accm, &c->work, &c->o_winner, &c->o_rounds,
+    for (DevBuf* b : {&c->x64, &c->x32, &c->region, &c->pap, &c->sets, &c->betas, &c->nbeta, &c->W, &c->tab, &c->cdf64, &c->cdfk64, &c->cdf32, &c->cdfk32, &c->ptab, &c->accm, &c->accb, &c->work, &c->o_winner, &c->o_rounds,
                       &c->o_reason, &c->o_final, &c->o_tallies, &c->o_whist, &c->o_rhist, &c->o_totals, &c->i_tape,
                       &c->p_prev, &c->p_cnt, &c->p_fat, &c->p_shares, &c->p_bw, &c->p_out, &c->p_cand, &c->p_pref})
         b->release();

@@ -76,6 +76,14 @@ struct Dense32Args {
     float* probe_scores;                // [E][C]
     float* probe_prefix;                // [E][probe_cap]
     int probe_cap;
+    // EXT instantiation only (candidate fatigue + stop-candidate live, launched by eng_full.cu as the FULL engine's fast path)
+    const uint32_t* accmask;            // [sets][E][accw] bit c of row e: candidate c is ACCEPTABLE to elector e (k_full_accmask, fp64-exact)
+    int accw;
+    const uint2* accb;                  // [sets][nch][epitch]: the same bits of (elector slot, chunk) as 8 bytes, 0x40 = acceptable (k_ext_accbytes)
+    int epitch;
+    int Fmax;                           // longest fatigue window of the batch (rows of the per-warp tally history)
+    size_t o_ext;                       // byte offset of the EXT part of the CTA-shared memory (accb | regb | regbits)
+    const uint8_t* probe_fatigued;      // PROBE: the fatigue mask to apply (or null)
 };
 
 #ifndef CSIM_NE
@@ -112,12 +120,32 @@ __host__ __device__ inline size_t dense32_warp_smem(int E, int nch, int L, int k
     return (n + 15) & ~(size_t)15;
 }
 
+// EXT instantiation: what candidate fatigue + stop-candidate add to the shared-memory footprint (the warp part follows the arrays of
+// dense32_warp_smem(..., model = true, warp_tab = true): a fatigued round plays from the warp's own, phi-folded copy of its round table)
+__host__ __device__ inline size_t dense32_ext_warp_smem(int E, int nch, int G, int Fmax) {
+    const size_t Ei = ((size_t)E + 3) & ~(size_t)3, n4 = ((size_t)nch + 3) & ~(size_t)3;
+    const size_t n = (size_t)dense32_cpp(nch, 8) * 4 /*phi*/ + (size_t)G * n4 * 4 /*rbpw*/ + 2 * 8 * 4 /*fatbits, thrbits*/ + (size_t)(Fmax < 1 ? 1 : Fmax) * Ei /*hist*/;
+    return (n + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t dense32_ext_cta_smem(int E, int nch, int G, int epitch) {
+    const size_t n = (size_t)nch * epitch * 8 /*accb*/ + (size_t)G * nch * 8 /*regb*/ + (size_t)G * ((E + 31) / 32) * 4 /*regbits*/;
+    return (n + 15) & ~(size_t)15;
+}
+// row of elector e in the acceptable-bytes table: the order in which the lanes of the trial kernel visit electors (quad-dealt
+// electors 4 (lane + 32 qi) + i sit at 128 qi + 32 i + lane, so the 32 lanes of a pass read 32 consecutive 8-byte entries)
+__host__ __device__ inline int dense32_slot(int e, int E) {
+    return e < (E & ~127) ? ((e >> 7) << 7) + ((e & 3) << 5) + ((e >> 2) & 31) : e;
+}
+
 // sm_100 packed fp32 (two lanes of a 64-bit register pair per instruction)
 __device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
     unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
 }
 __device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
     unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
 }
 __device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
     return ((unsigned long long)__float_as_uint(hi) << 32) | (unsigned long long)__float_as_uint(lo);
@@ -142,6 +170,25 @@ static __global__ void k_round_tables32(RosterDev ro, const DevSet* sets, const 
     t[c] = A; t[CP + c] = Ap; t[2 * CP + c] = BP; t[3 * CP + c] = BPp;
 }
 
+// EXT: acceptable(e, c) = !(|x_e - x_c| > D) in fp64 exactly as model.py:390, for every set with stop-candidate enabled, as one byte per
+// candidate (0x40 = acceptable: the top byte of the float 2.0) grouped by (chunk of 8 candidates, elector slot).
+// grid = (ceil(E * nch / 128), sets), block = 128.
+static __global__ void k_ext_accbytes(RosterDev ro, const DevSet* sets, int nch, int epitch, uint2* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, set = blockIdx.y;
+    const int E = ro.E;
+    if (i >= E * nch) return;
+    const int e = i / nch, j = i - e * nch;
+    const double xe = ro.x64[e], D = sets[set].stop_D;
+    uint32_t lo = 0, hi = 0;
+    for (int q = 0; q < 8; ++q) {
+        const int c = 8 * j + q;
+        if (c < E && !(fabs(xe - ro.x64[c]) > D)) {
+            if (q < 4) lo |= 0x40u << (8 * q); else hi |= 0x40u << (8 * (q - 4));
+        }
+    }
+    out[((size_t)set * nch + j) * epitch + dense32_slot(e, E)] = make_uint2(lo, hi);
+}
+
 // index of candidate c's P operand inside a round table; its X operand sits XOFF floats further
 template <int LC> __device__ __forceinline__ int tab_off(int c) { return LC == 8 ? (c >> 3) * 20 + ((c & 4) << 1) + (c & 3) : c; }
 // index of candidate c in the padded per-candidate arrays (regional rows, bandwagon)
@@ -156,10 +203,14 @@ struct LaneCtx32 {              // per-warp / per-round constants of the draw
     int C, G, L, nch, step0;
     bool use_bw;
     float* dbg_scores; float* dbg_prefix; int dbg_cap;      // PROBE only
+    // EXT only: phi = fatigue factor per candidate (padded like bw; 1 where not fatigued), bw then holds bandwagon * phi; rbp_cur = the
+    // regional prefix the probes use (the roster's counts, or this round's phi-weighted ones); flat_in_m = this round's prefix columns
+    // already hold every term (stop-candidate live: the masked pair loop), so a probe adds no table term
+    const float* phi; const float* rbp_cur; float boost; bool flat_in_m;
 };
 
 // One elector's scalars.  FACT: score(e,c) = A * min(BP_c, R * BQ_c);  else A = 1 and x is the ideology.
-struct Elector32 { float x, A, Ainv, R; int g, prev; };
+struct Elector32 { float x, A, Ainv, R; int g, prev; bool trig; const uint32_t* arow; };     // trig / arow: EXT only (stop-candidate, model.py:384-415)
 
 // The two point rules of a row as corrections of its chunk prefixes, in m units (score = A * m): the self score leaves from
 // chunk je on (model.py:418-424), stickiness adds from chunk jp on (model.py:357-367).  Applied when a prefix is probed.
@@ -173,14 +224,21 @@ __device__ __forceinline__ float pair_m32(const LaneCtx32& k, int c, const Elect
 }
 
 // every term of one score, inline (run-off rounds and the generic re-scan)
-template <int LC, bool MODEL, bool FACT>
+// bit c of an elector's "acceptable" row (EXT)
+__device__ __forceinline__ bool acc_bit(const uint32_t* arow, int c) { return (__ldg(arow + (c >> 5)) >> (c & 31)) & 1u; }
+
+// EXT (run-off rounds: k.T is the round's plain table there): fatigue scales the score, bandwagon included (k.bw holds bandwagon * phi),
+// and a triggered elector boosts the candidates acceptable to it (model.py:372-415)
+template <int LC, bool MODEL, bool FACT, bool EXT = false>
 __device__ __forceinline__ float full_score32(const LaneCtx32& k, int e, int c, const Elector32& el) {
     float v = el.A * pair_m32<LC, FACT>(k, c, el);
     if (k.reg[c] == el.g) v += k.bonus;
+    if (EXT) v *= k.phi[pad_c<LC>(c)];
     if (MODEL) {
         if (k.use_bw) v += k.bw[pad_c<LC>(c)];
         if (c == el.prev) v *= k.st1p;
     }
+    if (EXT) { if (el.trig && acc_bit(el.arow, c)) v *= k.boost; }
     return c == e ? 0.0f : v;
 }
 
@@ -267,6 +325,60 @@ __device__ __forceinline__ void chunk_math8(const ulonglong2& b0, const ulonglon
     }
 }
 
+// EXT, a round with stop-candidate threats: the pair loop carries EVERY term of the score, because a triggered elector multiplies
+// the whole score of the candidates acceptable to it (model.py:400-415) and "acceptable" is a per-(elector, candidate) fact.
+// In m units (score / A_e), for NE electors of a lane and one chunk of 8 candidates:
+//     mm  = min(BP'_c, R_e BQ'_c) + Ainv_e * ( [region_c == region_e] * bonus * phi_c + bandwagon_c * phi_c )     (BP', BQ': phi folded)
+//     acc += mm ;  accA += [acceptable(e, c)] * 2 mm        (the caller adds (boost - 1) / 2 * accA for a triggered elector)
+// The two 0/1 facts come as bytes (0x40 = yes) that ONE byte permute turns into the floats 2.0 / 0.0 (the byte becomes the float's
+// top byte), so a pair costs 1 FMNMX + 2 PRMT on the ALU pipe and 2.5 packed instructions on the FMA pipe; the candidate operands
+// (table, phi, bandwagon) are warp-uniform 128-bit loads shared by the NE electors.
+__device__ __forceinline__ float byte_w2(uint32_t w, int i) { return __uint_as_float(__byte_perm(w, 0u, 0x0444u | ((uint32_t)i << 12))); }
+
+template <int NE>
+__device__ __forceinline__ void chunk_ext8(const float* tc, const float* ph, const float* bwc, float hbonus, const uint2 (&ab)[NE], const uint2 (&rb)[NE],
+                                           const float (&Re)[NE], const float (&Ai)[NE], unsigned long long (&acc)[NE], unsigned long long (&accA)[NE]) {
+    const ulonglong2* t4 = reinterpret_cast<const ulonglong2*>(tc);
+    const ulonglong2* p4 = reinterpret_cast<const ulonglong2*>(ph);
+    const ulonglong2* w4 = reinterpret_cast<const ulonglong2*>(bwc);
+    const unsigned long long hb2 = f2_pack(hbonus, hbonus);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const ulonglong2 b = t4[2 * h], c = t4[2 * h + 1];                    // BP', BQ' of four candidates
+        const ulonglong2 f = p4[h], w = w4[h];                                // phi, bandwagon * phi
+        const unsigned long long rbx = f2_mul(hb2, f.x), rby = f2_mul(hb2, f.y);   // bonus / 2 * phi
+#pragma unroll
+        for (int t = 0; t < NE; ++t) {
+            const unsigned long long r2 = f2_pack(Re[t], Re[t]), a2 = f2_pack(Ai[t], Ai[t]);
+            const uint32_t rw = h ? rb[t].y : rb[t].x, aw = h ? ab[t].y : ab[t].x;
+            {
+                const unsigned long long t2 = f2_mul(r2, c.x);
+                const unsigned long long m2 = f2_pack(fminf(f2_lo(b.x), f2_lo(t2)), fminf(f2_hi(b.x), f2_hi(t2)));
+                const unsigned long long fl = f2_fma(f2_pack(byte_w2(rw, 0), byte_w2(rw, 1)), rbx, w.x);
+                const unsigned long long mm = f2_fma(a2, fl, m2);
+                acc[t] = f2_add(acc[t], mm);
+                accA[t] = f2_fma(f2_pack(byte_w2(aw, 0), byte_w2(aw, 1)), mm, accA[t]);
+            }
+            {
+                const unsigned long long t2 = f2_mul(r2, c.y);
+                const unsigned long long m2 = f2_pack(fminf(f2_lo(b.y), f2_lo(t2)), fminf(f2_hi(b.y), f2_hi(t2)));
+                const unsigned long long fl = f2_fma(f2_pack(byte_w2(rw, 2), byte_w2(rw, 3)), rby, w.y);
+                const unsigned long long mm = f2_fma(a2, fl, m2);
+                acc[t] = f2_add(acc[t], mm);
+                accA[t] = f2_fma(f2_pack(byte_w2(aw, 2), byte_w2(aw, 3)), mm, accA[t]);
+            }
+        }
+    }
+}
+
+// EXT: is some threat of this round unacceptable to the elector (model.py:384-400)?  thr = the round's threat bits, arow = the elector's
+// "acceptable" bits, W words each.
+__device__ __forceinline__ bool ext_triggered(const uint32_t* thr, const uint32_t* arow, int W) {
+    uint32_t any = 0;
+    for (int w = 0; w < W; ++w) any |= thr[w] & ~__ldg(arow + w);
+    return any != 0;
+}
+
 // Per-elector corrections to the exponential-part prefix, in m units: the self score (removed from e's
 // chunk on, model.py:418-424) and stickiness (added from prev's chunk on, model.py:357-367).
 template <int LC, bool MODEL, bool FACT>
@@ -286,19 +398,41 @@ __device__ __forceinline__ Corr32 corrections32(const LaneCtx32& k, int e, const
     return cr;
 }
 
+// EXT form of the same corrections (full-field rounds: k.T is the phi-folded table when a candidate is fatigued, k.bw = bandwagon * phi):
+// the whole self score and the whole stickiness increment, in m units, boost included.
+template <int LC, bool FACT>
+__device__ __forceinline__ Corr32 corrections32_ext(const LaneCtx32& k, int e, const Elector32& el) {
+    Corr32 cr;
+    float fe = k.bonus * k.phi[pad_c<LC>(e)];              // the self pair is of e's own region
+    if (k.use_bw) fe += k.bw[pad_c<LC>(e)];
+    cr.see = fmaf(fe, el.Ainv, pair_m32<LC, FACT>(k, e, el));
+    if (el.trig && acc_bit(el.arow, e)) cr.see *= k.boost;
+    cr.je = e / k.L;
+    cr.jp = 0x7fffffff; cr.sadd = 0.f;
+    if (el.prev >= 0 && el.prev != e) {
+        float fl = (k.reg[el.prev] == el.g) ? k.bonus * k.phi[pad_c<LC>(el.prev)] : 0.f;
+        if (k.use_bw) fl += k.bw[pad_c<LC>(el.prev)];
+        cr.sadd = fmaf(fl, el.Ainv, pair_m32<LC, FACT>(k, el.prev, el)) * (k.st1p - 1.0f);
+        if (el.trig && acc_bit(el.arow, el.prev)) cr.sadd *= k.boost;
+        cr.jp = el.prev / k.L;
+    }
+    return cr;
+}
+
 // prefix of the scores over chunks 0..j:  A * (exponential part + point rules) + regional bonus + bandwagon
-template <bool MODEL>
+template <bool MODEL, bool EXT = false>
 __device__ __forceinline__ float probe32(const LaneCtx32& k, const float* pref, int pstride, const float* rbrow, float A, const Corr32& cr, int j) {
     float m = pref[j * pstride];
     m = j >= cr.je ? m - cr.see : m;
     if (MODEL) m = j >= cr.jp ? m + cr.sadd : m;
+    if (EXT) { if (k.flat_in_m) return A * m; }             // warp-uniform
     float v = fmaf(k.bonus, rbrow[j], A * m);
     if (MODEL && k.use_bw) v += k.bwp[j];
     return v;
 }
 
 // The 8 scores of chunk jstar of elector e's row with every term inline (LC == 8): what the re-scan of finish_draw sums.
-template <bool MODEL, bool FACT>
+template <bool MODEL, bool FACT, bool EXT = false>
 __device__ __forceinline__ void rescan8_scores(const LaneCtx32& k, int jstar, int e, const Elector32& el, float (&v)[8]) {
     const int c0 = jstar * 8;
     const float4* t4 = reinterpret_cast<const float4*>(k.T + 20 * jstar);
@@ -313,16 +447,25 @@ __device__ __forceinline__ void rescan8_scores(const LaneCtx32& k, int jstar, in
         if (k.use_bw) { ba = *reinterpret_cast<const float4*>(k.bw + 12 * jstar); bb = *reinterpret_cast<const float4*>(k.bw + 12 * jstar + 4); }
     }
     const float nb = k.nb;
-#define CSIM_RESCAN(i, xv, pv, rv, bv)                                          \
+    // EXT: the table already carries phi (fatigue) on the exponential part and k.bw on the bandwagon; the regional bonus takes it here;
+    // a triggered elector boosts the candidates of this chunk that are acceptable to it
+    float4 fa = make_float4(1.f, 1.f, 1.f, 1.f), fb = fa;
+    uint32_t abits = 0;
+    if (EXT) {
+        fa = *reinterpret_cast<const float4*>(k.phi + 12 * jstar); fb = *reinterpret_cast<const float4*>(k.phi + 12 * jstar + 4);
+        if (el.trig) abits = (__ldg(el.arow + (c0 >> 5)) >> (c0 & 31)) & 0xFFu;
+    }
+#define CSIM_RESCAN(i, xv, pv, rv, bv, fv)                                      \
     {                                                                       \
         const float m = FACT ? fminf((pv), el.R * (xv)) : ex2_approx(fabsf(el.x - (xv)) * nb) * (pv); \
-        float s = fmaf(el.A, m, (rv));                                      \
+        float s = fmaf(el.A, m, EXT ? (rv) * (fv) : (rv));                  \
         if (MODEL) { s += (bv); if (ip == (i)) s *= k.st1p; }               \
+        if (EXT) { if ((abits >> (i)) & 1u) s *= k.boost; }                 \
         if (is == (i)) s = 0.0f;                                            \
         v[i] = s;                                                           \
     }
-    CSIM_RESCAN(0, xa.x, pa.x, ra.x, ba.x) CSIM_RESCAN(1, xa.y, pa.y, ra.y, ba.y) CSIM_RESCAN(2, xa.z, pa.z, ra.z, ba.z) CSIM_RESCAN(3, xa.w, pa.w, ra.w, ba.w)
-    CSIM_RESCAN(4, xb.x, pb.x, rb.x, bb.x) CSIM_RESCAN(5, xb.y, pb.y, rb.y, bb.y) CSIM_RESCAN(6, xb.z, pb.z, rb.z, bb.z) CSIM_RESCAN(7, xb.w, pb.w, rb.w, bb.w)
+    CSIM_RESCAN(0, xa.x, pa.x, ra.x, ba.x, fa.x) CSIM_RESCAN(1, xa.y, pa.y, ra.y, ba.y, fa.y) CSIM_RESCAN(2, xa.z, pa.z, ra.z, ba.z, fa.z) CSIM_RESCAN(3, xa.w, pa.w, ra.w, ba.w, fa.w)
+    CSIM_RESCAN(4, xb.x, pb.x, rb.x, bb.x, fb.x) CSIM_RESCAN(5, xb.y, pb.y, rb.y, bb.y, fb.y) CSIM_RESCAN(6, xb.z, pb.z, rb.z, bb.z, fb.z) CSIM_RESCAN(7, xb.w, pb.w, rb.w, bb.w, fb.w)
 #undef CSIM_RESCAN
 }
 
@@ -334,16 +477,16 @@ static __device__ __noinline__ int uniform_row_vote(float u, int C) {
 }
 
 // Phase 2: given the exponential-part prefix over chunks (pref[j * pstride], m units), draw the vote.
-template <int LC, bool MODEL, bool FACT, bool PROBE = false>
+template <int LC, bool MODEL, bool FACT, bool PROBE = false, bool EXT = false>
 __device__ __forceinline__ int finish_draw(const LaneCtx32& k, const float* pref, int pstride, int e, float u, const Elector32& el, const Corr32& cr) {
     const int C = k.C, L = LC > 0 ? LC : k.L, nch = k.nch;
-    const float* rbrow = k.rbp + el.g * nch;
+    const float* rbrow = (EXT ? k.rbp_cur : k.rbp) + el.g * nch;
     if (PROBE) {            // csim_engine_probs: the numbers this draw is made from
-        for (int j = 0; j < nch; ++j) k.dbg_prefix[(size_t)e * k.dbg_cap + j] = probe32<MODEL>(k, pref, pstride, rbrow, el.A, cr, j);
+        for (int j = 0; j < nch; ++j) k.dbg_prefix[(size_t)e * k.dbg_cap + j] = probe32<MODEL, EXT>(k, pref, pstride, rbrow, el.A, cr, j);
         for (int js = 0; js < nch; ++js) {
             if (LC == 8) {
                 float v[8];
-                rescan8_scores<MODEL, FACT>(k, js, e, el, v);
+                rescan8_scores<MODEL, FACT, EXT>(k, js, e, el, v);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) if (js * 8 + i < C) k.dbg_scores[(size_t)e * C + js * 8 + i] = v[i];
             } else {
@@ -351,7 +494,7 @@ __device__ __forceinline__ int finish_draw(const LaneCtx32& k, const float* pref
             }
         }
     }
-    const float S = probe32<MODEL>(k, pref, pstride, rbrow, el.A, cr, nch - 1);
+    const float S = probe32<MODEL, EXT>(k, pref, pstride, rbrow, el.A, cr, nch - 1);
     if (__builtin_expect(!(S > 0.0f), 0))          // all scores vanished: the reference makes the row uniform INCLUDING self (model.py:447-449)
         return uniform_row_vote(u, C);
     const float tgt = u * S;
@@ -362,13 +505,13 @@ __device__ __forceinline__ int finish_draw(const LaneCtx32& k, const float* pref
     int pos = 0;
     float below = 0.0f;
     if (nch > k.step0) {
-        const float f = probe32<MODEL>(k, pref, pstride, rbrow, el.A, cr, nch - k.step0 - 1);
+        const float f = probe32<MODEL, EXT>(k, pref, pstride, rbrow, el.A, cr, nch - k.step0 - 1);
         if (f <= tgt) { pos = nch - k.step0; below = f; }
     }
 #pragma unroll
     for (int step = 16; step > 0; step >>= 1) {
         if (step < k.step0) {
-            const float f = probe32<MODEL>(k, pref, pstride, rbrow, el.A, cr, pos + step - 1);
+            const float f = probe32<MODEL, EXT>(k, pref, pstride, rbrow, el.A, cr, pos + step - 1);
             if (f <= tgt) { pos += step; below = f; }
         }
     }
@@ -378,7 +521,7 @@ __device__ __forceinline__ int finish_draw(const LaneCtx32& k, const float* pref
     int cnt = 0;
     if (LC == 8) {
         float v[8];
-        rescan8_scores<MODEL, FACT>(k, jstar, e, el, v);
+        rescan8_scores<MODEL, FACT, EXT>(k, jstar, e, el, v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) { cum += v[i]; cnt += (cum <= tgt) ? 1 : 0; }
     } else {
@@ -412,8 +555,9 @@ __device__ __forceinline__ void stage_round_table(float* dst, const Dense32Args&
     }
 }
 
-template <int LC, bool MODEL, bool FACT, bool PROBE = false>
-__global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a) {
+template <int LC, bool MODEL, bool FACT, bool PROBE = false, bool EXT = false>
+__global__ void __launch_bounds__(EXT ? 512 : 256, EXT ? 1 : CSIM_MINB) k_trials_dense32(Dense32Args a) {
+    static_assert(!EXT || (LC == 8 && MODEL && FACT), "the EXT instantiation exists for chunks of 8, the model wiring and the factorised exponential");
     constexpr int NE = CSIM_NE;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -430,6 +574,27 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
     float* rbp = (float*)(smem_raw + dense32_o_rbp(nch, L));           // [G][nch]: #{c in chunks 0..j : region_c == g}
     float* rbf = (float*)(smem_raw + dense32_o_rbf(nch, L, G));        // [G][rbpitch]: the current set's bonus where region_c == g, else 0
     float* tabs = (float*)(smem_raw + dense32_o_tabs(nch, L, G));      // [n_tab][2 CP] round tables of the current set (cta_tabs)
+    // EXT: acceptable-bytes of the current set [nch][epitch], region-match bytes [G][nch] and region bit rows [G][Wb] of the roster
+    uint2* accb_s = nullptr; uint2* regb = nullptr; uint32_t* regbits = nullptr;
+    const int Wb = (C + 31) >> 5;
+    if (EXT) {
+        accb_s = (uint2*)(smem_raw + a.o_ext); regb = accb_s + (size_t)nch * a.epitch; regbits = (uint32_t*)(regb + G * nch);
+        for (int i = threadIdx.x; i < G * nch; i += blockDim.x) {
+            const int g = i / nch, j = i - g * nch;
+            uint32_t lo = 0, hi = 0;
+            for (int q = 0; q < 8; ++q) {
+                const int c = 8 * j + q;
+                if (c < C && a.ro.region[c] == g) { if (q < 4) lo |= 0x40u << (8 * q); else hi |= 0x40u << (8 * (q - 4)); }
+            }
+            regb[i] = make_uint2(lo, hi);
+        }
+        for (int i = threadIdx.x; i < G * Wb; i += blockDim.x) {
+            const int g = i / Wb, w = i - g * Wb;
+            uint32_t m = 0;
+            for (int b = 0; b < 32; ++b) { const int c = 32 * w + b; if (c < C && a.ro.region[c] == g) m |= 1u << b; }
+            regbits[i] = m;
+        }
+    }
     for (int c = threadIdx.x; c < CP; c += blockDim.x) reg[c] = c < C ? a.ro.region[c] : -1;
     for (int i = threadIdx.x; i < nch * G; i += blockDim.x) {
         const int j = i / G, g = i - j * G;
@@ -440,7 +605,7 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
     // ---- per-warp state ----------------------------------------------------------------------
     unsigned char* base = smem_raw + a.cta_smem + (size_t)wib * a.warp_smem;
     // 16-byte aligned float arrays first (they are read with 128-bit loads), then the int arrays
-    float* wtab = (float*)base;                 if (!a.cta_tabs) base += sizeof(float) * TF;              // own round table (fallback)
+    float* wtab = (float*)base;                 if (!a.cta_tabs || EXT) base += sizeof(float) * TF;       // own round table (fallback; EXT: the phi-folded copy)
     float* pref = (float*)base;                 base += sizeof(float) * DENSE32_PREF_COLS * nch * 32;   // prefix columns [j][t][lane]
     float* bw = nullptr; float* bwp = nullptr;
     if (MODEL) {
@@ -457,6 +622,17 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
     uint8_t* mark = (uint8_t*)base;               base += (Ei + 15) & ~15;
     uint32_t* wq = (uint32_t*)base;               // [32][4]: the quad of Philox words of each lane's current four electors (16-byte slots)
     uint32_t* tailw = wq + 32 * 4;                // [32][4]: the quads of the electors beyond the last whole 128, for several rounds ahead
+    // EXT per-warp state: fatigue factor per candidate (padded like bw), phi-weighted regional prefix, fatigue / threat bit rows, and
+    // the tallies of the last Fmax rounds (bytes: E <= 255)
+    float* phi = nullptr; float* rbpw = nullptr; uint32_t* fatbits = nullptr; uint32_t* thrbits = nullptr; uint8_t* hist = nullptr;
+    if (EXT) {
+        unsigned char* xb = (unsigned char*)(tailw + 32 * 4);
+        phi = (float*)xb;          xb += sizeof(float) * CPP;
+        rbpw = (float*)xb;         xb += sizeof(float) * G * ((nch + 3) & ~3);
+        fatbits = (uint32_t*)xb;   xb += 32;
+        thrbits = (uint32_t*)xb;   xb += 32;
+        hist = xb;
+    }
 
     const int m_quads = E >> 7;                              // whole Philox quads per lane
     const int n_main = 4 * m_quads;
@@ -474,6 +650,11 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
     kx.step0 = 1;
     while (kx.step0 * 2 <= nch) kx.step0 *= 2;
     kx.dbg_scores = a.probe_scores; kx.dbg_prefix = a.probe_prefix; kx.dbg_cap = a.probe_cap;
+    kx.phi = phi; kx.rbp_cur = rbp; kx.boost = 1.f; kx.flat_in_m = false;
+    // EXT: the current set's fatigue / stop-candidate constants, and this round's number of threats (0: no elector can be triggered)
+    bool en_fat = false, en_stop = false, neg_T = false;
+    int Fw = 0, fat_top_n = 0, fat_cnt = 0, stop_cnt = 0, n_thr = 0;
+    float pen = 1.f, bm1h = 0.f;
 
     int cur_set = -1;
     float bw_strength = 0.f, pwf = 1.f;
@@ -483,12 +664,19 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
     uint32_t tabA = 0;                        // element offset of this round's A | 1/A | BP | BQ block inside a.tab (32-bit: the launcher checks the size)
 
     // one elector's scalars for this round
-    auto load_elector = [&](int e, bool sticky_live) {
+    auto load_elector = [&](int e, bool sticky_live, int trig_known = -1) {
         Elector32 el;
         if (FACT) { el.A = __ldg(a.tab + (tabA + (uint32_t)e)); el.Ainv = __ldg(a.tab + (tabA + (uint32_t)(CP + e))); el.R = el.Ainv * el.Ainv; el.x = 0.f; }
         else { el.A = 1.f; el.Ainv = 1.f; el.R = 1.f; el.x = __ldg(a.ro.x32 + e); }
         el.g = reg[e];
         el.prev = (MODEL && sticky_live) ? votes[e] : -1;
+        el.trig = false; el.arow = nullptr;
+        if (EXT) {
+            if (n_thr > 0) {                                 // stop-candidate: triggered when some threat is unacceptable to e (model.py:384-400)
+                el.arow = a.accmask + ((size_t)cur_set * E + e) * a.accw;
+                el.trig = trig_known >= 0 ? trig_known != 0 : ext_triggered(thrbits, el.arow, Wb);
+            }
+        }
         return el;
     };
 
@@ -526,6 +714,15 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                                                 whole ? CP : a.nk_chunks * L);
                 }
             if (MODEL) for (int c = lane; c < CPP; c += 32) bw[c] = 0.0f;
+            if (EXT) {
+                en_fat = S->en_fat != 0; en_stop = S->en_stop != 0; neg_T = 0.0 > S->stop_T;
+                Fw = S->fat_rounds; fat_top_n = S->fat_top_n; fat_cnt = S->fat_cnt; stop_cnt = S->stop_cnt;
+                pen = S->f_fat_pen; kx.boost = S->f_stop_boost; bm1h = 0.5f * (S->f_stop_boost - 1.0f);
+                if (en_stop) {
+                    const uint2* src = a.accb + (size_t)set * nch * a.epitch;
+                    for (int i = threadIdx.x; i < nch * a.epitch; i += blockDim.x) accb_s[i] = __ldg(src + i);
+                }
+            }
             __syncthreads();
         }
         const float* nbeta = a.nbeta + (size_t)set * R;
@@ -542,12 +739,15 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
             int ef0 = 0, ef1 = 0;                                    // run-off pair when fast2
             int tail_r0 = -(1 << 30);                                // first round of the current tail stash (none yet)
             if (R == 0) { for (int c = lane; c < C; c += 32) tally[c] = 0; __syncwarp(); }
+            int n_hist = 0;                                          // EXT: rounds in the tally history
+            if (EXT) { for (int c = lane; c < CPP; c += 32) { phi[c] = 1.0f; bw[c] = 0.0f; } n_thr = 0; }
             if (PROBE && MODEL && (a.probe_prev_vote || a.probe_prev_count)) {      // start from the given previous-round state
                 for (int c = lane; c < C; c += 32) {
                     prev_tally[c] = a.probe_prev_count ? a.probe_prev_count[c] : 0;
                     votes[c] = a.probe_prev_vote ? a.probe_prev_vote[c] : -1;
+                    if (EXT) hist[c] = (uint8_t)prev_tally[c];
                 }
-                have_prev = true;
+                have_prev = true; n_hist = 1;
                 __syncwarp();
             }
 
@@ -564,6 +764,98 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                     stage_round_table<LC, FACT>(wtab, a, FACT ? a.tab + tabA : nullptr, pwf, CP, C, lane, 32);
                     kx.T = wtab;
                 }
+                bool use_fat = false;
+                if (EXT) {
+                    n_thr = 0;
+                    __syncwarp();
+                    // ---- candidate fatigue: the set, simulate.py:84-118, decided in fp64 exactly as exact64.cuh decides it; the
+                    //      factor per candidate, model.py:372-379
+                    if (en_fat) {
+                        bool window = false;
+                        if (r > Fw) {
+                            for (int c = lane; c < C; c += 32) mark[c] = 0;
+                            __syncwarp();
+                            const int nh = n_hist < Fw ? n_hist : Fw;
+                            if (fat_top_n > 0 && n_hist > 0 && nh > 0) {
+                                double* avg = (double*)pref;                     // the prefix columns are not live between rounds
+                                for (int c = lane; c < C; c += 32) {
+                                    double acc = __ddiv_rn((double)hist[(size_t)((n_hist - nh) % a.Fmax) * Ei + c], (double)E);
+                                    for (int q = 1; q < nh; ++q)
+                                        acc = __dadd_rn(acc, __ddiv_rn((double)hist[(size_t)((n_hist - nh + q) % a.Fmax) * Ei + c], (double)E));
+                                    avg[c] = __ddiv_rn(acc, (double)nh);
+                                }
+                                __syncwarp();
+                                const int n_imm = fat_top_n < C ? fat_top_n : C;
+                                for (int j = 0; j < n_imm; ++j) {                // top-n by mean share; ties -> highest index
+                                    double bv = -1.0; int ba = -1;
+                                    for (int c = lane; c < C; c += 32)
+                                        if (!mark[c] && (ba < 0 || avg[c] >= bv)) { bv = avg[c]; ba = c; }
+#pragma unroll
+                                    for (int off = 16; off > 0; off >>= 1) {
+                                        const double ov = __shfl_xor_sync(CSIM_FULL, bv, off);
+                                        const int oa = __shfl_xor_sync(CSIM_FULL, ba, off);
+                                        if (oa >= 0 && (ba < 0 || ov > bv || (ov == bv && oa > ba))) { bv = ov; ba = oa; }
+                                    }
+                                    if (lane == 0 && ba >= 0) mark[ba] = 1;
+                                    __syncwarp();
+                                }
+                            }
+                            window = n_hist >= Fw;
+                        }
+                        uint32_t anyf = 0;
+                        for (int c0 = 0; c0 < 32 * Wb; c0 += 32) {
+                            const int c = c0 + lane;
+                            bool f = false;
+                            if (window && c < C && !mark[c]) {
+                                f = true;
+                                for (int q = 0; q < Fw && f; ++q)                  // share < threshold, as an integer test (DevSet::fat_cnt)
+                                    f = (int)hist[(size_t)((n_hist - Fw + q) % a.Fmax) * Ei + c] < fat_cnt;
+                            }
+                            if (PROBE && a.probe_fatigued) f = c < C && a.probe_fatigued[c] != 0;
+                            const uint32_t m = __ballot_sync(CSIM_FULL, f);
+                            anyf |= m;
+                            if (lane == 0) fatbits[c0 >> 5] = m;
+                            if (c < CP) phi[pad_c<LC>(c)] = f ? pen : 1.0f;
+                        }
+                        use_fat = anyf != 0;
+                    }
+                    // ---- stop-candidate threats, model.py:384-400: candidates whose last share exceeds the threshold.  Round 1 has no
+                    //      previous shares: the reference tests 0.0 > threshold against every candidate (simulate.py:73, model.py:397),
+                    //      so with a NEGATIVE threat share every candidate is a threat already then
+                    if (en_stop && (have_prev || neg_T)) {
+                        const bool all_thr = !have_prev;
+                        for (int c0 = 0; c0 < 32 * Wb; c0 += 32) {
+                            const int c = c0 + lane;
+                            const bool t = c < C && (all_thr || prev_tally[c] >= stop_cnt);   // share > threshold (DevSet::stop_cnt)
+                            const uint32_t m = __ballot_sync(CSIM_FULL, t);
+                            n_thr += __popc(m);
+                            if (lane == 0) thrbits[c0 >> 5] = m;
+                        }
+                    }
+                    __syncwarp();
+                    kx.flat_in_m = n_thr > 0;
+                    kx.rbp_cur = rbp;
+                    if (!have_eff && use_fat) {                  // a full-field round with fatigued candidates plays from the phi-folded table
+                        const float* Ts = kx.T;
+                        for (int c = lane; c < CP; c += 32) {
+                            const int o = tab_off<LC>(c);
+                            const float f = phi[pad_c<LC>(c)];
+                            wtab[o] = Ts[o] * f; wtab[o + 4] = Ts[o + 4] * f;
+                        }
+                        kx.T = wtab;
+                        if (n_thr == 0) {                        // regional prefix with phi: (same-region candidates) - (1 - pen) (fatigued ones)
+                            for (int g = lane; g < G; g += 32) {
+                                int nf = 0;
+                                for (int j = 0; j < nch; ++j) {
+                                    const int sh = 8 * (j & 3);
+                                    nf += __popc((fatbits[j >> 2] >> sh) & (regbits[g * Wb + (j >> 2)] >> sh) & 0xFFu);
+                                    rbpw[g * nch + j] = (rbp[g * nch + j] - (float)nf) + pen * (float)nf;
+                                }
+                            }
+                            kx.rbp_cur = rbpw;
+                        }
+                    }
+                }
                 if (MODEL) {
                     if (has_bw && have_prev) {                                   // model.py:326-354
                         int mx, arg;
@@ -571,7 +863,11 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                         if (mx > 0) {
                             kx.use_bw = true;
                             const float inv = 1.0f / (float)mx;
-                            for (int c = lane; c < C; c += 32) bw[pad_c<LC>(c)] = (float)prev_tally[c] * inv * bw_strength;
+                            for (int c = lane; c < C; c += 32) {
+                                float v = (float)prev_tally[c] * inv * bw_strength;
+                                if (EXT) v *= phi[pad_c<LC>(c)];                  // fatigue scales the whole score (model.py:379)
+                                bw[pad_c<LC>(c)] = v;
+                            }
                             __syncwarp();
                             float s = 0.f;                                       // bandwagon of chunk `lane`, then prefix over chunks
                             if (lane < nch) for (int c = lane * L; c < (lane + 1) * L; ++c) s += bw[pad_c<LC>(c)];
@@ -611,19 +907,49 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
 #pragma unroll 1
                         for (int g = 0; g < 4 / NE; ++g) {
                             const int e0 = 4 * q + NE * g;
-                            float xe[NE], Re[NE];
+                            float xe[NE], Re[NE], Ai[NE];
                             unsigned long long acc[NE];
 #pragma unroll
                             for (int i = 0; i < NE; ++i) {          // all the pair loop needs of an elector: R_e (or its ideology)
-                                if (FACT) { const float Ainv = __ldg(a.tab + (tabA + (uint32_t)(CP + e0 + i))); Re[i] = Ainv * Ainv; xe[i] = 0.f; }
-                                else { Re[i] = 1.f; xe[i] = __ldg(a.ro.x32 + e0 + i); }
+                                if (FACT) { const float Ainv = __ldg(a.tab + (tabA + (uint32_t)(CP + e0 + i))); Re[i] = Ainv * Ainv; xe[i] = 0.f; Ai[i] = Ainv; }
+                                else { Re[i] = 1.f; xe[i] = __ldg(a.ro.x32 + e0 + i); Ai[i] = 1.f; }
                                 acc[i] = 0ull;
                             }
                             // phase 1: nothing but the pair arithmetic, its operand loads and one prefix store per elector
                             const float* tc = kx.T;
                             const int tstep = LC == 8 ? 20 : L;
                             float* pc = pref + lane;                                    // [j][t][lane]
-                            if (LC == 8 && FACT && CSIM_DENSE_PIPELINE) {
+                            uint32_t trigm = 0;                                         // EXT: bit i = elector e0 + i is triggered
+                            if (EXT && n_thr > 0) {
+                                // stop-candidate live this round: the masked pair loop (chunk_ext8), every term in the prefix column
+                                float bmh[NE];
+                                const uint2* abp[NE]; const uint2* rbq[NE];
+                                unsigned long long accA[NE];
+#pragma unroll
+                                for (int i = 0; i < NE; ++i) {
+                                    const int e = e0 + i;
+                                    const bool tg = ext_triggered(thrbits, a.accmask + ((size_t)cur_set * E + e) * a.accw, Wb);
+                                    trigm |= (tg ? 1u : 0u) << i;
+                                    bmh[i] = tg ? bm1h : 0.0f;
+                                    abp[i] = accb_s + ((qi << 7) + ((NE * g + i) << 5) + lane);     // dense32_slot(e, E)
+                                    rbq[i] = regb + reg[e] * nch;
+                                    accA[i] = 0ull;
+                                }
+                                const float hbonus = 0.5f * kx.bonus;
+                                const float* ph = phi; const float* bwc = bw;
+                                const int epitch = a.epitch;
+#pragma unroll 1
+                                for (int j = 0; j < nch; ++j) {
+                                    uint2 ab[NE], rb[NE];
+#pragma unroll
+                                    for (int i = 0; i < NE; ++i) { ab[i] = abp[i][j * epitch]; rb[i] = rbq[i][j]; }
+                                    chunk_ext8<NE>(tc, ph, bwc, hbonus, ab, rb, Re, Ai, acc, accA);
+#pragma unroll
+                                    for (int i = 0; i < NE; ++i)
+                                        pc[i * 32] = fmaf(bmh[i], f2_lo(accA[i]) + f2_hi(accA[i]), f2_lo(acc[i]) + f2_hi(acc[i]));
+                                    tc += 20; ph += 12; bwc += 12; pc += NE * 32;
+                                }
+                            } else if (LC == 8 && FACT && CSIM_DENSE_PIPELINE) {
                                 // software-pipelined: chunk j + 1's operands are in flight while chunk j is evaluated (the load past the
                                 // last chunk reads the next table / the warp's own arrays: inside the allocation, never used)
                                 const ulonglong2* t4 = reinterpret_cast<const ulonglong2*>(tc);
@@ -651,10 +977,12 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
 #pragma unroll 1
                             for (int i = 0; i < NE; ++i) {
                                 const int e = e0 + i;
-                                const Elector32 el = load_elector(e, sticky_live);
-                                const Corr32 cr = corrections32<LC, MODEL, FACT>(kx, e, el);
+                                const Elector32 el = load_elector(e, sticky_live, EXT ? (int)((trigm >> i) & 1u) : -1);
+                                Corr32 cr;
+                                if constexpr (EXT) cr = corrections32_ext<LC, FACT>(kx, e, el);
+                                else cr = corrections32<LC, MODEL, FACT>(kx, e, el);
                                 const uint32_t wa = wq[4 * lane + NE * g + i];
-                                const int vote = finish_draw<LC, MODEL, FACT, PROBE>(kx, pref + i * 32 + lane, NE * 32, e, u24_from_word(wa), el, cr);
+                                const int vote = finish_draw<LC, MODEL, FACT, PROBE, EXT>(kx, pref + i * 32 + lane, NE * 32, e, u24_from_word(wa), el, cr);
                                 atomicAdd(&tally[vote], 1);
                                 if (MODEL) votes[e] = vote;        // read only by this lane for its own electors: in-place is safe
                             }
@@ -679,11 +1007,25 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                         float run = 0.f;
                         __syncwarp();
                         if (act) {
-                            for (int j = j_lo; j < j_hi; ++j) {
-                                unsigned long long acc[1] = {0ull};
-                                chunk_acc<1, LC, FACT>(kx, kx.T + j * tstep, xe1, Re1, acc);
-                                run += f2_lo(acc[0]) + f2_hi(acc[0]);
-                                cl[j] = run;
+                            if (EXT && n_thr > 0) {                  // stop-candidate live: the masked pair loop (see the main part)
+                                const float Ai1[1] = {el.Ainv};
+                                const float bmh1 = el.trig ? bm1h : 0.0f, hbonus = 0.5f * kx.bonus;
+                                const uint2* abp = accb_s + e;       // dense32_slot(e, E) == e for the leftover electors
+                                const uint2* rbq = regb + el.g * nch;
+                                for (int j = j_lo; j < j_hi; ++j) {
+                                    unsigned long long acc[1] = {0ull}, accA[1] = {0ull};
+                                    const uint2 ab[1] = {abp[j * a.epitch]}, rb[1] = {rbq[j]};
+                                    chunk_ext8<1>(kx.T + j * 20, phi + j * 12, bw + j * 12, hbonus, ab, rb, Re1, Ai1, acc, accA);
+                                    run += fmaf(bmh1, f2_lo(accA[0]) + f2_hi(accA[0]), f2_lo(acc[0]) + f2_hi(acc[0]));
+                                    cl[j] = run;
+                                }
+                            } else {
+                                for (int j = j_lo; j < j_hi; ++j) {
+                                    unsigned long long acc[1] = {0ull};
+                                    chunk_acc<1, LC, FACT>(kx, kx.T + j * tstep, xe1, Re1, acc);
+                                    run += f2_lo(acc[0]) + f2_hi(acc[0]);
+                                    cl[j] = run;
+                                }
                             }
                         }
                         float off = run;                             // inclusive scan over the P lanes of an elector, then exclusive
@@ -695,8 +1037,10 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                         if (act && sub > 0) for (int j = j_lo; j < j_hi; ++j) cl[j] += off;
                         __syncwarp();
                         if (act && sub == 0) {
-                            const Corr32 cr = corrections32<LC, MODEL, FACT>(kx, e, el);
-                            const int vote = finish_draw<LC, MODEL, FACT, PROBE>(kx, cl, 1, e, u24_from_word(tail_r[e]), el, cr);
+                            Corr32 cr;
+                            if constexpr (EXT) cr = corrections32_ext<LC, FACT>(kx, e, el);
+                            else cr = corrections32<LC, MODEL, FACT>(kx, e, el);
+                            const int vote = finish_draw<LC, MODEL, FACT, PROBE, EXT>(kx, cl, 1, e, u24_from_word(tail_r[e]), el, cr);
                             atomicAdd(&tally[vote], 1);
                             if (MODEL) votes[e] = vote;
                         }
@@ -709,15 +1053,20 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                         // regions and bandwagon terms live in registers, and a vote is decided in m units (score / A_e: the
                         // comparison v0 > u (v0 + v1) does not depend on the positive factor A_e), so an elector costs one load.
                         const int o0 = tab_off<LC>(0), o1 = tab_off<LC>(1);
-                        const float P0 = kx.T[o0], X0 = kx.T[o0 + kx.xoff], P1 = kx.T[o1], X1 = kx.T[o1 + kx.xoff];
+                        float P0 = kx.T[o0], X0 = kx.T[o0 + kx.xoff], P1 = kx.T[o1], X1 = kx.T[o1 + kx.xoff];
                         const int g0 = reg[0], g1 = reg[1];
                         float f0 = 0.f, f1 = 0.f;
                         if (MODEL && kx.use_bw) { f0 = bw[pad_c<LC>(0)]; f1 = bw[pad_c<LC>(1)]; }
                         const float bonus = kx.bonus, nb = kx.nb, st1p = kx.st1p;
+                        float bon0 = bonus, bon1 = bonus;
+                        if (EXT) {                                   // fatigue scales the two candidates' whole scores (f0, f1 already carry it)
+                            const float ph0 = phi[pad_c<LC>(0)], ph1 = phi[pad_c<LC>(1)];
+                            P0 *= ph0; X0 *= ph0; P1 *= ph1; X1 *= ph1; bon0 *= ph0; bon1 *= ph1;
+                        }
                         auto play = [&](int e, uint32_t wa) {
                             const float u = u24_from_word(wa);
                             const int g = reg[e];
-                            const float b0 = (g == g0 ? bonus : 0.0f) + f0, b1 = (g == g1 ? bonus : 0.0f) + f1;
+                            const float b0 = (g == g0 ? bon0 : 0.0f) + f0, b1 = (g == g1 ? bon1 : 0.0f) + f1;
                             float w0, w1;
                             if (FACT) {
                                 const float Ainv = __ldg(a.tab + (tabA + (uint32_t)(CP + e))), Rr = Ainv * Ainv;
@@ -732,6 +1081,16 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                                 const int prev = votes[e];
                                 if (prev == 0) w0 *= st1p;
                                 if (prev == 1) w1 *= st1p;
+                            }
+                            if (EXT) {
+                                if (n_thr > 0) {                     // a triggered elector boosts the candidates acceptable to it (model.py:400-415)
+                                    const uint32_t* arow = a.accmask + ((size_t)cur_set * E + e) * a.accw;
+                                    if (ext_triggered(thrbits, arow, Wb)) {
+                                        const uint32_t aw = __ldg(arow);
+                                        if (aw & 1u) w0 *= kx.boost;
+                                        if (aw & 2u) w1 *= kx.boost;
+                                    }
+                                }
                             }
                             if (e == 0) w0 = 0.0f;
                             if (e == 1) w1 = 0.0f;
@@ -762,7 +1121,7 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                             const float u = u24_from_word(wa);
                             const Elector32 el = load_elector(e, sticky_live);
                             float sum = 0.f;
-                            for (int j = 0; j < k; ++j) sum += full_score32<LC, MODEL, FACT>(kx, e, j, el);
+                            for (int j = 0; j < k; ++j) sum += full_score32<LC, MODEL, FACT, EXT>(kx, e, j, el);
                             int jsel;
                             if (!(sum > 0.0f)) {
                                 jsel = (int)(u * (float)k);
@@ -770,7 +1129,7 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                                 const float tgt = u * sum;
                                 float cum = 0.f; jsel = -1; int lastpos = 0;
                                 for (int j = 0; j < k; ++j) {
-                                    const float v = full_score32<LC, MODEL, FACT>(kx, e, j, el);
+                                    const float v = full_score32<LC, MODEL, FACT, EXT>(kx, e, j, el);
                                     cum += v;
                                     if (v > 0.0f) lastpos = j;
                                     if (jsel < 0 && v > 0.0f && cum > tgt) jsel = j;
@@ -798,6 +1157,7 @@ __global__ void __launch_bounds__(256, CSIM_MINB) k_trials_dense32(Dense32Args a
                     for (int c = lane; c < C; c += 32)
                         a.out.round_tallies[(t * (uint64_t)R + (uint64_t)(r - 1)) * (uint64_t)C + c] = tally[c];
                 if (MODEL) for (int c = lane; c < C; c += 32) prev_tally[c] = tally[c];
+                if (EXT) { for (int c = lane; c < C; c += 32) hist[(size_t)(n_hist % a.Fmax) * Ei + c] = (uint8_t)tally[c]; ++n_hist; }
                 have_prev = true;
                 if (fast2) {
                     int mx, arg, second;

@@ -1,6 +1,104 @@
 // eng_full.cu — the FULL engine: launcher of k_trials_full32 (full32.cuh)
 #include "internal.cuh"
 #include "full32.cuh"
+#include "dense32.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// The FULL engine's fast path: the EXT instantiation of the dense kernel (dense32.cuh) — the factorised two-elector pair loop with
+// candidate fatigue folded into a per-warp copy of the round table and stop-candidate as a byte-masked second accumulator.  It takes
+// what that formulation can express: E <= 255 (chunks of 8, tallies in bytes), every factor non-negative, a factorisable beta
+// schedule, tables that fit in shared memory.  Everything else stays on k_trials_full32.  `*taken` says whether it ran.
+// ---------------------------------------------------------------------------------------------
+static csim_status launch_dense_ext(csim_ctx* c, const csim_run_args* ra, const std::vector<DevSet>& hs, const BatchDev& b, const TrialOut& out,
+                                    cudaStream_t st, bool any_stop, int accw, bool* taken) {
+    *taken = false;
+    const int E = c->E, G = c->G, R = b.R;
+    if (getenv("CSIM_FULL_LEGACY") || E > 255 || E < 2 || R < 1) return CSIM_OK;
+    for (int i = 0; i < ra->n_param_sets; ++i) {
+        const csim_params& q = ra->params[i];
+        std::vector<double> hb((size_t)R);
+        csim_beta_schedule(&q, 1, R, hb.data());
+        for (double be : hb) if (!(be >= 0.0) || !(be * c->x_half <= 26.0)) return CSIM_OK;      // not factorisable (dense32.cuh header)
+    }
+    Dense32Args a;
+    memset(&a, 0, sizeof a);
+    a.ro = roster_dev(c); a.b = b; a.out = out; a.nbeta = (const float*)c->nbeta.p; a.wiring = CSIM_WIRING_MODEL;
+    int kmax = 1, Fmax = 1;
+    a.n_tab_full = 1;
+    for (const DevSet& s : hs) {
+        kmax = std::max(kmax, s.k); Fmax = std::max(Fmax, s.fat_rounds);
+        a.n_tab_full = std::max(a.n_tab_full, s.k > 0 ? std::min(R, std::max(s.rr, 1)) : R);
+    }
+    a.kmax = kmax; a.Fmax = Fmax;
+    a.L = 8; a.nch = (E + 7) / 8;
+    a.epitch = (E + 1) & ~1;
+    a.accw = accw; a.accmask = (const uint32_t*)c->accm.p;
+    const int nk = (kmax + 7) / 8;
+    const int n_full = std::min(a.n_tab_full, R);
+    const size_t budget = 220 * 1024;
+    // CTA-shared round tables of all R rounds (whole tables for the full-field rounds, one short table per run-off round) when they fit
+    // beside at least 8 warps; else every warp stages the round it plays (its own table is there anyway: the phi-folded copy)
+    const size_t warp = dense32_warp_smem(E, a.nch, 8, kmax, true, true) + dense32_ext_warp_smem(E, a.nch, G, Fmax);
+    const size_t ext_cta = dense32_ext_cta_smem(E, a.nch, G, a.epitch);
+    size_t base_cta = (dense32_cta_smem(a.nch, 8, G, n_full, R - n_full, nk) + 15) & ~(size_t)15;
+    a.cta_tabs = 1; a.n_tab = R; a.n_tab_full = n_full; a.nk_chunks = nk;
+    if (base_cta + ext_cta + 8 * warp > budget) {
+        base_cta = (dense32_cta_smem(a.nch, 8, G, 0) + 15) & ~(size_t)15;
+        a.cta_tabs = 0; a.n_tab = 0; a.n_tab_full = 0;
+    }
+    if (base_cta + ext_cta + 2 * warp > budget) return CSIM_OK;                                 // (many regions): k_trials_full32
+    a.o_ext = base_cta; a.cta_smem = base_cta + ext_cta; a.warp_smem = warp;
+    int wpc = 16;
+    while (a.cta_smem + a.warp_smem * wpc > budget) --wpc;
+    a.warps_per_cta = wpc;
+    const size_t smem = a.cta_smem + a.warp_smem * wpc;
+    void (*kern)(Dense32Args) = k_trials_dense32<8, true, true, false, true>;
+    if (c->probe) {
+        kern = k_trials_dense32<8, true, true, true, true>;
+        a.probe_round = c->probe->round; a.probe_prev_vote = c->probe->prev_vote; a.probe_prev_count = c->probe->prev_count;
+        a.probe_fatigued = c->probe->fatigued;
+        a.probe_scores = c->probe->scores; a.probe_prefix = c->probe->prefix; a.probe_cap = c->probe->cap;
+        c->probe->nch = a.nch; c->probe->chunk = 8;
+    }
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpc * 32, smem));
+    if (per_sm < 1) return CSIM_OK;
+    const int CP = a.nch * 8;
+    const size_t tb = sizeof(float) * (size_t)b.n_sets * R * 4 * CP;
+    if (tb / sizeof(float) > 0xffffffffull) return CSIM_OK;
+    CU_TRY(c->tab.reserve(tb));
+    a.tab = (const float*)c->tab.p;
+    for (int sr0 = 0; sr0 < b.n_sets * R; sr0 += CSIM_GRID_TILE) {
+        dim3 g((CP + 127) / 128, std::min(CSIM_GRID_TILE, b.n_sets * R - sr0));
+        k_round_tables32<<<g, 128, 0, st>>>(a.ro, b.sets, (const double*)c->betas.p, R, CP, c->x_mid, (float*)c->tab.p, sr0);
+        ++c->launches;
+    }
+    if (any_stop) {                                           // the acceptable bits again, as bytes per (chunk, elector slot)
+        const size_t per_set = (size_t)a.nch * a.epitch;
+        CU_TRY(c->accb.reserve(sizeof(uint2) * per_set * b.n_sets));
+        CU_TRY(cudaMemsetAsync(c->accb.p, 0, sizeof(uint2) * per_set * b.n_sets, st));
+        a.accb = (const uint2*)c->accb.p;
+        for (int s0 = 0; s0 < b.n_sets; s0 += CSIM_GRID_TILE) {
+            dim3 g((E * a.nch + 127) / 128, std::min(CSIM_GRID_TILE, b.n_sets - s0));
+            k_ext_accbytes<<<g, 128, 0, st>>>(a.ro, b.sets + s0, a.nch, a.epitch, (uint2*)c->accb.p + (size_t)s0 * per_set);
+            ++c->launches;
+        }
+    }
+    const uint64_t ctas = (uint64_t)c->prop.multiProcessorCount * per_sm;
+    const uint64_t want = (a.b.n_sims * (uint64_t)std::max(a.b.n_sets, 1) + wpc - 1) / wpc;
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, ctas));
+    csim_status qs = work_queue(c, a.b.n_sets, a.b.n_sims, (uint64_t)grid * wpc, st, &a.wq);
+    if (qs != CSIM_OK) return qs;
+    CU_TRY(cudaEventRecord(c->ev0, st));
+    kern<<<grid, wpc * 32, smem, st>>>(a);
+    CU_TRY(cudaEventRecord(c->ev1, st));
+    c->ev_valid = true;
+    ++c->launches;
+    CU_TRY(cudaGetLastError());
+    *taken = true;
+    return CSIM_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // FULL engine (full32.cuh): fp32, every model term inline, fatigue + stop-candidate included
@@ -37,6 +135,11 @@ csim_status launch_full32(csim_ctx* c, const csim_run_args* ra, const std::vecto
         const csim_params& q = ra->params[i];
         neg = neg || q.regional_affinity_bonus < 0 || q.bandwagon_strength < 0 || q.papabile_weight_factor < 0 || q.stickiness_factor < -1 ||
               q.fatigue_penalty_factor < 0 || q.stop_candidate_boost_factor < 0;
+    }
+    if (ext && !neg) {                                        // fatigue / stop-candidate with non-negative factors: the dense EXT kernel
+        bool taken = false;
+        csim_status es = launch_dense_ext(c, ra, hs, b, out, st, any_stop, a.accw, &taken);
+        if (es != CSIM_OK || taken) return es;
     }
     void (*kern)(const Full32Args) = ext ? (neg ? k_trials_full32<true, true, false> : k_trials_full32<true, false, false>)
                                          : (neg ? k_trials_full32<false, true, false> : k_trials_full32<false, false, false>);

@@ -67,7 +67,7 @@ struct csim_ctx {
     cudaDeviceProp prop{};
     int E = 0, Epad = 0, G = 0;
     DevBuf x64, x32, region, pap;
-    DevBuf sets, betas, nbeta, W, tab, cdf64, cdfk64, cdf32, cdfk32, ptab, accm;
+    DevBuf sets, betas, nbeta, W, tab, cdf64, cdfk64, cdf32, cdfk32, ptab, accm, accb;
     DevBuf work;                        // per-set trial counters of the dynamically scheduled kernels (WorkQueue)
     double x_mid = 0.0, x_half = 0.0;   // centre and half-range of ideology_score (factorised exp)
     // host-buffer mode staging

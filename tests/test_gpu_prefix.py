@@ -406,7 +406,8 @@ def test_full_engine_fatigue_and_stop_vs_oracle(eng):
     assert np.array_equal(exact.winner, ref["winner"]) and np.array_equal(exact.rounds, ref["rounds"])
     # the extras change the outcome distribution: the test would be vacuous otherwise
     plain = eng.run([ps[3]] * 1, n, seed=3, wiring=O.WIRING_MODEL, engine=PREFIX, precision=FP32)
-    assert np.array_equal(plain.winner, w[3])                                          # set 3 has no extras: FULL == PREFIX trial for trial
+    # set 3 has no extras: FULL follows PREFIX trial for trial up to fp32 boundary draws (the batch runs on the factorised dense kernel)
+    assert_agree(plain.winner == w[3], "full", ref["rounds"].reshape(len(sets), n)[3].sum() * 134, what="full32 set without extras vs prefix")
     assert np.mean(w[0] != w[3]) > 0.2 and np.mean(w[2] != w[3]) > 0.05
 
 
