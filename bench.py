@@ -418,15 +418,27 @@ def main():
     full_engine = timed(ENGINE_FULL, WIRING_MODEL, 900, p=params_x)
     full_pairs = pair_evals(batch.rounds.cpu().numpy(), E, rr, k)             # this rank's last step (every step is the same size)
     full_kern_s = full_engine["trial_kernel_ms_per_step"] * 1e-3
-    full_engine.update(kernel="k_trials_full32<EXT=true,NEG=false>",
+    full_engine.update(kernel="k_trials_dense32<LC=8,MODEL=true,FACT=true,EXT=true> (the FULL engine's fast path, launched by eng_full.cu)",
                        note="`model` wiring with EVERY term live: cfg-2 parameters + candidate fatigue (3 rounds below 5 %) + stop-candidate "
-                            "(unacceptable distance 0.3): all E x C scores inline per trial per round (MUFU form)",
-                       roofline={"bound": "fp32", "unit": "G thread-instr/s", "achieved": full_pairs * FP32_PER_PAIR / full_kern_s * 1e-9, "peak": peak_fp32,
-                                 "frac": full_pairs * FP32_PER_PAIR / full_kern_s * 1e-9 / peak_fp32,
-                                 "sfu_frac": full_pairs * MUFU_PER_PAIR / full_kern_s * 1e-9 / peak_mufu,
-                                 "note": "this kernel IS the canonical formulation (FADD, FMUL, MUFU.EX2, FFMA + the model's terms per pair), so the SURVEY-8d "
-                                         "accounting (10 FP32 + 1 MUFU per pair) is the executed one here",
-                                 "ncu": ncu_digest("k_trials_full32")})
+                            "(unacceptable distance 0.3).  Round 2: the dense kernel's factorised two-elector pair loop with fatigue folded into a "
+                            "per-warp copy of the round table and stop-candidate as a byte-masked second accumulator; k_trials_full32 (MUFU form, "
+                            "every term inline) remains for negative factors, E > 255 and non-factorisable beta schedules",
+                       roofline={"bound": "fp32", "unit": "G pair-evaluations/s", "achieved": full_pairs / full_kern_s * 1e-9, "peak": fact_peak_pairs * 1e-9,
+                                 "frac": full_pairs / full_kern_s / fact_peak_pairs,
+                                 "note": "executed work: pair evaluations per second over the rate of the PLAIN factorised pair body (k_microbench<3>); in "
+                                         "rounds with stop-candidate threats the masked body executes 5.5 issue slots per pair instead of 2, so this "
+                                         "fraction understates the pipe utilisation of those rounds",
+                                 "algorithmic_equivalent_frac": full_pairs * FP32_PER_PAIR / full_kern_s * 1e-9 / peak_fp32,
+                                 "algorithmic_equivalent_note": "SURVEY-8d canonical accounting (10 FP32 per pair) against the measured FFMA rate; round 1 "
+                                                                "reported this figure (0.26) for the MUFU-form kernel, which executed it",
+                                 "ncu": ncu_digest("k_trials_dense32_ext")})
+    if not args.no_configs and world == 1:
+        os.environ["CSIM_FULL_LEGACY"] = "1"                      # the same step on k_trials_full32 (what round 1 and the first half of round 2 ran)
+        try:
+            lg = timed(ENGINE_FULL, WIRING_MODEL, 950, p=params_x, steps=min(args.steps, 3), warm=1)
+            full_engine["legacy_k_trials_full32"] = {k_: lg[k_] for k_ in ("value", "unit", "ms_per_step", "trial_kernel_ms_per_step", "steps")}
+        finally:
+            os.environ.pop("CSIM_FULL_LEGACY", None)
     model_wiring_dense = timed(ENGINE_DENSE, WIRING_MODEL, 800)
     model_wiring_dense.update(kernel="k_trials_dense32<LC=8,MODEL=true,FACT=true>",
                               note="`model` wiring (bandwagon + stickiness live, SURVEY 8f.1) on the dense kernel, for comparison")

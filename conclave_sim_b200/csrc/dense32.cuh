@@ -95,6 +95,9 @@ struct Dense32Args {
 #ifndef CSIM_DENSE_PIPELINE
 #define CSIM_DENSE_PIPELINE 1   // software-pipeline the operand loads of the pair loop (L = 8, factorised form)
 #endif
+#ifndef CSIM_EXT_PLAY4
+#define CSIM_EXT_PLAY4 0        // EXT, k = 2 run-off rounds: 1 = four unrolled copies of the per-elector body (as the plain kernel), 0 = one
+#endif
 #define DENSE32_PREF_COLS (CSIM_NE > 1 ? CSIM_NE : 1)
 // Shared-memory layouts whose chunks are GATHERED per lane by the re-scan (each lane re-reads the chunk ITS target fell into, with
 // 128-bit loads): with L = 8 a chunk is padded so that consecutive chunks start in different 16-byte bank groups — a round table
@@ -375,6 +378,7 @@ __device__ __forceinline__ void chunk_ext8(const float* tc, const float* ph, con
 // "acceptable" bits, W words each.
 __device__ __forceinline__ bool ext_triggered(const uint32_t* thr, const uint32_t* arow, int W) {
     uint32_t any = 0;
+#pragma unroll 1
     for (int w = 0; w < W; ++w) any |= thr[w] & ~__ldg(arow + w);
     return any != 0;
 }
@@ -537,6 +541,28 @@ __device__ __forceinline__ int finish_draw(const LaneCtx32& k, const float* pref
     vote = vote > maxc ? maxc : vote;                    // rounding at the chunk's upper edge
     if (vote == e) vote = e > 0 ? e - 1 : (C > 1 ? 1 : 0);
     return vote;
+}
+
+// EXT, candidate fatigue: among the unmarked candidates whose vote sum over the window is S, the one with the largest MEAN SHARE as the
+// reference computes it in fp64 (simulate.py:88-95: each round's votes / E, summed in round order, / rounds), ties -> highest index.
+// Out of line: only reached when two candidates tie on the integer sum.
+static __device__ __noinline__ int ext_top_mean_exact(const uint8_t* hist, const uint8_t* mark, const int* isum, int S, int n_hist, int nh, int Fmax,
+                                                      int Ei, int C, int E, int lane) {
+    double bv = -1.0; int ba = -1;
+    for (int c = lane; c < C; c += 32) {
+        if (mark[c] || isum[c] != S) continue;
+        double acc = __ddiv_rn((double)hist[(size_t)((n_hist - nh) % Fmax) * Ei + c], (double)E);
+        for (int q = 1; q < nh; ++q) acc = __dadd_rn(acc, __ddiv_rn((double)hist[(size_t)((n_hist - nh + q) % Fmax) * Ei + c], (double)E));
+        const double av = __ddiv_rn(acc, (double)nh);
+        if (ba < 0 || av >= bv) { bv = av; ba = c; }
+    }
+#pragma unroll 1
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_xor_sync(CSIM_FULL, bv, off);
+        const int oa = __shfl_xor_sync(CSIM_FULL, ba, off);
+        if (oa >= 0 && (ba < 0 || ov > bv || (ov == bv && oa > ba))) { bv = ov; ba = oa; }
+    }
+    return ba;
 }
 
 // One round's table from its source into shared memory, by `nthr` threads of which this is number `tid`:
@@ -740,14 +766,19 @@ __global__ void __launch_bounds__(EXT ? 512 : 256, EXT ? 1 : CSIM_MINB) k_trials
             int tail_r0 = -(1 << 30);                                // first round of the current tail stash (none yet)
             if (R == 0) { for (int c = lane; c < C; c += 32) tally[c] = 0; __syncwarp(); }
             int n_hist = 0;                                          // EXT: rounds in the tally history
-            if (EXT) { for (int c = lane; c < CPP; c += 32) { phi[c] = 1.0f; bw[c] = 0.0f; } n_thr = 0; }
+            int hrow = 0;                                            // EXT: row of the history ring the next tally goes to (= n_hist % Fmax)
+            if (EXT) {
+#pragma unroll 1
+                for (int c = lane; c < CPP; c += 32) { phi[c] = 1.0f; bw[c] = 0.0f; }
+                n_thr = 0;
+            }
             if (PROBE && MODEL && (a.probe_prev_vote || a.probe_prev_count)) {      // start from the given previous-round state
                 for (int c = lane; c < C; c += 32) {
                     prev_tally[c] = a.probe_prev_count ? a.probe_prev_count[c] : 0;
                     votes[c] = a.probe_prev_vote ? a.probe_prev_vote[c] : -1;
                     if (EXT) hist[c] = (uint8_t)prev_tally[c];
                 }
-                have_prev = true; n_hist = 1;
+                have_prev = true; n_hist = 1; hrow = a.Fmax > 1 ? 1 : 0;
                 __syncwarp();
             }
 
@@ -773,43 +804,61 @@ __global__ void __launch_bounds__(EXT ? 512 : 256, EXT ? 1 : CSIM_MINB) k_trials
                     if (en_fat) {
                         bool window = false;
                         if (r > Fw) {
+#pragma unroll 1
                             for (int c = lane; c < C; c += 32) mark[c] = 0;
                             __syncwarp();
                             const int nh = n_hist < Fw ? n_hist : Fw;
                             if (fat_top_n > 0 && n_hist > 0 && nh > 0) {
-                                double* avg = (double*)pref;                     // the prefix columns are not live between rounds
-                                for (int c = lane; c < C; c += 32) {
-                                    double acc = __ddiv_rn((double)hist[(size_t)((n_hist - nh) % a.Fmax) * Ei + c], (double)E);
-                                    for (int q = 1; q < nh; ++q)
-                                        acc = __dadd_rn(acc, __ddiv_rn((double)hist[(size_t)((n_hist - nh + q) % a.Fmax) * Ei + c], (double)E));
-                                    avg[c] = __ddiv_rn(acc, (double)nh);
+                                // top-n by mean share over the window, ties -> highest index.  The mean is the reference's fp64 expression
+                                // (sum of votes / E, / rounds); it is ordered like the integer vote sum except between candidates whose
+                                // sums are EQUAL (different compositions may round differently), so the ranking runs on packed integer
+                                // keys (sum << 8 | index, E <= 255) and only a tie at the top goes through the fp64 routine.
+                                int* isum = (int*)pref;                          // the prefix columns are not live between rounds
+#pragma unroll 1
+                                for (int c = lane; c < C; c += 32) isum[c] = 0;
+#pragma unroll 1
+                                for (int q = 0; q < nh; ++q) {
+                                    int row = hrow - nh + q;                     // the ring row of the q-th round of the window
+                                    row = row < 0 ? row + a.Fmax : row;
+                                    const uint8_t* hr = hist + row * Ei;
+#pragma unroll 1
+                                    for (int c = lane; c < C; c += 32) isum[c] += (int)hr[c];
                                 }
                                 __syncwarp();
                                 const int n_imm = fat_top_n < C ? fat_top_n : C;
-                                for (int j = 0; j < n_imm; ++j) {                // top-n by mean share; ties -> highest index
-                                    double bv = -1.0; int ba = -1;
-                                    for (int c = lane; c < C; c += 32)
-                                        if (!mark[c] && (ba < 0 || avg[c] >= bv)) { bv = avg[c]; ba = c; }
+#pragma unroll 1
+                                for (int j = 0; j < n_imm; ++j) {
+                                    int best = -1;
+#pragma unroll 1
+                                    for (int c = lane; c < C; c += 32) if (!mark[c]) best = max(best, (isum[c] << 8) | c);
 #pragma unroll
-                                    for (int off = 16; off > 0; off >>= 1) {
-                                        const double ov = __shfl_xor_sync(CSIM_FULL, bv, off);
-                                        const int oa = __shfl_xor_sync(CSIM_FULL, ba, off);
-                                        if (oa >= 0 && (ba < 0 || ov > bv || (ov == bv && oa > ba))) { bv = ov; ba = oa; }
+                                    for (int off = 16; off > 0; off >>= 1) best = max(best, __shfl_xor_sync(CSIM_FULL, best, off));
+                                    int pick = best & 255;
+                                    if (nh > 1) {
+                                        bool tie = false;
+#pragma unroll 1
+                                        for (int c = lane; c < C; c += 32) tie = tie || (!mark[c] && c != pick && isum[c] == (best >> 8));
+                                        if (__any_sync(CSIM_FULL, tie)) pick = ext_top_mean_exact(hist, mark, isum, best >> 8, n_hist, nh, a.Fmax, Ei, C, E, lane);
                                     }
-                                    if (lane == 0 && ba >= 0) mark[ba] = 1;
+                                    if (lane == 0) mark[pick] = 1;
                                     __syncwarp();
                                 }
                             }
                             window = n_hist >= Fw;
                         }
                         uint32_t anyf = 0;
+#pragma unroll 1
                         for (int c0 = 0; c0 < 32 * Wb; c0 += 32) {
                             const int c = c0 + lane;
                             bool f = false;
                             if (window && c < C && !mark[c]) {
                                 f = true;
-                                for (int q = 0; q < Fw && f; ++q)                  // share < threshold, as an integer test (DevSet::fat_cnt)
-                                    f = (int)hist[(size_t)((n_hist - Fw + q) % a.Fmax) * Ei + c] < fat_cnt;
+#pragma unroll 1
+                                for (int q = 0; q < Fw && f; ++q) {                // share < threshold, as an integer test (DevSet::fat_cnt)
+                                    int row = hrow - Fw + q;
+                                    row = row < 0 ? row + a.Fmax : row;
+                                    f = (int)hist[row * Ei + c] < fat_cnt;
+                                }
                             }
                             if (PROBE && a.probe_fatigued) f = c < C && a.probe_fatigued[c] != 0;
                             const uint32_t m = __ballot_sync(CSIM_FULL, f);
@@ -824,6 +873,7 @@ __global__ void __launch_bounds__(EXT ? 512 : 256, EXT ? 1 : CSIM_MINB) k_trials
                     //      so with a NEGATIVE threat share every candidate is a threat already then
                     if (en_stop && (have_prev || neg_T)) {
                         const bool all_thr = !have_prev;
+#pragma unroll 1
                         for (int c0 = 0; c0 < 32 * Wb; c0 += 32) {
                             const int c = c0 + lane;
                             const bool t = c < C && (all_thr || prev_tally[c] >= stop_cnt);   // share > threshold (DevSet::stop_cnt)
@@ -837,6 +887,7 @@ __global__ void __launch_bounds__(EXT ? 512 : 256, EXT ? 1 : CSIM_MINB) k_trials
                     kx.rbp_cur = rbp;
                     if (!have_eff && use_fat) {                  // a full-field round with fatigued candidates plays from the phi-folded table
                         const float* Ts = kx.T;
+#pragma unroll 1
                         for (int c = lane; c < CP; c += 32) {
                             const int o = tab_off<LC>(c);
                             const float f = phi[pad_c<LC>(c)];
@@ -844,8 +895,10 @@ __global__ void __launch_bounds__(EXT ? 512 : 256, EXT ? 1 : CSIM_MINB) k_trials
                         }
                         kx.T = wtab;
                         if (n_thr == 0) {                        // regional prefix with phi: (same-region candidates) - (1 - pen) (fatigued ones)
+#pragma unroll 1
                             for (int g = lane; g < G; g += 32) {
                                 int nf = 0;
+#pragma unroll 1
                                 for (int j = 0; j < nch; ++j) {
                                     const int sh = 8 * (j & 3);
                                     nf += __popc((fatbits[j >> 2] >> sh) & (regbits[g * Wb + (j >> 2)] >> sh) & 0xFFu);
@@ -896,32 +949,43 @@ __global__ void __launch_bounds__(EXT ? 512 : 256, EXT ? 1 : CSIM_MINB) k_trials
 
                 int cnt0 = 0;                                        // run-off (fast2): this lane's votes for ef0
                 if (!have_eff) {
-                    // =============== full-field round: NE electors of a lane at once =====================
-                    for (int qi = 0; qi < m_quads; ++qi) {
-                        const int q = lane + 32 * qi;
-                        {   // this lane's four words go to its own slot of shared memory: nothing of them stays live across the pair loop
-                            uint32_t w[4];
-                            philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)q, a.b.seed_lo, a.b.seed_hi, w);
-                            *reinterpret_cast<uint4*>(wq + 4 * lane) = make_uint4(w[0], w[1], w[2], w[3]);
-                        }
+                  if constexpr (EXT) {
+                    // =============== full-field round, EXT: ONE loop over the steps of the round ==========================
+                    // (a step = NE quad-dealt electors of every lane, or up to 32 leftover electors P lanes each), so that the
+                    // ~500-instruction per-elector tail (corrections + draw) exists ONCE, inline: with one copy per kind of step and
+                    // five of the run-off body the hot code was ~80 KB and the kernel instruction-fetch bound (no_instruction 5.0 per
+                    // issue, profiles/r02b_ncu_ext_v1_summary.txt); an out-of-line routine instead put the round's constants
+                    // (LaneCtx32) into local memory (long_scoreboard 0.1 -> 2.7 per issue, v2).
+                    constexpr int SPQ = 4 / NE;                                  // steps per quad iteration
+                    const int n_main_steps = m_quads * SPQ;
+                    const int n_steps = n_main_steps + ((n_left + 31) >> 5);
+                    const float hbonus = 0.5f * kx.bonus;
+                    const bool masked = n_thr > 0;                               // stop-candidate live this round: the masked pair loop
 #pragma unroll 1
-                        for (int g = 0; g < 4 / NE; ++g) {
+                    for (int step = 0; step < n_steps; ++step) {
+                        int nd, e_first, pstride, wsel = 0;
+                        const float* pbase;
+                        bool act_draw = true;
+                        uint32_t trigm = 0;                                      // bit i = draw i's elector is triggered
+                        if (step < n_main_steps) {
+                            const int qi = step / SPQ, g = step - qi * SPQ;
+                            const int q = lane + 32 * qi;
+                            if (g == 0) {
+                                uint32_t w[4];
+                                philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)q, a.b.seed_lo, a.b.seed_hi, w);
+                                *reinterpret_cast<uint4*>(wq + 4 * lane) = make_uint4(w[0], w[1], w[2], w[3]);
+                            }
                             const int e0 = 4 * q + NE * g;
-                            float xe[NE], Re[NE], Ai[NE];
+                            float Re[NE], Ai[NE];
                             unsigned long long acc[NE];
 #pragma unroll
-                            for (int i = 0; i < NE; ++i) {          // all the pair loop needs of an elector: R_e (or its ideology)
-                                if (FACT) { const float Ainv = __ldg(a.tab + (tabA + (uint32_t)(CP + e0 + i))); Re[i] = Ainv * Ainv; xe[i] = 0.f; Ai[i] = Ainv; }
-                                else { Re[i] = 1.f; xe[i] = __ldg(a.ro.x32 + e0 + i); Ai[i] = 1.f; }
-                                acc[i] = 0ull;
+                            for (int i = 0; i < NE; ++i) {
+                                const float Ainv = __ldg(a.tab + (tabA + (uint32_t)(CP + e0 + i)));
+                                Re[i] = Ainv * Ainv; Ai[i] = Ainv; acc[i] = 0ull;
                             }
-                            // phase 1: nothing but the pair arithmetic, its operand loads and one prefix store per elector
                             const float* tc = kx.T;
-                            const int tstep = LC == 8 ? 20 : L;
-                            float* pc = pref + lane;                                    // [j][t][lane]
-                            uint32_t trigm = 0;                                         // EXT: bit i = elector e0 + i is triggered
-                            if (EXT && n_thr > 0) {
-                                // stop-candidate live this round: the masked pair loop (chunk_ext8), every term in the prefix column
+                            float* pc = pref + lane;                             // [j][t][lane]
+                            if (masked) {
                                 float bmh[NE];
                                 const uint2* abp[NE]; const uint2* rbq[NE];
                                 unsigned long long accA[NE];
@@ -935,7 +999,6 @@ __global__ void __launch_bounds__(EXT ? 512 : 256, EXT ? 1 : CSIM_MINB) k_trials
                                     rbq[i] = regb + reg[e] * nch;
                                     accA[i] = 0ull;
                                 }
-                                const float hbonus = 0.5f * kx.bonus;
                                 const float* ph = phi; const float* bwc = bw;
                                 const int epitch = a.epitch;
 #pragma unroll 1
@@ -949,7 +1012,113 @@ __global__ void __launch_bounds__(EXT ? 512 : 256, EXT ? 1 : CSIM_MINB) k_trials
                                         pc[i * 32] = fmaf(bmh[i], f2_lo(accA[i]) + f2_hi(accA[i]), f2_lo(acc[i]) + f2_hi(acc[i]));
                                     tc += 20; ph += 12; bwc += 12; pc += NE * 32;
                                 }
-                            } else if (LC == 8 && FACT && CSIM_DENSE_PIPELINE) {
+                            } else {
+                                const ulonglong2* t4 = reinterpret_cast<const ulonglong2*>(tc);
+                                ulonglong2 nb0 = t4[0], nc0 = t4[1], nb1 = t4[2], nc1 = t4[3];
+#pragma unroll 2
+                                for (int j = 0; j < nch; ++j) {
+                                    const ulonglong2 b0 = nb0, c0 = nc0, b1 = nb1, c1 = nc1;
+                                    t4 += 5;                                                     // 80 bytes per chunk
+                                    nb0 = t4[0]; nc0 = t4[1]; nb1 = t4[2]; nc1 = t4[3];
+                                    chunk_math8<NE>(b0, c0, b1, c1, Re, acc);
+#pragma unroll
+                                    for (int i = 0; i < NE; ++i) pc[i * 32] = f2_lo(acc[i]) + f2_hi(acc[i]);   // running prefix, m units
+                                    pc += NE * 32;
+                                }
+                            }
+                            nd = NE; e_first = e0; pbase = pref + lane; pstride = NE * 32; wsel = NE * g;
+                        } else {
+                            // leftover electors: P lanes per elector, a contiguous range of chunks each (see the non-EXT form below)
+                            const int gb = (step - n_main_steps) << 5;
+                            const int n_it = min(32, n_left - gb);
+                            int P = 1;
+                            while (P * 2 * n_it <= 32) P *= 2;
+                            const int eli = lane / P, sub = lane - eli * P;
+                            const bool act = eli < n_it;
+                            const int e = e_left0 + gb + (act ? eli : 0);
+                            const float Ainv = __ldg(a.tab + (tabA + (uint32_t)(CP + e)));
+                            const float Re1[1] = {Ainv * Ainv}, Ai1[1] = {Ainv};
+                            float* cl = pref + eli * nch;                        // this elector's chunk prefixes (m units)
+                            const int per = (nch + P - 1) / P;
+                            const int j_lo = min(nch, sub * per), j_hi = min(nch, j_lo + per);
+                            float run = 0.f;
+                            __syncwarp();
+                            if (masked) {
+                                const bool tg = ext_triggered(thrbits, a.accmask + ((size_t)cur_set * E + e) * a.accw, Wb);
+                                trigm = tg ? 1u : 0u;
+                                if (act) {
+                                    const float bmh1 = tg ? bm1h : 0.0f;
+                                    const uint2* abp = accb_s + e;               // dense32_slot(e, E) == e for the leftover electors
+                                    const uint2* rbq = regb + reg[e] * nch;
+#pragma unroll 1
+                                    for (int j = j_lo; j < j_hi; ++j) {
+                                        unsigned long long acc[1] = {0ull}, accA[1] = {0ull};
+                                        const uint2 ab[1] = {abp[j * a.epitch]}, rb[1] = {rbq[j]};
+                                        chunk_ext8<1>(kx.T + j * 20, phi + j * 12, bw + j * 12, hbonus, ab, rb, Re1, Ai1, acc, accA);
+                                        run += fmaf(bmh1, f2_lo(accA[0]) + f2_hi(accA[0]), f2_lo(acc[0]) + f2_hi(acc[0]));
+                                        cl[j] = run;
+                                    }
+                                }
+                            } else if (act) {
+                                const float xe1[1] = {0.f};
+#pragma unroll 1
+                                for (int j = j_lo; j < j_hi; ++j) {
+                                    unsigned long long acc[1] = {0ull};
+                                    chunk_acc<1, LC, FACT>(kx, kx.T + j * 20, xe1, Re1, acc);
+                                    run += f2_lo(acc[0]) + f2_hi(acc[0]);
+                                    cl[j] = run;
+                                }
+                            }
+                            float off = run;                                     // inclusive scan over the P lanes of an elector, then exclusive
+                            for (int d = 1; d < P; d <<= 1) {
+                                const float o = __shfl_up_sync(CSIM_FULL, off, d);
+                                if (sub >= d) off += o;
+                            }
+                            off -= run;
+                            if (act && sub > 0) for (int j = j_lo; j < j_hi; ++j) cl[j] += off;
+                            __syncwarp();
+                            nd = 1; e_first = e; pbase = cl; pstride = 1; act_draw = act && sub == 0;
+                        }
+                        // ---- the per-elector tail: scalars, point-rule corrections, search + re-scan, tally
+#pragma unroll 1
+                        for (int i = 0; i < nd; ++i) {
+                            if (act_draw) {
+                                const int e = e_first + i;
+                                const Elector32 el = load_elector(e, sticky_live, (int)((trigm >> i) & 1u));
+                                const uint32_t wa = step < n_main_steps ? wq[4 * lane + wsel + i] : tail_r[e];
+                                const Corr32 cr = corrections32_ext<LC, FACT>(kx, e, el);
+                                const int vote = finish_draw<LC, MODEL, FACT, PROBE, true>(kx, pbase + i * 32, pstride, e, u24_from_word(wa), el, cr);
+                                atomicAdd(&tally[vote], 1);
+                                votes[e] = vote;                                 // read only by this lane for its own electors: in-place is safe
+                            }
+                        }
+                        if (step >= n_main_steps) __syncwarp();
+                    }
+                  } else {
+                    // =============== full-field round: NE electors of a lane at once =====================
+                    for (int qi = 0; qi < m_quads; ++qi) {
+                        const int q = lane + 32 * qi;
+                        {   // this lane's four words go to its own slot of shared memory: nothing of them stays live across the pair loop
+                            uint32_t w[4];
+                            philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)q, a.b.seed_lo, a.b.seed_hi, w);
+                            *reinterpret_cast<uint4*>(wq + 4 * lane) = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+#pragma unroll 1
+                        for (int g = 0; g < 4 / NE; ++g) {
+                            const int e0 = 4 * q + NE * g;
+                            float xe[NE], Re[NE];
+                            unsigned long long acc[NE];
+#pragma unroll
+                            for (int i = 0; i < NE; ++i) {          // all the pair loop needs of an elector: R_e (or its ideology)
+                                if (FACT) { const float Ainv = __ldg(a.tab + (tabA + (uint32_t)(CP + e0 + i))); Re[i] = Ainv * Ainv; xe[i] = 0.f; }
+                                else { Re[i] = 1.f; xe[i] = __ldg(a.ro.x32 + e0 + i); }
+                                acc[i] = 0ull;
+                            }
+                            // phase 1: nothing but the pair arithmetic, its operand loads and one prefix store per elector
+                            const float* tc = kx.T;
+                            const int tstep = LC == 8 ? 20 : L;
+                            float* pc = pref + lane;                                    // [j][t][lane]
+                            if (LC == 8 && FACT && CSIM_DENSE_PIPELINE) {
                                 // software-pipelined: chunk j + 1's operands are in flight while chunk j is evaluated (the load past the
                                 // last chunk reads the next table / the warp's own arrays: inside the allocation, never used)
                                 const ulonglong2* t4 = reinterpret_cast<const ulonglong2*>(tc);
@@ -977,12 +1146,10 @@ __global__ void __launch_bounds__(EXT ? 512 : 256, EXT ? 1 : CSIM_MINB) k_trials
 #pragma unroll 1
                             for (int i = 0; i < NE; ++i) {
                                 const int e = e0 + i;
-                                const Elector32 el = load_elector(e, sticky_live, EXT ? (int)((trigm >> i) & 1u) : -1);
-                                Corr32 cr;
-                                if constexpr (EXT) cr = corrections32_ext<LC, FACT>(kx, e, el);
-                                else cr = corrections32<LC, MODEL, FACT>(kx, e, el);
+                                const Elector32 el = load_elector(e, sticky_live);
+                                const Corr32 cr = corrections32<LC, MODEL, FACT>(kx, e, el);
                                 const uint32_t wa = wq[4 * lane + NE * g + i];
-                                const int vote = finish_draw<LC, MODEL, FACT, PROBE, EXT>(kx, pref + i * 32 + lane, NE * 32, e, u24_from_word(wa), el, cr);
+                                const int vote = finish_draw<LC, MODEL, FACT, PROBE>(kx, pref + i * 32 + lane, NE * 32, e, u24_from_word(wa), el, cr);
                                 atomicAdd(&tally[vote], 1);
                                 if (MODEL) votes[e] = vote;        // read only by this lane for its own electors: in-place is safe
                             }
@@ -1007,25 +1174,11 @@ __global__ void __launch_bounds__(EXT ? 512 : 256, EXT ? 1 : CSIM_MINB) k_trials
                         float run = 0.f;
                         __syncwarp();
                         if (act) {
-                            if (EXT && n_thr > 0) {                  // stop-candidate live: the masked pair loop (see the main part)
-                                const float Ai1[1] = {el.Ainv};
-                                const float bmh1 = el.trig ? bm1h : 0.0f, hbonus = 0.5f * kx.bonus;
-                                const uint2* abp = accb_s + e;       // dense32_slot(e, E) == e for the leftover electors
-                                const uint2* rbq = regb + el.g * nch;
-                                for (int j = j_lo; j < j_hi; ++j) {
-                                    unsigned long long acc[1] = {0ull}, accA[1] = {0ull};
-                                    const uint2 ab[1] = {abp[j * a.epitch]}, rb[1] = {rbq[j]};
-                                    chunk_ext8<1>(kx.T + j * 20, phi + j * 12, bw + j * 12, hbonus, ab, rb, Re1, Ai1, acc, accA);
-                                    run += fmaf(bmh1, f2_lo(accA[0]) + f2_hi(accA[0]), f2_lo(acc[0]) + f2_hi(acc[0]));
-                                    cl[j] = run;
-                                }
-                            } else {
-                                for (int j = j_lo; j < j_hi; ++j) {
-                                    unsigned long long acc[1] = {0ull};
-                                    chunk_acc<1, LC, FACT>(kx, kx.T + j * tstep, xe1, Re1, acc);
-                                    run += f2_lo(acc[0]) + f2_hi(acc[0]);
-                                    cl[j] = run;
-                                }
+                            for (int j = j_lo; j < j_hi; ++j) {
+                                unsigned long long acc[1] = {0ull};
+                                chunk_acc<1, LC, FACT>(kx, kx.T + j * tstep, xe1, Re1, acc);
+                                run += f2_lo(acc[0]) + f2_hi(acc[0]);
+                                cl[j] = run;
                             }
                         }
                         float off = run;                             // inclusive scan over the P lanes of an elector, then exclusive
@@ -1037,15 +1190,14 @@ __global__ void __launch_bounds__(EXT ? 512 : 256, EXT ? 1 : CSIM_MINB) k_trials
                         if (act && sub > 0) for (int j = j_lo; j < j_hi; ++j) cl[j] += off;
                         __syncwarp();
                         if (act && sub == 0) {
-                            Corr32 cr;
-                            if constexpr (EXT) cr = corrections32_ext<LC, FACT>(kx, e, el);
-                            else cr = corrections32<LC, MODEL, FACT>(kx, e, el);
-                            const int vote = finish_draw<LC, MODEL, FACT, PROBE, EXT>(kx, cl, 1, e, u24_from_word(tail_r[e]), el, cr);
+                            const Corr32 cr = corrections32<LC, MODEL, FACT>(kx, e, el);
+                            const int vote = finish_draw<LC, MODEL, FACT, PROBE>(kx, cl, 1, e, u24_from_word(tail_r[e]), el, cr);
                             atomicAdd(&tally[vote], 1);
                             if (MODEL) votes[e] = vote;
                         }
                         __syncwarp();
                     }
+                  }
                 } else {
                     // =============== run-off round: first k columns (simulate.py:144-154) ==================
                     if (fast2) {
@@ -1101,14 +1253,36 @@ __global__ void __launch_bounds__(EXT ? 512 : 256, EXT ? 1 : CSIM_MINB) k_trials
                             cnt0 += (j == 0);
                             if (MODEL) votes[e] = j == 0 ? ef0 : ef1;
                         };
-                        for (int qi = 0; qi < m_quads; ++qi) {
-                            const int q = lane + 32 * qi;
-                            uint32_t w[4];
-                            philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)q, a.b.seed_lo, a.b.seed_hi, w);
+                        if constexpr (EXT && !CSIM_EXT_PLAY4) {
+                            // ONE copy of the per-elector body (it is ~3x the plain one: the kernel's hot code has to stay inside the
+                            // instruction cache, see the header of the EXT section in DESIGN.md)
+                            uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll 1
+                            for (int n = 0; n < n_slots; ++n) {
+                                int e;
+                                uint32_t wa;
+                                if (n < n_main) {
+                                    const int q = lane + 32 * (n >> 2);
+                                    e = 4 * q + (n & 3);
+                                    if ((n & 3) == 0) philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)q, a.b.seed_lo, a.b.seed_hi, w);
+                                    const int sel = n & 3;
+                                    wa = sel == 0 ? w[0] : (sel == 1 ? w[1] : (sel == 2 ? w[2] : w[3]));
+                                } else {
+                                    e = e_single0 + 32 * (n - n_main);
+                                    wa = tail_r[e];
+                                }
+                                play(e, wa);
+                            }
+                        } else {
+                            for (int qi = 0; qi < m_quads; ++qi) {
+                                const int q = lane + 32 * qi;
+                                uint32_t w[4];
+                                philox4x32_10(s_lo, s_hi, (uint32_t)r, (uint32_t)q, a.b.seed_lo, a.b.seed_hi, w);
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) play(4 * q + i, w[i]);
+                                for (int i = 0; i < 4; ++i) play(4 * q + i, w[i]);
+                            }
+                            for (int e = e_single0; e < E; e += 32) play(e, tail_r[e]);
                         }
-                        for (int e = e_single0; e < E; e += 32) play(e, tail_r[e]);
                     } else {
                         uint32_t w[4] = {0, 0, 0, 0};
                         for (int n = 0; n < n_slots; ++n) {
@@ -1157,7 +1331,12 @@ __global__ void __launch_bounds__(EXT ? 512 : 256, EXT ? 1 : CSIM_MINB) k_trials
                     for (int c = lane; c < C; c += 32)
                         a.out.round_tallies[(t * (uint64_t)R + (uint64_t)(r - 1)) * (uint64_t)C + c] = tally[c];
                 if (MODEL) for (int c = lane; c < C; c += 32) prev_tally[c] = tally[c];
-                if (EXT) { for (int c = lane; c < C; c += 32) hist[(size_t)(n_hist % a.Fmax) * Ei + c] = (uint8_t)tally[c]; ++n_hist; }
+                if (EXT) {
+                    uint8_t* hr = hist + hrow * Ei;
+#pragma unroll 1
+                    for (int c = lane; c < C; c += 32) hr[c] = (uint8_t)tally[c];
+                    ++n_hist; hrow = hrow + 1 == a.Fmax ? 0 : hrow + 1;
+                }
                 have_prev = true;
                 if (fast2) {
                     int mx, arg, second;

@@ -49,6 +49,7 @@ static csim_status launch_dense_ext(csim_ctx* c, const csim_run_args* ra, const 
     if (base_cta + ext_cta + 2 * warp > budget) return CSIM_OK;                                 // (many regions): k_trials_full32
     a.o_ext = base_cta; a.cta_smem = base_cta + ext_cta; a.warp_smem = warp;
     int wpc = 16;
+    if (const char* ev = getenv("CSIM_EXT_WPC")) wpc = std::max(2, std::min(16, atoi(ev)));      // tuning aid
     while (a.cta_smem + a.warp_smem * wpc > budget) --wpc;
     a.warps_per_cta = wpc;
     const size_t smem = a.cta_smem + a.warp_smem * wpc;
