@@ -56,7 +56,7 @@ FP32_PER_PAIR, MUFU_PER_PAIR = 10, 1
 FACT_ISSUE_SLOTS_PER_PAIR = 2.0
 FALLBACK_FP32_GINSTR = 148 * 128 * 1.965     # architectural: SMs x FP32 lanes x GHz (used only if the microbench fails)
 FALLBACK_MUFU_GINSTR = 148 * 16 * 1.965
-NCU_DIGEST = os.path.join(ROOT, "profiles", "r02_ncu_digest.json")      # machine-readable digest of the committed ncu captures
+NCU_DIGEST = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02b_ncu_digest.json")
 
 
 def synthetic_roster(E: int, seed: int = 20250507):
@@ -124,7 +124,7 @@ def pair_evals(rounds: np.ndarray, E: int, rr: int, k: int) -> int:
 
 
 def ncu_digest(kernel_key: str):
-    """The committed ncu evidence for one kernel (profiles/r02_ncu_digest.json, written by profiles/ncu_summary.py --digest from the
+    """The committed ncu evidence for one kernel (profiles/r02b_ncu_digest.json, written by profiles/ncu_summary.py --digest from the
     .ncu-rep captures of this round): a pointer + the few numbers, read from the file — nothing is hard-coded here."""
     try:
         with open(NCU_DIGEST) as f:
@@ -397,7 +397,7 @@ def main():
                 "measured_peaks_ginstr": {"ffma": peak_fp32, "mufu_ex2": peak_mufu, "mufu_pair_body": peak_mix, "factorised_pair_body": peak_fact},
                 "traffic": None if dig is None else dig.get("dram_bytes_per_launch"),
                 "traffic_note": "dram__bytes_read + dram__bytes_write of ONE launch of this kernel at this step size from the committed ncu --set full "
-                                "capture (read from profiles/r02_ncu_digest.json at run time; null when the digest is absent); algorithmic HBM bytes per "
+                                "capture (read from profiles/r02b_ncu_digest.json at run time; null when the digest is absent); algorithmic HBM bytes per "
                                 f"launch = {out_bytes} (9 B/trial result rows + histograms): the kernel is compute-bound",
                 "hbm_writeback_gbs": out_bytes / kern_s * 1e-9, "ncu": dig}
 

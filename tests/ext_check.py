@@ -59,12 +59,14 @@ def probe_cases(eng):
                 emit(kind="probe", case=case["name"], r=r, error=repr(ex))
 
 
-def trial_cases(eng, quick):
-    from conclave_sim_b200 import FP32
-    base = dict(CFG2, stickiness_factor=1.2, bandwagon_strength=1.0)
-    EPK = dict(max_rounds=10, supermajority_threshold=0.6, runoff_threshold_rounds=6, fatigue_threshold_rounds=2, fatigue_vote_share_threshold=0.04,
-               fatigue_top_n_immune=2)
-    variants = {
+BASE = dict(CFG2, stickiness_factor=1.2, bandwagon_strength=1.0)
+EPK = dict(max_rounds=10, supermajority_threshold=0.6, runoff_threshold_rounds=6, fatigue_threshold_rounds=2, fatigue_vote_share_threshold=0.04,
+           fatigue_top_n_immune=2)
+
+
+def variants():
+    """name -> (ModelParams overrides, EngineParams overrides): each term of the EXT path alone and together."""
+    return {
         "fat_only": (dict(enable_candidate_fatigue=True), dict(enable_candidate_fatigue=True)),
         "stop_only": (dict(enable_stop_candidate=True, stop_candidate_threshold_unacceptable_distance=0.25, stop_candidate_threat_min_vote_share=0.1),
                       dict(enable_stop_candidate=True)),
@@ -78,11 +80,15 @@ def trial_cases(eng, quick):
                                     stop_candidate_threshold_unacceptable_distance=0.25, stop_candidate_threat_min_vote_share=0.1),
                                dict(enable_candidate_fatigue=True, enable_stop_candidate=True)),
     }
+
+
+def trial_cases(eng, quick):
+    from conclave_sim_b200 import FP32
     for E in ([135, 40] if quick else [135, 128, 40, 200, 2, 9, 255]):
         roster = O.synthetic_roster(E, seed=300 + E)
         upload(eng, roster)
-        for name, (mkw, ekw) in variants.items():
-            mp = O.ModelParams(**dict(base, **mkw))
+        for name, (mkw, ekw) in variants().items():
+            mp = O.ModelParams(**dict(BASE, **mkw))
             ep = O.EngineParams(**dict(EPK, **ekw))
             n = 256
             try:

@@ -427,6 +427,32 @@ def test_full_engine_on_ragged_rosters(eng, E):
     assert_agree((out.winner == ref["winner"]) & (out.rounds == ref["rounds"]), "full", ref["rounds"].sum() * E, what=f"full32 ragged E={E}")
 
 
+@pytest.mark.parametrize("E", [135, 255])
+def test_full_fast_path_term_by_term(eng, E, monkeypatch):
+    """The FULL engine's fast path (EXT instantiation of the dense kernel, dense32.cuh) term by term — fatigue only, stop-candidate only,
+    both, a k = 3 run-off, a negative threat share (every candidate a threat from round 1), no stickiness / bandwagon — against the fp64
+    oracle, and the legacy k_trials_full32 (CSIM_FULL_LEGACY=1) on the same batch: both follow the oracle per trial."""
+    from conclave_sim_b200 import FP32
+    import ext_check as X
+    roster = O.synthetic_roster(E, seed=300 + E)
+    upload(eng, roster)
+    n = 300
+    for name, (mkw, ekw) in X.variants().items():
+        mp = O.ModelParams(**dict(X.BASE, **mkw))
+        ep = O.EngineParams(**dict(X.EPK, **ekw))
+        ref = CO.run(roster, [(mp, ep)], O.WIRING_MODEL, n, seed=8, want_tallies=True)
+        for legacy in (False, True):
+            if legacy:
+                monkeypatch.setenv("CSIM_FULL_LEGACY", "1")
+            else:
+                monkeypatch.delenv("CSIM_FULL_LEGACY", raising=False)
+            out = eng.run([to_params(mp, ep)], n, seed=8, wiring=O.WIRING_MODEL, engine=FULL, precision=FP32, want_round_tallies=True)
+            assert (out.round_tallies[:, 0, :].sum(axis=1) == E).all()
+            assert_agree((out.winner == ref["winner"]) & (out.rounds == ref["rounds"]), "full", ref["rounds"].sum() * E,
+                         what=f"full32 {'legacy' if legacy else 'fast path'} {name} E={E}")
+        monkeypatch.delenv("CSIM_FULL_LEGACY", raising=False)
+
+
 def test_full_engine_without_extras_equals_prefix_and_scales(eng):
     """No fatigue / stop: the FULL kernel is a plain dense fp32 engine; on 200 000 trials it agrees with PREFIX per trial
     (different kernels, one Philox stream), conserves votes and is independent of how the sim-id range is cut."""
