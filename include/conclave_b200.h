@@ -71,9 +71,12 @@ typedef enum csim_status {
 #define CSIM_ENGINE_TABLE 2   /* ref_cli only: trial-invariant per-round CDF tables, built once */
 #define CSIM_ENGINE_PREFIX 3  /* fp32, both wirings: trial-invariant chunk-prefix tables + per-trial bandwagon /
                                  stickiness corrections, binary search over chunks, re-scan of one chunk */
-#define CSIM_ENGINE_FULL   4  /* fp32: every term of the model inline per (elector, candidate), candidate fatigue and
-                                 stop-candidate included (the fatigue set and the stop trigger are decided in fp64 exactly
-                                 as the exact engine decides them) */
+#define CSIM_ENGINE_FULL   4  /* fp32: every term of the model, candidate fatigue and stop-candidate included (the fatigue set
+                                 and the stop trigger are decided in fp64 exactly as the exact engine decides them).  Two
+                                 kernels behind it: with fatigue / stop-candidate live, E <= 255, non-negative factors and a
+                                 factorisable beta schedule the EXT instantiation of the dense kernel (fatigue folded into a
+                                 per-warp round table, stop-candidate as a byte-masked second accumulator); otherwise every
+                                 term inline per (elector, candidate) with the model's clamps (negative factors, any E) */
 
 /* arithmetic */
 #define CSIM_FP32 0           /* fast path: fp32 scores, ex2.approx, 24-bit uniforms */
