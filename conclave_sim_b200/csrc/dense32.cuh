@@ -95,6 +95,11 @@ struct Dense32Args {
 #ifndef CSIM_DENSE_PIPELINE
 #define CSIM_DENSE_PIPELINE 1   // software-pipeline the operand loads of the pair loop (L = 8, factorised form)
 #endif
+#ifndef CSIM_EXT_THREADS
+#define CSIM_EXT_THREADS 640    // EXT: threads per CTA the register allocation is bounded for (one CTA per SM): 20 warps at 96 registers.
+#endif                          // Measured with one elector per lane (eng_full.cu: CSIM_EXT_NE = 1), ms per 250 k trials with fatigue + stop live:
+                                // 512 / 576 / 608 / 640 / 768 threads = 14.04 / 14.40 / 13.76 / 12.94 / 14.33 (above 640 ptxas drops to 80 registers
+                                // and spills 200 B; shared memory holds 20 warps); two electors per lane at 512 threads, 128 registers: 14.90
 #ifndef CSIM_EXT_PLAY4
 #define CSIM_EXT_PLAY4 0        // EXT, k = 2 run-off rounds: 1 = four unrolled copies of the per-elector body (as the plain kernel), 0 = one
 #endif
@@ -582,7 +587,7 @@ __device__ __forceinline__ void stage_round_table(float* dst, const Dense32Args&
 }
 
 template <int LC, bool MODEL, bool FACT, bool PROBE = false, bool EXT = false>
-__global__ void __launch_bounds__(EXT ? 512 : 256, EXT ? 1 : CSIM_MINB) k_trials_dense32(Dense32Args a) {
+__global__ void __launch_bounds__(EXT ? CSIM_EXT_THREADS : 256, EXT ? 1 : CSIM_MINB) k_trials_dense32(Dense32Args a) {
     static_assert(!EXT || (LC == 8 && MODEL && FACT), "the EXT instantiation exists for chunks of 8, the model wiring and the factorised exponential");
     constexpr int NE = CSIM_NE;
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -1,6 +1,10 @@
 // eng_full.cu — the FULL engine: launcher of k_trials_full32 (full32.cuh)
 #include "internal.cuh"
 #include "full32.cuh"
+#ifndef CSIM_EXT_NE
+#define CSIM_EXT_NE 1                  // electors of a lane evaluated together by the EXT instantiation: 1 (the plain dense kernel shares the
+#endif                                 // candidate operands between 2: here the kernel is latency-bound and 20 warps of 96 registers with half
+#define CSIM_NE CSIM_EXT_NE            // the prefix columns beat 16 warps of 128; this unit holds no other instantiation of the dense kernel)
 #include "dense32.cuh"
 
 // ---------------------------------------------------------------------------------------------
@@ -48,8 +52,8 @@ static csim_status launch_dense_ext(csim_ctx* c, const csim_run_args* ra, const 
     }
     if (base_cta + ext_cta + 2 * warp > budget) return CSIM_OK;                                 // (many regions): k_trials_full32
     a.o_ext = base_cta; a.cta_smem = base_cta + ext_cta; a.warp_smem = warp;
-    int wpc = 16;
-    if (const char* ev = getenv("CSIM_EXT_WPC")) wpc = std::max(2, std::min(16, atoi(ev)));      // tuning aid
+    int wpc = CSIM_EXT_THREADS / 32;
+    if (const char* ev = getenv("CSIM_EXT_WPC")) wpc = std::max(2, std::min(wpc, atoi(ev)));     // tuning aid
     while (a.cta_smem + a.warp_smem * wpc > budget) --wpc;
     a.warps_per_cta = wpc;
     const size_t smem = a.cta_smem + a.warp_smem * wpc;
