@@ -45,6 +45,20 @@
 // Run-off rounds (simulate.py:144-154,183-186) only need the first k columns of the row
 // (P[e, :k] renormalised), so they cost k pair evaluations per elector; with k = 2 the tally is a
 // warp-reduced count and the round closes in O(1).
+//
+// EXT (template flag; chunks of 8, model wiring, factorised form; launched by eng_full.cu as the FULL engine's fast path): candidate
+// fatigue and stop-candidate in the same two-phase draw.
+//   fatigue (model.py:372-379) scales whole columns by a per-trial factor phi_c: a round with fatigued candidates plays from the
+//     warp's own copy of the round table with phi folded in, the bandwagon row is stored as bw * phi, and the regional prefix the
+//     probes read is rebuilt per round from bit rows (popc of fatigue bits & region bits): no extra instruction per pair;
+//   stop-candidate (model.py:384-415) scales, for a TRIGGERED elector, the whole score of the candidates acceptable to it: in a
+//     round with threats the pair loop carries every term and a second, byte-masked accumulator (chunk_ext8); "triggered" =
+//     (threat bits & ~acceptable bits) != 0; acceptable(e, c) is decided in fp64 once per parameter set (k_full_accmask bits,
+//     k_ext_accbytes bytes);
+//   the fatigue set is the reference's (simulate.py:84-118): tallies of the last F rounds in a ring of bytes, the immune top-n on
+//     packed integer keys with an fp64 tie routine out of line.
+// The quad-dealt and the leftover electors of a round go through ONE loop over "steps" so that the per-elector tail exists once
+// (instruction footprint: DESIGN.md 5.4b), one elector per lane (CSIM_EXT_NE), 20 warps per SM at 96 registers.
 #pragma once
 #include "common.cuh"
 

@@ -4,8 +4,10 @@
 // Fatigue scales whole columns by a per-trial factor and stop-candidate scales, per elector, the candidates within
 // an ideological distance — neither is a sum of per-candidate constants nor a point correction, so the
 // trial-invariant tables of prefix.cuh do not apply; this kernel evaluates every score of a row inline (the
-// "canonical dense per-trial formulation" of SURVEY §8d, MUFU form) and is what CSIM_ENGINE_AUTO falls to when
-// fatigue or stop-candidate is enabled in fp32.  One warp owns one trial; a lane owns whole electors:
+// "canonical dense per-trial formulation" of SURVEY §8d, MUFU form).  It is the GENERAL kernel of the FULL engine: batches with
+// fatigue / stop-candidate live, at most 255 electors, non-negative factors and a factorisable beta schedule run on the EXT
+// instantiation of the dense kernel instead (dense32.cuh, 1.6x faster; eng_full.cu decides).  One warp owns one trial; a lane owns
+// whole electors:
 //
 //   pass 1   the row's scores block by block (8 candidates, operands as 128-bit loads), running prefix per chunk
 //            into the lane's column of shared memory;
