@@ -140,6 +140,42 @@ def test_benchmarked_workload_probabilities(eng, E):
             check_against(eng, p, MODEL, engine, r, P_m, pv=pv, pc=pc, what=f"E={E} round {r} model engine {engine}")
 
 
+@pytest.mark.parametrize("E", [135, 200, 255])
+def test_full_fast_path_probabilities_at_bench_size(eng, E, monkeypatch):
+    """The FULL engine's fast path (EXT instantiation of the dense kernel) on rosters that fill whole Philox quads (the golden model
+    cases are <= 22 electors: leftover-elector path only): cfg-2 parameters + candidate fatigue + stop-candidate as bench.py times
+    them, a random fatigue mask, previous votes WITH threats (a few candidates above the threat share: the masked pair loop) and
+    WITHOUT (every share below it: the phi-folded plain loop), against the fp64 matrix (pinned to the reference at 1e-13 in
+    test_gpu_parity) — and the general kernel k_trials_full32 on the same inputs."""
+    from conclave_sim_b200 import FP64
+    roster = O.synthetic_roster(E)
+    upload(eng, roster)
+    mp = O.ModelParams(**dict(CFG2, enable_candidate_fatigue=True, enable_stop_candidate=True, stop_candidate_threshold_unacceptable_distance=0.3))
+    p = to_params(mp)
+    rng = np.random.default_rng(7000 + E)
+    for r in (2, 5):
+        beta = eng.beta_schedule(p, r, 1)[0]
+        for threats in (True, False):
+            if threats:                                    # three front-runners take 60 % of the votes
+                front = rng.choice(E, 3, replace=False)
+                pv = np.where(rng.random(E) < 0.6, front[rng.integers(0, 3, E)], rng.integers(0, E, E)).astype(np.int32)
+            else:
+                pv = rng.permutation(E).astype(np.int32)   # one vote each: every share is 1 / E < 0.15
+            pv[pv == np.arange(E)] = (pv[pv == np.arange(E)] + 1) % E
+            pc = np.bincount(pv, minlength=E).astype(np.int32)
+            assert (pc / E > 0.15).any() == threats
+            fat = rng.random(E) < 0.6
+            P_ref = eng.prob_matrix(p, beta, pv, pc, fat, pc / float(E), precision=FP64)
+            for legacy in (False, True):
+                if legacy:
+                    monkeypatch.setenv("CSIM_FULL_LEGACY", "1")
+                else:
+                    monkeypatch.delenv("CSIM_FULL_LEGACY", raising=False)
+                check_against(eng, p, MODEL, FULL, r, P_ref, pv=pv, pc=pc, fat=fat,
+                              what=f"E={E} round {r} threats={threats} {'k_trials_full32' if legacy else 'fast path'}")
+            monkeypatch.delenv("CSIM_FULL_LEGACY", raising=False)
+
+
 def test_probe_argument_errors(eng):
     from conclave_sim_b200._cabi import CsimError
     upload(eng, O.synthetic_roster(40))
