@@ -79,6 +79,12 @@ def variants():
         "both_nosticky_nobw": (dict(stickiness_factor=0.0, bandwagon_strength=0.0, enable_candidate_fatigue=True, enable_stop_candidate=True,
                                     stop_candidate_threshold_unacceptable_distance=0.25, stop_candidate_threat_min_vote_share=0.1),
                                dict(enable_candidate_fatigue=True, enable_stop_candidate=True)),
+        # 110 rounds without a run-off: 110 whole round tables do not fit in shared memory, every warp stages the round it plays
+        # (Dense32Args::cta_tabs = 0) and folds the fatigue factors into that copy in place.  Nobody reaches the supermajority with
+        # these terms live, so every trial plays all 110 rounds: the per-round tallies are what is compared
+        "both_long_no_runoff": (dict(enable_candidate_fatigue=True, enable_stop_candidate=True, stop_candidate_threshold_unacceptable_distance=0.25,
+                                     stop_candidate_threat_min_vote_share=0.1, beta_increment_amount=0.05),
+                                dict(enable_candidate_fatigue=True, enable_stop_candidate=True, max_rounds=110, runoff_candidate_count=0)),
     }
 
 

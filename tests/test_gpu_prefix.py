@@ -450,6 +450,15 @@ def test_full_fast_path_term_by_term(eng, E, monkeypatch):
             assert (out.round_tallies[:, 0, :].sum(axis=1) == E).all()
             assert_agree((out.winner == ref["winner"]) & (out.rounds == ref["rounds"]), "full", ref["rounds"].sum() * E,
                          what=f"full32 {'legacy' if legacy else 'fast path'} {name} E={E}")
+            if name == "both_long_no_runoff":              # 110 rounds each, no winner: the tallies carry the comparison
+                assert (ref["rounds"] == 110).all()
+                eq = (out.round_tallies == ref["round_tallies"])
+                # (a moved vote feeds back through bandwagon / stickiness, so a trial's tallies stay different once an fp32 boundary
+                # draw has flipped: measured 0.95 / 0.74 of the trials identical through 20 / 110 rounds at E = 255, on both kernels;
+                # a wrong table or factor leaves none)
+                eq20, eq_all = eq[:, :20, :].all(axis=(1, 2)).mean(), eq.all(axis=(1, 2)).mean()
+                print(f"full32 {'legacy' if legacy else 'fast path'} {name} E={E}: tallies identical through 20 / 110 rounds in {eq20:.3f} / {eq_all:.3f} of the trials")
+                assert eq20 >= 0.90 and eq_all >= 0.55, (name, legacy, eq20, eq_all)
         monkeypatch.delenv("CSIM_FULL_LEGACY", raising=False)
 
 
