@@ -14,7 +14,7 @@
 // schedule, tables that fit in shared memory.  Everything else stays on k_trials_full32.  `*taken` says whether it ran.
 // ---------------------------------------------------------------------------------------------
 static csim_status launch_dense_ext(csim_ctx* c, const csim_run_args* ra, const std::vector<DevSet>& hs, const BatchDev& b, const TrialOut& out,
-                                    cudaStream_t st, bool any_stop, int accw, bool* taken) {
+                                    cudaStream_t st, bool any_stop, int accw, int min_warps, bool* taken) {
     *taken = false;
     const int E = c->E, G = c->G, R = b.R;
     if (getenv("CSIM_FULL_LEGACY") || E > 255 || E < 2 || R < 1) return CSIM_OK;
@@ -40,21 +40,26 @@ static csim_status launch_dense_ext(csim_ctx* c, const csim_run_args* ra, const 
     const int nk = (kmax + 7) / 8;
     const int n_full = std::min(a.n_tab_full, R);
     const size_t budget = 220 * 1024;
-    // CTA-shared round tables of all R rounds (whole tables for the full-field rounds, one short table per run-off round) when they fit
-    // beside at least 8 warps; else every warp stages the round it plays (its own table is there anyway: the phi-folded copy)
+    // CTA-shared round tables of all R rounds (whole tables for the full-field rounds, one short table per run-off round) when that
+    // costs no warp; else every warp stages the round it plays (its own table is there anyway, the phi-folded copy: ~50 instructions
+    // per round, while a warp more or less is ~5 % of the kernel's speed)
     const size_t warp = dense32_warp_smem(E, a.nch, 8, kmax, true, true) + dense32_ext_warp_smem(E, a.nch, G, Fmax);
     const size_t ext_cta = dense32_ext_cta_smem(E, a.nch, G, a.epitch);
-    size_t base_cta = (dense32_cta_smem(a.nch, 8, G, n_full, R - n_full, nk) + 15) & ~(size_t)15;
-    a.cta_tabs = 1; a.n_tab = R; a.n_tab_full = n_full; a.nk_chunks = nk;
-    if (base_cta + ext_cta + 8 * warp > budget) {
-        base_cta = (dense32_cta_smem(a.nch, 8, G, 0) + 15) & ~(size_t)15;
-        a.cta_tabs = 0; a.n_tab = 0; a.n_tab_full = 0;
-    }
-    if (base_cta + ext_cta + 2 * warp > budget) return CSIM_OK;                                 // (many regions): k_trials_full32
+    const size_t ctaA = (dense32_cta_smem(a.nch, 8, G, n_full, R - n_full, nk) + 15) & ~(size_t)15;
+    const size_t ctaB = (dense32_cta_smem(a.nch, 8, G, 0) + 15) & ~(size_t)15;
+    int max_wpc = CSIM_EXT_THREADS / 32;
+    if (const char* ev = getenv("CSIM_EXT_WPC")) max_wpc = std::max(2, std::min(max_wpc, atoi(ev)));     // tuning aid
+    auto fit = [&](size_t cta) { int w = max_wpc; while (w > 0 && cta + ext_cta + warp * w > budget) --w; return w; };
+    const int wA = fit(ctaA), wB = fit(ctaB);
+    const bool shared_tabs = wA >= wB && wA > 0;
+    const size_t base_cta = shared_tabs ? ctaA : ctaB;
+    a.cta_tabs = shared_tabs ? 1 : 0; a.n_tab = shared_tabs ? R : 0; a.n_tab_full = shared_tabs ? n_full : 0; a.nk_chunks = nk;
+    const int wpc = shared_tabs ? wA : wB;
+    // many regions (bonus rows per region, CTA-shared and per warp): below ~10 warps per SM this kernel is no faster than
+    // k_trials_full32 with its 28 (12 / 8 warps measured 17 / 21 ms per 250 k trials against 21), so the caller asks for 10 when the
+    // general kernel fits and for 2 when it does not
+    if (wpc < min_warps) return CSIM_OK;
     a.o_ext = base_cta; a.cta_smem = base_cta + ext_cta; a.warp_smem = warp;
-    int wpc = CSIM_EXT_THREADS / 32;
-    if (const char* ev = getenv("CSIM_EXT_WPC")) wpc = std::max(2, std::min(wpc, atoi(ev)));     // tuning aid
-    while (a.cta_smem + a.warp_smem * wpc > budget) --wpc;
     a.warps_per_cta = wpc;
     const size_t smem = a.cta_smem + a.warp_smem * wpc;
     void (*kern)(Dense32Args) = k_trials_dense32<8, true, true, false, true>;
@@ -117,8 +122,7 @@ csim_status launch_full32(csim_ctx* c, const csim_run_args* ra, const std::vecto
     memset(&a, 0, sizeof a);
     int kmax = 1, Fmax = 1;
     for (const DevSet& s : hs) { kmax = std::max(kmax, s.k); Fmax = std::max(Fmax, s.fat_rounds); }
-    if (!full32_plan(a, E, c->G, R, kmax, Fmax, (size_t)c->prop.sharedMemPerBlockOptin))
-        return fail(CSIM_ERR_UNSUPPORTED, "full engine: a roster of %d electors (fatigue window %d) does not fit in shared memory", E, Fmax);
+    const bool general_fits = full32_plan(a, E, c->G, R, kmax, Fmax, (size_t)c->prop.sharedMemPerBlockOptin);
     a.ro = roster_dev(c); a.b = b; a.out = out; a.nbeta = (const float*)c->nbeta.p;
     a.accw = (E + 31) / 32; a.accmask = nullptr;
     bool any_stop = false;
@@ -143,9 +147,11 @@ csim_status launch_full32(csim_ctx* c, const csim_run_args* ra, const std::vecto
     }
     if (ext && !neg) {                                        // fatigue / stop-candidate with non-negative factors: the dense EXT kernel
         bool taken = false;
-        csim_status es = launch_dense_ext(c, ra, hs, b, out, st, any_stop, a.accw, &taken);
+        csim_status es = launch_dense_ext(c, ra, hs, b, out, st, any_stop, a.accw, general_fits ? 10 : 2, &taken);
         if (es != CSIM_OK || taken) return es;
     }
+    if (!general_fits)
+        return fail(CSIM_ERR_UNSUPPORTED, "full engine: a roster of %d electors (fatigue window %d) does not fit in shared memory", E, Fmax);
     void (*kern)(const Full32Args) = ext ? (neg ? k_trials_full32<true, true, false> : k_trials_full32<true, false, false>)
                                          : (neg ? k_trials_full32<false, true, false> : k_trials_full32<false, false, false>);
     if (c->probe) {
