@@ -176,6 +176,31 @@ def test_full_fast_path_probabilities_at_bench_size(eng, E, monkeypatch):
             monkeypatch.delenv("CSIM_FULL_LEGACY", raising=False)
 
 
+@pytest.mark.parametrize("case", list(G.extras_cases()), ids=lambda c: c["name"])
+def test_fatigue_and_stop_matrices_of_the_reference_on_full_size_rosters(eng, case, monkeypatch):
+    """The reference's OWN matrices with candidate fatigue + stop-candidate live on the real 134-elector roster and a 200-elector one
+    (tests/golden/model_extras.npz, oracle/gen_golden_extras.py): csim_prob_matrix in fp64 at 1e-13, and what the FULL engine's two
+    kernels (the fast path of dense32.cuh and k_trials_full32) draw from at north_star's 1e-5."""
+    from conclave_sim_b200 import FP64
+    mp, roster, r = case["mp"], case["roster"], case["round"]
+    upload(eng, roster)
+    E = roster.E
+    p = to_params(mp)
+    assert eng.beta_schedule(p, r, 1)[0] == case["beta"]
+    pv = None if r == 1 else case["prev_vote"].astype(np.int32)
+    pc = None if pv is None else np.bincount(pv, minlength=E).astype(np.int32)
+    P64 = eng.prob_matrix(p, case["beta"], pv, pc, case["fatigued"], case["shares"], precision=FP64)
+    assert np.allclose(P64, case["P"], rtol=1e-13, atol=0)
+    for legacy in (False, True):
+        if legacy:
+            monkeypatch.setenv("CSIM_FULL_LEGACY", "1")
+        else:
+            monkeypatch.delenv("CSIM_FULL_LEGACY", raising=False)
+        check_against(eng, p, MODEL, FULL, r, case["P"], pv=pv, pc=pc, fat=case["fatigued"],
+                      what=f"{case['name']} {'k_trials_full32' if legacy else 'fast path'}")
+    monkeypatch.delenv("CSIM_FULL_LEGACY", raising=False)
+
+
 def test_probe_argument_errors(eng):
     from conclave_sim_b200._cabi import CsimError
     upload(eng, O.synthetic_roster(40))

@@ -49,6 +49,18 @@ def test_prob_matrix_real_roster():
     assert np.array_equal(P, z["cfg2_model/P2"])
 
 
+@pytest.mark.parametrize("case", list(G.extras_cases()), ids=lambda c: c["name"])
+def test_prob_matrix_with_fatigue_and_stop_on_full_size_rosters(case):
+    """Candidate fatigue + stop-candidate on the real 134-elector roster and a 200-elector one (oracle/gen_golden_extras.py): the
+    reference's own matrices, bit for bit, and its beta schedule."""
+    mp, roster, r = case["mp"], case["roster"], case["round"]
+    assert O.beta_schedule(mp, r)[r - 1] == case["beta"]
+    P = O.prob_matrix(roster, mp, case["beta"], prev_vote=None if r == 1 else case["prev_vote"], fatigued=case["fatigued"], shares=case["shares"])
+    assert np.array_equal(P, case["P"])
+    if r > 1:      # the cases are meant to exercise both branches of the stop-candidate rule
+        assert (case["shares"] > mp.stop_candidate_threat_min_vote_share).any() == (r != 3)
+
+
 @pytest.mark.parametrize("case", list(G.engine_cases()), ids=lambda c: c["name"])
 def test_engine_matches_reference_worker(case):
     tapes = G.case_tapes(case)
