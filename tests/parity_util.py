@@ -18,7 +18,7 @@ import os
 
 import numpy as np
 
-RATE = {"dense": 1.0e-3, "table": 2.5e-4, "prefix": 2.5e-4, "full": 1.5e-3, "fp32": 1.0e-3}
+RATE = {"dense": 1.0e-3, "table": 2.5e-4, "prefix": 2.5e-4, "full": 5.0e-4, "fp32": 1.0e-3}      # full: both of its kernels measure 0.3e-4 … 1e-4 at scale (r02b)
 ENGINE_NAME = {0: "prefix", 1: "dense", 2: "table", 3: "prefix", 4: "full"}      # AUTO (0) resolves to table / prefix / full: the tightest of them
 
 
