@@ -40,6 +40,15 @@ def test_prob_matrix(case):
         assert np.allclose(P, case["P"][r - 1], rtol=1e-14, atol=0)
 
 
+@pytest.mark.parametrize("case", list(G.extras_cases()), ids=lambda c: c["name"])
+def test_prob_matrix_with_fatigue_and_stop_on_full_size_rosters(case):
+    """The reference's matrices with candidate fatigue + stop-candidate on the real roster and a 200-elector one (model_extras.npz)."""
+    mp, roster, r = case["mp"], case["roster"], case["round"]
+    assert CO.beta_schedule(mp, r, 1)[0] == case["beta"]
+    P = CO.prob_matrix(roster, mp, case["beta"], prev_vote=None if r == 1 else case["prev_vote"], fatigued=case["fatigued"], shares=case["shares"])
+    assert np.allclose(P, case["P"], rtol=1e-14, atol=0)
+
+
 @pytest.mark.parametrize("case", list(G.engine_cases()), ids=lambda c: c["name"])
 def test_engine_under_reference_tapes(case):
     tapes = G.case_tapes(case)
