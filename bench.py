@@ -426,7 +426,7 @@ def main():
                        roofline={"bound": "fp32", "unit": "G pair-evaluations/s", "achieved": full_pairs / full_kern_s * 1e-9, "peak": fact_peak_pairs * 1e-9,
                                  "frac": full_pairs / full_kern_s / fact_peak_pairs,
                                  "note": "executed work: pair evaluations per second over the rate of the PLAIN factorised pair body (k_microbench<3>); in "
-                                         "rounds with stop-candidate threats the masked body executes 5.5 issue slots per pair instead of 2, so this "
+                                         "rounds with stop-candidate threats the masked body executes 5.5 issue slots of arithmetic per pair (~8 with its operand loads) instead of 2, so this "
                                          "fraction understates the pipe utilisation of those rounds",
                                  "algorithmic_equivalent_frac": full_pairs * FP32_PER_PAIR / full_kern_s * 1e-9 / peak_fp32,
                                  "algorithmic_equivalent_note": "SURVEY-8d canonical accounting (10 FP32 per pair) against the measured FFMA rate; round 1 "
