@@ -785,6 +785,7 @@ __global__ void __launch_bounds__(EXT ? CSIM_EXT_THREADS : 256, EXT ? 1 : CSIM_M
             int tail_r0 = -(1 << 30);                                // first round of the current tail stash (none yet)
             if (R == 0) { for (int c = lane; c < C; c += 32) tally[c] = 0; __syncwarp(); }
             int n_hist = 0;                                          // EXT: rounds in the tally history
+            int prev_mx = 0;                                         // EXT: the largest tally of the previous round (the closing computes it)
             int hrow = 0;                                            // EXT: row of the history ring the next tally goes to (= n_hist % Fmax)
             if (EXT) {
 #pragma unroll 1
@@ -799,6 +800,7 @@ __global__ void __launch_bounds__(EXT ? CSIM_EXT_THREADS : 256, EXT ? 1 : CSIM_M
                 }
                 have_prev = true; n_hist = 1; hrow = a.Fmax > 1 ? 1 : 0;
                 __syncwarp();
+                if (EXT) { int arg0; warp_argmax_first(prev_tally, C, lane, prev_mx, arg0); }
             }
 
             for (int r = PROBE ? a.probe_round : 1; r <= R; ++r) {
@@ -931,24 +933,31 @@ __global__ void __launch_bounds__(EXT ? CSIM_EXT_THREADS : 256, EXT ? 1 : CSIM_M
                 if (MODEL) {
                     if (has_bw && have_prev) {                                   // model.py:326-354
                         int mx, arg;
-                        warp_argmax_first(prev_tally, C, lane, mx, arg);
+                        if constexpr (EXT) { mx = prev_mx; arg = 0; }           // the previous round's closing already found it
+                        else warp_argmax_first(prev_tally, C, lane, mx, arg);
+                        (void)arg;
                         if (mx > 0) {
                             kx.use_bw = true;
                             const float inv = 1.0f / (float)mx;
-                            for (int c = lane; c < C; c += 32) {
+                            // EXT: a run-off round only ever reads the first k candidates' terms (no full-field round follows it)
+                            const int nbw = (EXT && have_eff) ? min(C, max(k, 2)) : C;
+                            for (int c = lane; c < nbw; c += 32) {
                                 float v = (float)prev_tally[c] * inv * bw_strength;
                                 if (EXT) v *= phi[pad_c<LC>(c)];                  // fatigue scales the whole score (model.py:379)
                                 bw[pad_c<LC>(c)] = v;
                             }
                             __syncwarp();
-                            float s = 0.f;                                       // bandwagon of chunk `lane`, then prefix over chunks
-                            if (lane < nch) for (int c = lane * L; c < (lane + 1) * L; ++c) s += bw[pad_c<LC>(c)];
+                            // (EXT: the prefix over chunks is probed only in a full-field round without stop-candidate threats)
+                            if (!EXT || (!have_eff && n_thr == 0)) {
+                                float s = 0.f;                                   // bandwagon of chunk `lane`, then prefix over chunks
+                                if (lane < nch) for (int c = lane * L; c < (lane + 1) * L; ++c) s += bw[pad_c<LC>(c)];
 #pragma unroll
-                            for (int off = 1; off < 32; off <<= 1) {
-                                const float o = __shfl_up_sync(CSIM_FULL, s, off);
-                                if (lane >= off) s += o;
+                                for (int off = 1; off < 32; off <<= 1) {
+                                    const float o = __shfl_up_sync(CSIM_FULL, s, off);
+                                    if (lane >= off) s += o;
+                                }
+                                if (lane < nch) bwp[lane] = s;
                             }
-                            if (lane < nch) bwp[lane] = s;
                         }
                     }
                 }
@@ -1367,11 +1376,13 @@ __global__ void __launch_bounds__(EXT ? CSIM_EXT_THREADS : 256, EXT ? 1 : CSIM_M
                         warp_top2(tally, C, lane, k1, k2);
                         mx = (int)(k1 >> 16); arg = 0xFFFF - (int)(k1 & 0xFFFFu); second = 0xFFFF - (int)(k2 & 0xFFFFu);
                     }
+                    if (EXT) prev_mx = mx;
                     if (mx >= need) { winner = arg; reason = CSIM_REASON_WINNER; break; }        // simulate.py:174-180
                     if (r >= rr) { ef0 = arg; ef1 = second; have_eff = true; }                   // simulate.py:183-186
                 } else {
                     int mx, arg;
                     warp_argmax_first(tally, C, lane, mx, arg);
+                    if (EXT) prev_mx = mx;
                     if (mx >= need) { winner = arg; reason = CSIM_REASON_WINNER; break; }
                     if (r >= rr && k > 0) { warp_top_k(tally, C, k, lane, eff, mark); have_eff = true; }
                 }
