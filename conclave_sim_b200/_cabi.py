@@ -22,7 +22,7 @@ ENGINE_NAMES = {0: "auto", 1: "dense", 2: "table", 3: "prefix", 4: "full"}
 
 EXPORTS = ["csim_abi_version", "csim_last_error", "csim_create", "csim_destroy", "csim_device_info",
            "csim_upload_roster", "csim_beta_schedule", "csim_need_votes", "csim_prob_matrix", "csim_run",
-           "csim_stats", "csim_microbench", "csim_prefix_plan_query", "csim_prefix_slot", "csim_host_alloc", "csim_host_free", "csim_vote_threshold",
+           "csim_stats", "csim_microbench", "csim_prefix_plan_query", "csim_prefix_slot", "csim_full_plan_query", "csim_host_alloc", "csim_host_free", "csim_vote_threshold",
            "csim_last_run_info", "csim_engine_probs", "csim_device_count",
            "csim_nccl_load", "csim_nccl_version", "csim_nccl_unique_id", "csim_nccl_comm_create", "csim_nccl_comm_destroy",
            "csim_allreduce_hists", "csim_shard_range",
@@ -71,6 +71,12 @@ class CsimPrefixPlan(C.Structure):
                [("offsets", C.c_uint32 * 12)]
 
 
+class CsimFullPlan(C.Structure):
+    """struct csim_full_plan"""
+    _fields_ = [(n, C.c_int32) for n in ("fast_path", "general_fits", "warps_per_cta", "cta_tabs", "n_chunks", "acc_pitch")] + \
+               [(n, C.c_uint64) for n in ("smem_cta", "smem_per_warp", "smem_total")]
+
+
 _lib = None
 
 
@@ -101,6 +107,8 @@ def load_library() -> C.CDLL:
     lib.csim_microbench.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double)]
     lib.csim_prefix_plan_query.argtypes = [C.c_int32] * 6 + [C.c_uint64, C.c_int32, C.POINTER(CsimPrefixPlan)]
     lib.csim_prefix_plan_query.restype = C.c_int
+    lib.csim_full_plan_query.argtypes = [C.c_int32] * 7 + [C.POINTER(CsimFullPlan)]
+    lib.csim_full_plan_query.restype = C.c_int
     lib.csim_host_alloc.argtypes = [C.c_uint64, C.POINTER(C.c_void_p)]
     lib.csim_host_alloc.restype = C.c_int
     lib.csim_host_free.argtypes = [C.c_void_p]

@@ -13,37 +13,22 @@
 // what that formulation can express: E <= 255 (chunks of 8, tallies in bytes), every factor non-negative, a factorisable beta
 // schedule, tables that fit in shared memory.  Everything else stays on k_trials_full32.  `*taken` says whether it ran.
 // ---------------------------------------------------------------------------------------------
-static csim_status launch_dense_ext(csim_ctx* c, const csim_run_args* ra, const std::vector<DevSet>& hs, const BatchDev& b, const TrialOut& out,
-                                    cudaStream_t st, bool any_stop, int accw, int min_warps, bool* taken) {
-    *taken = false;
-    const int E = c->E, G = c->G, R = b.R;
-    if (getenv("CSIM_FULL_LEGACY") || E > 255 || E < 2 || R < 1) return CSIM_OK;
-    for (int i = 0; i < ra->n_param_sets; ++i) {
-        const csim_params& q = ra->params[i];
-        std::vector<double> hb((size_t)R);
-        csim_beta_schedule(&q, 1, R, hb.data());
-        for (double be : hb) if (!(be >= 0.0) || !(be * c->x_half <= 26.0)) return CSIM_OK;      // not factorisable (dense32.cuh header)
-    }
-    Dense32Args a;
-    memset(&a, 0, sizeof a);
-    a.ro = roster_dev(c); a.b = b; a.out = out; a.nbeta = (const float*)c->nbeta.p; a.wiring = CSIM_WIRING_MODEL;
-    int kmax = 1, Fmax = 1;
-    a.n_tab_full = 1;
-    for (const DevSet& s : hs) {
-        kmax = std::max(kmax, s.k); Fmax = std::max(Fmax, s.fat_rounds);
-        a.n_tab_full = std::max(a.n_tab_full, s.k > 0 ? std::min(R, std::max(s.rr, 1)) : R);
-    }
-    a.kmax = kmax; a.Fmax = Fmax;
+// Host-side plan of the fast path (pure arithmetic): layout, warps per CTA, whether the round tables of a set are CTA-shared.
+//   n_tab_full = rounds that can be full-field in some set of the batch; min_warps = fewest warps per CTA worth launching
+// Returns false when the shape is not the fast path's (E outside 2 .. 255, no round) or fewer than min_warps warps fit.
+static bool ext_plan(Dense32Args& a, int E, int G, int R, int n_tab_full, int kmax, int Fmax, int min_warps) {
+    if (E > 255 || E < 2 || R < 1) return false;
+    a.ro.E = E; a.ro.G = G;
+    a.kmax = kmax; a.Fmax = Fmax < 1 ? 1 : Fmax;
     a.L = 8; a.nch = (E + 7) / 8;
     a.epitch = (E + 1) & ~1;
-    a.accw = accw; a.accmask = (const uint32_t*)c->accm.p;
     const int nk = (kmax + 7) / 8;
-    const int n_full = std::min(a.n_tab_full, R);
+    const int n_full = std::max(1, std::min(n_tab_full, R));
     const size_t budget = 220 * 1024;
     // CTA-shared round tables of all R rounds (whole tables for the full-field rounds, one short table per run-off round) when that
     // costs no warp; else every warp stages the round it plays (its own table is there anyway, the phi-folded copy: ~50 instructions
     // per round, while a warp more or less is ~5 % of the kernel's speed)
-    const size_t warp = dense32_warp_smem(E, a.nch, 8, kmax, true, true) + dense32_ext_warp_smem(E, a.nch, G, Fmax);
+    const size_t warp = dense32_warp_smem(E, a.nch, 8, kmax, true, true) + dense32_ext_warp_smem(E, a.nch, G, a.Fmax);
     const size_t ext_cta = dense32_ext_cta_smem(E, a.nch, G, a.epitch);
     const size_t ctaA = (dense32_cta_smem(a.nch, 8, G, n_full, R - n_full, nk) + 15) & ~(size_t)15;
     const size_t ctaB = (dense32_cta_smem(a.nch, 8, G, 0) + 15) & ~(size_t)15;
@@ -58,9 +43,34 @@ static csim_status launch_dense_ext(csim_ctx* c, const csim_run_args* ra, const 
     // many regions (bonus rows per region, CTA-shared and per warp): below ~10 warps per SM this kernel is no faster than
     // k_trials_full32 with its 28 (12 / 8 warps measured 17 / 21 ms per 250 k trials against 21), so the caller asks for 10 when the
     // general kernel fits and for 2 when it does not
-    if (wpc < min_warps) return CSIM_OK;
+    if (wpc < min_warps) return false;
     a.o_ext = base_cta; a.cta_smem = base_cta + ext_cta; a.warp_smem = warp;
     a.warps_per_cta = wpc;
+    return true;
+}
+
+static csim_status launch_dense_ext(csim_ctx* c, const csim_run_args* ra, const std::vector<DevSet>& hs, const BatchDev& b, const TrialOut& out,
+                                    cudaStream_t st, bool any_stop, int accw, int min_warps, bool* taken) {
+    *taken = false;
+    const int E = c->E, G = c->G, R = b.R;
+    if (getenv("CSIM_FULL_LEGACY") || R < 1) return CSIM_OK;
+    for (int i = 0; i < ra->n_param_sets; ++i) {
+        const csim_params& q = ra->params[i];
+        std::vector<double> hb((size_t)R);
+        csim_beta_schedule(&q, 1, R, hb.data());
+        for (double be : hb) if (!(be >= 0.0) || !(be * c->x_half <= 26.0)) return CSIM_OK;      // not factorisable (dense32.cuh header)
+    }
+    Dense32Args a;
+    memset(&a, 0, sizeof a);
+    int kmax = 1, Fmax = 1, n_tab_full = 1;
+    for (const DevSet& s : hs) {
+        kmax = std::max(kmax, s.k); Fmax = std::max(Fmax, s.fat_rounds);
+        n_tab_full = std::max(n_tab_full, s.k > 0 ? std::min(R, std::max(s.rr, 1)) : R);
+    }
+    if (!ext_plan(a, E, G, R, n_tab_full, kmax, Fmax, min_warps)) return CSIM_OK;
+    a.ro = roster_dev(c); a.b = b; a.out = out; a.nbeta = (const float*)c->nbeta.p; a.wiring = CSIM_WIRING_MODEL;
+    a.accw = accw; a.accmask = (const uint32_t*)c->accm.p;
+    const int wpc = a.warps_per_cta;
     const size_t smem = a.cta_smem + a.warp_smem * wpc;
     void (*kern)(Dense32Args) = k_trials_dense32<8, true, true, false, true>;
     if (c->probe) {
@@ -181,3 +191,32 @@ csim_status launch_full32(csim_ctx* c, const csim_run_args* ra, const std::vecto
     return CSIM_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// csim_full_plan_query (header): which kernel the FULL engine would run for a batch with fatigue / stop-candidate live, and its budget
+// ---------------------------------------------------------------------------------------------
+extern "C" csim_status csim_full_plan_query(int32_t n_electors, int32_t n_regions, int32_t max_rounds, int32_t full_field_rounds, int32_t kmax,
+                                            int32_t fatigue_window, int32_t fast_path_eligible, csim_full_plan* out) {
+    if (!out) return fail(CSIM_ERR_INVALID, "csim_full_plan_query: out is NULL");
+    if (n_electors < 1 || n_electors >= 32768 || n_regions < 1 || n_regions > n_electors || max_rounds < 0 || kmax < 0)
+        return fail(CSIM_ERR_INVALID, "csim_full_plan_query: need 1 <= electors < 32768, 1 <= regions <= electors, rounds >= 0, kmax >= 0");
+    memset(out, 0, sizeof *out);
+    Full32Args g;
+    memset(&g, 0, sizeof g);
+    const bool general = full32_plan(g, n_electors, n_regions, max_rounds, std::max(kmax, 1), std::max(fatigue_window, 1), (size_t)232448);
+    out->general_fits = general ? 1 : 0;
+    Dense32Args a;
+    memset(&a, 0, sizeof a);
+    const bool fast = fast_path_eligible && !getenv("CSIM_FULL_LEGACY") &&
+                      ext_plan(a, n_electors, n_regions, max_rounds, full_field_rounds, std::max(kmax, 1), std::max(fatigue_window, 1), general ? 10 : 2);
+    if (fast) {
+        out->fast_path = 1; out->warps_per_cta = a.warps_per_cta; out->cta_tabs = a.cta_tabs; out->n_chunks = a.nch; out->acc_pitch = a.epitch;
+        out->smem_cta = a.cta_smem; out->smem_per_warp = a.warp_smem; out->smem_total = a.cta_smem + a.warp_smem * (uint64_t)a.warps_per_cta;
+    } else if (general) {
+        out->warps_per_cta = g.warps_per_cta; out->n_chunks = g.nch;
+        out->smem_cta = g.cta_smem; out->smem_per_warp = g.warp_smem; out->smem_total = g.cta_smem + g.warp_smem * (uint64_t)g.warps_per_cta;
+    } else {
+        return fail(CSIM_ERR_UNSUPPORTED, "full engine: a roster of %d electors / %d regions fits neither of its kernels", n_electors, n_regions);
+    }
+    return CSIM_OK;
+}

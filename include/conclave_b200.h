@@ -234,6 +234,26 @@ csim_status csim_prefix_plan_query(int32_t n_electors, int32_t n_regions, int32_
 /* table row of an elector inside one round's table (the order the lanes visit electors) */
 int32_t     csim_prefix_slot(int32_t elector, int32_t e_quad_end);
 
+/* Which of its two kernels the FULL engine would run for a batch with candidate fatigue / stop-candidate live, and its
+ * shared-memory budget (pure host arithmetic, no device needed; used by the CPU tests for any roster shape).
+ *   full_field_rounds   = rounds that can be full-field: min(max_rounds, max(runoff_threshold_rounds, 1)) when a run-off
+ *                         exists, else max_rounds;  fatigue_window = largest fatigue_threshold_rounds of the batch
+ *   fast_path_eligible  = 1 when every factor is non-negative and the beta schedule is factorisable (beta >= 0 and
+ *                         beta x half-range of the ideology scores <= 26): the caller's facts, not the roster's shape
+ * The fast path (the EXT instantiation of the dense kernel) is chosen when eligible, 2 <= electors <= 255 and at least 10
+ * of its warps fit per SM (2 when the general kernel k_trials_full32 does not fit at all). */
+typedef struct csim_full_plan {
+    int32_t  fast_path;         /* 1: the dense kernel's EXT instantiation; 0: k_trials_full32 */
+    int32_t  general_fits;      /* k_trials_full32 fits in shared memory */
+    int32_t  warps_per_cta;     /* of the kernel that would run (one CTA per SM) */
+    int32_t  cta_tabs;          /* fast path: the round tables of a parameter set are CTA-shared (1) or staged per warp per round (0) */
+    int32_t  n_chunks;          /* chunks of candidates per row */
+    int32_t  acc_pitch;         /* fast path: entries per chunk row of the acceptable-bytes table */
+    uint64_t smem_cta, smem_per_warp, smem_total;
+} csim_full_plan;
+csim_status csim_full_plan_query(int32_t n_electors, int32_t n_regions, int32_t max_rounds, int32_t full_field_rounds, int32_t kmax,
+                                 int32_t fatigue_window, int32_t fast_path_eligible, csim_full_plan* out);
+
 /* Page-locked host memory (cudaHostAlloc / cudaFreeHost) for the per-trial result arrays of a host-buffer csim_run:
  * copies into it run at full PCIe speed.  Optional: any host memory works. */
 csim_status csim_host_alloc(uint64_t bytes, void** out);

@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_struct_mirrors_match_header(tmp_path):
     """Compile a tiny C program printing sizeof/offsetof of the header's structs; compare with ctypes."""
-    from conclave_sim_b200._cabi import CsimParams, CsimRunArgs, CsimPrefixPlan
+    from conclave_sim_b200._cabi import CsimParams, CsimRunArgs, CsimPrefixPlan, CsimFullPlan
     from oracle.c_oracle import CParams
     fields_p = [f[0] for f in CsimParams._fields_]
     fields_r = [f[0] for f in CsimRunArgs._fields_]
@@ -53,6 +53,10 @@ def test_struct_mirrors_match_header(tmp_path):
     prog += 'printf("%zu\\n", sizeof(csim_prefix_plan));\n'
     for f in fields_q:
         prog += f'printf("%zu\\n", offsetof(csim_prefix_plan, {f}));\n'
+    fields_f = [f[0] for f in CsimFullPlan._fields_]
+    prog += 'printf("%zu\\n", sizeof(csim_full_plan));\n'
+    for f in fields_f:
+        prog += f'printf("%zu\\n", offsetof(csim_full_plan, {f}));\n'
     prog += "return 0;}\n"
     c = tmp_path / "t.c"
     c.write_text(prog)
@@ -61,7 +65,8 @@ def test_struct_mirrors_match_header(tmp_path):
     nums = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     exp = [ctypes.sizeof(CsimParams)] + [getattr(CsimParams, f).offset for f in fields_p] + \
           [ctypes.sizeof(CsimRunArgs)] + [getattr(CsimRunArgs, f).offset for f in fields_r] + \
-          [ctypes.sizeof(CsimPrefixPlan)] + [getattr(CsimPrefixPlan, f).offset for f in fields_q]
+          [ctypes.sizeof(CsimPrefixPlan)] + [getattr(CsimPrefixPlan, f).offset for f in fields_q] + \
+          [ctypes.sizeof(CsimFullPlan)] + [getattr(CsimFullPlan, f).offset for f in fields_f]
     assert nums == exp
     assert ctypes.sizeof(CParams) == ctypes.sizeof(CsimParams)
     assert [f[0] for f in CParams._fields_] == fields_p
